@@ -1,0 +1,266 @@
+// ============================================================================
+// selftest.cpp -- TEST INFRASTRUCTURE.  Pins the oracle against the
+// expectations hard-coded in the reference's own unit tests.  Each CHECK cites
+// the reference test it restates (paths relative to /root/reference/ddo/src).
+// Exit code 0 iff every check passes; one line per failed check.
+// ============================================================================
+#include "models.hpp"
+#include <cstdio>
+#include <map>
+
+using namespace ddo_oracle;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond, what)                                                     \
+    do {                                                                      \
+        ++g_checks;                                                           \
+        if (!(cond)) { ++g_fail; std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, what); } \
+    } while (0)
+
+using DummyMdd = Mdd<DummyState, DummyHash, DummyEq>;
+using CharMdd = Mdd<char, CharHash, CharEq>;
+using DummyCache = SimpleCache<DummyState, DummyHash, DummyEq>;
+using CharCache = SimpleCache<char, CharHash, CharEq>;
+
+struct DummyEnv {
+    DummyProblem pb; DummyRelax rlx; DummyRanking rk; NoCutoff nocut; FlagCutoff always{true};
+    EmptyCache<DummyState> ecache; EmptyDominanceChecker<DummyState> dom;
+    SubProblem<DummyState> root{std::make_shared<const DummyState>(DummyState{0, 0}), 0, {}, ISIZE_MAX, 0};
+    CompilationInput<DummyState> input(CompilationType t, size_t w, isize lb, Cache<DummyState>* cache = nullptr, const Cutoff* c = nullptr) {
+        return CompilationInput<DummyState>{t, &pb, &rlx, &rk, c ? c : &nocut, w, &root, lb, cache ? cache : &ecache, &dom};
+    }
+};
+
+static bool same_path(const Solution& s, std::vector<std::pair<size_t, isize>> exp) {
+    if (s.size() != exp.size()) return false;
+    for (size_t i = 0; i < s.size(); ++i) if (s[i].variable != exp[i].first || s[i].value != exp[i].second) return false;
+    return true;
+}
+
+static void test_dummy_dd() {
+    DummyEnv e; Completion c;
+    {   // clean.rs:1120-1150 root_remembers_the_pa_from_the_fringe_node
+        SubProblem<DummyState> r{std::make_shared<const DummyState>(DummyState{42, 1}), 42, {Decision{0, 42}}, ISIZE_MAX, 1};
+        for (auto t : {CompilationType::Exact, CompilationType::Relaxed, CompilationType::Restricted}) {
+            auto in = e.input(t, 3, ISIZE_MIN); in.residual = &r;
+            DummyMdd m; CHECK(m.compile(in, &c), "compile ok");
+            auto sol = m.best_solution();
+            CHECK(sol && sol->size() >= 1 && (*sol)[0] == (Decision{0, 42}), "root path kept in front of the best path");
+        }
+    }
+    {   // clean.rs:1152-1188 exact_completely_unrolls_the_mdd_no_matter_its_width
+        DummyMdd m; auto in = e.input(CompilationType::Exact, 1, ISIZE_MIN);
+        CHECK(m.compile(in, &c), "exact compile");
+        CHECK(m.best_value() == std::optional<isize>(6), "exact best 6");
+        CHECK(same_path(*m.best_solution(), {{2, 2}, {1, 2}, {0, 2}}), "exact best path");
+        CHECK(c.is_exact == m.is_exact() && c.best_value == m.best_value(), "completion coherent (clean.rs:1226-1254)");
+        CHECK(m.is_exact(), "an_exact_mdd_must_be_exact clean.rs:1473");
+    }
+    {   // clean.rs:1190-1224 restricted_drops_the_less_interesting_nodes
+        DummyMdd m; auto in = e.input(CompilationType::Restricted, 1, ISIZE_MIN);
+        CHECK(m.compile(in, &c), "restricted compile");
+        CHECK(m.best_value() == std::optional<isize>(6), "restricted best 6");
+        CHECK(same_path(*m.best_solution(), {{2, 2}, {1, 2}, {0, 2}}), "restricted best path");
+        CHECK(c.is_exact == m.is_exact() && c.best_value == m.best_value(), "completion coherent (clean.rs:1256-1284)");
+        CHECK(!m.is_exact(), "restricted W=1 is inexact");
+    }
+    {   // clean.rs:1405-1440 relaxed_merges_the_less_interesting_nodes
+        DummyMdd m; auto in = e.input(CompilationType::Relaxed, 1, ISIZE_MIN);
+        CHECK(m.compile(in, &c), "relaxed compile");
+        CHECK(m.best_value() == std::optional<isize>(24), "relaxed best 24");
+        CHECK(same_path(*m.best_solution(), {{2, 2}, {1, 0}, {0, 2}}), "relaxed best path [x2=2,x1=0,x0=2]");
+        CHECK(c.is_exact == m.is_exact() && c.best_value == m.best_value(), "completion coherent (clean.rs:1286-1314)");
+        // clean.rs:1442-1471 relaxed_populates_the_cutset_and_will_not_squash_first_layer
+        size_t n = 0; m.drain_cutset([&](SubProblem<DummyState>) { ++n; });
+        CHECK(n == 3, "cutset size 3: L1 not squashed");
+        CHECK(!m.is_exact(), "a_relaxed_mdd_is_not_exact_when_a_merge_occurred clean.rs:1530");
+    }
+    {   // clean.rs:1322-1403 cutoff
+        for (auto t : {CompilationType::Exact, CompilationType::Relaxed, CompilationType::Restricted}) {
+            DummyMdd m; auto in = e.input(t, 1, ISIZE_MIN, nullptr, &e.always);
+            CHECK(!m.compile(in, &c), "Err(CutoffOccurred)");
+        }
+    }
+    {   // clean.rs:1501-1528, 1559-1586 exact as long as no squash
+        DummyMdd m; auto in = e.input(CompilationType::Relaxed, 10, ISIZE_MIN);
+        CHECK(m.compile(in, &c) && m.is_exact(), "relaxed W=10 exact");
+        auto in2 = e.input(CompilationType::Restricted, 10, ISIZE_MIN);
+        CHECK(m.compile(in2, &c) && m.is_exact(), "restricted W=10 exact");
+    }
+    {   // clean.rs:1615-1668 infeasible
+        DummyEnv f; f.pb.infeasible = true;
+        DummyMdd m; auto in = f.input(CompilationType::Exact, SIZE_MAX, ISIZE_MIN);
+        CHECK(m.compile(in, &c), "infeasible compile");
+        CHECK(!m.best_solution() && !m.best_value(), "infeasible: no solution / value");
+    }
+    {   // clean.rs:1669-1749 rub pruning vs best_lb = 1000
+        for (auto t : {CompilationType::Exact, CompilationType::Relaxed, CompilationType::Restricted}) {
+            DummyMdd m; auto in = e.input(t, SIZE_MAX, 1000);
+            CHECK(m.compile(in, &c) && !m.best_solution(), "ub <= best_lb: nothing expanded");
+        }
+    }
+    {   // clean.rs:1750-1842 cache thresholds prune
+        for (auto t : {CompilationType::Exact, CompilationType::Relaxed, CompilationType::Restricted}) {
+            DummyCache cache; cache.initialize(e.pb);
+            for (isize v = 0; v <= 2; ++v) cache.update_threshold(std::make_shared<const DummyState>(DummyState{v, 1}), 1, v, true);
+            DummyMdd m; auto in = e.input(t, SIZE_MAX, ISIZE_MIN, &cache);
+            CHECK(m.compile(in, &c) && !m.best_solution(), "cache-threshold pruning");
+        }
+    }
+    {   // clean.rs:1844-1948 thresholds when exact
+        for (auto t : {CompilationType::Restricted, CompilationType::Relaxed}) {
+            DummyCache cache; cache.initialize(e.pb);
+            DummyMdd m; auto in = e.input(t, 10, ISIZE_MIN, &cache);
+            CHECK(m.compile(in, &c) && m.is_exact(), "exact W=10");
+            isize exp_by_depth[4] = {0, 2, 4, 6};
+            size_t maxv[4] = {0, 2, 4, 6};
+            for (size_t d = 0; d <= 3; ++d)
+                for (size_t v = 0; v <= maxv[d]; ++v) {
+                    auto th = cache.get_threshold(DummyState{(isize)v, d}, d);
+                    CHECK(th && th->value == exp_by_depth[d] && th->explored, "threshold table (exact)");
+                }
+        }
+    }
+    {   // clean.rs:1950-2054 thresholds when all pruned (best_lb = 15)
+        for (auto t : {CompilationType::Restricted, CompilationType::Relaxed}) {
+            DummyCache cache; cache.initialize(e.pb);
+            DummyMdd m; auto in = e.input(t, 10, 15, &cache);
+            CHECK(m.compile(in, &c) && m.is_exact(), "exact W=10 lb=15");
+            isize exp_by_depth[3] = {1, 3, 5};
+            size_t maxv[4] = {0, 2, 4, 6};
+            for (size_t d = 0; d <= 2; ++d)
+                for (size_t v = 0; v <= maxv[d]; ++v) {
+                    auto th = cache.get_threshold(DummyState{(isize)v, d}, d);
+                    CHECK(th && th->value == exp_by_depth[d] && th->explored, "threshold table (pruned)");
+                }
+            for (size_t v = 0; v <= 6; ++v) CHECK(!cache.get_threshold(DummyState{(isize)v, 3}, 3), "depth 3: none");
+        }
+    }
+}
+
+static void test_locbounds() {
+    LocBoundsPb pb; LocBoundsRelax rlx; CmpChar rk; NoCutoff nocut; EmptyDominanceChecker<char> dom;
+    SubProblem<char> root{std::make_shared<const char>('r'), 0, {}, ISIZE_MAX, 0};
+    auto run = [&](int cutset, isize lb, std::map<char, isize>& ubs, CharCache& cache, Completion& c, CharMdd& m) {
+        cache.initialize(pb);
+        CompilationInput<char> in{CompilationType::Relaxed, &pb, &rlx, &rk, &nocut, 3, &root, lb, &cache, &dom};
+        bool ok = m.compile(in, &c);
+        m.drain_cutset([&](SubProblem<char> n) { ubs[*n.state] = n.ub; });
+        return ok;
+    };
+    auto thr = [](CharCache& c, char s, size_t d) { return c.get_threshold(s, d); };
+    {   // clean.rs:2183-2242 (LEL)
+        std::map<char, isize> v; CharCache cache; Completion c; CharMdd m(LAST_EXACT_LAYER);
+        CHECK(run(LAST_EXACT_LAYER, 0, v, cache, c, m), "compile");
+        CHECK(!m.is_exact() && m.best_value() == std::optional<isize>(16), "LEL: inexact, best 16");
+        CHECK(v.size() == 2 && v['a'] == 16 && v['b'] == 14, "LEL cutset ubs a=16 b=14");
+        CHECK(thr(cache, 'r', 0) && thr(cache, 'a', 1) && thr(cache, 'b', 1), "thresholds r,a,b present");
+        for (auto p : std::vector<std::pair<char, size_t>>{{'M', 2}, {'e', 2}, {'f', 2}, {'g', 3}, {'h', 3}, {'i', 3}, {'t', 4}})
+            CHECK(!thr(cache, p.first, p.second), "no threshold below the LEL cutset");
+        CHECK(thr(cache, 'r', 0)->value == 0 && thr(cache, 'r', 0)->explored, "theta r = 0 explored");
+        CHECK(thr(cache, 'a', 1)->value == 10 && !thr(cache, 'a', 1)->explored, "theta a = 10");
+        CHECK(thr(cache, 'b', 1)->value == 7 && !thr(cache, 'b', 1)->explored, "theta b = 7");
+    }
+    {   // clean.rs:2244-2321 (frontier)
+        std::map<char, isize> v; CharCache cache; Completion c; CharMdd m(FRONTIER);
+        CHECK(run(FRONTIER, 0, v, cache, c, m), "compile");
+        CHECK(!m.is_exact() && m.best_value() == std::optional<isize>(16), "FC: inexact, best 16");
+        CHECK(v.size() == 4 && v['a'] == 16 && v['b'] == 14 && v['h'] == 13 && v['i'] == 14, "FC cutset ubs");
+        CHECK(!thr(cache, 'M', 2) && !thr(cache, 'g', 3) && !thr(cache, 't', 4), "no threshold for relaxed nodes");
+        struct E { char s; size_t d; isize v; bool ex; };
+        for (E x : std::vector<E>{{'r', 0, 0, true}, {'a', 1, 10, false}, {'b', 1, 7, false}, {'e', 2, 13, true}, {'f', 2, 12, true}, {'h', 3, 13, false}, {'i', 3, 14, false}}) {
+            auto t = thr(cache, x.s, x.d);
+            CHECK(t && t->value == x.v && t->explored == x.ex, "FC threshold table");
+        }
+    }
+    {   // clean.rs:2323-2398 (frontier, best_lb = 15)
+        std::map<char, isize> v; CharCache cache; Completion c; CharMdd m(FRONTIER);
+        CHECK(run(FRONTIER, 15, v, cache, c, m), "compile");
+        CHECK(!m.is_exact() && m.best_value() == std::optional<isize>(16), "FC lb=15: inexact, best 16");
+        CHECK(v.size() == 2 && v['a'] == 16 && v['b'] == 14, "FC lb=15 cutset ubs");
+        struct E { char s; size_t d; isize v; bool ex; };
+        for (E x : std::vector<E>{{'r', 0, 0, true}, {'a', 1, 10, false}, {'b', 1, 8, false}, {'e', 2, 15, true}, {'f', 2, 13, true}, {'h', 3, 15, true}, {'i', 3, 15, true}}) {
+            auto t = thr(cache, x.s, x.d);
+            CHECK(t && t->value == x.v && t->explored == x.ex, "FC lb=15 threshold table");
+        }
+    }
+}
+
+static void test_flags() {  // node_flags.rs:191-719 (semantics)
+    NodeFlags f = NodeFlags::new_exact();
+    CHECK(f.is_exact() && !f.is_relaxed() && !f.is_marked() && !f.is_cutset() && !f.is_deleted(), "new_exact");
+    f.set_relaxed(true); CHECK(!f.is_exact() && f.is_relaxed(), "relaxed masks exact (node_flags.rs:88)");
+    f.set_relaxed(false); CHECK(f.is_exact(), "un-relax");
+    NodeFlags r = NodeFlags::new_relaxed();
+    CHECK(!r.is_exact() && r.is_relaxed(), "new_relaxed");
+    r.set_exact(true); CHECK(!r.is_exact(), "relaxed stays inexact even with F_EXACT");
+    f.set_marked(true); f.set_cutset(true); f.set_deleted(true); f.set_pruned_by_cache(true); f.set_above_cutset(true);
+    CHECK(f.is_marked() && f.is_cutset() && f.is_deleted() && f.is_pruned_by_cache() && f.is_above_cutset() && f.is_exact(), "independent bits");
+    CHECK(NodeFlags::F_EXACT == 1 && NodeFlags::F_RELAXED == 2 && NodeFlags::F_MARKED == 4 && NodeFlags::F_CUTSET == 8 && NodeFlags::F_DELETED == 16 && NodeFlags::F_CACHE == 32 && NodeFlags::F_ABOVE_CUTSET == 64, "bit values node_flags.rs:51-63");
+}
+
+static void test_fringe() {  // no_duplicate.rs:326-663 + subproblem_ranking.rs doc-test :50-74
+    CmpChar rk; MaxUB<char> mx{&rk};
+    auto sp = [](char s, isize value, isize ub) { return SubProblem<char>{std::make_shared<const char>(s), value, {}, ub, 0}; };
+    {
+        NoDupFringe<char, CharHash, CharEq> q(mx);
+        q.push(sp('a', 10, 300)); q.push(sp('b', 2, 100)); q.push(sp('c', 24, 150));
+        q.push(sp('d', 13, 13)); q.push(sp('e', 65, 700)); q.push(sp('f', 19, 100));
+        std::string order;
+        while (auto n = q.pop()) order.push_back(*n->state);
+        CHECK(order == "eacfbd", "MaxUB pop order e,a,c,f,b,d");
+    }
+    {
+        NoDupFringe<char, CharHash, CharEq> q(mx);
+        CHECK(q.is_empty() && q.len() == 0, "empty");
+        q.push(sp('x', 5, 50)); q.push(sp('x', 7, 40));  // same state: longer path wins, ub = max
+        CHECK(q.len() == 1, "one entry per state");
+        auto n = q.pop();
+        CHECK(n && n->value == 7 && n->ub == 50, "longest path kept, ub = max(old,new)");
+        q.push(sp('x', 7, 40)); q.push(sp('x', 5, 60));
+        n = q.pop();
+        CHECK(n && n->value == 7 && n->ub == 60, "ub raised, value kept");
+        CHECK(!q.pop(), "pop on empty -> None");
+        q.push(sp('a', 1, 1)); q.push(sp('b', 1, 2)); q.clear();
+        CHECK(q.is_empty(), "clear");
+    }
+    {
+        SimpleFringe<char> q(mx);
+        q.push(sp('a', 10, 300)); q.push(sp('b', 2, 100)); q.push(sp('e', 65, 700));
+        CHECK(*q.pop()->state == 'e' && *q.pop()->state == 'a' && *q.pop()->state == 'b' && !q.pop(), "SimpleFringe order");
+    }
+}
+
+// parallel.rs:1256-1337 / sequential.rs:750-909: the 3-item / 7-item knapsacks solved by every solver flavour -> 220
+static void test_solvers_knapsack() {
+    using KMdd = Mdd<KnapsackState, KnapsackHash, KnapsackEq>;
+    (void)sizeof(KMdd);
+    for (int cutset : {LAST_EXACT_LAYER, FRONTIER})
+        for (int flavour = 0; flavour < 3; ++flavour)
+            for (int caching = 0; caching < 2; ++caching) {
+                Knapsack pb(50, {60, 100, 120}, {10, 20, 30});
+                KPRelax rlx(&pb); KPRanking rk; NbUnassignedWidth<KnapsackState> w(pb.nb_variables()); NoCutoff nocut;
+                EmptyDominanceChecker<KnapsackState> edom;
+                MaxUB<KnapsackState> mx{&rk};
+                NoDupFringe<KnapsackState, KnapsackHash, KnapsackEq> fr(mx);
+                EmptyCache<KnapsackState> ec; SimpleCache<KnapsackState, KnapsackHash, KnapsackEq> sc;
+                Cache<KnapsackState>* cache = caching ? (Cache<KnapsackState>*)&sc : (Cache<KnapsackState>*)&ec;
+                SolverConfig<KnapsackState> cfg{&pb, &rlx, &rk, &w, &edom, &nocut, &fr, cache, cutset};
+                Completion c; isize lb = 0, ub = 0; Solution sol;
+                if (flavour == 0) { SequentialSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg); c = s.maximize(); lb = s.best_lb; ub = s.best_ub; sol = *s.best_sol; }
+                else if (flavour == 1) { ParallelSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg, 4); c = s.maximize(); lb = s.best_lb; ub = s.best_ub; sol = *s.best_sol; }
+                else { if (caching) continue; WaveSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg, 3); c = s.maximize(); lb = s.best_lb; ub = s.best_ub; sol = *s.best_sol; }
+                CHECK(c.is_exact && c.best_value == std::optional<isize>(220) && lb == 220 && ub == 220, "3-item knapsack -> 220 (parallel.rs:902-950)");
+                CHECK(same_path(sol, {{0, 0}, {1, 1}, {2, 1}}), "decisions x0=0,x1=1,x2=1 (parallel.rs:941-948)");
+            }
+}
+
+int main() {
+    test_flags();
+    test_dummy_dd();
+    test_locbounds();
+    test_fringe();
+    test_solvers_knapsack();
+    std::printf("%s: %d checks, %d failed\n", g_fail ? "SELFTEST FAILED" : "SELFTEST OK", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}

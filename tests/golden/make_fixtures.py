@@ -1,0 +1,54 @@
+"""Provenance script for tests/golden (run in the build container, where /root/reference is mounted).
+
+Copies the *data* fixtures the reference's own tests use for the hot path (no reference source code):
+  * resources/visualisation_tests/*.dot  -- golden graphviz dumps compared verbatim by clean.rs:2401-2546
+  * resources/misp/*.clq (small ones)    -- DIMACS instances whose optima are asserted in ddo/examples/misp/tests.rs:66-193
+  * resources/knapsack/* (small ones)    -- instances whose optima are asserted in ddo/examples/knapsack/tests.rs:65-206
+and writes expected.json with the asserted optima (transcribed from those test files, with their line numbers).
+"""
+import json
+import re
+import shutil
+from pathlib import Path
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "keller4", "hamming8-2", "hamming8-4",
+        "brock200_2", "brock200_3", "brock200_4", "c-fat200-5"]
+KNAPSACK_MAX_ITEMS = 200
+
+
+def asserted(tests_rs: Path):
+    """{instance id: (value, line)} from `assert_eq!(solve_id("<id>"), <value>);` lines (ignored tests included)."""
+    out = {}
+    for ln, line in enumerate(tests_rs.read_text().splitlines(), 1):
+        m = re.search(r'assert_eq!\(solve_id\("([^"]+)"\),\s*(-?\d+)\)', line)
+        if m:
+            out[m.group(1)] = (int(m.group(2)), ln)
+    return out
+
+
+def main():
+    (OUT / "misp").mkdir(exist_ok=True)
+    (OUT / "knapsack").mkdir(exist_ok=True)
+    for f in (REF / "resources/visualisation_tests").glob("*.dot"):
+        shutil.copy(f, OUT / f.name)
+    expected = {"misp": {}, "knapsack": {}}
+    m = asserted(REF / "ddo/examples/misp/tests.rs")
+    for name in MISP:
+        shutil.copy(REF / "resources/misp" / f"{name}.clq", OUT / "misp" / f"{name}.clq")
+        v, ln = m[f"{name}.clq"]
+        expected["misp"][name] = {"optimum": v, "source": f"ddo/examples/misp/tests.rs:{ln}"}
+    k = asserted(REF / "ddo/examples/knapsack/tests.rs")
+    for name, (v, ln) in sorted(k.items()):
+        src = REF / "resources/knapsack" / name
+        n_items = int(src.read_text().split()[0])
+        if n_items <= KNAPSACK_MAX_ITEMS:
+            shutil.copy(src, OUT / "knapsack" / name)
+            expected["knapsack"][name] = {"optimum": v, "items": n_items, "source": f"ddo/examples/knapsack/tests.rs:{ln}"}
+    (OUT / "expected.json").write_text(json.dumps(expected, indent=1, sort_keys=True) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""ctypes binding of the CPU oracle (oracle/build/liboracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+LIB = ORACLE_DIR / "build" / "liboracle.so"
+SELFTEST = ORACLE_DIR / "build" / "selftest"
+
+I64_MIN = -(1 << 63)
+I64_MAX = (1 << 63) - 1
+EXACT, RELAXED, RESTRICTED = 0, 1, 2
+LEL, FRONTIER = 1, 2
+
+
+def build(force: bool = False) -> None:
+    srcs = [ORACLE_DIR / f for f in ("oracle_capi.cpp", "ddo_oracle.hpp", "models.hpp", "selftest.cpp")]
+    stale = force or not LIB.exists() or not SELFTEST.exists() or any(s.stat().st_mtime > min(LIB.stat().st_mtime, SELFTEST.stat().st_mtime) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "all"], check=True, capture_output=True)
+
+
+class DDResult(C.Structure):
+    _fields_ = [("has_best", C.c_int32), ("is_exact", C.c_int32), ("has_best_exact", C.c_int32), ("lel", C.c_int32),
+                ("best_value", C.c_int64), ("best_exact_value", C.c_int64), ("expanded", C.c_uint64), ("transitions", C.c_uint64),
+                ("n_layers", C.c_int32), ("cutset_size", C.c_int32), ("cutoff", C.c_int32), ("pad", C.c_int32)]
+
+
+class SolveResult(C.Structure):
+    _fields_ = [("has_value", C.c_int32), ("is_exact", C.c_int32), ("best_value", C.c_int64), ("best_lb", C.c_int64), ("best_ub", C.c_int64),
+                ("explored", C.c_uint64), ("expanded", C.c_uint64), ("transitions", C.c_uint64), ("compilations", C.c_uint64), ("waves", C.c_uint64),
+                ("seconds", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.oracle_misp_new.restype = C.c_void_p
+        _lib.oracle_misp_new.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.oracle_misp_free.argtypes = [C.c_void_p]
+        _lib.oracle_misp_words.argtypes = [C.c_void_p]
+        _lib.oracle_misp_dd_new.restype = C.c_void_p
+        _lib.oracle_misp_dd_new.argtypes = [C.c_void_p, C.c_int32]
+        _lib.oracle_misp_dd_free.argtypes = [C.c_void_p]
+        _lib.oracle_misp_dd_compile.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.POINTER(DDResult)]
+        _lib.oracle_misp_dd_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _lib.oracle_misp_dd_cutset.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32]
+        _lib.oracle_misp_dd_solution.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        _lib.oracle_misp_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64,
+                                           C.POINTER(SolveResult), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        _lib.oracle_misp_compile_many.restype = C.c_uint64
+        _lib.oracle_misp_compile_many.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        _lib.oracle_knapsack_solve.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
+                                               C.POINTER(SolveResult), C.c_void_p]
+        _lib.oracle_locbounds_dump.argtypes = [C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class OracleMisp:
+    """CPU oracle for one MISP instance."""
+
+    def __init__(self, inst):
+        self.inst = inst
+        self.h = lib().oracle_misp_new(inst.n, _p(inst.weights), len(inst.src), _p(inst.src), _p(inst.dst))
+        self.words = lib().oracle_misp_words(self.h)
+
+    def __del__(self):
+        try:
+            lib().oracle_misp_free(self.h)
+        except Exception:
+            pass
+
+    def compile(self, comp_type, max_width, root_state=None, root_value=0, root_depth=0, best_lb=I64_MIN, cutset_type=LEL, cutoff=False, want_paths=False):
+        L = lib()
+        dd = L.oracle_misp_dd_new(self.h, cutset_type)
+        try:
+            if root_state is None:
+                root_state = self.inst.initial_state()
+            root_state = np.ascontiguousarray(root_state, dtype=np.uint64)
+            res = DDResult()
+            rc = L.oracle_misp_dd_compile(dd, comp_type, max_width, _p(root_state), root_value, root_depth, best_lb, int(cutoff), C.byref(res))
+            out = {k: getattr(res, k) for k, _ in DDResult._fields_ if k != "pad"}
+            out["rc"] = rc
+            if rc != 0:
+                return out
+            n = self.inst.n
+            vars_ = np.zeros(n + 1, dtype=np.int32)
+            widths = np.zeros(n + 1, dtype=np.int32)
+            nl = L.oracle_misp_dd_layers(dd, _p(vars_), _p(widths), n + 1)
+            out["layer_vars"] = vars_[:nl].copy()
+            out["layer_widths"] = widths[:nl].copy()
+            cs = res.cutset_size
+            states = np.zeros((max(cs, 1), self.words), dtype=np.uint64)
+            values = np.zeros(max(cs, 1), dtype=np.int64)
+            ubs = np.zeros(max(cs, 1), dtype=np.int64)
+            depths = np.zeros(max(cs, 1), dtype=np.int32)
+            plens = np.zeros(max(cs, 1), dtype=np.int32)
+            stride = n
+            paths = np.zeros((max(cs, 1), stride, 2), dtype=np.int32) if want_paths else None
+            L.oracle_misp_dd_cutset(dd, _p(states), _p(values), _p(ubs), _p(depths), _p(plens), _p(paths), cs, stride)
+            out["cutset_states"] = states[:cs]
+            out["cutset_values"] = values[:cs]
+            out["cutset_ubs"] = ubs[:cs]
+            out["cutset_depths"] = depths[:cs]
+            if want_paths:
+                out["cutset_paths"] = [paths[i, : plens[i]].copy() for i in range(cs)]
+            for key, ex in (("best_solution", 0), ("best_exact_solution", 1)):
+                sv = np.zeros(n + 1, dtype=np.int32)
+                sx = np.zeros(n + 1, dtype=np.int32)
+                ln = L.oracle_misp_dd_solution(dd, ex, _p(sv), _p(sx), n + 1)
+                out[key] = None if ln < 0 else list(zip(sv[:ln].tolist(), sx[:ln].tolist()))
+            return out
+        finally:
+            L.oracle_misp_dd_free(dd)
+
+    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0):
+        """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (the reference CLI default, misp/main.rs:322-328)."""
+        m = {"sequential": 0, "wave": 1, "parallel": 2}[mode]
+        res = SolveResult()
+        sol = np.zeros(self.inst.n, dtype=np.int32)
+        sl = C.c_int32(0)
+        trace = np.zeros((max(trace_cap, 1), 4), dtype=np.int64)
+        tl = C.c_int32(0)
+        lib().oracle_misp_solve(self.h, m, k, 0 if width is not None else 1, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
+                                _p(sol), C.byref(sl), _p(trace) if trace_cap else None, trace_cap, C.byref(tl))
+        out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
+        out["solution"] = sorted(sol[: sl.value].tolist())
+        out["trace"] = trace[: tl.value].copy()
+        return out
+
+    def compile_many(self, roots_states, roots_values, roots_depths, widths, best_lb, threads, cutset_type=LEL):
+        n = len(roots_values)
+        rs = np.ascontiguousarray(roots_states, dtype=np.uint64)
+        rv = np.ascontiguousarray(roots_values, dtype=np.int64)
+        rd = np.ascontiguousarray(roots_depths, dtype=np.int32)
+        w = np.ascontiguousarray(widths, dtype=np.uint64)
+        rb = np.zeros(n, dtype=np.int64)
+        xb = np.zeros(n, dtype=np.int64)
+        cs = np.zeros(n, dtype=np.int32)
+        tr = C.c_uint64(0)
+        sec = C.c_double(0)
+        exp = lib().oracle_misp_compile_many(self.h, threads, n, _p(rs), _p(rv), _p(rd), _p(w), best_lb, cutset_type, _p(rb), _p(xb), _p(cs), C.byref(tr), C.byref(sec))
+        return {"expanded": int(exp), "transitions": int(tr.value), "seconds": float(sec.value), "restricted_best": rb, "relaxed_best": xb, "cutset_sizes": cs}
+
+
+def knapsack_solve(inst, solver="sequential", k=1, width=None, cutset_type=FRONTIER, caching=True):
+    res = SolveResult()
+    taken = np.zeros(len(inst.profit), dtype=np.int32)
+    lib().oracle_knapsack_solve(len(inst.profit), inst.capacity, _p(np.ascontiguousarray(inst.profit, dtype=np.int64)),
+                                _p(np.ascontiguousarray(inst.weight, dtype=np.int64)), 0 if solver == "sequential" else 2, k,
+                                0 if width is not None else 1, width or 0, cutset_type, int(caching), C.byref(res), _p(taken))
+    out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
+    out["taken"] = taken
+    return out
+
+
+def locbounds_dump(cutset_type=FRONTIER, best_lb=0) -> str:
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().oracle_locbounds_dump(cutset_type, best_lb, buf, len(buf))
+    assert n >= 0
+    return buf.value.decode()
+
+
+def run_selftest() -> subprocess.CompletedProcess:
+    build()
+    return subprocess.run([str(SELFTEST)], capture_output=True, text=True)

@@ -1,0 +1,169 @@
+"""The oracle against the reference's own golden vectors (CPU only).
+
+* oracle/selftest.cpp restates the reference's unit tests (clean.rs:1097-2668, node_flags.rs, no_duplicate.rs, solver tests).
+* tests/golden/*.dot are the reference's graphviz goldens (resources/visualisation_tests, compared verbatim by clean.rs:2401-2546):
+  every node's val / locb / rub / theta, every edge with decision, cost and best-edge pen width, cutset / relaxed / deleted styling.
+* tests/golden/misp, tests/golden/knapsack + expected.json: instance optima asserted by examples/{misp,knapsack}/tests.rs.
+"""
+import json
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from ddo_b200.instances import parse_dimacs, parse_knapsack, random_knapsack
+
+
+def test_selftest_restated_reference_unit_tests():
+    r = O.run_selftest()
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SELFTEST OK" in r.stdout
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# graphviz goldens
+# ----------------------------------------------------------------------------------------------------------------
+_NODE = re.compile(r'^(\d+) \[shape=(\w+),style=filled,color=("?[#\w]+"?),peripheries=(\d),group="(\w+)",label="\'(.)\'(.*)"\];$')
+_EDGE = re.compile(r'^(\d+) -> (\d+) \[penwidth=(\d),label="\(x(\d+) = (-?\d+)\)\\ncost = (-?\d+)"\];$')
+
+
+def parse_dot(text):
+    nodes, edges = {}, []
+    for raw in text.splitlines():
+        line = raw.strip()
+        m = _NODE.match(line)
+        if m:
+            nid, shape, color, periph, _group, label, rest = m.groups()
+            attrs = dict(re.findall(r"\\n(\w+): ([-+\w]+)", rest))
+            nodes[int(nid)] = {"label": label, "shape": shape, "color": color.strip('"'), "peripheries": int(periph), **attrs}
+            continue
+        m = _EDGE.match(line)
+        if m:
+            a, b, pen, var, val, cost = m.groups()
+            edges.append((int(a), int(b), int(pen), int(var), int(val), int(cost)))
+    return nodes, edges
+
+
+def parse_dump(text):
+    nodes, edges = {}, []
+    for line in text.splitlines():
+        t = line.split()
+        if t[0] == "N":
+            nodes[t[1]] = dict(val=t[2], locb=t[3], rub=t[4], theta=t[5], exact=t[6] == "1", relaxed=t[7] == "1", cutset=t[8] == "1", deleted=t[9] == "1")
+        else:
+            edges.append((t[1], t[2], int(t[3]), int(t[4]), int(t[5]), t[6] == "1"))
+    return nodes, edges
+
+
+def test_default_viz_golden_pins_every_node_and_edge(golden_dir):
+    """clean.rs:2401-2431 (test_default_visualisation): FC cutset, relaxed, W=3, best_lb=0."""
+    gnodes, gedges = parse_dot((golden_dir / "default_viz.dot").read_text())
+    onodes, oedges = parse_dump(O.locbounds_dump(O.FRONTIER, 0))
+    by_label = {v["label"]: v for v in gnodes.values()}
+    # default config hides deleted nodes: c and d are absent from the golden, present (deleted) in the oracle
+    assert set(by_label) == {k for k, v in onodes.items() if not v["deleted"]}
+    assert {k for k, v in onodes.items() if v["deleted"]} == {"c", "d"}
+    for label, g in by_label.items():
+        o = onodes[label]
+        assert g["val"] == o["val"], label
+        assert g["rub"] == o["rub"], label
+        assert g["theta"] == ("+inf" if o["theta"] == "none" else o["theta"]) or (g["theta"] == o["theta"]), label
+        # locb is printed for every node; the terminal's is 0
+        assert g["locb"] == o["locb"], label
+        assert (g["color"] == "red" and g["peripheries"] == 4) == o["cutset"], label  # cutset styling
+        assert (g["shape"] == "square") == o["relaxed"], label                      # merged nodes are squares
+    id2label = {k: v["label"] for k, v in gnodes.items()}
+    gset = sorted((id2label[a], id2label[b], var, val, cost, pen == 3) for a, b, pen, var, val, cost in gedges)
+    oset = sorted(e for e in oedges if not onodes[e[1]]["deleted"])
+    assert gset == oset
+
+
+def test_deleted_viz_golden_shows_merged_away_nodes(golden_dir):
+    """clean.rs:2471-2507 (show_deleted): the merged-away nodes c,d and their original edges are still in the DD."""
+    gnodes, gedges = parse_dot((golden_dir / "deleted_viz.dot").read_text())
+    onodes, oedges = parse_dump(O.locbounds_dump(O.FRONTIER, 0))
+    assert {v["label"] for v in gnodes.values()} == set(onodes)
+    id2label = {k: v["label"] for k, v in gnodes.items()}
+    gset = sorted((id2label[a], id2label[b], var, val, cost, pen == 3) for a, b, pen, var, val, cost in gedges)
+    assert gset == sorted(oedges)
+    # creation order of the nodes (ids in the golden) is reproduced up to the hash-order of the last two layers
+    order = [id2label[i] for i in sorted(id2label)]
+    assert order[:8] == ["r", "a", "b", "c", "d", "e", "f", "M"]
+    assert list(onodes)[:8] == order[:8]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# instance-level known answers
+# ----------------------------------------------------------------------------------------------------------------
+def _expected(golden_dir):
+    return json.loads((golden_dir / "expected.json").read_text())
+
+
+FAST_MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "hamming8-2", "brock200_2", "c-fat200-5"]
+SLOW_MISP = ["keller4", "brock200_3"]
+
+
+@pytest.mark.parametrize("name", FAST_MISP + SLOW_MISP)
+def test_misp_known_optima_parallel_solver(golden_dir, name):
+    """examples/misp/tests.rs: DefaultSolver (parallel, LEL, NbUnassignedWidth) proves the asserted optimum."""
+    exp = _expected(golden_dir)["misp"][name]
+    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    r = O.OracleMisp(inst).solve("parallel", k=8)
+    assert r["is_exact"] and r["best_value"] == exp["optimum"], exp["source"]
+    assert r["best_lb"] == r["best_ub"] == exp["optimum"]
+    _check_independent(inst, r["solution"], exp["optimum"])
+
+
+def _check_independent(inst, sol, value):
+    adj = set(zip(inst.src.tolist(), inst.dst.tolist())) | set(zip(inst.dst.tolist(), inst.src.tolist()))
+    assert all((a, b) not in adj for a in sol for b in sol if a != b)
+    assert int(inst.weights[sol].sum()) == value
+
+
+@pytest.mark.parametrize("name", FAST_MISP)
+def test_misp_sequential_wave_and_parallel_agree(golden_dir, name):
+    """Objective and proven bound are schedule independent; wave K=1 is exactly the sequential solver."""
+    exp = _expected(golden_dir)["misp"][name]["optimum"]
+    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    o = O.OracleMisp(inst)
+    seq = o.solve("sequential")
+    w1 = o.solve("wave", k=1)
+    w16 = o.solve("wave", k=16)
+    for r in (seq, w1, w16):
+        assert r["is_exact"] and r["best_value"] == exp and r["best_lb"] == exp and r["best_ub"] == exp
+    # same DDs compiled in the same order; the wave solver (like parallel.rs:531-535) clears the fringe at the first popped node
+    # with ub <= best_lb whereas sequential.rs:337 pops and discards them one by one, hence explored may only be smaller
+    assert (seq["expanded"], seq["transitions"], seq["compilations"]) == (w1["expanded"], w1["transitions"], w1["compilations"])
+    assert w1["explored"] <= seq["explored"]
+    assert seq["solution"] == w1["solution"]
+    # fixed width and frontier cutset variants reach the same optimum
+    assert o.solve("sequential", width=5)["best_value"] == exp
+    assert o.solve("sequential", cutset_type=O.FRONTIER)["best_value"] == exp
+
+
+def test_knapsack_known_optima(golden_dir):
+    """examples/knapsack/tests.rs:65-206 (SeqCachingSolverFc-equivalent: FC cutset + SimpleCache + KPDominance) -- BASELINE config 1 plumbing."""
+    exp = _expected(golden_dir)["knapsack"]
+    assert len(exp) >= 12
+    for name, e in exp.items():
+        inst = parse_knapsack((golden_dir / "knapsack" / name).read_text(), name)
+        for caching, cutset in ((True, O.FRONTIER), (False, O.LEL)):
+            if not caching and e["items"] > 23:
+                continue
+            r = O.knapsack_solve(inst, caching=caching, cutset_type=cutset)
+            assert r["is_exact"] and r["best_value"] == e["optimum"], (name, e["source"])
+            assert int(inst.profit[r["taken"] == 1].sum()) == e["optimum"]
+            assert int(inst.weight[r["taken"] == 1].sum()) <= inst.capacity
+
+
+def test_knapsack_config1_50_items_matches_dp():
+    """BASELINE config 1: 50-item instance, SequentialSolver on CPU; checked against a textbook DP."""
+    inst = random_knapsack(50, seed=1)
+    best = np.zeros(inst.capacity + 1, dtype=np.int64)
+    for p, w in zip(inst.profit.tolist(), inst.weight.tolist()):
+        best[w:] = np.maximum(best[w:], best[:-w] + p) if w <= inst.capacity else best[w:]
+    r = O.knapsack_solve(inst, solver="sequential", caching=True, cutset_type=O.FRONTIER)
+    assert r["is_exact"] and r["best_value"] == int(best[-1])
+    r2 = O.knapsack_solve(inst, solver="parallel", k=4, caching=True, cutset_type=O.FRONTIER)
+    assert r2["best_value"] == int(best[-1])
