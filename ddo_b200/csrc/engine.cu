@@ -1,0 +1,371 @@
+// engine.cu -- host side of the batch DD-compilation engine: arenas in HBM, the per-layer launch loop, result fetch.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace ddo {
+
+thread_local std::string g_last_error;
+unsigned long long g_kernel_launches = 0;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+            return DDO_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------------
+int model_create_misp(int32_t n, const int64_t* weights, int64_t m, const int32_t* src, const int32_t* dst, int device, MispModel** out) {
+    if (n <= 0 || m < 0 || (m > 0 && (!src || !dst)) || !out) { set_error("ddo_model_create_misp: invalid argument"); return DDO_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_error("invalid device ordinal"); return DDO_ERR_INVALID; }
+    if (n > 1024) { set_error("MISP device model supports n <= 1024 vertices"); return DDO_ERR_UNSUPPORTED; }
+    auto* M = new MispModel();
+    M->n = n; M->words = (n + 63) / 64; M->S = std::max(2, next_pow2(M->words)); M->device = device;
+    M->h_weight.assign(n, 1);
+    if (weights) for (int i = 0; i < n; ++i) M->h_weight[i] = weights[i];
+    M->unit_weights = true; M->weight_abs_sum = 0;
+    for (int i = 0; i < n; ++i) { if (M->h_weight[i] != 1) M->unit_weights = false; M->weight_abs_sum += M->h_weight[i] < 0 ? -M->h_weight[i] : M->h_weight[i]; }
+    if (M->weight_abs_sum >= (1ll << 30)) { delete M; set_error("sum of |weights| must be < 2^30 (values are 32-bit on the device)"); return DDO_ERR_UNSUPPORTED; }
+    // complement adjacency: full rows, then every edge removed in both directions (misp/main.rs:280-307)
+    M->h_nc.assign((size_t)n * M->S, 0);
+    for (int v = 0; v < n; ++v)
+        for (int u = 0; u < n; ++u) M->h_nc[(size_t)v * M->S + (u >> 6)] |= 1ull << (u & 63);
+    for (int64_t e = 0; e < m; ++e) {
+        int a = src[e], b = dst[e];
+        if (a < 0 || b < 0 || a >= n || b >= n) { delete M; set_error("edge endpoint out of range"); return DDO_ERR_INVALID; }
+        M->h_nc[(size_t)a * M->S + (b >> 6)] &= ~(1ull << (b & 63));
+        M->h_nc[(size_t)b * M->S + (a >> 6)] &= ~(1ull << (a & 63));
+    }
+    std::vector<int32_t> w32((size_t)M->S * 64, 0);
+    for (int i = 0; i < n; ++i) w32[i] = (int32_t)M->h_weight[i];
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&M->d_weight, w32.size() * 4) != cudaSuccess ||
+        cudaMalloc(&M->d_nc, M->h_nc.size() * 8) != cudaSuccess ||
+        cudaMemcpy(M->d_weight, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(M->d_nc, M->h_nc.data(), M->h_nc.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error(std::string("model upload: ") + cudaGetErrorString(cudaGetLastError()));
+        model_destroy(M);
+        return DDO_ERR_CUDA;
+    }
+    *out = M;
+    return DDO_OK;
+}
+void model_destroy(MispModel* M) {
+    if (!M) return;
+    if (M->d_weight) cudaFree(M->d_weight);
+    if (M->d_nc) cudaFree(M->d_nc);
+    delete M;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(Engine* E, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e)); return DDO_ERR_CUDA; }
+    E->allocations.push_back(q);
+    E->bytes_allocated += bytes;
+    *p = (T*)q;
+    return DDO_OK;
+}
+#define ALLOC(ptr, count)                                   \
+    do { int _r = dev_alloc(this, &(ptr), (size_t)(count)); if (_r != DDO_OK) return _r; } while (0)
+
+int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batch_cap, int cutset) {
+    if (!m || batch_cap < 1 || max_width_cap < 1) { set_error("ddo_mdd_create: invalid argument"); return DDO_ERR_INVALID; }
+    if (cutset != DDO_LAST_EXACT_LAYER) { set_error("device engine implements the LAST_EXACT_LAYER cutset only (FRONTIER: see DESIGN.md, next)"); return DDO_ERR_UNSUPPORTED; }
+    if (max_width_cap > (1u << 27)) { set_error("max_width_cap too large"); return DDO_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
+    if (dev != m->device) { set_error("model and mdd must live on the same device"); return DDO_ERR_INVALID; }
+    model = m; device = dev; cutset_type = cutset;
+    K = batch_cap; Wcap = (int)std::max<uint64_t>(max_width_cap, 2); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
+    Lmax = m->n + 1; PW = (Lmax + 63) / 64;
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    const size_t KW = (size_t)K * Wcap, KC = (size_t)K * C, KL = (size_t)K * Lmax;
+    ev.K = K; ev.Wcap = Wcap; ev.C = C; ev.T = T; ev.Lmax = Lmax; ev.n = m->n; ev.S = S; ev.PW = PW;
+    ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
+    ALLOC(ev.ctl, K); ALLOC(ev.active, 4);
+    ALLOC(ev.root_state, (size_t)K * S); ALLOC(ev.root_val, K); ALLOC(ev.root_depth, K); ALLOC(ev.root_width, K);
+    for (int b = 0; b < 2; ++b) { ALLOC(ev.cur_state[b], KW * S); ALLOC(ev.cur_val[b], KW); ALLOC(ev.cur_flag[b], KW); ALLOC(ev.vb[b], KW); }
+    ALLOC(ev.cur_rub, KW);
+    ALLOC(ev.cand_state, KC * S); ALLOC(ev.cand_rep, KC); ALLOC(ev.cand_first, KC); ALLOC(ev.cand_agg, KC); ALLOC(ev.cand_inex, KC);
+    ALLOC(ev.cand_rank, KC); ALLOC(ev.cand_slot, KC);
+    ALLOC(ev.uflag, KC); ALLOC(ev.ukey, KC); ALLOC(ev.uinex, KC); ALLOC(ev.ulist, KC); ALLOC(ev.ustat, KC); ALLOC(ev.pos_of, KC);
+    ALLOC(ev.table, (size_t)K * T);
+    ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
+    ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
+    ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
+    ALLOC(ev.best_path, (size_t)K * PW); ALLOC(ev.best_exact_path, (size_t)K * PW);
+    // drain buffers
+    ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
+    ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
+    ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
+    CUDA_TRY(cudaMallocHost(&h_root_state, (size_t)K * S * 8));
+    CUDA_TRY(cudaMallocHost(&h_root_val, (size_t)K * 4));
+    CUDA_TRY(cudaMallocHost(&h_root_depth, (size_t)K * 4));
+    CUDA_TRY(cudaMallocHost(&h_root_width, (size_t)K * 4));
+    CUDA_TRY(cudaMallocHost(&h_ctl, (size_t)K * sizeof(DDCtl)));
+    CUDA_TRY(cudaMallocHost(&h_active, 16));
+    CUDA_TRY(cudaMallocHost(&h_caps, (size_t)K * 16));
+    CUDA_TRY(cudaMallocHost(&h_counts, (size_t)(K + 1) * 8));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return DDO_OK;
+}
+
+void Engine::destroy() {
+    for (void* p : allocations) cudaFree(p);
+    allocations.clear();
+    for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_ctl, (void*)h_active, (void*)h_caps,
+                    (void*)h_counts, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path})
+        if (p) cudaFreeHost(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
+    if (count < 1 || count > K) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
+    const int words = model->words;
+    for (int i = 0; i < count; ++i) {
+        if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
+        if (values[i] < -(1ll << 30) || values[i] > (1ll << 30)) { set_error("root value outside the 31-bit device range"); return DDO_ERR_UNSUPPORTED; }
+        if (depths[i] < 0 || depths[i] > model->n) { set_error("root depth out of range"); return DDO_ERR_INVALID; }
+        for (int j = 0; j < S; ++j) h_root_state[(size_t)i * S + j] = j < words ? states[(size_t)i * words + j] : 0;
+        if (model->n & 63) {
+            uint64_t mask = (1ull << (model->n & 63)) - 1;
+            if (h_root_state[(size_t)i * S + words - 1] & ~mask) { set_error("root state has bits beyond nb_variables"); return DDO_ERR_INVALID; }
+        }
+        h_root_val[i] = (int32_t)values[i]; h_root_depth[i] = depths[i]; h_root_width[i] = (int32_t)widths[i];
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpyAsync(ev.root_state, h_root_state, (size_t)count * S * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ev.root_val, h_root_val, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ev.root_depth, h_root_depth, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ev.root_width, h_root_width, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    staged = count;
+    return DDO_OK;
+}
+
+template <int S>
+static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag) {
+    constexpr int G = S / 2;
+    const EV& ev = E->ev;
+    cudaStream_t st = E->stream;
+    k_init<S><<<count, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb);
+    ++g_kernel_launches;
+    const int npb = 256 / G;
+    const dim3 grid_nodes((E->Wcap + npb - 1) / npb, count), grid_cands((E->C + npb - 1) / npb, count);
+    const int CHUNK = 16;
+    for (int t = 0; t < E->Lmax; ++t) {
+        k_finish<S><<<count, 1024, 0, st>>>(ev, t);
+        k_compact<S><<<grid_cands, 256, 0, st>>>(ev, t);
+        k_expand<S><<<grid_nodes, 256, 0, st>>>(ev, t);
+        g_kernel_launches += 3;
+        if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {
+            CUDA_TRY(cudaMemcpyAsync(E->h_active, ev.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (*E->h_active <= 0) break;
+            if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;  // Cutoff::must_stop polled between layers (clean.rs:352)
+        }
+    }
+    // one more k_finish turns TERMINAL into DONE; harmless otherwise
+    k_finalize<<<(count + 63) / 64, 64, 0, st>>>(ev, count);
+    ++g_kernel_launches;
+    if (comp_type == DDO_RELAXED) { k_bottomup<<<count, 1024, 0, st>>>(ev); ++g_kernel_launches; }
+    CUDA_TRY(cudaGetLastError());
+    return DDO_OK;
+}
+
+int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
+    if (count < 1 || count > K || count > staged) { set_error("compile: batch not staged"); return DDO_ERR_INVALID; }
+    if (comp_type != DDO_EXACT && comp_type != DDO_RELAXED && comp_type != DDO_RESTRICTED) { set_error("bad compilation type"); return DDO_ERR_INVALID; }
+    for (int i = 0; i < count; ++i)
+        if (comp_type == DDO_RELAXED && h_root_width[i] < 1) { set_error("max_width must be >= 1 for a relaxed DD (the reference panics at clean.rs:827)"); return DDO_ERR_INVALID; }
+    if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)count * T * 8, stream));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    int rc;
+    switch (S) {
+        case 2: rc = run_layers<2>(this, count, comp_type, best_lb, cutoff_flag); break;
+        case 4: rc = run_layers<4>(this, count, comp_type, best_lb, cutoff_flag); break;
+        case 8: rc = run_layers<8>(this, count, comp_type, best_lb, cutoff_flag); break;
+        case 16: rc = run_layers<16>(this, count, comp_type, best_lb, cutoff_flag); break;
+        default: set_error("unsupported state width"); return DDO_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+    last_count = count; last_comp_type = comp_type; ctl_fetched = false;
+    return rc;
+}
+
+int Engine::fetch_ctl(int count) {
+    if (ctl_fetched && count <= last_count) return DDO_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpyAsync(h_ctl, ev.ctl, (size_t)last_count * sizeof(DDCtl), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    ctl_fetched = true;
+    for (int i = 0; i < last_count; ++i)
+        if (h_ctl[i].overflow) { set_error("a layer outgrew max_width_cap (Exact compilation needs a larger cap)"); return DDO_ERR_CAPACITY; }
+    return DDO_OK;
+}
+
+void Engine::fill_completion(int i, ddo_completion* out) const {
+    const DDCtl& c = h_ctl[i];
+    std::memset(out, 0, sizeof(*out));
+    out->is_exact = (c.lel < 0) || c.ebpo;  // clean.rs:241-243: is_exact || has_exact_best_path
+    out->has_best_value = c.has_best; out->best_value = c.has_best ? c.best_value : 0;
+    out->has_best_exact = c.has_best_exact; out->best_exact_value = c.has_best_exact ? c.best_exact_value : 0;
+    out->cutset_size = c.cutset_count;
+    out->lel_depth = c.lel < 0 ? -1 : c.root_depth + c.lel;
+    out->n_layers = c.t_term + (c.has_best ? 1 : 0);
+    out->expanded = c.expanded; out->transitions = c.transitions;
+}
+
+int Engine::best_solution(int index, int exact, ddo_decision* out, int32_t* len) {
+    if (index < 0 || index >= last_count || !len) { set_error("best_solution: bad index"); return DDO_ERR_INVALID; }
+    int rc = fetch_ctl(last_count);
+    if (rc != DDO_OK) return rc;
+    const DDCtl& c = h_ctl[index];
+    if (!(exact ? c.has_best_exact : c.has_best)) { set_error("no such solution"); return DDO_ERR_INVALID; }
+    const int L = c.t_term;  // decisions of layers 0..L-1
+    if (*len < L) { *len = L; set_error("best_solution: buffer too small"); return DDO_ERR_CAPACITY; }
+    std::vector<uint64_t> bits(PW);
+    std::vector<int32_t> vars(Lmax);
+    CUDA_TRY(cudaMemcpyAsync(bits.data(), (exact ? ev.best_exact_path : ev.best_path) + (size_t)index * PW, PW * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int i = 0; i < L; ++i) {  // reference order: terminal -> root (clean.rs:337-341)
+        const int tt = L - 1 - i;
+        out[i].variable = vars[tt];
+        out[i].value = (int32_t)((bits[tt >> 6] >> (tt & 63)) & 1);
+    }
+    *len = L;
+    return DDO_OK;
+}
+
+int Engine::layer_trace(int index, int32_t* vars, int32_t* widths, int cap) {
+    if (index < 0 || index >= last_count) { set_error("layer_trace: bad index"); return DDO_ERR_INVALID; }
+    int rc = fetch_ctl(last_count);
+    if (rc != DDO_OK) return rc;
+    const DDCtl& c = h_ctl[index];
+    const int L = std::max(0, c.t_term);  // expanded layers: 0..t_term-1
+    std::vector<int32_t> v(Lmax), w(Lmax);
+    CUDA_TRY(cudaMemcpyAsync(v.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(w.data(), ev.nlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int i = 0; i < L && i < cap; ++i) { vars[i] = v[i]; widths[i] = w[i]; }
+    return L;
+}
+
+// Batched drain: every DD i < count emits its MARKED cutset nodes with min(ub, ub_cap[i]) > lb_filter[i].
+// Results land in the pinned h_out_* arrays; returns the total number of records (<0: error).
+int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw_out) {
+    if (last_comp_type != DDO_RELAXED) { set_error("drain_cutset: the last batch was not a relaxed compilation (mdd.rs:103-110)"); return DDO_ERR_INVALID; }
+    if (count > last_count) { set_error("drain_cutset: bad count"); return DDO_ERR_INVALID; }
+    int rc = fetch_ctl(last_count);
+    if (rc != DDO_OK) return rc;
+    int max_lel = 0;
+    for (int i = 0; i < count; ++i) max_lel = std::max(max_lel, h_ctl[i].lel);
+    const int pw = std::max(1, (max_lel + 63) / 64);
+    *pw_out = pw;
+    long long* caps = (long long*)h_caps;
+    for (int i = 0; i < K; ++i) { caps[2 * i] = i < count ? ub_cap[i] : 0; caps[2 * i + 1] = i < count ? lb_filter[i] : INT64_MAX; }
+    // de-interleave on the device side via two strided copies
+    std::vector<long long> a(K), b(K);
+    for (int i = 0; i < K; ++i) { a[i] = caps[2 * i]; b[i] = caps[2 * i + 1]; }
+    std::memcpy(caps, a.data(), (size_t)K * 8); std::memcpy(caps + K, b.data(), (size_t)K * 8);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpyAsync(d_ub_cap, caps, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_lb_filter, caps + K, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    k_cutset_count<<<last_count, 1024, 0, stream>>>(ev, d_out, d_ub_cap, d_lb_filter, count);
+    k_cutset_offsets<<<1, 32, 0, stream>>>(d_out, last_count);
+    g_kernel_launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(h_counts, d_out.offset, (size_t)(last_count + 1) * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const int total = ((int32_t*)h_counts)[last_count];
+    if (total == 0) return 0;
+    if (pw > 8) CUDA_TRY(cudaMemsetAsync(d_out.path, 0, (size_t)total * pw * 8, stream));
+    const dim3 grid((Wcap + 255) / 256, last_count);
+    switch (S) {
+        case 2: k_cutset_write<2><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 4: k_cutset_write<4><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 8: k_cutset_write<8><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        default: k_cutset_write<16><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+    }
+    ++g_kernel_launches;
+    if (!h_out_state) {
+        const size_t KW = (size_t)K * Wcap;
+        CUDA_TRY(cudaMallocHost(&h_out_state, KW * S * 8));
+        CUDA_TRY(cudaMallocHost(&h_out_val, KW * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_ub, KW * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_dd, KW * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_path, KW * PW * 8));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_out_state, d_out.state, (size_t)total * S * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_val, d_out.val, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_ub, d_out.ub, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_dd, d_out.dd, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_path, d_out.path, (size_t)total * pw * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return total;
+}
+
+int Engine::fetch_vars(int index, std::vector<int32_t>& vars) {
+    vars.resize(Lmax);
+    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return DDO_OK;
+}
+
+int Engine::drain_cutset(int index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depth_out,
+                         int32_t* path_len_out, ddo_decision* paths, int32_t* count) {
+    if (index < 0 || index >= last_count || !count) { set_error("drain_cutset: bad index"); return DDO_ERR_INVALID; }
+    std::vector<int64_t> caps(last_count, 0), lbs(last_count, INT64_MAX);
+    caps[index] = ub_cap; lbs[index] = lb_filter;
+    int pw = 1;
+    int total = drain_all(last_count, caps.data(), lbs.data(), &pw);
+    if (total < 0) return total;
+    const DDCtl& c = h_ctl[index];
+    const int lel = std::max(0, c.lel);
+    if (depth_out) *depth_out = c.root_depth + lel;
+    if (path_len_out) *path_len_out = lel;
+    if (total > *count) { *count = total; set_error("drain_cutset: buffer too small"); return DDO_ERR_CAPACITY; }
+    std::vector<int32_t> vars;
+    if (paths && total > 0) { int rc = fetch_vars(index, vars); if (rc != DDO_OK) return rc; }
+    const int words = model->words;
+    for (int r = 0; r < total; ++r) {
+        if (states) for (int j = 0; j < words; ++j) states[(size_t)r * words + j] = h_out_state[(size_t)r * S + j];
+        if (values) values[r] = h_out_val[r];
+        if (ubs) ubs[r] = h_out_ub[r];
+        if (paths)
+            for (int i = 0; i < lel; ++i) {  // terminal -> root order (clean.rs:329-343)
+                const int tt = lel - 1 - i;
+                paths[(size_t)r * lel + i].variable = vars[tt];
+                paths[(size_t)r * lel + i].value = (int32_t)((h_out_path[(size_t)r * pw + (tt >> 6)] >> (tt & 63)) & 1);
+            }
+    }
+    *count = total;
+    return DDO_OK;
+}
+
+}  // namespace ddo

@@ -1,0 +1,130 @@
+// engine.hpp -- host-visible declarations of the B200 batch DD-compilation engine (MISP device model).
+// The engine compiles up to `K` decision diagrams in lock-step, one layer per step, entirely on the device.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ddo_b200.h"
+
+namespace ddo {
+
+void set_error(const std::string& msg);
+extern thread_local std::string g_last_error;
+extern unsigned long long g_kernel_launches;
+
+// ---------------------------------------------------------------------------------------------
+// Model: ddo/examples/misp/main.rs:37-209 as device-resident arrays.
+// ---------------------------------------------------------------------------------------------
+struct MispModel {
+    int n = 0;            // vertices
+    int words = 0;        // ceil(n/64): words of a packed state at the ABI
+    int S = 0;            // device words per state: power of two >= 2 (pad words are always zero)
+    int device = 0;
+    bool unit_weights = true;
+    int64_t weight_abs_sum = 0;
+    std::vector<int64_t> h_weight;
+    std::vector<uint64_t> h_nc;  // n x S complement-adjacency rows (main.rs:40-45)
+    int32_t* d_weight = nullptr;
+    uint64_t* d_nc = nullptr;
+};
+
+enum : int32_t { ST_ACTIVE = 0, ST_TERMINAL = 1, ST_DONE = 2 };
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
+// node flag bits kept in cur_flag / uinex / parent log
+constexpr uint32_t NF_INEXACT = 1u;  // !F_EXACT (node_flags.rs:51)
+constexpr uint32_t NF_RELAXED = 2u;  // F_RELAXED (node_flags.rs:53)
+constexpr uint32_t PLOG_INEXACT = 1u << 31, PLOG_RELAXED = 1u << 30, PLOG_CAND_MASK = (1u << 30) - 1;
+
+// Per-DD control block (device resident; copied back once per compile)
+struct DDCtl {
+    int32_t status, ncand, n_cur, var;
+    int32_t width, comp_type, root_depth, lel;  // lel: layer index of the last exact layer, -1 = never squashed
+    int32_t lel_pending, t_term, has_best, has_best_exact;
+    int32_t best_pos, best_exact_pos, best_value, best_exact_value;
+    int32_t ebpo, overflow, cutset_count, lel_n;
+    int32_t root_value, pad0;
+    int64_t best_lb;
+    unsigned long long expanded, transitions;
+};
+
+// Everything a kernel needs, passed by value.
+struct EV {
+    int K, Wcap, C, T, Lmax, n, S, PW;  // PW = uint64 words of a packed decision-bit path
+    int unit_weights;
+    const int32_t* weight;
+    const uint64_t* nc;
+    DDCtl* ctl;
+    int* active;  // number of DDs still compiling
+    // staged roots
+    uint64_t* root_state; int32_t* root_val; int32_t* root_depth; int32_t* root_width;
+    // current layer (ping-pong)
+    uint64_t* cur_state[2]; int32_t* cur_val[2]; uint8_t* cur_flag[2]; int32_t* cur_rub;
+    // candidates of the next layer
+    uint64_t* cand_state; uint32_t* cand_rep; uint32_t* cand_first; unsigned long long* cand_agg; uint8_t* cand_inex; uint32_t* cand_rank; uint32_t* cand_slot;
+    // unique nodes of the next layer
+    uint8_t* uflag; unsigned long long* ukey; uint8_t* uinex; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
+    unsigned long long* table;
+    // logs
+    uint32_t* plog;   // [K][Lmax][Wcap] best parent candidate + flags
+    uint32_t* clog;   // [K][Lmax][C]    child position of every candidate (relaxed only)
+    int32_t* nlog;    // [K][Lmax]       layer sizes
+    int32_t* vlog;    // [K][Lmax]       branching variables
+    int32_t* rslog;   // [K][Lmax][2]    (saved pos, recycled pos) of the recycled-merge corner case, else -1
+    // last exact layer snapshot
+    uint64_t* lel_state; int32_t* lel_val; int32_t* lel_rub;
+    // bottom-up scratch + cutset outputs
+    int32_t* vb[2];
+    int32_t* cs_ub; uint8_t* cs_marked;
+    // best paths (decision bits, one per layer) for best / best exact terminal node
+    uint64_t* best_path; uint64_t* best_exact_path;
+};
+
+// batched drain_cutset output (device side)
+struct DrainOut {
+    uint64_t* state; int32_t* val; int32_t* ub; int32_t* dd; uint64_t* path;  // [total] records
+    int32_t* count; int32_t* offset;  // [K+1]; offset[K] = total
+    uint32_t* loc;                    // [K][Wcap] local index of each emitted node
+};
+
+struct Engine {
+    const MispModel* model = nullptr;
+    int device = 0;
+    int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
+    int cutset_type = DDO_LAST_EXACT_LAYER;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    EV ev{};
+    std::vector<void*> allocations;
+    // pinned host staging
+    uint64_t* h_root_state = nullptr; int32_t* h_root_val = nullptr; int32_t* h_root_depth = nullptr; int32_t* h_root_width = nullptr;
+    DDCtl* h_ctl = nullptr; int* h_active = nullptr;
+    void* h_caps = nullptr; void* h_counts = nullptr;
+    DrainOut d_out{}; long long* d_ub_cap = nullptr; long long* d_lb_filter = nullptr;
+    // pinned results of the last drain_all (records [0,total))
+    uint64_t* h_out_state = nullptr; int32_t* h_out_val = nullptr; int32_t* h_out_ub = nullptr; int32_t* h_out_dd = nullptr; uint64_t* h_out_path = nullptr;
+    int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false;
+    size_t bytes_allocated = 0;
+
+    int create(const MispModel* m, int device, uint64_t max_width_cap, int batch_cap, int cutset_type);
+    void destroy();
+    int stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths);
+    int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
+    int fetch_ctl(int count);
+    void fill_completion(int i, ddo_completion* out) const;
+    int best_solution(int index, int exact, ddo_decision* out, int32_t* len);
+    int drain_cutset(int index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depth_out,
+                     int32_t* path_len_out, ddo_decision* paths, int32_t* count);
+    int layer_trace(int index, int32_t* vars, int32_t* widths, int cap);
+    // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
+    int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
+    int fetch_vars(int index, std::vector<int32_t>& vars);
+};
+
+int model_create_misp(int32_t n, const int64_t* weights, int64_t m, const int32_t* src, const int32_t* dst, int device, MispModel** out);
+void model_destroy(MispModel*);
+
+}  // namespace ddo

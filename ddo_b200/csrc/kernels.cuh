@@ -1,0 +1,778 @@
+// kernels.cuh -- hand-written sm_100a kernels of the batch DD-compilation engine (MISP device model).
+//
+// One "layer step" t -> t+1 of every DD of the batch is three launches:
+//   k_expand  (flat, G lanes per node)   clean.rs:360-370 + 728-776 + misp/main.rs:77-102,191-193:
+//             rough-upper-bound prune, transition / transition_cost of both decisions, 128-bit coalesced row loads and
+//             stores, open-addressing dedup (atomicCAS claim + 64-bit atomicMax of (value_top, candidate) per duplicate).
+//   k_finish  (one CTA per DD)           clean.rs:350 (misp/main.rs:109-143 next_variable), :779-876 (_restrict/_relax):
+//             canonical representatives, stable scan, positional-popcount histogram (warp bit-matrix transposes),
+//             MSD radix-select of the width cut with the full (value_top, popcount, lexicographic) key, OR-merge of the
+//             overflow, recycled-node lookup, last-exact-layer bookkeeping.
+//   k_compact (flat, G lanes per cand)   clean.rs:657-687: scatter survivors to the next layer (ping-pong SoA), parent log,
+//             child log, hash-table slot release, last-exact-layer snapshot.
+// After the last layer: k_finalize (best nodes, exact-best-path walk, clean.rs:620-655), k_bottomup (local bounds, clean.rs:448-475,
+// cutset upper bounds :417-445), k_cutset_{count,offsets,write} (drain_cutset compaction).
+#pragma once
+#include "engine.hpp"
+
+namespace ddo {
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ uint64_t word_hash(uint64_t w, int j) { return mix64(w + 0x9E3779B97F4A7C15ULL * (uint64_t)(j + 1)); }
+__device__ __forceinline__ unsigned long long pack_key(int32_t value, uint32_t cand) {
+    return ((unsigned long long)((uint32_t)value ^ 0x80000000u) << 32) | cand;
+}
+__device__ __forceinline__ int32_t key_value(unsigned long long key) { return (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u); }
+// ranking tie-break word: BitSet::cmp (lexicographic over ascending members) == unsigned order of ~bitreverse, larger = Greater
+__device__ __forceinline__ uint64_t lex_word(uint64_t w) { return ~__brevll(w); }
+
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {  // L2-only load (coherent across SMs inside one kernel)
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {  // streaming read-once row load
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint64_t u4lo(uint4 v) { return (uint64_t)v.x | ((uint64_t)v.y << 32); }
+__device__ __forceinline__ uint64_t u4hi(uint4 v) { return (uint64_t)v.z | ((uint64_t)v.w << 32); }
+__device__ __forceinline__ uint4 mk_u4(uint64_t lo, uint64_t hi) { return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)); }
+
+// ---- sub-warp group helpers (G = lanes per node, power of two <= 32) ------------------------------------------
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+    if (G == 32) return FULL_MASK;
+    unsigned lane = threadIdx.x & 31;
+    return ((G == 32 ? 0u : (1u << G)) - 1u) << (lane & ~(G - 1));
+}
+template <int G> __device__ __forceinline__ int group_sum(int v, unsigned m) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(m, v, d);
+    return v;
+}
+template <int G> __device__ __forceinline__ uint64_t group_xor64(uint64_t v, unsigned m) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v ^= __shfl_xor_sync(m, v, d);
+    return v;
+}
+template <int G> __device__ __forceinline__ bool group_all(bool p, unsigned m) { return (__ballot_sync(m, p) & m) == m; }
+template <int G> __device__ __forceinline__ bool group_any(bool p, unsigned m) { return (__ballot_sync(m, p) & m) != 0; }
+
+// ---- block helpers (blockDim.x == NT, multiple of 32, <= 1024) --------------------------------------------------
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(FULL_MASK, v, d));
+    return v;
+}
+// reduce over the block; result broadcast to all threads. `scratch` has >= 33 T slots.
+template <typename T, typename Op>
+__device__ T block_reduce(T v, Op op, T identity, T* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_reduce(v, op);
+    __syncthreads();  // protect scratch reuse
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        T x = lane < nw ? scratch[lane] : identity;
+        x = warp_reduce(x, op);
+        if (lane == 0) scratch[32] = x;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+// exclusive scan of one int per thread; returns exclusive prefix, *total = sum.  scratch: >= 33 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int n = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += n; }
+    __syncthreads();
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = lane < nw ? scratch[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int n = __shfl_up_sync(FULL_MASK, xi, d); if (lane >= d) xi += n; }
+        scratch[lane] = xi - x;  // exclusive warp offsets
+        if (lane == 31) scratch[32] = xi;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[w] + inc - v;
+}
+
+// 32x32 bit-matrix transpose across the lanes of a warp: afterwards bit r of lane b == bit b of (former) lane r.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        uint32_t p = __shfl_xor_sync(FULL_MASK, x, j);
+        if (!(lane & j)) { uint32_t t = ((x >> j) ^ p) & m; x ^= (t << j); }
+        else             { uint32_t t = ((p >> j) ^ x) & m; x ^= t; }
+        m ^= (m << (j >> 1));
+    }
+    return x;
+}
+
+// =================================================================================================================
+// k_init: root of every DD becomes the single "candidate" of layer 0 (clean.rs:383-405)
+// =================================================================================================================
+template <int S>
+__global__ void k_init(EV ev, int count, int comp_type, long long best_lb) {
+    const int k = blockIdx.x;
+    if (k >= count) return;
+    DDCtl* ctl = ev.ctl + k;
+    const size_t cb = (size_t)k * ev.C;
+    if (threadIdx.x < S) ev.cand_state[cb * S + threadIdx.x] = ev.root_state[(size_t)k * S + threadIdx.x];
+    if (threadIdx.x == 0) {
+        DDCtl c{};
+        c.status = ST_ACTIVE; c.ncand = 1; c.n_cur = 0; c.var = -1;
+        c.width = ev.root_width[k]; c.comp_type = comp_type; c.root_depth = ev.root_depth[k]; c.lel = -1;
+        c.t_term = -1; c.best_pos = -1; c.best_exact_pos = -1; c.root_value = ev.root_val[k];
+        c.best_lb = best_lb;
+        *ctl = c;
+        int pc = 0;
+        for (int j = 0; j < S; ++j) pc += __popcll(ev.root_state[(size_t)k * S + j]);
+        ev.cand_rep[cb] = 0; ev.cand_first[cb] = 0; ev.cand_agg[cb] = pack_key(ev.root_val[k], PLOG_CAND_MASK); ev.cand_inex[cb] = 0;
+        ev.cand_rank[cb] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(ev.root_state[(size_t)k * S]) >> 44);
+        ev.cand_slot[cb] = NONE32; ev.uflag[cb] = 0;
+        if (k == 0) *ev.active = count;
+    }
+}
+
+// =================================================================================================================
+// k_expand: layer t -> candidates of layer t+1
+// =================================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256) k_expand(EV ev, int t) {
+    constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
+    constexpr int NPB = 256 / G;      // nodes per block
+    const int k = blockIdx.y;
+    DDCtl* ctl = ev.ctl + k;
+    if (ctl->status != ST_ACTIVE) return;
+    const int n_cur = ctl->n_cur;
+    const int node = blockIdx.x * NPB + threadIdx.x / G;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ncand = 2 * n_cur;
+    if (blockIdx.x * NPB >= n_cur) return;
+    __shared__ unsigned int s_exp, s_tr;
+    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; }
+    __syncthreads();
+    const int sub = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    if (node < n_cur) {
+        const int buf = t & 1;
+        const size_t nb = (size_t)k * ev.Wcap + node;
+        const uint4 s4 = ld_stream_u4(reinterpret_cast<const uint4*>(ev.cur_state[buf] + nb * S) + sub);
+        uint64_t w0 = u4lo(s4), w1 = u4hi(s4);
+        const int val = ev.cur_val[buf][nb];
+        const uint32_t fl = ev.cur_flag[buf][nb];
+        // rough upper bound: sum of the weights of the remaining vertices (misp/main.rs:191-193)
+        int rub;
+        if (ev.unit_weights) rub = __popcll(w0) + __popcll(w1);
+        else {
+            rub = 0;
+            uint64_t x = w0; const int32_t* wp = ev.weight + (2 * sub) * 64;
+            while (x) { int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; }
+            x = w1; wp += 64;
+            while (x) { int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; }
+        }
+        rub = group_sum<G>(rub, gm);
+        const bool expandable = ((long long)rub + (long long)val) > ctl->best_lb;  // clean.rs:364-365 (no saturation possible in 32+32 bits)
+        const int v = ctl->var;
+        const int vw = v >> 6;
+        const bool owner = (vw >> 1) == sub;
+        const uint64_t bit = 1ull << (v & 63);
+        const bool has_v = group_any<G>(owner && (((vw & 1) ? w1 : w0) & bit), gm);  // misp/main.rs:96
+        const size_t cb = (size_t)k * ev.C;
+        const uint32_t c_yes = 2u * node, c_no = 2u * node + 1u;  // for_each_in_domain order: YES then NO (main.rs:95-102)
+        if (sub == 0) {
+            ev.cur_rub[nb] = rub;
+            ev.cand_rep[cb + c_yes] = NONE32; ev.cand_rep[cb + c_no] = NONE32;
+            ev.uflag[cb + c_yes] = 0; ev.uflag[cb + c_no] = 0;
+            if (expandable) { atomicAdd(&s_exp, 1u); atomicAdd(&s_tr, has_v ? 2u : 1u); }
+        }
+        if (expandable) {
+            if (owner) { if (vw & 1) w1 &= ~bit; else w0 &= ~bit; }  // res.remove(var) main.rs:79
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                // d == 0: YES child (only when v is in the state), d == 1: NO child
+                if (d == 0 && !has_v) continue;
+                uint64_t a0 = w0, a1 = w1;
+                int value = val;
+                if (d == 0) {
+                    const uint4 nc4 = __ldg(reinterpret_cast<const uint4*>(ev.nc + (size_t)v * S) + sub);  // main.rs:82
+                    a0 &= u4lo(nc4); a1 &= u4hi(nc4);
+                    value += ev.weight[v];  // main.rs:87-93
+                }
+                const uint32_t c = d == 0 ? c_yes : c_no;
+                uint4* dst = reinterpret_cast<uint4*>(ev.cand_state + (cb + c) * S) + sub;
+                st_stream_u4(dst, mk_u4(a0, a1));
+                const uint64_t h = mix64(group_xor64<G>(word_hash(a0, 2 * sub) ^ word_hash(a1, 2 * sub + 1), gm));
+                const int pc = group_sum<G>(__popcll(a0) + __popcll(a1), gm);
+                if (sub == 0) {
+                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(a0) >> 44);
+                    ev.cand_agg[cb + c] = pack_key(value, c);
+                    ev.cand_first[cb + c] = c;
+                    ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
+                }
+                __threadfence();
+                __syncwarp(gm);
+                // open-addressing insert (next_l.entry(), clean.rs:738)
+                const uint32_t tag = (uint32_t)(h >> 32);
+                const unsigned long long entry = ((unsigned long long)tag << 32) | c;
+                uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+                unsigned long long* tab = ev.table + (size_t)k * ev.T;
+                for (;;) {
+                    unsigned long long old = 0;
+                    if (sub == 0) old = atomicCAS(tab + slot, EMPTY64, entry);
+                    old = __shfl_sync(gm, old, (threadIdx.x & 31) & ~(G - 1));
+                    if (old == EMPTY64) {  // Entry::Vacant, clean.rs:739-765
+                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; }
+                        break;
+                    }
+                    if ((uint32_t)(old >> 32) == tag) {
+                        const uint32_t oc = (uint32_t)old;
+                        const uint4 o4 = ld_cg_u4(reinterpret_cast<const uint4*>(ev.cand_state + (cb + oc) * S) + sub);
+                        const bool eq = group_all<G>(u4lo(o4) == a0 && u4hi(o4) == a1, gm);
+                        if (eq) {  // Entry::Occupied, clean.rs:766-774 + append_edge_to! :199-220
+                            if (sub == 0) {
+                                atomicMax(ev.cand_agg + cb + oc, pack_key(value, c));   // value_top = max, `>=`: last (largest) candidate wins
+                                atomicMin(ev.cand_first + cb + oc, c);                    // canonical identity = first candidate
+                                if (fl & NF_INEXACT) ev.cand_inex[cb + oc] = 1;           // exact &= parent.exact
+                                ev.cand_rep[cb + c] = oc;
+                            }
+                            break;
+                        }
+                    }
+                    slot = (slot + 1) & (uint32_t)(ev.T - 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_exp) { atomicAdd(&ctl->expanded, (unsigned long long)s_exp); atomicAdd(&ctl->transitions, (unsigned long long)s_tr); }
+}
+
+// =================================================================================================================
+// k_finish: one CTA per DD.  Decides everything about layer t (whose candidates were produced by k_expand(t-1)).
+// =================================================================================================================
+struct FinishSmem {
+    int scan[40];
+    unsigned long long red64[40];
+    unsigned int hist[2048];   // vertex counters (n <= 2048) ; reused as 256-bin digit histogram by the select
+    unsigned long long merged[32];
+    int misc[16];
+};
+
+// compare two unique candidates by the cut order (clean.rs:803-808 + misp/main.rs:205-208): returns true if a is BETTER than b
+template <int S>
+__device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
+    const unsigned long long ka = (ev.ukey[cb + a] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + a];
+    const unsigned long long kb = (ev.ukey[cb + b] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + b];
+    if (ka != kb) return ka > kb;
+    for (int j = 0; j < S; ++j) {
+        const uint64_t xa = lex_word(ev.cand_state[(cb + a) * S + j]), xb = lex_word(ev.cand_state[(cb + b) * S + j]);
+        if (xa != xb) return xa > xb;
+    }
+    return false;
+}
+
+template <int S>
+__global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
+    constexpr int NT = 1024;
+    __shared__ FinishSmem sm;
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DDCtl* ctl = ev.ctl + k;
+    const int status = ctl->status;
+    if (status == ST_DONE) return;
+    if (status == ST_TERMINAL) { if (tid == 0) ctl->status = ST_DONE; return; }
+    const int ncand = ctl->ncand;
+    const size_t cb = (size_t)k * ev.C;
+    const size_t lb = (size_t)k * ev.Lmax;
+    if (tid == 0) ctl->lel_pending = 0;  // the snapshot requested by the previous step has been taken by k_compact
+
+    // ---- A. canonical representative of every distinct state = its first candidate (rule C1) -----------------
+    for (int c = tid; c < ncand; c += NT) {
+        if (ev.cand_rep[cb + c] == (uint32_t)c) {
+            const uint32_t f = ev.cand_first[cb + c];
+            ev.uflag[cb + f] = 1;
+            ev.ukey[cb + f] = ev.cand_agg[cb + c];
+            ev.uinex[cb + f] = ev.cand_inex[cb + c];
+        }
+    }
+    __syncthreads();
+    // ---- A'. ordered list of the unique candidates -----------------------------------------------------------
+    const int per = (ncand + NT - 1) / NT;
+    const int lo = min(tid * per, ncand), hi = min(lo + per, ncand);
+    int cnt = 0;
+    for (int c = lo; c < hi; ++c) cnt += (ev.uflag[cb + c] != 0);
+    int U;
+    int off = block_excl_scan(cnt, &U, sm.scan);
+    for (int c = lo; c < hi; ++c) if (ev.uflag[cb + c]) ev.ulist[cb + off++] = (uint32_t)c;
+    __syncthreads();
+
+    if (U == 0) {  // every node was pruned: empty layer (clean.rs:667-669) -> no best node
+        if (tid == 0) { ctl->status = ST_DONE; ctl->t_term = t; ctl->has_best = 0; ctl->has_best_exact = 0; ev.nlog[lb + t] = 0; atomicSub(ev.active, 1); }
+        return;
+    }
+
+    // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties ---
+    for (int i = tid; i < 2048; i += NT) sm.hist[i] = 0;
+    __syncthreads();
+    {
+        constexpr int W32 = 2 * S;                    // 32-bit words per state
+        constexpr int SLAB = W32 < 8 ? W32 : 8;       // words handled per pass (bounds the register footprint)
+        for (int slab = 0; slab < W32; slab += SLAB) {
+            uint32_t cntw[SLAB];
+#pragma unroll
+            for (int j = 0; j < SLAB; ++j) cntw[j] = 0;
+            for (int base = warp * 32; base < U; base += 32 * (NT / 32)) {
+                const int ui = base + lane;
+                uint32_t r[SLAB];
+                if (ui < U) {
+                    const uint4* p = reinterpret_cast<const uint4*>(ev.cand_state + (cb + ev.ulist[cb + ui]) * S) + slab / 4;
+#pragma unroll
+                    for (int q = 0; q < SLAB / 4; ++q) { uint4 v = p[q]; r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SLAB; ++j) r[j] = 0;
+                }
+#pragma unroll
+                for (int j = 0; j < SLAB; ++j) cntw[j] += __popc(warp_transpose32(r[j]));  // lane b: #states holding vertex 32(slab+j)+b
+            }
+#pragma unroll
+            for (int j = 0; j < SLAB; ++j) if (cntw[j]) atomicAdd(&sm.hist[32 * (slab + j) + lane], cntw[j]);
+        }
+    }
+    __syncthreads();
+    unsigned long long best = ~0ull;
+    for (int i = tid; i < ev.n; i += NT) { unsigned c = sm.hist[i]; if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i); }
+    best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, sm.red64);
+    const bool terminal = best == ~0ull;  // next_variable == None: the layer is the terminal layer (clean.rs:350,608-632)
+    const int var = terminal ? -1 : (int)(uint32_t)best;
+
+    // ---- C. width cut ----------------------------------------------------------------------------------------
+    const int W = ctl->width, comp = ctl->comp_type;
+    bool cut = false; int need = 0;
+    if (!terminal) {
+        if (comp == DDO_RESTRICTED && U > W) { cut = true; need = W; }               // clean.rs:782-787
+        else if (comp == DDO_RELAXED && U > W && t >= 2) { cut = true; need = W - 1; }  // clean.rs:788-793 (layers.len() > 1)
+    }
+    if (!cut && U > ev.Wcap) {
+        if (tid == 0) { ctl->status = ST_DONE; ctl->overflow = 1; ctl->t_term = t; atomicSub(ev.active, 1); }
+        return;
+    }
+    // ustat[ui]: 0 active (undecided), 1 keep, 2 drop
+    for (int ui = tid; ui < U; ui += NT) ev.ustat[cb + ui] = cut ? 0 : 1;
+    __syncthreads();
+    if (cut) {
+        int nactive = U;
+        bool done = false;
+        if (need == 0) { for (int ui = tid; ui < U; ui += NT) ev.ustat[cb + ui] = 2; done = true; }
+        for (int chunk = 0; chunk <= S && !done; ++chunk) {
+            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j: lexicographic word j-1
+            auto key_of = [&](int ui) -> unsigned long long {
+                const uint32_t c = ev.ulist[cb + ui];
+                if (chunk == 0) return (ev.ukey[cb + c] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + c];
+                return lex_word(ev.cand_state[(cb + c) * S + (chunk - 1)]);
+            };
+            unsigned long long kor = 0, kand = ~0ull;
+            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) { unsigned long long x = key_of(ui); kor |= x; kand &= x; }
+            kor = block_reduce(kor, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
+            kand = block_reduce(kand, [](unsigned long long a, unsigned long long b) { return a & b; }, ~0ull, sm.red64);
+            const unsigned long long diff = kor ^ kand;
+            for (int byte = 7; byte >= 0 && !done; --byte) {
+                if (((diff >> (8 * byte)) & 0xff) == 0) continue;  // every undecided key has the same digit here
+                for (int i = tid; i < 256; i += NT) sm.hist[i] = 0;
+                __syncthreads();
+                for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) atomicAdd(&sm.hist[(key_of(ui) >> (8 * byte)) & 0xff], 1u);
+                __syncthreads();
+                if (warp == 0) {  // bucket b with  #(digit > b) < need <= #(digit >= b)
+                    int c8[8]; int s = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { c8[q] = (int)sm.hist[255 - (lane * 8 + q)]; s += c8[q]; }  // lane 0 owns the 8 largest digits
+                    int inc = s;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
+                    int before = inc - s;  // count of digits strictly greater than this lane's 8 buckets
+                    if (before < need && need <= inc) {
+                        int acc = before;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (acc < need && need <= acc + c8[q]) { sm.misc[0] = 255 - (lane * 8 + q); sm.misc[1] = acc; sm.misc[2] = c8[q]; }
+                            acc += c8[q];
+                        }
+                    }
+                }
+                __syncthreads();
+                const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
+                need -= above; nactive = inb;
+                const bool all_keep = (need == nactive);
+                for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) {
+                    const int d = (int)((key_of(ui) >> (8 * byte)) & 0xff);
+                    if (d > b) ev.ustat[cb + ui] = 1; else if (d < b) ev.ustat[cb + ui] = 2; else if (all_keep) ev.ustat[cb + ui] = 1;
+                }
+                __syncthreads();
+                if (all_keep) done = true;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- D. stable positions of the survivors (rule C3) ---------------------------------------------------------
+    const int uper = (U + NT - 1) / NT;
+    const int ulo = min(tid * uper, U), uhi = min(ulo + uper, U);
+    int kc = 0;
+    for (int ui = ulo; ui < uhi; ++ui) kc += (ev.ustat[cb + ui] == 1);
+    int nkeep;
+    int kp = block_excl_scan(kc, &nkeep, sm.scan);
+    for (int ui = ulo; ui < uhi; ++ui) {
+        const uint32_t c = ev.ulist[cb + ui];
+        if (ev.ustat[cb + ui] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
+    }
+    int n_next = nkeep;
+    int s_pos = -1, r_pos = -1;
+    __syncthreads();
+
+    // ---- E. relaxation: merge the overflow (clean.rs:826-876; misp/main.rs:172-178 union) ------------------------
+    if (cut && comp == DDO_RELAXED) {
+        if (tid < 32) sm.merged[tid] = 0;
+        __syncthreads();
+        uint64_t acc[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) acc[j] = 0;
+        unsigned long long mkey = 0;
+        for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+            const uint32_t c = ev.ulist[cb + ui];
+#pragma unroll
+            for (int j = 0; j < S; ++j) acc[j] |= ev.cand_state[(cb + c) * S + j];
+            mkey = max(mkey, ev.ukey[cb + c]);
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint64_t x = warp_reduce(acc[j], [](uint64_t a, uint64_t b) { return a | b; });
+            if (lane == 0 && x) atomicOr(&sm.merged[j], (unsigned long long)x);
+        }
+        mkey = block_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        __syncthreads();
+        // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state
+        if (tid == 0) {
+            uint64_t h = 0;
+            for (int j = 0; j < S; ++j) h ^= word_hash(sm.merged[j], j);
+            h = mix64(h);
+            const uint32_t tag = (uint32_t)(h >> 32);
+            uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+            const unsigned long long* tab = ev.table + (size_t)k * ev.T;
+            int recycled = -1;
+            for (;;) {
+                const unsigned long long e = tab[slot];
+                if (e == EMPTY64) break;
+                if ((uint32_t)(e >> 32) == tag) {
+                    const uint32_t oc = (uint32_t)e;
+                    bool eq = true;
+                    for (int j = 0; j < S; ++j) eq = eq && ev.cand_state[(cb + oc) * S + j] == sm.merged[j];
+                    if (eq) { const uint32_t f = ev.cand_first[cb + oc]; if (ev.pos_of[cb + f] != NONE32) recycled = (int)f; break; }
+                }
+                slot = (slot + 1) & (uint32_t)(ev.T - 1);
+            }
+            sm.misc[4] = recycled;
+        }
+        __syncthreads();
+        const int recycled = sm.misc[4];
+        const int mpos = (recycled >= 0) ? (int)ev.pos_of[cb + recycled] : nkeep;
+        if (recycled >= 0) {
+            // clean.rs:868-871: the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node
+            uint32_t bestc = NONE32;
+            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+                const uint32_t c = ev.ulist[cb + ui];
+                if (bestc == NONE32 || cand_better<S>(ev, cb, c, bestc)) bestc = c;
+            }
+            __shared__ uint32_t s_best[NT];
+            s_best[tid] = bestc;
+            __syncthreads();
+            for (int d = NT / 2; d > 0; d >>= 1) {
+                if (tid < d) {
+                    const uint32_t a = s_best[tid], b2 = s_best[tid + d];
+                    if (a == NONE32 || (b2 != NONE32 && cand_better<S>(ev, cb, b2, a))) s_best[tid] = b2;
+                }
+                __syncthreads();
+            }
+            const uint32_t saved = s_best[0];
+            s_pos = nkeep; r_pos = mpos; n_next = nkeep + 1;
+            if (tid == 0) {
+                // the recycled node receives every relaxed edge: RELAXED flag, value_top = max (`>=`: the appended edges win ties)
+                const unsigned long long rk = ev.ukey[cb + recycled];
+                if (key_value(mkey) >= key_value(rk)) ev.ukey[cb + recycled] = mkey;
+                ev.uinex[cb + recycled] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
+            }
+            __syncthreads();
+            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+                const uint32_t c = ev.ulist[cb + ui];
+                if (c == saved) { ev.pos_of[cb + c] = (uint32_t)s_pos; ev.ustat[cb + ui] = 1; ev.uflag[cb + c] = 2; }
+                else ev.pos_of[cb + c] = (uint32_t)r_pos;
+            }
+        } else {
+            n_next = nkeep + 1;
+            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) ev.pos_of[cb + ev.ulist[cb + ui]] = (uint32_t)mpos;
+            // new merged node (clean.rs:832-849) written straight into the next layer
+            const int nbuf = t & 1;
+            const size_t nb = (size_t)k * ev.Wcap + mpos;
+            if (tid < S) ev.cur_state[nbuf][nb * S + tid] = sm.merged[tid];
+            if (tid == 0) {
+                ev.cur_val[nbuf][nb] = key_value(mkey);
+                ev.cur_flag[nbuf][nb] = (uint8_t)(NF_INEXACT | NF_RELAXED);
+                ev.plog[(lb + t) * ev.Wcap + mpos] = ((uint32_t)mkey & PLOG_CAND_MASK) | PLOG_INEXACT | PLOG_RELAXED;
+            }
+        }
+    }
+
+    // ---- F. terminal layer: best nodes (clean.rs:620-632, rule C4: last maximum) ----------------------------------
+    if (terminal) {
+        unsigned long long b_all = 0, b_ex = 0;  // (biased value, pos + 1)
+        for (int ui = tid; ui < U; ui += NT) {
+            const uint32_t c = ev.ulist[cb + ui];
+            const unsigned long long kk = (ev.ukey[cb + c] & 0xFFFFFFFF00000000ull) | (unsigned)(ev.pos_of[cb + c] + 1);
+            b_all = max(b_all, kk);
+            if (!(ev.uinex[cb + c] & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk);
+        }
+        b_all = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        b_ex = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        if (tid == 0) {
+            ctl->has_best = 1; ctl->best_value = key_value(b_all); ctl->best_pos = (int)(uint32_t)b_all - 1;
+            ctl->has_best_exact = b_ex != 0;
+            if (b_ex) { ctl->best_exact_value = key_value(b_ex); ctl->best_exact_pos = (int)(uint32_t)b_ex - 1; }
+        }
+    }
+
+    if (tid == 0) {
+        ev.nlog[lb + t] = n_next;
+        ev.vlog[lb + t] = var;
+        ev.rslog[(lb + t) * 2] = s_pos; ev.rslog[(lb + t) * 2 + 1] = r_pos;
+        ctl->n_cur = n_next; ctl->var = var;
+        if (cut && ctl->lel < 0) { ctl->lel = t - 1; ctl->lel_pending = 1; }  // _maybe_save_lel, clean.rs:796-800
+        if (terminal) { ctl->status = ST_TERMINAL; ctl->t_term = t; atomicSub(ev.active, 1); }
+    }
+}
+
+// =================================================================================================================
+// k_compact: scatter layer t into the ping-pong buffers, write logs, release hash slots, snapshot the LEL.
+// =================================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256) k_compact(EV ev, int t) {
+    constexpr int G = S / 2;
+    constexpr int CPB = 256 / G;
+    const int k = blockIdx.y;
+    const DDCtl* ctl = ev.ctl + k;
+    if (ctl->status == ST_DONE) return;
+    const int ncand = ctl->ncand;
+    if (blockIdx.x * CPB >= ncand) return;
+    const int c = blockIdx.x * CPB + threadIdx.x / G;
+    if (c >= ncand) return;
+    const int sub = threadIdx.x % G;
+    const size_t cb = (size_t)k * ev.C;
+    const size_t lb = (size_t)k * ev.Lmax;
+    const int nbuf = t & 1;
+    const bool relaxed = ctl->comp_type == DDO_RELAXED;
+    const uint32_t rep = ev.cand_rep[cb + c];
+    uint32_t child = NONE32;
+    if (rep != NONE32) {
+        const uint32_t f = ev.cand_first[cb + rep];
+        child = ev.pos_of[cb + f];
+        if (sub == 0 && rep == (uint32_t)c) {  // release the hash slot this candidate claimed
+            const uint32_t slot = ev.cand_slot[cb + c];
+            if (slot != NONE32) ev.table[(size_t)k * ev.T + slot] = EMPTY64;
+        }
+        if (ev.uflag[cb + c] == 2) {  // surviving canonical representative: becomes node `pos` of layer t
+            const uint32_t pos = ev.pos_of[cb + c];
+            const size_t nb = (size_t)k * ev.Wcap + pos;
+            const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(ev.cand_state + (cb + c) * S) + sub);
+            st_stream_u4(reinterpret_cast<uint4*>(ev.cur_state[nbuf] + nb * S) + sub, v);
+            if (sub == 0) {
+                const unsigned long long key = ev.ukey[cb + c];
+                const uint32_t fl = ev.uinex[cb + c];
+                ev.cur_val[nbuf][nb] = key_value(key);
+                ev.cur_flag[nbuf][nb] = (uint8_t)fl;
+                ev.plog[(lb + t) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
+            }
+        }
+    }
+    if (t > 0) {
+        if (relaxed && sub == 0) ev.clog[(lb + t - 1) * ev.C + c] = child;  // edge (parent c/2, decision) -> node `child` of layer t
+        if (ctl->lel_pending && relaxed && !(c & 1)) {  // layer t-1 is the last exact layer: keep its nodes for the cutset
+            const int i = c >> 1;
+            const size_t pb = (size_t)k * ev.Wcap + i;
+            const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(ev.cur_state[(t - 1) & 1] + pb * S) + sub);
+            st_stream_u4(reinterpret_cast<uint4*>(ev.lel_state + pb * S) + sub, v);
+            if (sub == 0) { ev.lel_val[pb] = ev.cur_val[(t - 1) & 1][pb]; ev.lel_rub[pb] = ev.cur_rub[pb]; }
+        }
+    }
+}
+
+// =================================================================================================================
+// k_finalize: exact-best-path walk (clean.rs:634-655) and decision bits of the best / best exact path (clean.rs:329-343)
+// =================================================================================================================
+__global__ void k_finalize(EV ev, int count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    DDCtl* ctl = ev.ctl + k;
+    const size_t lb = (size_t)k * ev.Lmax;
+    ctl->ebpo = 0;
+    if (ctl->overflow || !ctl->has_best) return;
+    const int T = ctl->t_term;
+    if (ctl->comp_type == DDO_RELAXED) {
+        int pos = ctl->best_pos, tt = T;
+        bool exact = true;
+        for (;;) {
+            const uint32_t e = ev.plog[(lb + tt) * ev.Wcap + pos];
+            if (!(e & PLOG_INEXACT)) { exact = true; break; }
+            if (e & PLOG_RELAXED) { exact = false; break; }
+            if (tt == 0) break;
+            pos = (int)((e & PLOG_CAND_MASK) >> 1); --tt;
+        }
+        ctl->ebpo = exact;
+        if (exact) { ctl->has_best_exact = 1; ctl->best_exact_pos = ctl->best_pos; ctl->best_exact_value = ctl->best_value; }  // clean.rs:638-640
+    }
+    for (int which = 0; which < 2; ++which) {
+        uint64_t* out = (which == 0 ? ev.best_path : ev.best_exact_path) + (size_t)k * ev.PW;
+        for (int w = 0; w < ev.PW; ++w) out[w] = 0;
+        if (which == 1 && !ctl->has_best_exact) continue;
+        int pos = which == 0 ? ctl->best_pos : ctl->best_exact_pos;
+        for (int tt = T; tt >= 1; --tt) {
+            const uint32_t cand = ev.plog[(lb + tt) * ev.Wcap + pos] & PLOG_CAND_MASK;
+            if (!(cand & 1u)) out[(tt - 1) >> 6] |= 1ull << ((tt - 1) & 63);  // even candidate = YES
+            pos = (int)(cand >> 1);
+        }
+    }
+}
+
+// =================================================================================================================
+// k_bottomup: local bounds of a relaxed DD (clean.rs:448-475) as a per-layer GATHER over the child log, then the cutset
+// upper bounds ub = min(value_top + rub, value_top + value_bot, best_value) of the last exact layer (clean.rs:426-428).
+// =================================================================================================================
+constexpr int32_t UNMARKED = INT32_MIN;
+__global__ void __launch_bounds__(1024, 1) k_bottomup(EV ev) {
+    const int k = blockIdx.x;
+    DDCtl* ctl = ev.ctl + k;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    if (tid == 0) { ctl->cutset_count = 0; ctl->lel_n = 0; }
+    if (ctl->comp_type != DDO_RELAXED || ctl->overflow || !ctl->has_best || ctl->lel < 0) return;
+    __shared__ int s_cnt;
+    if (tid == 0) s_cnt = 0;
+    const size_t lb = (size_t)k * ev.Lmax;
+    const int T = ctl->t_term, L = ctl->lel;
+    int32_t* nxt = ev.vb[0] + (size_t)k * ev.Wcap;
+    int32_t* cur = ev.vb[1] + (size_t)k * ev.Wcap;
+    for (int i = tid; i < ev.nlog[lb + T]; i += NT) nxt[i] = 0;  // terminal layer: value_bot = 0, MARKED
+    __syncthreads();
+    for (int tt = T - 1; tt >= L; --tt) {
+        const int n = ev.nlog[lb + tt];
+        const int wv = ev.weight[ev.vlog[lb + tt]];
+        const int s = ev.rslog[(lb + tt + 1) * 2], r = ev.rslog[(lb + tt + 1) * 2 + 1];
+        const uint32_t* cl = ev.clog + (lb + tt) * ev.C;
+        for (int i = tid; i < n; i += NT) {
+            int32_t best = UNMARKED;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const uint32_t ch = cl[2 * i + d];
+                if (ch == NONE32) continue;
+                const int cost = d == 0 ? wv : 0;
+                int32_t x = nxt[ch];
+                if (x != UNMARKED) best = max(best, x + cost);
+                if ((int)ch == s && r >= 0) { x = nxt[r]; if (x != UNMARKED) best = max(best, x + cost); }  // edges of the saved node were also copied to the recycled node
+            }
+            cur[i] = best;
+        }
+        __syncthreads();
+        int32_t* tmp = nxt; nxt = cur; cur = tmp;
+    }
+    const int n = ev.nlog[lb + L];
+    const size_t nb = (size_t)k * ev.Wcap;
+    int local = 0;
+    for (int i = tid; i < n; i += NT) {
+        const int32_t vbot = nxt[i];
+        const bool marked = vbot != UNMARKED;
+        ev.cs_marked[nb + i] = marked;
+        if (marked) {
+            const int val = ev.lel_val[nb + i];
+            ev.cs_ub[nb + i] = min(min(val + ev.lel_rub[nb + i], val + vbot), ctl->best_value);
+            ++local;
+        }
+    }
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (tid == 0) { ctl->cutset_count = s_cnt; ctl->lel_n = n; }
+}
+
+// =================================================================================================================
+// drain_cutset (clean.rs:417-445) + the solver-side filter (parallel.rs:460-461) as a batched stream compaction
+// =================================================================================================================
+__global__ void __launch_bounds__(1024, 1) k_cutset_count(EV ev, DrainOut o, const long long* ub_cap, const long long* lb_filter, int count) {
+    __shared__ int scan[40];
+    const int k = blockIdx.x;
+    const DDCtl* ctl = ev.ctl + k;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int n = (k < count && ctl->cutset_count > 0) ? ctl->lel_n : 0;
+    const size_t nb = (size_t)k * ev.Wcap;
+    const int per = (n + NT - 1) / NT, lo = min(tid * per, n), hi = min(lo + per, n);
+    const long long cap = ub_cap[k], lbf = lb_filter[k];
+    int c = 0;
+    for (int i = lo; i < hi; ++i) c += (ev.cs_marked[nb + i] && min((long long)ev.cs_ub[nb + i], cap) > lbf);
+    int total;
+    int off = block_excl_scan(c, &total, scan);
+    for (int i = lo; i < hi; ++i) {
+        const bool f = ev.cs_marked[nb + i] && min((long long)ev.cs_ub[nb + i], cap) > lbf;
+        o.loc[nb + i] = f ? (uint32_t)off++ : NONE32;
+    }
+    if (tid == 0) o.count[k] = total;
+}
+__global__ void k_cutset_offsets(DrainOut o, int K) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < K; ++k) { o.offset[k] = acc; acc += o.count[k]; }
+        o.offset[K] = acc;
+    }
+}
+template <int S>
+__global__ void __launch_bounds__(256) k_cutset_write(EV ev, DrainOut o, const long long* ub_cap, int pw) {
+    const int k = blockIdx.y;
+    const DDCtl* ctl = ev.ctl + k;
+    if (o.count[k] == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->lel_n) return;
+    const size_t nb = (size_t)k * ev.Wcap;
+    const uint32_t loc = o.loc[nb + i];
+    if (loc == NONE32) return;
+    const size_t rec = (size_t)o.offset[k] + loc;
+    for (int j = 0; j < S; ++j) o.state[rec * S + j] = ev.lel_state[(nb + i) * S + j];
+    o.val[rec] = ev.lel_val[nb + i];
+    o.ub[rec] = (int32_t)min((long long)ev.cs_ub[nb + i], ub_cap[k]);
+    o.dd[rec] = k;
+    const size_t lb = (size_t)k * ev.Lmax;
+    uint64_t bits[8];  // pw <= 8 (lel < 512) is enforced on the host; deeper cutsets use the slow path below
+    for (int w = 0; w < 8; ++w) bits[w] = 0;
+    int pos = i;
+    for (int tt = ctl->lel; tt >= 1; --tt) {
+        const uint32_t cand = ev.plog[(lb + tt) * ev.Wcap + pos] & PLOG_CAND_MASK;
+        if (!(cand & 1u)) {
+            if (pw <= 8) bits[(tt - 1) >> 6] |= 1ull << ((tt - 1) & 63);
+            else o.path[rec * pw + ((tt - 1) >> 6)] |= 1ull << ((tt - 1) & 63);
+        }
+        pos = (int)(cand >> 1);
+    }
+    if (pw <= 8) for (int w = 0; w < pw; ++w) o.path[rec * pw + w] = bits[w];
+}
+
+}  // namespace ddo

@@ -1,0 +1,339 @@
+// solver.cu -- host-side branch-and-bound driver (see solver.hpp).  No device code in this file.
+#include "solver.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace ddo {
+
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// NoDupFringe
+// ---------------------------------------------------------------------------------------------------------------
+uint64_t NoDupFringe::hash_state(const uint64_t* st, int W) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int j = 0; j < W; ++j) { h ^= st[j] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xff51afd7ed558ccdULL; h ^= h >> 32; }
+    return h;
+}
+// BitSet::cmp of bit-set 0.5.3 (lexicographic over ascending members), word-parallel
+static int lex_cmp(const uint64_t* a, const uint64_t* b, int W) {
+    for (int j = 0; j < W; ++j) {
+        const uint64_t d = a[j] ^ b[j];
+        if (!d) continue;
+        const int p = __builtin_ctzll(d);
+        const bool a_owns = (a[j] >> p) & 1;
+        const uint64_t* other = a_owns ? b : a;
+        bool has_more = p < 63 && (other[j] >> (p + 1)) != 0;
+        for (int q = j + 1; q < W && !has_more; ++q) has_more = other[q] != 0;
+        const int owner_cmp = has_more ? -1 : 1;
+        return a_owns ? owner_cmp : -owner_cmp;
+    }
+    return 0;
+}
+int NoDupFringe::compare_new(int32_t ub, int32_t value, int16_t pc, const uint64_t* st, int b) const {  // subproblem_ranking.rs:86-90
+    const Item& y = items_[b];
+    if (ub != y.ub) return ub < y.ub ? -1 : 1;
+    if (value != y.value) return value < y.value ? -1 : 1;
+    if (pc != popc_[b]) return pc < popc_[b] ? -1 : 1;  // misp/main.rs:205-208
+    return lex_cmp(st, state(b), W);
+}
+int NoDupFringe::compare(int a, int b) const { return compare_new(items_[a].ub, items_[a].value, popc_[a], state(a), b); }
+
+void NoDupFringe::clear() {  // no_duplicate.rs:168-174
+    states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); pos_.clear(); heap_.clear(); recycle_.clear();
+    table_.clear(); table_used_ = 0;
+}
+void NoDupFringe::rehash(size_t min_cap) {
+    size_t cap = 1024;
+    while (cap < min_cap) cap <<= 1;
+    table_.assign(cap, -1); table_used_ = 0;
+    for (int id : heap_) table_insert(id);
+}
+void NoDupFringe::table_insert(int id) {
+    const size_t mask = table_.size() - 1;
+    size_t s = hash_[id] & mask;
+    while (table_[s] >= 0) s = (s + 1) & mask;
+    if (table_[s] == -1) ++table_used_;
+    table_[s] = id;
+}
+int NoDupFringe::table_find(const uint64_t* st, uint64_t h) const {
+    if (table_.empty()) return -1;
+    const size_t mask = table_.size() - 1;
+    size_t s = h & mask;
+    while (table_[s] != -1) {
+        const int id = table_[s];
+        if (id >= 0 && hash_[id] == h && std::memcmp(state(id), st, (size_t)W * 8) == 0) return id;
+        s = (s + 1) & mask;
+    }
+    return -1;
+}
+void NoDupFringe::table_erase(int id) {
+    const size_t mask = table_.size() - 1;
+    size_t s = hash_[id] & mask;
+    while (table_[s] != id) s = (s + 1) & mask;
+    table_[s] = -2;
+}
+void NoDupFringe::bubble_up(int id) {  // no_duplicate.rs:227-242
+    size_t me = (size_t)pos_[id];
+    while (me != 0) {
+        const size_t par = (me - 1) / 2;
+        if (compare(heap_[me], heap_[par]) <= 0) break;
+        const int p_id = heap_[par];
+        pos_[p_id] = (int)me; pos_[id] = (int)par; heap_[me] = p_id; heap_[par] = id;
+        me = par;
+    }
+}
+void NoDupFringe::bubble_down(int id) {  // no_duplicate.rs:244-259,279-295
+    size_t me = (size_t)pos_[id];
+    const size_t size = heap_.size();
+    for (;;) {
+        const size_t left = me * 2 + 1, right = me * 2 + 2;
+        if (left >= size) break;
+        size_t kid = left;
+        if (right < size && compare(heap_[left], heap_[right]) <= 0) kid = right;
+        if (compare(heap_[me], heap_[kid]) >= 0) break;
+        const int k_id = heap_[kid];
+        pos_[k_id] = (int)me; pos_[id] = (int)kid; heap_[me] = k_id; heap_[kid] = id;
+        me = kid;
+    }
+}
+void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
+    const uint64_t h = hash_state(st, W);
+    const int found = table_find(st, h);
+    if (found >= 0) {  // Occupied, no_duplicate.rs:92-118
+        const int id = found;
+        const int32_t old_lp = items_[id].value, old_ub = items_[id].ub;
+        const int32_t merged_ub = std::max(ub, old_ub);
+        const bool up = compare_new(merged_ub, value, popc_[id], st, id) > 0;
+        if (value > old_lp) {
+            items_[id] = Item{value, merged_ub, depth, rec};
+            std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
+            std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
+        }
+        if (ub > old_ub) items_[id].ub = ub;
+        if (up) bubble_up(id);
+        return;
+    }
+    int id;  // Vacant, no_duplicate.rs:119-135
+    if (recycle_.empty()) {
+        id = (int)items_.size();
+        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); pos_.push_back(0);
+        states_.resize(states_.size() + W); bits_.resize(bits_.size() + PW);
+    } else { id = recycle_.back(); recycle_.pop_back(); }
+    items_[id] = Item{value, ub, depth, rec};
+    std::memcpy(&states_[(size_t)id * W], st, (size_t)W * 8);
+    std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
+    std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
+    int pc = 0;
+    for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
+    popc_[id] = (int16_t)pc; hash_[id] = h;
+    heap_.push_back(id);
+    pos_[id] = (int)heap_.size() - 1;
+    if ((table_used_ + 1) * 2 > table_.size()) rehash(heap_.size() * 4);  // re-inserts every live node, `id` included
+    else table_insert(id);
+    bubble_up(id);
+}
+int NoDupFringe::pop() {
+    if (heap_.empty()) return -1;
+    const int id = heap_[0];
+    heap_[0] = heap_.back(); heap_.pop_back();
+    if (!heap_.empty()) { pos_[heap_[0]] = 0; bubble_down(heap_[0]); }
+    recycle_.push_back(id);
+    table_erase(id);
+    return id;
+}
+// ---------------------------------------------------------------------------------------------------------------
+// Solver
+// ---------------------------------------------------------------------------------------------------------------
+Solver::Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws)
+    : model(m), eng(e), width_kind(wk), width(w), wave_size(ws), fringe(m->words, (m->n + 63) / 64) {}
+
+int Solver::init(bool push_root) {  // parallel.rs:368-385
+    fringe.clear(); recs.clear();
+    best_lb = INT64_MIN; best_ub = INT64_MAX; has_sol = false; best_sol.clear(); aborted = false;
+    explored = expanded = transitions = compilations = waves = 0; device_ms = fringe_ms = 0;
+    if (push_root) {
+        std::vector<uint64_t> st(model->words, 0), bits(1, 0);
+        for (int i = 0; i < model->n; ++i) st[i >> 6] |= 1ull << (i & 63);  // misp/main.rs:69-71
+        fringe.push(st.data(), 0, INT32_MAX, 0, -1, bits.data(), 0);
+    }
+    return DDO_OK;
+}
+
+void Solver::full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decision>& out) const {
+    if (rec == -1) return;
+    const PathRec& r = recs[rec];
+    full_path(r.parent_rec, r.parent_bits.data(), out);
+    for (size_t i = 0; i < r.vars.size(); ++i) out.push_back(ddo_decision{r.vars[i], (int32_t)((bits[i >> 6] >> (i & 63)) & 1)});
+}
+
+int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
+    const int W = model->words, PWN = (model->n + 63) / 64;
+    struct Popped { std::vector<uint64_t> state, bits; int32_t value, ub, depth, rec; };
+    std::vector<Popped> wv;
+    double t0 = now_ms();
+    int64_t top_ub = INT64_MIN;
+    while ((int)wv.size() < wave_size && !fringe.empty()) {  // get_workload, parallel.rs:500-559
+        const int id = fringe.pop();
+        const NoDupFringe::Item it = fringe.item(id);
+        const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
+        if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
+        if (wv.empty()) top_ub = ub;
+        Popped p;
+        p.state.assign(fringe.state(id), fringe.state(id) + W);
+        p.bits.assign(fringe.bits(id), fringe.bits(id) + PWN);
+        p.value = it.value; p.ub = it.ub; p.depth = it.depth; p.rec = it.rec;
+        wv.push_back(std::move(p));
+        ++explored;
+    }
+    fringe_ms += now_ms() - t0;
+    out3[1] = top_ub;
+    if (wv.empty()) { out3[0] = best_lb; out3[2] = 0; return DDO_OK; }
+    if (top_ub != INT64_MIN) best_ub = top_ub;
+    ++waves;
+    const int cnt = (int)wv.size();
+    std::vector<uint64_t> widths(cnt), states((size_t)cnt * W);
+    std::vector<int64_t> values(cnt);
+    std::vector<int32_t> depths(cnt);
+    for (int i = 0; i < cnt; ++i) {
+        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(model->n - wv[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
+        std::memcpy(&states[(size_t)i * W], wv[i].state.data(), (size_t)W * 8);
+        values[i] = wv[i].value; depths[i] = wv[i].depth;
+    }
+    auto improve = [&](int count, const std::vector<int>& map) -> int {  // maybe_update_best, parallel.rs:446-453, in wave order
+        int last = -1;
+        for (int j = 0; j < count; ++j) {
+            const DDCtl& c = eng->h_ctl[j];
+            expanded += c.expanded; transitions += c.transitions; ++compilations;
+            if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; last = j; }
+        }
+        if (last >= 0) {
+            std::vector<ddo_decision> dd(model->n + 1);
+            int32_t len = (int32_t)dd.size();
+            int rc = eng->best_solution(last, 1, dd.data(), &len);
+            if (rc != DDO_OK) return rc;
+            const Popped& root = wv[map[last]];
+            best_sol.clear();
+            full_path(root.rec, root.bits.data(), best_sol);
+            best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
+            has_sol = true;
+        }
+        return DDO_OK;
+    };
+    // 1. restriction (parallel.rs:396-423)
+    float ms = 0;
+    int rc = eng->stage_roots(cnt, widths.data(), states.data(), values.data(), depths.data());
+    if (rc != DDO_OK) return rc;
+    rc = eng->compile_staged(cnt, DDO_RESTRICTED, best_lb, cutoff_flag, &ms);
+    if (rc != DDO_OK) return rc;
+    device_ms += ms;
+    rc = eng->fetch_ctl(cnt);
+    if (rc != DDO_OK) return rc;
+    std::vector<int> ident(cnt);
+    for (int i = 0; i < cnt; ++i) ident[i] = i;
+    std::vector<int> open;  // sub-problems whose restricted DD is not exact
+    for (int i = 0; i < cnt; ++i) { const DDCtl& c = eng->h_ctl[i]; if (!(c.lel < 0)) open.push_back(i); }
+    rc = improve(cnt, ident);
+    if (rc != DDO_OK) return rc;
+    // 2. relaxation (parallel.rs:425-434)
+    if (!open.empty()) {
+        const int oc = (int)open.size();
+        std::vector<uint64_t> w2(oc), s2((size_t)oc * W);
+        std::vector<int64_t> v2(oc), caps(oc), lbs(oc);
+        std::vector<int32_t> d2(oc);
+        for (int j = 0; j < oc; ++j) {
+            const int i = open[j];
+            w2[j] = widths[i]; v2[j] = values[i]; d2[j] = depths[i];
+            std::memcpy(&s2[(size_t)j * W], &states[(size_t)i * W], (size_t)W * 8);
+        }
+        rc = eng->stage_roots(oc, w2.data(), s2.data(), v2.data(), d2.data());
+        if (rc != DDO_OK) return rc;
+        rc = eng->compile_staged(oc, DDO_RELAXED, best_lb, cutoff_flag, &ms);
+        if (rc != DDO_OK) return rc;
+        device_ms += ms;
+        rc = eng->fetch_ctl(oc);
+        if (rc != DDO_OK) return rc;
+        rc = improve(oc, open);
+        if (rc != DDO_OK) return rc;
+        // enqueue_cutset (parallel.rs:456-469): ub = min(node ub, root ub), kept iff ub > best_lb
+        for (int j = 0; j < oc; ++j) {
+            const DDCtl& c = eng->h_ctl[j];
+            const bool exact = (c.lel < 0) || c.ebpo;
+            caps[j] = wv[open[j]].ub == INT32_MAX ? INT64_MAX : wv[open[j]].ub;
+            lbs[j] = exact ? INT64_MAX : best_lb;
+        }
+        int pw = 1;
+        const int total = eng->drain_all(oc, caps.data(), lbs.data(), &pw);
+        if (total < 0) return total;
+        t0 = now_ms();
+        int cur_dd = -1, cur_rec = -1, lel = 0;
+        std::vector<int32_t> vars;
+        for (int r = 0; r < total; ++r) {
+            const int j = eng->h_out_dd[r];
+            if (j != cur_dd) {
+                cur_dd = j;
+                const DDCtl& c = eng->h_ctl[j];
+                lel = c.lel;
+                rc = eng->fetch_vars(j, vars);
+                if (rc != DDO_OK) return rc;
+                PathRec pr;
+                pr.parent_rec = wv[open[j]].rec; pr.parent_bits = wv[open[j]].bits;
+                pr.vars.assign(vars.begin(), vars.begin() + lel);
+                recs.push_back(std::move(pr));
+                cur_rec = (int)recs.size() - 1;
+            }
+            fringe.push(&eng->h_out_state[(size_t)r * eng->S], eng->h_out_val[r], eng->h_out_ub[r], wv[open[j]].depth + lel, cur_rec,
+                        &eng->h_out_path[(size_t)r * pw], std::min(pw, (lel + 63) / 64));
+        }
+        fringe_ms += now_ms() - t0;
+    }
+    out3[0] = best_lb;
+    out3[2] = fringe.empty() ? 0 : 1;
+    return DDO_OK;
+}
+
+void Solver::finish() { if (fringe.empty() && !aborted) best_ub = best_lb; }  // parallel.rs:512-515
+
+int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact, int32_t* has_value, int64_t* best_value) {  // parallel.rs:573-607
+    int rc = init(true);
+    if (rc != DDO_OK) return rc;
+    const double t_end = time_budget_s > 0 ? now_ms() + time_budget_s * 1000.0 : 0;
+    volatile int32_t cutoff = 0;
+    for (;;) {
+        if (fringe.empty()) break;
+        if ((max_waves && waves >= max_waves) || (t_end > 0 && now_ms() >= t_end)) { aborted = true; break; }  // TimeBudget, cutoff.rs:302-323
+        int64_t o3[3];
+        rc = wave(&cutoff, o3);
+        if (rc == DDO_CUTOFF) { aborted = true; break; }
+        if (rc != DDO_OK) return rc;
+    }
+    if (aborted) fringe.clear();  // abort_search, parallel.rs:479-489
+    else best_ub = best_lb;
+    std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });  // parallel.rs:605
+    if (is_exact) *is_exact = !aborted;
+    if (has_value) *has_value = has_sol;
+    if (best_value) *best_value = has_sol ? best_lb : 0;
+    return DDO_OK;
+}
+
+// Initial deal of the open sub-problems across ranks: every rank compiled the same root DD, so each one simply
+// keeps every nranks-th node of the common MaxUB order -- no data-path collective.
+int Solver::retain_share(int rank, int nranks) {
+    if (nranks <= 1) return DDO_OK;
+    if (rank < 0 || rank >= nranks) { set_error("retain_share: bad rank"); return DDO_ERR_INVALID; }
+    struct Keep { std::vector<uint64_t> state, bits; NoDupFringe::Item it; };
+    std::vector<Keep> keep;
+    const int W = model->words, PWN = (model->n + 63) / 64;
+    for (size_t idx = 0; !fringe.empty(); ++idx) {
+        const int id = fringe.pop();
+        if ((int)(idx % (size_t)nranks) != rank) continue;
+        Keep k; k.state.assign(fringe.state(id), fringe.state(id) + W); k.bits.assign(fringe.bits(id), fringe.bits(id) + PWN); k.it = fringe.item(id);
+        keep.push_back(std::move(k));
+    }
+    fringe.clear();
+    for (auto& k : keep) fringe.push(k.state.data(), k.it.value, k.it.ub, k.it.depth, k.it.rec, k.bits.data(), PWN);
+    return DDO_OK;
+}
+
+}  // namespace ddo

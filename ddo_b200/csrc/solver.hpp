@@ -1,0 +1,80 @@
+// solver.hpp -- host-side branch-and-bound driver over the device engine.
+//
+// Restates, natively, the callers of the hot path: `ParallelSolver` (ddo/src/implementation/solver/
+// parallel.rs:287-641) with its K workers running in lock-step as one device batch ("wave"), the `NoDupFringe`
+// (fringe/no_duplicate.rs:52-323) ordered by `MaxUB` (heuristics/subproblem_ranking.rs:86-90) with `MispRanking`
+// (examples/misp/main.rs:201-209), `FixedWidth` / `NbUnassignedWidth` (heuristics/width.rs:166-170,397-401) and `TimeBudget`
+// (heuristics/cutoff.rs:302-323).  Paths are kept as a tree of per-DD records so that a sub-problem costs O(state) host memory.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace ddo {
+
+// One record per compiled relaxed DD that produced open sub-problems: the decisions from that DD's root to its cutset layer share the
+// variable sequence; each sub-problem only stores one bit per layer.
+struct PathRec {
+    int32_t parent_rec;              // record of the DD root's own path, -1 for the problem root
+    std::vector<uint64_t> parent_bits;  // the DD root's decision bits inside parent_rec
+    std::vector<int32_t> vars;       // branching variable of each layer between the DD root and its cutset layer
+};
+
+class NoDupFringe {
+public:
+    NoDupFringe(int words, int pw) : W(words), PW(pw) {}
+    struct Item { int32_t value, ub, depth, rec; };
+    size_t len() const { return heap_.size(); }
+    bool empty() const { return heap_.empty(); }
+    void clear();
+    // no_duplicate.rs:88-140
+    void push(const uint64_t* state, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words);
+    // no_duplicate.rs:144-164; returns node id (valid until the next push)
+    int pop();
+    int top() const { return heap_.empty() ? -1 : heap_[0]; }
+    const uint64_t* state(int id) const { return &states_[(size_t)id * W]; }
+    const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
+    const Item& item(int id) const { return items_[id]; }
+private:
+    int W, PW;
+    std::vector<uint64_t> states_, bits_;
+    std::vector<Item> items_;
+    std::vector<int16_t> popc_;
+    std::vector<uint64_t> hash_;
+    std::vector<int> pos_, heap_, recycle_;
+    std::vector<int> table_;  // open addressing: node id or -1 (empty) / -2 (tombstone)
+    size_t table_used_ = 0;   // occupied + tombstones
+    int compare(int a, int b) const;  // MaxUB: ub, value, MispRanking
+    int compare_new(int32_t ub, int32_t value, int16_t pc, const uint64_t* st, int b) const;
+    void bubble_up(int id);
+    void bubble_down(int id);
+    void table_insert(int id);
+    int table_find(const uint64_t* st, uint64_t h) const;
+    void table_erase(int id);
+    void rehash(size_t min_cap);
+    static uint64_t hash_state(const uint64_t* st, int W);
+};
+
+struct Solver {
+    const MispModel* model; Engine* eng;
+    int width_kind; uint64_t width; int wave_size;
+    NoDupFringe fringe;
+    std::vector<PathRec> recs;
+    int64_t best_lb = INT64_MIN, best_ub = INT64_MAX;
+    bool has_sol = false; std::vector<ddo_decision> best_sol;
+    bool aborted = false;
+    uint64_t explored = 0, expanded = 0, transitions = 0, compilations = 0, waves = 0;
+    double device_ms = 0, fringe_ms = 0;
+
+    Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws);
+    int init(bool push_root);
+    int wave(const volatile int32_t* cutoff_flag, int64_t out3[3]);
+    int maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact, int32_t* has_value, int64_t* best_value);
+    void finish();
+    void full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decision>& out) const;
+    int retain_share(int rank, int nranks);
+};
+
+}  // namespace ddo

@@ -1,0 +1,132 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact (integer / bitset work)."""
+import json
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from ddo_b200 import CompilationType, FixedWidth, GpuMdd, Misp, NbUnassignedWidth, ParNoCachingSolverLel, SubProblem, gnp, parse_dimacs
+from ddo_b200 import _native as N
+from parity_util import check_instance, compare_dd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,p,seed", [(12, 0.3, 1), (30, 0.5, 2), (64, 0.2, 3), (65, 0.5, 4), (100, 0.1, 5), (128, 0.7, 6), (129, 0.3, 7), (200, 0.5, 8)])
+def test_dd_parity_random_graphs_all_widths(n, p, seed):
+    """Every observable of restricted / relaxed DDs over a sweep of widths (1 = everything merged ... wide = exact), several best_lb."""
+    inst = gnp(n, p, seed)
+    widths = [1, 2, 3, 5, 8, 13, 50, 400]
+    cnt = check_instance(inst, widths, best_lbs=(N.I64_MIN, 2, 6))
+    assert cnt == len(widths) * 2 * 3
+
+
+def test_dd_parity_weighted_instance():
+    inst = gnp(90, 0.3, 11)
+    rng = np.random.default_rng(5)
+    inst.weights[:] = rng.integers(1, 50, size=inst.n)
+    check_instance(inst, [1, 2, 4, 9, 30, 200], best_lbs=(N.I64_MIN, 100))
+
+
+def test_dd_parity_exact_compilation_and_capacity_error():
+    inst = gnp(40, 0.6, 12)
+    check_instance(inst, [4000], comp_types=(O.EXACT,))
+    pb = Misp(gnp(60, 0.1, 13))
+    mdd = GpuMdd(pb, 8, 1)
+    with pytest.raises(N.DdoError) as e:
+        mdd.compile(CompilationType.Exact, 8, SubProblem(pb.initial_state(), 0))
+    assert e.value.code == N.ERR_CAPACITY
+
+
+def test_dd_parity_subproblem_roots_deep_in_the_search():
+    """Roots taken from a real cutset (non-zero value, depth, partial states), compiled as one batch."""
+    inst = gnp(120, 0.4, 21)
+    oracle = O.OracleMisp(inst)
+    ref = oracle.compile(O.RELAXED, 20)
+    roots = [SubProblem(ref["cutset_states"][i].copy(), int(ref["cutset_values"][i]), [], int(ref["cutset_ubs"][i]), int(ref["cutset_depths"][i]))
+             for i in range(ref["cutset_size"])]
+    assert len(roots) >= 5
+    check_instance(inst, [3, 20], roots=roots, best_lbs=(N.I64_MIN, 10), check_paths=False)
+
+
+def test_error_behaviour_matches_reference():
+    pb = Misp(gnp(30, 0.5, 3))
+    mdd = GpuMdd(pb, 16, 2)
+    root = SubProblem(pb.initial_state(), 0)
+    with pytest.raises(N.DdoError):  # max_width == 0 panics in the reference (clean.rs:827)
+        mdd.compile(CompilationType.Relaxed, 0, root)
+    with pytest.raises(N.DdoError):  # width above the arena
+        mdd.compile(CompilationType.Restricted, 17, root)
+    flag = np.ones(1, dtype=np.int32)
+    from ddo_b200 import CutoffOccurred
+    with pytest.raises(CutoffOccurred):  # Err(Reason::CutoffOccurred), clean.rs:352-354
+        mdd.compile(CompilationType.Restricted, 4, root, cutoff=flag)
+    # infeasible / fully pruned: best_lb above every bound -> Ok(Completion{best_value: None}) (clean.rs:1669-1749)
+    c = mdd.compile(CompilationType.Relaxed, 4, root, best_lb=1000)
+    assert c.best_value is None and c.expanded == 0
+    with pytest.raises(N.DdoError):
+        GpuMdd(pb, 16, 1, cutset_type=N.FRONTIER)
+
+
+FAST = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "c-fat200-5"]
+
+
+@pytest.mark.parametrize("name", FAST + ["brock200_2", "hamming8-2"])
+def test_solver_known_optima_and_wave_trace_parity(golden_dir, name):
+    """Solver::maximize on the reference's DIMACS fixtures: asserted optimum (misp/tests.rs), proven bound, and the exact same
+    branch-and-bound trajectory as the oracle's wave solver (explored / expanded / transitions / compilations)."""
+    exp = json.loads((golden_dir / "expected.json").read_text())["misp"][name]["optimum"]
+    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    pb = Misp(inst)
+    K = 16
+    s = ParNoCachingSolverLel(pb, NbUnassignedWidth(inst.n), wave_size=K)
+    comp = s.maximize()
+    assert comp.is_exact and comp.best_value == exp
+    assert s.best_lower_bound() == s.best_upper_bound() == exp
+    ref = O.OracleMisp(inst).solve("wave", k=K)
+    st = s.stats()
+    assert (s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"])) == \
+           (ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"], ref["waves"])
+    sol = sorted(d.variable for d in s.best_solution() if d.value == 1)
+    assert sol == ref["solution"]
+    adj = set(zip(inst.src.tolist(), inst.dst.tolist())) | set(zip(inst.dst.tolist(), inst.src.tolist()))
+    assert all((a, b) not in adj for a in sol for b in sol if a != b) and len(sol) == exp
+
+
+def test_solver_fixed_width_matches_oracle_trace():
+    inst = gnp(150, 0.3, 31)
+    pb = Misp(inst)
+    s = ParNoCachingSolverLel(pb, FixedWidth(10), wave_size=32)
+    comp = s.maximize()
+    ref = O.OracleMisp(inst).solve("wave", k=32, width=10)
+    assert comp.is_exact and comp.best_value == ref["best_value"]
+    assert (s.explored(), int(s.stats()["expanded"])) == (ref["explored"], ref["expanded"])
+
+
+def test_full_size_config2_root_dd_bit_exact():
+    """BASELINE config 2 at full size: G(500, 0.5), W = 10 000 -- root restricted + relaxed DD against the oracle (a few seconds of CPU)."""
+    inst = gnp(500, 0.5, 1)
+    check_instance(inst, [10000], check_paths=False)
+
+
+def test_full_size_properties_batch():
+    """Size-independent properties at full size on a batch of real sub-problems: relaxed bound >= restricted value, cutset ubs bounded
+    by the DD bound, children states are subsets of the root state, a batch equals the same DDs compiled one by one."""
+    inst = gnp(500, 0.5, 2)
+    pb = Misp(inst)
+    W = 2000
+    mdd = GpuMdd(pb, W, 8)
+    root = SubProblem(pb.initial_state(), 0)
+    mdd.compile(CompilationType.Relaxed, W, root)
+    cs = mdd.drain_cutset(0, with_paths=False)[:8]
+    rel = mdd.compile_batch(CompilationType.Relaxed, [W] * len(cs), cs)
+    cuts = [mdd.drain_cutset(i, with_paths=False) for i in range(len(cs))]
+    res = mdd.compile_batch(CompilationType.Restricted, [W] * len(cs), cs)
+    for i, sp in enumerate(cs):
+        assert res[i].best_value <= rel[i].best_value <= sp.ub
+        for ch in cuts[i]:
+            assert ch.ub <= rel[i].best_value and ch.value >= sp.value
+            assert not np.any(ch.state & ~sp.state)
+    single = [mdd.compile(CompilationType.Relaxed, W, sp) for sp in cs[:3]]
+    for i, c in enumerate(single):
+        assert (c.best_value, c.expanded, c.cutset_size) == (rel[i].best_value, rel[i].expanded, rel[i].cutset_size)
