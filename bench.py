@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- MDD nodes expanded / s on BASELINE.json's headline configuration (MISP G(500, 0.5), width 10 000).
+
+One STEP = one `Solver::maximize()` of the instance to proven optimality (solver.rs:56): the root restricted + relaxed DD (width 10 000,
+500 layers) and then every open sub-problem of the branch-and-bound, in waves of `--wave` DDs compiled in lock-step on the device.
+`value` = nodes expanded (the rough-upper-bound test of clean.rs:365 passed) / device time of the compilations (CUDA events on the
+engine's stream, instance resident in HBM); `e2e` = the same count / wall clock of ddo_solver_maximize (host fringe, H2D of every wave's
+roots, D2H of completions and cutsets inside the timed region).  N > 1: the fringe is sharded over the ranks (ddo_b200/sharded.py).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--wave B] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "MDD nodes expanded/s, MISP n=500 width=10000"
+UNIT = "nodes/s"
+N_VERT, P_EDGE, SEED, WIDTH = 500, 0.5, 1, 10000
+
+
+def load_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ddo_b200 import FixedWidth, Misp, ParNoCachingSolverLel, gnp, kernel_launches
+    from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    inst = gnp(N_VERT, P_EDGE, SEED)
+    pb = Misp(inst, device=local_rank)
+    solver = ParNoCachingSolverLel(pb, FixedWidth(WIDTH), wave_size=args.wave)
+    sampler = ClockSampler(local_rank)
+    allred = torch_allreduce_max(torch.device("cuda", local_rank)) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        """one STEP = Solver::maximize() of the instance to proven optimality (every rank works on its shard of the fringe)."""
+        s0 = solver.stats()
+        t0 = time.perf_counter()
+        if world == 1:
+            comp = solver.maximize()
+            res = {"best_lb": solver.best_lower_bound(), "best_ub": solver.best_upper_bound(), "is_exact": comp.is_exact}
+        else:
+            res = sharded_maximize(solver, rank, world, allred)
+        wall = time.perf_counter() - t0
+        s1 = solver.stats()
+        # init() resets the counters, so s1 holds this step only (bytes are cumulative engine counters)
+        return {"wall": wall, "dev_ms": s1["device_ms"], "expanded": s1["expanded"], "transitions": s1["transitions"], "waves": s1["waves"],
+                "compilations": s1["compilations"], "fringe_ms": s1["fringe_ms"], "h2d": s1["bytes_h2d"] - s0["bytes_h2d"], "d2h": s1["bytes_d2h"] - s0["bytes_d2h"],
+                "explored": solver.explored(), **res}
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = kernel_launches()
+    sampler.start()
+    t0 = time.perf_counter()
+    steps = [step() for _ in range(args.steps)]
+    barrier()
+    wall_total = time.perf_counter() - t0
+    launches = kernel_launches() - launches0
+    clocks = sampler.stop()
+    last = steps[-1]
+    # per-kernel profile pass (CUDA events around every launch; separate from the timed passes), rank 0 / single GPU only
+    kt = None
+    if world == 1:
+        solver.mdd.set_profiling(True)
+        step()
+        kt = solver.mdd.kernel_times()
+        solver.mdd.set_profiling(False)
+
+    def allred_f(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=op); return float(t.item())
+
+    dev_ms = allred_f(sum(s["dev_ms"] for s in steps), dist.ReduceOp.MAX if world > 1 else None)
+    wall_max = allred_f(wall_total, dist.ReduceOp.MAX if world > 1 else None)
+    expanded_all = allred_f(sum(s["expanded"] for s in steps), dist.ReduceOp.SUM if world > 1 else None)
+    transitions_all = allred_f(sum(s["transitions"] for s in steps), dist.ReduceOp.SUM if world > 1 else None)
+    launches_all = allred_f(launches, dist.ReduceOp.SUM if world > 1 else None)
+    explored_all = allred_f(last["explored"], dist.ReduceOp.SUM if world > 1 else None)
+    h2d_all = allred_f(last["h2d"], dist.ReduceOp.SUM if world > 1 else None)
+    d2h_all = allred_f(last["d2h"], dist.ReduceOp.SUM if world > 1 else None)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    cbar = transitions_all / max(expanded_all, 1)
+    S_bytes = pb.words * 8
+    b_node = (S_bytes + 8) + cbar * (S_bytes + 16)  # read the parent once, write each child once
+    peak, peak_src = load_peaks()
+    line = {
+        "metric": METRIC, "value": expanded_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset / i32 value",
+        "data": "synthetic", "impl": "ddo_b200",
+        "config": {"workload": f"Solver::maximize to proven optimality, MISP G({N_VERT},{P_EDGE}) seed {SEED}, FixedWidth({WIDTH}), LEL cutset, NoDupFringe/MaxUB",
+                   "wave_size": args.wave, "objective": int(last["best_lb"]), "proven_upper_bound": int(last["best_ub"]), "is_exact": bool(last["is_exact"]),
+                   "explored_subproblems": int(explored_all), "expanded_nodes_per_step": int(expanded_all / args.steps), "waves_per_step_rank0": int(last["waves"]),
+                   "l2": "no L2 flush: every step re-runs the whole search (thousands of launches over >10 GB of arenas), far beyond the 126 MB L2",
+                   "parallelism": f"fringe sharded over {world} GPU(s); one allreduce(max) of 3 x int64 per wave, no data-path collective"},
+        "wall_ms_per_step": wall_max * 1e3 / args.steps,
+        "e2e": {"value": expanded_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                "note": "wall clock of ddo_solver_maximize (host fringe, H2D of every wave's roots, D2H of completions and cutsets included)"},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "host_fringe_ms_per_step": last["fringe_ms"],
+    }
+    if kt is not None:
+        dom = max(("k_expand", "k_finish", "k_compact"), key=lambda k: kt[k]["ms"])
+        dom_gbs = last["expanded"] * b_node / (kt[dom]["ms"] * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                            "peak_source": peak_src, "bytes_per_node": b_node, "mean_out_degree": cbar,
+                            "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in kt.items()},
+                            "kernel_launches_per_step": {k: v["launches"] for k, v in kt.items()},
+                            "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak,
+                            "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(inst, args.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(inst, budget_s: float):
+    """The CPU oracle's ParallelSolver ("restated reference": per-node heap states, hash-map dedup, full comparison sort for the width
+    cut, one mutex-protected fringe) on all host cores, same instance and width, under a TimeBudget (heuristics/cutoff.rs:302-323) --
+    a BOUNDED sample of the same search; the rate is expanded nodes / elapsed."""
+    import oracle_lib as O
+
+    cores = os.cpu_count() or 1
+    r = O.OracleMisp(inst).solve("parallel", k=cores, width=WIDTH, time_budget_s=budget_s)
+    return {"value": r["expanded"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"ParallelSolver({cores} threads) maximize() with TimeBudget({budget_s:g} s): {r['explored']} sub-problems explored, "
+                      f"{r['expanded']} nodes expanded in {r['seconds']:.1f} s, lb={r['best_lb']} (finished={bool(r['is_exact'])})",
+            "expanded": int(r["expanded"]), "seconds": r["seconds"]}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  ddo is Rust and cannot be built in this image (no cargo /
+    rustc), so this arm times the oracle port of ParallelSolver (oracle/), all host threads; each step is a time-boxed maximize()."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    from ddo_b200.instances import gnp
+
+    inst = gnp(N_VERT, P_EDGE, SEED)
+    o = O.OracleMisp(inst)
+    cores = os.cpu_count() or 1
+    budget = max(10.0, min(args.cpu_seconds, 200.0 / max(args.steps, 1)))
+    small = gnp(200, 0.5, SEED)
+    os_ = O.OracleMisp(small)
+    for _ in range(args.warmup):  # untimed: a small instance, warms the allocator and the thread pool
+        os_.solve("parallel", k=cores, width=100, time_budget_s=2.0)
+    exp, sec, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last = o.solve("parallel", k=cores, width=WIDTH, time_budget_s=budget)
+        exp += last["expanded"]; sec += last["seconds"]
+    v = exp / sec
+    sample = f"ParallelSolver({cores} threads) maximize() under TimeBudget({budget:g} s) per step"
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset / i64 value", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"Solver::maximize (time-boxed), MISP G({N_VERT},{P_EDGE}) seed {SEED}, FixedWidth({WIDTH}), LEL cutset, NoDupFringe/MaxUB",
+                       "note": "oracle port of ddo's ParallelSolver (Rust toolchain absent); CPU only, rank 0 only", "lb_at_cutoff": int(last["best_lb"])},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--wave", type=int, default=512, help="sub-problems compiled in lock-step per wave and per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="TimeBudget of the CPU baseline sample")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

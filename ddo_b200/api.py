@@ -209,6 +209,28 @@ class GpuMdd:
             out.append(SubProblem(states[i].copy(), int(values[i]), p, int(ubs[i]), int(depth.value)))
         return out
 
+    def drain_cutset_batch(self, count: int, ub_caps, lb_filters, out=None):
+        """Batched drain (ddo_mdd_drain_cutset_batch) into caller-provided numpy buffers `out` = dict(states, values, ubs, dd, bits).
+        Returns (total, path_words)."""
+        caps = np.asarray(ub_caps, dtype=np.int64)
+        lbs = np.asarray(lb_filters, dtype=np.int64)
+        o = out or {}
+        total = C.c_int64(len(o["values"]) if "values" in o else (len(o["states"]) if "states" in o else 0))
+        pw = C.c_int32(0)
+        N.check(N.lib().ddo_mdd_drain_cutset_batch(self.h, count, _ptr(caps), _ptr(lbs), _ptr(o.get("states")), _ptr(o.get("values")), _ptr(o.get("ubs")),
+                                                   _ptr(o.get("dd")), _ptr(o.get("bits")), C.byref(pw), C.byref(total)), "ddo_mdd_drain_cutset_batch")
+        return int(total.value), int(pw.value)
+
+    def set_profiling(self, on: bool):
+        N.lib().ddo_mdd_set_profiling(self.h, int(on))
+
+    def kernel_times(self):
+        ms = (C.c_double * 5)()
+        ln = (C.c_uint64 * 5)()
+        N.lib().ddo_mdd_kernel_times(self.h, C.byref(ms), C.byref(ln))
+        names = ["k_expand", "k_finish", "k_compact", "k_finalize_bottomup", "k_drain"]
+        return {n: {"ms": ms[i], "launches": int(ln[i])} for i, n in enumerate(names)}
+
     def layer_trace(self, index: int = 0):
         n = self.problem.nb_variables() + 1
         v = np.zeros(n, dtype=np.int32)
@@ -334,9 +356,9 @@ class ParNoCachingSolverLel:
         return int(N.lib().ddo_solver_fringe_len(self.h))
 
     def stats(self):
-        s = (C.c_double * 6)()
+        s = (C.c_double * 8)()
         N.lib().ddo_solver_stats(self.h, C.byref(s))
-        return dict(expanded=s[0], transitions=s[1], compilations=s[2], waves=s[3], device_ms=s[4], fringe_ms=s[5])
+        return dict(expanded=s[0], transitions=s[1], compilations=s[2], waves=s[3], device_ms=s[4], fringe_ms=s[5], bytes_h2d=s[6], bytes_d2h=s[7])
 
     def close(self):
         if getattr(self, "h", None):

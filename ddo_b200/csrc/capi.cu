@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/ddo_b200.h.
 #include <algorithm>
+#include <cstring>
 #include <new>
 
 #include "solver.hpp"
@@ -85,6 +86,39 @@ int ddo_mdd_drain_cutset(ddo_mdd* d, int32_t index, int64_t ub_cap, int64_t lb_f
     return d->e.drain_cutset(index, ub_cap, lb_filter, states, values, ubs, depth_out, path_len_out, paths, count);
     GUARD_END
 }
+int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps, const int64_t* lb_filters, uint64_t* states, int64_t* values,
+                               int64_t* ubs, int32_t* dd_index, uint64_t* path_bits, int32_t* path_words, int64_t* total) {
+    GUARD_BEGIN
+    if (!d || !ub_caps || !lb_filters || !total) { set_error("null argument"); return DDO_ERR_INVALID; }
+    Engine& e = d->e;
+    int pw = 1;
+    const int n = e.drain_all(count, ub_caps, lb_filters, &pw);
+    if (n < 0) return n;
+    if (path_words) *path_words = pw;
+    if ((int64_t)n > *total) { *total = n; set_error("drain_cutset_batch: buffer too small"); return DDO_ERR_CAPACITY; }
+    const int words = e.model->words;
+    for (int r = 0; r < n; ++r) {
+        if (states) for (int j = 0; j < words; ++j) states[(size_t)r * words + j] = e.h_out_state[(size_t)r * e.S + j];
+        if (values) values[r] = e.h_out_val[r];
+        if (ubs) ubs[r] = e.h_out_ub[r];
+        if (dd_index) dd_index[r] = e.h_out_dd[r];
+    }
+    if (path_bits && n > 0) std::memcpy(path_bits, e.h_out_path, (size_t)n * pw * 8);
+    *total = n;
+    return DDO_OK;
+    GUARD_END
+}
+int ddo_mdd_set_profiling(ddo_mdd* d, int32_t on) {
+    if (!d) return DDO_ERR_INVALID;
+    d->e.profiling = on != 0; d->e.prof_used = 0;
+    for (int i = 0; i < 5; ++i) { d->e.prof_ms[i] = 0; d->e.prof_launches[i] = 0; }
+    return DDO_OK;
+}
+int ddo_mdd_kernel_times(ddo_mdd* d, double ms[5], uint64_t launches[5]) {
+    if (!d || !ms || !launches) return DDO_ERR_INVALID;
+    for (int i = 0; i < 5; ++i) { ms[i] = d->e.prof_ms[i]; launches[i] = d->e.prof_launches[i]; }
+    return DDO_OK;
+}
 int ddo_mdd_layer_trace(ddo_mdd* d, int32_t index, int32_t* vars, int32_t* widths, int32_t cap) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
@@ -168,10 +202,11 @@ int ddo_solver_best_solution(const ddo_solver* s, ddo_decision* out, int32_t* le
 }
 uint64_t ddo_solver_explored(const ddo_solver* s) { return s->s->explored; }
 uint64_t ddo_solver_fringe_len(const ddo_solver* s) { return s->s->fringe.len(); }
-int ddo_solver_stats(const ddo_solver* s, double stats[6]) {
+int ddo_solver_stats(const ddo_solver* s, double stats[8]) {
     if (!s || !stats) return DDO_ERR_INVALID;
     stats[0] = (double)s->s->expanded; stats[1] = (double)s->s->transitions; stats[2] = (double)s->s->compilations; stats[3] = (double)s->s->waves;
     stats[4] = s->s->device_ms; stats[5] = s->s->fringe_ms;
+    stats[6] = (double)s->s->eng->bytes_h2d; stats[7] = (double)s->s->eng->bytes_d2h;
     return DDO_OK;
 }
 

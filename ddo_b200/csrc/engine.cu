@@ -95,13 +95,14 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     K = batch_cap; Wcap = (int)std::max<uint64_t>(max_width_cap, 2); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
     Lmax = m->n + 1; PW = (Lmax + 63) / 64;
     CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     const size_t KW = (size_t)K * Wcap, KC = (size_t)K * C, KL = (size_t)K * Lmax;
     ev.K = K; ev.Wcap = Wcap; ev.C = C; ev.T = T; ev.Lmax = Lmax; ev.n = m->n; ev.S = S; ev.PW = PW;
     ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
-    ALLOC(ev.ctl, K); ALLOC(ev.active, 4);
+    ALLOC(ev.ctl, K); ALLOC(ev.active, 4); ALLOC(ev.tile_off_e, K + 1); ALLOC(ev.tile_off_c, K + 1); ALLOC(ev.finish_counter, 4);
     ALLOC(ev.root_state, (size_t)K * S); ALLOC(ev.root_val, K); ALLOC(ev.root_depth, K); ALLOC(ev.root_width, K);
     for (int b = 0; b < 2; ++b) { ALLOC(ev.cur_state[b], KW * S); ALLOC(ev.cur_val[b], KW); ALLOC(ev.cur_flag[b], KW); ALLOC(ev.vb[b], KW); }
     ALLOC(ev.cur_rub, KW);
@@ -118,6 +119,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
+    CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
     CUDA_TRY(cudaMallocHost(&h_root_state, (size_t)K * S * 8));
     CUDA_TRY(cudaMallocHost(&h_root_val, (size_t)K * 4));
     CUDA_TRY(cudaMallocHost(&h_root_depth, (size_t)K * 4));
@@ -131,6 +133,8 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
 }
 
 void Engine::destroy() {
+    for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+    prof_events.clear();
     for (void* p : allocations) cudaFree(p);
     allocations.clear();
     for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_ctl, (void*)h_active, (void*)h_caps,
@@ -156,11 +160,31 @@ int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* state
         h_root_val[i] = (int32_t)values[i]; h_root_depth[i] = depths[i]; h_root_width[i] = (int32_t)widths[i];
     }
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMemcpyAsync(ev.root_state, h_root_state, (size_t)count * S * 8, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ev.root_val, h_root_val, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ev.root_depth, h_root_depth, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ev.root_width, h_root_width, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)count * S * 8); CUDA_TRY(cudaMemcpyAsync(ev.root_state, h_root_state, (size_t)count * S * 8, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)count * 4); CUDA_TRY(cudaMemcpyAsync(ev.root_val, h_root_val, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)count * 4); CUDA_TRY(cudaMemcpyAsync(ev.root_depth, h_root_depth, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)count * 4); CUDA_TRY(cudaMemcpyAsync(ev.root_width, h_root_width, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
     staged = count;
+    return DDO_OK;
+}
+
+void Engine::prof_mark(int kind) {
+    if (!profiling) return;
+    if (prof_used == prof_events.size()) { cudaEvent_t e; cudaEventCreate(&e); prof_events.push_back(e); prof_kinds.push_back(0); }
+    prof_kinds[prof_used] = kind;
+    cudaEventRecord(prof_events[prof_used++], stream);
+}
+int Engine::prof_collect() {
+    if (!profiling || prof_used == 0) { prof_used = 0; return DDO_OK; }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (size_t i = 1; i < prof_used; ++i) {
+        const int kind = prof_kinds[i];
+        if (kind < 0) continue;  // interval start marker
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, prof_events[i - 1], prof_events[i]));
+        prof_ms[kind] += ms; prof_launches[kind] += 1;
+    }
+    prof_used = 0;
     return DDO_OK;
 }
 
@@ -171,16 +195,22 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
     cudaStream_t st = E->stream;
     k_init<S><<<count, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb);
     ++g_kernel_launches;
+    E->prof_mark(-1);
     const int npb = 256 / G;
-    const dim3 grid_nodes((E->Wcap + npb - 1) / npb, count), grid_cands((E->C + npb - 1) / npb, count);
+    // flat kernels run grid-stride over the per-layer work plan; the grid only has to be large enough to fill the machine
+    const long long max_tiles = (long long)count * ((E->C + npb - 1) / npb);
+    const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = 16;
     for (int t = 0; t < E->Lmax; ++t) {
         k_finish<S><<<count, 1024, 0, st>>>(ev, t);
-        k_compact<S><<<grid_cands, 256, 0, st>>>(ev, t);
-        k_expand<S><<<grid_nodes, 256, 0, st>>>(ev, t);
+        E->prof_mark(1);
+        k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, count);
+        E->prof_mark(2);
+        k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, count);
+        E->prof_mark(0);
         g_kernel_launches += 3;
         if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {
-            CUDA_TRY(cudaMemcpyAsync(E->h_active, ev.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            E->bytes_d2h += sizeof(int); CUDA_TRY(cudaMemcpyAsync(E->h_active, ev.active, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             if (*E->h_active <= 0) break;
             if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;  // Cutoff::must_stop polled between layers (clean.rs:352)
@@ -190,6 +220,7 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
     k_finalize<<<(count + 63) / 64, 64, 0, st>>>(ev, count);
     ++g_kernel_launches;
     if (comp_type == DDO_RELAXED) { k_bottomup<<<count, 1024, 0, st>>>(ev); ++g_kernel_launches; }
+    E->prof_mark(3);
     CUDA_TRY(cudaGetLastError());
     return DDO_OK;
 }
@@ -214,6 +245,7 @@ int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vola
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     last_count = count; last_comp_type = comp_type; ctl_fetched = false;
     return rc;
 }
@@ -221,7 +253,7 @@ int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vola
 int Engine::fetch_ctl(int count) {
     if (ctl_fetched && count <= last_count) return DDO_OK;
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMemcpyAsync(h_ctl, ev.ctl, (size_t)last_count * sizeof(DDCtl), cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)last_count * sizeof(DDCtl)); CUDA_TRY(cudaMemcpyAsync(h_ctl, ev.ctl, (size_t)last_count * sizeof(DDCtl), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     ctl_fetched = true;
     for (int i = 0; i < last_count; ++i)
@@ -251,8 +283,8 @@ int Engine::best_solution(int index, int exact, ddo_decision* out, int32_t* len)
     if (*len < L) { *len = L; set_error("best_solution: buffer too small"); return DDO_ERR_CAPACITY; }
     std::vector<uint64_t> bits(PW);
     std::vector<int32_t> vars(Lmax);
-    CUDA_TRY(cudaMemcpyAsync(bits.data(), (exact ? ev.best_exact_path : ev.best_path) + (size_t)index * PW, PW * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)(PW * 8); CUDA_TRY(cudaMemcpyAsync(bits.data(), (exact ? ev.best_exact_path : ev.best_path) + (size_t)index * PW, PW * 8, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int i = 0; i < L; ++i) {  // reference order: terminal -> root (clean.rs:337-341)
         const int tt = L - 1 - i;
@@ -270,8 +302,8 @@ int Engine::layer_trace(int index, int32_t* vars, int32_t* widths, int cap) {
     const DDCtl& c = h_ctl[index];
     const int L = std::max(0, c.t_term);  // expanded layers: 0..t_term-1
     std::vector<int32_t> v(Lmax), w(Lmax);
-    CUDA_TRY(cudaMemcpyAsync(v.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(w.data(), ev.nlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(v.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(w.data(), ev.nlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int i = 0; i < L && i < cap; ++i) { vars[i] = v[i]; widths[i] = w[i]; }
     return L;
@@ -295,15 +327,16 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
     for (int i = 0; i < K; ++i) { a[i] = caps[2 * i]; b[i] = caps[2 * i + 1]; }
     std::memcpy(caps, a.data(), (size_t)K * 8); std::memcpy(caps + K, b.data(), (size_t)K * 8);
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMemcpyAsync(d_ub_cap, caps, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(d_lb_filter, caps + K, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)K * 8); CUDA_TRY(cudaMemcpyAsync(d_ub_cap, caps, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    bytes_h2d += (unsigned long long)((size_t)K * 8); CUDA_TRY(cudaMemcpyAsync(d_lb_filter, caps + K, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    prof_mark(-1);
     k_cutset_count<<<last_count, 1024, 0, stream>>>(ev, d_out, d_ub_cap, d_lb_filter, count);
     k_cutset_offsets<<<1, 32, 0, stream>>>(d_out, last_count);
     g_kernel_launches += 2;
-    CUDA_TRY(cudaMemcpyAsync(h_counts, d_out.offset, (size_t)(last_count + 1) * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)(last_count + 1) * 4); CUDA_TRY(cudaMemcpyAsync(h_counts, d_out.offset, (size_t)(last_count + 1) * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     const int total = ((int32_t*)h_counts)[last_count];
-    if (total == 0) return 0;
+    if (total == 0) { prof_used = 0; return 0; }
     if (pw > 8) CUDA_TRY(cudaMemsetAsync(d_out.path, 0, (size_t)total * pw * 8, stream));
     const dim3 grid((Wcap + 255) / 256, last_count);
     switch (S) {
@@ -313,6 +346,7 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
         default: k_cutset_write<16><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
     }
     ++g_kernel_launches;
+    prof_mark(4);
     if (!h_out_state) {
         const size_t KW = (size_t)K * Wcap;
         CUDA_TRY(cudaMallocHost(&h_out_state, KW * S * 8));
@@ -321,18 +355,19 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
         CUDA_TRY(cudaMallocHost(&h_out_dd, KW * 4));
         CUDA_TRY(cudaMallocHost(&h_out_path, KW * PW * 8));
     }
-    CUDA_TRY(cudaMemcpyAsync(h_out_state, d_out.state, (size_t)total * S * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out_val, d_out.val, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out_ub, d_out.ub, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out_dd, d_out.dd, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out_path, d_out.path, (size_t)total * pw * 8, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)total * S * 8); CUDA_TRY(cudaMemcpyAsync(h_out_state, d_out.state, (size_t)total * S * 8, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_val, d_out.val, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_ub, d_out.ub, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_dd, d_out.dd, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)total * pw * 8); CUDA_TRY(cudaMemcpyAsync(h_out_path, d_out.path, (size_t)total * pw * 8, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     return total;
 }
 
 int Engine::fetch_vars(int index, std::vector<int32_t>& vars) {
     vars.resize(Lmax);
-    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return DDO_OK;
 }

@@ -59,6 +59,7 @@ struct EV {
     const uint64_t* nc;
     DDCtl* ctl;
     int* active;  // number of DDs still compiling
+    int* tile_off_e; int* tile_off_c; unsigned int* finish_counter;  // per-layer work plan of k_expand / k_compact (exclusive tile offsets, [K+1])
     // staged roots
     uint64_t* root_state; int32_t* root_val; int32_t* root_depth; int32_t* root_width;
     // current layer (ping-pong)
@@ -95,6 +96,7 @@ struct Engine {
     int device = 0;
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
     int cutset_type = DDO_LAST_EXACT_LAYER;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     EV ev{};
@@ -108,6 +110,13 @@ struct Engine {
     uint64_t* h_out_state = nullptr; int32_t* h_out_val = nullptr; int32_t* h_out_ub = nullptr; int32_t* h_out_dd = nullptr; uint64_t* h_out_path = nullptr;
     int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false;
     size_t bytes_allocated = 0;
+    unsigned long long bytes_h2d = 0, bytes_d2h = 0;  // traffic over PCIe / NVLink-C2C issued by this engine
+    // optional per-kernel timing
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events; std::vector<int> prof_kinds; size_t prof_used = 0;
+    double prof_ms[5] = {0, 0, 0, 0, 0}; uint64_t prof_launches[5] = {0, 0, 0, 0, 0};
+    void prof_mark(int kind);   // record an event; the interval since the previous mark is attributed to `kind`
+    int prof_collect();
 
     int create(const MispModel* m, int device, uint64_t max_width_cap, int batch_cap, int cutset_type);
     void destroy();

@@ -155,22 +155,29 @@ __global__ void k_init(EV ev, int count, int comp_type, long long best_lb) {
 // =================================================================================================================
 // k_expand: layer t -> candidates of layer t+1
 // =================================================================================================================
+// tile -> (DD, first item) lookup over the per-layer work plan written by the last CTA of k_finish
+__device__ __forceinline__ int plan_find(const int* off, int count, int tile) {
+    int lo = 0, hi = count;  // largest k with off[k] <= tile
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+
 template <int S>
-__global__ void __launch_bounds__(256) k_expand(EV ev, int t) {
+__global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
-    constexpr int NPB = 256 / G;      // nodes per block
-    const int k = blockIdx.y;
-    DDCtl* ctl = ev.ctl + k;
-    if (ctl->status != ST_ACTIVE) return;
-    const int n_cur = ctl->n_cur;
-    const int node = blockIdx.x * NPB + threadIdx.x / G;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ncand = 2 * n_cur;
-    if (blockIdx.x * NPB >= n_cur) return;
+    constexpr int NPB = 256 / G;      // nodes per tile
     __shared__ unsigned int s_exp, s_tr;
-    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; }
-    __syncthreads();
+    const int total = ev.tile_off_e[count];
     const int sub = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int k = plan_find(ev.tile_off_e, count, tile);
+    DDCtl* ctl = ev.ctl + k;
+    const int n_cur = ctl->n_cur;
+    const int node = (tile - ev.tile_off_e[k]) * NPB + threadIdx.x / G;
+    __syncthreads();
+    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; }
+    __syncthreads();
     if (node < n_cur) {
         const int buf = t & 1;
         const size_t nb = (size_t)k * ev.Wcap + node;
@@ -263,7 +270,9 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t) {
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_exp) { atomicAdd(&ctl->expanded, (unsigned long long)s_exp); atomicAdd(&ctl->transitions, (unsigned long long)s_tr); }
+    }  // tile loop
 }
+
 
 // =================================================================================================================
 // k_finish: one CTA per DD.  Decides everything about layer t (whose candidates were produced by k_expand(t-1)).
@@ -290,19 +299,19 @@ __device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
+__device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
     constexpr int NT = 1024;
-    __shared__ FinishSmem sm;
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DDCtl* ctl = ev.ctl + k;
     const int status = ctl->status;
     if (status == ST_DONE) return;
-    if (status == ST_TERMINAL) { if (tid == 0) ctl->status = ST_DONE; return; }
-    const int ncand = ctl->ncand;
+    if (status == ST_TERMINAL) { __syncthreads(); if (tid == 0) ctl->status = ST_DONE; return; }
+    const int ncand = t == 0 ? 1 : 2 * ctl->n_cur;  // candidates produced by k_expand(t-1): two slots per node of layer t-1
     const size_t cb = (size_t)k * ev.C;
     const size_t lb = (size_t)k * ev.Lmax;
-    if (tid == 0) ctl->lel_pending = 0;  // the snapshot requested by the previous step has been taken by k_compact
+    __syncthreads();
+    if (tid == 0) { ctl->ncand = ncand; ctl->lel_pending = 0; }  // (the LEL snapshot requested by the previous step has been taken)
 
     // ---- A. canonical representative of every distinct state = its first candidate (rule C1) -----------------
     for (int c = tid; c < ncand; c += NT) {
@@ -567,20 +576,54 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
     }
 }
 
+template <int S>
+__global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
+    __shared__ FinishSmem sm;
+    __shared__ int s_last;
+    finish_body<S>(ev, t, sm);
+    // ---- work plan of the two flat kernels that follow: the last CTA to finish scans the per-DD tile counts --------------------
+    constexpr int G = S / 2, PER_TILE = 256 / G;
+    const int tid = threadIdx.x, count = gridDim.x;
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(ev.finish_counter, 1u) == (unsigned)count - 1u); }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile DDCtl* vc = ev.ctl;
+    const int per = (count + blockDim.x - 1) / blockDim.x;
+    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    int te = 0, tc = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        te += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
+        tc += st != ST_DONE ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+    }
+    int tote, totc;
+    int oe = block_excl_scan(te, &tote, sm.scan);
+    int oc = block_excl_scan(tc, &totc, sm.scan);
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        ev.tile_off_e[k] = oe; ev.tile_off_c[k] = oc;
+        oe += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
+        oc += st != ST_DONE ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+    }
+    if (tid == 0) { ev.tile_off_e[count] = tote; ev.tile_off_c[count] = totc; *ev.finish_counter = 0; }
+}
+
 // =================================================================================================================
 // k_compact: scatter layer t into the ping-pong buffers, write logs, release hash slots, snapshot the LEL.
 // =================================================================================================================
 template <int S>
-__global__ void __launch_bounds__(256) k_compact(EV ev, int t) {
+__global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
     constexpr int G = S / 2;
     constexpr int CPB = 256 / G;
-    const int k = blockIdx.y;
+    const int total = ev.tile_off_c[count];
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int k = plan_find(ev.tile_off_c, count, tile);
     const DDCtl* ctl = ev.ctl + k;
-    if (ctl->status == ST_DONE) return;
     const int ncand = ctl->ncand;
-    if (blockIdx.x * CPB >= ncand) return;
-    const int c = blockIdx.x * CPB + threadIdx.x / G;
-    if (c >= ncand) return;
+    const int c = (tile - ev.tile_off_c[k]) * CPB + threadIdx.x / G;
+    if (c >= ncand) continue;
     const int sub = threadIdx.x % G;
     const size_t cb = (size_t)k * ev.C;
     const size_t lb = (size_t)k * ev.Lmax;
@@ -619,6 +662,7 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t) {
             if (sub == 0) { ev.lel_val[pb] = ev.cur_val[(t - 1) & 1][pb]; ev.lel_rub[pb] = ev.cur_rub[pb]; }
         }
     }
+    }  // tile loop
 }
 
 // =================================================================================================================

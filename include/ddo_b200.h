@@ -106,6 +106,16 @@ int ddo_mdd_best_solution(ddo_mdd*, int32_t index, int32_t exact, ddo_decision* 
  * same for all nodes of a LEL cutset; terminal->root order like clean.rs:329-343).  *count in: capacity, out: number emitted. */
 int ddo_mdd_drain_cutset(ddo_mdd*, int32_t index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs,
                          int32_t* depth_out, int32_t* path_len_out, ddo_decision* paths, int32_t* count);
+/* drain_cutset for DDs 0..count-1 of the last RELAXED batch at once (what the wave solver uses): DD i emits its MARKED cutset nodes with
+ * min(ub, ub_caps[i]) > lb_filters[i], concatenated in DD order.  Outputs (caller-allocated, *total in: capacity in records, out: records
+ * emitted): states (words each), values, ubs, dd_index (owning DD), path_bits (*path_words uint64 each: bit t = decision taken in layer t
+ * of the owning DD; its variables come from ddo_mdd_layer_trace).  Any output pointer may be NULL. */
+int ddo_mdd_drain_cutset_batch(ddo_mdd*, int32_t count, const int64_t* ub_caps, const int64_t* lb_filters, uint64_t* states, int64_t* values,
+                               int64_t* ubs, int32_t* dd_index, uint64_t* path_bits, int32_t* path_words, int64_t* total);
+/* per-kernel device time (CUDA events around every launch; slows the launch loop, off by default).  kernel ids: 0 k_expand, 1 k_finish,
+ * 2 k_compact, 3 k_finalize+k_bottomup, 4 drain kernels.  Times accumulate until reset (on != 0 also resets). */
+int ddo_mdd_set_profiling(ddo_mdd*, int32_t on);
+int ddo_mdd_kernel_times(ddo_mdd*, double ms[5], uint64_t launches[5]);
 /* per-layer trace of DD `index`: branching variable (Problem::next_variable) and layer width after the cut; returns #layers expanded */
 int ddo_mdd_layer_trace(ddo_mdd*, int32_t index, int32_t* vars, int32_t* widths, int32_t cap);
 
@@ -138,8 +148,9 @@ int ddo_solver_best_value(const ddo_solver*, int32_t* has, int64_t* value);     
 int ddo_solver_best_solution(const ddo_solver*, ddo_decision* out, int32_t* len);/* solver.rs:71; sorted by variable (parallel.rs:605) */
 uint64_t ddo_solver_explored(const ddo_solver*);                       /* solver.rs:96 */
 uint64_t ddo_solver_fringe_len(const ddo_solver*);
-/* stats[0..5] = expanded nodes, transitions, compilations, waves, device ms in compile, host ms in fringe */
-int ddo_solver_stats(const ddo_solver*, double stats[6]);
+/* stats[0..7] = expanded nodes, transitions, compilations, waves, device ms in compile (CUDA events), host ms in fringe,
+ * bytes copied host->device and device->host by the engine since it was created */
+int ddo_solver_stats(const ddo_solver*, double stats[8]);
 
 #ifdef __cplusplus
 }
