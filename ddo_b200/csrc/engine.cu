@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace ddo {
@@ -101,7 +102,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     CUDA_TRY(cudaEventCreate(&ev1));
     const size_t KW = (size_t)K * Wcap, KC = (size_t)K * C, KL = (size_t)K * Lmax;
     ev.K = K; ev.Wcap = Wcap; ev.C = C; ev.T = T; ev.Lmax = Lmax; ev.n = m->n; ev.S = S; ev.PW = PW;
-    ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
+    ev.HN = 64 * S; ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
     ALLOC(ev.ctl, K); ALLOC(ev.active, 4); ALLOC(ev.tile_off_e, K + 1); ALLOC(ev.tile_off_c, K + 1); ALLOC(ev.finish_counter, 4);
     ALLOC(ev.root_state, (size_t)K * S); ALLOC(ev.root_val, K); ALLOC(ev.root_depth, K); ALLOC(ev.root_width, K);
     for (int b = 0; b < 2; ++b) { ALLOC(ev.cur_state[b], KW * S); ALLOC(ev.cur_val[b], KW); ALLOC(ev.cur_flag[b], KW); ALLOC(ev.vb[b], KW); }
@@ -109,7 +110,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(ev.cand_state, KC * S); ALLOC(ev.cand_rep, KC); ALLOC(ev.cand_first, KC); ALLOC(ev.cand_agg, KC); ALLOC(ev.cand_inex, KC);
     ALLOC(ev.cand_rank, KC); ALLOC(ev.cand_slot, KC);
     ALLOC(ev.uflag, KC); ALLOC(ev.ukey, KC); ALLOC(ev.uinex, KC); ALLOC(ev.ulist, KC); ALLOC(ev.ustat, KC); ALLOC(ev.pos_of, KC);
-    ALLOC(ev.table, (size_t)K * T);
+    ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S);
     ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
     ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
@@ -117,7 +118,8 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     // drain buffers
     ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
-    ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K); ALLOC(d_small, K);
+    if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512) small_ws = v; }
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
     CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
     CUDA_TRY(cudaMallocHost(&h_root_state, (size_t)K * S * 8));
@@ -126,6 +128,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     CUDA_TRY(cudaMallocHost(&h_root_width, (size_t)K * 4));
     CUDA_TRY(cudaMallocHost(&h_ctl, (size_t)K * sizeof(DDCtl)));
     CUDA_TRY(cudaMallocHost(&h_active, 16));
+    CUDA_TRY(cudaMallocHost(&h_small, (size_t)K * sizeof(SmallOut)));
     CUDA_TRY(cudaMallocHost(&h_caps, (size_t)K * 16));
     CUDA_TRY(cudaMallocHost(&h_counts, (size_t)(K + 1) * 8));
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -138,7 +141,7 @@ void Engine::destroy() {
     for (void* p : allocations) cudaFree(p);
     allocations.clear();
     for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_ctl, (void*)h_active, (void*)h_caps,
-                    (void*)h_counts, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path})
+                    (void*)h_counts, (void*)h_small, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path})
         if (p) cudaFreeHost(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -233,6 +236,7 @@ int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vola
     if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)count * T * 8, stream));
+    CUDA_TRY(cudaMemsetAsync(ev.vhist, 0, (size_t)count * 64 * S * 4, stream));
     CUDA_TRY(cudaEventRecord(ev0, stream));
     int rc;
     switch (S) {
@@ -248,6 +252,41 @@ int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vola
     { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     last_count = count; last_comp_type = comp_type; ctl_fetched = false;
     return rc;
+}
+
+template <int S>
+static int launch_small(Engine* E, int count, int64_t best_lb) {
+    const int Ws = E->small_ws, G = S / 2;
+    const size_t smem = (size_t)Ws * G * 16 * 3 + (size_t)Ws * 4 * 3 + (size_t)4 * Ws * 4 + (size_t)64 * S * 4 + (size_t)2 * Ws;
+    if (!E->small_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_small<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        E->small_attr_set = true;
+    }
+    k_small<S><<<count, 128, smem, E->stream>>>(E->ev, count, Ws, (long long)best_lb, E->d_small);
+    ++g_kernel_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DDO_OK;
+}
+
+int Engine::compile_small(int count, int64_t best_lb, float* device_ms) {
+    if (count < 1 || count > K || count > staged) { set_error("compile_small: batch not staged"); return DDO_ERR_INVALID; }
+    if (small_ws <= 0) { set_error("small path disabled"); return DDO_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    int rc;
+    switch (S) {
+        case 2: rc = launch_small<2>(this, count, best_lb); break;
+        case 4: rc = launch_small<4>(this, count, best_lb); break;
+        case 8: rc = launch_small<8>(this, count, best_lb); break;
+        case 16: rc = launch_small<16>(this, count, best_lb); break;
+        default: set_error("unsupported state width"); return DDO_ERR_UNSUPPORTED;
+    }
+    if (rc != DDO_OK) return rc;
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_small, d_small, (size_t)count * sizeof(SmallOut), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+    return DDO_OK;
 }
 
 int Engine::fetch_ctl(int count) {

@@ -54,6 +54,7 @@ struct DDCtl {
 // Everything a kernel needs, passed by value.
 struct EV {
     int K, Wcap, C, T, Lmax, n, S, PW;  // PW = uint64 words of a packed decision-bit path
+    int HN;                              // counters per DD in vhist (= 64 * S)
     int unit_weights;
     const int32_t* weight;
     const uint64_t* nc;
@@ -69,6 +70,7 @@ struct EV {
     // unique nodes of the next layer
     uint8_t* uflag; unsigned long long* ukey; uint8_t* uinex; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
     unsigned long long* table;
+    uint32_t* vhist;  // [K][HN] occurrences of every vertex among the distinct states of the layer being built
     // logs
     uint32_t* plog;   // [K][Lmax][Wcap] best parent candidate + flags
     uint32_t* clog;   // [K][Lmax][C]    child position of every candidate (relaxed only)
@@ -82,6 +84,13 @@ struct EV {
     int32_t* cs_ub; uint8_t* cs_marked;
     // best paths (decision bits, one per layer) for best / best exact terminal node
     uint64_t* best_path; uint64_t* best_exact_path;
+};
+
+// result of the shared-memory fast path (k_small), one per DD
+struct SmallOut {
+    int32_t status;      // 0 = compiled, 1 = overflow (recompile with the general engine)
+    int32_t has_best, best_value, layers;
+    unsigned long long expanded, transitions;
 };
 
 // batched drain_cutset output (device side)
@@ -130,6 +139,9 @@ struct Engine {
     int layer_trace(int index, int32_t* vars, int32_t* widths, int cap);
     // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
     int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
+    // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
+    int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;
+    int compile_small(int count, int64_t best_lb, float* device_ms);
     int fetch_vars(int index, std::vector<int32_t>& vars);
 };
 

@@ -150,6 +150,9 @@ __global__ void k_init(EV ev, int count, int comp_type, long long best_lb) {
         ev.cand_slot[cb] = NONE32; ev.uflag[cb] = 0;
         if (k == 0) *ev.active = count;
     }
+    // vertex histogram of the (single) root state, consumed by k_finish(0)
+    for (int u = threadIdx.x; u < S * 64; u += blockDim.x)
+        ev.vhist[(size_t)k * ev.HN + u] = (uint32_t)((ev.root_state[(size_t)k * S + (u >> 6)] >> (u & 63)) & 1ull);
 }
 
 // =================================================================================================================
@@ -166,17 +169,32 @@ template <int S>
 __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
-    __shared__ unsigned int s_exp, s_tr;
+    constexpr int W32 = 2 * S;        // 32-bit words per state
+    __shared__ unsigned int s_exp, s_tr, s_any;
+    __shared__ uint4 s_claim[2 * NPB * G];     // states claimed by this tile (zero rows for everything else): 2 candidates per node
+    __shared__ unsigned int s_hist[64 * S];    // per-vertex occurrence counts of the claimed states, flushed per DD
     const int total = ev.tile_off_e[count];
     const int sub = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // contiguous tile range per block, so that the histogram of consecutive tiles of one DD is flushed once
+    const int tpb = (total + gridDim.x - 1) / gridDim.x;
+    const int tile_lo = min((int)blockIdx.x * tpb, total), tile_hi = min(tile_lo + tpb, total);
+    for (int i = threadIdx.x; i < 64 * S; i += 256) s_hist[i] = 0;
+    int hist_k = -1;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
     const int k = plan_find(ev.tile_off_e, count, tile);
+    if (k != hist_k) {
+        __syncthreads();
+        if (hist_k >= 0) for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) { atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); s_hist[i] = 0; } }
+        hist_k = k;
+    }
     DDCtl* ctl = ev.ctl + k;
     const int n_cur = ctl->n_cur;
     const int node = (tile - ev.tile_off_e[k]) * NPB + threadIdx.x / G;
     __syncthreads();
-    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; }
+    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; s_any = 0; }
+    s_claim[threadIdx.x] = make_uint4(0, 0, 0, 0); s_claim[256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (node < n_cur) {
         const int buf = t & 1;
@@ -245,8 +263,9 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
                     unsigned long long old = 0;
                     if (sub == 0) old = atomicCAS(tab + slot, EMPTY64, entry);
                     old = __shfl_sync(gm, old, (threadIdx.x & 31) & ~(G - 1));
-                    if (old == EMPTY64) {  // Entry::Vacant, clean.rs:739-765
-                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; }
+                    if (old == EMPTY64) {  // Entry::Vacant, clean.rs:739-765: a new distinct state of the next layer
+                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; s_any = 1; }
+                        s_claim[(d * NPB + threadIdx.x / G) * G + sub] = mk_u4(a0, a1);
                         break;
                     }
                     if ((uint32_t)(old >> 32) == tag) {
@@ -270,7 +289,21 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_exp) { atomicAdd(&ctl->expanded, (unsigned long long)s_exp); atomicAdd(&ctl->transitions, (unsigned long long)s_tr); }
+    // next_variable's histogram (misp/main.rs:131-135), fused: every claimed row is a distinct state of the next layer.
+    // 2*NPB rows of W32 words; warp w transposes 32 rows x 32-bit columns at a time.
+    if (s_any) {
+        constexpr int ROWS = 2 * NPB;
+        const uint32_t* rows = reinterpret_cast<const uint32_t*>(s_claim);
+        for (int job = warp; job < (ROWS / 32) * W32; job += 8) {
+            const int rblk = job / W32, col = job % W32;
+            const uint32_t x = rows[(rblk * 32 + lane) * W32 + col];
+            const unsigned cnt = __popc(warp_transpose32(x));  // lane b: #rows holding vertex 32*col + b
+            if (cnt) atomicAdd(&s_hist[32 * col + lane], cnt);
+        }
+    }
     }  // tile loop
+    __syncthreads();
+    if (hist_k >= 0) for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); }
 }
 
 
@@ -338,37 +371,16 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
         return;
     }
 
-    // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties ---
-    for (int i = tid; i < 2048; i += NT) sm.hist[i] = 0;
-    __syncthreads();
+    // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties.
+    //         The occurrence counts were accumulated by k_expand / k_init over the distinct states; consume and clear them.
+    unsigned long long best = ~0ull;
     {
-        constexpr int W32 = 2 * S;                    // 32-bit words per state
-        constexpr int SLAB = W32 < 8 ? W32 : 8;       // words handled per pass (bounds the register footprint)
-        for (int slab = 0; slab < W32; slab += SLAB) {
-            uint32_t cntw[SLAB];
-#pragma unroll
-            for (int j = 0; j < SLAB; ++j) cntw[j] = 0;
-            for (int base = warp * 32; base < U; base += 32 * (NT / 32)) {
-                const int ui = base + lane;
-                uint32_t r[SLAB];
-                if (ui < U) {
-                    const uint4* p = reinterpret_cast<const uint4*>(ev.cand_state + (cb + ev.ulist[cb + ui]) * S) + slab / 4;
-#pragma unroll
-                    for (int q = 0; q < SLAB / 4; ++q) { uint4 v = p[q]; r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < SLAB; ++j) r[j] = 0;
-                }
-#pragma unroll
-                for (int j = 0; j < SLAB; ++j) cntw[j] += __popc(warp_transpose32(r[j]));  // lane b: #states holding vertex 32(slab+j)+b
-            }
-#pragma unroll
-            for (int j = 0; j < SLAB; ++j) if (cntw[j]) atomicAdd(&sm.hist[32 * (slab + j) + lane], cntw[j]);
+        uint32_t* vh = ev.vhist + (size_t)k * ev.HN;
+        for (int i = tid; i < ev.HN; i += NT) {
+            const unsigned c = __ldcg(vh + i);
+            if (c) { vh[i] = 0; if (i < ev.n) best = min(best, ((unsigned long long)c << 32) | (unsigned)i); }
         }
     }
-    __syncthreads();
-    unsigned long long best = ~0ull;
-    for (int i = tid; i < ev.n; i += NT) { unsigned c = sm.hist[i]; if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i); }
     best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, sm.red64);
     const bool terminal = best == ~0ull;  // next_variable == None: the layer is the terminal layer (clean.rs:350,608-632)
     const int var = terminal ? -1 : (int)(uint32_t)best;
@@ -663,6 +675,154 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
         }
     }
     }  // tile loop
+}
+
+// =================================================================================================================
+// k_small: one CTA compiles one whole DD in shared memory -- the fast path for the (vast majority of) sub-problems whose layers
+// stay narrow.  Valid only while no layer needs a cut (|layer| <= min(max_width, Ws)): then restricted == relaxed == exact DD, node
+// order is irrelevant and only (best value, expanded, transitions) are observable (clean.rs:345-381 with _squash_if_needed never
+// firing).  A DD that outgrows Ws or its max_width reports `overflow` and is recompiled by the general engine.
+// =================================================================================================================
+
+template <int S>
+__global__ void __launch_bounds__(128) k_small(EV ev, int count, int Ws, long long best_lb, SmallOut* out) {
+    constexpr int G = S / 2, NT = 128, GPB = NT / G, W32 = 2 * S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = blockIdx.x;
+    if (k >= count) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid % G, grp = tid / G;
+    const unsigned gm = group_mask<G>();
+    const int TS = 4 * Ws;  // hash slots (power of two: Ws is)
+    // carve shared memory
+    uint4* cur = reinterpret_cast<uint4*>(smem_raw);                       // [Ws][G]
+    uint4* cand = cur + (size_t)Ws * G;                                    // [2 Ws][G]
+    int32_t* curv = reinterpret_cast<int32_t*>(cand + (size_t)2 * Ws * G);  // [Ws]
+    int32_t* candv = curv + Ws;                                            // [2 Ws]
+    uint32_t* table = reinterpret_cast<uint32_t*>(candv + 2 * Ws);         // [TS]  candidate index + 1, 0 = empty
+    uint32_t* hist = table + TS;                                           // [64 S]
+    uint8_t* candf = reinterpret_cast<uint8_t*>(hist + 64 * S);            // [2 Ws] 0 invalid, 1 valid, 2 claimed (distinct)
+    __shared__ unsigned long long s_red[40];
+    __shared__ int s_n, s_exp, s_tr;
+    const int width = ev.root_width[k];
+    const int cap = min(Ws, width);
+    if (tid < G) cur[tid] = reinterpret_cast<const uint4*>(ev.root_state + (size_t)k * S)[tid];
+    if (tid == 0) { curv[0] = ev.root_val[k]; s_n = 1; }
+    unsigned long long expanded = 0, transitions = 0;
+    int n = 1, layers = 0, status = 0, has_best = 0, best_value = 0;
+    __syncthreads();
+    for (;;) {
+        // ---- next_variable: occurrences of every vertex among the n states of the layer (misp/main.rs:109-143) ----------
+        for (int i = tid; i < 64 * S; i += NT) hist[i] = 0;
+        if (tid == 0) { s_exp = 0; s_tr = 0; }
+        __syncthreads();
+        {
+            const uint32_t* rows = reinterpret_cast<const uint32_t*>(cur);
+            const int rblocks = (n + 31) / 32;
+            for (int job = warp; job < rblocks * W32; job += NT / 32) {
+                const int rb = job / W32, col = job % W32, row = rb * 32 + lane;
+                const uint32_t x = row < n ? rows[(size_t)row * W32 + col] : 0u;
+                const unsigned c = __popc(warp_transpose32(x));
+                if (c) atomicAdd(&hist[32 * col + lane], c);
+            }
+        }
+        __syncthreads();
+        unsigned long long best = ~0ull;
+        for (int i = tid; i < ev.n; i += NT) { const unsigned c = hist[i]; if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i); }
+        best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, s_red);
+        if (best == ~0ull) {  // terminal layer: best node = max value_top (clean.rs:620-632)
+            int bv = INT32_MIN;
+            for (int i = tid; i < n; i += NT) bv = max(bv, curv[i]);
+            unsigned long long r = block_reduce((unsigned long long)((uint32_t)bv ^ 0x80000000u), [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, s_red);
+            has_best = 1; best_value = (int32_t)((uint32_t)r ^ 0x80000000u);
+            break;
+        }
+        const int v = (int)(uint32_t)best;
+        const int vw = v >> 6;
+        const bool owner = (vw >> 1) == sub;
+        const uint64_t bit = 1ull << (v & 63);
+        const uint4 nc4 = __ldg(reinterpret_cast<const uint4*>(ev.nc + (size_t)v * S) + sub);
+        const int wv = ev.weight[v];
+        // ---- expansion (clean.rs:360-370, misp/main.rs:77-102,191-193) ---------------------------------------------------
+        for (int i = tid; i < TS; i += NT) table[i] = 0;
+        for (int i = tid; i < 2 * n; i += NT) candf[i] = 0;
+        __syncthreads();
+        int my_exp = 0, my_tr = 0;
+        for (int base = 0; base < n; base += GPB) {
+            const int node = base + grp;
+            if (node < n) {
+                const uint4 s4 = cur[(size_t)node * G + sub];
+                uint64_t w0 = u4lo(s4), w1 = u4hi(s4);
+                const int val = curv[node];
+                int rub;
+                if (ev.unit_weights) rub = __popcll(w0) + __popcll(w1);
+                else {
+                    rub = 0;
+                    uint64_t x = w0; const int32_t* wp = ev.weight + (2 * sub) * 64;
+                    while (x) { int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; }
+                    x = w1; wp += 64;
+                    while (x) { int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; }
+                }
+                rub = group_sum<G>(rub, gm);
+                const bool has_v = group_any<G>(owner && (((vw & 1) ? w1 : w0) & bit), gm);
+                if (((long long)rub + (long long)val) > best_lb) {
+                    if (owner) { if (vw & 1) w1 &= ~bit; else w0 &= ~bit; }
+                    cand[(size_t)(2 * node + 1) * G + sub] = mk_u4(w0, w1);                      // NO
+                    if (has_v) cand[(size_t)(2 * node) * G + sub] = mk_u4(w0 & u4lo(nc4), w1 & u4hi(nc4));  // YES
+                    if (sub == 0) {
+                        candv[2 * node + 1] = val; candf[2 * node + 1] = 1;
+                        if (has_v) { candv[2 * node] = val + wv; candf[2 * node] = 1; }
+                        ++my_exp; my_tr += has_v ? 2 : 1;
+                    }
+                }
+            }
+        }
+        if (my_exp) { atomicAdd(&s_exp, my_exp); atomicAdd(&s_tr, my_tr); }
+        __syncthreads();
+        expanded += (unsigned)s_exp; transitions += (unsigned)s_tr;
+        // ---- dedup (next_l.entry(), clean.rs:738-775): value_top = max over the duplicates --------------------------------
+        for (int base = 0; base < 2 * n; base += GPB) {
+            const int c = base + grp;
+            if (c < 2 * n && candf[c]) {
+                const uint4 m4 = cand[(size_t)c * G + sub];
+                const uint64_t h = mix64(group_xor64<G>(word_hash(u4lo(m4), 2 * sub) ^ word_hash(u4hi(m4), 2 * sub + 1), gm));
+                uint32_t slot = (uint32_t)h & (uint32_t)(TS - 1);
+                for (;;) {
+                    uint32_t old = 0;
+                    if (sub == 0) old = atomicCAS(&table[slot], 0u, (uint32_t)c + 1u);
+                    old = __shfl_sync(gm, old, lane & ~(G - 1));
+                    if (old == 0u) { if (sub == 0) candf[c] = 2; break; }
+                    const uint4 o4 = cand[(size_t)(old - 1) * G + sub];
+                    if (group_all<G>(o4.x == m4.x && o4.y == m4.y && o4.z == m4.z && o4.w == m4.w, gm)) {
+                        if (sub == 0) atomicMax(&candv[old - 1], candv[c]);
+                        break;
+                    }
+                    slot = (slot + 1) & (uint32_t)(TS - 1);
+                }
+            }
+        }
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        // ---- the distinct candidates become the next layer -----------------------------------------------------------------
+        int mine = 0;
+        for (int c = tid; c < 2 * n; c += NT) mine += (candf[c] == 2);
+        int U;
+        int off = block_excl_scan(mine, &U, reinterpret_cast<int*>(s_red));
+        ++layers;
+        if (U > cap) { status = 1; break; }
+        if (U == 0) { has_best = 0; break; }  // every node was pruned: no solution in this DD
+        for (int c = tid; c < 2 * n; c += NT) if (candf[c] == 2) {
+            for (int j = 0; j < G; ++j) cur[(size_t)off * G + j] = cand[(size_t)c * G + j];
+            curv[off] = candv[c];
+            ++off;
+        }
+        n = U;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        SmallOut o;
+        o.status = status; o.has_best = has_best; o.best_value = best_value; o.layers = layers; o.expanded = expanded; o.transitions = transitions;
+        out[k] = o;
+    }
 }
 
 // =================================================================================================================

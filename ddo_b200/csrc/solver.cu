@@ -201,61 +201,109 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         std::memcpy(&states[(size_t)i * W], wv[i].state.data(), (size_t)W * 8);
         values[i] = wv[i].value; depths[i] = wv[i].depth;
     }
-    auto improve = [&](int count, const std::vector<int>& map) -> int {  // maybe_update_best, parallel.rs:446-453, in wave order
-        int last = -1;
-        for (int j = 0; j < count; ++j) {
-            const DDCtl& c = eng->h_ctl[j];
-            expanded += c.expanded; transitions += c.transitions; ++compilations;
-            if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; last = j; }
-        }
-        if (last >= 0) {
-            std::vector<ddo_decision> dd(model->n + 1);
-            int32_t len = (int32_t)dd.size();
-            int rc = eng->best_solution(last, 1, dd.data(), &len);
-            if (rc != DDO_OK) return rc;
-            const Popped& root = wv[map[last]];
-            best_sol.clear();
-            full_path(root.rec, root.bits.data(), best_sol);
-            best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
-            has_sol = true;
-        }
-        return DDO_OK;
-    };
-    // 1. restriction (parallel.rs:396-423)
+    struct Res { bool exact = false, has = false; int32_t best = 0; };
+    std::vector<Res> res(cnt);
+    const int64_t lb0 = best_lb;  // every restricted DD of the wave is compiled against this snapshot
     float ms = 0;
-    int rc = eng->stage_roots(cnt, widths.data(), states.data(), values.data(), depths.data());
-    if (rc != DDO_OK) return rc;
-    rc = eng->compile_staged(cnt, DDO_RESTRICTED, best_lb, cutoff_flag, &ms);
-    if (rc != DDO_OK) return rc;
-    device_ms += ms;
-    rc = eng->fetch_ctl(cnt);
-    if (rc != DDO_OK) return rc;
-    std::vector<int> ident(cnt);
-    for (int i = 0; i < cnt; ++i) ident[i] = i;
-    std::vector<int> open;  // sub-problems whose restricted DD is not exact
-    for (int i = 0; i < cnt; ++i) { const DDCtl& c = eng->h_ctl[i]; if (!(c.lel < 0)) open.push_back(i); }
-    rc = improve(cnt, ident);
-    if (rc != DDO_OK) return rc;
-    // 2. relaxation (parallel.rs:425-434)
-    if (!open.empty()) {
-        const int oc = (int)open.size();
+    int rc;
+    // 1a. shared-memory fast path: one CTA per sub-problem; DDs that never need a cut are exact and finish here
+    std::vector<int> ov;  // sub-problems that need the general engine (a layer outgrew the fast path)
+    if (eng->small_ws > 0) {
+        rc = eng->stage_roots(cnt, widths.data(), states.data(), values.data(), depths.data());
+        if (rc != DDO_OK) return rc;
+        rc = eng->compile_small(cnt, lb0, &ms);
+        if (rc != DDO_OK) return rc;
+        device_ms += ms;
+        for (int i = 0; i < cnt; ++i) {
+            const SmallOut& o = eng->h_small[i];
+            if (o.status != 0) { ov.push_back(i); continue; }
+            res[i].exact = true; res[i].has = o.has_best != 0; res[i].best = o.best_value;
+            expanded += o.expanded; transitions += o.transitions; ++compilations;
+        }
+    } else {
+        for (int i = 0; i < cnt; ++i) ov.push_back(i);
+    }
+    // 1b. restriction with the general engine (parallel.rs:396-423)
+    auto stage_subset = [&](const std::vector<int>& idx) -> int {
+        const int oc = (int)idx.size();
         std::vector<uint64_t> w2(oc), s2((size_t)oc * W);
-        std::vector<int64_t> v2(oc), caps(oc), lbs(oc);
+        std::vector<int64_t> v2(oc);
         std::vector<int32_t> d2(oc);
         for (int j = 0; j < oc; ++j) {
-            const int i = open[j];
+            const int i = idx[j];
             w2[j] = widths[i]; v2[j] = values[i]; d2[j] = depths[i];
             std::memcpy(&s2[(size_t)j * W], &states[(size_t)i * W], (size_t)W * 8);
         }
-        rc = eng->stage_roots(oc, w2.data(), s2.data(), v2.data(), d2.data());
+        return eng->stage_roots(oc, w2.data(), s2.data(), v2.data(), d2.data());
+    };
+    if (!ov.empty()) {
+        rc = stage_subset(ov);
+        if (rc != DDO_OK) return rc;
+        rc = eng->compile_staged((int)ov.size(), DDO_RESTRICTED, lb0, cutoff_flag, &ms);
+        if (rc != DDO_OK) return rc;
+        device_ms += ms;
+        rc = eng->fetch_ctl((int)ov.size());
+        if (rc != DDO_OK) return rc;
+        for (size_t j = 0; j < ov.size(); ++j) {
+            const DDCtl& c = eng->h_ctl[j];
+            Res& r = res[ov[j]];
+            r.exact = c.lel < 0; r.has = c.has_best_exact != 0; r.best = c.best_exact_value;
+            expanded += c.expanded; transitions += c.transitions; ++compilations;
+        }
+    }
+    // maybe_update_best in wave order (parallel.rs:446-453)
+    auto take_solution = [&](int engine_index, int wave_index) -> int {
+        std::vector<ddo_decision> dd(model->n + 1);
+        int32_t len = (int32_t)dd.size();
+        int r2 = eng->best_solution(engine_index, 1, dd.data(), &len);
+        if (r2 != DDO_OK) return r2;
+        const Popped& root = wv[wave_index];
+        best_sol.clear();
+        full_path(root.rec, root.bits.data(), best_sol);
+        best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
+        has_sol = true;
+        return DDO_OK;
+    };
+    {
+        int last = -1;
+        for (int i = 0; i < cnt; ++i) if (res[i].has && (int64_t)res[i].best > best_lb) { best_lb = res[i].best; last = i; }
+        if (last >= 0) {
+            int ej = -1;
+            for (size_t j = 0; j < ov.size(); ++j) if (ov[j] == last) ej = (int)j;
+            if (ej < 0) {  // found by the fast path, which keeps no parent log: recompile that one DD with the general engine for its path
+                rc = stage_subset(std::vector<int>{last});
+                if (rc != DDO_OK) return rc;
+                rc = eng->compile_staged(1, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
+                if (rc != DDO_OK) return rc;
+                device_ms += ms;
+                ej = 0;
+            }
+            rc = take_solution(ej, last);
+            if (rc != DDO_OK) return rc;
+        }
+    }
+    std::vector<int> open;  // sub-problems whose restricted DD is not exact
+    for (int i : ov) if (!res[i].exact) open.push_back(i);
+    // 2. relaxation (parallel.rs:425-434)
+    if (!open.empty()) {
+        const int oc = (int)open.size();
+        std::vector<int64_t> caps(oc), lbs(oc);
+        rc = stage_subset(open);
         if (rc != DDO_OK) return rc;
         rc = eng->compile_staged(oc, DDO_RELAXED, best_lb, cutoff_flag, &ms);
         if (rc != DDO_OK) return rc;
         device_ms += ms;
         rc = eng->fetch_ctl(oc);
         if (rc != DDO_OK) return rc;
-        rc = improve(oc, open);
-        if (rc != DDO_OK) return rc;
+        {
+            int last = -1;
+            for (int j = 0; j < oc; ++j) {
+                const DDCtl& c = eng->h_ctl[j];
+                expanded += c.expanded; transitions += c.transitions; ++compilations;
+                if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; last = j; }
+            }
+            if (last >= 0) { rc = take_solution(last, open[last]); if (rc != DDO_OK) return rc; }
+        }
         // enqueue_cutset (parallel.rs:456-469): ub = min(node ub, root ub), kept iff ub > best_lb
         for (int j = 0; j < oc; ++j) {
             const DDCtl& c = eng->h_ctl[j];

@@ -103,6 +103,40 @@ def test_solver_fixed_width_matches_oracle_trace():
     assert (s.explored(), int(s.stats()["expanded"])) == (ref["explored"], ref["expanded"])
 
 
+def test_full_size_config2_solver_trajectory_matches_oracle_golden(golden_dir):
+    """BASELINE config 2 solved to proven optimality: objective, bound and the whole branch-and-bound trajectory (sub-problems explored,
+    nodes expanded, transitions, compilations, waves) equal the CPU oracle's wave solver, whose 15-minute run is committed as
+    tests/golden/config2_trajectory_k512.json (made by tests/golden/make_trajectory.py)."""
+    g = json.loads((golden_dir / "config2_trajectory_k512.json").read_text())
+    inst = gnp(500, 0.5, 1)
+    pb = Misp(inst)
+    s = ParNoCachingSolverLel(pb, FixedWidth(g["width"]), wave_size=g["wave_size"])
+    comp = s.maximize()
+    st = s.stats()
+    assert comp.is_exact and comp.best_value == g["best_value"] == 13
+    assert s.best_lower_bound() == g["best_lb"] and s.best_upper_bound() == g["best_ub"]
+    got = (s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]))
+    assert got == (g["explored"], g["expanded"], g["transitions"], g["compilations"], g["waves"])
+    sol = sorted(d.variable for d in s.best_solution() if d.value == 1)
+    assert sol == g["solution"]
+
+
+def test_small_dd_fast_path_equals_general_engine(monkeypatch):
+    """The shared-memory fast path (k_small) and the general layer-by-layer engine give the same search: same optimum, bounds and counters."""
+    inst = gnp(220, 0.4, 17)
+    out = []
+    for ws in ("256", "0"):
+        monkeypatch.setenv("DDO_SMALL_WS", ws)
+        s = ParNoCachingSolverLel(Misp(inst), FixedWidth(300), wave_size=64)
+        c = s.maximize()
+        st = s.stats()
+        out.append((c.best_value, c.is_exact, s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]),
+                    sorted(d.variable for d in s.best_solution() if d.value == 1)))
+    assert out[0] == out[1]
+    ref = O.OracleMisp(inst).solve("wave", k=64, width=300)
+    assert out[0][:4] == (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"])
+
+
 def test_full_size_config2_root_dd_bit_exact():
     """BASELINE config 2 at full size: G(500, 0.5), W = 10 000 -- root restricted + relaxed DD against the oracle (a few seconds of CPU)."""
     inst = gnp(500, 0.5, 1)
