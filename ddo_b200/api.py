@@ -276,7 +276,8 @@ class ParNoCachingSolverLel:
     DDs of one device batch.  ``custom(problem, width, cutoff_seconds, wave_size)`` mirrors ``ParallelSolver::custom`` (parallel.rs:319-358)
     with ``nb_threads`` replaced by the number of DDs compiled in lock-step."""
 
-    def __init__(self, problem: Misp, width, wave_size: int = 128, max_width_cap: Optional[int] = None, mdd: Optional[GpuMdd] = None):
+    def __init__(self, problem: Misp, width, wave_size: int = 128, max_width_cap: Optional[int] = None, mdd: Optional[GpuMdd] = None,
+                 batch_cap: Optional[int] = None):
         self.problem = problem
         if isinstance(width, FixedWidth):
             kind, w = N.WIDTH_FIXED, width.w
@@ -284,7 +285,7 @@ class ParNoCachingSolverLel:
         else:
             kind, w = N.WIDTH_NB_UNASSIGNED, 0
             cap = max_width_cap or problem.nb_variables()
-        self.mdd = mdd or GpuMdd(problem, cap, wave_size)
+        self.mdd = mdd or GpuMdd(problem, cap, min(wave_size, batch_cap) if batch_cap else wave_size)
         h = C.c_void_p()
         N.check(N.lib().ddo_solver_create(problem.h, self.mdd.h, kind, w, wave_size, C.byref(h)), "ddo_solver_create")
         self.h = h

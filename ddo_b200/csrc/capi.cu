@@ -154,7 +154,8 @@ int ddo_mdd_fetch_completions(ddo_mdd* d, int32_t count, ddo_completion* out) {
 int ddo_solver_create(const ddo_model* m, ddo_mdd* d, int32_t width_kind, uint64_t width, int32_t wave_size, ddo_solver** out) {
     GUARD_BEGIN
     if (!m || !d || !out) { set_error("null argument"); return DDO_ERR_INVALID; }
-    if (wave_size < 1 || wave_size > d->e.K) { set_error("wave_size must be in [1, batch_cap]"); return DDO_ERR_INVALID; }
+    if (wave_size < 1) { set_error("wave_size must be >= 1"); return DDO_ERR_INVALID; }
+    { int rr = d->e.reserve_roots(wave_size); if (rr != DDO_OK) return rr; }  // the wave may exceed batch_cap: only DDs that need a cut go through the general engine, batch_cap at a time
     if (width_kind == DDO_WIDTH_FIXED && (width < 1 || width > (uint64_t)d->e.Wcap)) { set_error("width must be in [1, max_width_cap]"); return DDO_ERR_INVALID; }
     if (width_kind == DDO_WIDTH_NB_UNASSIGNED && m->m->n > d->e.Wcap) { set_error("NbUnassignedWidth needs max_width_cap >= nb_variables"); return DDO_ERR_INVALID; }
     *out = new ddo_solver{new Solver(m->m, &d->e, width_kind, width, wave_size)};

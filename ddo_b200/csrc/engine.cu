@@ -93,7 +93,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
     if (dev != m->device) { set_error("model and mdd must live on the same device"); return DDO_ERR_INVALID; }
     model = m; device = dev; cutset_type = cutset;
-    K = batch_cap; Wcap = (int)std::max<uint64_t>(max_width_cap, 2); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
+    K = batch_cap; Wcap = (int)((std::max<uint64_t>(max_width_cap, 2) + 1) & ~1ull); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
     Lmax = m->n + 1; PW = (Lmax + 63) / 64;
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -104,12 +104,16 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ev.K = K; ev.Wcap = Wcap; ev.C = C; ev.T = T; ev.Lmax = Lmax; ev.n = m->n; ev.S = S; ev.PW = PW;
     ev.HN = 64 * S; ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
     ALLOC(ev.ctl, K); ALLOC(ev.active, 4); ALLOC(ev.tile_off_e, K + 1); ALLOC(ev.tile_off_c, K + 1); ALLOC(ev.finish_counter, 4);
-    ALLOC(ev.root_state, (size_t)K * S); ALLOC(ev.root_val, K); ALLOC(ev.root_depth, K); ALLOC(ev.root_width, K);
     for (int b = 0; b < 2; ++b) { ALLOC(ev.cur_state[b], KW * S); ALLOC(ev.cur_val[b], KW); ALLOC(ev.cur_flag[b], KW); ALLOC(ev.vb[b], KW); }
     ALLOC(ev.cur_rub, KW);
     ALLOC(ev.cand_state, KC * S); ALLOC(ev.cand_rep, KC); ALLOC(ev.cand_first, KC); ALLOC(ev.cand_agg, KC); ALLOC(ev.cand_inex, KC);
     ALLOC(ev.cand_rank, KC); ALLOC(ev.cand_slot, KC);
-    ALLOC(ev.uflag, KC); ALLOC(ev.ukey, KC); ALLOC(ev.uinex, KC); ALLOC(ev.ulist, KC); ALLOC(ev.ustat, KC); ALLOC(ev.pos_of, KC);
+    ALLOC(ev.uflag, KC); ALLOC(ev.ulist, KC); ALLOC(ev.pos_of, KC);
+    // keys (8 B) + status (1 B) of up to C distinct candidates: shared memory when they fit next to the 19 KB of static smem
+    finish_smem = (size_t)C * 9 + 16;
+    ev.smem_keys = finish_smem <= 200 * 1024;
+    if (ev.smem_keys) { ev.gkeys = nullptr; ev.ustat = nullptr; }
+    else { finish_smem = 0; ALLOC(ev.gkeys, KC); ALLOC(ev.ustat, KC); }
     ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S);
     ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
@@ -118,17 +122,13 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     // drain buffers
     ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
-    ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K); ALLOC(d_small, K);
-    if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512) small_ws = v; }
+    ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
     CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
-    CUDA_TRY(cudaMallocHost(&h_root_state, (size_t)K * S * 8));
-    CUDA_TRY(cudaMallocHost(&h_root_val, (size_t)K * 4));
-    CUDA_TRY(cudaMallocHost(&h_root_depth, (size_t)K * 4));
-    CUDA_TRY(cudaMallocHost(&h_root_width, (size_t)K * 4));
+    { int rr = reserve_roots(K); if (rr != DDO_OK) return rr; }
     CUDA_TRY(cudaMallocHost(&h_ctl, (size_t)K * sizeof(DDCtl)));
     CUDA_TRY(cudaMallocHost(&h_active, 16));
-    CUDA_TRY(cudaMallocHost(&h_small, (size_t)K * sizeof(SmallOut)));
     CUDA_TRY(cudaMallocHost(&h_caps, (size_t)K * 16));
     CUDA_TRY(cudaMallocHost(&h_counts, (size_t)(K + 1) * 8));
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -140,6 +140,7 @@ void Engine::destroy() {
     prof_events.clear();
     for (void* p : allocations) cudaFree(p);
     allocations.clear();
+    for (void* p : {(void*)ev.root_state, (void*)ev.root_val, (void*)ev.root_depth, (void*)ev.root_width, (void*)d_small}) if (p) cudaFree(p);
     for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_ctl, (void*)h_active, (void*)h_caps,
                     (void*)h_counts, (void*)h_small, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path})
         if (p) cudaFreeHost(p);
@@ -148,8 +149,29 @@ void Engine::destroy() {
     if (stream) cudaStreamDestroy(stream);
 }
 
+// (re)allocates the root staging area for `count` roots: the general engine uses the first K, the fast path all of them
+int Engine::reserve_roots(int count) {
+    if (count <= root_cap) return DDO_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    if (stream) CUDA_TRY(cudaStreamSynchronize(stream));
+    for (void* p : {(void*)ev.root_state, (void*)ev.root_val, (void*)ev.root_depth, (void*)ev.root_width, (void*)d_small}) if (p) cudaFree(p);
+    for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_small}) if (p) cudaFreeHost(p);
+    CUDA_TRY(cudaMalloc((void**)&ev.root_state, (size_t)count * S * 8));
+    CUDA_TRY(cudaMalloc((void**)&ev.root_val, (size_t)count * 4));
+    CUDA_TRY(cudaMalloc((void**)&ev.root_depth, (size_t)count * 4));
+    CUDA_TRY(cudaMalloc((void**)&ev.root_width, (size_t)count * 4));
+    CUDA_TRY(cudaMalloc((void**)&d_small, (size_t)count * sizeof(SmallOut)));
+    CUDA_TRY(cudaMallocHost(&h_root_state, (size_t)count * S * 8));
+    CUDA_TRY(cudaMallocHost(&h_root_val, (size_t)count * 4));
+    CUDA_TRY(cudaMallocHost(&h_root_depth, (size_t)count * 4));
+    CUDA_TRY(cudaMallocHost(&h_root_width, (size_t)count * 4));
+    CUDA_TRY(cudaMallocHost(&h_small, (size_t)count * sizeof(SmallOut)));
+    root_cap = count;
+    return DDO_OK;
+}
+
 int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
-    if (count < 1 || count > K) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
+    if (count < 1 || count > root_cap) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
     const int words = model->words;
     for (int i = 0; i < count; ++i) {
         if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
@@ -196,6 +218,10 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
     constexpr int G = S / 2;
     const EV& ev = E->ev;
     cudaStream_t st = E->stream;
+    if (E->finish_smem && !E->finish_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_finish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_smem));
+        E->finish_attr_set = true;
+    }
     k_init<S><<<count, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb);
     ++g_kernel_launches;
     E->prof_mark(-1);
@@ -205,7 +231,7 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = 16;
     for (int t = 0; t < E->Lmax; ++t) {
-        k_finish<S><<<count, 1024, 0, st>>>(ev, t);
+        k_finish<S><<<count, 1024, E->finish_smem, st>>>(ev, t);
         E->prof_mark(1);
         k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, count);
         E->prof_mark(2);
@@ -269,7 +295,7 @@ static int launch_small(Engine* E, int count, int64_t best_lb) {
 }
 
 int Engine::compile_small(int count, int64_t best_lb, float* device_ms) {
-    if (count < 1 || count > K || count > staged) { set_error("compile_small: batch not staged"); return DDO_ERR_INVALID; }
+    if (count < 1 || count > root_cap || count > staged) { set_error("compile_small: batch not staged"); return DDO_ERR_INVALID; }
     if (small_ws <= 0) { set_error("small path disabled"); return DDO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaEventRecord(ev0, stream));

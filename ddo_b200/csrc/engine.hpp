@@ -68,7 +68,8 @@ struct EV {
     // candidates of the next layer
     uint64_t* cand_state; uint32_t* cand_rep; uint32_t* cand_first; unsigned long long* cand_agg; uint8_t* cand_inex; uint32_t* cand_rank; uint32_t* cand_slot;
     // unique nodes of the next layer
-    uint8_t* uflag; unsigned long long* ukey; uint8_t* uinex; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
+    uint8_t* uflag; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
+    unsigned long long* gkeys; int smem_keys;  // cut keys of the distinct candidates: in k_finish's shared memory when 2*Wcap of them fit, else here
     unsigned long long* table;
     uint32_t* vhist;  // [K][HN] occurrences of every vertex among the distinct states of the layer being built
     // logs
@@ -106,6 +107,7 @@ struct Engine {
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
     int cutset_type = DDO_LAST_EXACT_LAYER;
     int num_sms = 148;
+    size_t finish_smem = 0; bool finish_attr_set = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     EV ev{};
@@ -129,6 +131,8 @@ struct Engine {
 
     int create(const MispModel* m, int device, uint64_t max_width_cap, int batch_cap, int cutset_type);
     void destroy();
+    int root_cap = 0;  // roots that can be staged at once (>= K): the wave size of the solver's fast path
+    int reserve_roots(int count);
     int stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths);
     int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
     int fetch_ctl(int count);

@@ -321,8 +321,8 @@ struct FinishSmem {
 // compare two unique candidates by the cut order (clean.rs:803-808 + misp/main.rs:205-208): returns true if a is BETTER than b
 template <int S>
 __device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
-    const unsigned long long ka = (ev.ukey[cb + a] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + a];
-    const unsigned long long kb = (ev.ukey[cb + b] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + b];
+    const unsigned long long ka = (ev.cand_agg[cb + a] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + a];
+    const unsigned long long kb = (ev.cand_agg[cb + b] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + b];
     if (ka != kb) return ka > kb;
     for (int j = 0; j < S; ++j) {
         const uint64_t xa = lex_word(ev.cand_state[(cb + a) * S + j]), xb = lex_word(ev.cand_state[(cb + b) * S + j]);
@@ -331,8 +331,9 @@ __device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
     return false;
 }
 
+// Keys / status of the distinct candidates live in shared memory when 2*Wcap of them fit (ev.smem_keys), else in global scratch.
 template <int S>
-__device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
+__device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long long* keys, uint8_t* stat) {
     constexpr int NT = 1024;
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -346,29 +347,58 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
     __syncthreads();
     if (tid == 0) { ctl->ncand = ncand; ctl->lel_pending = 0; }  // (the LEL snapshot requested by the previous step has been taken)
 
+    // every thread owns a contiguous chunk of candidates, a multiple of 4 so that the metadata is read with 128-bit loads
+    const int per = (((ncand + NT - 1) / NT) + 3) & ~3;
+    const int lo = min(tid * per, ncand), hi = min(lo + per, ncand);
+
     // ---- A. canonical representative of every distinct state = its first candidate (rule C1) -----------------
-    for (int c = tid; c < ncand; c += NT) {
-        if (ev.cand_rep[cb + c] == (uint32_t)c) {
-            const uint32_t f = ev.cand_first[cb + c];
-            ev.uflag[cb + f] = 1;
-            ev.ukey[cb + f] = ev.cand_agg[cb + c];
-            ev.uinex[cb + f] = ev.cand_inex[cb + c];
+    // claimers have cand_rep[c] == c; cand_first[c] is then the smallest candidate index with that state.  98 % of the time
+    // first == c and nothing moves (ukey / uinex alias cand_agg / cand_inex).
+    for (int c0 = lo; c0 < hi; c0 += 4) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(ev.cand_rep + cb + c0);
+        const uint4 f4 = *reinterpret_cast<const uint4*>(ev.cand_first + cb + c0);
+        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (uint32_t)(c0 + j);
+            if ((int)c < hi && rr[j] == c) {
+                const uint32_t f = ff[j];
+                ev.uflag[cb + f] = 1;
+                if (f != c) { ev.cand_agg[cb + f] = ev.cand_agg[cb + c]; ev.cand_inex[cb + f] = ev.cand_inex[cb + c]; }
+            }
         }
     }
     __syncthreads();
-    // ---- A'. ordered list of the unique candidates -----------------------------------------------------------
-    const int per = (ncand + NT - 1) / NT;
-    const int lo = min(tid * per, ncand), hi = min(lo + per, ncand);
+    // ---- A'. ordered list of the distinct candidates + their 64-bit cut keys ------------------------------------
     int cnt = 0;
-    for (int c = lo; c < hi; ++c) cnt += (ev.uflag[cb + c] != 0);
+    for (int c0 = lo; c0 < hi; c0 += 4) {
+        const uint32_t fl = *reinterpret_cast<const uint32_t*>(ev.uflag + cb + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cnt += (c0 + j < hi) && ((fl >> (8 * j)) & 0xff);
+    }
     int U;
-    int off = block_excl_scan(cnt, &U, sm.scan);
-    for (int c = lo; c < hi; ++c) if (ev.uflag[cb + c]) ev.ulist[cb + off++] = (uint32_t)c;
-    __syncthreads();
-
+    const int off0 = block_excl_scan(cnt, &U, sm.scan);
     if (U == 0) {  // every node was pruned: empty layer (clean.rs:667-669) -> no best node
         if (tid == 0) { ctl->status = ST_DONE; ctl->t_term = t; ctl->has_best = 0; ctl->has_best_exact = 0; ev.nlog[lb + t] = 0; atomicSub(ev.active, 1); }
         return;
+    }
+    const bool fits = U <= ev.Wcap * 2;  // always true; keys/stat are sized for 2*Wcap entries
+    (void)fits;
+    {
+        int off = off0;
+        for (int c0 = lo; c0 < hi; c0 += 4) {
+            const uint32_t fl = *reinterpret_cast<const uint32_t*>(ev.uflag + cb + c0);
+            if (!fl) continue;
+            unsigned long long ag[4]; uint32_t rk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((c0 + j < hi) && ((fl >> (8 * j)) & 0xff)) { ag[j] = ev.cand_agg[cb + c0 + j]; rk[j] = ev.cand_rank[cb + c0 + j]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((c0 + j < hi) && ((fl >> (8 * j)) & 0xff)) {
+                ev.ulist[cb + off] = (uint32_t)(c0 + j);
+                keys[off] = (ag[j] & 0xFFFFFFFF00000000ull) | rk[j];  // (value_top, popcount, 20 lexicographic bits)
+                ++off;
+            }
+        }
     }
 
     // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties.
@@ -396,22 +426,21 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
         if (tid == 0) { ctl->status = ST_DONE; ctl->overflow = 1; ctl->t_term = t; atomicSub(ev.active, 1); }
         return;
     }
-    // ustat[ui]: 0 active (undecided), 1 keep, 2 drop
-    for (int ui = tid; ui < U; ui += NT) ev.ustat[cb + ui] = cut ? 0 : 1;
+    // stat[ui]: 0 undecided, 1 keep, 2 drop
+    for (int ui = tid; ui < U; ui += NT) stat[ui] = cut ? 0 : 1;
     __syncthreads();
     if (cut) {
         int nactive = U;
         bool done = false;
-        if (need == 0) { for (int ui = tid; ui < U; ui += NT) ev.ustat[cb + ui] = 2; done = true; }
+        if (need == 0) { for (int ui = tid; ui < U; ui += NT) stat[ui] = 2; done = true; }
         for (int chunk = 0; chunk <= S && !done; ++chunk) {
-            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j: lexicographic word j-1
+            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j: lexicographic word j-1 of the state
             auto key_of = [&](int ui) -> unsigned long long {
-                const uint32_t c = ev.ulist[cb + ui];
-                if (chunk == 0) return (ev.ukey[cb + c] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + c];
-                return lex_word(ev.cand_state[(cb + c) * S + (chunk - 1)]);
+                if (chunk == 0) return keys[ui];
+                return lex_word(ev.cand_state[(cb + ev.ulist[cb + ui]) * S + (chunk - 1)]);
             };
             unsigned long long kor = 0, kand = ~0ull;
-            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) { unsigned long long x = key_of(ui); kor |= x; kand &= x; }
+            for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) { unsigned long long x = key_of(ui); kor |= x; kand &= x; }
             kor = block_reduce(kor, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
             kand = block_reduce(kand, [](unsigned long long a, unsigned long long b) { return a & b; }, ~0ull, sm.red64);
             const unsigned long long diff = kor ^ kand;
@@ -419,16 +448,16 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
                 if (((diff >> (8 * byte)) & 0xff) == 0) continue;  // every undecided key has the same digit here
                 for (int i = tid; i < 256; i += NT) sm.hist[i] = 0;
                 __syncthreads();
-                for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) atomicAdd(&sm.hist[(key_of(ui) >> (8 * byte)) & 0xff], 1u);
+                for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) atomicAdd(&sm.hist[(key_of(ui) >> (8 * byte)) & 0xff], 1u);
                 __syncthreads();
                 if (warp == 0) {  // bucket b with  #(digit > b) < need <= #(digit >= b)
-                    int c8[8]; int s = 0;
+                    int c8[8]; int s8 = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { c8[q] = (int)sm.hist[255 - (lane * 8 + q)]; s += c8[q]; }  // lane 0 owns the 8 largest digits
-                    int inc = s;
+                    for (int q = 0; q < 8; ++q) { c8[q] = (int)sm.hist[255 - (lane * 8 + q)]; s8 += c8[q]; }  // lane 0 owns the 8 largest digits
+                    int inc = s8;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
-                    int before = inc - s;  // count of digits strictly greater than this lane's 8 buckets
+                    int before = inc - s8;  // count of digits strictly greater than this lane's 8 buckets
                     if (before < need && need <= inc) {
                         int acc = before;
 #pragma unroll
@@ -442,9 +471,9 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
                 const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
                 need -= above; nactive = inb;
                 const bool all_keep = (need == nactive);
-                for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 0) {
+                for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) {
                     const int d = (int)((key_of(ui) >> (8 * byte)) & 0xff);
-                    if (d > b) ev.ustat[cb + ui] = 1; else if (d < b) ev.ustat[cb + ui] = 2; else if (all_keep) ev.ustat[cb + ui] = 1;
+                    if (d > b) stat[ui] = 1; else if (d < b) stat[ui] = 2; else if (all_keep) stat[ui] = 1;
                 }
                 __syncthreads();
                 if (all_keep) done = true;
@@ -453,16 +482,14 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
         __syncthreads();
     }
 
-    // ---- D. stable positions of the survivors (rule C3) ---------------------------------------------------------
-    const int uper = (U + NT - 1) / NT;
-    const int ulo = min(tid * uper, U), uhi = min(ulo + uper, U);
+    // ---- D. stable positions of the survivors (rule C3): every thread places the distinct candidates of its own chunk ----
     int kc = 0;
-    for (int ui = ulo; ui < uhi; ++ui) kc += (ev.ustat[cb + ui] == 1);
+    for (int i = 0; i < cnt; ++i) kc += (stat[off0 + i] == 1);
     int nkeep;
     int kp = block_excl_scan(kc, &nkeep, sm.scan);
-    for (int ui = ulo; ui < uhi; ++ui) {
-        const uint32_t c = ev.ulist[cb + ui];
-        if (ev.ustat[cb + ui] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
+    for (int i = 0; i < cnt; ++i) {
+        const uint32_t c = ev.ulist[cb + off0 + i];
+        if (stat[off0 + i] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
     }
     int n_next = nkeep;
     int s_pos = -1, r_pos = -1;
@@ -476,11 +503,12 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
 #pragma unroll
         for (int j = 0; j < S; ++j) acc[j] = 0;
         unsigned long long mkey = 0;
-        for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+        for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 2) {
             const uint32_t c = ev.ulist[cb + ui];
+            const uint4* sp = reinterpret_cast<const uint4*>(ev.cand_state + (cb + c) * S);
 #pragma unroll
-            for (int j = 0; j < S; ++j) acc[j] |= ev.cand_state[(cb + c) * S + j];
-            mkey = max(mkey, ev.ukey[cb + c]);
+            for (int j = 0; j < S / 2; ++j) { const uint4 v4 = sp[j]; acc[2 * j] |= u4lo(v4); acc[2 * j + 1] |= u4hi(v4); }
+            mkey = max(mkey, ev.cand_agg[cb + c]);
         }
 #pragma unroll
         for (int j = 0; j < S; ++j) {
@@ -517,7 +545,7 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
         if (recycled >= 0) {
             // clean.rs:868-871: the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node
             uint32_t bestc = NONE32;
-            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+            for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 2) {
                 const uint32_t c = ev.ulist[cb + ui];
                 if (bestc == NONE32 || cand_better<S>(ev, cb, c, bestc)) bestc = c;
             }
@@ -535,19 +563,19 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
             s_pos = nkeep; r_pos = mpos; n_next = nkeep + 1;
             if (tid == 0) {
                 // the recycled node receives every relaxed edge: RELAXED flag, value_top = max (`>=`: the appended edges win ties)
-                const unsigned long long rk = ev.ukey[cb + recycled];
-                if (key_value(mkey) >= key_value(rk)) ev.ukey[cb + recycled] = mkey;
-                ev.uinex[cb + recycled] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
+                const unsigned long long rk = ev.cand_agg[cb + recycled];
+                if (key_value(mkey) >= key_value(rk)) ev.cand_agg[cb + recycled] = mkey;
+                ev.cand_inex[cb + recycled] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
             }
             __syncthreads();
-            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
+            for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 2) {
                 const uint32_t c = ev.ulist[cb + ui];
-                if (c == saved) { ev.pos_of[cb + c] = (uint32_t)s_pos; ev.ustat[cb + ui] = 1; ev.uflag[cb + c] = 2; }
+                if (c == saved) { ev.pos_of[cb + c] = (uint32_t)s_pos; stat[ui] = 1; ev.uflag[cb + c] = 2; }
                 else ev.pos_of[cb + c] = (uint32_t)r_pos;
             }
         } else {
             n_next = nkeep + 1;
-            for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) ev.pos_of[cb + ev.ulist[cb + ui]] = (uint32_t)mpos;
+            for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 2) ev.pos_of[cb + ev.ulist[cb + ui]] = (uint32_t)mpos;
             // new merged node (clean.rs:832-849) written straight into the next layer
             const int nbuf = t & 1;
             const size_t nb = (size_t)k * ev.Wcap + mpos;
@@ -565,9 +593,9 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm) {
         unsigned long long b_all = 0, b_ex = 0;  // (biased value, pos + 1)
         for (int ui = tid; ui < U; ui += NT) {
             const uint32_t c = ev.ulist[cb + ui];
-            const unsigned long long kk = (ev.ukey[cb + c] & 0xFFFFFFFF00000000ull) | (unsigned)(ev.pos_of[cb + c] + 1);
+            const unsigned long long kk = (ev.cand_agg[cb + c] & 0xFFFFFFFF00000000ull) | (unsigned)(ev.pos_of[cb + c] + 1);
             b_all = max(b_all, kk);
-            if (!(ev.uinex[cb + c] & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk);
+            if (!(ev.cand_inex[cb + c] & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk);
         }
         b_all = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
         b_ex = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
@@ -592,7 +620,13 @@ template <int S>
 __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
     __shared__ FinishSmem sm;
     __shared__ int s_last;
-    finish_body<S>(ev, t, sm);
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    {
+        unsigned long long* keys; uint8_t* stat;
+        if (ev.smem_keys) { keys = reinterpret_cast<unsigned long long*>(dyn_smem); stat = dyn_smem + (size_t)ev.C * 8; }
+        else { keys = ev.gkeys + (size_t)blockIdx.x * ev.C; stat = ev.ustat + (size_t)blockIdx.x * ev.C; }
+        finish_body<S>(ev, t, sm, keys, stat);
+    }
     // ---- work plan of the two flat kernels that follow: the last CTA to finish scans the per-DD tile counts --------------------
     constexpr int G = S / 2, PER_TILE = 256 / G;
     const int tid = threadIdx.x, count = gridDim.x;
@@ -656,8 +690,8 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
             const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(ev.cand_state + (cb + c) * S) + sub);
             st_stream_u4(reinterpret_cast<uint4*>(ev.cur_state[nbuf] + nb * S) + sub, v);
             if (sub == 0) {
-                const unsigned long long key = ev.ukey[cb + c];
-                const uint32_t fl = ev.uinex[cb + c];
+                const unsigned long long key = ev.cand_agg[cb + c];
+                const uint32_t fl = ev.cand_inex[cb + c];
                 ev.cur_val[nbuf][nb] = key_value(key);
                 ev.cur_flag[nbuf][nb] = (uint8_t)fl;
                 ev.plog[(lb + t) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);

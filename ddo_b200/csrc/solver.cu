@@ -170,46 +170,72 @@ void Solver::full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decisi
 
 int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const int W = model->words, PWN = (model->n + 63) / 64;
-    struct Popped { std::vector<uint64_t> state, bits; int32_t value, ub, depth, rec; };
-    std::vector<Popped> wv;
+    // ---- get_workload (parallel.rs:500-559): pop up to wave_size open sub-problems ---------------------------------------------
     double t0 = now_ms();
     int64_t top_ub = INT64_MIN;
-    while ((int)wv.size() < wave_size && !fringe.empty()) {  // get_workload, parallel.rs:500-559
+    w_states.clear(); w_bits.clear(); w_items.clear();
+    while ((int)w_items.size() < wave_size && !fringe.empty()) {
         const int id = fringe.pop();
         const NoDupFringe::Item it = fringe.item(id);
         const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
         if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
-        if (wv.empty()) top_ub = ub;
-        Popped p;
-        p.state.assign(fringe.state(id), fringe.state(id) + W);
-        p.bits.assign(fringe.bits(id), fringe.bits(id) + PWN);
-        p.value = it.value; p.ub = it.ub; p.depth = it.depth; p.rec = it.rec;
-        wv.push_back(std::move(p));
+        if (w_items.empty()) top_ub = ub;
+        w_states.insert(w_states.end(), fringe.state(id), fringe.state(id) + W);
+        w_bits.insert(w_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
+        w_items.push_back(it);
         ++explored;
     }
     fringe_ms += now_ms() - t0;
     out3[1] = top_ub;
-    if (wv.empty()) { out3[0] = best_lb; out3[2] = 0; return DDO_OK; }
+    const int cnt = (int)w_items.size();
+    if (cnt == 0) { out3[0] = best_lb; out3[2] = 0; return DDO_OK; }
     if (top_ub != INT64_MIN) best_ub = top_ub;
     ++waves;
-    const int cnt = (int)wv.size();
-    std::vector<uint64_t> widths(cnt), states((size_t)cnt * W);
+    std::vector<uint64_t> widths(cnt);
     std::vector<int64_t> values(cnt);
     std::vector<int32_t> depths(cnt);
     for (int i = 0; i < cnt; ++i) {
-        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(model->n - wv[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
-        std::memcpy(&states[(size_t)i * W], wv[i].state.data(), (size_t)W * 8);
-        values[i] = wv[i].value; depths[i] = wv[i].depth;
+        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(model->n - w_items[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
+        values[i] = w_items[i].value; depths[i] = w_items[i].depth;
     }
     struct Res { bool exact = false, has = false; int32_t best = 0; };
     std::vector<Res> res(cnt);
     const int64_t lb0 = best_lb;  // every restricted DD of the wave is compiled against this snapshot
     float ms = 0;
     int rc;
-    // 1a. shared-memory fast path: one CTA per sub-problem; DDs that never need a cut are exact and finish here
+    const int cap = eng->K;  // DDs the general engine compiles in lock-step
+    std::vector<uint64_t> w2, s2; std::vector<int64_t> v2; std::vector<int32_t> d2;
+    auto stage_subset = [&](const int* idx, int oc) -> int {
+        w2.resize(oc); s2.resize((size_t)oc * W); v2.resize(oc); d2.resize(oc);
+        for (int j = 0; j < oc; ++j) {
+            const int i = idx[j];
+            w2[j] = widths[i]; v2[j] = values[i]; d2[j] = depths[i];
+            std::memcpy(&s2[(size_t)j * W], &w_states[(size_t)i * W], (size_t)W * 8);
+        }
+        return eng->stage_roots(oc, w2.data(), s2.data(), v2.data(), d2.data());
+    };
+    // the DD that improves the incumbent is recompiled alone by the general engine to read its best path (a handful of times per solve)
+    auto take_solution = [&](int wave_index, int comp_type, int64_t lb) -> int {
+        int r2 = stage_subset(&wave_index, 1);
+        if (r2 != DDO_OK) return r2;
+        r2 = eng->compile_staged(1, comp_type, lb, cutoff_flag, &ms);
+        if (r2 != DDO_OK) return r2;
+        device_ms += ms;
+        std::vector<ddo_decision> dd(model->n + 1);
+        int32_t len = (int32_t)dd.size();
+        r2 = eng->best_solution(0, 1, dd.data(), &len);
+        if (r2 != DDO_OK) return r2;
+        best_sol.clear();
+        full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], best_sol);
+        best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
+        has_sol = true;
+        return DDO_OK;
+    };
+
+    // ---- 1a. shared-memory fast path: one CTA per sub-problem; DDs that never need a cut are exact and finish here ----------------
     std::vector<int> ov;  // sub-problems that need the general engine (a layer outgrew the fast path)
     if (eng->small_ws > 0) {
-        rc = eng->stage_roots(cnt, widths.data(), states.data(), values.data(), depths.data());
+        rc = eng->stage_roots(cnt, widths.data(), w_states.data(), values.data(), depths.data());
         if (rc != DDO_OK) return rc;
         rc = eng->compile_small(cnt, lb0, &ms);
         if (rc != DDO_OK) return rc;
@@ -223,116 +249,95 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     } else {
         for (int i = 0; i < cnt; ++i) ov.push_back(i);
     }
-    // 1b. restriction with the general engine (parallel.rs:396-423)
-    auto stage_subset = [&](const std::vector<int>& idx) -> int {
-        const int oc = (int)idx.size();
-        std::vector<uint64_t> w2(oc), s2((size_t)oc * W);
-        std::vector<int64_t> v2(oc);
-        std::vector<int32_t> d2(oc);
-        for (int j = 0; j < oc; ++j) {
-            const int i = idx[j];
-            w2[j] = widths[i]; v2[j] = values[i]; d2[j] = depths[i];
-            std::memcpy(&s2[(size_t)j * W], &states[(size_t)i * W], (size_t)W * 8);
-        }
-        return eng->stage_roots(oc, w2.data(), s2.data(), v2.data(), d2.data());
-    };
-    if (!ov.empty()) {
-        rc = stage_subset(ov);
+    // ---- 1b. restriction with the general engine (parallel.rs:396-423), `cap` DDs at a time -----------------------------------------
+    for (size_t s0 = 0; s0 < ov.size(); s0 += (size_t)cap) {
+        const int oc = (int)std::min<size_t>((size_t)cap, ov.size() - s0);
+        rc = stage_subset(&ov[s0], oc);
         if (rc != DDO_OK) return rc;
-        rc = eng->compile_staged((int)ov.size(), DDO_RESTRICTED, lb0, cutoff_flag, &ms);
-        if (rc != DDO_OK) return rc;
-        device_ms += ms;
-        rc = eng->fetch_ctl((int)ov.size());
-        if (rc != DDO_OK) return rc;
-        for (size_t j = 0; j < ov.size(); ++j) {
-            const DDCtl& c = eng->h_ctl[j];
-            Res& r = res[ov[j]];
-            r.exact = c.lel < 0; r.has = c.has_best_exact != 0; r.best = c.best_exact_value;
-            expanded += c.expanded; transitions += c.transitions; ++compilations;
-        }
-    }
-    // maybe_update_best in wave order (parallel.rs:446-453)
-    auto take_solution = [&](int engine_index, int wave_index) -> int {
-        std::vector<ddo_decision> dd(model->n + 1);
-        int32_t len = (int32_t)dd.size();
-        int r2 = eng->best_solution(engine_index, 1, dd.data(), &len);
-        if (r2 != DDO_OK) return r2;
-        const Popped& root = wv[wave_index];
-        best_sol.clear();
-        full_path(root.rec, root.bits.data(), best_sol);
-        best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
-        has_sol = true;
-        return DDO_OK;
-    };
-    {
-        int last = -1;
-        for (int i = 0; i < cnt; ++i) if (res[i].has && (int64_t)res[i].best > best_lb) { best_lb = res[i].best; last = i; }
-        if (last >= 0) {
-            int ej = -1;
-            for (size_t j = 0; j < ov.size(); ++j) if (ov[j] == last) ej = (int)j;
-            if (ej < 0) {  // found by the fast path, which keeps no parent log: recompile that one DD with the general engine for its path
-                rc = stage_subset(std::vector<int>{last});
-                if (rc != DDO_OK) return rc;
-                rc = eng->compile_staged(1, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
-                if (rc != DDO_OK) return rc;
-                device_ms += ms;
-                ej = 0;
-            }
-            rc = take_solution(ej, last);
-            if (rc != DDO_OK) return rc;
-        }
-    }
-    std::vector<int> open;  // sub-problems whose restricted DD is not exact
-    for (int i : ov) if (!res[i].exact) open.push_back(i);
-    // 2. relaxation (parallel.rs:425-434)
-    if (!open.empty()) {
-        const int oc = (int)open.size();
-        std::vector<int64_t> caps(oc), lbs(oc);
-        rc = stage_subset(open);
-        if (rc != DDO_OK) return rc;
-        rc = eng->compile_staged(oc, DDO_RELAXED, best_lb, cutoff_flag, &ms);
+        rc = eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
         if (rc != DDO_OK) return rc;
         device_ms += ms;
         rc = eng->fetch_ctl(oc);
         if (rc != DDO_OK) return rc;
-        {
-            int last = -1;
+        for (int j = 0; j < oc; ++j) {
+            const DDCtl& c = eng->h_ctl[j];
+            Res& r = res[ov[s0 + j]];
+            r.exact = c.lel < 0; r.has = c.has_best_exact != 0; r.best = c.best_exact_value;
+            expanded += c.expanded; transitions += c.transitions; ++compilations;
+        }
+    }
+    {   // maybe_update_best in wave order (parallel.rs:446-453): the first DD reaching the new maximum keeps its solution
+        int last = -1;
+        for (int i = 0; i < cnt; ++i) if (res[i].has && (int64_t)res[i].best > best_lb) { best_lb = res[i].best; last = i; }
+        if (last >= 0) { rc = take_solution(last, DDO_RESTRICTED, lb0); if (rc != DDO_OK) return rc; }
+    }
+    std::vector<int> open;  // sub-problems whose restricted DD is not exact
+    for (int i : ov) if (!res[i].exact) open.push_back(i);
+
+    // ---- 2. relaxation (parallel.rs:425-434) + enqueue_cutset (parallel.rs:456-469) ----------------------------------------------------
+    if (!open.empty()) {
+        const int64_t lb1 = best_lb;  // every relaxed DD of the wave is compiled against this snapshot
+        struct Pending { int wave_index, lel, first, count, pw; };
+        std::vector<Pending> pend;
+        p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+        int improver = -1;
+        std::vector<int64_t> caps, lbs;
+        std::vector<int32_t> vars;
+        for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
+            const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
+            rc = stage_subset(&open[s0], oc);
+            if (rc != DDO_OK) return rc;
+            rc = eng->compile_staged(oc, DDO_RELAXED, lb1, cutoff_flag, &ms);
+            if (rc != DDO_OK) return rc;
+            device_ms += ms;
+            rc = eng->fetch_ctl(oc);
+            if (rc != DDO_OK) return rc;
+            caps.assign(oc, 0); lbs.assign(oc, 0);
             for (int j = 0; j < oc; ++j) {
                 const DDCtl& c = eng->h_ctl[j];
                 expanded += c.expanded; transitions += c.transitions; ++compilations;
-                if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; last = j; }
+                if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; improver = open[s0 + j]; }
+                const bool exact = (c.lel < 0) || c.ebpo;
+                const int32_t rub = w_items[open[s0 + j]].ub;
+                caps[j] = rub == INT32_MAX ? INT64_MAX : rub;
+                lbs[j] = exact ? INT64_MAX : best_lb;  // a lower bound on the final filter; re-applied below once the wave is complete
             }
-            if (last >= 0) { rc = take_solution(last, open[last]); if (rc != DDO_OK) return rc; }
+            int pw = 1;
+            const int total = eng->drain_all(oc, caps.data(), lbs.data(), &pw);
+            if (total < 0) return total;
+            int cur_dd = -1;
+            for (int r = 0; r < total; ++r) {
+                const int j = eng->h_out_dd[r];
+                if (j != cur_dd) {
+                    cur_dd = j;
+                    const int lel = eng->h_ctl[j].lel;
+                    rc = eng->fetch_vars(j, vars);
+                    if (rc != DDO_OK) return rc;
+                    pend.push_back(Pending{open[s0 + j], lel, (int)p_val.size(), 0, pw});
+                    p_vars.insert(p_vars.end(), vars.begin(), vars.begin() + lel);
+                }
+                p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
+                for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
+                p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
+                pend.back().count++;
+            }
         }
-        // enqueue_cutset (parallel.rs:456-469): ub = min(node ub, root ub), kept iff ub > best_lb
-        for (int j = 0; j < oc; ++j) {
-            const DDCtl& c = eng->h_ctl[j];
-            const bool exact = (c.lel < 0) || c.ebpo;
-            caps[j] = wv[open[j]].ub == INT32_MAX ? INT64_MAX : wv[open[j]].ub;
-            lbs[j] = exact ? INT64_MAX : best_lb;
-        }
-        int pw = 1;
-        const int total = eng->drain_all(oc, caps.data(), lbs.data(), &pw);
-        if (total < 0) return total;
+        if (improver >= 0) { rc = take_solution(improver, DDO_RELAXED, lb1); if (rc != DDO_OK) return rc; }
         t0 = now_ms();
-        int cur_dd = -1, cur_rec = -1, lel = 0;
-        std::vector<int32_t> vars;
-        for (int r = 0; r < total; ++r) {
-            const int j = eng->h_out_dd[r];
-            if (j != cur_dd) {
-                cur_dd = j;
-                const DDCtl& c = eng->h_ctl[j];
-                lel = c.lel;
-                rc = eng->fetch_vars(j, vars);
-                if (rc != DDO_OK) return rc;
-                PathRec pr;
-                pr.parent_rec = wv[open[j]].rec; pr.parent_bits = wv[open[j]].bits;
-                pr.vars.assign(vars.begin(), vars.begin() + lel);
-                recs.push_back(std::move(pr));
-                cur_rec = (int)recs.size() - 1;
+        size_t var_off = 0;
+        for (const Pending& pd : pend) {
+            PathRec pr;
+            pr.parent_rec = w_items[pd.wave_index].rec;
+            pr.parent_bits.assign(&w_bits[(size_t)pd.wave_index * PWN], &w_bits[(size_t)pd.wave_index * PWN] + PWN);
+            pr.vars.assign(p_vars.begin() + var_off, p_vars.begin() + var_off + pd.lel);
+            var_off += pd.lel;
+            int rec_id = -1;
+            for (int q = 0; q < pd.count; ++q) {
+                const size_t r = (size_t)pd.first + q;
+                if ((int64_t)p_ub[r] <= best_lb) continue;  // parallel.rs:461 with the final incumbent of the wave
+                if (rec_id < 0) { recs.push_back(pr); rec_id = (int)recs.size() - 1; }
+                fringe.push(&p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + pd.lel, rec_id, &p_bits[r * PWN], (pd.lel + 63) / 64);
             }
-            fringe.push(&eng->h_out_state[(size_t)r * eng->S], eng->h_out_val[r], eng->h_out_ub[r], wv[open[j]].depth + lel, cur_rec,
-                        &eng->h_out_path[(size_t)r * pw], std::min(pw, (lel + 63) / 64));
         }
         fringe_ms += now_ms() - t0;
     }

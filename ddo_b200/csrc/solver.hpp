@@ -67,6 +67,8 @@ struct Solver {
     bool aborted = false;
     uint64_t explored = 0, expanded = 0, transitions = 0, compilations = 0, waves = 0;
     double device_ms = 0, fringe_ms = 0;
+    // scratch of one wave (kept to avoid reallocations)
+    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars;
 
     Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws);
     int init(bool push_root);

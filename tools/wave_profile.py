@@ -9,8 +9,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from ddo_b200 import FixedWidth, Misp, ParNoCachingSolverLel, gnp  # noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+CAP = int(sys.argv[2]) if len(sys.argv) > 2 else min(K, 64)
 pb = Misp(gnp(500, 0.5, 1))
-s = ParNoCachingSolverLel(pb, FixedWidth(10000), wave_size=K)
+s = ParNoCachingSolverLel(pb, FixedWidth(10000), wave_size=K, batch_cap=CAP)
 for rep in range(2):
     s.init(True)
     rows, prev = [], s.stats()
