@@ -225,10 +225,10 @@ class GpuMdd:
         N.lib().ddo_mdd_set_profiling(self.h, int(on))
 
     def kernel_times(self):
-        ms = (C.c_double * 5)()
-        ln = (C.c_uint64 * 5)()
+        ms = (C.c_double * 6)()
+        ln = (C.c_uint64 * 6)()
         N.lib().ddo_mdd_kernel_times(self.h, C.byref(ms), C.byref(ln))
-        names = ["k_expand", "k_finish", "k_compact", "k_finalize_bottomup", "k_drain"]
+        names = ["k_expand", "k_finish", "k_compact", "k_finalize_bottomup", "k_drain", "k_small"]
         return {n: {"ms": ms[i], "launches": int(ln[i])} for i, n in enumerate(names)}
 
     def layer_trace(self, index: int = 0):

@@ -111,12 +111,12 @@ int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps
 int ddo_mdd_set_profiling(ddo_mdd* d, int32_t on) {
     if (!d) return DDO_ERR_INVALID;
     d->e.profiling = on != 0; d->e.prof_used = 0;
-    for (int i = 0; i < 5; ++i) { d->e.prof_ms[i] = 0; d->e.prof_launches[i] = 0; }
+    for (int i = 0; i < 6; ++i) { d->e.prof_ms[i] = 0; d->e.prof_launches[i] = 0; }
     return DDO_OK;
 }
-int ddo_mdd_kernel_times(ddo_mdd* d, double ms[5], uint64_t launches[5]) {
+int ddo_mdd_kernel_times(ddo_mdd* d, double ms[6], uint64_t launches[6]) {
     if (!d || !ms || !launches) return DDO_ERR_INVALID;
-    for (int i = 0; i < 5; ++i) { ms[i] = d->e.prof_ms[i]; launches[i] = d->e.prof_launches[i]; }
+    for (int i = 0; i < 6; ++i) { ms[i] = d->e.prof_ms[i]; launches[i] = d->e.prof_launches[i]; }
     return DDO_OK;
 }
 int ddo_mdd_layer_trace(ddo_mdd* d, int32_t index, int32_t* vars, int32_t* widths, int32_t cap) {

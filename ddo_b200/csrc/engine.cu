@@ -288,8 +288,10 @@ static int launch_small(Engine* E, int count, int64_t best_lb) {
         CUDA_TRY(cudaFuncSetAttribute(k_small<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         E->small_attr_set = true;
     }
+    E->prof_mark(-1);
     k_small<S><<<count, 128, smem, E->stream>>>(E->ev, count, Ws, (long long)best_lb, E->d_small);
     ++g_kernel_launches;
+    E->prof_mark(5);
     CUDA_TRY(cudaGetLastError());
     return DDO_OK;
 }
@@ -312,6 +314,7 @@ int Engine::compile_small(int count, int64_t best_lb, float* device_ms) {
     CUDA_TRY(cudaMemcpyAsync(h_small, d_small, (size_t)count * sizeof(SmallOut), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     return DDO_OK;
 }
 

@@ -125,7 +125,7 @@ struct Engine {
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events; std::vector<int> prof_kinds; size_t prof_used = 0;
-    double prof_ms[5] = {0, 0, 0, 0, 0}; uint64_t prof_launches[5] = {0, 0, 0, 0, 0};
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0}; uint64_t prof_launches[6] = {0, 0, 0, 0, 0, 0};
     void prof_mark(int kind);   // record an event; the interval since the previous mark is attributed to `kind`
     int prof_collect();
 

@@ -113,9 +113,9 @@ int ddo_mdd_drain_cutset(ddo_mdd*, int32_t index, int64_t ub_cap, int64_t lb_fil
 int ddo_mdd_drain_cutset_batch(ddo_mdd*, int32_t count, const int64_t* ub_caps, const int64_t* lb_filters, uint64_t* states, int64_t* values,
                                int64_t* ubs, int32_t* dd_index, uint64_t* path_bits, int32_t* path_words, int64_t* total);
 /* per-kernel device time (CUDA events around every launch; slows the launch loop, off by default).  kernel ids: 0 k_expand, 1 k_finish,
- * 2 k_compact, 3 k_finalize+k_bottomup, 4 drain kernels.  Times accumulate until reset (on != 0 also resets). */
+ * 2 k_compact, 3 k_finalize+k_bottomup, 4 drain kernels, 5 k_small.  Times accumulate until reset (on != 0 also resets). */
 int ddo_mdd_set_profiling(ddo_mdd*, int32_t on);
-int ddo_mdd_kernel_times(ddo_mdd*, double ms[5], uint64_t launches[5]);
+int ddo_mdd_kernel_times(ddo_mdd*, double ms[6], uint64_t launches[6]);
 /* per-layer trace of DD `index`: branching variable (Problem::next_variable) and layer width after the cut; returns #layers expanded */
 int ddo_mdd_layer_trace(ddo_mdd*, int32_t index, int32_t* vars, int32_t* widths, int32_t cap);
 

@@ -1040,65 +1040,94 @@ public:
     struct WaveTrace { size_t popped; isize best_lb; size_t fringe_len; isize top_ub; };
     std::vector<WaveTrace> trace;
 
-    Completion maximize() {
-        SubProblem<S> root{std::make_shared<const S>(c_.problem->initial_state()), c_.problem->initial_value(), {}, ISIZE_MAX, 0};
-        c_.fringe->push(root);
-        std::vector<Mdd<S, Hash, Eq>> mdds;
-        for (size_t i = 0; i < K_; ++i) mdds.emplace_back(c_.cutset_type);
+    // ---- stepwise form (what the fringe-sharded multi-GPU driver calls between its allreduce(max) steps) ----
+    void init(bool push_root) {
+        c_.fringe->clear();
+        best_lb = ISIZE_MIN; best_ub = ISIZE_MAX; best_sol.reset(); aborted = false; stats = SolverStats(); trace.clear();
+        mdds_.clear();
+        for (size_t i = 0; i < K_; ++i) mdds_.emplace_back(c_.cutset_type);
+        if (push_root) c_.fringe->push(SubProblem<S>{std::make_shared<const S>(c_.problem->initial_state()), c_.problem->initial_value(), {}, ISIZE_MAX, 0});
+    }
+    // one wave; out3 = {best_lb, ub of the best open node before the wave (ISIZE_MIN if none), 1 if work remains}; false on cutoff
+    bool wave(isize out3[3]) {
+        std::vector<SubProblem<S>> wave;
+        isize top_ub = ISIZE_MIN;
+        while (wave.size() < K_ && !c_.fringe->is_empty()) {
+            SubProblem<S> nn = *c_.fringe->pop();
+            if (nn.ub <= best_lb) { c_.fringe->clear(); break; }  // parallel.rs:531-535
+            if (wave.empty()) top_ub = nn.ub;
+            wave.push_back(std::move(nn));
+            stats.explored += 1;
+        }
+        out3[1] = top_ub;
+        if (wave.empty()) { out3[0] = best_lb; out3[2] = 0; return true; }
+        best_ub = top_ub;
+        stats.waves += 1;
+        auto& mdds = mdds_;
         EmptyCache<S> cache;
+        // restricted
+        isize lb = best_lb;
+        std::vector<char> exact(wave.size(), 0);
+        std::vector<size_t> widths(wave.size());
+        for (size_t i = 0; i < wave.size(); ++i) {
+            widths[i] = c_.width->max_width(wave[i]);
+            CompilationInput<S> in{CompilationType::Restricted, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
+            Completion comp;
+            if (!mdds[i].compile(in, &comp)) return false;
+            exact[i] = comp.is_exact;
+            account(mdds[i]);
+        }
+        for (size_t i = 0; i < wave.size(); ++i) maybe_update_best(mdds[i]);
+        // relaxed
+        lb = best_lb;
+        std::vector<char> relaxed_done(wave.size(), 0);
+        for (size_t i = 0; i < wave.size(); ++i) {
+            if (exact[i]) continue;
+            CompilationInput<S> in{CompilationType::Relaxed, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
+            Completion comp;
+            if (!mdds[i].compile(in, &comp)) return false;
+            relaxed_done[i] = 1;
+            exact[i] = comp.is_exact;
+            account(mdds[i]);
+        }
+        for (size_t i = 0; i < wave.size(); ++i) if (relaxed_done[i]) maybe_update_best(mdds[i]);
+        for (size_t i = 0; i < wave.size(); ++i) {
+            if (!relaxed_done[i] || exact[i]) continue;
+            isize ub = wave[i].ub, blb = best_lb;
+            mdds[i].drain_cutset([&](SubProblem<S> n) {
+                n.ub = std::min(ub, n.ub);
+                if (n.ub > blb) c_.fringe->push(std::move(n));
+            });
+        }
+        trace.push_back({wave.size(), best_lb, c_.fringe->len(), top_ub});
+        out3[0] = best_lb; out3[2] = c_.fringe->is_empty() ? 0 : 1;
+        return true;
+    }
+    void set_lower_bound(isize lb) { if (lb > best_lb) best_lb = lb; }
+    // keep every nranks-th open node of the common MaxUB order (SURVEY.md section 8e initial deal)
+    void retain_share(size_t rank, size_t nranks) {
+        if (nranks <= 1) return;
+        std::vector<SubProblem<S>> keep;
+        for (size_t idx = 0; !c_.fringe->is_empty(); ++idx) {
+            SubProblem<S> n = *c_.fringe->pop();
+            if (idx % nranks == rank) keep.push_back(std::move(n));
+        }
+        c_.fringe->clear();
+        for (auto& n : keep) c_.fringe->push(std::move(n));
+    }
+    void finish() {
+        if (c_.fringe->is_empty() && !aborted) best_ub = best_lb;
+        if (best_sol) std::stable_sort(best_sol->begin(), best_sol->end(), [](const Decision& a, const Decision& b) { return a.variable < b.variable; });
+    }
+    size_t fringe_len() const { return c_.fringe->len(); }
+
+    Completion maximize() {
+        init(true);
         for (;;) {
             if (c_.fringe->is_empty()) { best_ub = best_lb; break; }
             if (stats.waves >= max_waves) { aborted = true; break; }
-            std::vector<SubProblem<S>> wave;
-            isize top_ub = ISIZE_MIN;
-            while (wave.size() < K_ && !c_.fringe->is_empty()) {
-                SubProblem<S> nn = *c_.fringe->pop();
-                if (nn.ub <= best_lb) { c_.fringe->clear(); break; }  // parallel.rs:531-535
-                if (wave.empty()) top_ub = nn.ub;
-                wave.push_back(std::move(nn));
-                stats.explored += 1;
-            }
-            if (wave.empty()) continue;
-            best_ub = top_ub;
-            stats.waves += 1;
-            // restricted
-            isize lb = best_lb;
-            std::vector<char> exact(wave.size(), 0);
-            std::vector<size_t> widths(wave.size());
-            bool cut = false;
-            for (size_t i = 0; i < wave.size(); ++i) {
-                widths[i] = c_.width->max_width(wave[i]);
-                CompilationInput<S> in{CompilationType::Restricted, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
-                Completion comp;
-                if (!mdds[i].compile(in, &comp)) { cut = true; break; }
-                exact[i] = comp.is_exact;
-                account(mdds[i]);
-            }
-            if (cut) { abort_search(); break; }
-            for (size_t i = 0; i < wave.size(); ++i) maybe_update_best(mdds[i]);
-            // relaxed
-            lb = best_lb;
-            std::vector<char> relaxed_done(wave.size(), 0);
-            for (size_t i = 0; i < wave.size(); ++i) {
-                if (exact[i]) continue;
-                CompilationInput<S> in{CompilationType::Relaxed, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
-                Completion comp;
-                if (!mdds[i].compile(in, &comp)) { cut = true; break; }
-                relaxed_done[i] = 1;
-                exact[i] = comp.is_exact;
-                account(mdds[i]);
-            }
-            if (cut) { abort_search(); break; }
-            for (size_t i = 0; i < wave.size(); ++i) if (relaxed_done[i]) maybe_update_best(mdds[i]);
-            for (size_t i = 0; i < wave.size(); ++i) {
-                if (!relaxed_done[i] || exact[i]) continue;
-                isize ub = wave[i].ub, blb = best_lb;
-                mdds[i].drain_cutset([&](SubProblem<S> n) {
-                    n.ub = std::min(ub, n.ub);
-                    if (n.ub > blb) c_.fringe->push(std::move(n));
-                });
-            }
-            trace.push_back({wave.size(), best_lb, c_.fringe->len(), top_ub});
+            isize o3[3];
+            if (!wave(o3)) { abort_search(); break; }
         }
         if (best_sol) std::stable_sort(best_sol->begin(), best_sol->end(), [](const Decision& a, const Decision& b) { return a.variable < b.variable; });
         return Completion{!aborted, best_sol ? std::optional<isize>(best_lb) : std::nullopt};
@@ -1106,6 +1135,7 @@ public:
 private:
     SolverConfig<S> c_;
     size_t K_;
+    std::vector<Mdd<S, Hash, Eq>> mdds_;
     void account(const Mdd<S, Hash, Eq>& m) { stats.compilations++; stats.expanded += m.expanded; stats.transitions += m.transitions; }
     void maybe_update_best(const Mdd<S, Hash, Eq>& m) {
         isize v = m.best_exact_value().value_or(ISIZE_MIN);

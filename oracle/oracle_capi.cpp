@@ -26,6 +26,18 @@ struct MispDD {
     SubProblem<BitState> root;
     MispDD(MispHandle* h_, int cutset_type) : h(h_), mdd(cutset_type) {}
 };
+struct MispStepper {
+    MispHandle* h;
+    FixedWidth<BitState> fw; NbUnassignedWidth<BitState> nw; NoCutoff nocut; EmptyDominanceChecker<BitState> dom; EmptyCache<BitState> cache;
+    MaxUB<BitState> mx; MispFringe fringe;
+    std::unique_ptr<WaveSolver<BitState, BitStateHash, BitStateEq>> solver;
+    MispStepper(MispHandle* h_, int k, int width_kind, uint64_t width)
+        : h(h_), fw((size_t)width), nw(h_->pb.nb_vars), mx{&h_->rk}, fringe(mx) {
+        const WidthHeuristic<BitState>* wh = width_kind == 0 ? (const WidthHeuristic<BitState>*)&fw : (const WidthHeuristic<BitState>*)&nw;
+        SolverConfig<BitState> cfg{&h->pb, &h->rlx, &h->rk, wh, &dom, &nocut, &fringe, &cache, LAST_EXACT_LAYER};
+        solver.reset(new WaveSolver<BitState, BitStateHash, BitStateEq>(cfg, (size_t)k));
+    }
+};
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
@@ -199,6 +211,20 @@ uint64_t oracle_misp_compile_many(void* hp, int32_t threads, int32_t n_roots, co
     if (seconds) *seconds = now_s() - t0;
     if (transitions_out) *transitions_out = transitions.load();
     return expanded.load();
+}
+
+// stepwise wave solver (CPU stand-in for the device solver in the gloo tests of the fringe-sharded driver)
+void* oracle_misp_stepper_new(void* hp, int32_t k, int32_t width_kind, uint64_t width) { return new MispStepper((MispHandle*)hp, k, width_kind, width); }
+void oracle_misp_stepper_free(void* s) { delete (MispStepper*)s; }
+void oracle_misp_stepper_init(void* s, int32_t push_root) { ((MispStepper*)s)->solver->init(push_root != 0); }
+int32_t oracle_misp_stepper_wave(void* s, int64_t out3[3]) { isize o[3]; bool ok = ((MispStepper*)s)->solver->wave(o); out3[0] = o[0]; out3[1] = o[1]; out3[2] = o[2]; return ok ? 0 : 1; }
+void oracle_misp_stepper_set_lb(void* s, int64_t lb) { ((MispStepper*)s)->solver->set_lower_bound(lb); }
+void oracle_misp_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((MispStepper*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
+void oracle_misp_stepper_finish(void* s) { ((MispStepper*)s)->solver->finish(); }
+// out[0..5] = best_lb, best_ub, fringe_len, explored, expanded, has_solution
+void oracle_misp_stepper_state(void* s, int64_t out[6]) {
+    auto& w = *((MispStepper*)s)->solver;
+    out[0] = w.best_lb; out[1] = w.best_ub; out[2] = (int64_t)w.fringe_len(); out[3] = (int64_t)w.stats.explored; out[4] = (int64_t)w.stats.expanded; out[5] = w.best_sol.has_value();
 }
 
 // Knapsack (BASELINE config 1).  solver: 0 sequential, 2 parallel(k).  caching != 0: SimpleCache + KPDominance (SeqCachingSolverFc, knapsack/main.rs:329)

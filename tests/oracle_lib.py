@@ -65,6 +65,15 @@ def lib():
         _lib.oracle_misp_compile_many.restype = C.c_uint64
         _lib.oracle_misp_compile_many.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        _lib.oracle_misp_stepper_new.restype = C.c_void_p
+        _lib.oracle_misp_stepper_new.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
+        for f in ("free", "finish"):
+            getattr(_lib, f"oracle_misp_stepper_{f}").argtypes = [C.c_void_p]
+        _lib.oracle_misp_stepper_init.argtypes = [C.c_void_p, C.c_int32]
+        _lib.oracle_misp_stepper_wave.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 3)]
+        _lib.oracle_misp_stepper_set_lb.argtypes = [C.c_void_p, C.c_int64]
+        _lib.oracle_misp_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        _lib.oracle_misp_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
         _lib.oracle_knapsack_solve.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                                C.POINTER(SolveResult), C.c_void_p]
         _lib.oracle_locbounds_dump.argtypes = [C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
@@ -160,6 +169,55 @@ class OracleMisp:
         sec = C.c_double(0)
         exp = lib().oracle_misp_compile_many(self.h, threads, n, _p(rs), _p(rv), _p(rd), _p(w), best_lb, cutset_type, _p(rb), _p(xb), _p(cs), C.byref(tr), C.byref(sec))
         return {"expanded": int(exp), "transitions": int(tr.value), "seconds": float(sec.value), "restricted_best": rb, "relaxed_best": xb, "cutset_sizes": cs}
+
+
+class OracleStepper:
+    """Stepwise CPU wave solver with the interface ddo_b200.sharded.sharded_maximize expects (stand-in for the device solver)."""
+
+    def __init__(self, oracle: OracleMisp, wave_size: int, width=None):
+        self.o = oracle
+        self.h = lib().oracle_misp_stepper_new(oracle.h, wave_size, 0 if width is not None else 1, width or 0)
+
+    def __del__(self):
+        try:
+            lib().oracle_misp_stepper_free(self.h)
+        except Exception:
+            pass
+
+    def init(self, push_root=True):
+        lib().oracle_misp_stepper_init(self.h, int(push_root))
+
+    def wave(self):
+        out = (C.c_int64 * 3)()
+        rc = lib().oracle_misp_stepper_wave(self.h, C.byref(out))
+        assert rc == 0
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def set_lower_bound(self, lb):
+        lib().oracle_misp_stepper_set_lb(self.h, lb)
+
+    def retain_share(self, rank, nranks):
+        lib().oracle_misp_stepper_retain_share(self.h, rank, nranks)
+
+    def finish(self):
+        lib().oracle_misp_stepper_finish(self.h)
+
+    def _state(self):
+        out = (C.c_int64 * 6)()
+        lib().oracle_misp_stepper_state(self.h, C.byref(out))
+        return [int(x) for x in out]
+
+    def fringe_len(self):
+        return self._state()[2]
+
+    def best_lower_bound(self):
+        return self._state()[0]
+
+    def explored(self):
+        return self._state()[3]
+
+    def expanded(self):
+        return self._state()[4]
 
 
 def knapsack_solve(inst, solver="sequential", k=1, width=None, cutset_type=FRONTIER, caching=True):

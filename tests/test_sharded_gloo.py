@@ -1,0 +1,68 @@
+"""The N > 1 path on CPU: world_size-2 (and 3) gloo process groups drive the fringe-sharded branch-and-bound protocol of
+ddo_b200/sharded.py -- root DD on every rank, deterministic deal of the open sub-problems, one allreduce(max) of three int64 per wave --
+with the CPU oracle's stepwise wave solver standing in for the device solver (tests may use the oracle; the product never does)."""
+import json
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, spec, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+
+    import oracle_lib as O
+    from ddo_b200.instances import gnp, parse_dimacs
+    from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inst = gnp(*spec["gnp"]) if "gnp" in spec else parse_dimacs((ROOT / "tests" / "golden" / "misp" / spec["file"]).read_text())
+    stepper = O.OracleStepper(O.OracleMisp(inst), spec["wave"], spec.get("width"))
+    res = sharded_maximize(stepper, rank, world, torch_allreduce_max())
+    res.update(rank=rank, explored=stepper.explored(), expanded=stepper.expanded())
+    Path(out_dir, f"r{rank}.json").write_text(json.dumps(res))
+    dist.destroy_process_group()
+
+
+def _run(world, spec, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, spec, str(tmp_path)), nprocs=world, join=True)
+    return [json.loads((tmp_path / f"r{r}.json").read_text()) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_bnb_agrees_with_single_process(world, tmp_path):
+    import oracle_lib as O
+    from ddo_b200.instances import gnp
+
+    spec = {"gnp": (70, 0.25, 5), "wave": 4, "width": 6}
+    single = O.OracleMisp(gnp(*spec["gnp"])).solve("wave", k=spec["wave"], width=spec["width"])
+    res = _run(world, spec, tmp_path)
+    for r in res:  # every rank ends with the same proven optimum and bound
+        assert r["is_exact"] and r["best_lb"] == r["best_ub"] == single["best_value"]
+    # the shards partition the root's open nodes: every rank explored the root + a share, none did all the work alone
+    assert all(r["explored"] >= 1 for r in res)
+    assert sum(r["explored"] for r in res) >= single["explored"] - (0) and max(r["explored"] for r in res) < single["explored"] + world
+    # one collective per wave (two allreduce calls of 3 x int64: incumbent/termination, then bound), nothing on the data path
+    assert all(r["collectives"] <= 2 * r["waves"] + 1 for r in res)
+
+
+def test_sharded_bnb_known_optimum_dimacs(tmp_path):
+    exp = json.loads((ROOT / "tests" / "golden" / "expected.json").read_text())["misp"]["johnson8-4-4"]["optimum"]
+    res = _run(2, {"file": "johnson8-4-4.clq", "wave": 8}, tmp_path)
+    assert all(r["is_exact"] and r["best_lb"] == exp and r["best_ub"] == exp for r in res)
