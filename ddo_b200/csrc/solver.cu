@@ -40,6 +40,26 @@ int NoDupFringe::compare_new(int32_t ub, int32_t value, int16_t pc, const uint64
 }
 int NoDupFringe::compare(int a, int b) const { return compare_new(items_[a].ub, items_[a].value, popc_[a], state(a), b); }
 
+static inline uint64_t lex_word_host(uint64_t w) {  // ~bitreverse: larger = Greater in BitSet::cmp among equal popcounts
+    w = ((w >> 1) & 0x5555555555555555ull) | ((w & 0x5555555555555555ull) << 1);
+    w = ((w >> 2) & 0x3333333333333333ull) | ((w & 0x3333333333333333ull) << 2);
+    w = ((w >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((w & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return ~__builtin_bswap64(w);
+}
+NoDupFringe::HeapEnt NoDupFringe::make_ent(int id) const {
+    const Item& it = items_[id];
+    HeapEnt e;
+    e.k1 = ((uint64_t)((uint32_t)it.ub ^ 0x80000000u) << 32) | ((uint32_t)it.value ^ 0x80000000u);
+    e.k2 = ((uint64_t)(uint16_t)popc_[id] << 48) | (lex_word_host(state(id)[0]) >> 16);
+    e.id = id;
+    return e;
+}
+bool NoDupFringe::ent_less(const HeapEnt& a, const HeapEnt& b) const {
+    if (a.k1 != b.k1) return a.k1 < b.k1;
+    if (a.k2 != b.k2) return a.k2 < b.k2;
+    return lex_cmp(state(a.id), state(b.id), W) < 0;  // same ub, value, popcount and 48 leading lexicographic bits
+}
+
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
     states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); pos_.clear(); heap_.clear(); recycle_.clear();
     table_.clear(); table_used_ = 0;
@@ -48,7 +68,7 @@ void NoDupFringe::rehash(size_t min_cap) {
     size_t cap = 1024;
     while (cap < min_cap) cap <<= 1;
     table_.assign(cap, -1); table_used_ = 0;
-    for (int id : heap_) table_insert(id);
+    for (const HeapEnt& e : heap_) table_insert(e.id);
 }
 void NoDupFringe::table_insert(int id) {
     const size_t mask = table_.size() - 1;
@@ -76,27 +96,29 @@ void NoDupFringe::table_erase(int id) {
 }
 void NoDupFringe::bubble_up(int id) {  // no_duplicate.rs:227-242
     size_t me = (size_t)pos_[id];
+    const HeapEnt e = heap_[me];
     while (me != 0) {
         const size_t par = (me - 1) / 2;
-        if (compare(heap_[me], heap_[par]) <= 0) break;
-        const int p_id = heap_[par];
-        pos_[p_id] = (int)me; pos_[id] = (int)par; heap_[me] = p_id; heap_[par] = id;
+        if (!ent_less(heap_[par], e)) break;
+        heap_[me] = heap_[par]; pos_[heap_[me].id] = (int)me;
         me = par;
     }
+    heap_[me] = e; pos_[id] = (int)me;
 }
 void NoDupFringe::bubble_down(int id) {  // no_duplicate.rs:244-259,279-295
     size_t me = (size_t)pos_[id];
+    const HeapEnt e = heap_[me];
     const size_t size = heap_.size();
     for (;;) {
-        const size_t left = me * 2 + 1, right = me * 2 + 2;
+        const size_t left = me * 2 + 1, right = left + 1;
         if (left >= size) break;
         size_t kid = left;
-        if (right < size && compare(heap_[left], heap_[right]) <= 0) kid = right;
-        if (compare(heap_[me], heap_[kid]) >= 0) break;
-        const int k_id = heap_[kid];
-        pos_[k_id] = (int)me; pos_[id] = (int)kid; heap_[me] = k_id; heap_[kid] = id;
+        if (right < size && !ent_less(heap_[right], heap_[left])) kid = right;  // max_child_of: the right child wins ties (:291-294)
+        if (!ent_less(e, heap_[kid])) break;
+        heap_[me] = heap_[kid]; pos_[heap_[me].id] = (int)me;
         me = kid;
     }
+    heap_[me] = e; pos_[id] = (int)me;
 }
 void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
     const uint64_t h = hash_state(st, W);
@@ -112,6 +134,7 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
             std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
         }
         if (ub > old_ub) items_[id].ub = ub;
+        heap_[pos_[id]] = make_ent(id);  // the key stored in the heap follows the node
         if (up) bubble_up(id);
         return;
     }
@@ -128,7 +151,7 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     int pc = 0;
     for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
     popc_[id] = (int16_t)pc; hash_[id] = h;
-    heap_.push_back(id);
+    heap_.push_back(make_ent(id));
     pos_[id] = (int)heap_.size() - 1;
     if ((table_used_ + 1) * 2 > table_.size()) rehash(heap_.size() * 4);  // re-inserts every live node, `id` included
     else table_insert(id);
@@ -136,9 +159,9 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
 }
 int NoDupFringe::pop() {
     if (heap_.empty()) return -1;
-    const int id = heap_[0];
+    const int id = heap_[0].id;
     heap_[0] = heap_.back(); heap_.pop_back();
-    if (!heap_.empty()) { pos_[heap_[0]] = 0; bubble_down(heap_[0]); }
+    if (!heap_.empty()) { pos_[heap_[0].id] = 0; bubble_down(heap_[0].id); }
     recycle_.push_back(id);
     table_erase(id);
     return id;

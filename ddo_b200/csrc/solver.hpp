@@ -33,7 +33,6 @@ public:
     void push(const uint64_t* state, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words);
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
-    int top() const { return heap_.empty() ? -1 : heap_[0]; }
     const uint64_t* state(int id) const { return &states_[(size_t)id * W]; }
     const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
     const Item& item(int id) const { return items_[id]; }
@@ -43,7 +42,13 @@ private:
     std::vector<Item> items_;
     std::vector<int16_t> popc_;
     std::vector<uint64_t> hash_;
-    std::vector<int> pos_, heap_, recycle_;
+    // the heap stores the ordering key inline (MaxUB: ub, value; MispRanking: popcount, first lexicographic word) so that sift operations
+    // rarely touch the node storage; full ties fall back to the state comparison
+    struct HeapEnt { uint64_t k1, k2; int id; };
+    std::vector<HeapEnt> heap_;
+    std::vector<int> pos_, recycle_;
+    HeapEnt make_ent(int id) const;
+    bool ent_less(const HeapEnt& a, const HeapEnt& b) const;  // a strictly below b in the MaxUB order
     std::vector<int> table_;  // open addressing: node id or -1 (empty) / -2 (tombstone)
     size_t table_used_ = 0;   // occupied + tombstones
     int compare(int a, int b) const;  // MaxUB: ub, value, MispRanking
