@@ -183,7 +183,13 @@ def run_ours(args, rank, world, local_rank):
     if kt is not None:
         dom = max(("k_expand", "k_finish", "k_compact", "k_small"), key=lambda k: kt[k]["ms"])
         dom_gbs = last["expanded"] * b_node / (kt[dom]["ms"] * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+        traffic = None
+        tf = ROOT / "profiles" / "r01_traffic.json"
+        if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+            t = json.loads(tf.read_text())
+            if t["kernel"].startswith(dom):
+                traffic = {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"], "context": t["context"]}
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
                             "peak_source": peak_src, "bytes_per_node": b_node, "mean_out_degree": cbar,
                             "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in kt.items()},
                             "kernel_launches_per_step": {k: v["launches"] for k, v in kt.items()},
