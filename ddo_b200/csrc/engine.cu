@@ -114,7 +114,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ev.smem_keys = finish_smem <= 200 * 1024;
     if (ev.smem_keys) { ev.gkeys = nullptr; ev.ustat = nullptr; }
     else { finish_smem = 0; ALLOC(ev.gkeys, KC); ALLOC(ev.ustat, KC); }
-    ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S);
+    ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
     ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
     ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
@@ -123,6 +123,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
     CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
@@ -213,8 +214,9 @@ int Engine::prof_collect() {
     return DDO_OK;
 }
 
+// `count` DDs are initialised from the staged roots; `slots` (= count, or 2*count in dual mode) DD slots take part in every launch
 template <int S>
-static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag) {
+static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag) {
     constexpr int G = S / 2;
     const EV& ev = E->ev;
     cudaStream_t st = E->stream;
@@ -222,20 +224,20 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
         CUDA_TRY(cudaFuncSetAttribute(k_finish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_smem));
         E->finish_attr_set = true;
     }
-    k_init<S><<<count, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb);
+    k_init<S><<<slots, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb, slots > count);
     ++g_kernel_launches;
     E->prof_mark(-1);
     const int npb = 256 / G;
     // flat kernels run grid-stride over the per-layer work plan; the grid only has to be large enough to fill the machine
-    const long long max_tiles = (long long)count * ((E->C + npb - 1) / npb);
+    const long long max_tiles = (long long)slots * ((E->C + npb - 1) / npb);
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = 16;
     for (int t = 0; t < E->Lmax; ++t) {
-        k_finish<S><<<count, 1024, E->finish_smem, st>>>(ev, t);
+        k_finish<S><<<slots, 1024, E->finish_smem, st>>>(ev, t);
         E->prof_mark(1);
-        k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, count);
+        k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(2);
-        k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, count);
+        k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(0);
         g_kernel_launches += 3;
         if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {
@@ -246,12 +248,35 @@ static int run_layers(Engine* E, int count, int comp_type, int64_t best_lb, cons
         }
     }
     // one more k_finish turns TERMINAL into DONE; harmless otherwise
-    k_finalize<<<(count + 63) / 64, 64, 0, st>>>(ev, count);
+    k_finalize<<<(slots + 63) / 64, 64, 0, st>>>(ev, slots);
     ++g_kernel_launches;
-    if (comp_type == DDO_RELAXED) { k_bottomup<<<count, 1024, 0, st>>>(ev); ++g_kernel_launches; }
+    if (comp_type == DDO_RELAXED || slots > count) { k_bottomup<<<slots, 1024, 0, st>>>(ev); ++g_kernel_launches; }
     E->prof_mark(3);
     CUDA_TRY(cudaGetLastError());
     return DDO_OK;
+}
+
+static int compile_impl(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
+    const EV& ev = E->ev;
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)slots * E->T * 8, E->stream));
+    CUDA_TRY(cudaMemsetAsync(ev.vhist, 0, (size_t)slots * 64 * E->S * 4, E->stream));
+    CUDA_TRY(cudaMemsetAsync(ev.ucount, 0, (size_t)slots * 4, E->stream));
+    CUDA_TRY(cudaEventRecord(E->ev0, E->stream));
+    int rc;
+    switch (E->S) {
+        case 2: rc = run_layers<2>(E, count, slots, comp_type, best_lb, cutoff_flag); break;
+        case 4: rc = run_layers<4>(E, count, slots, comp_type, best_lb, cutoff_flag); break;
+        case 8: rc = run_layers<8>(E, count, slots, comp_type, best_lb, cutoff_flag); break;
+        case 16: rc = run_layers<16>(E, count, slots, comp_type, best_lb, cutoff_flag); break;
+        default: set_error("unsupported state width"); return DDO_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaEventRecord(E->ev1, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, E->ev0, E->ev1));
+    { int prc = E->prof_collect(); if (prc != DDO_OK) return prc; }
+    E->last_count = slots; E->last_comp_type = slots > count ? DDO_RELAXED : comp_type; E->ctl_fetched = false;
+    return rc;
 }
 
 int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
@@ -260,24 +285,15 @@ int Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vola
     for (int i = 0; i < count; ++i)
         if (comp_type == DDO_RELAXED && h_root_width[i] < 1) { set_error("max_width must be >= 1 for a relaxed DD (the reference panics at clean.rs:827)"); return DDO_ERR_INVALID; }
     if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;
-    CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)count * T * 8, stream));
-    CUDA_TRY(cudaMemsetAsync(ev.vhist, 0, (size_t)count * 64 * S * 4, stream));
-    CUDA_TRY(cudaEventRecord(ev0, stream));
-    int rc;
-    switch (S) {
-        case 2: rc = run_layers<2>(this, count, comp_type, best_lb, cutoff_flag); break;
-        case 4: rc = run_layers<4>(this, count, comp_type, best_lb, cutoff_flag); break;
-        case 8: rc = run_layers<8>(this, count, comp_type, best_lb, cutoff_flag); break;
-        case 16: rc = run_layers<16>(this, count, comp_type, best_lb, cutoff_flag); break;
-        default: set_error("unsupported state width"); return DDO_ERR_UNSUPPORTED;
-    }
-    CUDA_TRY(cudaEventRecord(ev1, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
-    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
-    last_count = count; last_comp_type = comp_type; ctl_fetched = false;
-    return rc;
+    return compile_impl(this, count, count, comp_type, best_lb, cutoff_flag, device_ms);
+}
+
+int Engine::compile_dual(int half, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
+    if (half < 1 || 2 * half > K || half > staged) { set_error("compile_dual: needs two DD slots per sub-problem"); return DDO_ERR_INVALID; }
+    for (int i = 0; i < half; ++i)
+        if (h_root_width[i] < 1) { set_error("max_width must be >= 1"); return DDO_ERR_INVALID; }
+    if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;
+    return compile_impl(this, half, 2 * half, DDO_RESTRICTED, best_lb, cutoff_flag, device_ms);
 }
 
 template <int S>

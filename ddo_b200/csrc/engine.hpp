@@ -31,7 +31,7 @@ struct MispModel {
     uint64_t* d_nc = nullptr;
 };
 
-enum : int32_t { ST_ACTIVE = 0, ST_TERMINAL = 1, ST_DONE = 2 };
+enum : int32_t { ST_ACTIVE = 0, ST_TERMINAL = 1, ST_DONE = 2, ST_WAITING = 3 };  // WAITING: relaxed twin slot that has not forked (yet)
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 // node flag bits kept in cur_flag / uinex / parent log
@@ -47,6 +47,7 @@ struct DDCtl {
     int32_t best_pos, best_exact_pos, best_value, best_exact_value;
     int32_t ebpo, overflow, cutset_count, lel_n;
     int32_t root_value, pad0;
+    int32_t primary, fork_t;  // relaxed twin of a restricted DD: slot of the primary and layer at which it forked (-1: ordinary DD)
     int64_t best_lb;
     unsigned long long expanded, transitions;
 };
@@ -71,6 +72,7 @@ struct EV {
     uint8_t* uflag; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
     unsigned long long* gkeys; int smem_keys;  // cut keys of the distinct candidates: in k_finish's shared memory when 2*Wcap of them fit, else here
     unsigned long long* table;
+    uint32_t* ucount; // [K] number of distinct states among the candidates being built (hash-slot claims of k_expand)
     uint32_t* vhist;  // [K][HN] occurrences of every vertex among the distinct states of the layer being built
     // logs
     uint32_t* plog;   // [K][Lmax][Wcap] best parent candidate + flags
@@ -107,6 +109,7 @@ struct Engine {
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
     int cutset_type = DDO_LAST_EXACT_LAYER;
     int num_sms = 148;
+    bool dual_enabled = true;  // fork the relaxed twin at the first cut of a restricted DD (DDO_DUAL=0 disables)
     size_t finish_smem = 0; bool finish_attr_set = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -135,6 +138,9 @@ struct Engine {
     int reserve_roots(int count);
     int stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths);
     int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
+    // dual mode: `half` restricted DDs in slots [0,half); the relaxed twin of DD j forks into slot half+j at the first width cut and then
+    // advances in the same launches (both against best_lb).  Results: ctl[j] restricted, ctl[half+j] relaxed (status WAITING = never forked).
+    int compile_dual(int half, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
     int fetch_ctl(int count);
     void fill_completion(int i, ddo_completion* out) const;
     int best_solution(int index, int exact, ddo_decision* out, int32_t* len);

@@ -130,9 +130,20 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
 // k_init: root of every DD becomes the single "candidate" of layer 0 (clean.rs:383-405)
 // =================================================================================================================
 template <int S>
-__global__ void k_init(EV ev, int count, int comp_type, long long best_lb) {
+__global__ void k_init(EV ev, int count, int comp_type, long long best_lb, int dual) {
     const int k = blockIdx.x;
-    if (k >= count) return;
+    if (k >= count) {  // dual mode: slot count + j is the (not yet forked) relaxed twin of DD j
+        if (dual && k < 2 * count && threadIdx.x == 0) {
+            const int p = k - count;
+            DDCtl c{};
+            c.status = ST_WAITING; c.ncand = 0; c.n_cur = 0; c.var = -1;
+            c.width = ev.root_width[p]; c.comp_type = DDO_RELAXED; c.root_depth = ev.root_depth[p]; c.lel = -1;
+            c.t_term = -1; c.best_pos = -1; c.best_exact_pos = -1; c.root_value = ev.root_val[p];
+            c.best_lb = best_lb; c.primary = p; c.fork_t = -1;
+            ev.ctl[k] = c;
+        }
+        return;
+    }
     DDCtl* ctl = ev.ctl + k;
     const size_t cb = (size_t)k * ev.C;
     if (threadIdx.x < S) ev.cand_state[cb * S + threadIdx.x] = ev.root_state[(size_t)k * S + threadIdx.x];
@@ -141,8 +152,9 @@ __global__ void k_init(EV ev, int count, int comp_type, long long best_lb) {
         c.status = ST_ACTIVE; c.ncand = 1; c.n_cur = 0; c.var = -1;
         c.width = ev.root_width[k]; c.comp_type = comp_type; c.root_depth = ev.root_depth[k]; c.lel = -1;
         c.t_term = -1; c.best_pos = -1; c.best_exact_pos = -1; c.root_value = ev.root_val[k];
-        c.best_lb = best_lb;
+        c.best_lb = best_lb; c.primary = -1; c.fork_t = -1;
         *ctl = c;
+        ev.ucount[k] = 1;
         int pc = 0;
         for (int j = 0; j < S; ++j) pc += __popcll(ev.root_state[(size_t)k * S + j]);
         ev.cand_rep[cb] = 0; ev.cand_first[cb] = 0; ev.cand_agg[cb] = pack_key(ev.root_val[k], PLOG_CAND_MASK); ev.cand_inex[cb] = 0;
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
     constexpr int W32 = 2 * S;        // 32-bit words per state
-    __shared__ unsigned int s_exp, s_tr, s_any;
+    __shared__ unsigned int s_exp, s_tr, s_any, s_claims;
     __shared__ uint4 s_claim[2 * NPB * G];     // states claimed by this tile (zero rows for everything else): 2 candidates per node
     __shared__ unsigned int s_hist[64 * S];    // per-vertex occurrence counts of the claimed states, flushed per DD
     const int total = ev.tile_off_e[count];
@@ -181,12 +193,16 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     const int tpb = (total + gridDim.x - 1) / gridDim.x;
     const int tile_lo = min((int)blockIdx.x * tpb, total), tile_hi = min(tile_lo + tpb, total);
     for (int i = threadIdx.x; i < 64 * S; i += 256) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_claims = 0;
     int hist_k = -1;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
     const int k = plan_find(ev.tile_off_e, count, tile);
     if (k != hist_k) {
         __syncthreads();
-        if (hist_k >= 0) for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) { atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); s_hist[i] = 0; } }
+        if (hist_k >= 0) {
+            for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) { atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); s_hist[i] = 0; } }
+            if (threadIdx.x == 0 && s_claims) { atomicAdd(ev.ucount + hist_k, s_claims); s_claims = 0; }
+        }
         hist_k = k;
     }
     DDCtl* ctl = ev.ctl + k;
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
                     if (sub == 0) old = atomicCAS(tab + slot, EMPTY64, entry);
                     old = __shfl_sync(gm, old, (threadIdx.x & 31) & ~(G - 1));
                     if (old == EMPTY64) {  // Entry::Vacant, clean.rs:739-765: a new distinct state of the next layer
-                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; s_any = 1; }
+                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; s_any = 1; atomicAdd(&s_claims, 1u); }
                         s_claim[(d * NPB + threadIdx.x / G) * G + sub] = mk_u4(a0, a1);
                         break;
                     }
@@ -303,7 +319,10 @@ __global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
     }
     }  // tile loop
     __syncthreads();
-    if (hist_k >= 0) for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); }
+    if (hist_k >= 0) {
+        for (int i = threadIdx.x; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); }
+        if (threadIdx.x == 0 && s_claims) atomicAdd(ev.ucount + hist_k, s_claims);
+    }
 }
 
 
@@ -341,9 +360,53 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
     const int status = ctl->status;
     if (status == ST_DONE) return;
     if (status == ST_TERMINAL) { __syncthreads(); if (tid == 0) ctl->status = ST_DONE; return; }
-    const int ncand = t == 0 ? 1 : 2 * ctl->n_cur;  // candidates produced by k_expand(t-1): two slots per node of layer t-1
     const size_t cb = (size_t)k * ev.C;
     const size_t lb = (size_t)k * ev.Lmax;
+    int vh_src = k;  // whose vertex histogram describes my candidates
+    if (status == ST_WAITING) {
+        // ---- relaxed twin: fork when the primary (restricted) DD is about to take its FIRST cut in this very step ---------------
+        // Until then both DDs are identical (clean.rs:779-795 never fired), so the twin starts from a copy of the primary's candidates.
+        // Everything read here is stable while the primary's own CTA runs finish(t) concurrently (its ctl->lel may already say t-1).
+        const int p = ctl->primary;
+        const DDCtl* pc = ev.ctl + p;
+        const int plel = pc->lel;
+        const bool fork = t >= 1 && ev.ucount[p] > (uint32_t)pc->width && (plel < 0 || plel == t - 1) && ev.nlog[(size_t)p * ev.Lmax + t - 1] > 0;
+        if (!fork) return;
+        const size_t pb = (size_t)p * ev.C, plb = (size_t)p * ev.Lmax;
+        const int n_prev = ev.nlog[plb + t - 1];
+        const int nc = 2 * n_prev;
+        {   // candidates (state rows + metadata), hash table, parent layer (for the LEL snapshot), per-layer logs
+            const uint4* s4 = reinterpret_cast<const uint4*>(ev.cand_state + pb * S); uint4* d4 = reinterpret_cast<uint4*>(ev.cand_state + cb * S);
+            for (int i = tid; i < nc * (S / 2); i += NT) d4[i] = s4[i];
+            for (int c = tid; c < nc; c += NT) {
+                ev.cand_agg[cb + c] = ev.cand_agg[pb + c]; ev.cand_first[cb + c] = ev.cand_first[pb + c]; ev.cand_rep[cb + c] = ev.cand_rep[pb + c];
+                ev.cand_inex[cb + c] = ev.cand_inex[pb + c]; ev.cand_rank[cb + c] = ev.cand_rank[pb + c]; ev.cand_slot[cb + c] = ev.cand_slot[pb + c];
+                ev.uflag[cb + c] = 0;
+            }
+            const unsigned long long* st = ev.table + (size_t)p * ev.T; unsigned long long* dt = ev.table + (size_t)k * ev.T;
+            for (int i = tid; i < ev.T; i += NT) dt[i] = st[i];
+            const int pbuf = (t - 1) & 1;
+            const uint4* cs4 = reinterpret_cast<const uint4*>(ev.cur_state[pbuf] + (size_t)p * ev.Wcap * S); uint4* cd4 = reinterpret_cast<uint4*>(ev.cur_state[pbuf] + (size_t)k * ev.Wcap * S);
+            for (int i = tid; i < n_prev * (S / 2); i += NT) cd4[i] = cs4[i];
+            for (int i = tid; i < n_prev; i += NT) {
+                ev.cur_val[pbuf][(size_t)k * ev.Wcap + i] = ev.cur_val[pbuf][(size_t)p * ev.Wcap + i];
+                ev.cur_rub[(size_t)k * ev.Wcap + i] = ev.cur_rub[(size_t)p * ev.Wcap + i];
+            }
+            for (int i = tid; i < t; i += NT) {
+                ev.nlog[lb + i] = ev.nlog[plb + i]; ev.vlog[lb + i] = ev.vlog[plb + i];
+                ev.rslog[(lb + i) * 2] = ev.rslog[(plb + i) * 2]; ev.rslog[(lb + i) * 2 + 1] = ev.rslog[(plb + i) * 2 + 1];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ctl->status = ST_ACTIVE; ctl->n_cur = n_prev; ctl->fork_t = t;
+            ctl->expanded = pc->expanded; ctl->transitions = pc->transitions;  // the shared prefix counts for both DDs
+            atomicAdd(ev.active, 1);
+        }
+        vh_src = p;
+        __syncthreads();
+    }
+    const int ncand = t == 0 ? 1 : 2 * ctl->n_cur;  // candidates produced by k_expand(t-1): two slots per node of layer t-1
     __syncthreads();
     if (tid == 0) { ctl->ncand = ncand; ctl->lel_pending = 0; }  // (the LEL snapshot requested by the previous step has been taken)
 
@@ -402,13 +465,13 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
     }
 
     // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties.
-    //         The occurrence counts were accumulated by k_expand / k_init over the distinct states; consume and clear them.
+    //         The occurrence counts were accumulated by k_expand / k_init over the distinct states.
     unsigned long long best = ~0ull;
     {
-        uint32_t* vh = ev.vhist + (size_t)k * ev.HN;
-        for (int i = tid; i < ev.HN; i += NT) {
+        const uint32_t* vh = ev.vhist + (size_t)vh_src * ev.HN;  // cleared by k_compact (a forking twin reads its primary's)
+        for (int i = tid; i < ev.n; i += NT) {
             const unsigned c = __ldcg(vh + i);
-            if (c) { vh[i] = 0; if (i < ev.n) best = min(best, ((unsigned long long)c << 32) | (unsigned)i); }
+            if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i);
         }
     }
     best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, sm.red64);
@@ -642,7 +705,7 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
     for (int k = lo; k < hi; ++k) {
         const int st = vc[k].status;
         te += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
-        tc += st != ST_DONE ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+        tc += (st == ST_ACTIVE || st == ST_TERMINAL) ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
     }
     int tote, totc;
     int oe = block_excl_scan(te, &tote, sm.scan);
@@ -651,7 +714,7 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
         const int st = vc[k].status;
         ev.tile_off_e[k] = oe; ev.tile_off_c[k] = oc;
         oe += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
-        oc += st != ST_DONE ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+        oc += (st == ST_ACTIVE || st == ST_TERMINAL) ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
     }
     if (tid == 0) { ev.tile_off_e[count] = tote; ev.tile_off_c[count] = totc; *ev.finish_counter = 0; }
 }
@@ -668,6 +731,10 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
     const int k = plan_find(ev.tile_off_c, count, tile);
     const DDCtl* ctl = ev.ctl + k;
     const int ncand = ctl->ncand;
+    if (tile == ev.tile_off_c[k]) {  // first tile of this DD: reset the per-layer accumulators that k_expand fills next
+        for (int i = threadIdx.x; i < ev.HN; i += 256) ev.vhist[(size_t)k * ev.HN + i] = 0;
+        if (threadIdx.x == 0) ev.ucount[k] = 0;
+    }
     const int c = (tile - ev.tile_off_c[k]) * CPB + threadIdx.x / G;
     if (c >= ncand) continue;
     const int sub = threadIdx.x % G;
@@ -859,6 +926,12 @@ __global__ void __launch_bounds__(128) k_small(EV ev, int count, int Ws, long lo
     }
 }
 
+// parent-log entry of node `pos` of layer `tt` of DD k: layers before a twin's fork belong to its primary
+__device__ __forceinline__ uint32_t plog_at(const EV& ev, const DDCtl* ctl, int k, int tt, int pos) {
+    const int src = (ctl->primary >= 0 && tt < ctl->fork_t) ? ctl->primary : k;
+    return ev.plog[((size_t)src * ev.Lmax + tt) * ev.Wcap + pos];
+}
+
 // =================================================================================================================
 // k_finalize: exact-best-path walk (clean.rs:634-655) and decision bits of the best / best exact path (clean.rs:329-343)
 // =================================================================================================================
@@ -874,7 +947,7 @@ __global__ void k_finalize(EV ev, int count) {
         int pos = ctl->best_pos, tt = T;
         bool exact = true;
         for (;;) {
-            const uint32_t e = ev.plog[(lb + tt) * ev.Wcap + pos];
+            const uint32_t e = plog_at(ev, ctl, k, tt, pos);
             if (!(e & PLOG_INEXACT)) { exact = true; break; }
             if (e & PLOG_RELAXED) { exact = false; break; }
             if (tt == 0) break;
@@ -889,7 +962,7 @@ __global__ void k_finalize(EV ev, int count) {
         if (which == 1 && !ctl->has_best_exact) continue;
         int pos = which == 0 ? ctl->best_pos : ctl->best_exact_pos;
         for (int tt = T; tt >= 1; --tt) {
-            const uint32_t cand = ev.plog[(lb + tt) * ev.Wcap + pos] & PLOG_CAND_MASK;
+            const uint32_t cand = plog_at(ev, ctl, k, tt, pos) & PLOG_CAND_MASK;
             if (!(cand & 1u)) out[(tt - 1) >> 6] |= 1ull << ((tt - 1) & 63);  // even candidate = YES
             pos = (int)(cand >> 1);
         }
@@ -1003,7 +1076,7 @@ __global__ void __launch_bounds__(256) k_cutset_write(EV ev, DrainOut o, const l
     for (int w = 0; w < 8; ++w) bits[w] = 0;
     int pos = i;
     for (int tt = ctl->lel; tt >= 1; --tt) {
-        const uint32_t cand = ev.plog[(lb + tt) * ev.Wcap + pos] & PLOG_CAND_MASK;
+        const uint32_t cand = plog_at(ev, ctl, k, tt, pos) & PLOG_CAND_MASK;
         if (!(cand & 1u)) {
             if (pw <= 8) bits[(tt - 1) >> 6] |= 1ull << ((tt - 1) & 63);
             else o.path[rec * pw + ((tt - 1) >> 6)] |= 1ull << ((tt - 1) & 63);

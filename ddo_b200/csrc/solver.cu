@@ -272,21 +272,76 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     } else {
         for (int i = 0; i < cnt; ++i) ov.push_back(i);
     }
-    // ---- 1b. restriction with the general engine (parallel.rs:396-423), `cap` DDs at a time -----------------------------------------
-    for (size_t s0 = 0; s0 < ov.size(); s0 += (size_t)cap) {
-        const int oc = (int)std::min<size_t>((size_t)cap, ov.size() - s0);
+    // ---- 1b. restriction with the general engine (parallel.rs:396-423) --------------------------------------------------------------
+    // Dual mode: the relaxed twin of a restricted DD forks on the device at the first width cut and advances in the same launches, so an
+    // inexact sub-problem costs one pass of ~n layers instead of two.  Both twins see lb0; the relaxed results are kept only if the
+    // restricted DDs of this wave did not improve the incumbent (lb1 == lb0, the common case) -- otherwise they are recompiled against lb1.
+    struct Pending { int wave_index, lel, first, count; };
+    struct TwinRes { int wave_index; unsigned long long expanded, transitions; bool has; int32_t best; };
+    std::vector<Pending> pend;
+    std::vector<TwinRes> twins;
+    p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+    std::vector<int64_t> caps, lbs;
+    std::vector<int32_t> vars;
+    // collects the cutset records of the last relaxed batch: slot -> wave index through `slot_wave`
+    auto collect_drain = [&](int slots, const std::vector<int>& slot_wave) -> int {
+        int pw = 1;
+        const int total = eng->drain_all(slots, caps.data(), lbs.data(), &pw);
+        if (total < 0) return total;
+        int cur_dd = -1;
+        for (int r = 0; r < total; ++r) {
+            const int j = eng->h_out_dd[r];
+            if (j != cur_dd) {
+                cur_dd = j;
+                const int lel = eng->h_ctl[j].lel;
+                int r2 = eng->fetch_vars(j, vars);
+                if (r2 != DDO_OK) return r2;
+                pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
+                p_vars.insert(p_vars.end(), vars.begin(), vars.begin() + lel);
+            }
+            p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
+            for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
+            p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
+            pend.back().count++;
+        }
+        return DDO_OK;
+    };
+    bool dual = eng->dual_enabled && cap >= 2;
+    for (int i : ov) if (widths[i] < 1) dual = false;
+    const int chunk = dual ? cap / 2 : cap;
+    std::vector<int> slot_wave;
+    for (size_t s0 = 0; s0 < ov.size(); s0 += (size_t)chunk) {
+        const int oc = (int)std::min<size_t>((size_t)chunk, ov.size() - s0);
         rc = stage_subset(&ov[s0], oc);
         if (rc != DDO_OK) return rc;
-        rc = eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
+        rc = dual ? eng->compile_dual(oc, lb0, cutoff_flag, &ms) : eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
         if (rc != DDO_OK) return rc;
         device_ms += ms;
-        rc = eng->fetch_ctl(oc);
+        rc = eng->fetch_ctl(dual ? 2 * oc : oc);
         if (rc != DDO_OK) return rc;
         for (int j = 0; j < oc; ++j) {
             const DDCtl& c = eng->h_ctl[j];
             Res& r = res[ov[s0 + j]];
             r.exact = c.lel < 0; r.has = c.has_best_exact != 0; r.best = c.best_exact_value;
             expanded += c.expanded; transitions += c.transitions; ++compilations;
+        }
+        if (dual) {
+            caps.assign(2 * oc, 0); lbs.assign(2 * oc, INT64_MAX);
+            slot_wave.assign(2 * oc, -1);
+            bool any = false;
+            for (int j = 0; j < oc; ++j) {
+                const DDCtl& c = eng->h_ctl[oc + j];
+                if (c.status == ST_WAITING) continue;  // the restricted DD never needed a cut: exact, no relaxation (parallel.rs:421-423)
+                const int wi = ov[s0 + j];
+                twins.push_back(TwinRes{wi, c.expanded, c.transitions, c.has_best_exact != 0, c.best_exact_value});
+                const bool exact = (c.lel < 0) || c.ebpo;
+                const int32_t rub = w_items[wi].ub;
+                caps[oc + j] = rub == INT32_MAX ? INT64_MAX : rub;
+                lbs[oc + j] = exact ? INT64_MAX : lb0;
+                slot_wave[oc + j] = wi;
+                any = any || !exact;
+            }
+            if (any) { rc = collect_drain(2 * oc, slot_wave); if (rc != DDO_OK) return rc; }
         }
     }
     {   // maybe_update_best in wave order (parallel.rs:446-453): the first DD reaching the new maximum keeps its solution
@@ -300,49 +355,37 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     // ---- 2. relaxation (parallel.rs:425-434) + enqueue_cutset (parallel.rs:456-469) ----------------------------------------------------
     if (!open.empty()) {
         const int64_t lb1 = best_lb;  // every relaxed DD of the wave is compiled against this snapshot
-        struct Pending { int wave_index, lel, first, count, pw; };
-        std::vector<Pending> pend;
-        p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
         int improver = -1;
-        std::vector<int64_t> caps, lbs;
-        std::vector<int32_t> vars;
-        for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
-            const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
-            rc = stage_subset(&open[s0], oc);
-            if (rc != DDO_OK) return rc;
-            rc = eng->compile_staged(oc, DDO_RELAXED, lb1, cutoff_flag, &ms);
-            if (rc != DDO_OK) return rc;
-            device_ms += ms;
-            rc = eng->fetch_ctl(oc);
-            if (rc != DDO_OK) return rc;
-            caps.assign(oc, 0); lbs.assign(oc, 0);
-            for (int j = 0; j < oc; ++j) {
-                const DDCtl& c = eng->h_ctl[j];
-                expanded += c.expanded; transitions += c.transitions; ++compilations;
-                if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; improver = open[s0 + j]; }
-                const bool exact = (c.lel < 0) || c.ebpo;
-                const int32_t rub = w_items[open[s0 + j]].ub;
-                caps[j] = rub == INT32_MAX ? INT64_MAX : rub;
-                lbs[j] = exact ? INT64_MAX : best_lb;  // a lower bound on the final filter; re-applied below once the wave is complete
+        if (dual && lb1 == lb0) {
+            // the twins were compiled against the right bound: adopt them, in wave order
+            for (const TwinRes& tw : twins) {
+                expanded += tw.expanded; transitions += tw.transitions; ++compilations;
+                if (tw.has && (int64_t)tw.best > best_lb) { best_lb = tw.best; improver = tw.wave_index; }
             }
-            int pw = 1;
-            const int total = eng->drain_all(oc, caps.data(), lbs.data(), &pw);
-            if (total < 0) return total;
-            int cur_dd = -1;
-            for (int r = 0; r < total; ++r) {
-                const int j = eng->h_out_dd[r];
-                if (j != cur_dd) {
-                    cur_dd = j;
-                    const int lel = eng->h_ctl[j].lel;
-                    rc = eng->fetch_vars(j, vars);
-                    if (rc != DDO_OK) return rc;
-                    pend.push_back(Pending{open[s0 + j], lel, (int)p_val.size(), 0, pw});
-                    p_vars.insert(p_vars.end(), vars.begin(), vars.begin() + lel);
+        } else {
+            pend.clear(); p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+            for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
+                const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
+                rc = stage_subset(&open[s0], oc);
+                if (rc != DDO_OK) return rc;
+                rc = eng->compile_staged(oc, DDO_RELAXED, lb1, cutoff_flag, &ms);
+                if (rc != DDO_OK) return rc;
+                device_ms += ms;
+                rc = eng->fetch_ctl(oc);
+                if (rc != DDO_OK) return rc;
+                caps.assign(oc, 0); lbs.assign(oc, 0); slot_wave.assign(oc, -1);
+                for (int j = 0; j < oc; ++j) {
+                    const DDCtl& c = eng->h_ctl[j];
+                    expanded += c.expanded; transitions += c.transitions; ++compilations;
+                    if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; improver = open[s0 + j]; }
+                    const bool exact = (c.lel < 0) || c.ebpo;
+                    const int32_t rub = w_items[open[s0 + j]].ub;
+                    caps[j] = rub == INT32_MAX ? INT64_MAX : rub;
+                    lbs[j] = exact ? INT64_MAX : best_lb;  // a lower bound on the final filter; re-applied below once the wave is complete
+                    slot_wave[j] = open[s0 + j];
                 }
-                p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
-                for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
-                p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
-                pend.back().count++;
+                rc = collect_drain(oc, slot_wave);
+                if (rc != DDO_OK) return rc;
             }
         }
         if (improver >= 0) { rc = take_solution(improver, DDO_RELAXED, lb1); if (rc != DDO_OK) return rc; }

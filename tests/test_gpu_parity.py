@@ -137,6 +137,24 @@ def test_small_dd_fast_path_equals_general_engine(monkeypatch):
     assert out[0][:4] == (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"])
 
 
+def test_dual_mode_fork_equals_sequential_restricted_then_relaxed(monkeypatch):
+    """Forking the relaxed twin on the device at the first cut of the restricted DD (dual mode) gives the same search as compiling the
+    two DDs one after the other; instance and widths chosen so that many sub-problems are inexact and the incumbent improves mid-wave."""
+    inst = gnp(110, 0.25, 23)
+    out = []
+    for dual in ("1", "0"):
+        monkeypatch.setenv("DDO_DUAL", dual)
+        s = ParNoCachingSolverLel(Misp(inst), FixedWidth(24), wave_size=48, batch_cap=32)
+        c = s.maximize()
+        st = s.stats()
+        out.append((c.best_value, c.is_exact, s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]),
+                    sorted(d.variable for d in s.best_solution() if d.value == 1)))
+    assert out[0] == out[1]
+    ref = O.OracleMisp(inst).solve("wave", k=48, width=24)
+    assert out[0][:6] == (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"])
+    assert out[0][7] == ref["solution"]
+
+
 def test_full_size_config2_root_dd_bit_exact():
     """BASELINE config 2 at full size: G(500, 0.5), W = 10 000 -- root restricted + relaxed DD against the oracle (a few seconds of CPU)."""
     inst = gnp(500, 0.5, 1)
