@@ -178,7 +178,7 @@ __device__ __forceinline__ int plan_find(const int* off, int count, int tile) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(256) k_expand(EV ev, int t, int count) {
+__global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
     constexpr int W32 = 2 * S;        // 32-bit words per state
@@ -414,9 +414,22 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
     const int per = (((ncand + NT - 1) / NT) + 3) & ~3;
     const int lo = min(tid * per, ncand), hi = min(lo + per, ncand);
 
+    // ---- B (issued first, consumed later). next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest
+    //      index on ties; the occurrence counts were accumulated by k_expand / k_init over the distinct states.
+    unsigned long long best = ~0ull;
+    {
+        const uint32_t* vh = ev.vhist + (size_t)vh_src * ev.HN;  // cleared by k_compact (a forking twin reads its primary's)
+        for (int i = tid; i < ev.n; i += NT) {
+            const unsigned c = __ldcg(vh + i);
+            if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i);
+        }
+    }
     // ---- A. canonical representative of every distinct state = its first candidate (rule C1) -----------------
     // claimers have cand_rep[c] == c; cand_first[c] is then the smallest candidate index with that state.  98 % of the time
-    // first == c and nothing moves (ukey / uinex alias cand_agg / cand_inex).
+    // first == c and nothing moves.  The "is canonical" flags live in the (not yet used) status array.
+    uint8_t* uniq = stat;
+    for (int c0 = lo; c0 < hi; c0 += 4) *reinterpret_cast<uint32_t*>(uniq + c0) = 0u;
+    __syncthreads();
     for (int c0 = lo; c0 < hi; c0 += 4) {
         const uint4 r4 = *reinterpret_cast<const uint4*>(ev.cand_rep + cb + c0);
         const uint4 f4 = *reinterpret_cast<const uint4*>(ev.cand_first + cb + c0);
@@ -426,53 +439,28 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
             const uint32_t c = (uint32_t)(c0 + j);
             if ((int)c < hi && rr[j] == c) {
                 const uint32_t f = ff[j];
-                ev.uflag[cb + f] = 1;
+                uniq[f] = 1;
                 if (f != c) { ev.cand_agg[cb + f] = ev.cand_agg[cb + c]; ev.cand_inex[cb + f] = ev.cand_inex[cb + c]; }
             }
         }
     }
     __syncthreads();
-    // ---- A'. ordered list of the distinct candidates + their 64-bit cut keys ------------------------------------
+    // ---- A'. ordered list of the distinct candidates ---------------------------------------------------------------
     int cnt = 0;
-    for (int c0 = lo; c0 < hi; c0 += 4) {
-        const uint32_t fl = *reinterpret_cast<const uint32_t*>(ev.uflag + cb + c0);
+    uint32_t myflags[8];  // unique flags of my chunk, 4 per word (per <= 32 covers 2 x Wcap <= 32768; longer chunks re-read shared memory)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cnt += (c0 + j < hi) && ((fl >> (8 * j)) & 0xff);
+    for (int q = 0; q < 8; ++q) myflags[q] = 0;
+    for (int c0 = lo, q = 0; c0 < hi; c0 += 4, ++q) {
+        uint32_t fl = *reinterpret_cast<const uint32_t*>(uniq + c0);
+        if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u;  // ignore flags beyond my chunk
+        if (q < 8) myflags[q] = fl;
+        cnt += __popc(fl & 0x01010101u);
     }
     int U;
-    const int off0 = block_excl_scan(cnt, &U, sm.scan);
+    const int off0 = block_excl_scan(cnt, &U, sm.scan);  // (its barriers also order the reads of `uniq` before `stat` is reused)
     if (U == 0) {  // every node was pruned: empty layer (clean.rs:667-669) -> no best node
         if (tid == 0) { ctl->status = ST_DONE; ctl->t_term = t; ctl->has_best = 0; ctl->has_best_exact = 0; ev.nlog[lb + t] = 0; atomicSub(ev.active, 1); }
         return;
-    }
-    const bool fits = U <= ev.Wcap * 2;  // always true; keys/stat are sized for 2*Wcap entries
-    (void)fits;
-    {
-        int off = off0;
-        for (int c0 = lo; c0 < hi; c0 += 4) {
-            const uint32_t fl = *reinterpret_cast<const uint32_t*>(ev.uflag + cb + c0);
-            if (!fl) continue;
-            unsigned long long ag[4]; uint32_t rk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if ((c0 + j < hi) && ((fl >> (8 * j)) & 0xff)) { ag[j] = ev.cand_agg[cb + c0 + j]; rk[j] = ev.cand_rank[cb + c0 + j]; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if ((c0 + j < hi) && ((fl >> (8 * j)) & 0xff)) {
-                ev.ulist[cb + off] = (uint32_t)(c0 + j);
-                keys[off] = (ag[j] & 0xFFFFFFFF00000000ull) | rk[j];  // (value_top, popcount, 20 lexicographic bits)
-                ++off;
-            }
-        }
-    }
-
-    // ---- B. next_variable (misp/main.rs:109-143): vertex occurring in the fewest states, lowest index on ties.
-    //         The occurrence counts were accumulated by k_expand / k_init over the distinct states.
-    unsigned long long best = ~0ull;
-    {
-        const uint32_t* vh = ev.vhist + (size_t)vh_src * ev.HN;  // cleared by k_compact (a forking twin reads its primary's)
-        for (int i = tid; i < ev.n; i += NT) {
-            const unsigned c = __ldcg(vh + i);
-            if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i);
-        }
     }
     best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, sm.red64);
     const bool terminal = best == ~0ull;  // next_variable == None: the layer is the terminal layer (clean.rs:350,608-632)
@@ -489,8 +477,29 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
         if (tid == 0) { ctl->status = ST_DONE; ctl->overflow = 1; ctl->t_term = t; atomicSub(ev.active, 1); }
         return;
     }
-    // stat[ui]: 0 undecided, 1 keep, 2 drop
-    for (int ui = tid; ui < U; ui += NT) stat[ui] = cut ? 0 : 1;
+    {   // my distinct candidates, in order: list them; when a cut is needed also build the 64-bit keys and reset the status bytes
+        int off = off0;
+        for (int c0 = lo, q = 0; c0 < hi; c0 += 4, ++q) {
+            uint32_t fl;
+            if (q < 8) fl = myflags[q];
+            else { fl = *reinterpret_cast<const uint32_t*>(uniq + c0); if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u; }
+            if (!fl) continue;
+            unsigned long long ag[4] = {0, 0, 0, 0}; uint32_t rk[4] = {0, 0, 0, 0};
+            if (cut) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) { ag[j] = ev.cand_agg[cb + c0 + j]; rk[j] = ev.cand_rank[cb + c0 + j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) {
+                ev.ulist[cb + off] = (uint32_t)(c0 + j);
+                if (cut) keys[off] = (ag[j] & 0xFFFFFFFF00000000ull) | rk[j];  // (value_top, popcount, 20 lexicographic bits)
+                ++off;
+            }
+        }
+    }
+    // stat[ui]: 0 undecided, 1 keep, 2 drop   (long chunks, q >= 8, still read `uniq` above: keep the barrier before overwriting it)
+    __syncthreads();
+    if (cut) for (int ui = tid; ui < U; ui += NT) stat[ui] = 0;
     __syncthreads();
     if (cut) {
         int nactive = U;
@@ -546,13 +555,24 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
     }
 
     // ---- D. stable positions of the survivors (rule C3): every thread places the distinct candidates of its own chunk ----
-    int kc = 0;
-    for (int i = 0; i < cnt; ++i) kc += (stat[off0 + i] == 1);
-    int nkeep;
-    int kp = block_excl_scan(kc, &nkeep, sm.scan);
-    for (int i = 0; i < cnt; ++i) {
-        const uint32_t c = ev.ulist[cb + off0 + i];
-        if (stat[off0 + i] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
+    int nkeep, kp;
+    if (cut) {
+        int kc = 0;
+        for (int i = 0; i < cnt; ++i) kc += (stat[off0 + i] == 1);
+        kp = block_excl_scan(kc, &nkeep, sm.scan);
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t c = ev.ulist[cb + off0 + i];
+            if (stat[off0 + i] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
+        }
+    } else {  // no cut: every distinct candidate survives at its rank in the ordered list
+        nkeep = U; kp = off0;
+        for (int c0 = lo, q = 0; c0 < hi; c0 += 4, ++q) {
+            uint32_t fl;
+            if (q < 8) fl = myflags[q];
+            else { fl = *reinterpret_cast<const uint32_t*>(uniq + c0); if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u; }  // `uniq` is intact: no cut
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) { ev.pos_of[cb + c0 + j] = (uint32_t)kp++; ev.uflag[cb + c0 + j] = 2; }
+        }
     }
     int n_next = nkeep;
     int s_pos = -1, r_pos = -1;
