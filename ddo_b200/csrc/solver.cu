@@ -38,7 +38,6 @@ int NoDupFringe::compare_new(int32_t ub, int32_t value, int16_t pc, const uint64
     if (pc != popc_[b]) return pc < popc_[b] ? -1 : 1;  // misp/main.rs:205-208
     return lex_cmp(st, state(b), W);
 }
-int NoDupFringe::compare(int a, int b) const { return compare_new(items_[a].ub, items_[a].value, popc_[a], state(a), b); }
 
 static inline uint64_t lex_word_host(uint64_t w) {  // ~bitreverse: larger = Greater in BitSet::cmp among equal popcounts
     w = ((w >> 1) & 0x5555555555555555ull) | ((w & 0x5555555555555555ull) << 1);
@@ -46,29 +45,33 @@ static inline uint64_t lex_word_host(uint64_t w) {  // ~bitreverse: larger = Gre
     w = ((w >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((w & 0x0F0F0F0F0F0F0F0Full) << 4);
     return ~__builtin_bswap64(w);
 }
-NoDupFringe::HeapEnt NoDupFringe::make_ent(int id) const {
+NoDupFringe::Ent NoDupFringe::make_ent(int id) const {
     const Item& it = items_[id];
-    HeapEnt e;
+    Ent e;
     e.k1 = ((uint64_t)((uint32_t)it.ub ^ 0x80000000u) << 32) | ((uint32_t)it.value ^ 0x80000000u);
     e.k2 = ((uint64_t)(uint16_t)popc_[id] << 48) | (lex_word_host(state(id)[0]) >> 16);
-    e.id = id;
+    e.id = id; e.ver = ver_[id];
     return e;
 }
-bool NoDupFringe::ent_less(const HeapEnt& a, const HeapEnt& b) const {
+bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
     if (a.k1 != b.k1) return a.k1 < b.k1;
     if (a.k2 != b.k2) return a.k2 < b.k2;
+    if (a.id == b.id) return a.ver < b.ver;
     return lex_cmp(state(a.id), state(b.id), W) < 0;  // same ub, value, popcount and 48 leading lexicographic bits
 }
 
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
-    states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); pos_.clear(); heap_.clear(); recycle_.clear();
+    states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); ver_.clear(); recycle_.clear();
+    pending_.clear(); runs_.clear(); live_ = 0;
     table_.clear(); table_used_ = 0;
 }
 void NoDupFringe::rehash(size_t min_cap) {
     size_t cap = 1024;
     while (cap < min_cap) cap <<= 1;
+    std::vector<int> old;
+    old.swap(table_);
     table_.assign(cap, -1); table_used_ = 0;
-    for (const HeapEnt& e : heap_) table_insert(e.id);
+    for (int id : old) if (id >= 0) table_insert(id);
 }
 void NoDupFringe::table_insert(int id) {
     const size_t mask = table_.size() - 1;
@@ -94,54 +97,28 @@ void NoDupFringe::table_erase(int id) {
     while (table_[s] != id) s = (s + 1) & mask;
     table_[s] = -2;
 }
-void NoDupFringe::bubble_up(int id) {  // no_duplicate.rs:227-242
-    size_t me = (size_t)pos_[id];
-    const HeapEnt e = heap_[me];
-    while (me != 0) {
-        const size_t par = (me - 1) / 2;
-        if (!ent_less(heap_[par], e)) break;
-        heap_[me] = heap_[par]; pos_[heap_[me].id] = (int)me;
-        me = par;
-    }
-    heap_[me] = e; pos_[id] = (int)me;
-}
-void NoDupFringe::bubble_down(int id) {  // no_duplicate.rs:244-259,279-295
-    size_t me = (size_t)pos_[id];
-    const HeapEnt e = heap_[me];
-    const size_t size = heap_.size();
-    for (;;) {
-        const size_t left = me * 2 + 1, right = left + 1;
-        if (left >= size) break;
-        size_t kid = left;
-        if (right < size && !ent_less(heap_[right], heap_[left])) kid = right;  // max_child_of: the right child wins ties (:291-294)
-        if (!ent_less(e, heap_[kid])) break;
-        heap_[me] = heap_[kid]; pos_[heap_[me].id] = (int)me;
-        me = kid;
-    }
-    heap_[me] = e; pos_[id] = (int)me;
-}
 void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
     const uint64_t h = hash_state(st, W);
     const int found = table_find(st, h);
-    if (found >= 0) {  // Occupied, no_duplicate.rs:92-118
+    if (found >= 0) {  // Occupied, no_duplicate.rs:92-118: keep the longer path, ub = max of the known ubs
         const int id = found;
         const int32_t old_lp = items_[id].value, old_ub = items_[id].ub;
         const int32_t merged_ub = std::max(ub, old_ub);
-        const bool up = compare_new(merged_ub, value, popc_[id], st, id) > 0;
+        bool changed = false;
         if (value > old_lp) {
             items_[id] = Item{value, merged_ub, depth, rec};
             std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
             std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
+            changed = true;
         }
-        if (ub > old_ub) items_[id].ub = ub;
-        heap_[pos_[id]] = make_ent(id);  // the key stored in the heap follows the node
-        if (up) bubble_up(id);
+        if (ub > old_ub) { items_[id].ub = ub; changed = true; }
+        if (changed) { ++ver_[id]; pending_.push_back(make_ent(id)); }  // re-keyed: the old entry goes stale
         return;
     }
     int id;  // Vacant, no_duplicate.rs:119-135
     if (recycle_.empty()) {
         id = (int)items_.size();
-        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); pos_.push_back(0);
+        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
         states_.resize(states_.size() + W); bits_.resize(bits_.size() + PW);
     } else { id = recycle_.back(); recycle_.pop_back(); }
     items_[id] = Item{value, ub, depth, rec};
@@ -151,19 +128,44 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     int pc = 0;
     for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
     popc_[id] = (int16_t)pc; hash_[id] = h;
-    heap_.push_back(make_ent(id));
-    pos_[id] = (int)heap_.size() - 1;
-    if ((table_used_ + 1) * 2 > table_.size()) rehash(heap_.size() * 4);  // re-inserts every live node, `id` included
-    else table_insert(id);
-    bubble_up(id);
+    ++ver_[id];
+    if ((table_used_ + 1) * 2 > table_.size()) rehash((live_ + 1) * 4);
+    table_insert(id);
+    pending_.push_back(make_ent(id));
+    ++live_;
+}
+void NoDupFringe::flush_pending() {
+    if (pending_.empty()) return;
+    std::sort(pending_.begin(), pending_.end(), [this](const Ent& a, const Ent& b) { return ent_less(a, b); });
+    runs_.emplace_back();
+    runs_.back().swap(pending_);
+    if (runs_.size() > 24) {  // keep the number of runs bounded: merge everything, dropping stale entries
+        std::vector<Ent> all;
+        size_t total = 0;
+        for (auto& r : runs_) total += r.size();
+        all.reserve(total);
+        for (auto& r : runs_) for (const Ent& e : r) if (e.ver == ver_[e.id]) all.push_back(e);
+        std::sort(all.begin(), all.end(), [this](const Ent& a, const Ent& b) { return ent_less(a, b); });
+        runs_.clear();
+        runs_.push_back(std::move(all));
+    }
 }
 int NoDupFringe::pop() {
-    if (heap_.empty()) return -1;
-    const int id = heap_[0].id;
-    heap_[0] = heap_.back(); heap_.pop_back();
-    if (!heap_.empty()) { pos_[heap_[0].id] = 0; bubble_down(heap_[0].id); }
+    if (live_ == 0) return -1;
+    flush_pending();
+    int best_run = -1;
+    for (size_t r = 0; r < runs_.size(); ++r) {
+        auto& run = runs_[r];
+        while (!run.empty() && run.back().ver != ver_[run.back().id]) run.pop_back();  // stale
+        if (run.empty()) continue;
+        if (best_run < 0 || ent_less(runs_[best_run].back(), run.back())) best_run = (int)r;
+    }
+    const int id = runs_[best_run].back().id;
+    runs_[best_run].pop_back();
+    ++ver_[id];  // any other entry of this node is now stale
     recycle_.push_back(id);
     table_erase(id);
+    --live_;
     return id;
 }
 // ---------------------------------------------------------------------------------------------------------------

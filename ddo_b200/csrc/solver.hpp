@@ -26,8 +26,8 @@ class NoDupFringe {
 public:
     NoDupFringe(int words, int pw) : W(words), PW(pw) {}
     struct Item { int32_t value, ub, depth, rec; };
-    size_t len() const { return heap_.size(); }
-    bool empty() const { return heap_.empty(); }
+    size_t len() const { return live_; }
+    bool empty() const { return live_ == 0; }
     void clear();
     // no_duplicate.rs:88-140
     void push(const uint64_t* state, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words);
@@ -37,24 +37,27 @@ public:
     const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
     const Item& item(int id) const { return items_[id]; }
 private:
+    // Priority structure: the reference's updatable binary heap (no_duplicate.rs:206-323) pops in the MaxUB order, a strict total order
+    // for MISP (ub, value, then MispRanking on distinct states).  Pushes arrive in bursts (the cutsets of a wave) and pops in bursts (the
+    // next wave), so the same order is served by sorted runs: a burst of pushes is sorted once into a new run, a pop takes the largest of
+    // the runs' tails.  An entry is stale when its node was popped or re-keyed since (version mismatch) and is skipped.
+    struct Ent { uint64_t k1, k2; int id; uint32_t ver; };
     int W, PW;
     std::vector<uint64_t> states_, bits_;
     std::vector<Item> items_;
     std::vector<int16_t> popc_;
     std::vector<uint64_t> hash_;
-    // the heap stores the ordering key inline (MaxUB: ub, value; MispRanking: popcount, first lexicographic word) so that sift operations
-    // rarely touch the node storage; full ties fall back to the state comparison
-    struct HeapEnt { uint64_t k1, k2; int id; };
-    std::vector<HeapEnt> heap_;
-    std::vector<int> pos_, recycle_;
-    HeapEnt make_ent(int id) const;
-    bool ent_less(const HeapEnt& a, const HeapEnt& b) const;  // a strictly below b in the MaxUB order
+    std::vector<uint32_t> ver_;
+    std::vector<int> recycle_;
+    std::vector<Ent> pending_;
+    std::vector<std::vector<Ent>> runs_;
+    size_t live_ = 0;
     std::vector<int> table_;  // open addressing: node id or -1 (empty) / -2 (tombstone)
     size_t table_used_ = 0;   // occupied + tombstones
-    int compare(int a, int b) const;  // MaxUB: ub, value, MispRanking
+    Ent make_ent(int id) const;
+    bool ent_less(const Ent& a, const Ent& b) const;  // a strictly below b in the MaxUB order
     int compare_new(int32_t ub, int32_t value, int16_t pc, const uint64_t* st, int b) const;
-    void bubble_up(int id);
-    void bubble_down(int id);
+    void flush_pending();
     void table_insert(int id);
     int table_find(const uint64_t* st, uint64_t h) const;
     void table_erase(int id);
