@@ -239,7 +239,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         E->prof_mark(2);
         k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(0);
-        g_kernel_launches += 3;
+        g_kernel_launches += 3; ++E->layer_steps;
         if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {
             E->bytes_d2h += sizeof(int); CUDA_TRY(cudaMemcpyAsync(E->h_active, ev.active, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));

@@ -124,6 +124,7 @@ struct Engine {
     uint64_t* h_out_state = nullptr; int32_t* h_out_val = nullptr; int32_t* h_out_ub = nullptr; int32_t* h_out_dd = nullptr; uint64_t* h_out_path = nullptr;
     int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false;
     size_t bytes_allocated = 0;
+    unsigned long long layer_steps = 0;  // layer steps (k_finish + k_compact + k_expand) launched so far
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;  // traffic over PCIe / NVLink-C2C issued by this engine
     // optional per-kernel timing
     bool profiling = false;

@@ -2,6 +2,8 @@
 #include "solver.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ddo {
@@ -172,7 +174,9 @@ int NoDupFringe::pop() {
 // Solver
 // ---------------------------------------------------------------------------------------------------------------
 Solver::Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws)
-    : model(m), eng(e), width_kind(wk), width(w), wave_size(ws), fringe(m->words, (m->n + 63) / 64) {}
+    : model(m), eng(e), width_kind(wk), width(w), wave_size(ws), fringe(m->words, (m->n + 63) / 64) {
+    if (const char* p = std::getenv("DDO_WAVE_TRACE")) trace_file = std::fopen(p, "w");
+}
 
 int Solver::init(bool push_root) {  // parallel.rs:368-385
     fringe.clear(); recs.clear();
@@ -228,6 +232,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const int64_t lb0 = best_lb;  // every restricted DD of the wave is compiled against this snapshot
     float ms = 0;
     int rc;
+    double tr_small = 0, tr_general = 0; const uint64_t tr_steps0 = eng->layer_steps, tr_exp0 = expanded;  // DDO_WAVE_TRACE (diagnostics only)
     const int cap = eng->K;  // DDs the general engine compiles in lock-step
     std::vector<uint64_t> w2, s2; std::vector<int64_t> v2; std::vector<int32_t> d2;
     auto stage_subset = [&](const int* idx, int oc) -> int {
@@ -264,7 +269,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         if (rc != DDO_OK) return rc;
         rc = eng->compile_small(cnt, lb0, &ms);
         if (rc != DDO_OK) return rc;
-        device_ms += ms;
+        device_ms += ms; tr_small += ms;
         for (int i = 0; i < cnt; ++i) {
             const SmallOut& o = eng->h_small[i];
             if (o.status != 0) { ov.push_back(i); continue; }
@@ -318,7 +323,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         if (rc != DDO_OK) return rc;
         rc = dual ? eng->compile_dual(oc, lb0, cutoff_flag, &ms) : eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
         if (rc != DDO_OK) return rc;
-        device_ms += ms;
+        device_ms += ms; tr_general += ms;
         rc = eng->fetch_ctl(dual ? 2 * oc : oc);
         if (rc != DDO_OK) return rc;
         for (int j = 0; j < oc; ++j) {
@@ -372,7 +377,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 if (rc != DDO_OK) return rc;
                 rc = eng->compile_staged(oc, DDO_RELAXED, lb1, cutoff_flag, &ms);
                 if (rc != DDO_OK) return rc;
-                device_ms += ms;
+                device_ms += ms; tr_general += ms;
                 rc = eng->fetch_ctl(oc);
                 if (rc != DDO_OK) return rc;
                 caps.assign(oc, 0); lbs.assign(oc, 0); slot_wave.assign(oc, -1);
@@ -409,6 +414,9 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
         fringe_ms += now_ms() - t0;
     }
+    if (trace_file)
+        std::fprintf(trace_file, "%llu %d %zu %zu %.3f %.3f %llu %llu %zu\n", (unsigned long long)waves, cnt, ov.size(), open.size(), tr_small, tr_general,
+                     (unsigned long long)(eng->layer_steps - tr_steps0), (unsigned long long)(expanded - tr_exp0), fringe.len());
     out3[0] = best_lb;
     out3[2] = fringe.empty() ? 0 : 1;
     return DDO_OK;

@@ -8,6 +8,7 @@
 #pragma once
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <vector>
 
 #include "engine.hpp"
@@ -75,6 +76,7 @@ struct Solver {
     bool aborted = false;
     uint64_t explored = 0, expanded = 0, transitions = 0, compilations = 0, waves = 0;
     double device_ms = 0, fringe_ms = 0;
+    FILE* trace_file = nullptr;  // DDO_WAVE_TRACE=<path>: one line per wave (wave, popped, general DDs, inexact, small ms, general ms, layer steps, expanded, fringe)
     // scratch of one wave (kept to avoid reallocations)
     std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars;
 

@@ -145,3 +145,80 @@ def random_knapsack(n: int, seed: int) -> KnapsackInstance:
     profit = np.array([1 + rng.next() % 1000 for _ in range(n)], dtype=np.int64)
     weight = np.array([1 + rng.next() % 1000 for _ in range(n)], dtype=np.int64)
     return KnapsackInstance(int(weight.sum() // 2), profit, weight, f"kp_{n}_{seed}")
+
+
+@dataclass
+class Max2SatInstance:
+    """A weighted MAX2SAT instance: ``clauses`` is int64[m, 3] = (weight, literal x, literal y); the literal of variable i (0-based) is
+    +-(i + 1); x == y encodes a unit clause.  Duplicated clauses keep the LAST weight (the reference inserts into a hash map,
+    ddo/examples/max2sat/data.rs:99,106)."""
+
+    n: int
+    clauses: np.ndarray
+    name: str = ""
+    words: int = field(init=False)
+
+    def __post_init__(self):
+        self.words = (self.n + 1) // 2  # int32 benefits packed two per uint64 word at the ABI
+        self.clauses = np.ascontiguousarray(self.clauses, dtype=np.int64).reshape(-1, 3)
+
+    def initial_state(self) -> np.ndarray:
+        return np.zeros(self.words, dtype=np.uint64)  # model.rs:259-264: all benefits zero
+
+    def to_wcnf(self) -> str:
+        lines = [f"p wcnf {self.n} {len(self.clauses)}"]
+        for w, x, y in self.clauses.tolist():
+            lines.append(f"{w} {x} 0" if x == y else f"{w} {x} {y} 0")
+        return "\n".join(lines) + "\n"
+
+
+_WC_COMMENT = re.compile(r"^c\s.*$")
+_WC_PB = re.compile(r"^p\s+wcnf\s+(?P<vars>\d+)\s+(?P<clauses>\d+)")
+_WC_BIN = re.compile(r"^(?P<w>-?\d+)\s+(?P<x>-?\d+)\s+(?P<y>-?\d+)\s+0")
+_WC_UNIT = re.compile(r"^(?P<w>-?\d+)\s+(?P<x>-?\d+)-?\s+0")
+
+
+def parse_wcnf(text: str, name: str = "") -> Max2SatInstance:
+    """Same grammar as the reference's reader (ddo/examples/max2sat/data.rs:66-110): the four regular expressions are tried in the same
+    order; lines matching none of them are ignored."""
+    n = 0
+    clauses = []
+    for raw in text.splitlines():
+        line = raw.strip()
+        if not line or _WC_COMMENT.match(line):
+            continue
+        m = _WC_PB.match(line)
+        if m:
+            n = int(m.group("vars"))
+            continue
+        m = _WC_BIN.match(line)
+        if m:
+            clauses.append((int(m.group("w")), int(m.group("x")), int(m.group("y"))))
+            continue
+        m = _WC_UNIT.match(line)
+        if m:
+            clauses.append((int(m.group("w")), int(m.group("x")), int(m.group("x"))))
+            continue
+    return Max2SatInstance(n, np.array(clauses, dtype=np.int64).reshape(-1, 3), name)
+
+
+def read_wcnf(path: str) -> Max2SatInstance:
+    with open(path) as f:
+        return parse_wcnf(f.read(), name=str(path))
+
+
+def random_max2sat(n: int, m: int, seed: int, max_weight: int = 10) -> Max2SatInstance:
+    """The synthetic family of BASELINE.json config 3: m clauses over two distinct uniform variables, each literal
+    negated with probability 1/2, integer weight uniform in [1, max_weight]; SplitMix64(seed)."""
+    rng = SplitMix64(seed)
+    clauses = []
+    for _ in range(m):
+        a = rng.next() % n
+        b = rng.next() % (n - 1)
+        if b >= a:
+            b += 1
+        x = (a + 1) * (-1 if rng.next() & 1 else 1)
+        y = (b + 1) * (-1 if rng.next() & 1 else 1)
+        w = 1 + rng.next() % max_weight
+        clauses.append((w, x, y))
+    return Max2SatInstance(n, np.array(clauses, dtype=np.int64), f"max2sat_{n}_{m}_{seed}")

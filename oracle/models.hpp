@@ -205,6 +205,168 @@ struct KPDominance : Dominance<KnapsackState> {  // :193-218
 };
 
 // ---------------------------------------------------------------------------
+// MAX2SAT (BASELINE config 3).  examples/max2sat/model.rs:29-348, relax.rs:43-89, heuristics.rs:30-37, data.rs:31-110
+// State = depth + marginal benefit of assigning True to every variable (model.rs:59-62).
+// Canonical choices where the reference leaves the outcome to an unstable sort / heap layout (SURVEY hard part 2):
+//   * variable order: model.rs:149-151 sorts unstably by the sum of clause weights -> here stable (ties by variable id);
+//   * ranking: heuristics.rs:33-37 compares rank() = sum |benefit| only; ties are refined by (depth, lexicographic benefits as
+//     signed integers, ascending variable id), which makes the cut and the fringe order a function of the states alone.
+// ---------------------------------------------------------------------------
+struct M2State { size_t depth; std::vector<isize> sub; };
+struct M2Hash {
+    size_t operator()(const M2State& s) const {
+        uint64_t h = (uint64_t)s.depth * 0x9E3779B97F4A7C15ull;
+        for (isize x : s.sub) h = ((h << 5 | h >> 59) ^ (uint64_t)x) * 0x517cc1b727220a95ull;
+        return (size_t)h;
+    }
+};
+struct M2Eq { bool operator()(const M2State& a, const M2State& b) const { return a.depth == b.depth && a.sub == b.sub; } };
+constexpr isize M2_T = 1, M2_F = -1;  // model.rs:30-32
+struct M2Clause { isize w, x, y; };   // weight, literals (x == y: unit clause); literal of variable i (0-based) is +-(i+1)
+
+struct Max2Sat : Problem<M2State> {  // model.rs:98-349
+    size_t nb_vars;
+    isize initial = 0;
+    std::vector<isize> weights;  // (2n)^2 table, model.rs:141
+    std::vector<isize> sum_of_clause_weights;
+    std::vector<size_t> order;   // vars_by_sum_of_clause_weights
+    std::vector<isize> nk, estimates;
+    static size_t mk_lit(isize x) { size_t a = (size_t)((x < 0 ? -x : x) - 1); return a + a + (x > 0 ? 1 : 0); }  // model.rs:116-121
+    size_t offset(isize x, isize y) const { isize a = std::min(x, y), b = std::max(x, y); return mk_lit(a) * 2 * nb_vars + mk_lit(b); }  // :165-170
+    isize weight(isize x, isize y) const { return weights[offset(x, y)]; }
+    static isize t(size_t v) { return (isize)v + 1; }
+    static isize f(size_t v) { return -((isize)v + 1); }
+    static isize pos(isize x) { return x > 0 ? x : 0; }
+
+    // data.rs:99,106: `weights.insert(BinaryClause::new(x, y), w)` -- a repeated clause keeps the LAST weight.  The reference then iterates
+    // the hash map (model.rs:136); every per-clause effect below is order independent once duplicates are resolved.
+    Max2Sat(size_t n, const std::vector<M2Clause>& clauses) : nb_vars(n), weights(4 * n * n, 0), sum_of_clause_weights(n, 0), order(n) {
+        std::vector<M2Clause> uniq;
+        std::unordered_map<uint64_t, size_t> seen;
+        for (const M2Clause& c : clauses) {
+            isize a = std::min(c.x, c.y), b = std::max(c.x, c.y);
+            uint64_t key = (uint64_t)mk_lit(a) * 2 * n + mk_lit(b);
+            auto it = seen.find(key);
+            if (it == seen.end()) { seen.emplace(key, uniq.size()); uniq.push_back(M2Clause{c.w, a, b}); }
+            else uniq[it->second].w = c.w;
+        }
+        for (const M2Clause& c : uniq) {  // model.rs:136-147
+            weights[offset(c.x, c.y)] = c.w;
+            sum_of_clause_weights[(size_t)((c.x < 0 ? -c.x : c.x) - 1)] += c.w;
+            if (c.x != c.y) sum_of_clause_weights[(size_t)((c.y < 0 ? -c.y : c.y) - 1)] += c.w;
+            if (c.x == -c.y) initial += c.w;
+        }
+        for (size_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return sum_of_clause_weights[a] < sum_of_clause_weights[b]; });  // :149-151
+        estimates.assign(n, 0); nk.assign(n, 0);
+        // precompute_estimate(k), model.rs:204-238, as a suffix sum: estimate(k) = estimate(k+1) + terms of i = k
+        isize acc = 0;
+        for (size_t i = n; i-- > 0;) {
+            size_t vi = order[i];
+            for (size_t j = i + 1; j < n; ++j) {
+                size_t vj = order[j];
+                isize tt = weight(t(vi), t(vj)), tf = weight(t(vi), f(vj)), ft = weight(f(vi), t(vj)), ff = weight(f(vi), f(vj));
+                isize wtt = tt + tf + ft, wtf = tt + tf + ff, wft = tt + ft + ff, wff = tf + ft + ff;
+                acc += std::max(std::max(wtt, wtf), std::max(wft, wff));
+            }
+            acc += weight(t(vi), f(vi)) + std::max(weight(t(vi), t(vi)), weight(f(vi), f(vi)));
+            estimates[i] = acc;
+        }
+        for (size_t k = 0; k < n; ++k) {  // precompute_nk, model.rs:190-197
+            isize sum = 0;
+            for (size_t i = 0; i < k; ++i) sum += weight(t(order[i]), f(order[i]));
+            nk[k] = sum;
+        }
+    }
+    isize fast_upper_bound(const M2State& state) const {  // model.rs:240-249
+        isize mb = 0;
+        for (isize b : state.sub) mb += b < 0 ? -b : b;
+        return mb + estimates[state.depth] - initial + nk[state.depth];
+    }
+    size_t nb_variables() const override { return nb_vars; }
+    M2State initial_state() const override { return M2State{0, std::vector<isize>(nb_vars, 0)}; }
+    isize initial_value() const override { return initial; }
+    void for_each_in_domain(Variable v, const M2State&, const DecisionCallback& cb) const override {  // :270-273
+        cb(Decision{v.id, M2_T}); cb(Decision{v.id, M2_F});
+    }
+    M2State transition(const M2State& state, Decision d) const override {  // :275-292
+        size_t k = d.variable;
+        M2State ret = state;
+        ret.depth += 1;
+        ret.sub[k] = 0;
+        size_t nrem = nb_vars - (state.depth + 1);  // varset(), :173-181
+        if (d.value == M2_F) for (size_t i = 0; i < nrem; ++i) { size_t l = order[i]; ret.sub[l] += weight(t(k), t(l)) - weight(t(k), f(l)); }
+        else for (size_t i = 0; i < nrem; ++i) { size_t l = order[i]; ret.sub[l] += weight(f(k), t(l)) - weight(f(k), f(l)); }
+        return ret;
+    }
+    isize transition_cost(const M2State& state, const M2State&, Decision d) const override {  // :294-328
+        size_t k = d.variable;
+        size_t nrem = nb_vars - (state.depth + 1);
+        if (d.value == M2_F) {
+            isize res = pos(-state.sub[k]);
+            isize sum = weight(f(k), f(k));
+            for (size_t i = 0; i < nrem; ++i) {
+                size_t l = order[i];
+                isize wff = weight(f(k), f(l)), wft = weight(f(k), t(l)), wtt = weight(t(k), t(l)), wtf = weight(t(k), f(l));
+                sum += (wff + wft) + std::min(pos(state.sub[l]) + wtt, pos(-state.sub[l]) + wtf);
+            }
+            return res + sum;
+        }
+        isize res = pos(state.sub[k]);
+        isize sum = weight(t(k), t(k));
+        for (size_t i = 0; i < nrem; ++i) {
+            size_t l = order[i];
+            isize wtt = weight(t(k), t(l)), wtf = weight(t(k), f(l)), wff = weight(f(k), f(l)), wft = weight(f(k), t(l));
+            sum += (wtf + wtt) + std::min(pos(state.sub[l]) + wft, pos(-state.sub[l]) + wff);
+        }
+        return res + sum;
+    }
+    std::optional<Variable> next_variable(size_t, const std::vector<const M2State*>& next_layer) const override {  // :330-348
+        if (next_layer.empty()) return std::nullopt;
+        size_t depth = next_layer[0]->depth;
+        if (depth < nb_vars) return Variable{order[nb_vars - depth - 1]};
+        return std::nullopt;
+    }
+};
+struct Max2SatRelax : Relaxation<M2State> {  // relax.rs:43-89
+    const Max2Sat* pb;
+    explicit Max2SatRelax(const Max2Sat* p) : pb(p) {}
+    M2State merge(const std::vector<const M2State*>& states) const override {  // :46-77
+        std::vector<isize> benefits(pb->nb_vars, 0);
+        for (size_t v = 0; v < pb->nb_vars; ++v) {
+            isize sign = 0, min_benef = ISIZE_MAX; bool same = true;
+            for (const M2State* st : states) {
+                isize x = st->sub[v], ax = x < 0 ? -x : x;
+                min_benef = std::min(min_benef, ax);
+                if (sign == 0 && x != 0) sign = ax / x;
+                else if (sign * x < 0) { same = false; break; }
+            }
+            if (same) benefits[v] = sign * min_benef;
+        }
+        return M2State{states[0]->depth, std::move(benefits)};
+    }
+    isize relax(const M2State&, const M2State& dst, const M2State& relaxed, Decision, isize cost) const override {  // :78-84
+        isize rc = cost;
+        for (size_t v = 0; v < pb->nb_vars; ++v) {
+            isize a = dst.sub[v], b = relaxed.sub[v];
+            rc += (a < 0 ? -a : a) - (b < 0 ? -b : b);
+        }
+        return rc;
+    }
+    isize fast_upper_bound(const M2State& s) const override { return pb->fast_upper_bound(s); }  // :86-88
+};
+struct Max2SatRanking : StateRanking<M2State> {  // heuristics.rs:30-37 (+ canonical refinement of ties, see above)
+    static isize rank(const M2State& s) { isize r = 0; for (isize x : s.sub) r += x < 0 ? -x : x; return r; }  // model.rs:77-81
+    int compare(const M2State& a, const M2State& b) const override {
+        isize ra = rank(a), rb = rank(b);
+        if (ra != rb) return ra < rb ? -1 : 1;
+        if (a.depth != b.depth) return a.depth < b.depth ? -1 : 1;
+        for (size_t v = 0; v < a.sub.size(); ++v) if (a.sub[v] != b.sub[v]) return a.sub[v] < b.sub[v] ? -1 : 1;
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Fixtures of the reference's unit tests (clean.rs:2552-2667)
 // ---------------------------------------------------------------------------
 struct DummyState { isize value; size_t depth; };

@@ -10,39 +10,67 @@
 using namespace ddo_oracle;
 
 namespace {
-using MispMdd = Mdd<BitState, BitStateHash, BitStateEq>;
-using MispFringe = NoDupFringe<BitState, BitStateHash, BitStateEq>;
-
+// ---- model adapters: everything the generic entry points need to know about a model -------------------------------------------
 struct MispHandle {
+    using State = BitState; using Hash = BitStateHash; using Eq = BitStateEq;
     Misp pb;
     MispRelax rlx;
     MispRanking rk;
     MispHandle(size_t n, const isize* w, size_t m, const int32_t* s, const int32_t* d) : pb(n, w, m, s, d), rlx(&pb) {}
+    size_t abi_words() const { return pb.words; }  // uint64 words of a packed state at the ABI
+    State state_from_abi(const uint64_t* p, size_t /*depth*/) const { BitState s; s.w.assign(p, p + pb.words); return s; }
+    void state_to_abi(const State& s, uint64_t* p) const { std::memcpy(p, s.w.data(), pb.words * 8); }
 };
-struct MispDD {
-    MispHandle* h;
-    MispMdd mdd;
-    std::vector<SubProblem<BitState>> cutset;  // drained copy
-    SubProblem<BitState> root;
-    MispDD(MispHandle* h_, int cutset_type) : h(h_), mdd(cutset_type) {}
-};
-struct MispStepper {
-    MispHandle* h;
-    FixedWidth<BitState> fw; NbUnassignedWidth<BitState> nw; NoCutoff nocut; EmptyDominanceChecker<BitState> dom; EmptyCache<BitState> cache;
-    MaxUB<BitState> mx; MispFringe fringe;
-    std::unique_ptr<WaveSolver<BitState, BitStateHash, BitStateEq>> solver;
-    MispStepper(MispHandle* h_, int k, int width_kind, uint64_t width)
-        : h(h_), fw((size_t)width), nw(h_->pb.nb_vars), mx{&h_->rk}, fringe(mx) {
-        const WidthHeuristic<BitState>* wh = width_kind == 0 ? (const WidthHeuristic<BitState>*)&fw : (const WidthHeuristic<BitState>*)&nw;
-        SolverConfig<BitState> cfg{&h->pb, &h->rlx, &h->rk, wh, &dom, &nocut, &fringe, &cache, LAST_EXACT_LAYER};
-        solver.reset(new WaveSolver<BitState, BitStateHash, BitStateEq>(cfg, (size_t)k));
+// MAX2SAT states cross the ABI as n int32 benefits packed two per uint64 word (little endian), the depth travels separately
+struct M2Handle {
+    using State = M2State; using Hash = M2Hash; using Eq = M2Eq;
+    Max2Sat pb;
+    Max2SatRelax rlx;
+    Max2SatRanking rk;
+    M2Handle(size_t n, const std::vector<M2Clause>& c) : pb(n, c), rlx(&pb) {}
+    size_t abi_words() const { return (pb.nb_vars + 1) / 2; }
+    State state_from_abi(const uint64_t* p, size_t depth) const {
+        const int32_t* q = (const int32_t*)p;
+        M2State s{depth, std::vector<isize>(pb.nb_vars)};
+        for (size_t i = 0; i < pb.nb_vars; ++i) s.sub[i] = q[i];
+        return s;
+    }
+    void state_to_abi(const State& s, uint64_t* p) const {
+        std::memset(p, 0, abi_words() * 8);
+        int32_t* q = (int32_t*)p;
+        for (size_t i = 0; i < pb.nb_vars; ++i) q[i] = (int32_t)s.sub[i];
     }
 };
+template <class H>
+struct DD {
+    using S = typename H::State;
+    H* h;
+    Mdd<S, typename H::Hash, typename H::Eq> mdd;
+    std::vector<SubProblem<S>> cutset;  // drained copy
+    SubProblem<S> root;
+    DD(H* h_, int cutset_type) : h(h_), mdd(cutset_type) {}
+};
+template <class H>
+struct Stepper {
+    using S = typename H::State;
+    H* h;
+    FixedWidth<S> fw; NbUnassignedWidth<S> nw; NoCutoff nocut; EmptyDominanceChecker<S> dom; EmptyCache<S> cache;
+    MaxUB<S> mx; NoDupFringe<S, typename H::Hash, typename H::Eq> fringe;
+    std::unique_ptr<WaveSolver<S, typename H::Hash, typename H::Eq>> solver;
+    Stepper(H* h_, int k, int width_kind, uint64_t width)
+        : h(h_), fw((size_t)width), nw(h_->pb.nb_variables()), mx{&h_->rk}, fringe(mx) {
+        const WidthHeuristic<S>* wh = width_kind == 0 ? (const WidthHeuristic<S>*)&fw : (const WidthHeuristic<S>*)&nw;
+        SolverConfig<S> cfg{&h->pb, &h->rlx, &h->rk, wh, &dom, &nocut, &fringe, &cache, LAST_EXACT_LAYER};
+        solver.reset(new WaveSolver<S, typename H::Hash, typename H::Eq>(cfg, (size_t)k));
+    }
+};
+using MispDD = DD<MispHandle>;
+using MispStepper = Stepper<MispHandle>;
+using MispMdd = Mdd<BitState, BitStateHash, BitStateEq>;
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
 extern "C" {
-
 struct oracle_dd_result {
     int32_t has_best; int32_t is_exact; int32_t has_best_exact; int32_t lel;  // lel: -1 = none (never squashed)
     int64_t best_value; int64_t best_exact_value;
@@ -55,26 +83,19 @@ struct oracle_solve_result {
     uint64_t explored; uint64_t expanded; uint64_t transitions; uint64_t compilations; uint64_t waves;
     double seconds;
 };
-
-void* oracle_misp_new(int32_t n, const int64_t* weights, int32_t m, const int32_t* src, const int32_t* dst) {
-    return new MispHandle((size_t)n, weights, (size_t)m, src, dst);
 }
-void oracle_misp_free(void* h) { delete (MispHandle*)h; }
-int32_t oracle_misp_words(void* h) { return (int32_t)((MispHandle*)h)->pb.words; }
 
-void* oracle_misp_dd_new(void* h, int32_t cutset_type) { return new MispDD((MispHandle*)h, cutset_type); }
-void oracle_misp_dd_free(void* dd) { delete (MispDD*)dd; }
-
+namespace {
 // comp_type: 0 Exact, 1 Relaxed, 2 Restricted (abstraction/mdd.rs:40-47 order).  Returns 0 ok, 1 cutoff.
-int32_t oracle_misp_dd_compile(void* ddp, int32_t comp_type, uint64_t max_width, const uint64_t* root_state, int64_t root_value,
-                               uint64_t root_depth, int64_t best_lb, int32_t cutoff_now, oracle_dd_result* out) {
-    MispDD* dd = (MispDD*)ddp;
-    MispHandle* h = dd->h;
-    BitState s; s.w.assign(root_state, root_state + h->pb.words);
-    dd->root = SubProblem<BitState>{std::make_shared<const BitState>(std::move(s)), root_value, {}, ISIZE_MAX, (size_t)root_depth};
-    EmptyCache<BitState> cache; EmptyDominanceChecker<BitState> dom; FlagCutoff cut(cutoff_now != 0);
+template <class H>
+int32_t dd_compile(DD<H>* dd, int32_t comp_type, uint64_t max_width, const uint64_t* root_state, int64_t root_value, uint64_t root_depth,
+                   int64_t best_lb, int32_t cutoff_now, oracle_dd_result* out) {
+    using S = typename H::State;
+    H* h = dd->h;
+    dd->root = SubProblem<S>{std::make_shared<const S>(h->state_from_abi(root_state, (size_t)root_depth)), root_value, {}, ISIZE_MAX, (size_t)root_depth};
+    EmptyCache<S> cache; EmptyDominanceChecker<S> dom; FlagCutoff cut(cutoff_now != 0);
     CompilationType t = comp_type == 0 ? CompilationType::Exact : (comp_type == 1 ? CompilationType::Relaxed : CompilationType::Restricted);
-    CompilationInput<BitState> in{t, &h->pb, &h->rlx, &h->rk, &cut, (size_t)max_width, &dd->root, best_lb, &cache, &dom};
+    CompilationInput<S> in{t, &h->pb, &h->rlx, &h->rk, &cut, (size_t)max_width, &dd->root, best_lb, &cache, &dom};
     Completion c;
     std::memset(out, 0, sizeof(*out));
     if (!dd->mdd.compile(in, &c)) { out->cutoff = 1; return 1; }
@@ -88,26 +109,26 @@ int32_t oracle_misp_dd_compile(void* ddp, int32_t comp_type, uint64_t max_width,
     auto lel = dd->mdd.lel();
     out->lel = (lel && *lel < dd->mdd.layers.size()) ? (int32_t)*lel : -1;
     dd->cutset.clear();
-    dd->mdd.drain_cutset([&](SubProblem<BitState> n) { dd->cutset.push_back(std::move(n)); });
+    dd->mdd.drain_cutset([&](SubProblem<S> n) { dd->cutset.push_back(std::move(n)); });
     out->cutset_size = (int32_t)dd->cutset.size();
     return 0;
 }
 // per expanded layer: branching variable and |curr_l| after the cut
-int32_t oracle_misp_dd_layers(void* ddp, int32_t* vars, int32_t* widths, int32_t cap) {
-    MispDD* dd = (MispDD*)ddp;
+template <class H>
+int32_t dd_layers(DD<H>* dd, int32_t* vars, int32_t* widths, int32_t cap) {
     int32_t n = (int32_t)dd->mdd.layer_vars.size();
     for (int32_t i = 0; i < n && i < cap; ++i) { vars[i] = (int32_t)dd->mdd.layer_vars[i]; widths[i] = (int32_t)dd->mdd.layer_widths[i]; }
     return n;
 }
 // drained cutset (MARKED nodes only, clean.rs:417-445) in drain order.  paths: path_stride (var,value) int32 pairs per node.
-int32_t oracle_misp_dd_cutset(void* ddp, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, int32_t* path_lens,
-                              int32_t* paths, int32_t cap, int32_t path_stride) {
-    MispDD* dd = (MispDD*)ddp;
-    size_t W = dd->h->pb.words;
+template <class H>
+int32_t dd_cutset(DD<H>* dd, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, int32_t* path_lens, int32_t* paths, int32_t cap,
+                  int32_t path_stride) {
+    size_t W = dd->h->abi_words();
     int32_t n = (int32_t)dd->cutset.size();
     for (int32_t i = 0; i < n && i < cap; ++i) {
         const auto& sp = dd->cutset[i];
-        std::memcpy(states + (size_t)i * W, sp.state->w.data(), W * 8);
+        dd->h->state_to_abi(*sp.state, states + (size_t)i * W);
         values[i] = sp.value; ubs[i] = sp.ub; depths[i] = (int32_t)sp.depth;
         path_lens[i] = (int32_t)sp.path.size();
         if (paths)
@@ -119,52 +140,135 @@ int32_t oracle_misp_dd_cutset(void* ddp, uint64_t* states, int64_t* values, int6
     return n;
 }
 // best (exact != 0: best exact) solution as (var,value) pairs in path order; returns length or -1 if None
-int32_t oracle_misp_dd_solution(void* ddp, int32_t exact, int32_t* vars, int32_t* vals, int32_t cap) {
-    MispDD* dd = (MispDD*)ddp;
+template <class H>
+int32_t dd_solution(DD<H>* dd, int32_t exact, int32_t* vars, int32_t* vals, int32_t cap) {
     auto sol = exact ? dd->mdd.best_exact_solution() : dd->mdd.best_solution();
     if (!sol) return -1;
     for (int32_t i = 0; i < (int32_t)sol->size() && i < cap; ++i) { vars[i] = (int32_t)(*sol)[i].variable; vals[i] = (int32_t)(*sol)[i].value; }
     return (int32_t)sol->size();
 }
-
 // mode: 0 SequentialSolver, 1 WaveSolver(k), 2 ParallelSolver(k threads).  width_kind: 0 FixedWidth(width), 1 NbUnassignedWidth.
-// sol_yes: vertices with decision YES (cap n).  trace (mode 1): 4 int64 per wave (popped, best_lb, fringe_len, top_ub).
-int32_t oracle_misp_solve(void* hp, int32_t mode, int32_t k, int32_t width_kind, uint64_t width, int32_t cutset_type, double time_budget_s,
-                          uint64_t max_waves, oracle_solve_result* out, int32_t* sol_yes, int32_t* sol_len, int64_t* trace, int32_t trace_cap,
-                          int32_t* trace_len) {
-    MispHandle* h = (MispHandle*)hp;
-    FixedWidth<BitState> fw((size_t)width); NbUnassignedWidth<BitState> nw(h->pb.nb_vars);
-    const WidthHeuristic<BitState>* wh = width_kind == 0 ? (const WidthHeuristic<BitState>*)&fw : (const WidthHeuristic<BitState>*)&nw;
+// sol_vars / sol_vals: the best solution sorted by variable (cap nb_variables).  trace (mode 1): 4 int64 per wave (popped, best_lb, fringe_len, top_ub).
+template <class H>
+int32_t solve(H* h, int32_t mode, int32_t k, int32_t width_kind, uint64_t width, int32_t cutset_type, double time_budget_s, uint64_t max_waves,
+              oracle_solve_result* out, int32_t* sol_vars, int32_t* sol_vals, int32_t* sol_len, int64_t* trace, int32_t trace_cap, int32_t* trace_len) {
+    using S = typename H::State; using HS = typename H::Hash; using EQ = typename H::Eq;
+    FixedWidth<S> fw((size_t)width); NbUnassignedWidth<S> nw(h->pb.nb_variables());
+    const WidthHeuristic<S>* wh = width_kind == 0 ? (const WidthHeuristic<S>*)&fw : (const WidthHeuristic<S>*)&nw;
     NoCutoff nocut; std::unique_ptr<TimeBudget> tb;
     const Cutoff* cut = &nocut;
     if (time_budget_s > 0) { tb.reset(new TimeBudget(time_budget_s)); cut = tb.get(); }
-    EmptyDominanceChecker<BitState> dom; EmptyCache<BitState> cache;
-    MaxUB<BitState> mx{&h->rk};
-    MispFringe fringe(mx);
-    SolverConfig<BitState> cfg{&h->pb, &h->rlx, &h->rk, wh, &dom, cut, &fringe, &cache, cutset_type};
+    EmptyDominanceChecker<S> dom; EmptyCache<S> cache;
+    MaxUB<S> mx{&h->rk};
+    NoDupFringe<S, HS, EQ> fringe(mx);
+    SolverConfig<S> cfg{&h->pb, &h->rlx, &h->rk, wh, &dom, cut, &fringe, &cache, cutset_type};
     std::memset(out, 0, sizeof(*out));
     if (trace_len) *trace_len = 0;
     double t0 = now_s();
     Completion c; SolverStats st; isize lb, ub; std::optional<Solution> sol;
-    if (mode == 0) { SequentialSolver<BitState, BitStateHash, BitStateEq> s(cfg); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
+    if (mode == 0) { SequentialSolver<S, HS, EQ> s(cfg); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
     else if (mode == 1) {
-        WaveSolver<BitState, BitStateHash, BitStateEq> s(cfg, (size_t)k); s.max_waves = max_waves ? max_waves : UINT64_MAX;
+        WaveSolver<S, HS, EQ> s(cfg, (size_t)k); s.max_waves = max_waves ? max_waves : UINT64_MAX;
         c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol;
         if (trace) {
             int32_t n = 0;
             for (auto& t : s.trace) { if (n >= trace_cap) break; trace[4 * n] = (int64_t)t.popped; trace[4 * n + 1] = t.best_lb; trace[4 * n + 2] = (int64_t)t.fringe_len; trace[4 * n + 3] = t.top_ub; ++n; }
             *trace_len = n;
         }
-    } else { ParallelSolver<BitState, BitStateHash, BitStateEq> s(cfg, (size_t)k); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
+    } else { ParallelSolver<S, HS, EQ> s(cfg, (size_t)k); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
     out->seconds = now_s() - t0;
     out->has_value = c.best_value.has_value(); out->best_value = c.best_value.value_or(0); out->is_exact = c.is_exact;
     out->best_lb = lb; out->best_ub = ub;
     out->explored = st.explored; out->expanded = st.expanded; out->transitions = st.transitions; out->compilations = st.compilations; out->waves = st.waves;
     int32_t n = 0;
-    if (sol && sol_yes) for (auto& d : *sol) if (d.value == MISP_YES) sol_yes[n++] = (int32_t)d.variable;
+    if (sol && sol_vars && sol_vals) for (auto& d : *sol) { sol_vars[n] = (int32_t)d.variable; sol_vals[n] = (int32_t)d.value; ++n; }
     if (sol_len) *sol_len = n;
     return 0;
 }
+template <class H> void stepper_state(Stepper<H>* s, int64_t out[6]) {
+    auto& w = *s->solver;
+    out[0] = w.best_lb; out[1] = w.best_ub; out[2] = (int64_t)w.fringe_len(); out[3] = (int64_t)w.stats.explored; out[4] = (int64_t)w.stats.expanded; out[5] = w.best_sol.has_value();
+}
+template <class H> int32_t stepper_wave(Stepper<H>* s, int64_t out3[3]) { isize o[3]; bool ok = s->solver->wave(o); out3[0] = o[0]; out3[1] = o[1]; out3[2] = o[2]; return ok ? 0 : 1; }
+}  // namespace
+
+extern "C" {
+
+// ---- MISP (BASELINE configs 2, 5) -------------------------------------------------------------------------------------------------
+void* oracle_misp_new(int32_t n, const int64_t* weights, int32_t m, const int32_t* src, const int32_t* dst) {
+    return new MispHandle((size_t)n, weights, (size_t)m, src, dst);
+}
+void oracle_misp_free(void* h) { delete (MispHandle*)h; }
+int32_t oracle_misp_words(void* h) { return (int32_t)((MispHandle*)h)->pb.words; }
+void* oracle_misp_dd_new(void* h, int32_t cutset_type) { return new MispDD((MispHandle*)h, cutset_type); }
+void oracle_misp_dd_free(void* dd) { delete (MispDD*)dd; }
+int32_t oracle_misp_dd_compile(void* ddp, int32_t comp_type, uint64_t max_width, const uint64_t* root_state, int64_t root_value,
+                               uint64_t root_depth, int64_t best_lb, int32_t cutoff_now, oracle_dd_result* out) {
+    return dd_compile((MispDD*)ddp, comp_type, max_width, root_state, root_value, root_depth, best_lb, cutoff_now, out);
+}
+int32_t oracle_misp_dd_layers(void* ddp, int32_t* vars, int32_t* widths, int32_t cap) { return dd_layers((MispDD*)ddp, vars, widths, cap); }
+int32_t oracle_misp_dd_cutset(void* ddp, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, int32_t* path_lens,
+                              int32_t* paths, int32_t cap, int32_t path_stride) {
+    return dd_cutset((MispDD*)ddp, states, values, ubs, depths, path_lens, paths, cap, path_stride);
+}
+int32_t oracle_misp_dd_solution(void* ddp, int32_t exact, int32_t* vars, int32_t* vals, int32_t cap) { return dd_solution((MispDD*)ddp, exact, vars, vals, cap); }
+// sol_yes: vertices with decision YES (cap n)
+int32_t oracle_misp_solve(void* hp, int32_t mode, int32_t k, int32_t width_kind, uint64_t width, int32_t cutset_type, double time_budget_s,
+                          uint64_t max_waves, oracle_solve_result* out, int32_t* sol_yes, int32_t* sol_len, int64_t* trace, int32_t trace_cap,
+                          int32_t* trace_len) {
+    MispHandle* h = (MispHandle*)hp;
+    std::vector<int32_t> vars(h->pb.nb_vars + 1), vals(h->pb.nb_vars + 1);
+    int32_t len = 0;
+    int32_t rc = solve(h, mode, k, width_kind, width, cutset_type, time_budget_s, max_waves, out, vars.data(), vals.data(), &len, trace, trace_cap, trace_len);
+    int32_t n = 0;
+    if (sol_yes) for (int32_t i = 0; i < len; ++i) if (vals[i] == MISP_YES) sol_yes[n++] = vars[i];
+    if (sol_len) *sol_len = n;
+    return rc;
+}
+
+// ---- MAX2SAT (BASELINE config 3).  clauses: m triples (weight, literal x, literal y), literals +-(variable + 1), x == y for a unit clause ----
+void* oracle_m2s_new(int32_t n, int32_t m, const int64_t* clauses) {
+    std::vector<M2Clause> c((size_t)m);
+    for (int32_t i = 0; i < m; ++i) c[i] = M2Clause{clauses[3 * i], clauses[3 * i + 1], clauses[3 * i + 2]};
+    return new M2Handle((size_t)n, c);
+}
+void oracle_m2s_free(void* h) { delete (M2Handle*)h; }
+int32_t oracle_m2s_words(void* h) { return (int32_t)((M2Handle*)h)->abi_words(); }
+int64_t oracle_m2s_initial_value(void* h) { return ((M2Handle*)h)->pb.initial; }
+void oracle_m2s_order(void* h, int32_t* out) { auto& o = ((M2Handle*)h)->pb.order; for (size_t i = 0; i < o.size(); ++i) out[i] = (int32_t)o[i]; }
+// model-level known answers (model.rs:396-448): transition / cost / rank / rub of one state
+void oracle_m2s_transition(void* hp, const int32_t* sub, int32_t depth, int32_t var, int32_t value, int32_t* out_sub, int64_t* cost, int64_t* rank, int64_t* rub) {
+    M2Handle* h = (M2Handle*)hp;
+    M2State s{(size_t)depth, std::vector<isize>(sub, sub + h->pb.nb_vars)};
+    Decision d{(size_t)var, value};
+    M2State r = h->pb.transition(s, d);
+    for (size_t i = 0; i < h->pb.nb_vars; ++i) out_sub[i] = (int32_t)r.sub[i];
+    if (cost) *cost = h->pb.transition_cost(s, r, d);
+    if (rank) *rank = Max2SatRanking::rank(r);
+    if (rub) *rub = (size_t)depth < h->pb.nb_vars ? h->pb.fast_upper_bound(s) : 0;
+}
+void* oracle_m2s_dd_new(void* h, int32_t cutset_type) { return new DD<M2Handle>((M2Handle*)h, cutset_type); }
+void oracle_m2s_dd_free(void* dd) { delete (DD<M2Handle>*)dd; }
+int32_t oracle_m2s_dd_compile(void* ddp, int32_t comp_type, uint64_t max_width, const uint64_t* root_state, int64_t root_value,
+                              uint64_t root_depth, int64_t best_lb, int32_t cutoff_now, oracle_dd_result* out) {
+    return dd_compile((DD<M2Handle>*)ddp, comp_type, max_width, root_state, root_value, root_depth, best_lb, cutoff_now, out);
+}
+int32_t oracle_m2s_dd_layers(void* ddp, int32_t* vars, int32_t* widths, int32_t cap) { return dd_layers((DD<M2Handle>*)ddp, vars, widths, cap); }
+int32_t oracle_m2s_dd_cutset(void* ddp, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, int32_t* path_lens, int32_t* paths,
+                             int32_t cap, int32_t path_stride) {
+    return dd_cutset((DD<M2Handle>*)ddp, states, values, ubs, depths, path_lens, paths, cap, path_stride);
+}
+int32_t oracle_m2s_dd_solution(void* ddp, int32_t exact, int32_t* vars, int32_t* vals, int32_t cap) { return dd_solution((DD<M2Handle>*)ddp, exact, vars, vals, cap); }
+int32_t oracle_m2s_solve(void* hp, int32_t mode, int32_t k, int32_t width_kind, uint64_t width, int32_t cutset_type, double time_budget_s,
+                         uint64_t max_waves, oracle_solve_result* out, int32_t* sol_vars, int32_t* sol_vals, int32_t* sol_len, int64_t* trace,
+                         int32_t trace_cap, int32_t* trace_len) {
+    return solve((M2Handle*)hp, mode, k, width_kind, width, cutset_type, time_budget_s, max_waves, out, sol_vars, sol_vals, sol_len, trace, trace_cap, trace_len);
+}
+void* oracle_m2s_stepper_new(void* hp, int32_t k, int32_t width_kind, uint64_t width) { return new Stepper<M2Handle>((M2Handle*)hp, k, width_kind, width); }
+void oracle_m2s_stepper_free(void* s) { delete (Stepper<M2Handle>*)s; }
+void oracle_m2s_stepper_init(void* s, int32_t push_root) { ((Stepper<M2Handle>*)s)->solver->init(push_root != 0); }
+int32_t oracle_m2s_stepper_wave(void* s, int64_t out3[3]) { return stepper_wave((Stepper<M2Handle>*)s, out3); }
+void oracle_m2s_stepper_state(void* s, int64_t out[6]) { stepper_state((Stepper<M2Handle>*)s, out); }
 
 // CPU baseline of one bench "step": for each root, restricted DD then (if inexact) relaxed DD, all against the same best_lb,
 // on `threads` worker threads each owning one Mdd (the ParallelSolver worker body, parallel.rs:391-437, without the fringe).

@@ -4,6 +4,7 @@ Copies the *data* fixtures the reference's own tests use for the hot path (no re
   * resources/visualisation_tests/*.dot  -- golden graphviz dumps compared verbatim by clean.rs:2401-2546
   * resources/misp/*.clq (small ones)    -- DIMACS instances whose optima are asserted in ddo/examples/misp/tests.rs:66-193
   * resources/knapsack/* (small ones)    -- instances whose optima are asserted in ddo/examples/knapsack/tests.rs:65-206
+  * resources/max2sat/*.wcnf (small)     -- instances whose optima are asserted in ddo/examples/max2sat/tests.rs:65-103
 and writes expected.json with the asserted optima (transcribed from those test files, with their line numbers).
 """
 import json
@@ -17,15 +18,16 @@ OUT = Path(__file__).resolve().parent
 MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "keller4", "hamming8-2", "hamming8-4",
         "brock200_2", "brock200_3", "brock200_4", "c-fat200-5"]
 KNAPSACK_MAX_ITEMS = 200
+MAX2SAT = ["debug", "debug2", "pass", "tautology", "unit", "negative_wt", "frb10-6-1", "frb10-6-2", "frb10-6-3", "frb10-6-4"]
 
 
 def asserted(tests_rs: Path):
     """{instance id: (value, line)} from `assert_eq!(solve_id("<id>"), <value>);` lines (ignored tests included)."""
     out = {}
     for ln, line in enumerate(tests_rs.read_text().splitlines(), 1):
-        m = re.search(r'assert_eq!\(solve_id\("([^"]+)"\),\s*(-?\d+)\)', line)
+        m = re.search(r'assert_eq!\(solve_id\("([^"]+)"\),\s*(-?[\d_]+)\)', line)
         if m:
-            out[m.group(1)] = (int(m.group(2)), ln)
+            out[m.group(1)] = (int(m.group(2).replace("_", "")), ln)
     return out
 
 
@@ -34,7 +36,13 @@ def main():
     (OUT / "knapsack").mkdir(exist_ok=True)
     for f in (REF / "resources/visualisation_tests").glob("*.dot"):
         shutil.copy(f, OUT / f.name)
-    expected = {"misp": {}, "knapsack": {}}
+    (OUT / "max2sat").mkdir(exist_ok=True)
+    expected = {"misp": {}, "knapsack": {}, "max2sat": {}}
+    x = asserted(REF / "ddo/examples/max2sat/tests.rs")
+    for name in MAX2SAT:
+        shutil.copy(REF / "resources/max2sat" / f"{name}.wcnf", OUT / "max2sat" / f"{name}.wcnf")
+        v, ln = x[f"{name}.wcnf"]
+        expected["max2sat"][name] = {"optimum": v, "source": f"ddo/examples/max2sat/tests.rs:{ln}"}
     m = asserted(REF / "ddo/examples/misp/tests.rs")
     for name in MISP:
         shutil.copy(REF / "resources/misp" / f"{name}.clq", OUT / "misp" / f"{name}.clq")

@@ -74,6 +74,29 @@ def lib():
         _lib.oracle_misp_stepper_set_lb.argtypes = [C.c_void_p, C.c_int64]
         _lib.oracle_misp_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         _lib.oracle_misp_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
+        _lib.oracle_m2s_new.restype = C.c_void_p
+        _lib.oracle_m2s_new.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
+        _lib.oracle_m2s_free.argtypes = [C.c_void_p]
+        _lib.oracle_m2s_words.argtypes = [C.c_void_p]
+        _lib.oracle_m2s_initial_value.restype = C.c_int64
+        _lib.oracle_m2s_initial_value.argtypes = [C.c_void_p]
+        _lib.oracle_m2s_order.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.oracle_m2s_transition.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        _lib.oracle_m2s_dd_new.restype = C.c_void_p
+        _lib.oracle_m2s_dd_new.argtypes = [C.c_void_p, C.c_int32]
+        _lib.oracle_m2s_dd_free.argtypes = [C.c_void_p]
+        _lib.oracle_m2s_dd_compile.argtypes = _lib.oracle_misp_dd_compile.argtypes
+        _lib.oracle_m2s_dd_layers.argtypes = _lib.oracle_misp_dd_layers.argtypes
+        _lib.oracle_m2s_dd_cutset.argtypes = _lib.oracle_misp_dd_cutset.argtypes
+        _lib.oracle_m2s_dd_solution.argtypes = _lib.oracle_misp_dd_solution.argtypes
+        _lib.oracle_m2s_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64,
+                                          C.POINTER(SolveResult), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        _lib.oracle_m2s_stepper_new.restype = C.c_void_p
+        _lib.oracle_m2s_stepper_new.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
+        _lib.oracle_m2s_stepper_free.argtypes = [C.c_void_p]
+        _lib.oracle_m2s_stepper_init.argtypes = [C.c_void_p, C.c_int32]
+        _lib.oracle_m2s_stepper_wave.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 3)]
+        _lib.oracle_m2s_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
         _lib.oracle_knapsack_solve.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                                C.POINTER(SolveResult), C.c_void_p]
         _lib.oracle_locbounds_dump.argtypes = [C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
@@ -84,22 +107,28 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-class OracleMisp:
-    """CPU oracle for one MISP instance."""
+class _OracleModel:
+    """Entry points shared by the models (oracle_<prefix>_dd_* of oracle/oracle_capi.cpp)."""
 
-    def __init__(self, inst):
-        self.inst = inst
-        self.h = lib().oracle_misp_new(inst.n, _p(inst.weights), len(inst.src), _p(inst.src), _p(inst.dst))
-        self.words = lib().oracle_misp_words(self.h)
+    PREFIX = ""
+
+    def _f(self, name):
+        return getattr(lib(), f"oracle_{self.PREFIX}_{name}")
 
     def __del__(self):
         try:
-            lib().oracle_misp_free(self.h)
+            self._f("free")(self.h)
         except Exception:
             pass
 
-    def compile(self, comp_type, max_width, root_state=None, root_value=0, root_depth=0, best_lb=I64_MIN, cutset_type=LEL, cutoff=False, want_paths=False):
-        L = lib()
+    def compile(self, comp_type, max_width, root_state=None, root_value=None, root_depth=0, best_lb=I64_MIN, cutset_type=LEL, cutoff=False, want_paths=False):
+        class _L:
+            pass
+        L = _L()
+        for nm in ("dd_new", "dd_free", "dd_compile", "dd_layers", "dd_cutset", "dd_solution"):
+            setattr(L, f"oracle_misp_{nm}", self._f(nm))
+        if root_value is None:
+            root_value = self.initial_value()
         dd = L.oracle_misp_dd_new(self.h, cutset_type)
         try:
             if root_state is None:
@@ -141,6 +170,21 @@ class OracleMisp:
         finally:
             L.oracle_misp_dd_free(dd)
 
+
+
+class OracleMisp(_OracleModel):
+    """CPU oracle for one MISP instance."""
+
+    PREFIX = "misp"
+
+    def __init__(self, inst):
+        self.inst = inst
+        self.h = lib().oracle_misp_new(inst.n, _p(inst.weights), len(inst.src), _p(inst.src), _p(inst.dst))
+        self.words = lib().oracle_misp_words(self.h)
+
+    def initial_value(self):
+        return 0
+
     def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0):
         """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (the reference CLI default, misp/main.rs:322-328)."""
         m = {"sequential": 0, "wave": 1, "parallel": 2}[mode]
@@ -169,6 +213,48 @@ class OracleMisp:
         sec = C.c_double(0)
         exp = lib().oracle_misp_compile_many(self.h, threads, n, _p(rs), _p(rv), _p(rd), _p(w), best_lb, cutset_type, _p(rb), _p(xb), _p(cs), C.byref(tr), C.byref(sec))
         return {"expanded": int(exp), "transitions": int(tr.value), "seconds": float(sec.value), "restricted_best": rb, "relaxed_best": xb, "cutset_sizes": cs}
+
+
+class OracleM2s(_OracleModel):
+    """CPU oracle for one MAX2SAT instance (states: n int32 benefits packed in uint64 words)."""
+
+    PREFIX = "m2s"
+
+    def __init__(self, inst):
+        self.inst = inst
+        self.h = lib().oracle_m2s_new(inst.n, len(inst.clauses), _p(inst.clauses))
+        self.words = lib().oracle_m2s_words(self.h)
+
+    def initial_value(self):
+        return int(lib().oracle_m2s_initial_value(self.h))
+
+    def order(self):
+        o = np.zeros(self.inst.n, dtype=np.int32)
+        lib().oracle_m2s_order(self.h, _p(o))
+        return o
+
+    def transition(self, sub, depth, var, value):
+        sub = np.ascontiguousarray(sub, dtype=np.int32)
+        out = np.zeros(self.inst.n, dtype=np.int32)
+        cost, rank, rub = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        lib().oracle_m2s_transition(self.h, _p(sub), depth, var, value, _p(out), C.byref(cost), C.byref(rank), C.byref(rub))
+        return out, int(cost.value), int(rank.value), int(rub.value)
+
+    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0):
+        """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (max2sat/main.rs:87-93)."""
+        m = {"sequential": 0, "wave": 1, "parallel": 2}[mode]
+        res = SolveResult()
+        sv = np.zeros(self.inst.n + 1, dtype=np.int32)
+        sx = np.zeros(self.inst.n + 1, dtype=np.int32)
+        sl = C.c_int32(0)
+        trace = np.zeros((max(trace_cap, 1), 4), dtype=np.int64)
+        tl = C.c_int32(0)
+        lib().oracle_m2s_solve(self.h, m, k, 0 if width is not None else 1, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
+                               _p(sv), _p(sx), C.byref(sl), _p(trace) if trace_cap else None, trace_cap, C.byref(tl))
+        out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
+        out["solution"] = list(zip(sv[: sl.value].tolist(), sx[: sl.value].tolist()))
+        out["trace"] = trace[: tl.value].copy()
+        return out
 
 
 class OracleStepper:

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from ddo_b200.instances import parse_dimacs, parse_knapsack, random_knapsack
+from ddo_b200.instances import parse_dimacs, parse_knapsack, random_knapsack, read_wcnf
 
 
 def test_selftest_restated_reference_unit_tests():
@@ -167,3 +167,58 @@ def test_knapsack_config1_50_items_matches_dp():
     assert r["is_exact"] and r["best_value"] == int(best[-1])
     r2 = O.knapsack_solve(inst, solver="parallel", k=4, caching=True, cutset_type=O.FRONTIER)
     assert r2["best_value"] == int(best[-1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# MAX2SAT (BASELINE config 3)
+# ----------------------------------------------------------------------------------------------------------------
+def test_max2sat_model_unit_vectors(golden_dir):
+    """examples/max2sat/model.rs:388-448 (test_initial_value, test_next_state, test_rank) and data.rs:118-125 (4 clauses, 3 vars)."""
+    inst = read_wcnf(golden_dir / "max2sat" / "debug2.wcnf")
+    assert inst.n == 3 and len(inst.clauses) == 4
+    o = O.OracleM2s(inst)
+    assert o.initial_value() == 0
+    root = np.zeros(3, dtype=np.int32)
+    nod_f, _, _, _ = o.transition(root, 0, 0, -1)
+    assert nod_f.tolist() == [0, -4, 3]
+    nod_t, _, _, _ = o.transition(root, 0, 0, 1)
+    assert nod_t.tolist() == [0, 0, 0]
+    benef = [-183, -122, -61, -183, -183, -183, -122, -122, -183, -122, -61, -122, 0, -122, -122, -122, -122, -122, -183, -122, -61, 0, -122, -61, 0, 0, 0, 0, 0,
+             -244, -61, -183, 0, -122, -244, -183, -61, -61, -122, -122, -122, -183, -122, 0, -183, -61, -183, -122, -122, -183, -183, -61, -61, -122, 0, 0, 0, 0, 0, 0]
+    assert int(np.abs(np.array(benef)).sum()) == 5917  # model.rs:434-448: rank() is the sum of absolute benefits
+
+
+def test_max2sat_known_optima(golden_dir):
+    """examples/max2sat/tests.rs:65-106: the ten instances the reference solves in its (non-ignored) tests."""
+    exp = _expected(golden_dir)["max2sat"]
+    assert len(exp) == 10
+    for name, e in exp.items():
+        inst = read_wcnf(golden_dir / "max2sat" / f"{name}.wcnf")
+        o = O.OracleM2s(inst)
+        if inst.n > 10:  # frb10-6-*: 60 variables; one default-width sequential solve each is ~7 s -> use the threaded solver
+            r = o.solve("parallel", k=8)
+        else:
+            r = o.solve("sequential")
+            assert o.solve("sequential", width=2)["best_value"] == e["optimum"]
+            assert o.solve("wave", k=4, width=3)["best_value"] == e["optimum"]
+        assert r["is_exact"] and r["best_value"] == e["optimum"], (name, e["source"])
+        # the decision vector really has that value: count the satisfied clause weights
+        model = dict(r["solution"])
+        assert len(model) == inst.n
+        uniq = {}
+        for w, x, y in inst.clauses.tolist():
+            uniq[(min(x, y), max(x, y))] = w
+        sat = sum(w for (x, y), w in uniq.items() if model[abs(x) - 1] * x > 0 or model[abs(y) - 1] * y > 0)
+        assert sat == e["optimum"], name
+
+
+def test_max2sat_restricted_relaxed_bracket_the_optimum(golden_dir):
+    """A restricted DD gives a lower bound, a relaxed DD an upper bound, the exact DD the optimum (clean.rs:345-381 on the MAX2SAT model)."""
+    inst = read_wcnf(golden_dir / "max2sat" / "pass.wcnf")
+    o = O.OracleM2s(inst)
+    ex = o.compile(O.EXACT, 1 << 20)
+    assert ex["is_exact"] and ex["best_value"] == 54
+    for w in (1, 2, 3):
+        lo = o.compile(O.RESTRICTED, w)
+        hi = o.compile(O.RELAXED, w)
+        assert lo["best_value"] <= 54 <= hi["best_value"]
