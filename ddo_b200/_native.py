@@ -33,6 +33,8 @@ SYMBOLS = {
     "ddo_device_count": (C.c_int, []),
     "ddo_kernel_launches": (C.c_uint64, []),
     "ddo_model_create_misp": (C.c_int, [C.c_int32, _P, C.c_int64, _P, _P, C.c_int, C.POINTER(_P)]),
+    "ddo_model_create_max2sat": (C.c_int, [C.c_int32, C.c_int64, _P, C.c_int, C.POINTER(_P)]),
+    "ddo_model_kind": (C.c_int32, [_P]),
     "ddo_model_destroy": (None, [_P]),
     "ddo_model_nb_variables": (C.c_int32, [_P]),
     "ddo_model_state_words": (C.c_int32, [_P]),

@@ -2,6 +2,7 @@
 
 Reference items mirrored (paths relative to /root/reference/ddo/):
   Problem / Relaxation / StateRanking for MISP   examples/misp/main.rs:37-209    -> ``Misp`` (one declarative device model)
+  Max2Sat / Max2SatRelax / Max2SatRanking        examples/max2sat/{model,relax,heuristics}.rs -> ``Max2Sat``
   CompilationInput / CompilationType             src/abstraction/mdd.rs:40-71    -> ``GpuMdd.compile(...)`` keyword arguments
   DecisionDiagram                                src/abstraction/mdd.rs:75-114   -> ``GpuMdd``
   SubProblem / Decision / Completion / Reason    src/common.rs:58-121            -> ``SubProblem`` / ``Decision`` / ``Completion`` / ``CutoffOccurred``
@@ -17,7 +18,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .instances import MispInstance
+from .instances import Max2SatInstance, MispInstance
 
 LAST_EXACT_LAYER = N.LAST_EXACT_LAYER
 
@@ -109,6 +110,53 @@ class Misp:
 
     def initial_value(self) -> int:  # dp.rs:43
         return 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            N.lib().ddo_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Max2Sat:
+    """MAX2SAT as a device model: Max2Sat + Max2SatRelax + Max2SatRanking of examples/max2sat/{model,relax,heuristics}.rs, resident in HBM.
+    A state is n int32 marginal benefits packed two per uint64 word (``unpack_state`` gives the benefits); its depth is SubProblem.depth."""
+
+    def __init__(self, inst: Max2SatInstance, device: int = 0):
+        self.inst = inst
+        self.device = device
+        h = C.c_void_p()
+        N.check(N.lib().ddo_model_create_max2sat(inst.n, len(inst.clauses), _ptr(inst.clauses), device, C.byref(h)), "ddo_model_create_max2sat")
+        self.h = h
+        self.words = N.lib().ddo_model_state_words(h)
+
+    def nb_variables(self) -> int:  # dp.rs:39
+        return N.lib().ddo_model_nb_variables(self.h)
+
+    def _initial(self):
+        s = np.zeros(self.words, dtype=np.uint64)
+        v = C.c_int64(0)
+        N.check(N.lib().ddo_model_initial_state(self.h, _ptr(s), C.byref(v)), "ddo_model_initial_state")
+        return s, int(v.value)
+
+    def initial_state(self) -> np.ndarray:  # model.rs:259-264
+        return self._initial()[0]
+
+    def initial_value(self) -> int:  # model.rs:266-269: sum of the tautologies
+        return self._initial()[1]
+
+    def unpack_state(self, state: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(state, dtype=np.uint64).view(np.int32)[: self.inst.n].copy()
+
+    def pack_state(self, benefits) -> np.ndarray:
+        b = np.zeros(2 * self.words, dtype=np.int32)
+        b[: self.inst.n] = benefits
+        return b.view(np.uint64).copy()
 
     def close(self):
         if getattr(self, "h", None):

@@ -3,12 +3,13 @@
 #include <cstring>
 #include <new>
 
+#include "m2s_engine.hpp"
 #include "solver.hpp"
 
 using namespace ddo;
 
-struct ddo_model { MispModel* m; };
-struct ddo_mdd { Engine e; };
+struct ddo_model { int kind; MispModel* m; M2Model* m2; };
+struct ddo_mdd { int kind; Engine* ep; };
 struct ddo_solver { Solver* s; };
 
 #define GUARD_BEGIN try {
@@ -27,15 +28,30 @@ int ddo_model_create_misp(int32_t n, const int64_t* weights, int64_t m, const in
     MispModel* M = nullptr;
     int rc = model_create_misp(n, weights, m, src, dst, device, &M);
     if (rc != DDO_OK) return rc;
-    *out = new ddo_model{M};
+    *out = new ddo_model{DDO_MODEL_MISP, M, nullptr};
     return DDO_OK;
     GUARD_END
 }
-void ddo_model_destroy(ddo_model* m) { if (m) { model_destroy(m->m); delete m; } }
-int32_t ddo_model_nb_variables(const ddo_model* m) { return m ? m->m->n : 0; }
-int32_t ddo_model_state_words(const ddo_model* m) { return m ? m->m->words : 0; }
+int ddo_model_create_max2sat(int32_t n, int64_t m, const int64_t* clauses, int device, ddo_model** out) {
+    GUARD_BEGIN
+    M2Model* M = nullptr;
+    int rc = model_create_max2sat(n, m, clauses, device, &M);
+    if (rc != DDO_OK) return rc;
+    *out = new ddo_model{DDO_MODEL_MAX2SAT, nullptr, M};
+    return DDO_OK;
+    GUARD_END
+}
+int32_t ddo_model_kind(const ddo_model* m) { return m ? m->kind : -1; }
+void ddo_model_destroy(ddo_model* m) { if (m) { if (m->m) model_destroy(m->m); if (m->m2) model_destroy(m->m2); delete m; } }
+int32_t ddo_model_nb_variables(const ddo_model* m) { return !m ? 0 : (m->kind == DDO_MODEL_MISP ? m->m->n : m->m2->n); }
+int32_t ddo_model_state_words(const ddo_model* m) { return !m ? 0 : (m->kind == DDO_MODEL_MISP ? m->m->words : m->m2->words); }
 int ddo_model_initial_state(const ddo_model* m, uint64_t* state_out, int64_t* value_out) {
     if (!m || !state_out) { set_error("null argument"); return DDO_ERR_INVALID; }
+    if (m->kind == DDO_MODEL_MAX2SAT) {  // model.rs:259-269: all benefits zero, value = weight of the tautologies
+        for (int j = 0; j < m->m2->words; ++j) state_out[j] = 0;
+        if (value_out) *value_out = m->m2->initial;
+        return DDO_OK;
+    }
     for (int j = 0; j < m->m->words; ++j) state_out[j] = 0;
     for (int i = 0; i < m->m->n; ++i) state_out[i >> 6] |= 1ull << (i & 63);
     if (value_out) *value_out = 0;
@@ -45,27 +61,29 @@ int ddo_model_initial_state(const ddo_model* m, uint64_t* state_out, int64_t* va
 int ddo_mdd_create(const ddo_model* m, int device, uint64_t max_width_cap, int32_t batch_cap, int32_t cutset_type, ddo_mdd** out) {
     GUARD_BEGIN
     if (!m || !out) { set_error("null argument"); return DDO_ERR_INVALID; }
-    ddo_mdd* d = new ddo_mdd();
-    int rc = d->e.create(m->m, device, max_width_cap, batch_cap, cutset_type);
-    if (rc != DDO_OK) { d->e.destroy(); delete d; return rc; }
+    ddo_mdd* d = new ddo_mdd{m->kind, nullptr};
+    int rc;
+    if (m->kind == DDO_MODEL_MAX2SAT) { M2Engine* me = new M2Engine(); d->ep = me; rc = me->create_m2s(m->m2, device, max_width_cap, batch_cap, cutset_type); }
+    else { d->ep = new Engine(); rc = d->ep->create(m->m, device, max_width_cap, batch_cap, cutset_type); }
+    if (rc != DDO_OK) { d->ep->destroy(); delete d->ep; delete d; return rc; }
     *out = d;
     return DDO_OK;
     GUARD_END
 }
-void ddo_mdd_destroy(ddo_mdd* d) { if (d) { d->e.destroy(); delete d; } }
+void ddo_mdd_destroy(ddo_mdd* d) { if (d) { d->ep->destroy(); delete d->ep; delete d; } }
 
 int ddo_mdd_compile_batch(ddo_mdd* d, int32_t count, int32_t comp_type, const uint64_t* max_widths, const uint64_t* root_states,
                           const int64_t* root_values, const int32_t* root_depths, int64_t best_lb, const volatile int32_t* cutoff_flag,
                           ddo_completion* out) {
     GUARD_BEGIN
     if (!d || !max_widths || !root_states || !root_values || !root_depths) { set_error("null argument"); return DDO_ERR_INVALID; }
-    int rc = d->e.stage_roots(count, max_widths, root_states, root_values, root_depths);
+    int rc = d->ep->stage_roots(count, max_widths, root_states, root_values, root_depths);
     if (rc != DDO_OK) return rc;
-    rc = d->e.compile_staged(count, comp_type, best_lb, cutoff_flag, nullptr);
+    rc = d->ep->compile_staged(count, comp_type, best_lb, cutoff_flag, nullptr);
     if (rc != DDO_OK) return rc;
-    rc = d->e.fetch_ctl(count);
+    rc = d->ep->fetch_ctl(count);
     if (rc != DDO_OK) return rc;
-    if (out) for (int i = 0; i < count; ++i) d->e.fill_completion(i, out + i);
+    if (out) for (int i = 0; i < count; ++i) d->ep->fill_completion(i, out + i);
     return DDO_OK;
     GUARD_END
 }
@@ -76,27 +94,27 @@ int ddo_mdd_compile(ddo_mdd* d, int32_t comp_type, uint64_t max_width, const uin
 int ddo_mdd_best_solution(ddo_mdd* d, int32_t index, int32_t exact, ddo_decision* out, int32_t* len) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return d->e.best_solution(index, exact, out, len);
+    return d->ep->best_solution(index, exact, out, len);
     GUARD_END
 }
 int ddo_mdd_drain_cutset(ddo_mdd* d, int32_t index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs,
                          int32_t* depth_out, int32_t* path_len_out, ddo_decision* paths, int32_t* count) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return d->e.drain_cutset(index, ub_cap, lb_filter, states, values, ubs, depth_out, path_len_out, paths, count);
+    return d->ep->drain_cutset(index, ub_cap, lb_filter, states, values, ubs, depth_out, path_len_out, paths, count);
     GUARD_END
 }
 int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps, const int64_t* lb_filters, uint64_t* states, int64_t* values,
                                int64_t* ubs, int32_t* dd_index, uint64_t* path_bits, int32_t* path_words, int64_t* total) {
     GUARD_BEGIN
     if (!d || !ub_caps || !lb_filters || !total) { set_error("null argument"); return DDO_ERR_INVALID; }
-    Engine& e = d->e;
+    Engine& e = *d->ep;
     int pw = 1;
     const int n = e.drain_all(count, ub_caps, lb_filters, &pw);
     if (n < 0) return n;
     if (path_words) *path_words = pw;
     if ((int64_t)n > *total) { *total = n; set_error("drain_cutset_batch: buffer too small"); return DDO_ERR_CAPACITY; }
-    const int words = e.model->words;
+    const int words = e.abi_words;
     for (int r = 0; r < n; ++r) {
         if (states) for (int j = 0; j < words; ++j) states[(size_t)r * words + j] = e.h_out_state[(size_t)r * e.S + j];
         if (values) values[r] = e.h_out_val[r];
@@ -110,43 +128,43 @@ int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps
 }
 int ddo_mdd_set_profiling(ddo_mdd* d, int32_t on) {
     if (!d) return DDO_ERR_INVALID;
-    d->e.profiling = on != 0; d->e.prof_used = 0;
-    for (int i = 0; i < 6; ++i) { d->e.prof_ms[i] = 0; d->e.prof_launches[i] = 0; }
+    d->ep->profiling = on != 0; d->ep->prof_used = 0;
+    for (int i = 0; i < 6; ++i) { d->ep->prof_ms[i] = 0; d->ep->prof_launches[i] = 0; }
     return DDO_OK;
 }
 int ddo_mdd_kernel_times(ddo_mdd* d, double ms[6], uint64_t launches[6]) {
     if (!d || !ms || !launches) return DDO_ERR_INVALID;
-    for (int i = 0; i < 6; ++i) { ms[i] = d->e.prof_ms[i]; launches[i] = d->e.prof_launches[i]; }
+    for (int i = 0; i < 6; ++i) { ms[i] = d->ep->prof_ms[i]; launches[i] = d->ep->prof_launches[i]; }
     return DDO_OK;
 }
 int ddo_mdd_layer_trace(ddo_mdd* d, int32_t index, int32_t* vars, int32_t* widths, int32_t cap) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return d->e.layer_trace(index, vars, widths, cap);
+    return d->ep->layer_trace(index, vars, widths, cap);
     GUARD_END
 }
 int ddo_mdd_stage_roots(ddo_mdd* d, int32_t count, const uint64_t* max_widths, const uint64_t* root_states, const int64_t* root_values,
                         const int32_t* root_depths) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
-    int rc = d->e.stage_roots(count, max_widths, root_states, root_values, root_depths);
+    int rc = d->ep->stage_roots(count, max_widths, root_states, root_values, root_depths);
     if (rc != DDO_OK) return rc;
-    if (cudaStreamSynchronize(d->e.stream) != cudaSuccess) { set_error("stage_roots: sync failed"); return DDO_ERR_CUDA; }
+    if (cudaStreamSynchronize(d->ep->stream) != cudaSuccess) { set_error("stage_roots: sync failed"); return DDO_ERR_CUDA; }
     return DDO_OK;
     GUARD_END
 }
 int ddo_mdd_compile_staged(ddo_mdd* d, int32_t count, int32_t comp_type, int64_t best_lb, float* device_ms) {
     GUARD_BEGIN
     if (!d) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return d->e.compile_staged(count, comp_type, best_lb, nullptr, device_ms);
+    return d->ep->compile_staged(count, comp_type, best_lb, nullptr, device_ms);
     GUARD_END
 }
 int ddo_mdd_fetch_completions(ddo_mdd* d, int32_t count, ddo_completion* out) {
     GUARD_BEGIN
     if (!d || !out) { set_error("null argument"); return DDO_ERR_INVALID; }
-    int rc = d->e.fetch_ctl(count);
+    int rc = d->ep->fetch_ctl(count);
     if (rc != DDO_OK) return rc;
-    for (int i = 0; i < count; ++i) d->e.fill_completion(i, out + i);
+    for (int i = 0; i < count; ++i) d->ep->fill_completion(i, out + i);
     return DDO_OK;
     GUARD_END
 }
@@ -155,10 +173,14 @@ int ddo_solver_create(const ddo_model* m, ddo_mdd* d, int32_t width_kind, uint64
     GUARD_BEGIN
     if (!m || !d || !out) { set_error("null argument"); return DDO_ERR_INVALID; }
     if (wave_size < 1) { set_error("wave_size must be >= 1"); return DDO_ERR_INVALID; }
-    { int rr = d->e.reserve_roots(wave_size); if (rr != DDO_OK) return rr; }  // the wave may exceed batch_cap: only DDs that need a cut go through the general engine, batch_cap at a time
-    if (width_kind == DDO_WIDTH_FIXED && (width < 1 || width > (uint64_t)d->e.Wcap)) { set_error("width must be in [1, max_width_cap]"); return DDO_ERR_INVALID; }
-    if (width_kind == DDO_WIDTH_NB_UNASSIGNED && m->m->n > d->e.Wcap) { set_error("NbUnassignedWidth needs max_width_cap >= nb_variables"); return DDO_ERR_INVALID; }
-    *out = new ddo_solver{new Solver(m->m, &d->e, width_kind, width, wave_size)};
+    { int rr = d->ep->reserve_roots(wave_size); if (rr != DDO_OK) return rr; }  // the wave may exceed batch_cap: only DDs that need a cut go through the general engine, batch_cap at a time
+    if (width_kind == DDO_WIDTH_FIXED && (width < 1 || width > (uint64_t)d->ep->Wcap)) { set_error("width must be in [1, max_width_cap]"); return DDO_ERR_INVALID; }
+    if (m->kind != d->kind) { set_error("model and mdd are of different kinds"); return DDO_ERR_INVALID; }
+    if (width_kind == DDO_WIDTH_NB_UNASSIGNED && ddo_model_nb_variables(m) > d->ep->Wcap) { set_error("NbUnassignedWidth needs max_width_cap >= nb_variables"); return DDO_ERR_INVALID; }
+    std::vector<uint64_t> rs((size_t)ddo_model_state_words(m));
+    int64_t rv = 0;
+    ddo_model_initial_state(m, rs.data(), &rv);
+    *out = new ddo_solver{new Solver(d->ep, m->kind, rs.data(), rv, width_kind, width, wave_size)};
     return DDO_OK;
     GUARD_END
 }

@@ -92,7 +92,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
     if (dev != m->device) { set_error("model and mdd must live on the same device"); return DDO_ERR_INVALID; }
-    model = m; device = dev; cutset_type = cutset;
+    model = m; device = dev; cutset_type = cutset; n_vars = m->n; abi_words = m->words;
     K = batch_cap; Wcap = (int)((std::max<uint64_t>(max_width_cap, 2) + 1) & ~1ull); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
     Lmax = m->n + 1; PW = (Lmax + 63) / 64;
     CUDA_TRY(cudaSetDevice(dev));
@@ -173,13 +173,13 @@ int Engine::reserve_roots(int count) {
 
 int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
     if (count < 1 || count > root_cap) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
-    const int words = model->words;
+    const int words = abi_words;
     for (int i = 0; i < count; ++i) {
         if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
         if (values[i] < -(1ll << 30) || values[i] > (1ll << 30)) { set_error("root value outside the 31-bit device range"); return DDO_ERR_UNSUPPORTED; }
-        if (depths[i] < 0 || depths[i] > model->n) { set_error("root depth out of range"); return DDO_ERR_INVALID; }
+        if (depths[i] < 0 || depths[i] > n_vars) { set_error("root depth out of range"); return DDO_ERR_INVALID; }
         for (int j = 0; j < S; ++j) h_root_state[(size_t)i * S + j] = j < words ? states[(size_t)i * words + j] : 0;
-        if (model->n & 63) {
+        if (model && (model->n & 63)) {
             uint64_t mask = (1ull << (model->n & 63)) - 1;
             if (h_root_state[(size_t)i * S + words - 1] & ~mask) { set_error("root state has bits beyond nb_variables"); return DDO_ERR_INVALID; }
         }
@@ -373,7 +373,7 @@ int Engine::best_solution(int index, int exact, ddo_decision* out, int32_t* len)
     for (int i = 0; i < L; ++i) {  // reference order: terminal -> root (clean.rs:337-341)
         const int tt = L - 1 - i;
         out[i].variable = vars[tt];
-        out[i].value = (int32_t)((bits[tt >> 6] >> (tt & 63)) & 1);
+        out[i].value = bit_value[(bits[tt >> 6] >> (tt & 63)) & 1];
     }
     *len = L;
     return DDO_OK;
@@ -471,7 +471,7 @@ int Engine::drain_cutset(int index, int64_t ub_cap, int64_t lb_filter, uint64_t*
     if (total > *count) { *count = total; set_error("drain_cutset: buffer too small"); return DDO_ERR_CAPACITY; }
     std::vector<int32_t> vars;
     if (paths && total > 0) { int rc = fetch_vars(index, vars); if (rc != DDO_OK) return rc; }
-    const int words = model->words;
+    const int words = abi_words;
     for (int r = 0; r < total; ++r) {
         if (states) for (int j = 0; j < words; ++j) states[(size_t)r * words + j] = h_out_state[(size_t)r * S + j];
         if (values) values[r] = h_out_val[r];
@@ -480,7 +480,7 @@ int Engine::drain_cutset(int index, int64_t ub_cap, int64_t lb_filter, uint64_t*
             for (int i = 0; i < lel; ++i) {  // terminal -> root order (clean.rs:329-343)
                 const int tt = lel - 1 - i;
                 paths[(size_t)r * lel + i].variable = vars[tt];
-                paths[(size_t)r * lel + i].value = (int32_t)((h_out_path[(size_t)r * pw + (tt >> 6)] >> (tt & 63)) & 1);
+                paths[(size_t)r * lel + i].value = bit_value[(h_out_path[(size_t)r * pw + (tt >> 6)] >> (tt & 63)) & 1];
             }
     }
     *count = total;

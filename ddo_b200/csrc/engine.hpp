@@ -104,7 +104,9 @@ struct DrainOut {
 };
 
 struct Engine {
-    const MispModel* model = nullptr;
+    const MispModel* model = nullptr;  // null for engines of other device models (M2Engine)
+    int n_vars = 0, abi_words = 0;     // nb_variables and uint64 words of a packed state at the ABI
+    int32_t bit_value[2] = {0, 1};     // decision value of a path bit: MISP NO / YES; MAX2SAT F = -1 / T = +1
     int device = 0;
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
     int cutset_type = DDO_LAST_EXACT_LAYER;
@@ -133,12 +135,13 @@ struct Engine {
     void prof_mark(int kind);   // record an event; the interval since the previous mark is attributed to `kind`
     int prof_collect();
 
+    virtual ~Engine() = default;
     int create(const MispModel* m, int device, uint64_t max_width_cap, int batch_cap, int cutset_type);
-    void destroy();
+    virtual void destroy();
     int root_cap = 0;  // roots that can be staged at once (>= K): the wave size of the solver's fast path
-    int reserve_roots(int count);
+    virtual int reserve_roots(int count);
     int stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths);
-    int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
+    virtual int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
     // dual mode: `half` restricted DDs in slots [0,half); the relaxed twin of DD j forks into slot half+j at the first width cut and then
     // advances in the same launches (both against best_lb).  Results: ctl[j] restricted, ctl[half+j] relaxed (status WAITING = never forked).
     int compile_dual(int half, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms);
@@ -149,7 +152,7 @@ struct Engine {
                      int32_t* path_len_out, ddo_decision* paths, int32_t* count);
     int layer_trace(int index, int32_t* vars, int32_t* widths, int cap);
     // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
-    int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
+    virtual int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
     // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
     int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;
     int compile_small(int count, int64_t best_lb, float* device_ms);

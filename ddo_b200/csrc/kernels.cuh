@@ -955,13 +955,14 @@ __device__ __forceinline__ uint32_t plog_at(const EV& ev, const DDCtl* ctl, int 
 // =================================================================================================================
 // k_finalize: exact-best-path walk (clean.rs:634-655) and decision bits of the best / best exact path (clean.rs:329-343)
 // =================================================================================================================
-__global__ void k_finalize(EV ev, int count) {
+static __global__ void k_finalize(EV ev, int count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     DDCtl* ctl = ev.ctl + k;
     const size_t lb = (size_t)k * ev.Lmax;
     ctl->ebpo = 0;
-    if (ctl->overflow || !ctl->has_best) return;
+    if (ctl->overflow) return;
+    if (!ctl->has_best) { ctl->ebpo = ctl->comp_type == DDO_RELAXED; return; }  // _has_exact_best_path(None) == true (clean.rs:643-655): an infeasible relaxed DD is exact
     const int T = ctl->t_term;
     if (ctl->comp_type == DDO_RELAXED) {
         int pos = ctl->best_pos, tt = T;
@@ -994,7 +995,7 @@ __global__ void k_finalize(EV ev, int count) {
 // upper bounds ub = min(value_top + rub, value_top + value_bot, best_value) of the last exact layer (clean.rs:426-428).
 // =================================================================================================================
 constexpr int32_t UNMARKED = INT32_MIN;
-__global__ void __launch_bounds__(1024, 1) k_bottomup(EV ev) {
+static __global__ void __launch_bounds__(1024, 1) k_bottomup(EV ev) {
     const int k = blockIdx.x;
     DDCtl* ctl = ev.ctl + k;
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -1050,7 +1051,7 @@ __global__ void __launch_bounds__(1024, 1) k_bottomup(EV ev) {
 // =================================================================================================================
 // drain_cutset (clean.rs:417-445) + the solver-side filter (parallel.rs:460-461) as a batched stream compaction
 // =================================================================================================================
-__global__ void __launch_bounds__(1024, 1) k_cutset_count(EV ev, DrainOut o, const long long* ub_cap, const long long* lb_filter, int count) {
+static __global__ void __launch_bounds__(1024, 1) k_cutset_count(EV ev, DrainOut o, const long long* ub_cap, const long long* lb_filter, int count) {
     __shared__ int scan[40];
     const int k = blockIdx.x;
     const DDCtl* ctl = ev.ctl + k;
@@ -1069,7 +1070,7 @@ __global__ void __launch_bounds__(1024, 1) k_cutset_count(EV ev, DrainOut o, con
     }
     if (tid == 0) o.count[k] = total;
 }
-__global__ void k_cutset_offsets(DrainOut o, int K) {
+static __global__ void k_cutset_offsets(DrainOut o, int K) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int acc = 0;
         for (int k = 0; k < K; ++k) { o.offset[k] = acc; acc += o.count[k]; }

@@ -33,12 +33,15 @@ static int lex_cmp(const uint64_t* a, const uint64_t* b, int W) {
     }
     return 0;
 }
-int NoDupFringe::compare_new(int32_t ub, int32_t value, int16_t pc, const uint64_t* st, int b) const {  // subproblem_ranking.rs:86-90
-    const Item& y = items_[b];
-    if (ub != y.ub) return ub < y.ub ? -1 : 1;
-    if (value != y.value) return value < y.value ? -1 : 1;
-    if (pc != popc_[b]) return pc < popc_[b] ? -1 : 1;  // misp/main.rs:205-208
-    return lex_cmp(st, state(b), W);
+// canonical lexicographic order of two MAX2SAT states: benefits as signed integers, ascending variable id (oracle/models.hpp Max2SatRanking)
+static int lex_cmp_i32(const uint64_t* a, const uint64_t* b, int W) {
+    const int32_t* x = reinterpret_cast<const int32_t*>(a); const int32_t* y = reinterpret_cast<const int32_t*>(b);
+    for (int j = 0; j < 2 * W; ++j) if (x[j] != y[j]) return x[j] < y[j] ? -1 : 1;
+    return 0;
+}
+int NoDupFringe::state_cmp(int a, int b) const {
+    if (kind_ == DDO_MODEL_MAX2SAT) return lex_cmp_i32(state(a), state(b), W);
+    return lex_cmp(state(a), state(b), W);
 }
 
 static inline uint64_t lex_word_host(uint64_t w) {  // ~bitreverse: larger = Greater in BitSet::cmp among equal popcounts
@@ -51,7 +54,8 @@ NoDupFringe::Ent NoDupFringe::make_ent(int id) const {
     const Item& it = items_[id];
     Ent e;
     e.k1 = ((uint64_t)((uint32_t)it.ub ^ 0x80000000u) << 32) | ((uint32_t)it.value ^ 0x80000000u);
-    e.k2 = ((uint64_t)(uint16_t)popc_[id] << 48) | (lex_word_host(state(id)[0]) >> 16);
+    if (kind_ == DDO_MODEL_MAX2SAT) e.k2 = ((uint64_t)(uint32_t)popc_[id] << 32) | ((uint64_t)(uint32_t)it.depth << 8);  // (rank, depth)
+    else e.k2 = ((uint64_t)(uint16_t)popc_[id] << 48) | (lex_word_host(state(id)[0]) >> 16);
     e.id = id; e.ver = ver_[id];
     return e;
 }
@@ -59,7 +63,7 @@ bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
     if (a.k1 != b.k1) return a.k1 < b.k1;
     if (a.k2 != b.k2) return a.k2 < b.k2;
     if (a.id == b.id) return a.ver < b.ver;
-    return lex_cmp(state(a.id), state(b.id), W) < 0;  // same ub, value, popcount and 48 leading lexicographic bits
+    return state_cmp(a.id, b.id) < 0;  // same ub, value and ranking key prefix
 }
 
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
@@ -82,13 +86,13 @@ void NoDupFringe::table_insert(int id) {
     if (table_[s] == -1) ++table_used_;
     table_[s] = id;
 }
-int NoDupFringe::table_find(const uint64_t* st, uint64_t h) const {
+int NoDupFringe::table_find(const uint64_t* st, uint64_t h, int32_t depth) const {
     if (table_.empty()) return -1;
     const size_t mask = table_.size() - 1;
     size_t s = h & mask;
     while (table_[s] != -1) {
         const int id = table_[s];
-        if (id >= 0 && hash_[id] == h && std::memcmp(state(id), st, (size_t)W * 8) == 0) return id;
+        if (id >= 0 && hash_[id] == h && std::memcmp(state(id), st, (size_t)W * 8) == 0 && (kind_ != DDO_MODEL_MAX2SAT || items_[id].depth == depth)) return id;
         s = (s + 1) & mask;
     }
     return -1;
@@ -100,8 +104,8 @@ void NoDupFringe::table_erase(int id) {
     table_[s] = -2;
 }
 void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
-    const uint64_t h = hash_state(st, W);
-    const int found = table_find(st, h);
+    const uint64_t h = hash_state(st, W) ^ (kind_ == DDO_MODEL_MAX2SAT ? 0x9E3779B97F4A7C15ull * (uint64_t)(depth + 1) : 0ull);
+    const int found = table_find(st, h, depth);
     if (found >= 0) {  // Occupied, no_duplicate.rs:92-118: keep the longer path, ub = max of the known ubs
         const int id = found;
         const int32_t old_lp = items_[id].value, old_ub = items_[id].ub;
@@ -128,8 +132,9 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
     std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
     int pc = 0;
-    for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
-    popc_[id] = (int16_t)pc; hash_[id] = h;
+    if (kind_ == DDO_MODEL_MAX2SAT) { const int32_t* x = reinterpret_cast<const int32_t*>(st); for (int j = 0; j < 2 * W; ++j) pc += x[j] < 0 ? -x[j] : x[j]; }
+    else for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
+    popc_[id] = pc; hash_[id] = h;
     ++ver_[id];
     if ((table_used_ + 1) * 2 > table_.size()) rehash((live_ + 1) * 4);
     table_insert(id);
@@ -173,8 +178,9 @@ int NoDupFringe::pop() {
 // ---------------------------------------------------------------------------------------------------------------
 // Solver
 // ---------------------------------------------------------------------------------------------------------------
-Solver::Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws)
-    : model(m), eng(e), width_kind(wk), width(w), wave_size(ws), fringe(m->words, (m->n + 63) / 64) {
+Solver::Solver(Engine* e, int kind, const uint64_t* rs, int64_t rv, int wk, uint64_t w, int ws)
+    : eng(e), model_kind(kind), n_vars(e->n_vars), words(e->abi_words), root_state(rs, rs + e->abi_words), root_value(rv), width_kind(wk), width(w),
+      wave_size(ws), fringe(e->abi_words, (e->n_vars + 63) / 64, kind) {
     if (const char* p = std::getenv("DDO_WAVE_TRACE")) trace_file = std::fopen(p, "w");
 }
 
@@ -183,9 +189,8 @@ int Solver::init(bool push_root) {  // parallel.rs:368-385
     best_lb = INT64_MIN; best_ub = INT64_MAX; has_sol = false; best_sol.clear(); aborted = false;
     explored = expanded = transitions = compilations = waves = 0; device_ms = fringe_ms = 0;
     if (push_root) {
-        std::vector<uint64_t> st(model->words, 0), bits(1, 0);
-        for (int i = 0; i < model->n; ++i) st[i >> 6] |= 1ull << (i & 63);  // misp/main.rs:69-71
-        fringe.push(st.data(), 0, INT32_MAX, 0, -1, bits.data(), 0);
+        std::vector<uint64_t> bits(1, 0);
+        fringe.push(root_state.data(), (int32_t)root_value, INT32_MAX, 0, -1, bits.data(), 0);  // parallel.rs:368-385
     }
     return DDO_OK;
 }
@@ -194,11 +199,11 @@ void Solver::full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decisi
     if (rec == -1) return;
     const PathRec& r = recs[rec];
     full_path(r.parent_rec, r.parent_bits.data(), out);
-    for (size_t i = 0; i < r.vars.size(); ++i) out.push_back(ddo_decision{r.vars[i], (int32_t)((bits[i >> 6] >> (i & 63)) & 1)});
+    for (size_t i = 0; i < r.vars.size(); ++i) out.push_back(ddo_decision{r.vars[i], eng->bit_value[(bits[i >> 6] >> (i & 63)) & 1]});
 }
 
 int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
-    const int W = model->words, PWN = (model->n + 63) / 64;
+    const int W = words, PWN = (n_vars + 63) / 64;
     // ---- get_workload (parallel.rs:500-559): pop up to wave_size open sub-problems ---------------------------------------------
     double t0 = now_ms();
     int64_t top_ub = INT64_MIN;
@@ -224,7 +229,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     std::vector<int64_t> values(cnt);
     std::vector<int32_t> depths(cnt);
     for (int i = 0; i < cnt; ++i) {
-        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(model->n - w_items[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
+        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(n_vars - w_items[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
         values[i] = w_items[i].value; depths[i] = w_items[i].depth;
     }
     struct Res { bool exact = false, has = false; int32_t best = 0; };
@@ -251,7 +256,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         r2 = eng->compile_staged(1, comp_type, lb, cutoff_flag, &ms);
         if (r2 != DDO_OK) return r2;
         device_ms += ms;
-        std::vector<ddo_decision> dd(model->n + 1);
+        std::vector<ddo_decision> dd(n_vars + 1);
         int32_t len = (int32_t)dd.size();
         r2 = eng->best_solution(0, 1, dd.data(), &len);
         if (r2 != DDO_OK) return r2;
@@ -453,7 +458,7 @@ int Solver::retain_share(int rank, int nranks) {
     if (rank < 0 || rank >= nranks) { set_error("retain_share: bad rank"); return DDO_ERR_INVALID; }
     struct Keep { std::vector<uint64_t> state, bits; NoDupFringe::Item it; };
     std::vector<Keep> keep;
-    const int W = model->words, PWN = (model->n + 63) / 64;
+    const int W = words, PWN = (n_vars + 63) / 64;
     for (size_t idx = 0; !fringe.empty(); ++idx) {
         const int id = fringe.pop();
         if ((int)(idx % (size_t)nranks) != rank) continue;

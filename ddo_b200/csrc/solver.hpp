@@ -25,7 +25,10 @@ struct PathRec {
 
 class NoDupFringe {
 public:
-    NoDupFringe(int words, int pw) : W(words), PW(pw) {}
+    // kind: DDO_MODEL_MISP -- MispRanking (popcount, BitSet::cmp), states compared without their depth (BitSet alone is the state);
+    //       DDO_MODEL_MAX2SAT -- Max2SatRanking (rank = sum |benefit|, heuristics.rs:33-37) refined canonically by (depth, lexicographic
+    //       benefits); the depth is part of the state (model.rs:59-62 derives Hash / Eq over both fields).
+    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) {}
     struct Item { int32_t value, ub, depth, rec; };
     size_t len() const { return live_; }
     bool empty() const { return live_ == 0; }
@@ -43,10 +46,10 @@ private:
     // next wave), so the same order is served by sorted runs: a burst of pushes is sorted once into a new run, a pop takes the largest of
     // the runs' tails.  An entry is stale when its node was popped or re-keyed since (version mismatch) and is skipped.
     struct Ent { uint64_t k1, k2; int id; uint32_t ver; };
-    int W, PW;
+    int W, PW, kind_;
     std::vector<uint64_t> states_, bits_;
     std::vector<Item> items_;
-    std::vector<int16_t> popc_;
+    std::vector<int32_t> popc_;  // ranking key of the state: popcount (MISP) / sum |benefit| (MAX2SAT)
     std::vector<uint64_t> hash_;
     std::vector<uint32_t> ver_;
     std::vector<int> recycle_;
@@ -57,17 +60,18 @@ private:
     size_t table_used_ = 0;   // occupied + tombstones
     Ent make_ent(int id) const;
     bool ent_less(const Ent& a, const Ent& b) const;  // a strictly below b in the MaxUB order
-    int compare_new(int32_t ub, int32_t value, int16_t pc, const uint64_t* st, int b) const;
+    int state_cmp(int a, int b) const;  // final tie-break of the ranking between two stored nodes
     void flush_pending();
     void table_insert(int id);
-    int table_find(const uint64_t* st, uint64_t h) const;
+    int table_find(const uint64_t* st, uint64_t h, int32_t depth) const;
     void table_erase(int id);
     void rehash(size_t min_cap);
     static uint64_t hash_state(const uint64_t* st, int W);
 };
 
 struct Solver {
-    const MispModel* model; Engine* eng;
+    Engine* eng; int model_kind; int n_vars, words;
+    std::vector<uint64_t> root_state; int64_t root_value;  // Problem::initial_state / initial_value
     int width_kind; uint64_t width; int wave_size;
     NoDupFringe fringe;
     std::vector<PathRec> recs;
@@ -80,7 +84,7 @@ struct Solver {
     // scratch of one wave (kept to avoid reallocations)
     std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars;
 
-    Solver(const MispModel* m, Engine* e, int wk, uint64_t w, int ws);
+    Solver(Engine* e, int model_kind, const uint64_t* root_state, int64_t root_value, int wk, uint64_t w, int ws);
     int init(bool push_root);
     int wave(const volatile int32_t* cutoff_flag, int64_t out3[3]);
     int maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact, int32_t* has_value, int64_t* best_value);

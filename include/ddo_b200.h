@@ -39,6 +39,9 @@ extern "C" {
 #define DDO_LAST_EXACT_LAYER 1
 #define DDO_FRONTIER 2
 /* WidthHeuristic, src/implementation/heuristics/width.rs:166-170 (FixedWidth), :397-401 (NbUnassignedWidth) */
+#define DDO_MODEL_MISP 0      /* examples/misp/main.rs */
+#define DDO_MODEL_MAX2SAT 1   /* examples/max2sat/{model,relax,heuristics}.rs */
+
 #define DDO_WIDTH_FIXED 0
 #define DDO_WIDTH_NB_UNASSIGNED 1
 
@@ -76,6 +79,15 @@ uint64_t ddo_kernel_launches(void);         /* count of this library's kernel la
  * main.rs:299-307 converts the file's 1-based ids).  Uploads the complement-adjacency rows once (main.rs:40-45). */
 int ddo_model_create_misp(int32_t n, const int64_t* weights, int64_t m, const int32_t* edge_src, const int32_t* edge_dst,
                           int device, ddo_model** out);
+/* ---- model: examples/max2sat/model.rs:98-349 (Max2Sat), relax.rs:43-89 (Max2SatRelax), heuristics.rs:30-37 (Max2SatRanking) ---- */
+/* n variables, m clauses as int64 triples (weight, literal x, literal y); the literal of variable i (0-based) is +-(i+1), x == y encodes a
+ * unit clause (data.rs:31-58).  A repeated clause keeps its LAST weight (data.rs:99,106 insert into a hash map).  Uploads the clause-weight
+ * rows of every branching variable and the fast_upper_bound tables (model.rs:183-238) once.  A state is n int32 marginal benefits
+ * (model.rs:59-62), packed two per uint64 word at this ABI; its depth travels as root_depth.  Decision values: T = 1, F = -1 (model.rs:30-32).
+ * Canonical refinements where the reference leaves ties to unstable sorts: variable order ties by variable id (model.rs:149-151); ranking
+ * ties (equal sum |benefit|) by depth, then lexicographic signed benefits. */
+int ddo_model_create_max2sat(int32_t n, int64_t m, const int64_t* clauses, int device, ddo_model** out);
+int32_t ddo_model_kind(const ddo_model*);           /* DDO_MODEL_* */
 void ddo_model_destroy(ddo_model*);
 int32_t ddo_model_nb_variables(const ddo_model*);   /* Problem::nb_variables, src/abstraction/dp.rs:39 */
 int32_t ddo_model_state_words(const ddo_model*);    /* uint64 words of one packed state (bit v of the BitSet = bit v%64 of word v/64) */

@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 import oracle_lib as O
-from ddo_b200 import CompilationType, GpuMdd, Misp, SubProblem
+from ddo_b200 import CompilationType, GpuMdd, Max2Sat, Misp, SubProblem
 from ddo_b200 import _native as N
 
 CT = {O.EXACT: CompilationType.Exact, O.RELAXED: CompilationType.Relaxed, O.RESTRICTED: CompilationType.Restricted}
@@ -48,11 +48,11 @@ def compare_dd(oracle: O.OracleMisp, mdd: GpuMdd, index: int, comp_type: int, wi
     return ref
 
 
-def check_instance(inst, widths, comp_types=(O.RESTRICTED, O.RELAXED), best_lbs=(N.I64_MIN,), batch=None, roots=None, check_paths=True):
+def check_instance(inst, widths, comp_types=(O.RESTRICTED, O.RELAXED), best_lbs=(N.I64_MIN,), batch=None, roots=None, check_paths=True, model="misp"):
     """Compile the given roots (default: the problem root) for every width / type / best_lb, batched on the device, and compare each DD."""
-    oracle = O.OracleMisp(inst)
-    pb = Misp(inst)
-    roots = roots or [SubProblem(inst.initial_state(), 0, [], N.I64_MAX, 0)]
+    oracle = O.OracleMisp(inst) if model == "misp" else O.OracleM2s(inst)
+    pb = Misp(inst) if model == "misp" else Max2Sat(inst)
+    roots = roots or [SubProblem(inst.initial_state(), pb.initial_value(), [], N.I64_MAX, 0)]
     jobs = [(w, r) for w in widths for r in roots]
     mdd = GpuMdd(pb, max(max(widths), 2), batch or len(jobs))
     n = 0
