@@ -31,6 +31,43 @@ for p in (str(ROOT), str(ROOT / "tests")):
 METRIC = "MDD nodes expanded/s, MISP n=500 width=10000"
 UNIT = "nodes/s"
 N_VERT, P_EDGE, SEED, WIDTH = 500, 0.5, 1, 10000
+# --workload max2sat: BASELINE config 3 (a secondary line; the headline metric is config 2 above)
+M2S_METRIC = "MDD nodes expanded/s, MAX2SAT 500 vars / 3000 clauses width=5000"
+M2S_VARS, M2S_CLAUSES, M2S_WIDTH = 500, 3000, 5000
+
+
+class Workload:
+    """What differs between the two measured configurations: instance, device model, oracle, the work of one step."""
+
+    def __init__(self, args):
+        self.kind = args.workload
+        if self.kind == "misp":
+            from ddo_b200.instances import gnp
+            self.inst = gnp(N_VERT, P_EDGE, SEED)
+            self.metric, self.width = METRIC, WIDTH
+            self.desc = f"MISP G({N_VERT},{P_EDGE}) seed {SEED}, FixedWidth({WIDTH}), LEL cutset, NoDupFringe/MaxUB"
+            self.step_desc = "Solver::maximize to proven optimality"
+            self.max_waves = 0
+            self.dtype = "u64 bitset / i32 value"
+        else:
+            from ddo_b200.instances import random_max2sat
+            self.inst = random_max2sat(M2S_VARS, M2S_CLAUSES, SEED)
+            self.metric, self.width = M2S_METRIC, M2S_WIDTH
+            self.desc = f"MAX2SAT random {M2S_VARS} vars / {M2S_CLAUSES} clauses seed {SEED}, FixedWidth({M2S_WIDTH}), LEL cutset, NoDupFringe/MaxUB"
+            self.max_waves = args.max_waves or 2
+            self.step_desc = f"Solver::maximize cut off after {self.max_waves} waves (the instance is far beyond proof of optimality; every step repeats the same deterministic search prefix)"
+            self.dtype = "i32 benefit vector / i32 value"
+
+    def problem(self, device):
+        from ddo_b200 import Max2Sat, Misp
+        return Misp(self.inst, device=device) if self.kind == "misp" else Max2Sat(self.inst, device=device)
+
+    def oracle(self):
+        import oracle_lib as O
+        return O.OracleMisp(self.inst) if self.kind == "misp" else O.OracleM2s(self.inst)
+
+    def state_bytes(self, pb):
+        return pb.words * 8 if self.kind == "misp" else 4 * self.inst.n
 
 
 def load_peaks():
@@ -89,7 +126,7 @@ class ClockSampler:
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from ddo_b200 import FixedWidth, Misp, ParNoCachingSolverLel, gnp, kernel_launches
+    from ddo_b200 import FixedWidth, ParNoCachingSolverLel, kernel_launches
     from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
 
     if not torch.cuda.is_available():
@@ -97,9 +134,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    inst = gnp(N_VERT, P_EDGE, SEED)
-    pb = Misp(inst, device=local_rank)
-    solver = ParNoCachingSolverLel(pb, FixedWidth(WIDTH), wave_size=args.wave, batch_cap=args.batch_cap)
+    wl = Workload(args)
+    inst = wl.inst
+    pb = wl.problem(local_rank)
+    solver = ParNoCachingSolverLel(pb, FixedWidth(wl.width), wave_size=args.wave, batch_cap=args.batch_cap)
     sampler = ClockSampler(local_rank)
     allred = torch_allreduce_max(torch.device("cuda", local_rank)) if world > 1 else None
 
@@ -113,10 +151,10 @@ def run_ours(args, rank, world, local_rank):
         s0 = solver.stats()
         t0 = time.perf_counter()
         if world == 1:
-            comp = solver.maximize()
+            comp = solver.maximize(max_waves=wl.max_waves)
             res = {"best_lb": solver.best_lower_bound(), "best_ub": solver.best_upper_bound(), "is_exact": comp.is_exact}
         else:
-            res = sharded_maximize(solver, rank, world, allred)
+            res = sharded_maximize(solver, rank, world, allred, max_waves=wl.max_waves)
         wall = time.perf_counter() - t0
         s1 = solver.stats()
         # init() resets the counters, so s1 holds this step only (bytes are cumulative engine counters)
@@ -161,14 +199,14 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
         return
     cbar = transitions_all / max(expanded_all, 1)
-    S_bytes = pb.words * 8
+    S_bytes = wl.state_bytes(pb)
     b_node = (S_bytes + 8) + cbar * (S_bytes + 16)  # read the parent once, write each child once
     peak, peak_src = load_peaks()
     line = {
-        "metric": METRIC, "value": expanded_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset / i32 value",
+        "metric": wl.metric, "value": expanded_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": wl.dtype,
         "data": "synthetic", "impl": "ddo_b200",
-        "config": {"workload": f"Solver::maximize to proven optimality, MISP G({N_VERT},{P_EDGE}) seed {SEED}, FixedWidth({WIDTH}), LEL cutset, NoDupFringe/MaxUB",
+        "config": {"workload": f"{wl.step_desc}, {wl.desc}",
                    "wave_size": args.wave, "batch_cap": args.batch_cap, "objective": int(last["best_lb"]), "proven_upper_bound": int(last["best_ub"]), "is_exact": bool(last["is_exact"]),
                    "explored_subproblems": int(explored_all), "expanded_nodes_per_step": int(expanded_all / args.steps), "waves_per_step_rank0": int(last["waves"]),
                    "l2": "no L2 flush: every step re-runs the whole search (thousands of launches over >10 GB of arenas), far beyond the 126 MB L2",
@@ -181,13 +219,15 @@ def run_ours(args, rank, world, local_rank):
         "host_fringe_ms_per_step": last["fringe_ms"],
     }
     if kt is not None:
-        dom = max(("k_expand", "k_finish", "k_compact", "k_small"), key=lambda k: kt[k]["ms"])
+        if wl.kind != "misp":
+            kt["m2_merge"] = kt.pop("k_small")  # the MAX2SAT engine times its merge kernels in that slot
+        dom = max((k for k in kt if k not in ("k_finalize_bottomup", "k_drain")), key=lambda k: kt[k]["ms"])
         dom_gbs = last["expanded"] * b_node / (kt[dom]["ms"] * 1e-3) / 1e9
         traffic = None
-        tf = ROOT / "profiles" / "r01_traffic.json"
+        tf = ROOT / "profiles" / ("r01_traffic.json" if wl.kind == "misp" else "r01_traffic_max2sat.json")
         if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
             t = json.loads(tf.read_text())
-            if t["kernel"].startswith(dom):
+            if t["kernel"].startswith(dom) or t["kernel"].startswith(dom.replace("k_", "m2_")):
                 traffic = {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"], "context": t["context"]}
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
                             "peak_source": peak_src, "bytes_per_node": b_node, "mean_out_degree": cbar,
@@ -196,23 +236,41 @@ def run_ours(args, rank, world, local_rank):
                             "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak,
                             "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(inst, args.cpu_seconds)
+        line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(inst, budget_s: float):
+def cpu_baseline(wl, budget_s: float):
     """The CPU oracle's ParallelSolver ("restated reference": per-node heap states, hash-map dedup, full comparison sort for the width
     cut, one mutex-protected fringe) on all host cores, same instance and width, under a TimeBudget (heuristics/cutoff.rs:302-323) --
     a BOUNDED sample of the same search; the rate is expanded nodes / elapsed."""
-    import oracle_lib as O
-
     cores = os.cpu_count() or 1
-    r = O.OracleMisp(inst).solve("parallel", k=cores, width=WIDTH, time_budget_s=budget_s)
+    if wl.kind == "max2sat":
+        return cpu_sample_max2sat(wl, cores, budget_s)
+    r = wl.oracle().solve("parallel", k=cores, width=wl.width, time_budget_s=budget_s)
     return {"value": r["expanded"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"ParallelSolver({cores} threads) maximize() with TimeBudget({budget_s:g} s): {r['explored']} sub-problems explored, "
                       f"{r['expanded']} nodes expanded in {r['seconds']:.1f} s, lb={r['best_lb']} (finished={bool(r['is_exact'])})",
+            "expanded": int(r["expanded"]), "seconds": r["seconds"]}
+
+
+def cpu_sample_max2sat(wl, cores: int, budget_s: float):
+    """MAX2SAT at W = 5000 takes the CPU path more than a minute per DD, and a ParallelSolver run starts with ONE open sub-problem (its other
+    threads idle until the root DDs are done), so a bounded sample of `maximize()` would time a single thread.  Instead every thread gets work
+    from the start: the exact cutset of a narrow relaxed root DD (W = cores) gives >= cores independent sub-problems of the same search,
+    and `cores` workers compile their restricted + relaxed DDs at the full width under a TimeBudget (the ParallelSolver worker body,
+    parallel.rs:391-437, without the fringe); layers expanded before the cutoff count."""
+    import oracle_lib as O
+
+    o = wl.oracle()
+    r0 = o.compile(O.RELAXED, max(cores, 2))
+    n = int(r0["cutset_size"])
+    r = o.compile_many(r0["cutset_states"], r0["cutset_values"], r0["cutset_depths"], [wl.width] * n, O.I64_MIN, cores, time_budget_s=budget_s)
+    return {"value": r["expanded"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} worker threads compiling restricted + relaxed DDs (W={wl.width}) of {n} independent depth-{int(r0['cutset_depths'][0])} sub-problems under "
+                      f"TimeBudget({budget_s:g} s): {r['expanded']} nodes expanded in {r['seconds']:.1f} s",
             "expanded": int(r["expanded"]), "seconds": r["seconds"]}
 
 
@@ -224,9 +282,24 @@ def run_reference(args, rank, world):
     import oracle_lib as O
     from ddo_b200.instances import gnp
 
-    inst = gnp(N_VERT, P_EDGE, SEED)
-    o = O.OracleMisp(inst)
+    wl = Workload(args)
     cores = os.cpu_count() or 1
+    if wl.kind == "max2sat":
+        exp, sec, smp = 0, 0.0, None
+        budget = max(10.0, min(args.cpu_seconds, 200.0 / max(args.steps + args.warmup, 1)))
+        for i in range(args.warmup + args.steps):
+            smp = cpu_sample_max2sat(wl, cores, budget)
+            if i >= args.warmup:
+                exp += smp["expanded"]; sec += smp["seconds"]
+        v = exp / sec
+        line = {"metric": wl.metric, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i64 benefit vector / i64 value", "data": "synthetic", "impl": "reference",
+                "config": {"workload": f"time-boxed DD compilations, {wl.desc}", "note": "oracle port of ddo's DD compilation (Rust toolchain absent); CPU only, rank 0 only"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp["sample"]},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    o = wl.oracle()
     budget = max(10.0, min(args.cpu_seconds, 200.0 / max(args.steps, 1)))
     small = gnp(200, 0.5, SEED)
     os_ = O.OracleMisp(small)
@@ -234,13 +307,13 @@ def run_reference(args, rank, world):
         os_.solve("parallel", k=cores, width=100, time_budget_s=2.0)
     exp, sec, last = 0, 0.0, None
     for _ in range(args.steps):
-        last = o.solve("parallel", k=cores, width=WIDTH, time_budget_s=budget)
+        last = o.solve("parallel", k=cores, width=wl.width, time_budget_s=budget)
         exp += last["expanded"]; sec += last["seconds"]
     v = exp / sec
     sample = f"ParallelSolver({cores} threads) maximize() under TimeBudget({budget:g} s) per step"
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset / i64 value", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"Solver::maximize (time-boxed), MISP G({N_VERT},{P_EDGE}) seed {SEED}, FixedWidth({WIDTH}), LEL cutset, NoDupFringe/MaxUB",
+    line = {"metric": wl.metric, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": wl.dtype.replace("i32 value", "i64 value"), "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"Solver::maximize (time-boxed), {wl.desc}",
                        "note": "oracle port of ddo's ParallelSolver (Rust toolchain absent); CPU only, rank 0 only", "lb_at_cutoff": int(last["best_lb"])},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -256,8 +329,13 @@ def main():
     ap.add_argument("--batch-cap", type=int, default=512, help="DDs the general (layer-by-layer) engine compiles in lock-step")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="TimeBudget of the CPU baseline sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="misp", choices=["misp", "max2sat"], help="misp = BASELINE config 2 (the headline metric); max2sat = config 3")
+    ap.add_argument("--max-waves", type=int, default=0, help="max2sat: waves per step (default 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave
+        if args.wave == 2048: args.wave = 64
+        if args.batch_cap == 512: args.batch_cap = 64
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

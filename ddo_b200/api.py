@@ -276,7 +276,7 @@ class GpuMdd:
         ms = (C.c_double * 6)()
         ln = (C.c_uint64 * 6)()
         N.lib().ddo_mdd_kernel_times(self.h, C.byref(ms), C.byref(ln))
-        names = ["k_expand", "k_finish", "k_compact", "k_finalize_bottomup", "k_drain", "k_small"]
+        names = ["k_expand", "k_finish", "k_compact", "k_finalize_bottomup", "k_drain", "k_small"]  # MAX2SAT engine: slot "k_small" = merge kernels
         return {n: {"ms": ms[i], "launches": int(ln[i])} for i, n in enumerate(names)}
 
     def layer_trace(self, index: int = 0):

@@ -174,6 +174,9 @@ int M2Engine::create_m2s(const M2Model* m, int dev, uint64_t max_width_cap, int 
     ALLOC(v.cand_state, KC * NW); ALLOC(v.cand_rep, KC); ALLOC(v.cand_first, KC); ALLOC(v.cand_agg, KC); ALLOC(v.cand_inex, KC);
     ALLOC(v.cand_rank, KC); ALLOC(v.cand_slot, KC); ALLOC(v.cand_cost, KC);
     ALLOC(v.uflag, KC); ALLOC(v.ulist, KC); ALLOC(v.ustat, KC); ALLOC(v.pos_of, KC); ALLOC(v.gkeys, KC);
+    finish_smem = (size_t)C * 9 + 16;  // keys (8 B) + status (1 B) of up to C distinct candidates next to ~9 KB of static shared memory
+    v.smem_keys = finish_smem <= 200 * 1024;
+    if (!v.smem_keys) finish_smem = 0;
     ALLOC(v.table, (size_t)K * T);
     ALLOC(v.mrg_min, (size_t)K * NW); ALLOC(v.mrg_max, (size_t)K * NW);
     ALLOC(v.plog, KL * Wcap); ALLOC(v.clog, KL * C); ALLOC(v.colog, KL * C); ALLOC(v.nlog, KL); ALLOC(v.vlog, KL); ALLOC(v.rslog, KL * 3);
@@ -217,6 +220,10 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
     const M2EV& v = mv;
     CUDA_TRY(cudaMemsetAsync(v.table, 0xFF, (size_t)count * T * 8, st));
     CUDA_TRY(cudaEventRecord(ev0, st));
+    if (finish_smem && !finish_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(m2_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finish_smem));
+        finish_attr_set = true;
+    }
     m2_init<<<count, 256, 0, st>>>(v, count, comp_type, (long long)best_lb);
     ++g_kernel_launches;
     prof_mark(-1);
@@ -228,14 +235,15 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
     const int CHUNK = 16;
     int rc = DDO_OK;
     for (int t = 0; t < Lmax; ++t) {
-        m2_finish<<<count, 1024, 0, st>>>(v, t);
+        m2_finish<<<count, 1024, finish_smem, st>>>(v, t);
         ++g_kernel_launches;
+        prof_mark(1);
         if (relaxed && t >= 2) {
             m2_merge<<<merge_grid, 256, 0, st>>>(v);
             m2_merge_fin<<<count, 256, 0, st>>>(v, t);
             g_kernel_launches += 2;
+            prof_mark(5);
         }
-        prof_mark(1);
         m2_compact<<<flat_grid, 256, 0, st>>>(v, t, count);
         prof_mark(2);
         switch (ch) {

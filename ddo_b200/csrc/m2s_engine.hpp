@@ -24,7 +24,7 @@ struct M2Aux {  // per DD, per layer step: what m2_finish hands to the merge ker
 };
 
 struct M2EV {
-    int K, Wcap, C, T, Lmax, n, NW, NW4, PW;
+    int K, Wcap, C, T, Lmax, n, NW, NW4, PW, smem_keys;
     // model (device resident, immutable)
     const int32_t* ord;                                   // vars_by_sum_of_clause_weights, model.rs:149-151
     const int32_t *PT, *QT, *PF, *QF;                     // [n][NW] clause-weight rows of the branching variable (see m2s_engine.cu)

@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(1024, 1) m2_finish(M2EV ev, int t) {
     M2Aux* aux = ev.aux + k;
     const size_t cb = (size_t)k * ev.C;
     const size_t lb = (size_t)k * ev.Lmax;
-    unsigned long long* keys = ev.gkeys + cb;
-    uint8_t* stat = ev.ustat + cb;
+    // cut keys / status bytes of the distinct candidates: shared memory when 2*Wcap of them fit (ev.smem_keys), else global scratch
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned long long* keys = ev.smem_keys ? reinterpret_cast<unsigned long long*>(dyn_smem) : ev.gkeys + cb;
+    uint8_t* stat = ev.smem_keys ? dyn_smem + (size_t)ev.C * 8 : ev.ustat + cb;
     const int status = ctl->status;
     bool live = true;
     if (status == ST_DONE) live = false;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(1024, 1) m2_finish(M2EV ev, int t) {
                 mkey = max(mkey, pack_key(key_value(a) + (int32_t)ev.cand_rank[cb + c], (uint32_t)a));
             }
             mkey = block_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+            if (ev.smem_keys) for (int ui = tid; ui < U; ui += NT) ev.ustat[cb + ui] = stat[ui];  // the merge kernels read the status from global memory
             for (int i = tid; i < ev.NW; i += NT) { ev.mrg_min[(size_t)k * ev.NW + i] = INT32_MAX; ev.mrg_max[(size_t)k * ev.NW + i] = INT32_MIN; }
             if (tid == 0) { aux->cut_relaxed = 1; aux->nkeep = nkeep; aux->U = U; aux->mkey = mkey; aux->mpos = nkeep; aux->rank_m = 0; }
             n_next = nkeep + 1;  // the merged node, or (recycled corner case, clean.rs:868-871) the saved node

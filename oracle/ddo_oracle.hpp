@@ -1242,12 +1242,12 @@ private:
         size_t width = c_.width->max_width(node);
         CompilationInput<S> in{CompilationType::Restricted, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, width, &node, lb, c_.cache, c_.dominance};
         Completion comp;
-        if (!mdd.compile(in, &comp)) return false;
+        if (!mdd.compile(in, &comp)) { account_aborted(mdd); return false; }
         maybe_update_best(mdd);
         if (comp.is_exact) return true;
         in.comp_type = CompilationType::Relaxed;
         in.best_lb = read_lb();
-        if (!mdd.compile(in, &comp)) return false;
+        if (!mdd.compile(in, &comp)) { account_aborted(mdd); return false; }
         maybe_update_best(mdd);
         if (!comp.is_exact) {  // enqueue_cutset :456-469
             std::lock_guard<std::mutex> g(mu_);
@@ -1263,6 +1263,8 @@ private:
         }
         return true;
     }
+    // metric counter only: the layers a DD expanded before Cutoff::must_stop fired (clean.rs:352) still count as work done
+    void account_aborted(const Mdd<S, Hash, Eq>& mdd) { std::lock_guard<std::mutex> g(mu_); stats.expanded += mdd.expanded; stats.transitions += mdd.transitions; }
     void maybe_update_best(const Mdd<S, Hash, Eq>& mdd) {  // parallel.rs:446-453
         std::lock_guard<std::mutex> g(mu_);
         stats.compilations++; stats.expanded += mdd.expanded; stats.transitions += mdd.transitions;

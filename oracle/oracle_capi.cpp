@@ -270,41 +270,50 @@ void oracle_m2s_stepper_init(void* s, int32_t push_root) { ((Stepper<M2Handle>*)
 int32_t oracle_m2s_stepper_wave(void* s, int64_t out3[3]) { return stepper_wave((Stepper<M2Handle>*)s, out3); }
 void oracle_m2s_stepper_state(void* s, int64_t out[6]) { stepper_state((Stepper<M2Handle>*)s, out); }
 
-// CPU baseline of one bench "step": for each root, restricted DD then (if inexact) relaxed DD, all against the same best_lb,
-// on `threads` worker threads each owning one Mdd (the ParallelSolver worker body, parallel.rs:391-437, without the fringe).
+// CPU baseline of a batch of independent sub-problems: for each root, restricted DD then (if inexact) relaxed DD, all against the same
+// best_lb, on `threads` worker threads each owning one Mdd (the ParallelSolver worker body, parallel.rs:391-437, without the fringe).
+// time_budget_s > 0: a TimeBudget cutoff (cutoff.rs:302-323) stops every worker; the layers expanded before the cutoff still count.
 // per-root outputs (all optional): best exact value of the restricted DD (or INT64_MIN), best value of the relaxed DD (or INT64_MIN),
 // cutset size.  Returns total expanded nodes; *seconds = wall-clock.
-uint64_t oracle_misp_compile_many(void* hp, int32_t threads, int32_t n_roots, const uint64_t* root_states, const int64_t* root_values,
-                                  const int32_t* root_depths, const uint64_t* widths, int64_t best_lb, int32_t cutset_type,
-                                  int64_t* restricted_best, int64_t* relaxed_best, int32_t* cutset_sizes, uint64_t* transitions_out, double* seconds) {
-    MispHandle* h = (MispHandle*)hp;
-    size_t W = h->pb.words;
+}  // extern "C"
+namespace {
+template <class H>
+uint64_t compile_many(H* h, int32_t threads, int32_t n_roots, const uint64_t* root_states, const int64_t* root_values, const int32_t* root_depths,
+                      const uint64_t* widths, int64_t best_lb, int32_t cutset_type, double time_budget_s, int64_t* restricted_best,
+                      int64_t* relaxed_best, int32_t* cutset_sizes, uint64_t* transitions_out, double* seconds) {
+    using S = typename H::State;
+    size_t W = h->abi_words();
     std::atomic<int32_t> next{0};
     std::atomic<uint64_t> expanded{0}, transitions{0};
+    NoCutoff nocut; std::unique_ptr<TimeBudget> tb;
+    const Cutoff* cut = &nocut;
+    if (time_budget_s > 0) { tb.reset(new TimeBudget(time_budget_s)); cut = tb.get(); }
     double t0 = now_s();
     auto work = [&]() {
-        MispMdd mdd(cutset_type);
-        EmptyCache<BitState> cache; EmptyDominanceChecker<BitState> dom; NoCutoff nocut;
+        Mdd<S, typename H::Hash, typename H::Eq> mdd(cutset_type);
+        EmptyCache<S> cache; EmptyDominanceChecker<S> dom;
         uint64_t exp = 0, tr = 0;
         for (;;) {
             int32_t i = next.fetch_add(1);
             if (i >= n_roots) break;
-            BitState s; s.w.assign(root_states + (size_t)i * W, root_states + (size_t)(i + 1) * W);
-            SubProblem<BitState> root{std::make_shared<const BitState>(std::move(s)), root_values[i], {}, ISIZE_MAX, (size_t)root_depths[i]};
-            CompilationInput<BitState> in{CompilationType::Restricted, &h->pb, &h->rlx, &h->rk, &nocut, (size_t)widths[i], &root, best_lb, &cache, &dom};
+            SubProblem<S> root{std::make_shared<const S>(h->state_from_abi(root_states + (size_t)i * W, (size_t)root_depths[i])), root_values[i], {}, ISIZE_MAX,
+                               (size_t)root_depths[i]};
+            CompilationInput<S> in{CompilationType::Restricted, &h->pb, &h->rlx, &h->rk, cut, (size_t)widths[i], &root, best_lb, &cache, &dom};
             Completion c;
-            mdd.compile(in, &c);
+            bool ok = mdd.compile(in, &c);
             exp += mdd.expanded; tr += mdd.transitions;
+            if (!ok) break;
             if (restricted_best) restricted_best[i] = mdd.best_exact_value().value_or(ISIZE_MIN);
             if (relaxed_best) relaxed_best[i] = ISIZE_MIN;
             if (cutset_sizes) cutset_sizes[i] = 0;
             if (c.is_exact) continue;
             in.comp_type = CompilationType::Relaxed;
-            mdd.compile(in, &c);
+            ok = mdd.compile(in, &c);
             exp += mdd.expanded; tr += mdd.transitions;
+            if (!ok) break;
             if (relaxed_best) relaxed_best[i] = mdd.best_value().value_or(ISIZE_MIN);
             int32_t n = 0;
-            if (!c.is_exact) mdd.drain_cutset([&](SubProblem<BitState>) { ++n; });
+            if (!c.is_exact) mdd.drain_cutset([&](SubProblem<S>) { ++n; });
             if (cutset_sizes) cutset_sizes[i] = n;
         }
         expanded += exp; transitions += tr;
@@ -315,6 +324,20 @@ uint64_t oracle_misp_compile_many(void* hp, int32_t threads, int32_t n_roots, co
     if (seconds) *seconds = now_s() - t0;
     if (transitions_out) *transitions_out = transitions.load();
     return expanded.load();
+}
+}  // namespace
+extern "C" {
+uint64_t oracle_misp_compile_many(void* hp, int32_t threads, int32_t n_roots, const uint64_t* root_states, const int64_t* root_values,
+                                  const int32_t* root_depths, const uint64_t* widths, int64_t best_lb, int32_t cutset_type,
+                                  int64_t* restricted_best, int64_t* relaxed_best, int32_t* cutset_sizes, uint64_t* transitions_out, double* seconds) {
+    return compile_many((MispHandle*)hp, threads, n_roots, root_states, root_values, root_depths, widths, best_lb, cutset_type, 0.0, restricted_best, relaxed_best,
+                        cutset_sizes, transitions_out, seconds);
+}
+uint64_t oracle_m2s_compile_many(void* hp, int32_t threads, int32_t n_roots, const uint64_t* root_states, const int64_t* root_values,
+                                 const int32_t* root_depths, const uint64_t* widths, int64_t best_lb, int32_t cutset_type, double time_budget_s,
+                                 int64_t* restricted_best, int64_t* relaxed_best, int32_t* cutset_sizes, uint64_t* transitions_out, double* seconds) {
+    return compile_many((M2Handle*)hp, threads, n_roots, root_states, root_values, root_depths, widths, best_lb, cutset_type, time_budget_s, restricted_best,
+                        relaxed_best, cutset_sizes, transitions_out, seconds);
 }
 
 // stepwise wave solver (CPU stand-in for the device solver in the gloo tests of the fringe-sharded driver)

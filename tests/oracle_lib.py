@@ -91,6 +91,9 @@ def lib():
         _lib.oracle_m2s_dd_solution.argtypes = _lib.oracle_misp_dd_solution.argtypes
         _lib.oracle_m2s_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64,
                                           C.POINTER(SolveResult), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        _lib.oracle_m2s_compile_many.restype = C.c_uint64
+        _lib.oracle_m2s_compile_many.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib.oracle_m2s_stepper_new.restype = C.c_void_p
         _lib.oracle_m2s_stepper_new.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
         _lib.oracle_m2s_stepper_free.argtypes = [C.c_void_p]
@@ -255,6 +258,26 @@ class OracleM2s(_OracleModel):
         out["solution"] = list(zip(sv[: sl.value].tolist(), sx[: sl.value].tolist()))
         out["trace"] = trace[: tl.value].copy()
         return out
+
+
+def _m2s_compile_many(self, roots_states, roots_values, roots_depths, widths, best_lb, threads, cutset_type=LEL, time_budget_s=0.0):
+    """`threads` workers compile restricted + relaxed DDs of independent roots (parallel.rs:391-437 without the fringe), optionally time-boxed."""
+    n = len(roots_values)
+    rs = np.ascontiguousarray(roots_states, dtype=np.uint64)
+    rv = np.ascontiguousarray(roots_values, dtype=np.int64)
+    rd = np.ascontiguousarray(roots_depths, dtype=np.int32)
+    w = np.ascontiguousarray(widths, dtype=np.uint64)
+    rb = np.zeros(n, dtype=np.int64)
+    xb = np.zeros(n, dtype=np.int64)
+    cs = np.zeros(n, dtype=np.int32)
+    tr = C.c_uint64(0)
+    sec = C.c_double(0)
+    exp = lib().oracle_m2s_compile_many(self.h, threads, n, _p(rs), _p(rv), _p(rd), _p(w), best_lb, cutset_type, time_budget_s, _p(rb), _p(xb), _p(cs),
+                                        C.byref(tr), C.byref(sec))
+    return {"expanded": int(exp), "transitions": int(tr.value), "seconds": float(sec.value), "restricted_best": rb, "relaxed_best": xb, "cutset_sizes": cs}
+
+
+OracleM2s.compile_many = _m2s_compile_many
 
 
 class OracleStepper:
