@@ -86,7 +86,9 @@ def lib():
     if _lib is None:
         if not LIB_PATH.exists():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
-        _lib = C.CDLL(str(LIB_PATH))
+        import os
+        path = os.environ.get("DDO_B200_LIB", str(LIB_PATH))  # development: an alternative build of the same library (kernel tuning A/B runs)
+        _lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(_lib, name)
             fn.restype = res

@@ -113,18 +113,24 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* scratch) 
 }
 
 // 32x32 bit-matrix transpose across the lanes of a warp: afterwards bit r of lane b == bit b of (former) lane r.
+// Five butterfly steps of shuffle + rotate + one LOP3: a lane whose index has bit j clear keeps its fields with (index & j) == 0 and takes
+// the partner's same fields into the others, a lane with bit j set does the opposite (the bits a rotate wraps around are masked away).
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
     const unsigned lane = threadIdx.x & 31;
-    uint32_t m = 0x0000FFFFu;
 #pragma unroll
     for (int j = 16; j > 0; j >>= 1) {
-        uint32_t p = __shfl_xor_sync(FULL_MASK, x, j);
-        if (!(lane & j)) { uint32_t t = ((x >> j) ^ p) & m; x ^= (t << j); }
-        else             { uint32_t t = ((p >> j) ^ x) & m; x ^= t; }
-        m ^= (m << (j >> 1));
+        const uint32_t m = j == 16 ? 0x0000FFFFu : (j == 8 ? 0x00FF00FFu : (j == 4 ? 0x0F0F0F0Fu : (j == 2 ? 0x33333333u : 0x55555555u)));
+        const bool hi = (lane & j) != 0;
+        const uint32_t p = __shfl_xor_sync(FULL_MASK, x, j);
+        const uint32_t q = __funnelshift_l(p, p, hi ? 32 - j : j);
+        const uint32_t mm = hi ? ~m : m;
+        x = (x & mm) | (q & ~mm);
     }
     return x;
 }
+
+// state hash of the dedup table: multilinear over the 64-bit words, h = mix64(sum_j word_j * hash_mul(j)) (mod 2^64, odd multipliers)
+__device__ __forceinline__ uint64_t hash_mul(int j) { return mix64(0x9E3779B97F4A7C15ULL * (uint64_t)(j + 1)) | 1ull; }
 
 // =================================================================================================================
 // k_init: root of every DD becomes the single "candidate" of layer 0 (clean.rs:383-405)
@@ -177,26 +183,32 @@ __device__ __forceinline__ int plan_find(const int* off, int count, int tile) {
     return lo;
 }
 
+#ifndef DDO_EXPAND_MINB
+#define DDO_EXPAND_MINB 8
+#endif
 template <int S>
-__global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
+__global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, int count) {
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
-    constexpr int W32 = 2 * S;        // 32-bit words per state
-    __shared__ unsigned int s_exp, s_tr, s_any, s_claims;
-    __shared__ uint4 s_claim[2 * NPB * G];     // states claimed by this tile (zero rows for everything else): 2 candidates per node
+    constexpr int RP = G >= 8 ? 1 : 8 / G;  // claimed rows per 128 bytes of the staging buffer (bank swizzle below)
+    __shared__ unsigned int s_exp, s_tr, s_rows, s_claims;
+    __shared__ uint4 s_claim[2 * NPB * G];     // distinct states claimed by this tile (zero rows elsewhere): row r, chunk q at [r*G + (q ^ ((r / RP) & (G-1)))]
     __shared__ unsigned int s_hist[64 * S];    // per-vertex occurrence counts of the claimed states, flushed per DD
-    const int total = ev.tile_off_e[count];
+    const int* off = ev.tile_off_e;  // (L1-resident; staging the plan in shared memory measured slower)
+    const int total = off[count];
     const int sub = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t hc0 = hash_mul(2 * sub), hc1 = hash_mul(2 * sub + 1);
     // contiguous tile range per block, so that the histogram of consecutive tiles of one DD is flushed once
     const int tpb = (total + gridDim.x - 1) / gridDim.x;
     const int tile_lo = min((int)blockIdx.x * tpb, total), tile_hi = min(tile_lo + tpb, total);
     for (int i = threadIdx.x; i < 64 * S; i += 256) s_hist[i] = 0;
     if (threadIdx.x == 0) s_claims = 0;
     int hist_k = -1;
+    int k = tile_lo < tile_hi ? plan_find(off, count, tile_lo) : 0;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
-    const int k = plan_find(ev.tile_off_e, count, tile);
+    while (off[k + 1] <= tile) ++k;  // tiles of a block are consecutive: the DD index only moves forward
     if (k != hist_k) {
         __syncthreads();
         if (hist_k >= 0) {
@@ -207,9 +219,9 @@ __global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
     }
     DDCtl* ctl = ev.ctl + k;
     const int n_cur = ctl->n_cur;
-    const int node = (tile - ev.tile_off_e[k]) * NPB + threadIdx.x / G;
+    const int node = (tile - off[k]) * NPB + threadIdx.x / G;
     __syncthreads();
-    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; s_any = 0; }
+    if (threadIdx.x == 0) { s_exp = 0; s_tr = 0; s_rows = 0; }
     s_claim[threadIdx.x] = make_uint4(0, 0, 0, 0); s_claim[256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (node < n_cur) {
@@ -260,7 +272,10 @@ __global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
                 const uint32_t c = d == 0 ? c_yes : c_no;
                 uint4* dst = reinterpret_cast<uint4*>(ev.cand_state + (cb + c) * S) + sub;
                 st_stream_u4(dst, mk_u4(a0, a1));
-                const uint64_t h = mix64(group_xor64<G>(word_hash(a0, 2 * sub) ^ word_hash(a1, 2 * sub + 1), gm));
+                uint64_t hs = a0 * hc0 + a1 * hc1;
+#pragma unroll
+                for (int dd = G / 2; dd > 0; dd >>= 1) hs += __shfl_xor_sync(gm, hs, dd);
+                const uint64_t h = mix64(hs);
                 const int pc = group_sum<G>(__popcll(a0) + __popcll(a1), gm);
                 if (sub == 0) {
                     ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(a0) >> 44);
@@ -280,8 +295,9 @@ __global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
                     if (sub == 0) old = atomicCAS(tab + slot, EMPTY64, entry);
                     old = __shfl_sync(gm, old, (threadIdx.x & 31) & ~(G - 1));
                     if (old == EMPTY64) {  // Entry::Vacant, clean.rs:739-765: a new distinct state of the next layer
-                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; s_any = 1; atomicAdd(&s_claims, 1u); }
-                        s_claim[(d * NPB + threadIdx.x / G) * G + sub] = mk_u4(a0, a1);
+                        const unsigned row = d * NPB + threadIdx.x / G;
+                        if (sub == 0) { ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot; atomicAdd(&s_rows, 1u); }
+                        s_claim[row * G + (sub ^ ((row / RP) & (G - 1)))] = mk_u4(a0, a1);
                         break;
                     }
                     if ((uint32_t)(old >> 32) == tag) {
@@ -305,16 +321,22 @@ __global__ void __launch_bounds__(256, 8) k_expand(EV ev, int t, int count) {
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_exp) { atomicAdd(&ctl->expanded, (unsigned long long)s_exp); atomicAdd(&ctl->transitions, (unsigned long long)s_tr); }
-    // next_variable's histogram (misp/main.rs:131-135), fused: every claimed row is a distinct state of the next layer.
-    // 2*NPB rows of W32 words; warp w transposes 32 rows x 32-bit columns at a time.
-    if (s_any) {
-        constexpr int ROWS = 2 * NPB;
-        const uint32_t* rows = reinterpret_cast<const uint32_t*>(s_claim);
-        for (int job = warp; job < (ROWS / 32) * W32; job += 8) {
-            const int rblk = job / W32, col = job % W32;
-            const uint32_t x = rows[(rblk * 32 + lane) * W32 + col];
-            const unsigned cnt = __popc(warp_transpose32(x));  // lane b: #rows holding vertex 32*col + b
-            if (cnt) atomicAdd(&s_hist[32 * col + lane], cnt);
+    // next_variable's histogram (misp/main.rs:131-135), fused: every claimed row is a distinct state of the next layer.  Warp w transposes
+    // 32 rows x 32-bit columns at a time (one 128-bit chunk = four column blocks per conflict-free shared-memory load).
+    const int nrows = (int)s_rows;
+    if (nrows > 0) {
+        const int nblk = (2 * NPB) >> 5;
+        if (threadIdx.x == 0) s_claims += (unsigned)nrows;
+        for (int job = warp; job < nblk * G; job += 8) {
+            const int rblk = job / G, q = job % G;
+            const int row = rblk * 32 + lane;
+            const uint4 x4 = s_claim[row * G + (q ^ ((row / RP) & (G - 1)))];
+            const uint32_t xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned cnt = __popc(warp_transpose32(xs[e]));  // lane b: #rows holding vertex 32*(4q+e) + b
+                if (cnt) atomicAdd(&s_hist[32 * (4 * q + e) + lane], cnt);
+            }
         }
     }
     }  // tile loop
@@ -603,7 +625,7 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
         // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state
         if (tid == 0) {
             uint64_t h = 0;
-            for (int j = 0; j < S; ++j) h ^= word_hash(sm.merged[j], j);
+            for (int j = 0; j < S; ++j) h += sm.merged[j] * hash_mul(j);
             h = mix64(h);
             const uint32_t tag = (uint32_t)(h >> 32);
             uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
@@ -746,16 +768,17 @@ template <int S>
 __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
     constexpr int G = S / 2;
     constexpr int CPB = 256 / G;
-    const int total = ev.tile_off_c[count];
+    const int* off = ev.tile_off_c;  // (L1-resident after the first lookups; staging it in shared memory measured slower)
+    const int total = off[count];
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int k = plan_find(ev.tile_off_c, count, tile);
+    const int k = plan_find(off, count, tile);
     const DDCtl* ctl = ev.ctl + k;
     const int ncand = ctl->ncand;
-    if (tile == ev.tile_off_c[k]) {  // first tile of this DD: reset the per-layer accumulators that k_expand fills next
+    if (tile == off[k]) {  // first tile of this DD: reset the per-layer accumulators that k_expand fills next
         for (int i = threadIdx.x; i < ev.HN; i += 256) ev.vhist[(size_t)k * ev.HN + i] = 0;
         if (threadIdx.x == 0) ev.ucount[k] = 0;
     }
-    const int c = (tile - ev.tile_off_c[k]) * CPB + threadIdx.x / G;
+    const int c = (tile - off[k]) * CPB + threadIdx.x / G;
     if (c >= ncand) continue;
     const int sub = threadIdx.x % G;
     const size_t cb = (size_t)k * ev.C;

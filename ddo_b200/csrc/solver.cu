@@ -267,6 +267,31 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         return DDO_OK;
     };
 
+    // A general-engine DD that improves on everything seen so far in the wave has its best exact path read while its batch is still
+    // resident on the device; only an improver of the fast path (which keeps no paths) has to be recompiled by take_solution.
+    std::vector<std::pair<int, std::vector<ddo_decision>>> captured;  // (wave index, decisions from that DD's root), restricted / relaxed
+    int32_t run_best_restricted = INT32_MIN, run_best_relaxed = INT32_MIN;
+    auto capture = [&](int slot, int wave_index) -> int {
+        std::vector<ddo_decision> dd(n_vars + 1);
+        int32_t len = (int32_t)dd.size();
+        const int r2 = eng->best_solution(slot, 1, dd.data(), &len);
+        if (r2 != DDO_OK) return r2;
+        dd.resize(len);
+        captured.emplace_back(wave_index, std::move(dd));
+        return DDO_OK;
+    };
+    auto use_captured = [&](int wave_index) -> bool {
+        for (auto it = captured.rbegin(); it != captured.rend(); ++it)
+            if (it->first == wave_index) {
+                best_sol.clear();
+                full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], best_sol);
+                best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
+                has_sol = true;
+                return true;
+            }
+        return false;
+    };
+
     // ---- 1a. shared-memory fast path: one CTA per sub-problem; DDs that never need a cut are exact and finish here ----------------
     std::vector<int> ov;  // sub-problems that need the general engine (a layer outgrew the fast path)
     if (eng->small_ws > 0) {
@@ -336,6 +361,11 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             Res& r = res[ov[s0 + j]];
             r.exact = c.lel < 0; r.has = c.has_best_exact != 0; r.best = c.best_exact_value;
             expanded += c.expanded; transitions += c.transitions; ++compilations;
+            if (r.has && (int64_t)r.best > lb0 && r.best > run_best_restricted) {
+                run_best_restricted = r.best;
+                rc = capture(j, ov[s0 + j]);
+                if (rc != DDO_OK) return rc;
+            }
         }
         if (dual) {
             caps.assign(2 * oc, 0); lbs.assign(2 * oc, INT64_MAX);
@@ -346,6 +376,11 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 if (c.status == ST_WAITING) continue;  // the restricted DD never needed a cut: exact, no relaxation (parallel.rs:421-423)
                 const int wi = ov[s0 + j];
                 twins.push_back(TwinRes{wi, c.expanded, c.transitions, c.has_best_exact != 0, c.best_exact_value});
+                if (c.has_best_exact && (int64_t)c.best_exact_value > lb0 && c.best_exact_value > run_best_relaxed) {
+                    run_best_relaxed = c.best_exact_value;
+                    rc = capture(oc + j, -1 - wi);  // relaxed twins are filed under -1 - wave index
+                    if (rc != DDO_OK) return rc;
+                }
                 const bool exact = (c.lel < 0) || c.ebpo;
                 const int32_t rub = w_items[wi].ub;
                 caps[oc + j] = rub == INT32_MAX ? INT64_MAX : rub;
@@ -359,7 +394,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     {   // maybe_update_best in wave order (parallel.rs:446-453): the first DD reaching the new maximum keeps its solution
         int last = -1;
         for (int i = 0; i < cnt; ++i) if (res[i].has && (int64_t)res[i].best > best_lb) { best_lb = res[i].best; last = i; }
-        if (last >= 0) { rc = take_solution(last, DDO_RESTRICTED, lb0); if (rc != DDO_OK) return rc; }
+        if (last >= 0 && !use_captured(last)) { rc = take_solution(last, DDO_RESTRICTED, lb0); if (rc != DDO_OK) return rc; }
     }
     std::vector<int> open;  // sub-problems whose restricted DD is not exact
     for (int i : ov) if (!res[i].exact) open.push_back(i);
@@ -389,7 +424,11 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 for (int j = 0; j < oc; ++j) {
                     const DDCtl& c = eng->h_ctl[j];
                     expanded += c.expanded; transitions += c.transitions; ++compilations;
-                    if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) { best_lb = c.best_exact_value; improver = open[s0 + j]; }
+                    if (c.has_best_exact && (int64_t)c.best_exact_value > best_lb) {
+                        best_lb = c.best_exact_value; improver = open[s0 + j];
+                        rc = capture(j, -1 - improver);
+                        if (rc != DDO_OK) return rc;
+                    }
                     const bool exact = (c.lel < 0) || c.ebpo;
                     const int32_t rub = w_items[open[s0 + j]].ub;
                     caps[j] = rub == INT32_MAX ? INT64_MAX : rub;
@@ -400,7 +439,18 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 if (rc != DDO_OK) return rc;
             }
         }
-        if (improver >= 0) { rc = take_solution(improver, DDO_RELAXED, lb1); if (rc != DDO_OK) return rc; }
+        if (improver >= 0) {
+            const int wi = improver;
+            bool got = false;
+            for (auto it = captured.rbegin(); it != captured.rend() && !got; ++it)
+                if (it->first == -1 - wi) {
+                    best_sol.clear();
+                    full_path(w_items[wi].rec, &w_bits[(size_t)wi * PWN], best_sol);
+                    best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
+                    has_sol = true; got = true;
+                }
+            if (!got) { rc = take_solution(improver, DDO_RELAXED, lb1); if (rc != DDO_OK) return rc; }
+        }
         t0 = now_ms();
         size_t var_off = 0;
         for (const Pending& pd : pend) {
