@@ -110,8 +110,8 @@ int model_create_max2sat(int32_t n, int64_t m, const int64_t* clauses, int devic
         }
         AT[k] = (int32_t)at; AF[k] = (int32_t)af;
     }
-    std::vector<unsigned long long> hmul(NW);
-    for (size_t i = 0; i < NW; ++i) hmul[i] = host_mix64(0x9E3779B97F4A7C15ULL * (i + 1)) | 1ull;
+    std::vector<uint32_t> hmul(NW);
+    for (size_t i = 0; i < NW; ++i) hmul[i] = (uint32_t)(host_mix64(0x9E3779B97F4A7C15ULL * (i + 1)) >> 32) | 1u;
     bool ok = cudaSetDevice(device) == cudaSuccess && upload(&M->d_ord, M->h_ord) == cudaSuccess && upload(&M->d_PT, PT) == cudaSuccess &&
               upload(&M->d_QT, QT) == cudaSuccess && upload(&M->d_PF, PF) == cudaSuccess && upload(&M->d_QF, QF) == cudaSuccess &&
               upload(&M->d_AT, AT) == cudaSuccess && upload(&M->d_AF, AF) == cudaSuccess && upload(&M->d_est, est) == cudaSuccess &&
@@ -168,10 +168,10 @@ int M2Engine::create_m2s(const M2Model* m, int dev, uint64_t max_width_cap, int 
     v.K = K; v.Wcap = Wcap; v.C = C; v.T = T; v.Lmax = Lmax; v.n = m->n; v.NW = NW; v.NW4 = NW / 4; v.PW = PW;
     v.ord = m->d_ord; v.PT = m->d_PT; v.QT = m->d_QT; v.PF = m->d_PF; v.QF = m->d_QF; v.AT = m->d_AT; v.AF = m->d_AF;
     v.est = m->d_est; v.nk = m->d_nk; v.initial = m->initial; v.hmul = m->d_hmul;
-    ALLOC(v.ctl, K); ALLOC(v.aux, K); ALLOC(v.active, 4); ALLOC(v.tile_off_e, K + 1); ALLOC(v.tile_off_c, K + 1); ALLOC(v.finish_counter, 4);
-    for (int b = 0; b < 2; ++b) { ALLOC(v.cur_state[b], KW * NW); ALLOC(v.cur_val[b], KW); ALLOC(v.cur_flag[b], KW); ALLOC(v.cur_rank[b], KW); ALLOC(v.vb[b], KW); }
+    ALLOC(v.ctl, K); ALLOC(v.aux, K); ALLOC(v.active, 4); ALLOC(v.lel_any, 4); ALLOC(v.tile_off_e, K + 1); ALLOC(v.tile_off_c, K + 1); ALLOC(v.finish_counter, 4);
+    for (int b = 0; b < 2; ++b) { ALLOC(v.cur_src[b], KW); ALLOC(v.cand_state[b], (size_t)K * (C + 1) * NW); ALLOC(v.cur_val[b], KW); ALLOC(v.cur_flag[b], KW); ALLOC(v.cur_rank[b], KW); ALLOC(v.vb[b], KW); }
     ALLOC(v.cur_rub, KW);
-    ALLOC(v.cand_state, KC * NW); ALLOC(v.cand_rep, KC); ALLOC(v.cand_first, KC); ALLOC(v.cand_agg, KC); ALLOC(v.cand_inex, KC);
+    ALLOC(v.cand_rep, KC); ALLOC(v.cand_first, KC); ALLOC(v.cand_agg, KC); ALLOC(v.cand_inex, KC);
     ALLOC(v.cand_rank, KC); ALLOC(v.cand_slot, KC); ALLOC(v.cand_cost, KC);
     ALLOC(v.uflag, KC); ALLOC(v.ulist, KC); ALLOC(v.ustat, KC); ALLOC(v.pos_of, KC); ALLOC(v.gkeys, KC);
     finish_smem = (size_t)C * 9 + 16;  // keys (8 B) + status (1 B) of up to C distinct candidates next to ~9 KB of static shared memory
@@ -229,6 +229,7 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
     prof_mark(-1);
     const long long max_tiles = (long long)count * ((C + 7) / 8);
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)num_sms * 8);
+    const int compact_grid = (int)std::min<long long>((max_tiles + 31) / 32, (long long)num_sms * 8);
     const int ch = (v.NW4 + 31) / 32;
     const bool relaxed = comp_type == DDO_RELAXED;
     const dim3 merge_grid((C + 63) / 64, count);
@@ -239,12 +240,12 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
         ++g_kernel_launches;
         prof_mark(1);
         if (relaxed && t >= 2) {
-            m2_merge<<<merge_grid, 256, 0, st>>>(v);
+            m2_merge<<<merge_grid, 256, 0, st>>>(v, t);
             m2_merge_fin<<<count, 256, 0, st>>>(v, t);
             g_kernel_launches += 2;
             prof_mark(5);
         }
-        m2_compact<<<flat_grid, 256, 0, st>>>(v, t, count);
+        m2_compact<<<compact_grid, 256, 0, st>>>(v, t, count);
         prof_mark(2);
         switch (ch) {
             case 1: launch_expand<1>(this, flat_grid, t, count); break;

@@ -14,7 +14,7 @@ struct M2Model {
     std::vector<int32_t> h_ord;
     int32_t* d_ord = nullptr; int32_t *d_PT = nullptr, *d_QT = nullptr, *d_PF = nullptr, *d_QF = nullptr, *d_AT = nullptr, *d_AF = nullptr;
     long long *d_est = nullptr, *d_nk = nullptr;
-    unsigned long long* d_hmul = nullptr;
+    uint32_t* d_hmul = nullptr;
 };
 
 // ---- kernel argument blocks (passed by value) ---------------------------------------------------------------------------------
@@ -30,11 +30,12 @@ struct M2EV {
     const int32_t *PT, *QT, *PF, *QF;                     // [n][NW] clause-weight rows of the branching variable (see m2s_engine.cu)
     const int32_t *AT, *AF;                               // [n] state-independent part of the transition cost
     const long long *est, *nk; long long initial;         // fast_upper_bound tables, model.rs:183-249
-    const unsigned long long* hmul;                       // [NW] odd multipliers of the multilinear state hash
-    DDCtl* ctl; M2Aux* aux; int* active; int* tile_off_e; int* tile_off_c; unsigned int* finish_counter;
+    const uint32_t* hmul;                                 // [NW] odd 32-bit multipliers of the multilinear state hash (64-bit accumulator)
+    DDCtl* ctl; M2Aux* aux; int* active; int* lel_any; int* tile_off_e; int* tile_off_c; unsigned int* finish_counter;
     int32_t* root_state; int32_t* root_val; int32_t* root_depth; int32_t* root_width;
-    int32_t* cur_state[2]; int32_t* cur_val[2]; uint8_t* cur_flag[2]; int32_t* cur_rank[2]; int32_t* cur_rub;
-    int32_t* cand_state; uint32_t* cand_rep; uint32_t* cand_first; unsigned long long* cand_agg; uint8_t* cand_inex; uint32_t* cand_rank;
+    uint32_t* cur_src[2]; int32_t* cur_val[2]; uint8_t* cur_flag[2]; int32_t* cur_rank[2]; int32_t* cur_rub;  // cur_src: candidate row holding the node's state
+    // cand_state[b]: [K][C + 1][NW] state rows of the candidates of the layers with parity b (+ the merged node in row C)
+    int32_t* cand_state[2]; uint32_t* cand_rep; uint32_t* cand_first; unsigned long long* cand_agg; uint8_t* cand_inex; uint32_t* cand_rank;
     uint32_t* cand_slot; int32_t* cand_cost;
     uint8_t* uflag; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of; unsigned long long* gkeys;
     unsigned long long* table;

@@ -32,6 +32,10 @@ __device__ __forceinline__ int warp_sum32(int v) {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
     return v;
 }
+// State rows live only in the candidate buffers: the candidates of layer t (and its merged node, row C) in buffer t & 1.  A node of the
+// current layer is a reference (cur_src) to the candidate row it came from, so a layer step moves every row exactly once (parent read,
+// child write) -- there is no separate copy of the current layer.
+__device__ __forceinline__ int32_t* m2_row(const M2EV& ev, int b, int k, uint32_t c) { return ev.cand_state[b] + ((size_t)k * (ev.C + 1) + c) * ev.NW; }
 __device__ __forceinline__ int iabs(int x) { return x < 0 ? -x : x; }
 __device__ __forceinline__ int ipos(int x) { return x > 0 ? x : 0; }
 
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(256) m2_init(M2EV ev, int count, int comp_type
     int rank = 0;
     for (int i = threadIdx.x; i < ev.NW; i += 256) {
         const int v = ev.root_state[(size_t)k * ev.NW + i];
-        ev.cand_state[cb * ev.NW + i] = v;
+        m2_row(ev, 0, k, 0)[i] = v;
         rank += iabs(v);
         ev.mrg_min[(size_t)k * ev.NW + i] = INT32_MAX; ev.mrg_max[(size_t)k * ev.NW + i] = INT32_MIN;
     }
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(256) m2_init(M2EV ev, int count, int comp_type
         ev.cand_rep[cb] = 0; ev.cand_first[cb] = 0; ev.cand_agg[cb] = pack_key(ev.root_val[k], PLOG_CAND_MASK); ev.cand_inex[cb] = 0;
         ev.cand_rank[cb] = (uint32_t)rank; ev.cand_slot[cb] = NONE32; ev.cand_cost[cb] = 0; ev.uflag[cb] = 0;
         M2Aux a{}; ev.aux[k] = a;
-        if (k == 0) *ev.active = count;
+        if (k == 0) { *ev.active = count; *ev.lel_any = -1; }
     }
 }
 
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(256) m2_init(M2EV ev, int count, int comp_type
 // m2_expand: layer t -> candidates of layer t+1.  One warp per node; CH = 128-bit chunks of a row per lane.
 // =================================================================================================================
 template <int CH>
-__global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
+__global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t, int count) {
     const int total = ev.tile_off_e[count];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW4 = ev.NW4;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
             const size_t cb = (size_t)k * ev.C;
             const int depth = ctl->root_depth + t;
             const int var = ev.ord[ev.n - depth - 1];  // model.rs:330-348
-            const int4* row = reinterpret_cast<const int4*>(ev.cur_state[buf] + nb * ev.NW);
+            const int4* row = reinterpret_cast<const int4*>(m2_row(ev, buf, k, ev.cur_src[buf][nb]));
             int4 s[CH];
 #pragma unroll
             for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; s[q] = i < NW4 ? ld_stream_i4(row + i) : make_int4(0, 0, 0, 0); }
@@ -116,12 +120,14 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
                     for (int q = 0; q < CH; ++q) if (lane + 32 * q == owner_chunk) { const int e = var & 3; sv = e == 0 ? s[q].x : (e == 1 ? s[q].y : (e == 2 ? s[q].z : s[q].w)); }
                     sv = __shfl_sync(FULL_MASK, sv, owner_chunk & 31);
                 }
+                // both children are computed and streamed out first, ONE fence makes their rows visible, then both are inserted
+                int values[2]; unsigned long long hashes[2];
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
                     const int32_t* Pd = (d == 0 ? ev.PT : ev.PF) + (size_t)var * ev.NW;
                     const int32_t* Qd = (d == 0 ? ev.QT : ev.QF) + (size_t)var * ev.NW;
                     const uint32_t c = d == 0 ? c_t : c_f;
-                    int4* dst = reinterpret_cast<int4*>(ev.cand_state + (cb + c) * ev.NW);
+                    int4* dst = reinterpret_cast<int4*>(m2_row(ev, buf ^ 1, k, c));
                     int cost = 0, crank = 0;
                     unsigned long long h = 0;
 #pragma unroll
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
                         const int i = lane + 32 * q;
                         if (i < NW4) {
                             const int4 P = __ldg(reinterpret_cast<const int4*>(Pd) + i), Q = __ldg(reinterpret_cast<const int4*>(Qd) + i);
-                            const ulonglong2 m01 = __ldg(reinterpret_cast<const ulonglong2*>(ev.hmul) + 2 * i), m23 = __ldg(reinterpret_cast<const ulonglong2*>(ev.hmul) + 2 * i + 1);
+                            const uint4 m = __ldg(reinterpret_cast<const uint4*>(ev.hmul) + i);
                             int4 x = s[q], r;
                             // transition (model.rs:275-292) and the state-dependent part of transition_cost (model.rs:294-328)
                             r.x = x.x + P.x - Q.x; r.y = x.y + P.y - Q.y; r.z = x.z + P.z - Q.z; r.w = x.w + P.w - Q.w;
@@ -137,14 +143,15 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
                                     min(ipos(x.w) + P.w, ipos(-x.w) + Q.w);
                             if (i == (var >> 2)) { const int e = var & 3; if (e == 0) r.x = 0; else if (e == 1) r.y = 0; else if (e == 2) r.z = 0; else r.w = 0; }  // ret[k] = 0
                             crank += iabs(r.x) + iabs(r.y) + iabs(r.z) + iabs(r.w);
-                            h += (unsigned long long)(uint32_t)r.x * m01.x + (unsigned long long)(uint32_t)r.y * m01.y + (unsigned long long)(uint32_t)r.z * m23.x +
-                                 (unsigned long long)(uint32_t)r.w * m23.y;
+                            h += (unsigned long long)(uint32_t)r.x * m.x + (unsigned long long)(uint32_t)r.y * m.y + (unsigned long long)(uint32_t)r.z * m.z +
+                                 (unsigned long long)(uint32_t)r.w * m.w;
                             st_stream_i4(dst + i, r);
                         }
                     }
                     cost = warp_sum32(cost); crank = warp_sum32(crank); h = mix64(warp_sum64(h));
                     cost += (d == 0 ? ev.AT[var] + ipos(sv) : ev.AF[var] + ipos(-sv));
                     const int value = val + cost;
+                    values[d] = value; hashes[d] = h;
                     if (lane == 0) {
                         ev.cand_rank[cb + c] = (uint32_t)crank;
                         ev.cand_agg[cb + c] = pack_key(value, c);
@@ -152,8 +159,14 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
                         ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
                         ev.cand_cost[cb + c] = cost;
                     }
-                    __threadfence();
-                    __syncwarp();
+                }
+                __threadfence();
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    const uint32_t c = d == 0 ? c_t : c_f;
+                    const int value = values[d];
+                    const unsigned long long h = hashes[d];
                     // open-addressing insert (next_l.entry(), clean.rs:738)
                     const uint32_t tag = (uint32_t)(h >> 32);
                     const unsigned long long entry = ((unsigned long long)tag << 32) | c;
@@ -169,8 +182,8 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
                         }
                         if ((uint32_t)(old >> 32) == tag) {
                             const uint32_t oc = (uint32_t)old;
-                            const int4* orow = reinterpret_cast<const int4*>(ev.cand_state + (cb + oc) * ev.NW);
-                            const int4* mrow = reinterpret_cast<const int4*>(ev.cand_state + (cb + c) * ev.NW);
+                            const int4* orow = reinterpret_cast<const int4*>(m2_row(ev, buf ^ 1, k, oc));
+                            const int4* mrow = reinterpret_cast<const int4*>(m2_row(ev, buf ^ 1, k, c));
                             bool eq = true;
                             for (int i = lane; i < NW4; i += 32) { const int4 a = ld_cg_i4(orow + i), b = ld_cg_i4(mrow + i); eq = eq && a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
                             eq = __all_sync(FULL_MASK, eq);
@@ -201,11 +214,11 @@ __global__ void __launch_bounds__(256) m2_expand(M2EV ev, int t, int count) {
 }
 
 // cut order between two distinct candidates (clean.rs:803-808 + heuristics.rs:33-37 + canonical tie-break): true if a is BETTER than b
-__device__ inline bool m2_cand_better(const M2EV& ev, size_t cb, uint32_t a, uint32_t b) {
+__device__ inline bool m2_cand_better(const M2EV& ev, int buf, int k, size_t cb, uint32_t a, uint32_t b) {
     const unsigned long long ka = (ev.cand_agg[cb + a] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + a];
     const unsigned long long kb = (ev.cand_agg[cb + b] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + b];
     if (ka != kb) return ka > kb;
-    const int32_t* ra = ev.cand_state + (cb + a) * ev.NW; const int32_t* rb = ev.cand_state + (cb + b) * ev.NW;
+    const int32_t* ra = m2_row(ev, buf, k, a); const int32_t* rb = m2_row(ev, buf, k, b);
     for (int j = 0; j < ev.n; ++j) if (ra[j] != rb[j]) return ra[j] > rb[j];
     return false;
 }
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(1024, 1) m2_finish(M2EV ev, int t) {
                 // key chunk 0: (value_top, rank); chunk j: benefits 2j-2, 2j-1 as order-preserving unsigned words (canonical tie-break)
                 auto key_of = [&](int ui) -> unsigned long long {
                     if (chunk == 0) return keys[ui];
-                    const int32_t* r = ev.cand_state + (cb + ev.ulist[cb + ui]) * ev.NW + 2 * (chunk - 1);
+                    const int32_t* r = m2_row(ev, t & 1, k, ev.ulist[cb + ui]) + 2 * (chunk - 1);
                     return ((unsigned long long)((uint32_t)r[0] ^ 0x80000000u) << 32) | ((uint32_t)r[1] ^ 0x80000000u);
                 };
                 unsigned long long kor = 0, kand = ~0ull;
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(1024, 1) m2_finish(M2EV ev, int t) {
             ev.vlog[lb + t] = var;
             ev.rslog[(lb + t) * 3] = -1; ev.rslog[(lb + t) * 3 + 1] = -1; ev.rslog[(lb + t) * 3 + 2] = 0;
             ctl->n_cur = n_next; ctl->var = var;
-            if (cut && ctl->lel < 0) { ctl->lel = t - 1; ctl->lel_pending = 1; }  // _maybe_save_lel, clean.rs:796-800
+            if (cut && ctl->lel < 0) { ctl->lel = t - 1; ctl->lel_pending = 1; if (comp == DDO_RELAXED) *ev.lel_any = t; }  // _maybe_save_lel, clean.rs:796-800
             if (terminal) { ctl->status = ST_TERMINAL; ctl->t_term = t; atomicSub(ev.active, 1); }
         }
     } while (false);
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(1024, 1) m2_finish(M2EV ev, int t) {
 // merged[v] = min if min > 0 (all positive), max if max < 0 (all negative), else 0 (a zero, or both signs).
 // grid = (chunks of 64 distinct candidates, DDs); thread j owns the 128-bit column chunk j of every row of its chunk.
 // =================================================================================================================
-__global__ void __launch_bounds__(256) m2_merge(M2EV ev) {
+__global__ void __launch_bounds__(256) m2_merge(M2EV ev, int t) {
     const int k = blockIdx.y;
     const M2Aux* aux = ev.aux + k;
     if (!aux->cut_relaxed) return;
@@ -447,7 +460,7 @@ __global__ void __launch_bounds__(256) m2_merge(M2EV ev) {
     for (int ui = u0; ui < u1; ++ui) {
         if (ev.ustat[cb + ui] != 2) continue;
         const uint32_t c = ev.ulist[cb + ui];
-        const int4 v = ld_stream_i4(reinterpret_cast<const int4*>(ev.cand_state + (cb + c) * ev.NW) + j);
+        const int4 v = ld_stream_i4(reinterpret_cast<const int4*>(m2_row(ev, t & 1, k, c)) + j);
         mn.x = min(mn.x, v.x); mn.y = min(mn.y, v.y); mn.z = min(mn.z, v.z); mn.w = min(mn.w, v.w);
         mx.x = max(mx.x, v.x); mx.y = max(mx.y, v.y); mx.z = max(mx.z, v.z); mx.w = max(mx.w, v.w);
         any = true;
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(256) m2_merge_fin(M2EV ev, int t) {
         const int m = (i < ev.n) ? (mn > 0 ? mn : (mx < 0 ? mx : 0)) : 0;
         mrow[i] = m;
         rank += iabs(m);
-        h += (unsigned long long)(uint32_t)m * ev.hmul[i];
+        h += (unsigned long long)(uint32_t)m * ev.hmul[i];  // 32-bit odd multipliers, 64-bit accumulator
     }
     rank = warp_sum32(rank); h = warp_sum64(h);
     if (lane == 0) { s_red[warp] = rank; s_h[warp] = h; }
@@ -504,7 +517,7 @@ __global__ void __launch_bounds__(256) m2_merge_fin(M2EV ev, int t) {
             if (e == EMPTY64) break;
             if ((uint32_t)(e >> 32) == tag) {
                 const uint32_t oc = (uint32_t)e;
-                const int32_t* orow = ev.cand_state + (cb + oc) * ev.NW;
+                const int32_t* orow = m2_row(ev, t & 1, k, oc);
                 bool eq = true;
                 for (int i = lane; i < ev.NW; i += 32) eq = eq && orow[i] == mrow[i];
                 eq = __all_sync(FULL_MASK, eq);
@@ -521,14 +534,14 @@ __global__ void __launch_bounds__(256) m2_merge_fin(M2EV ev, int t) {
         uint32_t bestc = NONE32;
         for (int ui = tid; ui < U; ui += NT) if (ev.ustat[cb + ui] == 2) {
             const uint32_t c = ev.ulist[cb + ui];
-            if (bestc == NONE32 || m2_cand_better(ev, cb, c, bestc)) bestc = c;
+            if (bestc == NONE32 || m2_cand_better(ev, t & 1, k, cb, c, bestc)) bestc = c;
         }
         s_best[tid] = bestc;
         __syncthreads();
         for (int d = NT / 2; d > 0; d >>= 1) {
             if (tid < d) {
                 const uint32_t a = s_best[tid], b2 = s_best[tid + d];
-                if (a == NONE32 || (b2 != NONE32 && m2_cand_better(ev, cb, b2, a))) s_best[tid] = b2;
+                if (a == NONE32 || (b2 != NONE32 && m2_cand_better(ev, t & 1, k, cb, b2, a))) s_best[tid] = b2;
             }
             __syncthreads();
         }
@@ -547,8 +560,10 @@ __global__ void __launch_bounds__(256) m2_merge_fin(M2EV ev, int t) {
         // new merged node (clean.rs:832-849) written straight into the next layer
         const int nbuf = t & 1;
         const size_t nb = (size_t)k * ev.Wcap + nkeep;
-        for (int i = tid; i < ev.NW; i += NT) ev.cur_state[nbuf][nb * ev.NW + i] = mrow[i];
+        int32_t* drow = m2_row(ev, nbuf, k, (uint32_t)ev.C);  // the extra row of the layer's candidate buffer
+        for (int i = tid; i < ev.NW; i += NT) drow[i] = mrow[i];
         if (tid == 0) {
+            ev.cur_src[nbuf][nb] = (uint32_t)ev.C;
             ev.cur_val[nbuf][nb] = value_m;
             ev.cur_flag[nbuf][nb] = (uint8_t)(NF_INEXACT | NF_RELAXED);
             ev.cur_rank[nbuf][nb] = rank_m;
@@ -563,58 +578,68 @@ __global__ void __launch_bounds__(256) m2_merge_fin(M2EV ev, int t) {
 // m2_compact: scatter layer t into the ping-pong buffers, write logs, release hash slots, snapshot the LEL.  One warp per candidate.
 // =================================================================================================================
 __global__ void __launch_bounds__(256) m2_compact(M2EV ev, int t, int count) {
+    // tiles of 8 candidates (the work plan's granularity): 32 tiles = 256 candidates per CTA pass, one THREAD per candidate (rows are not
+    // moved any more); the last-exact-layer snapshot, taken once per relaxed DD, copies rows with one warp per row.
     const int total = ev.tile_off_c[count];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int k = plan_find(ev.tile_off_c, count, tile);
-        const DDCtl* ctl = ev.ctl + k;
-        const M2Aux* aux = ev.aux + k;
-        const int ncand = ctl->ncand;
-        const int c = (tile - ev.tile_off_c[k]) * 8 + warp;
-        if (c >= ncand) continue;
-        const size_t cb = (size_t)k * ev.C;
-        const size_t lb = (size_t)k * ev.Lmax;
-        const int nbuf = t & 1;
-        const bool relaxed = ctl->comp_type == DDO_RELAXED;
-        const uint32_t rep = ev.cand_rep[cb + c];
-        uint32_t child = NONE32;
-        int cost = 0;
-        if (rep != NONE32) {
-            const uint32_t f = ev.cand_first[cb + rep];
-            child = ev.pos_of[cb + f];
-            cost = ev.cand_cost[cb + c];
-            if (child == M2_DROPPED) {  // edge re-pointed to the merged node with its relaxed cost (clean.rs:851-866, relax.rs:78-84)
-                child = (uint32_t)aux->mpos;
-                cost += (int32_t)ev.cand_rank[cb + rep] - aux->rank_m;
-            }
-            if (lane == 0 && rep == (uint32_t)c) {  // release the hash slot this candidate claimed
-                const uint32_t slot = ev.cand_slot[cb + c];
-                if (slot != NONE32) ev.table[(size_t)k * ev.T + slot] = EMPTY64;
-            }
-            if (ev.uflag[cb + c] == 2) {  // surviving canonical representative: becomes node `pos` of layer t
-                const uint32_t pos = ev.pos_of[cb + c];
-                const size_t nb = (size_t)k * ev.Wcap + pos;
-                const int4* src = reinterpret_cast<const int4*>(ev.cand_state + (cb + c) * ev.NW);
-                int4* dst = reinterpret_cast<int4*>(ev.cur_state[nbuf] + nb * ev.NW);
-                for (int i = lane; i < ev.NW4; i += 32) st_stream_i4(dst + i, ld_stream_i4(src + i));
-                if (lane == 0) {
-                    const unsigned long long key = ev.cand_agg[cb + c];
-                    const uint32_t fl = ev.cand_inex[cb + c];
-                    ev.cur_val[nbuf][nb] = key_value(key);
-                    ev.cur_flag[nbuf][nb] = (uint8_t)fl;
-                    ev.cur_rank[nbuf][nb] = (int32_t)ev.cand_rank[cb + c];
-                    ev.plog[(lb + t) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
+    for (int tile0 = blockIdx.x * 32; tile0 < total; tile0 += gridDim.x * 32) {
+        {
+            const int tile = tile0 + (threadIdx.x >> 3);
+            if (tile < total) {
+                const int k = plan_find(ev.tile_off_c, count, tile);
+                const DDCtl* ctl = ev.ctl + k;
+                const M2Aux* aux = ev.aux + k;
+                const int c = (tile - ev.tile_off_c[k]) * 8 + (threadIdx.x & 7);
+                if (c < ctl->ncand) {
+                    const size_t cb = (size_t)k * ev.C;
+                    const size_t lb = (size_t)k * ev.Lmax;
+                    const int nbuf = t & 1;
+                    const bool relaxed = ctl->comp_type == DDO_RELAXED;
+                    const uint32_t rep = ev.cand_rep[cb + c];
+                    uint32_t child = NONE32;
+                    int cost = 0;
+                    if (rep != NONE32) {
+                        const uint32_t f = ev.cand_first[cb + rep];
+                        child = ev.pos_of[cb + f];
+                        cost = ev.cand_cost[cb + c];
+                        if (child == M2_DROPPED) {  // edge re-pointed to the merged node with its relaxed cost (clean.rs:851-866, relax.rs:78-84)
+                            child = (uint32_t)aux->mpos;
+                            cost += (int32_t)ev.cand_rank[cb + rep] - aux->rank_m;
+                        }
+                        if (rep == (uint32_t)c) {  // release the hash slot this candidate claimed
+                            const uint32_t slot = ev.cand_slot[cb + c];
+                            if (slot != NONE32) ev.table[(size_t)k * ev.T + slot] = EMPTY64;
+                        }
+                        if (ev.uflag[cb + c] == 2) {  // surviving canonical representative: becomes node `pos` of layer t
+                            const uint32_t pos = ev.pos_of[cb + c];
+                            const size_t nb = (size_t)k * ev.Wcap + pos;
+                            const unsigned long long key = ev.cand_agg[cb + c];
+                            const uint32_t fl = ev.cand_inex[cb + c];
+                            ev.cur_src[nbuf][nb] = (uint32_t)c;  // the row stays where m2_expand wrote it
+                            ev.cur_val[nbuf][nb] = key_value(key);
+                            ev.cur_flag[nbuf][nb] = (uint8_t)fl;
+                            ev.cur_rank[nbuf][nb] = (int32_t)ev.cand_rank[cb + c];
+                            ev.plog[(lb + t) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
+                        }
+                    }
+                    if (t > 0 && relaxed) { ev.clog[(lb + t - 1) * ev.C + c] = child; ev.colog[(lb + t - 1) * ev.C + c] = cost; }
                 }
             }
         }
-        if (t > 0) {
-            if (relaxed && lane == 0) { ev.clog[(lb + t - 1) * ev.C + c] = child; ev.colog[(lb + t - 1) * ev.C + c] = cost; }
-            if (ctl->lel_pending && relaxed && !(c & 1)) {  // layer t-1 is the last exact layer: keep its nodes for the cutset
+        if (t > 0 && *ev.lel_any == t) {  // layer t-1 is the last exact layer of some relaxed DD: keep its nodes (states, values, rough upper bounds) for the cutset
+            for (int q = warp; q < 32 * 4; q += 8) {  // 32 tiles x 4 even candidates
+                const int tile = tile0 + (q >> 2);
+                if (tile >= total) break;
+                const int k = plan_find(ev.tile_off_c, count, tile);
+                const DDCtl* ctl = ev.ctl + k;
+                if (!ctl->lel_pending || ctl->comp_type != DDO_RELAXED) continue;
+                const int c = (tile - ev.tile_off_c[k]) * 8 + 2 * (q & 3);
+                if (c >= ctl->ncand) continue;
                 const int i = c >> 1;
                 const size_t pb = (size_t)k * ev.Wcap + i;
-                const int4* src = reinterpret_cast<const int4*>(ev.cur_state[(t - 1) & 1] + pb * ev.NW);
+                const int4* src = reinterpret_cast<const int4*>(m2_row(ev, (t - 1) & 1, k, ev.cur_src[(t - 1) & 1][pb]));
                 int4* dst = reinterpret_cast<int4*>(ev.lel_state + pb * ev.NW);
-                for (int q = lane; q < ev.NW4; q += 32) st_stream_i4(dst + q, ld_stream_i4(src + q));
+                for (int j = lane; j < ev.NW4; j += 32) st_stream_i4(dst + j, ld_stream_i4(src + j));
                 if (lane == 0) { ev.lel_val[pb] = ev.cur_val[(t - 1) & 1][pb]; ev.lel_rub[pb] = ev.cur_rub[pb]; }
             }
         }

@@ -125,10 +125,10 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     if (recycle_.empty()) {
         id = (int)items_.size();
         items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
-        states_.resize(states_.size() + W); bits_.resize(bits_.size() + PW);
+        states_.grow(); bits_.resize(bits_.size() + PW);
     } else { id = recycle_.back(); recycle_.pop_back(); }
     items_[id] = Item{value, ub, depth, rec};
-    std::memcpy(&states_[(size_t)id * W], st, (size_t)W * 8);
+    std::memcpy(states_.at(id), st, (size_t)W * 8);
     std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
     std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
     int pc = 0;
@@ -325,6 +325,8 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         int pw = 1;
         const int total = eng->drain_all(slots, caps.data(), lbs.data(), &pw);
         if (total < 0) return total;
+        p_states.reserve(p_states.size() + (size_t)total * W); p_bits.reserve(p_bits.size() + (size_t)total * PWN);
+        p_val.reserve(p_val.size() + total); p_ub.reserve(p_ub.size() + total);
         int cur_dd = -1;
         for (int r = 0; r < total; ++r) {
             const int j = eng->h_out_dd[r];

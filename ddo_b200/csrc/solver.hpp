@@ -9,6 +9,8 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <memory>
+#include <algorithm>
 #include <vector>
 
 #include "engine.hpp"
@@ -28,7 +30,7 @@ public:
     // kind: DDO_MODEL_MISP -- MispRanking (popcount, BitSet::cmp), states compared without their depth (BitSet alone is the state);
     //       DDO_MODEL_MAX2SAT -- Max2SatRanking (rank = sum |benefit|, heuristics.rs:33-37) refined canonically by (depth, lexicographic
     //       benefits); the depth is part of the state (model.rs:59-62 derives Hash / Eq over both fields).
-    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) {}
+    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) { states_.init(words); }
     struct Item { int32_t value, ub, depth, rec; };
     size_t len() const { return live_; }
     bool empty() const { return live_ == 0; }
@@ -37,7 +39,7 @@ public:
     void push(const uint64_t* state, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words);
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
-    const uint64_t* state(int id) const { return &states_[(size_t)id * W]; }
+    const uint64_t* state(int id) const { return states_.at(id); }
     const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
     const Item& item(int id) const { return items_[id]; }
 private:
@@ -47,7 +49,15 @@ private:
     // the runs' tails.  An entry is stale when its node was popped or re-keyed since (version mismatch) and is skipped.
     struct Ent { uint64_t k1, k2; int id; uint32_t ver; };
     int W, PW, kind_;
-    std::vector<uint64_t> states_, bits_;
+    // states live in fixed blocks (no reallocation copies: a MAX2SAT fringe holds gigabytes of 2 KB states)
+    struct Arena {
+        int W = 1; size_t per_block = 1; std::vector<std::unique_ptr<uint64_t[]>> blocks; size_t count = 0;
+        void init(int w) { W = w; per_block = std::max<size_t>(1, ((size_t)1 << 22) / (size_t)w); }
+        uint64_t* at(size_t id) const { return blocks[id / per_block].get() + (id % per_block) * (size_t)W; }
+        void grow() { if (count == blocks.size() * per_block) blocks.emplace_back(new uint64_t[per_block * (size_t)W]); ++count; }
+        void clear() { blocks.clear(); count = 0; }
+    } states_;
+    std::vector<uint64_t> bits_;
     std::vector<Item> items_;
     std::vector<int32_t> popc_;  // ranking key of the state: popcount (MISP) / sum |benefit| (MAX2SAT)
     std::vector<uint64_t> hash_;
