@@ -206,8 +206,18 @@ int M2Engine::reserve_roots(int count) {
     return rc;
 }
 
+// dynamic shared memory of m2_expand: the four clause-weight rows of the branching variable + the hash multipliers (TMA staging buffers)
 template <int CH>
-static void launch_expand(M2Engine* E, int grid, int t, int count) { m2_expand<CH><<<grid, 256, 0, E->stream>>>(E->mv, t, count); }
+static cudaError_t launch_expand(M2Engine* E, int grid, int t, int count) {
+    const size_t smem = (size_t)5 * E->mv.NW * 4;
+    if (!E->expand_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(m2_expand<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        E->expand_attr_set = true;
+    }
+    m2_expand<CH><<<grid, 256, smem, E->stream>>>(E->mv, t, count);
+    return cudaSuccess;
+}
 
 int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
     if (count < 1 || count > K || count > staged) { set_error("compile: batch not staged"); return DDO_ERR_INVALID; }
@@ -248,10 +258,10 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
         m2_compact<<<compact_grid, 256, 0, st>>>(v, t, count);
         prof_mark(2);
         switch (ch) {
-            case 1: launch_expand<1>(this, flat_grid, t, count); break;
-            case 2: launch_expand<2>(this, flat_grid, t, count); break;
-            case 3: case 4: launch_expand<4>(this, flat_grid, t, count); break;
-            default: launch_expand<8>(this, flat_grid, t, count); break;
+            case 1: CUDA_TRY(launch_expand<1>(this, flat_grid, t, count)); break;
+            case 2: CUDA_TRY(launch_expand<2>(this, flat_grid, t, count)); break;
+            case 3: case 4: CUDA_TRY(launch_expand<4>(this, flat_grid, t, count)); break;
+            default: CUDA_TRY(launch_expand<8>(this, flat_grid, t, count)); break;
         }
         prof_mark(0);
         g_kernel_launches += 2; ++layer_steps;

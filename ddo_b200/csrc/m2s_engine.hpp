@@ -50,6 +50,7 @@ struct M2EV {
 struct M2Engine : Engine {
     const M2Model* m2 = nullptr;
     M2EV mv{};
+    bool expand_attr_set = false;
     int create_m2s(const M2Model* m, int device, uint64_t max_width_cap, int batch_cap, int cutset_type);
     int reserve_roots(int count) override;
     int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) override;

@@ -76,24 +76,78 @@ __global__ void __launch_bounds__(256) m2_init(M2EV ev, int count, int comp_type
 // =================================================================================================================
 // m2_expand: layer t -> candidates of layer t+1.  One warp per node; CH = 128-bit chunks of a row per lane.
 // =================================================================================================================
+// ---- TMA 1-D bulk copies (cp.async.bulk + mbarrier) ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// Every CTA walks a CONTIGUOUS range of tiles (8 nodes of one DD each), so the branching variable -- a function of the DD's depth -- changes
+// rarely: its four clause-weight rows (and, once, the hash multipliers) are staged in shared memory by TMA bulk copies and shared by the
+// eight warps, instead of being re-fetched through L1/L2 by every warp for every node.  Warps then run without block barriers.
 template <int CH>
 __global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t, int count) {
-    const int total = ev.tile_off_e[count];
+    const int* off = ev.tile_off_e;
+    const int total = off[count];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW4 = ev.NW4;
-    __shared__ unsigned int s_exp[8];
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int k = plan_find(ev.tile_off_e, count, tile);
+    const int buf = t & 1;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];  // [5][NW]: PT, QT, PF, QF rows of the current variable, hash multipliers
+    int4* sP[2] = {reinterpret_cast<int4*>(dyn_smem), reinterpret_cast<int4*>(dyn_smem) + 2 * NW4};
+    int4* sQ[2] = {reinterpret_cast<int4*>(dyn_smem) + NW4, reinterpret_cast<int4*>(dyn_smem) + 3 * NW4};
+    const uint4* sM = reinterpret_cast<const uint4*>(dyn_smem) + 4 * NW4;
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t row_bytes = (uint32_t)ev.NW * 4u;
+    const int tpb = (total + gridDim.x - 1) / gridDim.x;
+    const int tile_lo = min((int)blockIdx.x * tpb, total), tile_hi = min(tile_lo + tpb, total);
+    if (tile_lo >= tile_hi) return;
+    if (threadIdx.x == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    uint32_t phase = 0;
+    int k = plan_find(off, count, tile_lo);
+    int cur_var = -1, cur_k = -1;
+    unsigned exp_acc = 0;  // nodes of DD cur_k expanded by this warp since the last flush (lane 0)
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        while (off[k + 1] <= tile) ++k;
         DDCtl* ctl = ev.ctl + k;
+        const int depth = ctl->root_depth + t;
+        const int var = ev.ord[ev.n - depth - 1];  // model.rs:330-348
+        if (k != cur_k) {
+            if (lane == 0 && exp_acc) { atomicAdd(&ev.ctl[cur_k].expanded, (unsigned long long)exp_acc); atomicAdd(&ev.ctl[cur_k].transitions, (unsigned long long)(2 * exp_acc)); }
+            exp_acc = 0; cur_k = k;
+        }
+        if (var != cur_var) {  // block-uniform: every warp walks the same tiles
+            __syncthreads();   // everybody is done with the previous rows
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const bool first = cur_var < 0;
+                mbar_expect_tx(&s_bar, (first ? 5u : 4u) * row_bytes);
+                bulk_g2s(sP[0], ev.PT + (size_t)var * ev.NW, row_bytes, &s_bar);
+                bulk_g2s(sQ[0], ev.QT + (size_t)var * ev.NW, row_bytes, &s_bar);
+                bulk_g2s(sP[1], ev.PF + (size_t)var * ev.NW, row_bytes, &s_bar);
+                bulk_g2s(sQ[1], ev.QF + (size_t)var * ev.NW, row_bytes, &s_bar);
+                if (first) bulk_g2s(const_cast<uint4*>(sM), ev.hmul, row_bytes, &s_bar);
+            }
+            mbar_wait(&s_bar, phase); phase ^= 1;
+            cur_var = var;
+        }
         const int n_cur = ctl->n_cur;
-        const int node = (tile - ev.tile_off_e[k]) * 8 + warp;
-        unsigned my_exp = 0;
+        const int node = (tile - off[k]) * 8 + warp;
         if (node < n_cur) {
-            const int buf = t & 1;
             const size_t nb = (size_t)k * ev.Wcap + node;
             const size_t cb = (size_t)k * ev.C;
-            const int depth = ctl->root_depth + t;
-            const int var = ev.ord[ev.n - depth - 1];  // model.rs:330-348
             const int4* row = reinterpret_cast<const int4*>(m2_row(ev, buf, k, ev.cur_src[buf][nb]));
             int4 s[CH];
 #pragma unroll
@@ -111,7 +165,7 @@ __global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t
                 ev.uflag[cb + c_t] = 0; ev.uflag[cb + c_f] = 0;
             }
             if (expandable) {
-                my_exp = 1;
+                ++exp_acc;
                 // benefit of the branching variable itself (pos(state[k]) / pos(-state[k]) of model.rs:298,313)
                 int sv = 0;
                 {
@@ -124,8 +178,6 @@ __global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t
                 int values[2]; unsigned long long hashes[2];
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
-                    const int32_t* Pd = (d == 0 ? ev.PT : ev.PF) + (size_t)var * ev.NW;
-                    const int32_t* Qd = (d == 0 ? ev.QT : ev.QF) + (size_t)var * ev.NW;
                     const uint32_t c = d == 0 ? c_t : c_f;
                     int4* dst = reinterpret_cast<int4*>(m2_row(ev, buf ^ 1, k, c));
                     int cost = 0, crank = 0;
@@ -134,8 +186,8 @@ __global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t
                     for (int q = 0; q < CH; ++q) {
                         const int i = lane + 32 * q;
                         if (i < NW4) {
-                            const int4 P = __ldg(reinterpret_cast<const int4*>(Pd) + i), Q = __ldg(reinterpret_cast<const int4*>(Qd) + i);
-                            const uint4 m = __ldg(reinterpret_cast<const uint4*>(ev.hmul) + i);
+                            const int4 P = sP[d][i], Q = sQ[d][i];
+                            const uint4 m = sM[i];
                             int4 x = s[q], r;
                             // transition (model.rs:275-292) and the state-dependent part of transition_cost (model.rs:294-328)
                             r.x = x.x + P.x - Q.x; r.y = x.y + P.y - Q.y; r.z = x.z + P.z - Q.z; r.w = x.w + P.w - Q.w;
@@ -202,15 +254,8 @@ __global__ void __launch_bounds__(256, CH <= 4 ? 4 : 2) m2_expand(M2EV ev, int t
                 }
             }
         }
-        if (lane == 0) s_exp[warp] = my_exp;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned e = 0;
-            for (int w = 0; w < 8; ++w) e += s_exp[w];
-            if (e) { atomicAdd(&ctl->expanded, (unsigned long long)e); atomicAdd(&ctl->transitions, (unsigned long long)(2 * e)); }
-        }
-        __syncthreads();
     }
+    if (lane == 0 && exp_acc) { atomicAdd(&ev.ctl[cur_k].expanded, (unsigned long long)exp_acc); atomicAdd(&ev.ctl[cur_k].transitions, (unsigned long long)(2 * exp_acc)); }
 }
 
 // cut order between two distinct candidates (clean.rs:803-808 + heuristics.rs:33-37 + canonical tie-break): true if a is BETTER than b
