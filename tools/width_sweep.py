@@ -11,6 +11,7 @@ from ddo_b200 import FixedWidth, Misp, ParNoCachingSolverLel, gnp  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
 widths = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1000, 2000, 5000, 10000, 20000, 50000, 100000]
+mem_budget = float(sys.argv[3]) * 1e9 if len(sys.argv) > 3 else 6e9  # device memory the DD arenas may take (GB)
 peak = 6530.6
 pk = ROOT / "MEASURED_PEAKS.json"
 if pk.exists():
@@ -18,7 +19,7 @@ if pk.exists():
 inst = gnp(1000, 0.5, 1)
 pb = Misp(inst)
 for w in widths:
-    cap = max(2, min(256, int(6e9 // (w * 1001 * 20))))  # ~20 B of logs per node and layer: keep the arenas of one engine under ~6 GB x 2
+    cap = max(2, min(256, int(mem_budget // (w * 1001 * 20))))  # ~20 B of logs per node and layer per DD slot
     s = ParNoCachingSolverLel(pb, FixedWidth(w), wave_size=2048, batch_cap=cap)
     s.maximize(max_waves=2)  # warm-up (allocations, first launches)
     t0 = time.perf_counter()
