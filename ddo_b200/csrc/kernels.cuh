@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, i
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
     constexpr int RP = G >= 8 ? 1 : 8 / G;  // claimed rows per 128 bytes of the staging buffer (bank swizzle below)
-    __shared__ unsigned int s_exp, s_tr, s_rows, s_claims;
+    // per-tile counters and the per-DD claim counter live in separate 16-byte slots: thread 0 updates the claim counter while the other
+    // threads may still be reading the tile counters (the compiler is free to fetch neighbouring words with one vector load)
+    __shared__ __align__(16) unsigned int s_tilectr[4];
+    __shared__ __align__(16) unsigned int s_claimbox[4];
+    unsigned int& s_exp = s_tilectr[0]; unsigned int& s_tr = s_tilectr[1]; unsigned int& s_rows = s_tilectr[2]; unsigned int& s_claims = s_claimbox[0];
     __shared__ uint4 s_claim[2 * NPB * G];     // distinct states claimed by this tile (zero rows elsewhere): row r, chunk q at [r*G + (q ^ ((r / RP) & (G-1)))]
     __shared__ unsigned int s_hist[64 * S];    // per-vertex occurrence counts of the claimed states, flushed per DD
     const int* off = ev.tile_off_e;  // (L1-resident; staging the plan in shared memory measured slower)

@@ -269,6 +269,9 @@ void oracle_m2s_stepper_free(void* s) { delete (Stepper<M2Handle>*)s; }
 void oracle_m2s_stepper_init(void* s, int32_t push_root) { ((Stepper<M2Handle>*)s)->solver->init(push_root != 0); }
 int32_t oracle_m2s_stepper_wave(void* s, int64_t out3[3]) { return stepper_wave((Stepper<M2Handle>*)s, out3); }
 void oracle_m2s_stepper_state(void* s, int64_t out[6]) { stepper_state((Stepper<M2Handle>*)s, out); }
+void oracle_m2s_stepper_set_lb(void* s, int64_t lb) { ((Stepper<M2Handle>*)s)->solver->set_lower_bound(lb); }
+void oracle_m2s_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((Stepper<M2Handle>*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
+void oracle_m2s_stepper_finish(void* s) { ((Stepper<M2Handle>*)s)->solver->finish(); }
 
 // CPU baseline of a batch of independent sub-problems: for each root, restricted DD then (if inexact) relaxed DD, all against the same
 // best_lb, on `threads` worker threads each owning one Mdd (the ParallelSolver worker body, parallel.rs:391-437, without the fringe).

@@ -100,6 +100,9 @@ def lib():
         _lib.oracle_m2s_stepper_init.argtypes = [C.c_void_p, C.c_int32]
         _lib.oracle_m2s_stepper_wave.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 3)]
         _lib.oracle_m2s_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
+        _lib.oracle_m2s_stepper_set_lb.argtypes = [C.c_void_p, C.c_int64]
+        _lib.oracle_m2s_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        _lib.oracle_m2s_stepper_finish.argtypes = [C.c_void_p]
         _lib.oracle_knapsack_solve.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                                C.POINTER(SolveResult), C.c_void_p]
         _lib.oracle_locbounds_dump.argtypes = [C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
@@ -283,37 +286,41 @@ OracleM2s.compile_many = _m2s_compile_many
 class OracleStepper:
     """Stepwise CPU wave solver with the interface ddo_b200.sharded.sharded_maximize expects (stand-in for the device solver)."""
 
-    def __init__(self, oracle: OracleMisp, wave_size: int, width=None):
+    def __init__(self, oracle, wave_size: int, width=None):
         self.o = oracle
-        self.h = lib().oracle_misp_stepper_new(oracle.h, wave_size, 0 if width is not None else 1, width or 0)
+        self.p = oracle.PREFIX
+        self.h = self._f("stepper_new")(oracle.h, wave_size, 0 if width is not None else 1, width or 0)
+
+    def _f(self, name):
+        return getattr(lib(), f"oracle_{self.p}_{name}")
 
     def __del__(self):
         try:
-            lib().oracle_misp_stepper_free(self.h)
+            self._f("stepper_free")(self.h)
         except Exception:
             pass
 
     def init(self, push_root=True):
-        lib().oracle_misp_stepper_init(self.h, int(push_root))
+        self._f("stepper_init")(self.h, int(push_root))
 
     def wave(self):
         out = (C.c_int64 * 3)()
-        rc = lib().oracle_misp_stepper_wave(self.h, C.byref(out))
+        rc = self._f("stepper_wave")(self.h, C.byref(out))
         assert rc == 0
         return int(out[0]), int(out[1]), int(out[2])
 
     def set_lower_bound(self, lb):
-        lib().oracle_misp_stepper_set_lb(self.h, lb)
+        self._f("stepper_set_lb")(self.h, lb)
 
     def retain_share(self, rank, nranks):
-        lib().oracle_misp_stepper_retain_share(self.h, rank, nranks)
+        self._f("stepper_retain_share")(self.h, rank, nranks)
 
     def finish(self):
-        lib().oracle_misp_stepper_finish(self.h)
+        self._f("stepper_finish")(self.h)
 
     def _state(self):
         out = (C.c_int64 * 6)()
-        lib().oracle_misp_stepper_state(self.h, C.byref(out))
+        self._f("stepper_state")(self.h, C.byref(out))
         return [int(x) for x in out]
 
     def fringe_len(self):

@@ -25,14 +25,17 @@ def _worker(rank, world, port, spec, out_dir):
     import torch.distributed as dist
 
     import oracle_lib as O
-    from ddo_b200.instances import gnp, parse_dimacs
+    from ddo_b200.instances import gnp, parse_dimacs, random_max2sat
     from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    inst = gnp(*spec["gnp"]) if "gnp" in spec else parse_dimacs((ROOT / "tests" / "golden" / "misp" / spec["file"]).read_text())
-    stepper = O.OracleStepper(O.OracleMisp(inst), spec["wave"], spec.get("width"))
+    if "m2s" in spec:
+        oracle = O.OracleM2s(random_max2sat(*spec["m2s"]))
+    else:
+        oracle = O.OracleMisp(gnp(*spec["gnp"]) if "gnp" in spec else parse_dimacs((ROOT / "tests" / "golden" / "misp" / spec["file"]).read_text()))
+    stepper = O.OracleStepper(oracle, spec["wave"], spec.get("width"))
     res = sharded_maximize(stepper, rank, world, torch_allreduce_max())
     res.update(rank=rank, explored=stepper.explored(), expanded=stepper.expanded())
     Path(out_dir, f"r{rank}.json").write_text(json.dumps(res))
@@ -66,3 +69,16 @@ def test_sharded_bnb_known_optimum_dimacs(tmp_path):
     exp = json.loads((ROOT / "tests" / "golden" / "expected.json").read_text())["misp"]["johnson8-4-4"]["optimum"]
     res = _run(2, {"file": "johnson8-4-4.clq", "wave": 8}, tmp_path)
     assert all(r["is_exact"] and r["best_lb"] == exp and r["best_ub"] == exp for r in res)
+
+
+def test_sharded_bnb_max2sat_agrees_with_single_process(tmp_path):
+    """The same protocol over the MAX2SAT model (BASELINE config 3 is fringe-sharded over 1 -> 8 GPUs)."""
+    import oracle_lib as O
+    from ddo_b200.instances import random_max2sat
+
+    spec = {"m2s": (22, 110, 4), "wave": 4, "width": 5}
+    single = O.OracleM2s(random_max2sat(*spec["m2s"])).solve("wave", k=spec["wave"], width=spec["width"])
+    res = _run(2, spec, tmp_path)
+    for r in res:
+        assert r["is_exact"] and r["best_lb"] == r["best_ub"] == single["best_value"]
+    assert all(r["explored"] >= 1 for r in res) and max(r["explored"] for r in res) < single["explored"] + 2
