@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace ddo {
 
@@ -143,7 +144,25 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
 }
 void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
-    std::sort(pending_.begin(), pending_.end(), [this](const Ent& a, const Ent& b) { return ent_less(a, b); });
+    auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
+    if (pending_.size() < (1u << 15)) std::sort(pending_.begin(), pending_.end(), less);
+    else {  // a wide wave's cutsets (hundreds of thousands of nodes): sort eight slices on eight threads, then merge pairwise
+        constexpr int T = 8;
+        const size_t n = pending_.size();
+        size_t cut[T + 1];
+        for (int i = 0; i <= T; ++i) cut[i] = n * (size_t)i / T;
+        {
+            std::vector<std::thread> ts;
+            for (int i = 0; i < T; ++i) ts.emplace_back([&, i] { std::sort(pending_.begin() + cut[i], pending_.begin() + cut[i + 1], less); });
+            for (auto& t : ts) t.join();
+        }
+        for (int step = 1; step < T; step *= 2) {
+            std::vector<std::thread> ts;
+            for (int i = 0; i + step < T; i += 2 * step)
+                ts.emplace_back([&, i, step] { std::inplace_merge(pending_.begin() + cut[i], pending_.begin() + cut[i + step], pending_.begin() + cut[std::min(i + 2 * step, T)], less); });
+            for (auto& t : ts) t.join();
+        }
+    }
     runs_.emplace_back();
     runs_.back().swap(pending_);
     if (runs_.size() > 24) {  // keep the number of runs bounded: merge everything, dropping stale entries
@@ -206,6 +225,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const int W = words, PWN = (n_vars + 63) / 64;
     // ---- get_workload (parallel.rs:500-559): pop up to wave_size open sub-problems ---------------------------------------------
     double t0 = now_ms();
+    const double tr_wave0 = t0;
     int64_t top_ub = INT64_MIN;
     w_states.clear(); w_bits.clear(); w_items.clear();
     while ((int)w_items.size() < wave_size && !fringe.empty()) {
@@ -220,6 +240,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         ++explored;
     }
     fringe_ms += now_ms() - t0;
+    const double tr_pop = now_ms() - t0;
     out3[1] = top_ub;
     const int cnt = (int)w_items.size();
     if (cnt == 0) { out3[0] = best_lb; out3[2] = 0; return DDO_OK; }
@@ -472,8 +493,8 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         fringe_ms += now_ms() - t0;
     }
     if (trace_file)
-        std::fprintf(trace_file, "%llu %d %zu %zu %.3f %.3f %llu %llu %zu\n", (unsigned long long)waves, cnt, ov.size(), open.size(), tr_small, tr_general,
-                     (unsigned long long)(eng->layer_steps - tr_steps0), (unsigned long long)(expanded - tr_exp0), fringe.len());
+        std::fprintf(trace_file, "%llu %d %zu %zu %.3f %.3f %llu %llu %zu %.3f %.3f\n", (unsigned long long)waves, cnt, ov.size(), open.size(), tr_small, tr_general,
+                     (unsigned long long)(eng->layer_steps - tr_steps0), (unsigned long long)(expanded - tr_exp0), fringe.len(), tr_pop, now_ms() - tr_wave0);
     out3[0] = best_lb;
     out3[2] = fringe.empty() ? 0 : 1;
     return DDO_OK;
