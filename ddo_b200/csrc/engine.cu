@@ -108,7 +108,14 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(ev.cur_rub, KW);
     ALLOC(ev.cand_state, KC * S); ALLOC(ev.cand_rep, KC); ALLOC(ev.cand_first, KC); ALLOC(ev.cand_agg, KC); ALLOC(ev.cand_inex, KC);
     ALLOC(ev.cand_rank, KC); ALLOC(ev.cand_slot, KC);
-    ALLOC(ev.uflag, KC); ALLOC(ev.ulist, KC); ALLOC(ev.pos_of, KC);
+    ALLOC(ev.uflag, KC); ALLOC(ev.ulist, KC); ALLOC(ev.pos_of, KC); ALLOC(ev.gflag, KC + 16);
+    {   // cluster finish: per-CTA capacity of distinct candidates = its slice of the candidates
+        const int per = (((C + FCL_CS * FCL_NT - 1) / (FCL_CS * FCL_NT)) + 3) & ~3;
+        finish_cl_kcap = per * FCL_NT;
+        finish_cl_smem = (size_t)finish_cl_kcap * 9 + 16;
+        if (finish_cl_smem > 200 * 1024) finish_cl_max = 0;  // slices of very wide layers do not fit shared memory: one-CTA finish with global keys
+        if (const char* e = getenv("DDO_FINISH_CL_MAX")) finish_cl_max = std::min(finish_cl_max > 0 ? 1 << 20 : 0, atoi(e));
+    }
     // keys (8 B) + status (1 B) of up to C distinct candidates: shared memory when they fit next to the 19 KB of static smem
     finish_smem = (size_t)C * 9 + 16;
     ev.smem_keys = finish_smem <= 200 * 1024;
@@ -224,6 +231,11 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         CUDA_TRY(cudaFuncSetAttribute(k_finish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_smem));
         E->finish_attr_set = true;
     }
+    const bool use_cl = slots <= E->finish_cl_max;
+    if (use_cl && !E->finish_cl_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_finish_cl<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_cl_smem));
+        E->finish_cl_attr_set = true;
+    }
     k_init<S><<<slots, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb, slots > count);
     ++g_kernel_launches;
     E->prof_mark(-1);
@@ -233,7 +245,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = 16;
     for (int t = 0; t < E->Lmax; ++t) {
-        k_finish<S><<<slots, 1024, E->finish_smem, st>>>(ev, t);
+        if (use_cl) k_finish_cl<S><<<slots * FCL_CS, FCL_NT, E->finish_cl_smem, st>>>(ev, t, E->finish_cl_kcap);
+        else k_finish<S><<<slots, 1024, E->finish_smem, st>>>(ev, t);
         E->prof_mark(1);
         k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(2);

@@ -70,6 +70,7 @@ struct EV {
     uint64_t* cand_state; uint32_t* cand_rep; uint32_t* cand_first; unsigned long long* cand_agg; uint8_t* cand_inex; uint32_t* cand_rank; uint32_t* cand_slot;
     // unique nodes of the next layer
     uint8_t* uflag; uint32_t* ulist; uint8_t* ustat; uint32_t* pos_of;
+    uint8_t* gflag;   // [K][C] canonical-candidate flags of the cluster finish (k_finish_cl)
     unsigned long long* gkeys; int smem_keys;  // cut keys of the distinct candidates: in k_finish's shared memory when 2*Wcap of them fit, else here
     unsigned long long* table;
     uint32_t* ucount; // [K] number of distinct states among the candidates being built (hash-slot claims of k_expand)
@@ -113,6 +114,7 @@ struct Engine {
     int num_sms = 148;
     bool dual_enabled = true;  // fork the relaxed twin at the first cut of a restricted DD (DDO_DUAL=0 disables)
     size_t finish_smem = 0; bool finish_attr_set = false;
+    int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     EV ev{};

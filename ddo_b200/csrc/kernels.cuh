@@ -15,6 +15,8 @@
 #pragma once
 #include "engine.hpp"
 
+#include <cooperative_groups.h>
+
 namespace ddo {
 
 #define FULL_MASK 0xffffffffu
@@ -739,6 +741,457 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
     // ---- work plan of the two flat kernels that follow: the last CTA to finish scans the per-DD tile counts --------------------
     constexpr int G = S / 2, PER_TILE = 256 / G;
     const int tid = threadIdx.x, count = gridDim.x;
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(ev.finish_counter, 1u) == (unsigned)count - 1u); }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile DDCtl* vc = ev.ctl;
+    const int per = (count + blockDim.x - 1) / blockDim.x;
+    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    int te = 0, tc = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        te += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
+        tc += (st == ST_ACTIVE || st == ST_TERMINAL) ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+    }
+    int tote, totc;
+    int oe = block_excl_scan(te, &tote, sm.scan);
+    int oc = block_excl_scan(tc, &totc, sm.scan);
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        ev.tile_off_e[k] = oe; ev.tile_off_c[k] = oc;
+        oe += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
+        oc += (st == ST_ACTIVE || st == ST_TERMINAL) ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
+    }
+    if (tid == 0) { ev.tile_off_e[count] = tote; ev.tile_off_c[count] = totc; *ev.finish_counter = 0; }
+}
+
+// =================================================================================================================
+// k_finish_cl: the same decisions as k_finish taken by a thread-block CLUSTER per DD (FCL_CS CTAs of FCL_NT threads), for narrow
+// batches, where one CTA per DD leaves the machine idle and its ~45 us chain of block barriers and L2 round trips is the latency of
+// a layer step.  Every CTA owns a contiguous slice of the candidates (keys and status bytes of its distinct candidates in its own shared
+// memory); counts, offsets, digit histograms, the merged state and maxima are exchanged through distributed shared memory between
+// cluster barriers.  All control decisions are cluster-uniform (every CTA executes the same sequence of cluster barriers).
+// =================================================================================================================
+namespace cg = cooperative_groups;
+constexpr int FCL_CS = 8;
+constexpr int FCL_NT = 256;
+
+struct FinishClSmem {
+    int scan[40];
+    unsigned long long red64[40];
+    unsigned int hist[2][256];        // local digit histograms, double-buffered across cluster barriers
+    unsigned int ghist[256];          // cluster-wide digit histogram
+    unsigned long long merged[32];
+    unsigned long long xch[2][4];     // exchange slots (double-buffered): up to 4 block-uniform values per exchange
+    int misc[16];
+};
+
+struct ClusterXchg {
+    cg::cluster_group cl; FinishClSmem* sm; int phase; int hphase; unsigned rank;
+    // fold of up to 4 block-uniform values over the CTAs of the cluster; result uniform in the whole cluster
+    template <class Op> __device__ void allreduce(unsigned long long* v, int n, Op op) {
+        if (threadIdx.x == 0) for (int i = 0; i < n; ++i) sm->xch[phase][i] = v[i];
+        cl.sync();
+        for (int i = 0; i < n; ++i) {
+            unsigned long long acc = *cl.map_shared_rank(&sm->xch[phase][i], 0);
+            for (unsigned r = 1; r < FCL_CS; ++r) acc = op(acc, *cl.map_shared_rank(&sm->xch[phase][i], r));
+            v[i] = acc;
+        }
+        phase ^= 1;
+    }
+    // exclusive prefix over the ranks of one block-uniform count; *total = sum over the cluster
+    __device__ int scan(int v, int* total) {
+        if (threadIdx.x == 0) sm->xch[phase][0] = (unsigned long long)(unsigned)v;
+        cl.sync();
+        int pre = 0, tot = 0;
+        for (unsigned r = 0; r < FCL_CS; ++r) { const int x = (int)*cl.map_shared_rank(&sm->xch[phase][0], r); if (r < rank) pre += x; tot += x; }
+        phase ^= 1;
+        *total = tot;
+        return pre;
+    }
+};
+
+template <int S>
+__device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned long long* keys, uint8_t* stat, int kcap) {
+    constexpr int NT = FCL_NT;
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned rank = cl.block_rank();
+    ClusterXchg X{cl, &sm, 0, 0, rank};
+    const int k = blockIdx.x / FCL_CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gt = (int)rank * NT + tid;  // thread index in the cluster: candidate chunks are contiguous in this order
+    DDCtl* ctl = ev.ctl + k;
+    const int status = ctl->status;
+    if (status == ST_DONE) return;
+    if (status == ST_TERMINAL) { cl.sync(); if (rank == 0 && tid == 0) ctl->status = ST_DONE; return; }
+    const size_t cb = (size_t)k * ev.C;
+    const size_t lb = (size_t)k * ev.Lmax;
+    int vh_src = k;
+    if (status == ST_WAITING) {  // relaxed twin: fork at the primary's first cut (see finish_body)
+        const int p = ctl->primary;
+        const DDCtl* pc = ev.ctl + p;
+        const int plel = pc->lel;
+        const bool fork = t >= 1 && ev.ucount[p] > (uint32_t)pc->width && (plel < 0 || plel == t - 1) && ev.nlog[(size_t)p * ev.Lmax + t - 1] > 0;
+        if (!fork) return;
+        const size_t pb = (size_t)p * ev.C, plb = (size_t)p * ev.Lmax;
+        const int n_prev = ev.nlog[plb + t - 1];
+        const int nc = 2 * n_prev;
+        constexpr int GN = FCL_CS * NT;
+        {
+            const uint4* s4 = reinterpret_cast<const uint4*>(ev.cand_state + pb * S); uint4* d4 = reinterpret_cast<uint4*>(ev.cand_state + cb * S);
+            for (int i = gt; i < nc * (S / 2); i += GN) d4[i] = s4[i];
+            for (int c = gt; c < nc; c += GN) {
+                ev.cand_agg[cb + c] = ev.cand_agg[pb + c]; ev.cand_first[cb + c] = ev.cand_first[pb + c]; ev.cand_rep[cb + c] = ev.cand_rep[pb + c];
+                ev.cand_inex[cb + c] = ev.cand_inex[pb + c]; ev.cand_rank[cb + c] = ev.cand_rank[pb + c]; ev.cand_slot[cb + c] = ev.cand_slot[pb + c];
+                ev.uflag[cb + c] = 0;
+            }
+            const unsigned long long* st = ev.table + (size_t)p * ev.T; unsigned long long* dt = ev.table + (size_t)k * ev.T;
+            for (int i = gt; i < ev.T; i += GN) dt[i] = st[i];
+            const int pbuf = (t - 1) & 1;
+            const uint4* cs4 = reinterpret_cast<const uint4*>(ev.cur_state[pbuf] + (size_t)p * ev.Wcap * S); uint4* cd4 = reinterpret_cast<uint4*>(ev.cur_state[pbuf] + (size_t)k * ev.Wcap * S);
+            for (int i = gt; i < n_prev * (S / 2); i += GN) cd4[i] = cs4[i];
+            for (int i = gt; i < n_prev; i += GN) {
+                ev.cur_val[pbuf][(size_t)k * ev.Wcap + i] = ev.cur_val[pbuf][(size_t)p * ev.Wcap + i];
+                ev.cur_rub[(size_t)k * ev.Wcap + i] = ev.cur_rub[(size_t)p * ev.Wcap + i];
+            }
+            for (int i = gt; i < t; i += GN) {
+                ev.nlog[lb + i] = ev.nlog[plb + i]; ev.vlog[lb + i] = ev.vlog[plb + i];
+                ev.rslog[(lb + i) * 2] = ev.rslog[(plb + i) * 2]; ev.rslog[(lb + i) * 2 + 1] = ev.rslog[(plb + i) * 2 + 1];
+            }
+        }
+        __threadfence();
+        cl.sync();
+        if (rank == 0 && tid == 0) {
+            ctl->status = ST_ACTIVE; ctl->fork_t = t;
+            ctl->expanded = pc->expanded; ctl->transitions = pc->transitions;
+            atomicAdd(ev.active, 1);
+        }
+        // n_cur is needed by every CTA below: take it from the copy source instead of ctl (written by rank 0 only)
+        vh_src = p;
+    }
+    const int n_cur_here = status == ST_WAITING ? ev.nlog[(size_t)ctl->primary * ev.Lmax + t - 1] : ctl->n_cur;
+    const int ncand = t == 0 ? 1 : 2 * n_cur_here;
+    if (rank == 0 && tid == 0) { if (status == ST_WAITING) ctl->n_cur = n_cur_here; ctl->ncand = ncand; ctl->lel_pending = 0; }
+
+    const int per = (((ncand + FCL_CS * NT - 1) / (FCL_CS * NT)) + 3) & ~3;
+    const int lo = min(gt * per, ncand), hi = min(lo + per, ncand);
+
+    // ---- B. next_variable: argmin of the vertex histogram (every CTA computes it: n <= 1024 L2 loads, no exchange needed) -----------
+    unsigned long long best = ~0ull;
+    {
+        const uint32_t* vh = ev.vhist + (size_t)vh_src * ev.HN;
+        for (int i = tid; i < ev.n; i += NT) {
+            const unsigned c = __ldcg(vh + i);
+            if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)i);
+        }
+    }
+    // ---- A. canonical representatives: flags in global memory (a first candidate may belong to another CTA's slice) ------------------
+    uint8_t* uniq = ev.gflag + cb;
+    for (int c0 = lo; c0 < hi; c0 += 4) *reinterpret_cast<uint32_t*>(uniq + c0) = 0u;
+    __threadfence();
+    cl.sync();
+    for (int c0 = lo; c0 < hi; c0 += 4) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(ev.cand_rep + cb + c0);
+        const uint4 f4 = *reinterpret_cast<const uint4*>(ev.cand_first + cb + c0);
+        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (uint32_t)(c0 + j);
+            if ((int)c < hi && rr[j] == c) {
+                const uint32_t f = ff[j];
+                uniq[f] = 1;
+                if (f != c) { ev.cand_agg[cb + f] = ev.cand_agg[cb + c]; ev.cand_inex[cb + f] = ev.cand_inex[cb + c]; }
+            }
+        }
+    }
+    __threadfence();
+    cl.sync();
+    // ---- A'. ordered list of the distinct candidates -------------------------------------------------------------------------------
+    int cnt = 0;
+    for (int c0 = lo; c0 < hi; c0 += 4) {
+        uint32_t fl = __ldcg(reinterpret_cast<const uint32_t*>(uniq + c0));
+        if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u;
+        cnt += __popc(fl & 0x01010101u);
+    }
+    int Ublk;
+    const int offb = block_excl_scan(cnt, &Ublk, sm.scan);
+    int U;
+    const int cta_off = X.scan(Ublk, &U);   // first distinct candidate of this CTA in the DD-wide ordered list
+    const int off0 = cta_off + offb;
+    if (U == 0) {
+        if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->t_term = t; ctl->has_best = 0; ctl->has_best_exact = 0; ev.nlog[lb + t] = 0; atomicSub(ev.active, 1); }
+        return;
+    }
+    best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, sm.red64);
+    const bool terminal = best == ~0ull;
+    const int var = terminal ? -1 : (int)(uint32_t)best;
+
+    // ---- C. width cut --------------------------------------------------------------------------------------------------------------
+    const int W = ctl->width, comp = ctl->comp_type;
+    bool cut = false; int need = 0;
+    if (!terminal) {
+        if (comp == DDO_RESTRICTED && U > W) { cut = true; need = W; }
+        else if (comp == DDO_RELAXED && U > W && t >= 2) { cut = true; need = W - 1; }
+    }
+    if (!cut && U > ev.Wcap) {
+        if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->overflow = 1; ctl->t_term = t; atomicSub(ev.active, 1); }
+        return;
+    }
+    // local index of a distinct candidate of this CTA: li = ui - cta_off, 0 <= li < Ublk (<= kcap)
+    {
+        int off = off0;
+        for (int c0 = lo; c0 < hi; c0 += 4) {
+            uint32_t fl = __ldcg(reinterpret_cast<const uint32_t*>(uniq + c0));
+            if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u;
+            if (!fl) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) {
+                ev.ulist[cb + off] = (uint32_t)(c0 + j);
+                if (cut) keys[off - cta_off] = (ev.cand_agg[cb + c0 + j] & 0xFFFFFFFF00000000ull) | ev.cand_rank[cb + c0 + j];
+                ++off;
+            }
+        }
+    }
+    __syncthreads();
+    if (cut) for (int li = tid; li < Ublk; li += NT) stat[li] = 0;
+    __syncthreads();
+    if (cut) {
+        bool done = false;
+        if (need == 0) { for (int li = tid; li < Ublk; li += NT) stat[li] = 2; done = true; }
+        for (int chunk = 0; chunk <= S && !done; ++chunk) {
+            auto key_of = [&](int li) -> unsigned long long {
+                if (chunk == 0) return keys[li];
+                return lex_word(ev.cand_state[(cb + ev.ulist[cb + cta_off + li]) * S + (chunk - 1)]);
+            };
+            unsigned long long kk[2] = {0ull, 0ull};  // OR of the undecided keys, OR of their complements (AND = ~kk[1]; one fold serves both)
+            for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) { unsigned long long x = key_of(li); kk[0] |= x; kk[1] |= ~x; }
+            kk[0] = block_reduce(kk[0], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
+            kk[1] = block_reduce(kk[1], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
+            X.allreduce(kk, 2, [](unsigned long long a, unsigned long long b) { return a | b; });
+            const unsigned long long diff = kk[0] ^ ~kk[1];
+            for (int byte = 7; byte >= 0 && !done; --byte) {
+                if (((diff >> (8 * byte)) & 0xff) == 0) continue;
+                unsigned int* h = sm.hist[X.hphase];
+                for (int i = tid; i < 256; i += NT) h[i] = 0;
+                __syncthreads();
+                for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) atomicAdd(&h[(key_of(li) >> (8 * byte)) & 0xff], 1u);
+                cl.sync();
+                for (int i = tid; i < 256; i += NT) {
+                    unsigned int a = 0;
+                    for (unsigned r = 0; r < FCL_CS; ++r) a += *cl.map_shared_rank(&h[i], r);
+                    sm.ghist[i] = a;
+                }
+                X.hphase ^= 1;
+                __syncthreads();
+                if (warp == 0) {
+                    int c8[8]; int s8 = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { c8[q] = (int)sm.ghist[255 - (lane * 8 + q)]; s8 += c8[q]; }
+                    int inc = s8;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
+                    int before = inc - s8;
+                    if (before < need && need <= inc) {
+                        int acc = before;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (acc < need && need <= acc + c8[q]) { sm.misc[0] = 255 - (lane * 8 + q); sm.misc[1] = acc; sm.misc[2] = c8[q]; }
+                            acc += c8[q];
+                        }
+                    }
+                }
+                __syncthreads();
+                const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
+                need -= above;
+                const bool all_keep = (need == inb);
+                for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) {
+                    const int d = (int)((key_of(li) >> (8 * byte)) & 0xff);
+                    if (d > b) stat[li] = 1; else if (d < b) stat[li] = 2; else if (all_keep) stat[li] = 1;
+                }
+                __syncthreads();
+                if (all_keep) done = true;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- D. stable positions of the survivors ----------------------------------------------------------------------------------------
+    int nkeep, kp;
+    if (cut) {
+        int kc = 0;
+        for (int i = 0; i < cnt; ++i) kc += (stat[off0 - cta_off + i] == 1);
+        int kblk;
+        const int kpb = block_excl_scan(kc, &kblk, sm.scan);
+        kp = X.scan(kblk, &nkeep) + kpb;
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t c = ev.ulist[cb + off0 + i];
+            if (stat[off0 - cta_off + i] == 1) { ev.pos_of[cb + c] = (uint32_t)kp++; ev.uflag[cb + c] = 2; } else ev.pos_of[cb + c] = NONE32;
+        }
+    } else {
+        nkeep = U; kp = off0;
+        for (int c0 = lo; c0 < hi; c0 += 4) {
+            uint32_t fl = __ldcg(reinterpret_cast<const uint32_t*>(uniq + c0));
+            if (c0 + 4 > hi) fl &= (1u << (8 * (hi - c0))) - 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) { ev.pos_of[cb + c0 + j] = (uint32_t)kp++; ev.uflag[cb + c0 + j] = 2; }
+        }
+    }
+    int n_next = nkeep;
+    int s_pos = -1, r_pos = -1;
+    __syncthreads();
+
+    // ---- E. relaxation: merge the overflow ------------------------------------------------------------------------------------------
+    if (cut && comp == DDO_RELAXED) {
+        if (tid < 32) sm.merged[tid] = 0;
+        __syncthreads();
+        uint64_t acc[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) acc[j] = 0;
+        unsigned long long mkey = 0;
+        for (int li = tid; li < Ublk; li += NT) if (stat[li] == 2) {
+            const uint32_t c = ev.ulist[cb + cta_off + li];
+            const uint4* sp = reinterpret_cast<const uint4*>(ev.cand_state + (cb + c) * S);
+#pragma unroll
+            for (int j = 0; j < S / 2; ++j) { const uint4 v4 = sp[j]; acc[2 * j] |= u4lo(v4); acc[2 * j + 1] |= u4hi(v4); }
+            mkey = max(mkey, ev.cand_agg[cb + c]);
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint64_t x = warp_reduce(acc[j], [](uint64_t a, uint64_t b) { return a | b; });
+            if (lane == 0 && x) atomicOr(&sm.merged[j], (unsigned long long)x);
+        }
+        mkey = block_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        X.allreduce(&mkey, 1, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });  // (its barrier also publishes sm.merged and pos_of)
+        __threadfence();
+        if (tid < S) {  // the cluster-wide union, gathered by every CTA (S <= 16 words x 8 ranks)
+            unsigned long long m = 0;
+            for (unsigned r = 0; r < FCL_CS; ++r) m |= *cl.map_shared_rank(&sm.merged[tid], r);
+            sm.merged[16 + tid] = m;
+        }
+        __syncthreads();
+        // recycled ? a KEPT node whose state equals the merged state (every CTA runs the same lookup: cluster-uniform result)
+        if (tid == 0) {
+            uint64_t h = 0;
+            for (int j = 0; j < S; ++j) h += sm.merged[16 + j] * hash_mul(j);
+            h = mix64(h);
+            const uint32_t tag = (uint32_t)(h >> 32);
+            uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+            const unsigned long long* tab = ev.table + (size_t)k * ev.T;
+            int recycled = -1;
+            for (;;) {
+                const unsigned long long e = tab[slot];
+                if (e == EMPTY64) break;
+                if ((uint32_t)(e >> 32) == tag) {
+                    const uint32_t oc = (uint32_t)e;
+                    bool eq = true;
+                    for (int j = 0; j < S; ++j) eq = eq && ev.cand_state[(cb + oc) * S + j] == sm.merged[16 + j];
+                    if (eq) { const uint32_t f = ev.cand_first[cb + oc]; if (__ldcg(ev.pos_of + cb + f) != NONE32) recycled = (int)f; break; }
+                }
+                slot = (slot + 1) & (uint32_t)(ev.T - 1);
+            }
+            sm.misc[4] = recycled;
+        }
+        __syncthreads();
+        const int recycled = sm.misc[4];
+        const int mpos = (recycled >= 0) ? (int)__ldcg(ev.pos_of + cb + recycled) : nkeep;
+        cl.sync();  // every CTA has finished its lookup (it reads pos_of) before anybody re-points the merged-away candidates below
+        if (recycled >= 0) {
+            // the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node (clean.rs:868-871)
+            uint32_t bestc = NONE32;
+            for (int li = tid; li < Ublk; li += NT) if (stat[li] == 2) {
+                const uint32_t c = ev.ulist[cb + cta_off + li];
+                if (bestc == NONE32 || cand_better<S>(ev, cb, c, bestc)) bestc = c;
+            }
+            __shared__ uint32_t s_best[NT];
+            s_best[tid] = bestc;
+            __syncthreads();
+            for (int d = NT / 2; d > 0; d >>= 1) {
+                if (tid < d) {
+                    const uint32_t a = s_best[tid], b2 = s_best[tid + d];
+                    if (a == NONE32 || (b2 != NONE32 && cand_better<S>(ev, cb, b2, a))) s_best[tid] = b2;
+                }
+                __syncthreads();
+            }
+            unsigned long long bc = s_best[0];
+            // best over the cluster: every CTA folds the eight local winners in rank order with the same comparator
+            if (tid == 0) sm.xch[X.phase][0] = bc;
+            cl.sync();
+            uint32_t saved = NONE32;
+            for (unsigned r = 0; r < FCL_CS; ++r) {
+                const uint32_t c = (uint32_t)*cl.map_shared_rank(&sm.xch[X.phase][0], r);
+                if (c != NONE32 && (saved == NONE32 || cand_better<S>(ev, cb, c, saved))) saved = c;
+            }
+            X.phase ^= 1;
+            s_pos = nkeep; r_pos = mpos; n_next = nkeep + 1;
+            cl.sync();  // every CTA has read cand_agg[recycled] through cand_better before rank 0 rewrites it
+            if (rank == 0 && tid == 0) {
+                const unsigned long long rk = ev.cand_agg[cb + recycled];
+                if (key_value(mkey) >= key_value(rk)) ev.cand_agg[cb + recycled] = mkey;
+                ev.cand_inex[cb + recycled] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
+            }
+            for (int li = tid; li < Ublk; li += NT) if (stat[li] == 2) {
+                const uint32_t c = ev.ulist[cb + cta_off + li];
+                if (c == saved) { ev.pos_of[cb + c] = (uint32_t)s_pos; stat[li] = 1; ev.uflag[cb + c] = 2; }
+                else ev.pos_of[cb + c] = (uint32_t)r_pos;
+            }
+        } else {
+            n_next = nkeep + 1;
+            for (int li = tid; li < Ublk; li += NT) if (stat[li] == 2) ev.pos_of[cb + ev.ulist[cb + cta_off + li]] = (uint32_t)mpos;
+            if (rank == 0) {  // new merged node (clean.rs:832-849) written straight into the next layer
+                const int nbuf = t & 1;
+                const size_t nb = (size_t)k * ev.Wcap + mpos;
+                if (tid < S) ev.cur_state[nbuf][nb * S + tid] = sm.merged[16 + tid];
+                if (tid == 0) {
+                    ev.cur_val[nbuf][nb] = key_value(mkey);
+                    ev.cur_flag[nbuf][nb] = (uint8_t)(NF_INEXACT | NF_RELAXED);
+                    ev.plog[(lb + t) * ev.Wcap + mpos] = ((uint32_t)mkey & PLOG_CAND_MASK) | PLOG_INEXACT | PLOG_RELAXED;
+                }
+            }
+        }
+    }
+
+    // ---- F. terminal layer: best nodes (last maximum in canonical order) -------------------------------------------------------------
+    if (terminal) {
+        unsigned long long bb[2] = {0ull, 0ull};
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t c = ev.ulist[cb + off0 + i];
+            const unsigned long long kk = (ev.cand_agg[cb + c] & 0xFFFFFFFF00000000ull) | (unsigned)(ev.pos_of[cb + c] + 1);
+            bb[0] = max(bb[0], kk);
+            if (!(ev.cand_inex[cb + c] & (NF_INEXACT | NF_RELAXED))) bb[1] = max(bb[1], kk);
+        }
+        bb[0] = block_reduce(bb[0], [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        bb[1] = block_reduce(bb[1], [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+        X.allreduce(bb, 2, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+        if (rank == 0 && tid == 0) {
+            ctl->has_best = 1; ctl->best_value = key_value(bb[0]); ctl->best_pos = (int)(uint32_t)bb[0] - 1;
+            ctl->has_best_exact = bb[1] != 0;
+            if (bb[1]) { ctl->best_exact_value = key_value(bb[1]); ctl->best_exact_pos = (int)(uint32_t)bb[1] - 1; }
+        }
+    }
+    if (rank == 0 && tid == 0) {
+        ev.nlog[lb + t] = n_next;
+        ev.vlog[lb + t] = var;
+        ev.rslog[(lb + t) * 2] = s_pos; ev.rslog[(lb + t) * 2 + 1] = r_pos;
+        ctl->n_cur = n_next; ctl->var = var;
+        if (cut && ctl->lel < 0) { ctl->lel = t - 1; ctl->lel_pending = 1; }
+        if (terminal) { ctl->status = ST_TERMINAL; ctl->t_term = t; atomicSub(ev.active, 1); }
+    }
+}
+
+template <int S>
+__global__ void __cluster_dims__(FCL_CS, 1, 1) __launch_bounds__(FCL_NT) k_finish_cl(EV ev, int t, int kcap) {
+    __shared__ FinishClSmem sm;
+    __shared__ int s_last;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    cg::cluster_group cl = cg::this_cluster();
+    finish_body_cl<S>(ev, t, sm, reinterpret_cast<unsigned long long*>(dyn_smem), dyn_smem + (size_t)kcap * 8, kcap);
+    cl.sync();  // nobody leaves while a neighbour may still read its shared memory
+    if (cl.block_rank() != 0) return;
+    // ---- work plan of the two flat kernels that follow (as in k_finish): the last rank-0 CTA scans the per-DD tile counts ----------------
+    constexpr int G = S / 2, PER_TILE = 256 / G;
+    const int tid = threadIdx.x, count = gridDim.x / FCL_CS;
     __syncthreads();
     if (tid == 0) { __threadfence(); s_last = (atomicAdd(ev.finish_counter, 1u) == (unsigned)count - 1u); }
     __syncthreads();
