@@ -335,9 +335,9 @@ def main():
     ap.add_argument("--max-waves", type=int, default=0, help="max2sat: waves per step (default 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave
-        if args.wave == 2048: args.wave = 64
-        if args.batch_cap == 512: args.batch_cap = 64
+    if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave -- one DD per SM (m2_finish is one CTA per DD)
+        if args.wave == 2048: args.wave = 148
+        if args.batch_cap == 512: args.batch_cap = 148
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

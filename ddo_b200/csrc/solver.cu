@@ -15,9 +15,15 @@ static inline double now_ms() { return std::chrono::duration<double, std::milli>
 // NoDupFringe
 // ---------------------------------------------------------------------------------------------------------------
 uint64_t NoDupFringe::hash_state(const uint64_t* st, int W) {
-    uint64_t h = 0x9E3779B97F4A7C15ull;
-    for (int j = 0; j < W; ++j) { h ^= st[j] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xff51afd7ed558ccdULL; h ^= h >> 32; }
-    return h;
+    // four independent multiply-xor lanes (a MAX2SAT state is 250 words: one dependent chain would cost a multiply latency per word)
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+    int j = 0;
+    for (; j + 4 <= W; j += 4)
+        for (int q = 0; q < 4; ++q) { h[q] = (h[q] ^ st[j + q]) * 0xff51afd7ed558ccdULL; h[q] ^= h[q] >> 29; }
+    for (; j < W; ++j) { h[0] = (h[0] ^ st[j]) * 0xff51afd7ed558ccdULL; h[0] ^= h[0] >> 29; }
+    uint64_t x = h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7);
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 32;
+    return x;
 }
 // BitSet::cmp of bit-set 0.5.3 (lexicographic over ascending members), word-parallel
 static int lex_cmp(const uint64_t* a, const uint64_t* b, int W) {

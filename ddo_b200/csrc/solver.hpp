@@ -55,7 +55,7 @@ private:
         void init(int w) { W = w; per_block = std::max<size_t>(1, ((size_t)1 << 22) / (size_t)w); }
         uint64_t* at(size_t id) const { return blocks[id / per_block].get() + (id % per_block) * (size_t)W; }
         void grow() { if (count == blocks.size() * per_block) blocks.emplace_back(new uint64_t[per_block * (size_t)W]); ++count; }
-        void clear() { blocks.clear(); count = 0; }
+        void clear() { count = 0; }  // the blocks stay (no page faults when the next search refills them)
     } states_;
     std::vector<uint64_t> bits_;
     std::vector<Item> items_;
