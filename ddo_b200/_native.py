@@ -12,7 +12,7 @@ OK, CUTOFF = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5
 EXACT, RELAXED, RESTRICTED = 0, 1, 2
 LAST_EXACT_LAYER, FRONTIER = 1, 2
-WIDTH_FIXED, WIDTH_NB_UNASSIGNED = 0, 1
+WIDTH_FIXED, WIDTH_NB_UNASSIGNED, WIDTH_TIMES_NB_UNASSIGNED, WIDTH_DIVBY_NB_UNASSIGNED = 0, 1, 2, 3
 I64_MIN, I64_MAX = -(1 << 63), (1 << 63) - 1
 
 

@@ -88,6 +88,38 @@ class NbUnassignedWidth:  # width.rs:397-401
         return self.nb_vars - sp.depth
 
 
+class Times:  # width.rs:636-641
+    def __init__(self, k: int, inner):
+        self.k, self.inner = int(k), inner
+
+    def max_width(self, sp: SubProblem) -> int:
+        return max(1, self.k * self.inner.max_width(sp))
+
+
+class DivBy:  # width.rs:875-880
+    def __init__(self, k: int, inner):
+        self.k, self.inner = int(k), inner
+
+    def max_width(self, sp: SubProblem) -> int:
+        return max(1, self.inner.max_width(sp) // self.k)
+
+
+def _width_spec(width, nb_vars: int):
+    """(kind, parameter, largest width it can ask for) of a WidthHeuristic for the C ABI."""
+    if isinstance(width, FixedWidth):
+        return N.WIDTH_FIXED, width.w, width.w
+    if isinstance(width, NbUnassignedWidth):
+        return N.WIDTH_NB_UNASSIGNED, 0, nb_vars
+    if isinstance(width, (Times, DivBy)) and isinstance(width.inner, FixedWidth):  # a constant: fold it
+        w = width.max_width(SubProblem(None, 0))
+        return N.WIDTH_FIXED, w, w
+    if isinstance(width, Times) and isinstance(width.inner, NbUnassignedWidth):
+        return N.WIDTH_TIMES_NB_UNASSIGNED, width.k, width.k * nb_vars
+    if isinstance(width, DivBy) and isinstance(width.inner, NbUnassignedWidth):
+        return N.WIDTH_DIVBY_NB_UNASSIGNED, width.k, nb_vars
+    raise TypeError("unsupported WidthHeuristic: FixedWidth, NbUnassignedWidth, Times(k, .) and DivBy(k, .) of those are available")
+
+
 class Misp:
     """MISP as a device model: Problem + MispRelax + MispRanking of examples/misp/main.rs:37-209, resident in HBM."""
 
@@ -327,12 +359,8 @@ class ParNoCachingSolverLel:
     def __init__(self, problem: Misp, width, wave_size: int = 128, max_width_cap: Optional[int] = None, mdd: Optional[GpuMdd] = None,
                  batch_cap: Optional[int] = None):
         self.problem = problem
-        if isinstance(width, FixedWidth):
-            kind, w = N.WIDTH_FIXED, width.w
-            cap = max_width_cap or w
-        else:
-            kind, w = N.WIDTH_NB_UNASSIGNED, 0
-            cap = max_width_cap or problem.nb_variables()
+        kind, w, need = _width_spec(width, problem.nb_variables())
+        cap = max_width_cap or need
         self.mdd = mdd or GpuMdd(problem, cap, min(wave_size, batch_cap) if batch_cap else wave_size)
         h = C.c_void_p()
         N.check(N.lib().ddo_solver_create(problem.h, self.mdd.h, kind, w, wave_size, C.byref(h)), "ddo_solver_create")

@@ -176,7 +176,10 @@ int ddo_solver_create(const ddo_model* m, ddo_mdd* d, int32_t width_kind, uint64
     { int rr = d->ep->reserve_roots(wave_size); if (rr != DDO_OK) return rr; }  // the wave may exceed batch_cap: only DDs that need a cut go through the general engine, batch_cap at a time
     if (width_kind == DDO_WIDTH_FIXED && (width < 1 || width > (uint64_t)d->ep->Wcap)) { set_error("width must be in [1, max_width_cap]"); return DDO_ERR_INVALID; }
     if (m->kind != d->kind) { set_error("model and mdd are of different kinds"); return DDO_ERR_INVALID; }
-    if (width_kind == DDO_WIDTH_NB_UNASSIGNED && ddo_model_nb_variables(m) > d->ep->Wcap) { set_error("NbUnassignedWidth needs max_width_cap >= nb_variables"); return DDO_ERR_INVALID; }
+    if (width_kind < DDO_WIDTH_FIXED || width_kind > DDO_WIDTH_DIVBY_NB_UNASSIGNED) { set_error("unknown width heuristic"); return DDO_ERR_INVALID; }
+    if ((width_kind == DDO_WIDTH_NB_UNASSIGNED || width_kind == DDO_WIDTH_DIVBY_NB_UNASSIGNED) && ddo_model_nb_variables(m) > d->ep->Wcap) { set_error("NbUnassignedWidth needs max_width_cap >= nb_variables"); return DDO_ERR_INVALID; }
+    if (width_kind == DDO_WIDTH_TIMES_NB_UNASSIGNED && (width < 1 || width * (uint64_t)ddo_model_nb_variables(m) > (uint64_t)d->ep->Wcap)) { set_error("Times(k, NbUnassignedWidth) needs max_width_cap >= k * nb_variables"); return DDO_ERR_INVALID; }
+    if (width_kind == DDO_WIDTH_DIVBY_NB_UNASSIGNED && width < 1) { set_error("DivBy(k, ...) needs k >= 1"); return DDO_ERR_INVALID; }
     std::vector<uint64_t> rs((size_t)ddo_model_state_words(m));
     int64_t rv = 0;
     ddo_model_initial_state(m, rs.data(), &rv);

@@ -256,7 +256,13 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     std::vector<int64_t> values(cnt);
     std::vector<int32_t> depths(cnt);
     for (int i = 0; i < cnt; ++i) {
-        widths[i] = width_kind == DDO_WIDTH_FIXED ? width : (uint64_t)(n_vars - w_items[i].depth);  // width.rs:166-170,397-401 (path.len() == depth)
+        const uint64_t unassigned = (uint64_t)(n_vars - w_items[i].depth);  // NbUnassignedWidth, width.rs:397-401 (path.len() == depth)
+        switch (width_kind) {
+            case DDO_WIDTH_FIXED: widths[i] = width; break;                                                            // width.rs:166-170
+            case DDO_WIDTH_TIMES_NB_UNASSIGNED: widths[i] = std::max<uint64_t>(1, width * unassigned); break;            // width.rs:636-641
+            case DDO_WIDTH_DIVBY_NB_UNASSIGNED: widths[i] = std::max<uint64_t>(1, unassigned / std::max<uint64_t>(width, 1)); break;  // width.rs:875-880
+            default: widths[i] = unassigned; break;
+        }
         values[i] = w_items[i].value; depths[i] = w_items[i].depth;
     }
     struct Res { bool exact = false, has = false; int32_t best = 0; };

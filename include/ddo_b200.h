@@ -44,6 +44,8 @@ extern "C" {
 
 #define DDO_WIDTH_FIXED 0
 #define DDO_WIDTH_NB_UNASSIGNED 1
+#define DDO_WIDTH_TIMES_NB_UNASSIGNED 2   /* Times(width, NbUnassignedWidth(n)), src/implementation/heuristics/width.rs:636-641: max(1, width * (n - depth)) */
+#define DDO_WIDTH_DIVBY_NB_UNASSIGNED 3   /* DivBy(width, NbUnassignedWidth(n)), width.rs:875-880: max(1, (n - depth) / width) */
 
 typedef struct ddo_model ddo_model;   /* an immutable problem instance resident in HBM (Problem + Relaxation + StateRanking) */
 typedef struct ddo_mdd ddo_mdd;       /* D::default(): one reusable batch of DD workspaces on one GPU (parallel.rs:580)   */

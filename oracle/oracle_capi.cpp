@@ -153,8 +153,11 @@ template <class H>
 int32_t solve(H* h, int32_t mode, int32_t k, int32_t width_kind, uint64_t width, int32_t cutset_type, double time_budget_s, uint64_t max_waves,
               oracle_solve_result* out, int32_t* sol_vars, int32_t* sol_vals, int32_t* sol_len, int64_t* trace, int32_t trace_cap, int32_t* trace_len) {
     using S = typename H::State; using HS = typename H::Hash; using EQ = typename H::Eq;
+    // width_kind: 0 FixedWidth(width), 1 NbUnassignedWidth, 2 Times(width, NbUnassignedWidth), 3 DivBy(width, NbUnassignedWidth)  (width.rs)
     FixedWidth<S> fw((size_t)width); NbUnassignedWidth<S> nw(h->pb.nb_variables());
-    const WidthHeuristic<S>* wh = width_kind == 0 ? (const WidthHeuristic<S>*)&fw : (const WidthHeuristic<S>*)&nw;
+    Times<S> tw((size_t)width, &nw); DivBy<S> dw((size_t)std::max<uint64_t>(width, 1), &nw);
+    const WidthHeuristic<S>* wh = width_kind == 0 ? (const WidthHeuristic<S>*)&fw : width_kind == 2 ? (const WidthHeuristic<S>*)&tw
+                                  : width_kind == 3 ? (const WidthHeuristic<S>*)&dw : (const WidthHeuristic<S>*)&nw;
     NoCutoff nocut; std::unique_ptr<TimeBudget> tb;
     const Cutoff* cut = &nocut;
     if (time_budget_s > 0) { tb.reset(new TimeBudget(time_budget_s)); cut = tb.get(); }

@@ -191,15 +191,17 @@ class OracleMisp(_OracleModel):
     def initial_value(self):
         return 0
 
-    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0):
-        """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (the reference CLI default, misp/main.rs:322-328)."""
+    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0, width_kind=None):
+        """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (the reference CLI default, misp/main.rs:322-328);
+        width_kind 2 / 3: Times(width, NbUnassignedWidth) / DivBy(width, NbUnassignedWidth)."""
         m = {"sequential": 0, "wave": 1, "parallel": 2}[mode]
+        wk = width_kind if width_kind is not None else (0 if width is not None else 1)
         res = SolveResult()
         sol = np.zeros(self.inst.n, dtype=np.int32)
         sl = C.c_int32(0)
         trace = np.zeros((max(trace_cap, 1), 4), dtype=np.int64)
         tl = C.c_int32(0)
-        lib().oracle_misp_solve(self.h, m, k, 0 if width is not None else 1, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
+        lib().oracle_misp_solve(self.h, m, k, wk, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
                                 _p(sol), C.byref(sl), _p(trace) if trace_cap else None, trace_cap, C.byref(tl))
         out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
         out["solution"] = sorted(sol[: sl.value].tolist())
@@ -246,16 +248,17 @@ class OracleM2s(_OracleModel):
         lib().oracle_m2s_transition(self.h, _p(sub), depth, var, value, _p(out), C.byref(cost), C.byref(rank), C.byref(rub))
         return out, int(cost.value), int(rank.value), int(rub.value)
 
-    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0):
+    def solve(self, mode="sequential", k=1, width=None, cutset_type=LEL, time_budget_s=0.0, max_waves=0, trace_cap=0, width_kind=None):
         """mode: sequential | wave | parallel.  width None -> NbUnassignedWidth (max2sat/main.rs:87-93)."""
         m = {"sequential": 0, "wave": 1, "parallel": 2}[mode]
+        wk = width_kind if width_kind is not None else (0 if width is not None else 1)
         res = SolveResult()
         sv = np.zeros(self.inst.n + 1, dtype=np.int32)
         sx = np.zeros(self.inst.n + 1, dtype=np.int32)
         sl = C.c_int32(0)
         trace = np.zeros((max(trace_cap, 1), 4), dtype=np.int64)
         tl = C.c_int32(0)
-        lib().oracle_m2s_solve(self.h, m, k, 0 if width is not None else 1, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
+        lib().oracle_m2s_solve(self.h, m, k, wk, width or 0, cutset_type, time_budget_s, max_waves, C.byref(res),
                                _p(sv), _p(sx), C.byref(sl), _p(trace) if trace_cap else None, trace_cap, C.byref(tl))
         out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
         out["solution"] = list(zip(sv[: sl.value].tolist(), sx[: sl.value].tolist()))

@@ -182,3 +182,17 @@ def test_full_size_properties_batch():
     single = [mdd.compile(CompilationType.Relaxed, W, sp) for sp in cs[:3]]
     for i, c in enumerate(single):
         assert (c.best_value, c.expanded, c.cutset_size) == (rel[i].best_value, rel[i].expanded, rel[i].cutset_size)
+
+
+def test_solver_times_and_divby_width_heuristics_match_oracle():
+    """Times(k, NbUnassignedWidth) / DivBy(k, NbUnassignedWidth) (heuristics/width.rs:636-641,875-880) evaluated per sub-problem on the host."""
+    from ddo_b200 import DivBy, Times
+
+    inst = gnp(90, 0.3, 41)
+    for wh, kind, k in ((Times(2, NbUnassignedWidth(inst.n)), 2, 2), (DivBy(4, NbUnassignedWidth(inst.n)), 3, 4)):
+        s = ParNoCachingSolverLel(Misp(inst), wh, wave_size=16)
+        comp = s.maximize()
+        ref = O.OracleMisp(inst).solve("wave", k=16, width=k, width_kind=kind)
+        assert comp.is_exact and comp.best_value == ref["best_value"]
+        assert (s.explored(), int(s.stats()["expanded"])) == (ref["explored"], ref["expanded"])
+    assert Times(3, FixedWidth(5)).max_width(SubProblem(None, 0)) == 15 and DivBy(10, FixedWidth(5)).max_width(SubProblem(None, 0)) == 1
