@@ -115,6 +115,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
         finish_cl_smem = (size_t)finish_cl_kcap * 9 + 16;
         if (finish_cl_smem > 200 * 1024) finish_cl_max = 0;  // slices of very wide layers do not fit shared memory: one-CTA finish with global keys
         if (const char* e = getenv("DDO_FINISH_CL_MAX")) finish_cl_max = std::min(finish_cl_max > 0 ? 1 << 20 : 0, atoi(e));
+        if (const char* e = getenv("DDO_EXPAND1_MIN")) expand1_min = atoi(e);
     }
     // keys (8 B) + status (1 B) of up to C distinct candidates: shared memory when they fit next to the 19 KB of static smem
     finish_smem = (size_t)C * 9 + 16;
@@ -231,6 +232,14 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         CUDA_TRY(cudaFuncSetAttribute(k_finish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_smem));
         E->finish_attr_set = true;
     }
+    // wide batches: one thread per node (k_expand1); narrow ones keep G lanes per node (more CTAs in flight for a handful of tiles)
+    const bool use_e1 = slots >= E->expand1_min;
+    const size_t e1_smem = (size_t)512 * G * 16;
+    const int e1_grid = E->num_sms * 3;
+    if (use_e1 && !E->expand1_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_expand1<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e1_smem));
+        E->expand1_attr_set = true;
+    }
     const bool use_cl = slots <= E->finish_cl_max;
     if (use_cl && !E->finish_cl_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_finish_cl<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_cl_smem));
@@ -250,7 +259,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         E->prof_mark(1);
         k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(2);
-        k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
+        if (use_e1) k_expand1<S><<<e1_grid, 256, e1_smem, st>>>(ev, t, slots);
+        else k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(0);
         g_kernel_launches += 3; ++E->layer_steps;
         if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {

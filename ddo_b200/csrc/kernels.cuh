@@ -355,6 +355,217 @@ __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, i
 
 
 // =================================================================================================================
+// k_expand1: the same layer expansion with ONE THREAD per node (the whole S-word state in registers), for wide batches.  With G lanes
+// per node (k_expand) every warp instruction serves 32/G nodes and the group reductions (rough upper bound, hash, popcount, equality)
+// are shuffles; here a warp instruction serves 32 nodes and those reductions are plain register arithmetic: ~4x fewer warp instructions
+// per node.  A CTA handles up to G consecutive tiles of the work plan (256 nodes) of ONE DD at a time; the claimed rows are staged in
+// shared memory, compacted through a bit mask, and bit-transposed into the per-vertex histogram exactly as in k_expand.
+// =================================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256, 3) k_expand1(EV ev, int t, int count) {
+    constexpr int G = S / 2;                 // 128-bit chunks per state
+    constexpr int PLAN = 256 / G;            // nodes per tile of the work plan (written by k_finish for k_expand's geometry)
+    constexpr int RP = G >= 8 ? 1 : 8 / G;   // bank swizzle of the staged rows, as in k_expand
+    extern __shared__ __align__(16) uint4 s_claim[];   // [512 row slots][G]: slot = d * 256 + thread
+    __shared__ unsigned int s_hist[64 * S];
+    __shared__ unsigned int s_mask[16], s_pref[17];     // claimed row slots (bit mask) and the exclusive prefix of its popcounts
+    __shared__ unsigned short s_rowmap[512];            // r-th claimed row -> slot
+    __shared__ __align__(16) unsigned int s_tilectr[4];
+    __shared__ __align__(16) unsigned int s_claimbox[4];
+    unsigned int& s_exp = s_tilectr[0]; unsigned int& s_tr = s_tilectr[1]; unsigned int& s_claims = s_claimbox[0];
+    const int* off = ev.tile_off_e;
+    const int total = off[count];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tpb = (total + gridDim.x - 1) / gridDim.x;
+    const int tile_lo = min((int)blockIdx.x * tpb, total), tile_hi = min(tile_lo + tpb, total);
+    for (int i = tid; i < 64 * S; i += 256) s_hist[i] = 0;
+    if (tid == 0) s_claims = 0;
+    int hist_k = -1;
+    int k = tile_lo < tile_hi ? plan_find(off, count, tile_lo) : 0;
+    const int buf = t & 1;
+    for (int tile = tile_lo; tile < tile_hi;) {
+        while (off[k + 1] <= tile) ++k;
+        const int ntiles = min(G, min(off[k + 1], tile_hi) - tile);  // consecutive plan tiles of this DD taken together
+        if (k != hist_k) {
+            __syncthreads();
+            if (hist_k >= 0) {
+                for (int i = tid; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) { atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); s_hist[i] = 0; } }
+                if (tid == 0 && s_claims) { atomicAdd(ev.ucount + hist_k, s_claims); s_claims = 0; }
+            }
+            hist_k = k;
+        }
+        DDCtl* ctl = ev.ctl + k;
+        const int n_cur = ctl->n_cur;
+        const int node = (tile - off[k]) * PLAN + tid;
+        const bool active = tid < ntiles * PLAN && node < n_cur;
+        __syncthreads();
+        if (tid < 16) s_mask[tid] = 0;
+        if (tid == 0) { s_exp = 0; s_tr = 0; }
+        __syncthreads();
+        bool claimed0 = false, claimed1 = false;
+        {
+            const int v = ctl->var;
+            const int vw = v >> 6;
+            const uint64_t bit = 1ull << (v & 63);
+            const size_t cb = (size_t)k * ev.C;
+            uint64_t w[S];
+            int val = 0; uint32_t fl = 0;
+            bool expandable = false, has_v = false;
+            if (active) {
+                const size_t nb = (size_t)k * ev.Wcap + node;
+                const uint4* src = reinterpret_cast<const uint4*>(ev.cur_state[buf] + nb * S);
+#pragma unroll
+                for (int q = 0; q < G; ++q) { const uint4 x = ld_stream_u4(src + q); w[2 * q] = u4lo(x); w[2 * q + 1] = u4hi(x); }
+                val = ev.cur_val[buf][nb];
+                fl = ev.cur_flag[buf][nb];
+                int rub = 0;
+                if (ev.unit_weights) {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) rub += __popcll(w[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) { uint64_t x = w[j]; const int32_t* wp = ev.weight + j * 64; while (x) { const int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; } }
+                }
+                expandable = ((long long)rub + (long long)val) > ctl->best_lb;  // clean.rs:364-365
+#pragma unroll
+                for (int j = 0; j < S; ++j) if (j == vw && (w[j] & bit)) has_v = true;  // misp/main.rs:96
+                ev.cur_rub[nb] = rub;
+                *reinterpret_cast<uint2*>(ev.cand_rep + cb + 2u * node) = make_uint2(NONE32, NONE32);
+                *reinterpret_cast<uchar2*>(ev.uflag + cb + 2u * node) = make_uchar2(0, 0);
+            }
+            {   // counters, warp-aggregated
+                const unsigned me = __ballot_sync(FULL_MASK, expandable), mv = __ballot_sync(FULL_MASK, expandable && has_v);
+                if (lane == 0 && me) { atomicAdd(&s_exp, (unsigned)__popc(me)); atomicAdd(&s_tr, (unsigned)(__popc(me) + __popc(mv))); }
+            }
+            if (expandable) {
+                const uint32_t c_yes = 2u * node, c_no = 2u * node + 1u;  // for_each_in_domain order: YES then NO (main.rs:95-102)
+#pragma unroll
+                for (int j = 0; j < S; ++j) if (j == vw) w[j] &= ~bit;  // res.remove(var), main.rs:79
+                const uint4* ncrow = reinterpret_cast<const uint4*>(ev.nc + (size_t)v * S);
+                uint64_t hsh[2]; int vals[2];
+                // both children are written first, ONE fence publishes their rows, then both are inserted
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    if (d == 0 && !has_v) continue;
+                    const uint32_t c = d == 0 ? c_yes : c_no;
+                    uint4* dst = reinterpret_cast<uint4*>(ev.cand_state + (cb + c) * S);
+                    uint64_t hs = 0; int pc = 0; uint64_t first_word = 0;
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        uint64_t a0 = w[2 * q], a1 = w[2 * q + 1];
+                        if (d == 0) { const uint4 n4 = __ldg(ncrow + q); a0 &= u4lo(n4); a1 &= u4hi(n4); }  // main.rs:82
+                        st_stream_u4(dst + q, mk_u4(a0, a1));
+                        hs += a0 * hash_mul(2 * q) + a1 * hash_mul(2 * q + 1);
+                        pc += __popcll(a0) + __popcll(a1);
+                        if (q == 0) first_word = a0;
+                    }
+                    const int value = d == 0 ? val + ev.weight[v] : val;  // main.rs:87-93
+                    hsh[d] = mix64(hs); vals[d] = value;
+                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(first_word) >> 44);
+                    ev.cand_agg[cb + c] = pack_key(value, c);
+                    ev.cand_first[cb + c] = c;
+                    ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
+                }
+                __threadfence();
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    if (d == 0 && !has_v) continue;
+                    const uint32_t c = d == 0 ? c_yes : c_no;
+                    const uint64_t h = hsh[d];
+                    const int value = vals[d];
+                    const uint32_t tag = (uint32_t)(h >> 32);
+                    const unsigned long long entry = ((unsigned long long)tag << 32) | c;
+                    uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+                    unsigned long long* tab = ev.table + (size_t)k * ev.T;
+                    for (;;) {
+                        const unsigned long long old = atomicCAS(tab + slot, EMPTY64, entry);
+                        if (old == EMPTY64) {  // Entry::Vacant: a new distinct state of the next layer
+                            ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot;
+                            if (d == 0) claimed0 = true; else claimed1 = true;
+                            break;
+                        }
+                        if ((uint32_t)(old >> 32) == tag) {
+                            const uint32_t oc = (uint32_t)old;
+                            const uint4* orow = reinterpret_cast<const uint4*>(ev.cand_state + (cb + oc) * S);
+                            bool eq = true;
+#pragma unroll
+                            for (int q = 0; q < G; ++q) {
+                                uint64_t a0 = w[2 * q], a1 = w[2 * q + 1];
+                                if (d == 0) { const uint4 n4 = __ldg(ncrow + q); a0 &= u4lo(n4); a1 &= u4hi(n4); }
+                                const uint4 o4 = ld_cg_u4(orow + q);
+                                eq = eq && u4lo(o4) == a0 && u4hi(o4) == a1;
+                            }
+                            if (eq) {  // Entry::Occupied, clean.rs:766-774 + append_edge_to! :199-220
+                                atomicMax(ev.cand_agg + cb + oc, pack_key(value, c));
+                                atomicMin(ev.cand_first + cb + oc, c);
+                                if (fl & NF_INEXACT) ev.cand_inex[cb + oc] = 1;
+                                ev.cand_rep[cb + c] = oc;
+                                break;
+                            }
+                        }
+                        slot = (slot + 1) & (uint32_t)(ev.T - 1);
+                    }
+                }
+                // stage the claimed rows for the vertex histogram
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    if (!(d == 0 ? claimed0 : claimed1)) continue;
+                    const int row = d * 256 + tid;
+                    atomicOr(&s_mask[row >> 5], 1u << (row & 31));
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        uint64_t a0 = w[2 * q], a1 = w[2 * q + 1];
+                        if (d == 0) { const uint4 n4 = __ldg(ncrow + q); a0 &= u4lo(n4); a1 &= u4hi(n4); }
+                        s_claim[row * G + (q ^ ((row / RP) & (G - 1)))] = mk_u4(a0, a1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && s_exp) { atomicAdd(&ctl->expanded, (unsigned long long)s_exp); atomicAdd(&ctl->transitions, (unsigned long long)s_tr); }
+        if (warp == 0) {  // exclusive prefix of the mask popcounts
+            const unsigned p = lane < 16 ? (unsigned)__popc(s_mask[lane]) : 0u;
+            unsigned inc = p;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned n = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += n; }
+            if (lane < 16) s_pref[lane] = inc - p;
+            if (lane == 15) s_pref[16] = inc;
+        }
+        __syncthreads();
+        const int nrows = (int)s_pref[16];
+        if (nrows > 0) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) if (d == 0 ? claimed0 : claimed1) {
+                const int row = d * 256 + tid;
+                const unsigned r = s_pref[row >> 5] + (unsigned)__popc(s_mask[row >> 5] & ((1u << (row & 31)) - 1u));
+                s_rowmap[r] = (unsigned short)row;
+            }
+            if (tid == 0) s_claims += (unsigned)nrows;
+            __syncthreads();
+            const int nblk = (nrows + 31) >> 5;
+            for (int job = warp; job < nblk * G; job += 8) {
+                const int rblk = job / G, q = job % G;
+                const int ri = rblk * 32 + lane;
+                uint4 x4 = make_uint4(0, 0, 0, 0);
+                if (ri < nrows) { const int row = s_rowmap[ri]; x4 = s_claim[row * G + (q ^ ((row / RP) & (G - 1)))]; }
+                const uint32_t xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned cnt = __popc(warp_transpose32(xs[e]));
+                    if (cnt) atomicAdd(&s_hist[32 * (4 * q + e) + lane], cnt);
+                }
+            }
+        }
+        tile += ntiles;
+    }
+    __syncthreads();
+    if (hist_k >= 0) {
+        for (int i = tid; i < 64 * S; i += 256) { const unsigned v = s_hist[i]; if (v) atomicAdd(ev.vhist + (size_t)hist_k * ev.HN + i, v); }
+        if (tid == 0 && s_claims) atomicAdd(ev.ucount + hist_k, s_claims);
+    }
+}
+
+// =================================================================================================================
 // k_finish: one CTA per DD.  Decides everything about layer t (whose candidates were produced by k_expand(t-1)).
 // =================================================================================================================
 struct FinishSmem {
