@@ -232,7 +232,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         CUDA_TRY(cudaFuncSetAttribute(k_finish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_smem));
         E->finish_attr_set = true;
     }
-    // wide batches: one thread per node (k_expand1); narrow ones keep G lanes per node (more CTAs in flight for a handful of tiles)
+    // one thread per node (k_expand1) measured faster than G lanes per node (k_expand) at every batch size; DDO_EXPAND1_MIN=<slots>
+    // brings the lane-group kernel back for batches below that size (A/B runs)
     const bool use_e1 = slots >= E->expand1_min;
     const size_t e1_smem = (size_t)512 * G * 16;
     const int e1_grid = E->num_sms * 3;
