@@ -589,6 +589,27 @@ __device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
     return false;
 }
 
+// Tie-break keys of the width cut beyond (value_top, popcount, 20 lexicographic bits).  BitSet::cmp orders two sets of EQUAL size by their
+// ascending member lists: at the first difference the set owning the smaller vertex is Less.  So chunk j >= 1 of the radix-select key packs
+// the members of rank MK*(j-1) .. MK*j-1 of the state, BK bits each, most significant first: dense information (a raw 64-bit word of a
+// late, sparse state holds a member or two, and a digit over 8 such vertices splits a tied group by ~20 % -- twenty-odd passes; a digit
+// over member indices splits it 256-fold).  Sets of equal size pad identically, so the padding value never decides.
+template <int S> struct MemberKey { static constexpr int BK = S <= 8 ? 9 : 10, MK = S <= 8 ? 7 : 6, CHUNKS = (64 * S + MK - 1) / MK; };
+template <int S>
+__device__ unsigned long long member_key(const uint64_t* st, int first_rank) {
+    constexpr int BK = MemberKey<S>::BK, MK = MemberKey<S>::MK;
+    unsigned long long key = 0; int got = 0, skip = first_rank;
+    for (int j = 0; j < S && got < MK; ++j) {
+        uint64_t w = st[j];
+        const int pc = __popcll(w);
+        if (skip >= pc) { skip -= pc; continue; }
+        while (skip > 0) { w &= w - 1; --skip; }
+        while (w && got < MK) { key = (key << BK) | (unsigned long long)(j * 64 + __ffsll((long long)w) - 1); ++got; w &= w - 1; }
+    }
+    for (; got < MK; ++got) key = (key << BK) | ((1ull << BK) - 1ull);
+    return key;
+}
+
 // Keys / status of the distinct candidates live in shared memory when 2*Wcap of them fit (ev.smem_keys), else in global scratch.
 template <int S>
 __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long long* keys, uint8_t* stat) {
@@ -744,12 +765,13 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
         int nactive = U;
         bool done = false;
         if (need == 0) { for (int ui = tid; ui < U; ui += NT) stat[ui] = 2; done = true; }
-        for (int chunk = 0; chunk <= S && !done; ++chunk) {
-            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j: lexicographic word j-1 of the state
-            auto key_of = [&](int ui) -> unsigned long long {
-                if (chunk == 0) return keys[ui];
-                return lex_word(ev.cand_state[(cb + ev.ulist[cb + ui]) * S + (chunk - 1)]);
-            };
+        for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
+            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j >= 1: the next MK members of the state (member_key)
+            if (chunk > 0) {
+                for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) keys[ui] = member_key<S>(ev.cand_state + (cb + ev.ulist[cb + ui]) * S, MemberKey<S>::MK * (chunk - 1));
+                __syncthreads();
+            }
+            auto key_of = [&](int ui) -> unsigned long long { return keys[ui]; };
             unsigned long long kor = 0, kand = ~0ull;
             for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) { unsigned long long x = key_of(ui); kor |= x; kand &= x; }
             kor = block_reduce(kor, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
@@ -1171,11 +1193,12 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
     if (cut) {
         bool done = false;
         if (need == 0) { for (int li = tid; li < Ublk; li += NT) stat[li] = 2; done = true; }
-        for (int chunk = 0; chunk <= S && !done; ++chunk) {
-            auto key_of = [&](int li) -> unsigned long long {
-                if (chunk == 0) return keys[li];
-                return lex_word(ev.cand_state[(cb + ev.ulist[cb + cta_off + li]) * S + (chunk - 1)]);
-            };
+        for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
+            if (chunk > 0) {  // the next MK members of every still undecided state (member_key)
+                for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) keys[li] = member_key<S>(ev.cand_state + (cb + ev.ulist[cb + cta_off + li]) * S, MemberKey<S>::MK * (chunk - 1));
+                __syncthreads();
+            }
+            auto key_of = [&](int li) -> unsigned long long { return keys[li]; };
             unsigned long long kk[2] = {0ull, 0ull};  // OR of the undecided keys, OR of their complements (AND = ~kk[1]; one fold serves both)
             for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) { unsigned long long x = key_of(li); kk[0] |= x; kk[1] |= ~x; }
             kk[0] = block_reduce(kk[0], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, sm.red64);
