@@ -337,6 +337,18 @@ static int launch_small(Engine* E, int count, int64_t best_lb) {
 }
 
 int Engine::compile_small(int count, int64_t best_lb, float* device_ms) {
+    const int rc = compile_small_launch(count, best_lb);
+    if (rc != DDO_OK) return rc;
+    return compile_small_wait(device_ms);
+}
+int Engine::compile_small_wait(float* device_ms) {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
+    return DDO_OK;
+}
+// launch + result copy are only enqueued: the host may prepare the next wave while the device works (Solver::wave)
+int Engine::compile_small_launch(int count, int64_t best_lb) {
     if (count < 1 || count > root_cap || count > staged) { set_error("compile_small: batch not staged"); return DDO_ERR_INVALID; }
     if (small_ws <= 0) { set_error("small path disabled"); return DDO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
@@ -352,9 +364,6 @@ int Engine::compile_small(int count, int64_t best_lb, float* device_ms) {
     if (rc != DDO_OK) return rc;
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaMemcpyAsync(h_small, d_small, (size_t)count * sizeof(SmallOut), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
-    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     return DDO_OK;
 }
 

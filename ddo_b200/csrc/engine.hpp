@@ -159,6 +159,8 @@ struct Engine {
     // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
     int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;
     int compile_small(int count, int64_t best_lb, float* device_ms);
+    int compile_small_launch(int count, int64_t best_lb);
+    int compile_small_wait(float* device_ms);
     int fetch_vars(int index, std::vector<int32_t>& vars);
 };
 

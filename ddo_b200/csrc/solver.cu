@@ -210,7 +210,7 @@ Solver::Solver(Engine* e, int kind, const uint64_t* rs, int64_t rv, int wk, uint
 }
 
 int Solver::init(bool push_root) {  // parallel.rs:368-385
-    fringe.clear(); recs.clear();
+    fringe.clear(); recs.clear(); pre_valid = false; pre_items.clear();
     best_lb = INT64_MIN; best_ub = INT64_MAX; has_sol = false; best_sol.clear(); aborted = false;
     explored = expanded = transitions = compilations = waves = 0; device_ms = fringe_ms = 0;
     if (push_root) {
@@ -234,6 +234,19 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const double tr_wave0 = t0;
     int64_t top_ub = INT64_MIN;
     w_states.clear(); w_bits.clear(); w_items.clear();
+    if (pre_valid) {  // the nodes popped ahead of time, re-checked against the current incumbent in pop order
+        pre_valid = false;
+        for (size_t i = 0; i < pre_items.size(); ++i) {
+            const NoDupFringe::Item it = pre_items[i];
+            const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
+            if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
+            if (w_items.empty()) top_ub = ub;
+            w_states.insert(w_states.end(), &pre_states[i * W], &pre_states[i * W] + W);
+            w_bits.insert(w_bits.end(), &pre_bits[i * PWN], &pre_bits[i * PWN] + PWN);
+            w_items.push_back(it);
+            ++explored;
+        }
+    } else
     while ((int)w_items.size() < wave_size && !fringe.empty()) {
         const int id = fringe.pop();
         const NoDupFringe::Item it = fringe.item(id);
@@ -330,7 +343,10 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     if (eng->small_ws > 0) {
         rc = eng->stage_roots(cnt, widths.data(), w_states.data(), values.data(), depths.data());
         if (rc != DDO_OK) return rc;
-        rc = eng->compile_small(cnt, lb0, &ms);
+        rc = eng->compile_small_launch(cnt, lb0);
+        if (rc != DDO_OK) return rc;
+        if (pipeline) { const double tp = now_ms(); prepop(); fringe_ms += now_ms() - tp; }  // overlaps the device
+        rc = eng->compile_small_wait(&ms);
         if (rc != DDO_OK) return rc;
         device_ms += ms; tr_small += ms;
         for (int i = 0; i < cnt; ++i) {
@@ -341,6 +357,11 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
     } else {
         for (int i = 0; i < cnt; ++i) ov.push_back(i);
+    }
+    if (pre_valid) {  // keep the speculation only if this wave cannot change the fringe or the incumbent
+        bool keep = ov.empty();
+        for (int i = 0; i < cnt && keep; ++i) if (res[i].has && (int64_t)res[i].best > best_lb) keep = false;
+        if (!keep) { const double tp = now_ms(); unpop(); fringe_ms += now_ms() - tp; }
     }
     // ---- 1b. restriction with the general engine (parallel.rs:396-423) --------------------------------------------------------------
     // Dual mode: the relaxed twin of a restricted DD forks on the device at the first width cut and advances in the same launches, so an
@@ -508,8 +529,31 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         std::fprintf(trace_file, "%llu %d %zu %zu %.3f %.3f %llu %llu %zu %.3f %.3f\n", (unsigned long long)waves, cnt, ov.size(), open.size(), tr_small, tr_general,
                      (unsigned long long)(eng->layer_steps - tr_steps0), (unsigned long long)(expanded - tr_exp0), fringe.len(), tr_pop, now_ms() - tr_wave0);
     out3[0] = best_lb;
-    out3[2] = fringe.empty() ? 0 : 1;
+    out3[2] = (fringe.empty() && !pre_valid) ? 0 : 1;
     return DDO_OK;
+}
+
+void Solver::prepop() {
+    const int W = words, PWN = (n_vars + 63) / 64;
+    pre_states.clear(); pre_bits.clear(); pre_items.clear();
+    while ((int)pre_items.size() < wave_size && !fringe.empty()) {
+        const int id = fringe.pop();
+        const NoDupFringe::Item it = fringe.item(id);
+        const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
+        if (ub <= best_lb) { fringe.clear(); break; }  // nothing left can improve on the incumbent (it only grows): safe ahead of time too
+        pre_states.insert(pre_states.end(), fringe.state(id), fringe.state(id) + W);
+        pre_bits.insert(pre_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
+        pre_items.push_back(it);
+    }
+    pre_valid = !pre_items.empty();
+}
+void Solver::unpop() {
+    const int W = words, PWN = (n_vars + 63) / 64;
+    for (size_t i = 0; i < pre_items.size(); ++i) {
+        const NoDupFringe::Item& it = pre_items[i];
+        fringe.push(&pre_states[i * W], it.value, it.ub, it.depth, it.rec, &pre_bits[i * PWN], PWN);
+    }
+    pre_items.clear(); pre_valid = false;
 }
 
 void Solver::finish() { if (fringe.empty() && !aborted) best_ub = best_lb; }  // parallel.rs:512-515
@@ -519,14 +563,16 @@ int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact
     if (rc != DDO_OK) return rc;
     const double t_end = time_budget_s > 0 ? now_ms() + time_budget_s * 1000.0 : 0;
     volatile int32_t cutoff = 0;
+    pipeline = true; pre_valid = false;
     for (;;) {
-        if (fringe.empty()) break;
+        if (fringe.empty() && !pre_valid) break;
         if ((max_waves && waves >= max_waves) || (t_end > 0 && now_ms() >= t_end)) { aborted = true; break; }  // TimeBudget, cutoff.rs:302-323
         int64_t o3[3];
         rc = wave(&cutoff, o3);
         if (rc == DDO_CUTOFF) { aborted = true; break; }
         if (rc != DDO_OK) return rc;
     }
+    pipeline = false; pre_valid = false;
     if (aborted) fringe.clear();  // abort_search, parallel.rs:479-489
     else best_ub = best_lb;
     std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });  // parallel.rs:605

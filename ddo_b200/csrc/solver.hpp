@@ -91,6 +91,12 @@ struct Solver {
     uint64_t explored = 0, expanded = 0, transitions = 0, compilations = 0, waves = 0;
     double device_ms = 0, fringe_ms = 0;
     FILE* trace_file = nullptr;  // DDO_WAVE_TRACE=<path>: one line per wave (wave, popped, general DDs, inexact, small ms, general ms, layer steps, expanded, fringe)
+    // Speculative pre-pop (maximize() only): while the device compiles the fast-path DDs of a wave, the host pops the nodes of the NEXT wave.
+    // If the wave turns out to push nothing and leaves best_lb alone (the common case: every DD of the fast path is exact), those are exactly
+    // the nodes the next wave would pop; otherwise they are pushed back before anything else happens.
+    bool pipeline = false, pre_valid = false;
+    std::vector<uint64_t> pre_states, pre_bits; std::vector<NoDupFringe::Item> pre_items;
+    void prepop(); void unpop();
     // scratch of one wave (kept to avoid reallocations)
     std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars;
 
