@@ -133,6 +133,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
+    if (const char* e = getenv("DDO_SMALL_WS_FIRST")) { int v = atoi(e); if (v == 0 || v == 32 || v == 64 || v == 128) small_ws_first = v; }
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
     CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
     { int rr = reserve_roots(K); if (rr != DDO_OK) return rr; }
@@ -321,11 +322,12 @@ int Engine::compile_dual(int half, int64_t best_lb, const volatile int32_t* cuto
 }
 
 template <int S>
-static int launch_small(Engine* E, int count, int64_t best_lb) {
-    const int Ws = E->small_ws, G = S / 2;
-    const size_t smem = (size_t)Ws * G * 16 * 3 + (size_t)Ws * 4 * 3 + (size_t)4 * Ws * 4 + (size_t)64 * S * 4 + (size_t)2 * Ws;
+static int launch_small(Engine* E, int count, int64_t best_lb, int Ws) {
+    const int G = S / 2;
+    auto smem_of = [&](int ws) { return (size_t)ws * G * 16 * 3 + (size_t)ws * 4 * 3 + (size_t)4 * ws * 4 + (size_t)64 * S * 4 + (size_t)2 * ws; };
+    const size_t smem = smem_of(Ws);
     if (!E->small_attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_small<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_small<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(E->small_ws)));
         E->small_attr_set = true;
     }
     E->prof_mark(-1);
@@ -348,17 +350,18 @@ int Engine::compile_small_wait(float* device_ms) {
     return DDO_OK;
 }
 // launch + result copy are only enqueued: the host may prepare the next wave while the device works (Solver::wave)
-int Engine::compile_small_launch(int count, int64_t best_lb) {
+int Engine::compile_small_launch(int count, int64_t best_lb, int ws) {
+    if (ws <= 0 || ws > small_ws) ws = small_ws;
     if (count < 1 || count > root_cap || count > staged) { set_error("compile_small: batch not staged"); return DDO_ERR_INVALID; }
     if (small_ws <= 0) { set_error("small path disabled"); return DDO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaEventRecord(ev0, stream));
     int rc;
     switch (S) {
-        case 2: rc = launch_small<2>(this, count, best_lb); break;
-        case 4: rc = launch_small<4>(this, count, best_lb); break;
-        case 8: rc = launch_small<8>(this, count, best_lb); break;
-        case 16: rc = launch_small<16>(this, count, best_lb); break;
+        case 2: rc = launch_small<2>(this, count, best_lb, ws); break;
+        case 4: rc = launch_small<4>(this, count, best_lb, ws); break;
+        case 8: rc = launch_small<8>(this, count, best_lb, ws); break;
+        case 16: rc = launch_small<16>(this, count, best_lb, ws); break;
         default: set_error("unsupported state width"); return DDO_ERR_UNSUPPORTED;
     }
     if (rc != DDO_OK) return rc;

@@ -157,9 +157,10 @@ struct Engine {
     // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
     virtual int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
     // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
+    int small_ws_first = 64;  // first-tier capacity of the fast path (more CTAs per SM); 0 = single tier
     int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;
     int compile_small(int count, int64_t best_lb, float* device_ms);
-    int compile_small_launch(int count, int64_t best_lb);
+    int compile_small_launch(int count, int64_t best_lb, int ws = 0);  // ws: fast-path capacity of this launch (0 = small_ws)
     int compile_small_wait(float* device_ms);
     int fetch_vars(int index, std::vector<int32_t>& vars);
 };

@@ -343,7 +343,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     if (eng->small_ws > 0) {
         rc = eng->stage_roots(cnt, widths.data(), w_states.data(), values.data(), depths.data());
         if (rc != DDO_OK) return rc;
-        rc = eng->compile_small_launch(cnt, lb0);
+        rc = eng->compile_small_launch(cnt, lb0, eng->small_ws_first > 0 && eng->small_ws_first < eng->small_ws ? eng->small_ws_first : eng->small_ws);
         if (rc != DDO_OK) return rc;
         if (pipeline) { const double tp = now_ms(); prepop(); fringe_ms += now_ms() - tp; }  // overlaps the device
         rc = eng->compile_small_wait(&ms);
@@ -354,6 +354,26 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             if (o.status != 0) { ov.push_back(i); continue; }
             res[i].exact = true; res[i].has = o.has_best != 0; res[i].best = o.best_value;
             expanded += o.expanded; transitions += o.transitions; ++compilations;
+        }
+        // second tier: the DDs that outgrew the first (small, many CTAs per SM) capacity get the full fast-path capacity before they
+        // fall back to the layer-by-layer engine
+        if (!ov.empty() && eng->small_ws_first > 0 && eng->small_ws_first < eng->small_ws) {
+            std::vector<int> ov1;
+            ov1.swap(ov);
+            rc = stage_subset(ov1.data(), (int)ov1.size());
+            if (rc != DDO_OK) return rc;
+            rc = eng->compile_small_launch((int)ov1.size(), lb0, eng->small_ws);
+            if (rc != DDO_OK) return rc;
+            rc = eng->compile_small_wait(&ms);
+            if (rc != DDO_OK) return rc;
+            device_ms += ms; tr_small += ms;
+            for (size_t j = 0; j < ov1.size(); ++j) {
+                const SmallOut& o = eng->h_small[j];
+                const int i = ov1[j];
+                if (o.status != 0) { ov.push_back(i); continue; }
+                res[i].exact = true; res[i].has = o.has_best != 0; res[i].best = o.best_value;
+                expanded += o.expanded; transitions += o.transitions; ++compilations;
+            }
         }
     } else {
         for (int i = 0; i < cnt; ++i) ov.push_back(i);
