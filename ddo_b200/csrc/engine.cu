@@ -116,6 +116,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
         if (finish_cl_smem > 200 * 1024) finish_cl_max = 0;  // slices of very wide layers do not fit shared memory: one-CTA finish with global keys
         if (const char* e = getenv("DDO_FINISH_CL_MAX")) finish_cl_max = std::min(finish_cl_max > 0 ? 1 << 20 : 0, atoi(e));
         if (const char* e = getenv("DDO_EXPAND1_MIN")) expand1_min = atoi(e);
+        if (const char* e = getenv("DDO_COMPACT1_MIN")) compact1_min = atoi(e);
     }
     // keys (8 B) + status (1 B) of up to C distinct candidates: shared memory when they fit next to the 19 KB of static smem
     finish_smem = (size_t)C * 9 + 16;
@@ -236,6 +237,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     // one thread per node (k_expand1) measured faster than G lanes per node (k_expand) at every batch size; DDO_EXPAND1_MIN=<slots>
     // brings the lane-group kernel back for batches below that size (A/B runs)
     const bool use_e1 = slots >= E->expand1_min;
+    const bool use_c1 = slots >= E->compact1_min;
     const size_t e1_smem = (size_t)512 * G * 16;
     const int e1_grid = E->num_sms * 3;
     if (use_e1 && !E->expand1_attr_set) {
@@ -259,7 +261,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         if (use_cl) k_finish_cl<S><<<slots * FCL_CS, FCL_NT, E->finish_cl_smem, st>>>(ev, t, E->finish_cl_kcap);
         else k_finish<S><<<slots, 1024, E->finish_smem, st>>>(ev, t);
         E->prof_mark(1);
-        k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
+        if (use_c1) k_compact1<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
+        else k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
         E->prof_mark(2);
         if (use_e1) k_expand1<S><<<e1_grid, 256, e1_smem, st>>>(ev, t, slots);
         else k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);

@@ -114,6 +114,7 @@ struct Engine {
     int num_sms = 148;
     bool dual_enabled = true;  // fork the relaxed twin at the first cut of a restricted DD (DDO_DUAL=0 disables)
     size_t finish_smem = 0; bool finish_attr_set = false;
+    int compact1_min = 1;  // thread-per-candidate compaction (k_compact1) for batches of >= compact1_min DD slots (DDO_COMPACT1_MIN)
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;

@@ -1513,6 +1513,77 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
 }
 
 // =================================================================================================================
+// k_compact1: the same compaction with ONE THREAD per candidate.  k_compact is bound by the latency of its gather chain
+// (rep -> first -> pos_of -> row) times the candidates in flight; a thread per candidate keeps G times more of them in flight.
+// Grid-stride over units of 32 candidates (one warp each; a tile of the work plan holds 256 / G candidates = 8 / G units).
+// =================================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256) k_compact1(EV ev, int t, int count) {
+    constexpr int G = S / 2;
+    constexpr int CPB = 256 / G;        // candidates per tile of the work plan
+    constexpr int UPT = CPB / 32;       // 32-candidate units per plan tile
+    const int* off = ev.tile_off_c;
+    const int total_units = off[count] * UPT;
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * 256 + threadIdx.x) >> 5, wstride = (gridDim.x * 256) >> 5;
+    for (int u = wglobal; u < total_units; u += wstride) {
+        const int tile = u / UPT;
+        const int k = plan_find(off, count, tile);
+        const DDCtl* ctl = ev.ctl + k;
+        const int ncand = ctl->ncand;
+        const int c0 = (tile - off[k]) * CPB + (u % UPT) * 32;
+        if (c0 == 0) {  // first unit of this DD: reset the per-layer accumulators that the expansion fills next
+            for (int i = lane; i < ev.HN; i += 32) ev.vhist[(size_t)k * ev.HN + i] = 0;
+            if (lane == 0) ev.ucount[k] = 0;
+        }
+        const int c = c0 + lane;
+        if (c >= ncand) continue;
+        const size_t cb = (size_t)k * ev.C;
+        const size_t lb = (size_t)k * ev.Lmax;
+        const int nbuf = t & 1;
+        const bool relaxed = ctl->comp_type == DDO_RELAXED;
+        const uint32_t rep = ev.cand_rep[cb + c];
+        uint32_t child = NONE32;
+        if (rep != NONE32) {
+            const uint32_t f = ev.cand_first[cb + rep];
+            child = ev.pos_of[cb + f];
+            if (rep == (uint32_t)c) {  // release the hash slot this candidate claimed
+                const uint32_t slot = ev.cand_slot[cb + c];
+                if (slot != NONE32) ev.table[(size_t)k * ev.T + slot] = EMPTY64;
+            }
+            if (ev.uflag[cb + c] == 2) {  // surviving canonical representative: becomes node `pos` of layer t
+                const uint32_t pos = ev.pos_of[cb + c];
+                const size_t nb = (size_t)k * ev.Wcap + pos;
+                const uint4* src = reinterpret_cast<const uint4*>(ev.cand_state + (cb + c) * S);
+                uint4* dst = reinterpret_cast<uint4*>(ev.cur_state[nbuf] + nb * S);
+                uint4 v[G];
+#pragma unroll
+                for (int q = 0; q < G; ++q) v[q] = ld_stream_u4(src + q);
+#pragma unroll
+                for (int q = 0; q < G; ++q) st_stream_u4(dst + q, v[q]);
+                const unsigned long long key = ev.cand_agg[cb + c];
+                const uint32_t fl = ev.cand_inex[cb + c];
+                ev.cur_val[nbuf][nb] = key_value(key);
+                ev.cur_flag[nbuf][nb] = (uint8_t)fl;
+                ev.plog[(lb + t) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
+            }
+        }
+        if (t > 0) {
+            if (relaxed) ev.clog[(lb + t - 1) * ev.C + c] = child;
+            if (ctl->lel_pending && relaxed && !(c & 1)) {  // layer t-1 is the last exact layer: keep its nodes for the cutset
+                const int i = c >> 1;
+                const size_t pb = (size_t)k * ev.Wcap + i;
+                const uint4* src = reinterpret_cast<const uint4*>(ev.cur_state[(t - 1) & 1] + pb * S);
+                uint4* dst = reinterpret_cast<uint4*>(ev.lel_state + pb * S);
+#pragma unroll
+                for (int q = 0; q < G; ++q) st_stream_u4(dst + q, ld_stream_u4(src + q));
+                ev.lel_val[pb] = ev.cur_val[(t - 1) & 1][pb]; ev.lel_rub[pb] = ev.cur_rub[pb];
+            }
+        }
+    }
+}
+
+// =================================================================================================================
 // k_small: one CTA compiles one whole DD in shared memory -- the fast path for the (vast majority of) sub-problems whose layers
 // stay narrow.  Valid only while no layer needs a cut (|layer| <= min(max_width, Ws)): then restricted == relaxed == exact DD, node
 // order is irrelevant and only (best value, expanded, transitions) are observable (clean.rs:345-381 with _squash_if_needed never
