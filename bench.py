@@ -227,15 +227,19 @@ def run_ours(args, rank, world, local_rank):
         dom_gbs = last["expanded"] * b_node / (kt[dom]["ms"] * 1e-3) / 1e9
         traffic = None
         tf = ROOT / "profiles" / ("r01_traffic.json" if wl.kind == "misp" else "r01_traffic_max2sat.json")
-        if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-            t = json.loads(tf.read_text())
-            if t["kernel"].startswith(dom) or t["kernel"].startswith(dom.replace("k_", "m2_")) or "traffic_of" in t:  # a capture of the kernel that moves the bytes, named in the file
-                traffic = {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"], "context": t["context"]}
+        if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
+            tj = json.loads(tf.read_text())
+            for t in tj.get("entries", [tj]):
+                if t["kernel"].startswith(dom) or t["kernel"].startswith(dom.replace("k_", "m2_")):
+                    traffic = {"kernel": t["kernel"], "bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "context": t["context"]}
+                    if "algorithmic_bytes" in t:
+                        traffic["algorithmic_bytes_per_launch"] = t["algorithmic_bytes"]
+                    break
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
                             "peak_source": peak_src, "bytes_per_node": b_node, "mean_out_degree": cbar,
                             "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in kt.items()},
                             "kernel_launches_per_step": {k: v["launches"] for k, v in kt.items()},
-                            "achieved_by_kernel": {k: round(last["expanded"] * b_node / (v["ms"] * 1e-3) / 1e9, 1) for k, v in kt.items() if v["ms"] > 0},
+                            "achieved_by_kernel": {k: round(last["expanded"] * b_node / (v["ms"] * 1e-3) / 1e9, 1) for k, v in kt.items() if v["ms"] > 0 and k not in ("k_finalize_bottomup", "k_drain")},
                             "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak,
                             "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
     if not args.no_cpu_baseline:

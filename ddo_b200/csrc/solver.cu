@@ -395,6 +395,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     std::vector<int64_t> caps, lbs;
     std::vector<int32_t> vars;
     // collects the cutset records of the last relaxed batch: slot -> wave index through `slot_wave`
+    bool p_direct = false;  // the wave's only relaxed batch: its records are pushed straight from the engine's pinned drain buffer (no staging copy)
     auto collect_drain = [&](int slots, const std::vector<int>& slot_wave) -> int {
         int pw = 1;
         const int total = eng->drain_all(slots, caps.data(), lbs.data(), &pw);
@@ -412,7 +413,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
                 p_vars.insert(p_vars.end(), vars.begin(), vars.begin() + lel);
             }
-            p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
+            if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
             for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
             p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
             pend.back().count++;
@@ -487,6 +488,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             }
         } else {
             pend.clear(); p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+            p_direct = open.size() <= (size_t)cap;
             for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
                 const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
                 rc = stage_subset(&open[s0], oc);
@@ -540,7 +542,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 const size_t r = (size_t)pd.first + q;
                 if ((int64_t)p_ub[r] <= best_lb) continue;  // parallel.rs:461 with the final incumbent of the wave
                 if (rec_id < 0) { recs.push_back(pr); rec_id = (int)recs.size() - 1; }
-                fringe.push(&p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + pd.lel, rec_id, &p_bits[r * PWN], (pd.lel + 63) / 64);
+                fringe.push(p_direct ? &eng->h_out_state[r * (size_t)eng->S] : &p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + pd.lel, rec_id, &p_bits[r * PWN], (pd.lel + 63) / 64);
             }
         }
         fringe_ms += now_ms() - t0;
