@@ -32,6 +32,18 @@ __device__ __forceinline__ unsigned long long pack_key(int32_t value, uint32_t c
 __device__ __forceinline__ int32_t key_value(unsigned long long key) { return (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u); }
 // ranking tie-break word: BitSet::cmp (lexicographic over ascending members) == unsigned order of ~bitreverse, larger = Greater
 __device__ __forceinline__ uint64_t lex_word(uint64_t w) { return ~__brevll(w); }
+// Low 20 bits of a candidate's rank word: its two smallest members, RB bits each (9 for n <= 512, 10 for n <= 1024), all ones where there
+// is none.  Among sets of equal size BitSet::cmp is the lexicographic order of the ascending member lists, so (popcount, m1, m2) is an
+// order-preserving prefix of the ranking -- and a dense one: the first members of a late, sparse state say far more than the membership
+// of the 20 lowest vertices.
+template <int S> struct RankBits { static constexpr int RB = S <= 8 ? 9 : 10; };
+template <int S> __device__ __forceinline__ void rank_take(uint64_t w, int base, int& got, uint32_t& mk) {
+    while (w && got < 2) { mk = (mk << RankBits<S>::RB) | (uint32_t)(base + __ffsll((long long)w) - 1); ++got; w &= w - 1; }
+}
+template <int S> __device__ __forceinline__ uint32_t rank_pad(int got, uint32_t mk) {
+    for (; got < 2; ++got) mk = (mk << RankBits<S>::RB) | ((1u << RankBits<S>::RB) - 1u);
+    return mk;
+}
 
 __device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {  // L2-only load (coherent across SMs inside one kernel)
     uint4 r;
@@ -166,7 +178,11 @@ __global__ void k_init(EV ev, int count, int comp_type, long long best_lb, int d
         int pc = 0;
         for (int j = 0; j < S; ++j) pc += __popcll(ev.root_state[(size_t)k * S + j]);
         ev.cand_rep[cb] = 0; ev.cand_first[cb] = 0; ev.cand_agg[cb] = pack_key(ev.root_val[k], PLOG_CAND_MASK); ev.cand_inex[cb] = 0;
-        ev.cand_rank[cb] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(ev.root_state[(size_t)k * S]) >> 44);
+        {
+            int got = 0; uint32_t mk = 0;
+            for (int j = 0; j < S; ++j) rank_take<S>(ev.root_state[(size_t)k * S + j], 64 * j, got, mk);
+            ev.cand_rank[cb] = ((uint32_t)pc << 20) | rank_pad<S>(got, mk);
+        }
         ev.cand_slot[cb] = NONE32; ev.uflag[cb] = 0;
         if (k == 0) *ev.active = count;
     }
@@ -283,8 +299,24 @@ __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, i
                 for (int dd = G / 2; dd > 0; dd >>= 1) hs += __shfl_xor_sync(gm, hs, dd);
                 const uint64_t h = mix64(hs);
                 const int pc = group_sum<G>(__popcll(a0) + __popcll(a1), gm);
+                uint32_t mk2;
+                {   // the two smallest members of the child: every lane lists up to two of its own, the group merges them in lane order
+                    int lcnt = 0; uint32_t lmk = 0;
+                    rank_take<S>(a0, 128 * sub, lcnt, lmk); rank_take<S>(a1, 128 * sub + 64, lcnt, lmk);
+                    int got = 0; uint32_t mk = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < G; ++s2) {
+                        const int srcl = ((threadIdx.x & 31) & ~(G - 1)) + s2;
+                        const int c2 = __shfl_sync(gm, lcnt, srcl); const uint32_t l2 = __shfl_sync(gm, lmk, srcl);
+                        if (got < 2 && c2 > 0) {
+                            if (c2 == 2) { if (got == 0) { mk = l2; got = 2; } else { mk = (mk << RankBits<S>::RB) | (l2 >> RankBits<S>::RB); got = 2; } }
+                            else { mk = (mk << RankBits<S>::RB) | l2; got += 1; }
+                        }
+                    }
+                    mk2 = rank_pad<S>(got, mk);
+                }
                 if (sub == 0) {
-                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(a0) >> 44);
+                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | mk2;
                     ev.cand_agg[cb + c] = pack_key(value, c);
                     ev.cand_first[cb + c] = c;
                     ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
@@ -449,7 +481,7 @@ __global__ void __launch_bounds__(256, 3) k_expand1(EV ev, int t, int count) {
                     if (d == 0 && !has_v) continue;
                     const uint32_t c = d == 0 ? c_yes : c_no;
                     uint4* dst = reinterpret_cast<uint4*>(ev.cand_state + (cb + c) * S);
-                    uint64_t hs = 0; int pc = 0; uint64_t first_word = 0;
+                    uint64_t hs = 0; int pc = 0; int got = 0; uint32_t mk = 0;
 #pragma unroll
                     for (int q = 0; q < G; ++q) {
                         uint64_t a0 = w[2 * q], a1 = w[2 * q + 1];
@@ -457,11 +489,11 @@ __global__ void __launch_bounds__(256, 3) k_expand1(EV ev, int t, int count) {
                         st_stream_u4(dst + q, mk_u4(a0, a1));
                         hs += a0 * hash_mul(2 * q) + a1 * hash_mul(2 * q + 1);
                         pc += __popcll(a0) + __popcll(a1);
-                        if (q == 0) first_word = a0;
+                        rank_take<S>(a0, 128 * q, got, mk); rank_take<S>(a1, 128 * q + 64, got, mk);
                     }
                     const int value = d == 0 ? val + ev.weight[v] : val;  // main.rs:87-93
                     hsh[d] = mix64(hs); vals[d] = value;
-                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | (uint32_t)(lex_word(first_word) >> 44);
+                    ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | rank_pad<S>(got, mk);
                     ev.cand_agg[cb + c] = pack_key(value, c);
                     ev.cand_first[cb + c] = c;
                     ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
@@ -589,7 +621,7 @@ __device__ bool cand_better(const EV& ev, size_t cb, uint32_t a, uint32_t b) {
     return false;
 }
 
-// Tie-break keys of the width cut beyond (value_top, popcount, 20 lexicographic bits).  BitSet::cmp orders two sets of EQUAL size by their
+// Tie-break keys of the width cut beyond (value_top, popcount, two smallest members).  BitSet::cmp orders two sets of EQUAL size by their
 // ascending member lists: at the first difference the set owning the smaller vertex is Less.  So chunk j >= 1 of the radix-select key packs
 // the members of rank MK*(j-1) .. MK*j-1 of the state, BK bits each, most significant first: dense information (a raw 64-bit word of a
 // late, sparse state holds a member or two, and a digit over 8 such vertices splits a tied group by ~20 % -- twenty-odd passes; a digit
@@ -752,7 +784,7 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
 #pragma unroll
             for (int j = 0; j < 4; ++j) if ((fl >> (8 * j)) & 0xff) {
                 ev.ulist[cb + off] = (uint32_t)(c0 + j);
-                if (cut) keys[off] = (ag[j] & 0xFFFFFFFF00000000ull) | rk[j];  // (value_top, popcount, 20 lexicographic bits)
+                if (cut) keys[off] = (ag[j] & 0xFFFFFFFF00000000ull) | rk[j];  // (value_top, popcount, two smallest members)
                 ++off;
             }
         }
@@ -766,7 +798,7 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
         bool done = false;
         if (need == 0) { for (int ui = tid; ui < U; ui += NT) stat[ui] = 2; done = true; }
         for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
-            // key chunk 0: (value_top, popcount, 20 lexicographic bits); chunk j >= 1: the next MK members of the state (member_key)
+            // key chunk 0: (value_top, popcount, two smallest members); chunk j >= 1: the next MK members of the state (member_key)
             if (chunk > 0) {
                 for (int ui = tid; ui < U; ui += NT) if (stat[ui] == 0) keys[ui] = member_key<S>(ev.cand_state + (cb + ev.ulist[cb + ui]) * S, MemberKey<S>::MK * (chunk - 1));
                 __syncthreads();

@@ -196,3 +196,27 @@ def test_solver_times_and_divby_width_heuristics_match_oracle():
         assert comp.is_exact and comp.best_value == ref["best_value"]
         assert (s.explored(), int(s.stats()["expanded"])) == (ref["explored"], ref["expanded"])
     assert Times(3, FixedWidth(5)).max_width(SubProblem(None, 0)) == 15 and DivBy(10, FixedWidth(5)).max_width(SubProblem(None, 0)) == 1
+
+
+@pytest.mark.parametrize("env", [{"DDO_FINISH_CL_MAX": "0"}, {"DDO_EXPAND1_MIN": "1000000000", "DDO_COMPACT1_MIN": "1000000000"}, {"DDO_SMALL_WS_FIRST": "0"},
+                                 {"DDO_FINISH_CL_MAX": "0", "DDO_EXPAND1_MIN": "1000000000", "DDO_COMPACT1_MIN": "1000000000", "DDO_SMALL_WS_FIRST": "0", "DDO_DUAL": "0"}])
+def test_kernel_variants_give_the_same_search(monkeypatch, env):
+    """Every alternative kernel path (one-CTA finish instead of the cluster finish, lane-group expansion / compaction instead of thread-per-node,
+    single-tier fast path, no dual mode) compiles the same DDs: same optimum, bounds, counters and solution as the default build and the oracle."""
+    inst = gnp(160, 0.3, 29)
+    ref = O.OracleMisp(inst).solve("wave", k=32, width=40)
+
+    def run():
+        s = ParNoCachingSolverLel(Misp(inst), FixedWidth(40), wave_size=32, batch_cap=32)
+        c = s.maximize()
+        st = s.stats()
+        return (c.best_value, c.is_exact, s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]),
+                sorted(d.variable for d in s.best_solution() if d.value == 1))
+
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = run()
+    assert base == alt
+    assert base[:6] == (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"])
+    assert base[7] == ref["solution"]
