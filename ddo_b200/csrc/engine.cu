@@ -488,6 +488,16 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
     return total;
 }
 
+// branching variables of every DD of the last batch in ONE copy: [slots][Lmax] (a per-DD copy + synchronize costs ~10 us each, and a wide
+// wave drains hundreds of DDs)
+int Engine::fetch_vars_all(int slots, std::vector<int32_t>& vars) {
+    vars.resize((size_t)slots * Lmax);
+    bytes_d2h += (unsigned long long)((size_t)slots * Lmax * 4);
+    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog, (size_t)slots * Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return DDO_OK;
+}
+
 int Engine::fetch_vars(int index, std::vector<int32_t>& vars) {
     vars.resize(Lmax);
     bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));

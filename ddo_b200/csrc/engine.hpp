@@ -164,6 +164,7 @@ struct Engine {
     int compile_small_launch(int count, int64_t best_lb, int ws = 0);  // ws: fast-path capacity of this launch (0 = small_ws)
     int compile_small_wait(float* device_ms);
     int fetch_vars(int index, std::vector<int32_t>& vars);
+    int fetch_vars_all(int slots, std::vector<int32_t>& vars);
 };
 
 int model_create_misp(int32_t n, const int64_t* weights, int64_t m, const int32_t* src, const int32_t* dst, int device, MispModel** out);

@@ -403,15 +403,14 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         p_states.reserve(p_states.size() + (size_t)total * W); p_bits.reserve(p_bits.size() + (size_t)total * PWN);
         p_val.reserve(p_val.size() + total); p_ub.reserve(p_ub.size() + total);
         int cur_dd = -1;
+        if (total > 0) { const int r2 = eng->fetch_vars_all(slots, vars); if (r2 != DDO_OK) return r2; }
         for (int r = 0; r < total; ++r) {
             const int j = eng->h_out_dd[r];
             if (j != cur_dd) {
                 cur_dd = j;
                 const int lel = eng->h_ctl[j].lel;
-                int r2 = eng->fetch_vars(j, vars);
-                if (r2 != DDO_OK) return r2;
                 pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
-                p_vars.insert(p_vars.end(), vars.begin(), vars.begin() + lel);
+                p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lmax, vars.begin() + (size_t)j * eng->Lmax + lel);
             }
             if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
             for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);

@@ -143,7 +143,9 @@ int ddo_mdd_fetch_completions(ddo_mdd*, int32_t count, ddo_completion* out);
 /* ---- Solver: src/abstraction/solver.rs:32-97, implementation/solver/parallel.rs:287-641 ----
  * Branch-and-bound over a NoDupFringe (fringe/no_duplicate.rs) ordered by MaxUB (heuristics/subproblem_ranking.rs:86-90); each wave
  * pops up to wave_size open sub-problems and compiles their restricted then relaxed DDs on the device.  wave_size may exceed the mdd's
- * batch_cap: narrow sub-problems are compiled by the shared-memory fast path (one CTA each), the others batch_cap at a time. */
+ * batch_cap: narrow sub-problems are compiled by the shared-memory fast path (one CTA each), the others batch_cap at a time.
+ * width_kind / width = the WidthHeuristic (heuristics/width.rs), evaluated per sub-problem on the host: DDO_WIDTH_FIXED (FixedWidth(width)),
+ * DDO_WIDTH_NB_UNASSIGNED (width ignored), DDO_WIDTH_TIMES_NB_UNASSIGNED / DDO_WIDTH_DIVBY_NB_UNASSIGNED (Times / DivBy(width, NbUnassignedWidth)). */
 int ddo_solver_create(const ddo_model*, ddo_mdd*, int32_t width_kind, uint64_t width, int32_t wave_size, ddo_solver** out);
 void ddo_solver_destroy(ddo_solver*);
 /* Solver::maximize (solver.rs:56).  time_budget_s <= 0: NoCutoff; else TimeBudget (heuristics/cutoff.rs:302-323). max_waves 0: unlimited */
