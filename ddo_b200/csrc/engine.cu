@@ -239,7 +239,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     const bool use_e1 = slots >= E->expand1_min;
     const bool use_c1 = slots >= E->compact1_min;
     const size_t e1_smem = (size_t)512 * G * 16;
-    const int e1_grid = E->num_sms * 3;
+    const int e1_grid = E->num_sms * DDO_EXPAND1_MINB;  // one resident wave of CTAs (contiguous tile ranges)
     if (use_e1 && !E->expand1_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_expand1<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e1_smem));
         E->expand1_attr_set = true;

@@ -393,8 +393,11 @@ __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, i
 // per node.  A CTA handles up to G consecutive tiles of the work plan (256 nodes) of ONE DD at a time; the claimed rows are staged in
 // shared memory, compacted through a bit mask, and bit-transposed into the per-vertex histogram exactly as in k_expand.
 // =================================================================================================================
+#ifndef DDO_EXPAND1_MINB
+#define DDO_EXPAND1_MINB 4
+#endif
 template <int S>
-__global__ void __launch_bounds__(256, 3) k_expand1(EV ev, int t, int count) {
+__global__ void __launch_bounds__(256, DDO_EXPAND1_MINB) k_expand1(EV ev, int t, int count) {
     constexpr int G = S / 2;                 // 128-bit chunks per state
     constexpr int PLAN = 256 / G;            // nodes per tile of the work plan (written by k_finish for k_expand's geometry)
     constexpr int RP = G >= 8 ? 1 : 8 / G;   // bank swizzle of the staged rows, as in k_expand
