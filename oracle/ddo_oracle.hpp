@@ -11,7 +11,8 @@
 // unit-test expectations (oracle/selftest.cpp restates clean.rs:1190-2398,
 // node_flags.rs, no_duplicate.rs tests), the golden graphviz dumps in
 // resources/visualisation_tests (tests/golden/*.dot) and the known optima of
-// the DIMACS / knapsack instances asserted by examples/*/tests.rs.
+// the DIMACS / knapsack / MAX2SAT instances asserted by examples/*/tests.rs
+// (plus the MAX2SAT model unit vectors of examples/max2sat/model.rs:388-448).
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference/ddo/src unless stated).
@@ -25,6 +26,8 @@
 //   C3. after a cut the surviving nodes are put back in node-creation order
 //       (merged node, resp. the "saved" node of the recycled case, last).
 //   C4. best terminal node = last maximum in C1 order (Rust max_by_key).
+//   C5/C6 (MAX2SAT, models.hpp): stable variable order; ranking ties refined
+//       by (depth, lexicographic benefits).
 // Everything else (e.g. the order in which relaxed edges are appended,
 // clean.rs:851-866, and the `>=` "last tie wins" rule, clean.rs:215) is verbatim.
 // ============================================================================
