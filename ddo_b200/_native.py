@@ -46,6 +46,7 @@ SYMBOLS = {
     "ddo_mdd_best_solution": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "ddo_mdd_drain_cutset": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32)]),
     "ddo_mdd_drain_cutset_batch": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "ddo_mdd_drain_layer_index": (C.c_int, [_P, _P, C.c_int64]),
     "ddo_mdd_set_profiling": (C.c_int, [_P, C.c_int32]),
     "ddo_mdd_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double * 6), C.POINTER(C.c_uint64 * 6)]),
     "ddo_mdd_layer_trace": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32]),

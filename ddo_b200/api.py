@@ -21,6 +21,7 @@ from . import _native as N
 from .instances import Max2SatInstance, MispInstance
 
 LAST_EXACT_LAYER = N.LAST_EXACT_LAYER
+FRONTIER = N.FRONTIER
 
 
 class CompilationType:  # src/abstraction/mdd.rs:40-47
@@ -213,6 +214,7 @@ class GpuMdd:
     def __init__(self, problem: Misp, max_width_cap: int, batch_cap: int = 1, cutset_type: int = LAST_EXACT_LAYER):
         self.problem = problem
         self.batch_cap = batch_cap
+        self.cutset_type = cutset_type
         h = C.c_void_p()
         N.check(N.lib().ddo_mdd_create(problem.h, problem.device, max_width_cap, batch_cap, cutset_type, C.byref(h)), "ddo_mdd_create")
         self.h = h
@@ -267,6 +269,8 @@ class GpuMdd:
 
     def drain_cutset(self, index: int = 0, ub_cap: int = N.I64_MAX, lb_filter: int = N.I64_MIN, with_paths: bool = True) -> List[SubProblem]:
         """drain_cutset (clean.rs:417-445): the MARKED cutset nodes as SubProblems (path = root path ++ decisions, clean.rs:329-343)."""
+        if self.cutset_type == N.FRONTIER:
+            return self._drain_frontier(index, ub_cap, lb_filter, with_paths)
         c = self._last[index]
         cap = max(c.cutset_size, 1)
         W = self.problem.words
@@ -288,6 +292,36 @@ class GpuMdd:
                 p += [Decision(paths[i * plen.value + j].variable, paths[i * plen.value + j].value) for j in range(plen.value)]
             out.append(SubProblem(states[i].copy(), int(values[i]), p, int(ubs[i]), int(depth.value)))
         return out
+
+    def _drain_frontier(self, index: int, ub_cap: int, lb_filter: int, with_paths: bool) -> List[SubProblem]:
+        """FRONTIER cutset (clean.rs:586-606) of DD `index`: the nodes sit in different layers, so every record carries its own layer
+        (ddo_mdd_drain_layer_index); canonical order = layer descending, position ascending."""
+        n = len(self._last)
+        cap = max(self._last[index].cutset_size, 1)
+        W = self.problem.words
+        caps = np.zeros(n, dtype=np.int64)
+        lbs = np.full(n, N.I64_MAX, dtype=np.int64)
+        caps[index] = ub_cap
+        lbs[index] = lb_filter
+        pwmax = (self.problem.nb_variables() + 64) // 64
+        out = dict(states=np.zeros((cap, W), dtype=np.uint64), values=np.zeros(cap, dtype=np.int64), ubs=np.zeros(cap, dtype=np.int64),
+                   dd=np.zeros(cap, dtype=np.int32), bits=np.zeros(cap * pwmax, dtype=np.uint64))
+        total, pw = self.drain_cutset_batch(n, caps, lbs, out)
+        layers = np.zeros(max(total, 1), dtype=np.int32)
+        N.check(N.lib().ddo_mdd_drain_layer_index(self.h, _ptr(layers), len(layers)), "ddo_mdd_drain_layer_index")
+        root = self._roots[index]
+        vars_, _ = self.layer_trace(index) if (with_paths and total) else (None, None)
+        bits = out["bits"][: total * pw].reshape(total, pw) if total else None
+        res = []
+        for i in range(total):
+            tt = int(layers[i])
+            p = list(root.path)
+            if with_paths:  # terminal -> root order like clean.rs:329-343
+                for t in range(tt - 1, -1, -1):
+                    b = int((int(bits[i, t >> 6]) >> (t & 63)) & 1)
+                    p.append(Decision(int(vars_[t]), b))  # MISP: YES = 1, NO = 0
+            res.append(SubProblem(out["states"][i].copy(), int(out["values"][i]), p, int(out["ubs"][i]), root.depth + tt))
+        return res
 
     def drain_cutset_batch(self, count: int, ub_caps, lb_filters, out=None):
         """Batched drain (ddo_mdd_drain_cutset_batch) into caller-provided numpy buffers `out` = dict(states, values, ubs, dd, bits).
@@ -356,12 +390,14 @@ class ParNoCachingSolverLel:
     DDs of one device batch.  ``custom(problem, width, cutoff_seconds, wave_size)`` mirrors ``ParallelSolver::custom`` (parallel.rs:319-358)
     with ``nb_threads`` replaced by the number of DDs compiled in lock-step."""
 
+    CUTSET_TYPE = LAST_EXACT_LAYER
+
     def __init__(self, problem: Misp, width, wave_size: int = 128, max_width_cap: Optional[int] = None, mdd: Optional[GpuMdd] = None,
                  batch_cap: Optional[int] = None):
         self.problem = problem
         kind, w, need = _width_spec(width, problem.nb_variables())
         cap = max_width_cap or need
-        self.mdd = mdd or GpuMdd(problem, cap, min(wave_size, batch_cap) if batch_cap else wave_size)
+        self.mdd = mdd or GpuMdd(problem, cap, min(wave_size, batch_cap) if batch_cap else wave_size, cutset_type=self.CUTSET_TYPE)
         h = C.c_void_p()
         N.check(N.lib().ddo_solver_create(problem.h, self.mdd.h, kind, w, wave_size, C.byref(h)), "ddo_solver_create")
         self.h = h
@@ -447,6 +483,11 @@ class ParNoCachingSolverLel:
             self.close()
         except Exception:
             pass
+
+
+class ParNoCachingSolverFc(ParNoCachingSolverLel):
+    """`ParNoCachingSolverFc` (solver/mod.rs): the same solver over DDs with the FRONTIER cutset (clean.rs:586-606).  MISP device model."""
+    CUTSET_TYPE = FRONTIER
 
 
 DefaultSolver = ParNoCachingSolverLel  # solver/mod.rs:29

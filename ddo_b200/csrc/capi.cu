@@ -112,6 +112,7 @@ int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps
     int pw = 1;
     const int n = e.drain_all(count, ub_caps, lb_filters, &pw);
     if (n < 0) return n;
+    e.last_drain_total = n;
     if (path_words) *path_words = pw;
     if ((int64_t)n > *total) { *total = n; set_error("drain_cutset_batch: buffer too small"); return DDO_ERR_CAPACITY; }
     const int words = e.abi_words;
@@ -124,6 +125,16 @@ int ddo_mdd_drain_cutset_batch(ddo_mdd* d, int32_t count, const int64_t* ub_caps
     if (path_bits && n > 0) std::memcpy(path_bits, e.h_out_path, (size_t)n * pw * 8);
     *total = n;
     return DDO_OK;
+    GUARD_END
+}
+int ddo_mdd_drain_layer_index(ddo_mdd* d, int32_t* layer_index, int64_t cap) {
+    GUARD_BEGIN
+    if (!d || !layer_index) { set_error("null argument"); return DDO_ERR_INVALID; }
+    Engine& e = *d->ep;
+    const int n = e.last_drain_total;
+    if ((int64_t)n > cap) { set_error("drain_layer_index: buffer too small"); return DDO_ERR_CAPACITY; }
+    for (int r = 0; r < n; ++r) layer_index[r] = e.cutset_type == DDO_FRONTIER ? e.h_out_tt[r] : e.h_ctl[e.h_out_dd[r]].lel;
+    return n;
     GUARD_END
 }
 int ddo_mdd_set_profiling(ddo_mdd* d, int32_t on) {

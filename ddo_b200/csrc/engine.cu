@@ -1,5 +1,6 @@
 // engine.cu -- host side of the batch DD-compilation engine: arenas in HBM, the per-layer launch loop, result fetch.
 #include "kernels.cuh"
+#include "frontier.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -87,8 +88,11 @@ static int dev_alloc(Engine* E, T** p, size_t count) {
 
 int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batch_cap, int cutset) {
     if (!m || batch_cap < 1 || max_width_cap < 1) { set_error("ddo_mdd_create: invalid argument"); return DDO_ERR_INVALID; }
-    if (cutset != DDO_LAST_EXACT_LAYER) { set_error("device engine implements the LAST_EXACT_LAYER cutset only (FRONTIER: see DESIGN.md, next)"); return DDO_ERR_UNSUPPORTED; }
+    if (cutset != DDO_LAST_EXACT_LAYER && cutset != DDO_FRONTIER) { set_error("cutset_type must be DDO_LAST_EXACT_LAYER or DDO_FRONTIER (mdd.rs:24-28)"); return DDO_ERR_INVALID; }
     if (max_width_cap > (1u << 27)) { set_error("max_width_cap too large"); return DDO_ERR_INVALID; }
+    if (cutset == DDO_FRONTIER && (max_width_cap + 2 >= (1u << FC_POS_BITS) || (uint64_t)(m->n + 1) * (max_width_cap + 2) >= (1ull << 30))) {
+        set_error("FRONTIER cutset: max_width_cap * (n + 1) must stay below 2^30 frontier records per DD"); return DDO_ERR_UNSUPPORTED;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
     if (dev != m->device) { set_error("model and mdd must live on the same device"); return DDO_ERR_INVALID; }
@@ -129,10 +133,23 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
     ALLOC(ev.best_path, (size_t)K * PW); ALLOC(ev.best_exact_path, (size_t)K * PW);
     // drain buffers
-    ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
+    out_cap = KW;
+    ev.fc_node = nullptr; ev.fc_ub = nullptr; ev.fc_aux = nullptr; ev.fc_cap = 0; d_out.tt = nullptr;
+    if (cutset == DDO_FRONTIER) {
+        // every node above the terminal layer may be a frontier node; the drain buffers hold DDO_FC_OUT_FACTOR (default 8) layers' worth
+        ev.fc_cap = (unsigned long long)(Lmax - 1) * Wcap;
+        const size_t KF = (size_t)K * ev.fc_cap;
+        ALLOC(ev.fc_node, KF); ALLOC(ev.fc_ub, KF); ALLOC(ev.fc_aux, KF);
+        int factor = 8;
+        if (const char* e = getenv("DDO_FC_OUT_FACTOR")) factor = std::max(1, atoi(e));
+        out_cap = std::min(KF, std::max<size_t>(KW * (size_t)factor, 1u << 16));
+        ALLOC(d_out.tt, out_cap);
+    }
+    ALLOC(d_out.state, out_cap * S); ALLOC(d_out.val, out_cap); ALLOC(d_out.ub, out_cap); ALLOC(d_out.dd, out_cap); ALLOC(d_out.path, out_cap * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
+    if (cutset == DDO_FRONTIER) dual_enabled = false;  // the twin's logs start at its fork layer; the frontier sweep reads whole DDs
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     if (const char* e = getenv("DDO_SMALL_WS_FIRST")) { int v = atoi(e); if (v == 0 || v == 32 || v == 64 || v == 128) small_ws_first = v; }
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
@@ -153,7 +170,8 @@ void Engine::destroy() {
     allocations.clear();
     for (void* p : {(void*)ev.root_state, (void*)ev.root_val, (void*)ev.root_depth, (void*)ev.root_width, (void*)d_small}) if (p) cudaFree(p);
     for (void* p : {(void*)h_root_state, (void*)h_root_val, (void*)h_root_depth, (void*)h_root_width, (void*)h_ctl, (void*)h_active, (void*)h_caps,
-                    (void*)h_counts, (void*)h_small, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path})
+                    (void*)h_counts, (void*)h_small, (void*)h_out_state, (void*)h_out_val, (void*)h_out_ub, (void*)h_out_dd, (void*)h_out_path,
+                    (void*)h_out_tt})
         if (p) cudaFreeHost(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -278,7 +296,14 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     // one more k_finish turns TERMINAL into DONE; harmless otherwise
     k_finalize<<<(slots + 63) / 64, 64, 0, st>>>(ev, slots);
     ++g_kernel_launches;
-    if (comp_type == DDO_RELAXED || slots > count) { k_bottomup<<<slots, 1024, 0, st>>>(ev); ++g_kernel_launches; }
+    if (E->cutset_type == DDO_FRONTIER) {
+        // clean.rs:586-606 + 448-475: frontier membership and local bounds in one bottom-up sweep, then the upper bound of every member
+        if (comp_type == DDO_RELAXED) {
+            k_fc_sweep<<<slots, 1024, 0, st>>>(ev);
+            k_fc_eval<S><<<dim3(64, slots), 256, 0, st>>>(ev);
+            g_kernel_launches += 2;
+        }
+    } else if (comp_type == DDO_RELAXED || slots > count) { k_bottomup<<<slots, 1024, 0, st>>>(ev); ++g_kernel_launches; }
     E->prof_mark(3);
     CUDA_TRY(cudaGetLastError());
     return DDO_OK;
@@ -437,6 +462,7 @@ int Engine::layer_trace(int index, int32_t* vars, int32_t* widths, int cap) {
 int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw_out) {
     if (last_comp_type != DDO_RELAXED) { set_error("drain_cutset: the last batch was not a relaxed compilation (mdd.rs:103-110)"); return DDO_ERR_INVALID; }
     if (count > last_count) { set_error("drain_cutset: bad count"); return DDO_ERR_INVALID; }
+    if (cutset_type == DDO_FRONTIER) return drain_all_frontier(count, ub_cap, lb_filter, pw_out);
     int rc = fetch_ctl(last_count);
     if (rc != DDO_OK) return rc;
     int max_lel = 0;
@@ -477,12 +503,66 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
         CUDA_TRY(cudaMallocHost(&h_out_ub, KW * 4));
         CUDA_TRY(cudaMallocHost(&h_out_dd, KW * 4));
         CUDA_TRY(cudaMallocHost(&h_out_path, KW * PW * 8));
+        CUDA_TRY(cudaMallocHost(&h_out_tt, KW * 4));
     }
     bytes_d2h += (unsigned long long)((size_t)total * S * 8); CUDA_TRY(cudaMemcpyAsync(h_out_state, d_out.state, (size_t)total * S * 8, cudaMemcpyDeviceToHost, stream));
     bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_val, d_out.val, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
     bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_ub, d_out.ub, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
     bytes_d2h += (unsigned long long)((size_t)total * 4); CUDA_TRY(cudaMemcpyAsync(h_out_dd, d_out.dd, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
     bytes_d2h += (unsigned long long)((size_t)total * pw * 8); CUDA_TRY(cudaMemcpyAsync(h_out_path, d_out.path, (size_t)total * pw * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int r = 0; r < total; ++r) h_out_tt[r] = h_ctl[h_out_dd[r]].lel;  // a LEL cutset is one layer of its DD
+    { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
+    return total;
+}
+
+// The same for a FRONTIER engine (frontier.cuh): the records of a DD come from different layers, h_out_tt holds the layer of each.
+int Engine::drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw_out) {
+    int rc = fetch_ctl(last_count);
+    if (rc != DDO_OK) return rc;
+    int max_t = 0;
+    for (int i = 0; i < count; ++i) max_t = std::max(max_t, h_ctl[i].t_term);
+    const int pw = std::min(16, std::max(1, (max_t + 63) / 64));
+    *pw_out = pw;
+    long long* caps = (long long*)h_caps;
+    for (int i = 0; i < K; ++i) { caps[i] = i < count ? ub_cap[i] : 0; caps[K + i] = i < count ? lb_filter[i] : INT64_MAX; }
+    CUDA_TRY(cudaSetDevice(device));
+    bytes_h2d += (unsigned long long)((size_t)K * 16);
+    CUDA_TRY(cudaMemcpyAsync(d_ub_cap, caps, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_lb_filter, caps + K, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    prof_mark(-1);
+    k_fc_count<<<last_count, 1024, 0, stream>>>(ev, d_out, d_ub_cap, d_lb_filter, count);
+    k_cutset_offsets<<<1, 32, 0, stream>>>(d_out, last_count);
+    g_kernel_launches += 2;
+    bytes_d2h += (unsigned long long)((size_t)(last_count + 1) * 4); CUDA_TRY(cudaMemcpyAsync(h_counts, d_out.offset, (size_t)(last_count + 1) * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const int total = ((int32_t*)h_counts)[last_count];
+    if (total == 0) { prof_used = 0; return 0; }
+    if ((size_t)total > out_cap) { prof_used = 0; set_error("frontier cutset larger than the drain buffers (raise DDO_FC_OUT_FACTOR)"); return DDO_ERR_CAPACITY; }
+    const dim3 grid(64, last_count);
+    switch (S) {
+        case 2: k_fc_write<2><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 4: k_fc_write<4><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 8: k_fc_write<8><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        default: k_fc_write<16><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+    }
+    ++g_kernel_launches;
+    prof_mark(4);
+    if (!h_out_state) {
+        CUDA_TRY(cudaMallocHost(&h_out_state, out_cap * S * 8));
+        CUDA_TRY(cudaMallocHost(&h_out_val, out_cap * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_ub, out_cap * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_dd, out_cap * 4));
+        CUDA_TRY(cudaMallocHost(&h_out_path, out_cap * PW * 8));
+        CUDA_TRY(cudaMallocHost(&h_out_tt, out_cap * 4));
+    }
+    bytes_d2h += (unsigned long long)((size_t)total * (S * 8 + 16 + pw * 8));
+    CUDA_TRY(cudaMemcpyAsync(h_out_state, d_out.state, (size_t)total * S * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_val, d_out.val, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_ub, d_out.ub, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_dd, d_out.dd, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_tt, d_out.tt, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out_path, d_out.path, (size_t)total * pw * 8, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     { int prc = prof_collect(); if (prc != DDO_OK) return prc; }
     return total;
@@ -508,6 +588,10 @@ int Engine::fetch_vars(int index, std::vector<int32_t>& vars) {
 int Engine::drain_cutset(int index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depth_out,
                          int32_t* path_len_out, ddo_decision* paths, int32_t* count) {
     if (index < 0 || index >= last_count || !count) { set_error("drain_cutset: bad index"); return DDO_ERR_INVALID; }
+    if (cutset_type == DDO_FRONTIER) {
+        set_error("a FRONTIER cutset has one depth per node: use ddo_mdd_drain_cutset_batch + ddo_mdd_drain_layer_index");
+        return DDO_ERR_UNSUPPORTED;
+    }
     std::vector<int64_t> caps(last_count, 0), lbs(last_count, INT64_MAX);
     caps[index] = ub_cap; lbs[index] = lb_filter;
     int pw = 1;

@@ -88,7 +88,12 @@ struct EV {
     int32_t* cs_ub; uint8_t* cs_marked;
     // best paths (decision bits, one per layer) for best / best exact terminal node
     uint64_t* best_path; uint64_t* best_exact_path;
+    // FRONTIER cutset (frontier.cuh; allocated by engines created with DDO_FRONTIER only): [K][fc_cap] records of the MARKED cutset nodes
+    // in canonical order (layer descending, position ascending): node = layer << FC_POS_BITS | position, upper bound, scratch (value_bot, then
+    // the local output index of a drain)
+    uint32_t* fc_node; int32_t* fc_ub; int32_t* fc_aux; unsigned long long fc_cap;
 };
+constexpr int FC_POS_BITS = 21;
 
 // result of the shared-memory fast path (k_small), one per DD
 struct SmallOut {
@@ -100,6 +105,7 @@ struct SmallOut {
 // batched drain_cutset output (device side)
 struct DrainOut {
     uint64_t* state; int32_t* val; int32_t* ub; int32_t* dd; uint64_t* path;  // [total] records
+    int32_t* tt;                      // [total] layer of the record inside its DD (FRONTIER engines only; a LEL cutset has one layer per DD)
     int32_t* count; int32_t* offset;  // [K+1]; offset[K] = total
     uint32_t* loc;                    // [K][Wcap] local index of each emitted node
 };
@@ -128,6 +134,9 @@ struct Engine {
     DrainOut d_out{}; long long* d_ub_cap = nullptr; long long* d_lb_filter = nullptr;
     // pinned results of the last drain_all (records [0,total))
     uint64_t* h_out_state = nullptr; int32_t* h_out_val = nullptr; int32_t* h_out_ub = nullptr; int32_t* h_out_dd = nullptr; uint64_t* h_out_path = nullptr;
+    int32_t* h_out_tt = nullptr;   // layer of every record inside its DD (LEL: the DD's last exact layer)
+    size_t out_cap = 0;            // records the drain buffers hold (LEL: K * Wcap)
+    int last_drain_total = 0;      // records of the last ddo_mdd_drain_cutset_batch
     int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false;
     size_t bytes_allocated = 0;
     unsigned long long layer_steps = 0;  // layer steps (k_finish + k_compact + k_expand) launched so far
@@ -157,6 +166,7 @@ struct Engine {
     int layer_trace(int index, int32_t* vars, int32_t* widths, int cap);
     // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
     virtual int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
+    int drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);  // MISP engine, DDO_FRONTIER
     // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
     int small_ws_first = 64;  // first-tier capacity of the fast path (more CTAs per SM); 0 = single tier
     int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;

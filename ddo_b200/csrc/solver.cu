@@ -220,11 +220,12 @@ int Solver::init(bool push_root) {  // parallel.rs:368-385
     return DDO_OK;
 }
 
-void Solver::full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decision>& out) const {
+void Solver::full_path(int32_t rec, const uint64_t* bits, int32_t depth, std::vector<ddo_decision>& out) const {
     if (rec == -1) return;
     const PathRec& r = recs[rec];
-    full_path(r.parent_rec, r.parent_bits.data(), out);
-    for (size_t i = 0; i < r.vars.size(); ++i) out.push_back(ddo_decision{r.vars[i], eng->bit_value[(bits[i >> 6] >> (i & 63)) & 1]});
+    full_path(r.parent_rec, r.parent_bits.data(), r.base_depth, out);
+    const size_t len = std::min<size_t>(r.vars.size(), (size_t)std::max(0, depth - r.base_depth));  // decisions taken inside this DD
+    for (size_t i = 0; i < len; ++i) out.push_back(ddo_decision{r.vars[i], eng->bit_value[(bits[i >> 6] >> (i & 63)) & 1]});
 }
 
 int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
@@ -307,7 +308,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         r2 = eng->best_solution(0, 1, dd.data(), &len);
         if (r2 != DDO_OK) return r2;
         best_sol.clear();
-        full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], best_sol);
+        full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], w_items[wave_index].depth, best_sol);
         best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
         has_sol = true;
         return DDO_OK;
@@ -330,7 +331,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         for (auto it = captured.rbegin(); it != captured.rend(); ++it)
             if (it->first == wave_index) {
                 best_sol.clear();
-                full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], best_sol);
+                full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], w_items[wave_index].depth, best_sol);
                 best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
                 has_sol = true;
                 return true;
@@ -391,7 +392,8 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     struct TwinRes { int wave_index; unsigned long long expanded, transitions; bool has; int32_t best; };
     std::vector<Pending> pend;
     std::vector<TwinRes> twins;
-    p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+    p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear(); p_tt.clear();
+    const bool frontier = eng->cutset_type == DDO_FRONTIER;  // cutset nodes of one DD sit in different layers (clean.rs:586-606)
     std::vector<int64_t> caps, lbs;
     std::vector<int32_t> vars;
     // collects the cutset records of the last relaxed batch: slot -> wave index through `slot_wave`
@@ -408,13 +410,14 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             const int j = eng->h_out_dd[r];
             if (j != cur_dd) {
                 cur_dd = j;
-                const int lel = eng->h_ctl[j].lel;
+                const int lel = frontier ? std::max(0, eng->h_ctl[j].t_term) : eng->h_ctl[j].lel;  // layers whose variables the paths may use
                 pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
                 p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lmax, vars.begin() + (size_t)j * eng->Lmax + lel);
             }
             if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
             for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
             p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
+            p_tt.push_back(frontier ? eng->h_out_tt[r] : pend.back().lel);
             pend.back().count++;
         }
         return DDO_OK;
@@ -486,7 +489,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 if (tw.has && (int64_t)tw.best > best_lb) { best_lb = tw.best; improver = tw.wave_index; }
             }
         } else {
-            pend.clear(); p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear();
+            pend.clear(); p_states.clear(); p_bits.clear(); p_val.clear(); p_ub.clear(); p_vars.clear(); p_tt.clear();
             p_direct = open.size() <= (size_t)cap;
             for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
                 const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
@@ -522,7 +525,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             for (auto it = captured.rbegin(); it != captured.rend() && !got; ++it)
                 if (it->first == -1 - wi) {
                     best_sol.clear();
-                    full_path(w_items[wi].rec, &w_bits[(size_t)wi * PWN], best_sol);
+                    full_path(w_items[wi].rec, &w_bits[(size_t)wi * PWN], w_items[wi].depth, best_sol);
                     best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
                     has_sol = true; got = true;
                 }
@@ -535,13 +538,14 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             pr.parent_rec = w_items[pd.wave_index].rec;
             pr.parent_bits.assign(&w_bits[(size_t)pd.wave_index * PWN], &w_bits[(size_t)pd.wave_index * PWN] + PWN);
             pr.vars.assign(p_vars.begin() + var_off, p_vars.begin() + var_off + pd.lel);
+            pr.base_depth = w_items[pd.wave_index].depth;
             var_off += pd.lel;
             int rec_id = -1;
             for (int q = 0; q < pd.count; ++q) {
                 const size_t r = (size_t)pd.first + q;
                 if ((int64_t)p_ub[r] <= best_lb) continue;  // parallel.rs:461 with the final incumbent of the wave
                 if (rec_id < 0) { recs.push_back(pr); rec_id = (int)recs.size() - 1; }
-                fringe.push(p_direct ? &eng->h_out_state[r * (size_t)eng->S] : &p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + pd.lel, rec_id, &p_bits[r * PWN], (pd.lel + 63) / 64);
+                fringe.push(p_direct ? &eng->h_out_state[r * (size_t)eng->S] : &p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + p_tt[r], rec_id, &p_bits[r * PWN], (p_tt[r] + 63) / 64);
             }
         }
         fringe_ms += now_ms() - t0;

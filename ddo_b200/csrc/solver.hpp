@@ -22,7 +22,9 @@ namespace ddo {
 struct PathRec {
     int32_t parent_rec;              // record of the DD root's own path, -1 for the problem root
     std::vector<uint64_t> parent_bits;  // the DD root's decision bits inside parent_rec
-    std::vector<int32_t> vars;       // branching variable of each layer between the DD root and its cutset layer
+    std::vector<int32_t> vars;       // branching variable of each layer between the DD root and its deepest cutset node
+    int32_t base_depth = 0;          // depth of the DD root: a sub-problem of depth d uses the first d - base_depth layers (all of them for
+                                     // a LAST_EXACT_LAYER cutset; the nodes of a FRONTIER cutset sit in different layers)
 };
 
 class NoDupFringe {
@@ -98,14 +100,14 @@ struct Solver {
     std::vector<uint64_t> pre_states, pre_bits; std::vector<NoDupFringe::Item> pre_items;
     void prepop(); void unpop();
     // scratch of one wave (kept to avoid reallocations)
-    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars;
+    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt;
 
     Solver(Engine* e, int model_kind, const uint64_t* root_state, int64_t root_value, int wk, uint64_t w, int ws);
     int init(bool push_root);
     int wave(const volatile int32_t* cutoff_flag, int64_t out3[3]);
     int maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact, int32_t* has_value, int64_t* best_value);
     void finish();
-    void full_path(int32_t rec, const uint64_t* bits, std::vector<ddo_decision>& out) const;
+    void full_path(int32_t rec, const uint64_t* bits, int32_t depth, std::vector<ddo_decision>& out) const;
     int retain_share(int rank, int nranks);
 };
 

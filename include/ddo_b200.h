@@ -118,6 +118,7 @@ int ddo_mdd_best_solution(ddo_mdd*, int32_t index, int32_t exact, ddo_decision* 
  * Emits, in cutset order, every MARKED cutset node whose ub' = min(ub, ub_cap) is > lb_filter (the filter of parallel.rs:460-461; pass
  * INT64_MAX / INT64_MIN to disable): states (count x words), values, ubs, and the decisions from the DD root to the node (path_len each,
  * same for all nodes of a LEL cutset; terminal->root order like clean.rs:329-343).  *count in: capacity, out: number emitted. */
+/* (LAST_EXACT_LAYER engines; a FRONTIER engine answers DDO_ERR_UNSUPPORTED: its nodes have different depths, see the batch form.) */
 int ddo_mdd_drain_cutset(ddo_mdd*, int32_t index, int64_t ub_cap, int64_t lb_filter, uint64_t* states, int64_t* values, int64_t* ubs,
                          int32_t* depth_out, int32_t* path_len_out, ddo_decision* paths, int32_t* count);
 /* drain_cutset for DDs 0..count-1 of the last RELAXED batch at once (what the wave solver uses): DD i emits its MARKED cutset nodes with
@@ -126,6 +127,11 @@ int ddo_mdd_drain_cutset(ddo_mdd*, int32_t index, int64_t ub_cap, int64_t lb_fil
  * of the owning DD; its variables come from ddo_mdd_layer_trace).  Any output pointer may be NULL. */
 int ddo_mdd_drain_cutset_batch(ddo_mdd*, int32_t count, const int64_t* ub_caps, const int64_t* lb_filters, uint64_t* states, int64_t* values,
                                int64_t* ubs, int32_t* dd_index, uint64_t* path_bits, int32_t* path_words, int64_t* total);
+/* Layer (inside its owning DD) of every record of the last ddo_mdd_drain_cutset_batch: the depth of record r is root_depth[dd_index[r]] +
+ * layer_index[r] and its path has layer_index[r] decisions.  A LAST_EXACT_LAYER cutset has one layer per DD (clean.rs:566-583); the nodes of
+ * a FRONTIER cutset (clean.rs:586-606: every exact node with an edge into an inexact node) come from different layers and are emitted in the
+ * canonical order (layer descending, position in the layer ascending).  Returns the number of records (< 0: error). */
+int ddo_mdd_drain_layer_index(ddo_mdd*, int32_t* layer_index, int64_t cap);
 /* per-kernel device time (CUDA events around every launch; slows the launch loop, off by default).  kernel ids: 0 k_expand, 1 k_finish,
  * 2 k_compact, 3 k_finalize+k_bottomup, 4 drain kernels, 5 k_small.  Times accumulate until reset (on != 0 also resets). */
 int ddo_mdd_set_profiling(ddo_mdd*, int32_t on);

@@ -359,6 +359,7 @@ public:
         std::optional<isize> theta;
         NodeFlags flags;
         size_t depth;
+        size_t pos = 0;   // position in its layer after the cut (canonical order C1/C3); not a field of the reference's Node
     };
     struct Edge { NodeId from, to; Decision decision; isize cost; };  // clean.rs:74-85
     struct EdgesList { bool cons; size_t head, tail; };                // clean.rs:89-92
@@ -378,6 +379,13 @@ public:
     template <class F>
     void drain_cutset(F func) {  // clean.rs:417-445
         auto bv = best_value();
+        if (cutset_type_ == FRONTIER)
+            // C7: the reference pushes frontier nodes in the order its bottom-up edge walk meets them (clean.rs:586-606), which inherits the
+            // hash order of the layers; canonically they are drained by (layer descending, position in the layer ascending)
+            std::stable_sort(cutset.begin(), cutset.end(), [&](NodeId a, NodeId b) {
+                if (nodes[a].depth != nodes[b].depth) return nodes[a].depth > nodes[b].depth;
+                return nodes[a].pos < nodes[b].pos;
+            });
         if (bv) {
             for (NodeId id : cutset) {
                 const Node& node = nodes[id];
@@ -664,6 +672,7 @@ private:
         if (!layers.empty()) _filter_with_cache(input, curr_l);
         _filter_with_dominance(input, curr_l);
         _squash_if_needed(input, curr_l);
+        for (size_t i = 0; i < curr_l.size(); ++i) nodes[curr_l[i]].pos = i;
         if (layers.empty()) layers.push_back(Layer{0, nodes.size()});
         else layers.push_back(Layer{layers.back().to, nodes.size()});
         return true;

@@ -11,9 +11,10 @@ from ddo_b200 import _native as N
 CT = {O.EXACT: CompilationType.Exact, O.RELAXED: CompilationType.Relaxed, O.RESTRICTED: CompilationType.Restricted}
 
 
-def compare_dd(oracle: O.OracleMisp, mdd: GpuMdd, index: int, comp_type: int, width: int, root_state, root_value, root_depth, best_lb, check_paths=True):
+def compare_dd(oracle: O.OracleMisp, mdd: GpuMdd, index: int, comp_type: int, width: int, root_state, root_value, root_depth, best_lb, check_paths=True,
+               cutset_type=O.LEL):
     """Assert device DD `index` of the last batch == oracle DD on the same CompilationInput. Returns the oracle result."""
-    ref = oracle.compile(comp_type, width, root_state, root_value, root_depth, best_lb, want_paths=check_paths)
+    ref = oracle.compile(comp_type, width, root_state, root_value, root_depth, best_lb, cutset_type=cutset_type, want_paths=check_paths)
     c = mdd._last[index]
     ctx = f"comp={comp_type} W={width} depth={root_depth} lb={best_lb}"
     assert (c.best_value is not None) == bool(ref["has_best"]), ctx
@@ -48,13 +49,14 @@ def compare_dd(oracle: O.OracleMisp, mdd: GpuMdd, index: int, comp_type: int, wi
     return ref
 
 
-def check_instance(inst, widths, comp_types=(O.RESTRICTED, O.RELAXED), best_lbs=(N.I64_MIN,), batch=None, roots=None, check_paths=True, model="misp"):
+def check_instance(inst, widths, comp_types=(O.RESTRICTED, O.RELAXED), best_lbs=(N.I64_MIN,), batch=None, roots=None, check_paths=True, model="misp",
+                   cutset_type=O.LEL):
     """Compile the given roots (default: the problem root) for every width / type / best_lb, batched on the device, and compare each DD."""
     oracle = O.OracleMisp(inst) if model == "misp" else O.OracleM2s(inst)
     pb = Misp(inst) if model == "misp" else Max2Sat(inst)
     roots = roots or [SubProblem(inst.initial_state(), pb.initial_value(), [], N.I64_MAX, 0)]
     jobs = [(w, r) for w in widths for r in roots]
-    mdd = GpuMdd(pb, max(max(widths), 2), batch or len(jobs))
+    mdd = GpuMdd(pb, max(max(widths), 2), batch or len(jobs), cutset_type=cutset_type)
     n = 0
     try:
         for ct in comp_types:
@@ -63,7 +65,7 @@ def check_instance(inst, widths, comp_types=(O.RESTRICTED, O.RELAXED), best_lbs=
                     chunk = jobs[s : s + mdd.batch_cap]
                     mdd.compile_batch(CT[ct], [w for w, _ in chunk], [r for _, r in chunk], lb)
                     for i, (w, r) in enumerate(chunk):
-                        compare_dd(oracle, mdd, i, ct, w, r.state, r.value, r.depth, lb, check_paths)
+                        compare_dd(oracle, mdd, i, ct, w, r.state, r.value, r.depth, lb, check_paths, cutset_type)
                         n += 1
     finally:
         mdd.close()

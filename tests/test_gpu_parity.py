@@ -64,8 +64,8 @@ def test_error_behaviour_matches_reference():
     # infeasible / fully pruned: best_lb above every bound -> Ok(Completion{best_value: None}) (clean.rs:1669-1749)
     c = mdd.compile(CompilationType.Relaxed, 4, root, best_lb=1000)
     assert c.best_value is None and c.expanded == 0
-    with pytest.raises(N.DdoError):
-        GpuMdd(pb, 16, 1, cutset_type=N.FRONTIER)
+    with pytest.raises(N.DdoError):  # only LAST_EXACT_LAYER = 1 and FRONTIER = 2 exist (mdd.rs:24-28; the reference panics at clean.rs:559)
+        GpuMdd(pb, 16, 1, cutset_type=3)
 
 
 FAST = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "c-fat200-5"]
