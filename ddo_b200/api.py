@@ -319,7 +319,7 @@ class GpuMdd:
             if with_paths:  # terminal -> root order like clean.rs:329-343
                 for t in range(tt - 1, -1, -1):
                     b = int((int(bits[i, t >> 6]) >> (t & 63)) & 1)
-                    p.append(Decision(int(vars_[t]), b))  # MISP: YES = 1, NO = 0
+                    p.append(Decision(int(vars_[t]), (b if isinstance(self.problem, Misp) else 2 * b - 1)))  # MISP: YES = 1 / NO = 0; MAX2SAT: T = 1 / F = -1
             res.append(SubProblem(out["states"][i].copy(), int(out["values"][i]), p, int(out["ubs"][i]), root.depth + tt))
         return res
 

@@ -86,6 +86,18 @@ static int dev_alloc(Engine* E, T** p, size_t count) {
 #define ALLOC(ptr, count)                                   \
     do { int _r = dev_alloc(this, &(ptr), (size_t)(count)); if (_r != DDO_OK) return _r; } while (0)
 
+// every node above the terminal layer may be a frontier node; the drain buffers hold DDO_FC_OUT_FACTOR (default 8) layers' worth
+int Engine::alloc_frontier(uint32_t** node, int32_t** ub, int32_t** aux, unsigned long long* cap) {
+    *cap = (unsigned long long)(Lmax - 1) * Wcap;
+    const size_t KF = (size_t)K * *cap, KW = (size_t)K * Wcap;
+    ALLOC(*node, KF); ALLOC(*ub, KF); ALLOC(*aux, KF);
+    int factor = 8;
+    if (const char* e = getenv("DDO_FC_OUT_FACTOR")) factor = std::max(1, atoi(e));
+    out_cap = std::min(KF, std::max<size_t>(KW * (size_t)factor, 1u << 16));
+    ALLOC(d_out.tt, out_cap);
+    return DDO_OK;
+}
+
 int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batch_cap, int cutset) {
     if (!m || batch_cap < 1 || max_width_cap < 1) { set_error("ddo_mdd_create: invalid argument"); return DDO_ERR_INVALID; }
     if (cutset != DDO_LAST_EXACT_LAYER && cutset != DDO_FRONTIER) { set_error("cutset_type must be DDO_LAST_EXACT_LAYER or DDO_FRONTIER (mdd.rs:24-28)"); return DDO_ERR_INVALID; }
@@ -135,16 +147,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     // drain buffers
     out_cap = KW;
     ev.fc_node = nullptr; ev.fc_ub = nullptr; ev.fc_aux = nullptr; ev.fc_cap = 0; d_out.tt = nullptr;
-    if (cutset == DDO_FRONTIER) {
-        // every node above the terminal layer may be a frontier node; the drain buffers hold DDO_FC_OUT_FACTOR (default 8) layers' worth
-        ev.fc_cap = (unsigned long long)(Lmax - 1) * Wcap;
-        const size_t KF = (size_t)K * ev.fc_cap;
-        ALLOC(ev.fc_node, KF); ALLOC(ev.fc_ub, KF); ALLOC(ev.fc_aux, KF);
-        int factor = 8;
-        if (const char* e = getenv("DDO_FC_OUT_FACTOR")) factor = std::max(1, atoi(e));
-        out_cap = std::min(KF, std::max<size_t>(KW * (size_t)factor, 1u << 16));
-        ALLOC(d_out.tt, out_cap);
-    }
+    if (cutset == DDO_FRONTIER) { int fr = alloc_frontier(&ev.fc_node, &ev.fc_ub, &ev.fc_aux, &ev.fc_cap); if (fr != DDO_OK) return fr; }
     ALLOC(d_out.state, out_cap * S); ALLOC(d_out.val, out_cap); ALLOC(d_out.ub, out_cap); ALLOC(d_out.dd, out_cap); ALLOC(d_out.path, out_cap * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
@@ -516,6 +519,17 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
     return total;
 }
 
+void Engine::fc_launch_count(int count) { k_fc_count<EV><<<last_count, 1024, 0, stream>>>(ev, d_out, d_ub_cap, d_lb_filter, count); }
+void Engine::fc_launch_write(int pw) {
+    const dim3 grid(64, last_count);
+    switch (S) {
+        case 2: k_fc_write<2><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 4: k_fc_write<4><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        case 8: k_fc_write<8><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+        default: k_fc_write<16><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
+    }
+}
+
 // The same for a FRONTIER engine (frontier.cuh): the records of a DD come from different layers, h_out_tt holds the layer of each.
 int Engine::drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw_out) {
     int rc = fetch_ctl(last_count);
@@ -531,7 +545,7 @@ int Engine::drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* 
     CUDA_TRY(cudaMemcpyAsync(d_ub_cap, caps, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_lb_filter, caps + K, (size_t)K * 8, cudaMemcpyHostToDevice, stream));
     prof_mark(-1);
-    k_fc_count<<<last_count, 1024, 0, stream>>>(ev, d_out, d_ub_cap, d_lb_filter, count);
+    fc_launch_count(count);
     k_cutset_offsets<<<1, 32, 0, stream>>>(d_out, last_count);
     g_kernel_launches += 2;
     bytes_d2h += (unsigned long long)((size_t)(last_count + 1) * 4); CUDA_TRY(cudaMemcpyAsync(h_counts, d_out.offset, (size_t)(last_count + 1) * 4, cudaMemcpyDeviceToHost, stream));
@@ -539,13 +553,7 @@ int Engine::drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* 
     const int total = ((int32_t*)h_counts)[last_count];
     if (total == 0) { prof_used = 0; return 0; }
     if ((size_t)total > out_cap) { prof_used = 0; set_error("frontier cutset larger than the drain buffers (raise DDO_FC_OUT_FACTOR)"); return DDO_ERR_CAPACITY; }
-    const dim3 grid(64, last_count);
-    switch (S) {
-        case 2: k_fc_write<2><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
-        case 4: k_fc_write<4><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
-        case 8: k_fc_write<8><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
-        default: k_fc_write<16><<<grid, 256, 0, stream>>>(ev, d_out, d_ub_cap, pw); break;
-    }
+    fc_launch_write(pw);
     ++g_kernel_launches;
     prof_mark(4);
     if (!h_out_state) {

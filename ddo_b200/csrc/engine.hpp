@@ -166,7 +166,10 @@ struct Engine {
     int layer_trace(int index, int32_t* vars, int32_t* widths, int cap);
     // batched drain for the solver: records of every DD in h_out_*; returns total (<0 error); *pw = uint64 words of path bits per record
     virtual int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);
-    int drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);  // MISP engine, DDO_FRONTIER
+    int drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw);  // DDO_FRONTIER engines
+    virtual void fc_launch_count(int count);   // the model's frontier drain kernels (frontier.cuh / m2s_frontier.cuh)
+    virtual void fc_launch_write(int pw);
+    int alloc_frontier(uint32_t** node, int32_t** ub, int32_t** aux, unsigned long long* cap);  // record arrays + drain buffers sized for a frontier
     // shared-memory fast path: every staged root compiled by one CTA (exact DDs only); results in h_small[0..count)
     int small_ws_first = 64;  // first-tier capacity of the fast path (more CTAs per SM); 0 = single tier
     int small_ws = 256; SmallOut* d_small = nullptr; SmallOut* h_small = nullptr; bool small_attr_set = false;

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) k_fc_eval(EV ev) {
 // =================================================================================================================
 // drain: count (the solver's filter min(ub, ub_cap) > lb_filter, parallel.rs:460-461) -> offsets (k_cutset_offsets) -> write
 // =================================================================================================================
-static __global__ void __launch_bounds__(1024, 1) k_fc_count(EV ev, DrainOut o, const long long* ub_cap, const long long* lb_filter, int count) {
+template <class EVT>
+__global__ void __launch_bounds__(1024, 1) k_fc_count(EVT ev, DrainOut o, const long long* ub_cap, const long long* lb_filter, int count) {
     __shared__ int scan[40];
     const int k = blockIdx.x;
     const DDCtl* ctl = ev.ctl + k;

@@ -1,5 +1,6 @@
 // m2s_engine.cu -- host side of the MAX2SAT device model: instance tables in HBM, arenas, the per-layer launch loop.
 #include "m2s_kernels.cuh"
+#include "m2s_frontier.cuh"
 #include "m2s_engine.hpp"
 
 #include <algorithm>
@@ -146,8 +147,11 @@ static int dev_alloc(Engine* E, T** p, size_t count) {
 
 int M2Engine::create_m2s(const M2Model* m, int dev, uint64_t max_width_cap, int batch_cap, int cutset) {
     if (!m || batch_cap < 1 || max_width_cap < 1) { set_error("ddo_mdd_create: invalid argument"); return DDO_ERR_INVALID; }
-    if (cutset != DDO_LAST_EXACT_LAYER) { set_error("device engine implements the LAST_EXACT_LAYER cutset only (FRONTIER: see DESIGN.md, next)"); return DDO_ERR_UNSUPPORTED; }
+    if (cutset != DDO_LAST_EXACT_LAYER && cutset != DDO_FRONTIER) { set_error("cutset_type must be DDO_LAST_EXACT_LAYER or DDO_FRONTIER (mdd.rs:24-28)"); return DDO_ERR_INVALID; }
     if (max_width_cap > (1u << 24)) { set_error("max_width_cap too large"); return DDO_ERR_INVALID; }
+    if (cutset == DDO_FRONTIER && (max_width_cap + 2 >= (1u << FC_POS_BITS) || (uint64_t)(m->n + 1) * (max_width_cap + 2) >= (1ull << 30))) {
+        set_error("FRONTIER cutset: max_width_cap * (n + 1) must stay below 2^30 frontier records per DD"); return DDO_ERR_UNSUPPORTED;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (there is no CPU fallback)"); return DDO_ERR_NO_DEVICE; }
     if (dev != m->device) { set_error("model and mdd must live on the same device"); return DDO_ERR_INVALID; }
@@ -183,7 +187,10 @@ int M2Engine::create_m2s(const M2Model* m, int dev, uint64_t max_width_cap, int 
     ALLOC(v.lel_state, KW * NW); ALLOC(v.lel_val, KW); ALLOC(v.lel_rub, KW);
     ALLOC(v.cs_ub, KW); ALLOC(v.cs_marked, KW);
     ALLOC(v.best_path, (size_t)K * PW); ALLOC(v.best_exact_path, (size_t)K * PW);
-    ALLOC(d_out.state, KW * S); ALLOC(d_out.val, KW); ALLOC(d_out.ub, KW); ALLOC(d_out.dd, KW); ALLOC(d_out.path, KW * PW);
+    out_cap = KW;
+    v.fc_node = nullptr; v.fc_ub = nullptr; v.fc_aux = nullptr; v.fc_cap = 0; d_out.tt = nullptr;
+    if (cutset == DDO_FRONTIER) { int fr = alloc_frontier(&v.fc_node, &v.fc_ub, &v.fc_aux, &v.fc_cap); if (fr != DDO_OK) return fr; }
+    ALLOC(d_out.state, out_cap * S); ALLOC(d_out.val, out_cap); ALLOC(d_out.ub, out_cap); ALLOC(d_out.dd, out_cap); ALLOC(d_out.path, out_cap * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     // what the base class reads (fetch_ctl, best_solution, layer_trace, fetch_vars)
@@ -275,7 +282,17 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
     if (rc == DDO_OK) {
         m2_finalize<<<(count + 63) / 64, 64, 0, st>>>(v, count);
         ++g_kernel_launches;
-        if (relaxed) { m2_bottomup<<<count, 1024, 0, st>>>(v); ++g_kernel_launches; }
+        if (relaxed && cutset_type == DDO_FRONTIER) {  // clean.rs:586-606 + 448-475 in one sweep, then the upper bound of every member
+            m2_fc_sweep<<<count, 1024, 0, st>>>(v);
+            const dim3 eg(64, count);
+            switch (ch) {
+                case 1: m2_fc_eval<1><<<eg, 256, 0, st>>>(v); break;
+                case 2: m2_fc_eval<2><<<eg, 256, 0, st>>>(v); break;
+                case 3: case 4: m2_fc_eval<4><<<eg, 256, 0, st>>>(v); break;
+                default: m2_fc_eval<8><<<eg, 256, 0, st>>>(v); break;
+            }
+            g_kernel_launches += 2;
+        } else if (relaxed) { m2_bottomup<<<count, 1024, 0, st>>>(v); ++g_kernel_launches; }
         prof_mark(3);
     }
     CUDA_TRY(cudaGetLastError());
@@ -287,9 +304,21 @@ int M2Engine::compile_staged(int count, int comp_type, int64_t best_lb, const vo
     return rc;
 }
 
+void M2Engine::fc_launch_count(int count) { k_fc_count<M2EV><<<last_count, 1024, 0, stream>>>(mv, d_out, d_ub_cap, d_lb_filter, count); }
+void M2Engine::fc_launch_write(int pw) {
+    const dim3 grid(64, last_count);
+    switch ((mv.NW4 + 31) / 32) {
+        case 1: m2_fc_write<1><<<grid, 256, 0, stream>>>(mv, d_out, d_ub_cap, pw); break;
+        case 2: m2_fc_write<2><<<grid, 256, 0, stream>>>(mv, d_out, d_ub_cap, pw); break;
+        case 3: case 4: m2_fc_write<4><<<grid, 256, 0, stream>>>(mv, d_out, d_ub_cap, pw); break;
+        default: m2_fc_write<8><<<grid, 256, 0, stream>>>(mv, d_out, d_ub_cap, pw); break;
+    }
+}
+
 int M2Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw_out) {
     if (last_comp_type != DDO_RELAXED) { set_error("drain_cutset: the last batch was not a relaxed compilation (mdd.rs:103-110)"); return DDO_ERR_INVALID; }
     if (count > last_count) { set_error("drain_cutset: bad count"); return DDO_ERR_INVALID; }
+    if (cutset_type == DDO_FRONTIER) return drain_all_frontier(count, ub_cap, lb_filter, pw_out);
     int rc = fetch_ctl(last_count);
     if (rc != DDO_OK) return rc;
     int max_lel = 0;

@@ -44,6 +44,7 @@ struct M2EV {
     int32_t* lel_state; int32_t* lel_val; int32_t* lel_rub;
     int32_t* vb[2]; int32_t* cs_ub; uint8_t* cs_marked;
     uint64_t* best_path; uint64_t* best_exact_path;
+    uint32_t* fc_node; int32_t* fc_ub; int32_t* fc_aux; unsigned long long fc_cap;  // FRONTIER cutset records, as in EV (m2s_frontier.cuh)
 };
 
 
@@ -55,6 +56,8 @@ struct M2Engine : Engine {
     int reserve_roots(int count) override;
     int compile_staged(int count, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) override;
     int drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter, int* pw) override;
+    void fc_launch_count(int count) override;
+    void fc_launch_write(int pw) override;
 };
 
 int model_create_max2sat(int32_t n, int64_t m, const int64_t* clauses, int device, M2Model** out);

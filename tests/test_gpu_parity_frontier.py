@@ -1,4 +1,5 @@
-"""GPU parity tests of the FRONTIER cutset (clean.rs:586-606): the device sweep (ddo_b200/csrc/frontier.cuh) against the CPU oracle, bit-exact.
+"""GPU parity tests of the FRONTIER cutset (clean.rs:586-606): the device sweeps (ddo_b200/csrc/frontier.cuh, m2s_frontier.cuh) against the CPU
+oracle, bit-exact, for both device models.
 
 Compared per relaxed DD: the frontier node set in canonical order (layer descending, position ascending), every node's state (re-derived on
 the device by replaying its best path), value_top, upper bound min(value_top + rub, value_top + value_bot, best_value), depth and path;
@@ -9,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from ddo_b200 import CompilationType, FixedWidth, GpuMdd, Max2Sat, Misp, NbUnassignedWidth, ParNoCachingSolverFc, SubProblem, gnp, parse_dimacs, random_max2sat
+from ddo_b200 import CompilationType, FixedWidth, GpuMdd, Max2Sat, Misp, NbUnassignedWidth, ParNoCachingSolverFc, SubProblem, gnp, parse_dimacs, random_max2sat, read_wcnf
 from ddo_b200 import _native as N
 from parity_util import check_instance
 
@@ -104,9 +105,49 @@ def test_frontier_solver_fixed_width_matches_oracle_trace():
     assert sol == ref["solution"]
 
 
-def test_frontier_is_not_built_for_the_max2sat_device_model_yet():
-    pb = Max2Sat(random_max2sat(20, 60, 1))
-    with pytest.raises(N.DdoError) as e:
-        GpuMdd(pb, 16, 1, cutset_type=N.FRONTIER)
-    assert e.value.code == N.ERR_UNSUPPORTED
-    pb.close()
+# ---- MAX2SAT device model (m2s_frontier.cuh) ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,m,seed", [(3, 4, 1), (9, 30, 2), (16, 60, 3), (33, 150, 4), (61, 400, 5), (130, 900, 6)])
+def test_frontier_max2sat_dd_parity_all_widths(n, m, seed):
+    inst = random_max2sat(n, m, seed)
+    widths = [1, 2, 3, 5, 8, 13, 50, 300]
+    lo = O.OracleM2s(inst).compile(O.RESTRICTED, 3)["best_value"]
+    cnt = check_instance(inst, widths, best_lbs=(N.I64_MIN, lo - 3, lo + 2), model="m2s", cutset_type=O.FRONTIER)
+    assert cnt == len(widths) * 2 * 3
+
+
+def test_frontier_max2sat_ties_and_reference_fixtures(golden_dir):
+    for seed in (7, 8):
+        check_instance(random_max2sat(24, 40, seed, max_weight=1), [1, 2, 4, 7, 16, 64], model="m2s", cutset_type=O.FRONTIER)
+    for name, widths in (("debug2", [1, 2, 8]), ("pass", [1, 2, 3, 50]), ("negative_wt", [1, 4]), ("frb10-6-1", [1, 4, 25, 150])):
+        check_instance(read_wcnf(golden_dir / "max2sat" / f"{name}.wcnf"), widths, model="m2s", cutset_type=O.FRONTIER)
+
+
+def test_frontier_max2sat_subproblem_roots():
+    inst = random_max2sat(70, 500, 21)
+    oracle = O.OracleM2s(inst)
+    ref = oracle.compile(O.RELAXED, 12, cutset_type=O.FRONTIER)
+    roots = [SubProblem(ref["cutset_states"][i].copy(), int(ref["cutset_values"][i]), [], int(ref["cutset_ubs"][i]), int(ref["cutset_depths"][i]))
+             for i in range(min(ref["cutset_size"], 24))]
+    assert len(roots) >= 5 and len({r.depth for r in roots}) > 1
+    lo = oracle.compile(O.RESTRICTED, 5)["best_value"]
+    check_instance(inst, [3, 12], roots=roots, best_lbs=(N.I64_MIN, lo), check_paths=False, model="m2s", cutset_type=O.FRONTIER)
+
+
+def test_frontier_max2sat_full_state_size():
+    """BASELINE config 3's state size (500 variables, 2 KB rows) at a width the oracle finishes in seconds."""
+    check_instance(random_max2sat(500, 3000, 1), [8], comp_types=(O.RELAXED,), model="m2s", check_paths=False, cutset_type=O.FRONTIER)
+
+
+@pytest.mark.parametrize("n,m,seed,width,K", [(25, 100, 3, 4, 8), (35, 200, 5, 10, 16), (40, 250, 6, 16, 16)])
+def test_frontier_max2sat_solver_trajectory(n, m, seed, width, K):
+    inst = random_max2sat(n, m, seed)
+    s = ParNoCachingSolverFc(Max2Sat(inst), FixedWidth(width), wave_size=K)
+    comp = s.maximize()
+    ref = O.OracleM2s(inst).solve("wave", k=K, width=width, cutset_type=O.FRONTIER)
+    st = s.stats()
+    assert comp.is_exact and comp.best_value == ref["best_value"] == O.OracleM2s(inst).solve("wave", k=K, width=width)["best_value"]
+    assert s.best_lower_bound() == s.best_upper_bound() == ref["best_value"]
+    assert (s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"])) == \
+           (ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"], ref["waves"])
+    assert [(d.variable, d.value) for d in s.best_solution()] == ref["solution"]
