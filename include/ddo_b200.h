@@ -27,7 +27,7 @@ extern "C" {
 #define DDO_ERR_INVALID (-1)    /* bad argument (the reference panics: e.g. max_width == 0 underflows at clean.rs:827) */
 #define DDO_ERR_CUDA (-2)       /* CUDA runtime failure; ddo_last_error() has the text */
 #define DDO_ERR_CAPACITY (-3)   /* a layer (Exact compilation) or a batch outgrew the arenas given to ddo_mdd_create */
-#define DDO_ERR_UNSUPPORTED (-4)/* feature outside the device model (e.g. FRONTIER cutset, value range > 31 bits) */
+#define DDO_ERR_UNSUPPORTED (-4)/* feature outside the device model (e.g. value range > 31 bits, n > 1024) */
 #define DDO_ERR_NO_DEVICE (-5)  /* no CUDA device: there is NO CPU fallback */
 
 /* ---- enums (values follow the reference) --------------------------------- */
