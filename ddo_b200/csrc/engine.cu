@@ -152,6 +152,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
+    if (const char* e = getenv("DDO_PDL")) pdl_enabled = atoi(e) != 0;
     if (cutset == DDO_FRONTIER) dual_enabled = false;  // the twin's logs start at its fork layer; the frontier sweep reads whole DDs
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     if (const char* e = getenv("DDO_SMALL_WS_FIRST")) { int v = atoi(e); if (v == 0 || v == 32 || v == 64 || v == 128) small_ws_first = v; }
@@ -245,6 +246,18 @@ int Engine::prof_collect() {
     return DDO_OK;
 }
 
+// launch with (pdl) or without programmatic stream serialization: see pdl_enter() in kernels.cuh
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // `count` DDs are initialised from the staged roots; `slots` (= count, or 2*count in dual mode) DD slots take part in every launch
 template <int S>
 static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag) {
@@ -278,15 +291,16 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     const long long max_tiles = (long long)slots * ((E->C + npb - 1) / npb);
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = 16;
+    const bool pdl = E->pdl_enabled && !E->profiling;  // the profiling events between launches serialise the stream anyway
     for (int t = 0; t < E->Lmax; ++t) {
-        if (use_cl) k_finish_cl<S><<<slots * FCL_CS, FCL_NT, E->finish_cl_smem, st>>>(ev, t, E->finish_cl_kcap);
-        else k_finish<S><<<slots, 1024, E->finish_smem, st>>>(ev, t);
+        if (use_cl) CUDA_TRY(launch_k(pdl, k_finish_cl<S>, dim3(slots * FCL_CS), dim3(FCL_NT), E->finish_cl_smem, st, ev, t, E->finish_cl_kcap));
+        else CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(slots), dim3(1024), E->finish_smem, st, ev, t));
         E->prof_mark(1);
-        if (use_c1) k_compact1<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
-        else k_compact<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
+        if (use_c1) CUDA_TRY(launch_k(pdl, k_compact1<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
+        else CUDA_TRY(launch_k(pdl, k_compact<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         E->prof_mark(2);
-        if (use_e1) k_expand1<S><<<e1_grid, 256, e1_smem, st>>>(ev, t, slots);
-        else k_expand<S><<<flat_grid, 256, 0, st>>>(ev, t, slots);
+        if (use_e1) CUDA_TRY(launch_k(pdl, k_expand1<S>, dim3(e1_grid), dim3(256), e1_smem, st, ev, t, slots));
+        else CUDA_TRY(launch_k(pdl, k_expand<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         E->prof_mark(0);
         g_kernel_launches += 3; ++E->layer_steps;
         if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {

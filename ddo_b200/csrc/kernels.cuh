@@ -36,6 +36,14 @@ __device__ __forceinline__ uint64_t lex_word(uint64_t w) { return ~__brevll(w); 
 // is none.  Among sets of equal size BitSet::cmp is the lexicographic order of the ascending member lists, so (popcount, m1, m2) is an
 // order-preserving prefix of the ranking -- and a dense one: the first members of a late, sparse state say far more than the membership
 // of the 20 lowest vertices.
+// Programmatic dependent launch (the three kernels of a layer step are launched with programmatic stream serialization, engine.cu): wait
+// until the previous kernel of the stream has completed and its writes are visible, then let the NEXT kernel's CTAs become resident behind
+// this one so that they start the moment this grid drains (launch latency and CTA rasterisation leave the critical path of narrow batches).
+// Both instructions are no-ops in a grid launched without the attribute.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 template <int S> struct RankBits { static constexpr int RB = S <= 8 ? 9 : 10; };
 template <int S> __device__ __forceinline__ void rank_take(uint64_t w, int base, int& got, uint32_t& mk) {
     while (w && got < 2) { mk = (mk << RankBits<S>::RB) | (uint32_t)(base + __ffsll((long long)w) - 1); ++got; w &= w - 1; }
@@ -206,6 +214,7 @@ __device__ __forceinline__ int plan_find(const int* off, int count, int tile) {
 #endif
 template <int S>
 __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, int count) {
+    pdl_enter();
     constexpr int G = S / 2;          // lanes per node, each owning one 128-bit chunk (two words)
     constexpr int NPB = 256 / G;      // nodes per tile
     constexpr int RP = G >= 8 ? 1 : 8 / G;  // claimed rows per 128 bytes of the staging buffer (bank swizzle below)
@@ -398,6 +407,7 @@ __global__ void __launch_bounds__(256, DDO_EXPAND_MINB) k_expand(EV ev, int t, i
 #endif
 template <int S>
 __global__ void __launch_bounds__(256, DDO_EXPAND1_MINB) k_expand1(EV ev, int t, int count) {
+    pdl_enter();
     constexpr int G = S / 2;                 // 128-bit chunks per state
     constexpr int PLAN = 256 / G;            // nodes per tile of the work plan (written by k_finish for k_expand's geometry)
     constexpr int RP = G >= 8 ? 1 : 8 / G;   // bank swizzle of the staged rows, as in k_expand
@@ -997,6 +1007,7 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
 
 template <int S>
 __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
+    pdl_enter();
     __shared__ FinishSmem sm;
     __shared__ int s_last;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1451,6 +1462,7 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
 
 template <int S>
 __global__ void __cluster_dims__(FCL_CS, 1, 1) __launch_bounds__(FCL_NT) k_finish_cl(EV ev, int t, int kcap) {
+    pdl_enter();
     __shared__ FinishClSmem sm;
     __shared__ int s_last;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1492,6 +1504,7 @@ __global__ void __cluster_dims__(FCL_CS, 1, 1) __launch_bounds__(FCL_NT) k_finis
 // =================================================================================================================
 template <int S>
 __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
+    pdl_enter();
     constexpr int G = S / 2;
     constexpr int CPB = 256 / G;
     const int* off = ev.tile_off_c;  // (L1-resident after the first lookups; staging it in shared memory measured slower)
@@ -1554,6 +1567,7 @@ __global__ void __launch_bounds__(256) k_compact(EV ev, int t, int count) {
 // =================================================================================================================
 template <int S>
 __global__ void __launch_bounds__(256) k_compact1(EV ev, int t, int count) {
+    pdl_enter();
     constexpr int G = S / 2;
     constexpr int CPB = 256 / G;        // candidates per tile of the work plan
     constexpr int UPT = CPB / 32;       // 32-candidate units per plan tile

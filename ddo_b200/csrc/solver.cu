@@ -76,42 +76,57 @@ bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
     states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); ver_.clear(); recycle_.clear();
     pending_.clear(); runs_.clear(); live_ = 0;
-    table_.clear(); table_used_ = 0;
+    for (Shard& sh : shards_) { std::fill(sh.tab.begin(), sh.tab.end(), -1); sh.used = 0; sh.live = 0; }  // the tables keep their size for the next search
 }
-void NoDupFringe::rehash(size_t min_cap) {
-    size_t cap = 1024;
+void NoDupFringe::rehash(Shard& sh, size_t min_cap) {
+    size_t cap = 256;
     while (cap < min_cap) cap <<= 1;
     std::vector<int> old;
-    old.swap(table_);
-    table_.assign(cap, -1); table_used_ = 0;
-    for (int id : old) if (id >= 0) table_insert(id);
+    old.swap(sh.tab);
+    sh.tab.assign(cap, -1); sh.used = 0;
+    const size_t mask = cap - 1;
+    for (int id : old)
+        if (id >= 0) {
+            size_t s = hash_[id] & mask;
+            while (sh.tab[s] >= 0) s = (s + 1) & mask;
+            sh.tab[s] = id; ++sh.used;
+        }
 }
 void NoDupFringe::table_insert(int id) {
-    const size_t mask = table_.size() - 1;
+    Shard& sh = shards_[shard_of(hash_[id])];
+    if ((sh.used + 1) * 2 > sh.tab.size()) rehash(sh, (sh.live + 1) * 4);
+    const size_t mask = sh.tab.size() - 1;
     size_t s = hash_[id] & mask;
-    while (table_[s] >= 0) s = (s + 1) & mask;
-    if (table_[s] == -1) ++table_used_;
-    table_[s] = id;
+    while (sh.tab[s] >= 0) s = (s + 1) & mask;
+    if (sh.tab[s] == -1) ++sh.used;
+    sh.tab[s] = id; ++sh.live;
 }
 int NoDupFringe::table_find(const uint64_t* st, uint64_t h, int32_t depth) const {
-    if (table_.empty()) return -1;
-    const size_t mask = table_.size() - 1;
+    const Shard& sh = shards_[shard_of(h)];
+    if (sh.tab.empty()) return -1;
+    const size_t mask = sh.tab.size() - 1;
     size_t s = h & mask;
-    while (table_[s] != -1) {
-        const int id = table_[s];
+    while (sh.tab[s] != -1) {
+        const int id = sh.tab[s];
         if (id >= 0 && hash_[id] == h && std::memcmp(state(id), st, (size_t)W * 8) == 0 && (kind_ != DDO_MODEL_MAX2SAT || items_[id].depth == depth)) return id;
         s = (s + 1) & mask;
     }
     return -1;
 }
 void NoDupFringe::table_erase(int id) {
-    const size_t mask = table_.size() - 1;
+    Shard& sh = shards_[shard_of(hash_[id])];
+    const size_t mask = sh.tab.size() - 1;
     size_t s = hash_[id] & mask;
-    while (table_[s] != id) s = (s + 1) & mask;
-    table_[s] = -2;
+    while (sh.tab[s] != id) s = (s + 1) & mask;
+    sh.tab[s] = -2; --sh.live;
 }
-void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
-    const uint64_t h = hash_state(st, W) ^ (kind_ == DDO_MODEL_MAX2SAT ? 0x9E3779B97F4A7C15ull * (uint64_t)(depth + 1) : 0ull);
+uint64_t NoDupFringe::key_hash(const uint64_t* st, int32_t depth) const {
+    return hash_state(st, W) ^ (kind_ == DDO_MODEL_MAX2SAT ? 0x9E3779B97F4A7C15ull * (uint64_t)(depth + 1) : 0ull);
+}
+// One push (no_duplicate.rs:88-140) against the shard of `h`.  Touches only that shard's table and the per-node slots of the node it finds
+// or of `new_id`, so pushes into different shards may run concurrently.
+int NoDupFringe::push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words,
+                          int new_id, std::vector<Ent>& pending) {
     const int found = table_find(st, h, depth);
     if (found >= 0) {  // Occupied, no_duplicate.rs:92-118: keep the longer path, ub = max of the known ubs
         const int id = found;
@@ -125,15 +140,10 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
             changed = true;
         }
         if (ub > old_ub) { items_[id].ub = ub; changed = true; }
-        if (changed) { ++ver_[id]; pending_.push_back(make_ent(id)); }  // re-keyed: the old entry goes stale
-        return;
+        if (changed) { ++ver_[id]; pending.push_back(make_ent(id)); }  // re-keyed: the old entry goes stale
+        return 0;
     }
-    int id;  // Vacant, no_duplicate.rs:119-135
-    if (recycle_.empty()) {
-        id = (int)items_.size();
-        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
-        states_.grow(); bits_.resize(bits_.size() + PW);
-    } else { id = recycle_.back(); recycle_.pop_back(); }
+    const int id = new_id;  // Vacant, no_duplicate.rs:119-135
     items_[id] = Item{value, ub, depth, rec};
     std::memcpy(states_.at(id), st, (size_t)W * 8);
     std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
@@ -143,10 +153,86 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     else for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
     popc_[id] = pc; hash_[id] = h;
     ++ver_[id];
-    if ((table_used_ + 1) * 2 > table_.size()) rehash((live_ + 1) * 4);
     table_insert(id);
-    pending_.push_back(make_ent(id));
-    ++live_;
+    pending.push_back(make_ent(id));
+    return 1;
+}
+void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
+    int id;
+    const bool fresh = recycle_.empty();
+    if (fresh) {
+        id = (int)items_.size();
+        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
+        states_.grow(); bits_.resize(bits_.size() + PW);
+    } else id = recycle_.back();
+    if (push_one(st, key_hash(st, depth), value, ub, depth, rec, bits, nbits_words, id, pending_)) {
+        if (!fresh) recycle_.pop_back();
+        ++live_;
+    } else if (fresh) recycle_.push_back(id);  // the slot was not needed: keep it for the next push
+}
+void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
+    const size_t n = recs.size();
+    const int T = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency()));
+    if (n < 8192) { for (const PushRec& r : recs) push(r.state, r.value, r.ub, r.depth, r.rec, r.bits, r.nbits_words); return; }
+    const double T0 = now_ms();
+    // hashes, then the records of every shard in record order (stable counting sort)
+    std::vector<uint64_t> h(n);
+    {
+        std::vector<std::thread> ts;
+        for (int w = 0; w < T; ++w)
+            ts.emplace_back([&, w] { for (size_t i = n * w / T; i < n * (w + 1) / T; ++i) h[i] = key_hash(recs[i].state, recs[i].depth); });
+        for (auto& t : ts) t.join();
+    }
+    std::vector<uint32_t> start(NS + 1, 0), order(n);
+    for (size_t i = 0; i < n; ++i) ++start[shard_of(h[i]) + 1];
+    for (int s = 0; s < NS; ++s) start[s + 1] += start[s];
+    {
+        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < n; ++i) order[fill[shard_of(h[i])]++] = (uint32_t)i;
+    }
+    const double T1 = now_ms();
+    // tentative node slot of every record, handed out in SHARD order so that the slots one thread writes are contiguous (no cache lines
+    // shared between threads): recycled slots first, then fresh ones; a record that hits an existing node leaves its slot unused
+    std::vector<int> slot(n);
+    const size_t nrec = std::min(n, recycle_.size());
+    const size_t base = items_.size(), fresh = n - nrec;
+    for (size_t q = 0; q < n; ++q) slot[order[q]] = q < fresh ? (int)(base + q) : recycle_[recycle_.size() - 1 - (q - fresh)];
+    recycle_.resize(recycle_.size() - nrec);
+    items_.resize(base + fresh); popc_.resize(base + fresh, 0); hash_.resize(base + fresh, 0); ver_.resize(base + fresh, 0);
+    for (size_t i = 0; i < fresh; ++i) states_.grow();
+    bits_.resize(bits_.size() + fresh * (size_t)PW);
+    const double T2 = now_ms();
+    std::vector<std::vector<Ent>> pend(T);
+    std::vector<std::vector<int>> unused(T);
+    std::vector<size_t> added(T, 0);
+    {
+        std::vector<std::thread> ts;
+        for (int w = 0; w < T; ++w)
+            ts.emplace_back([&, w] {
+                pend[w].reserve(n / T + 64);
+                size_t add = 0;  // thread-local: the per-thread result slots share cache lines
+                for (int s = w; s < NS; s += T) {
+                    Shard& sh = shards_[s];  // one growth step for the whole burst instead of a chain of doublings
+                    const size_t want = sh.used + (start[s + 1] - start[s]) + 1;
+                    if (want * 2 > sh.tab.size()) rehash(sh, std::max<size_t>(want * 2, (sh.live + (start[s + 1] - start[s]) + 1) * 4));
+                    for (uint32_t q = start[s]; q < start[s + 1]; ++q) {
+                        const uint32_t i = order[q];
+                        const PushRec& r = recs[i];
+                        if (push_one(r.state, h[i], r.value, r.ub, r.depth, r.rec, r.bits, r.nbits_words, slot[i], pend[w])) ++add;
+                        else unused[w].push_back(slot[i]);
+                    }
+                }
+                added[w] = add;
+            });
+        for (auto& t : ts) t.join();
+    }
+    const double T3 = now_ms();
+    for (int w = 0; w < T; ++w) {
+        pending_.insert(pending_.end(), pend[w].begin(), pend[w].end());
+        recycle_.insert(recycle_.end(), unused[w].begin(), unused[w].end());
+        live_ += added[w];
+    }
+    if (getenv("DDO_PUSH_TRACE")) std::fprintf(stderr, "push_many n=%zu hash+sort %.2f alloc %.2f insert %.2f merge %.2f ms\n", n, T1 - T0, T2 - T1, T3 - T2, now_ms() - T3);
 }
 void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
@@ -171,15 +257,22 @@ void NoDupFringe::flush_pending() {
     }
     runs_.emplace_back();
     runs_.back().swap(pending_);
-    if (runs_.size() > 24) {  // keep the number of runs bounded: merge everything, dropping stale entries
-        std::vector<Ent> all;
-        size_t total = 0;
-        for (auto& r : runs_) total += r.size();
-        all.reserve(total);
-        for (auto& r : runs_) for (const Ent& e : r) if (e.ver == ver_[e.id]) all.push_back(e);
-        std::sort(all.begin(), all.end(), [this](const Ent& a, const Ent& b) { return ent_less(a, b); });
-        runs_.clear();
-        runs_.push_back(std::move(all));
+    // Keep the runs few and geometrically sized (a pop looks at every run's tail): the newest run absorbs its predecessor while that one is
+    // at most twice its size, and beyond eight runs regardless -- O(n log n) merge work over a search, stale entries dropped on the way.
+    while (runs_.size() >= 2) {
+        std::vector<Ent>& x = runs_[runs_.size() - 2];
+        std::vector<Ent>& y = runs_.back();
+        if (x.size() > 2 * y.size() && runs_.size() <= 8) break;
+        std::vector<Ent> m;
+        m.reserve(x.size() + y.size());
+        size_t i = 0, j = 0;
+        while (i < x.size() || j < y.size()) {
+            const bool take_x = j == y.size() || (i < x.size() && !ent_less(y[j], x[i]));
+            const Ent& e = take_x ? x[i++] : y[j++];
+            if (e.ver == ver_[e.id]) m.push_back(e);
+        }
+        runs_.pop_back();
+        runs_.back().swap(m);
     }
 }
 int NoDupFringe::pop() {
@@ -194,6 +287,10 @@ int NoDupFringe::pop() {
     }
     const int id = runs_[best_run].back().id;
     runs_[best_run].pop_back();
+    if (runs_[best_run].size() >= 8) {  // the next pops most likely come from the same run: start fetching their node records and states
+        const int nid = runs_[best_run][runs_[best_run].size() - 8].id;
+        __builtin_prefetch(&items_[nid]); __builtin_prefetch(states_.at(nid)); __builtin_prefetch(&bits_[(size_t)nid * PW]);
+    }
     ++ver_[id];  // any other entry of this node is now stale
     recycle_.push_back(id);
     table_erase(id);
@@ -415,7 +512,8 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lmax, vars.begin() + (size_t)j * eng->Lmax + lel);
             }
             if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
-            for (int q = 0; q < PWN; ++q) p_bits.push_back(q < pw ? eng->h_out_path[(size_t)r * pw + q] : 0ull);
+            p_bits.resize(p_bits.size() + PWN, 0ull);
+            std::memcpy(&p_bits[p_bits.size() - PWN], &eng->h_out_path[(size_t)r * pw], (size_t)std::min(pw, PWN) * 8);
             p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
             p_tt.push_back(frontier ? eng->h_out_tt[r] : pend.back().lel);
             pend.back().count++;
@@ -533,6 +631,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
         t0 = now_ms();
         size_t var_off = 0;
+        push_recs.clear();
         for (const Pending& pd : pend) {
             PathRec pr;
             pr.parent_rec = w_items[pd.wave_index].rec;
@@ -545,9 +644,11 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 const size_t r = (size_t)pd.first + q;
                 if ((int64_t)p_ub[r] <= best_lb) continue;  // parallel.rs:461 with the final incumbent of the wave
                 if (rec_id < 0) { recs.push_back(pr); rec_id = (int)recs.size() - 1; }
-                fringe.push(p_direct ? &eng->h_out_state[r * (size_t)eng->S] : &p_states[r * W], p_val[r], p_ub[r], w_items[pd.wave_index].depth + p_tt[r], rec_id, &p_bits[r * PWN], (p_tt[r] + 63) / 64);
+                push_recs.push_back(NoDupFringe::PushRec{p_direct ? &eng->h_out_state[r * (size_t)eng->S] : &p_states[r * W], &p_bits[r * PWN], p_val[r], p_ub[r],
+                                                         w_items[pd.wave_index].depth + p_tt[r], rec_id, (p_tt[r] + 63) / 64});
             }
         }
+        fringe.push_many(push_recs);  // enqueue_cutset (parallel.rs:456-469) in wave order
         fringe_ms += now_ms() - t0;
     }
     if (trace_file)

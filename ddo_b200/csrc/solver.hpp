@@ -39,6 +39,11 @@ public:
     void clear();
     // no_duplicate.rs:88-140
     void push(const uint64_t* state, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words);
+    // A burst of pushes (the cutsets of a wide wave: hundreds of thousands of sub-problems), equivalent to push() of every record in order.
+    // Large bursts run on several host threads: the state index is split into NS shards by the top bits of the state hash, equal states
+    // fall into one shard and are handled by one thread in record order, so duplicates resolve exactly as in the sequential loop.
+    struct PushRec { const uint64_t* state; const uint64_t* bits; int32_t value, ub, depth, rec, nbits_words; };
+    void push_many(const std::vector<PushRec>& recs);
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
     const uint64_t* state(int id) const { return states_.at(id); }
@@ -68,8 +73,14 @@ private:
     std::vector<Ent> pending_;
     std::vector<std::vector<Ent>> runs_;
     size_t live_ = 0;
-    std::vector<int> table_;  // open addressing: node id or -1 (empty) / -2 (tombstone)
-    size_t table_used_ = 0;   // occupied + tombstones
+    // state index: NS open-addressing tables (node id, -1 empty, -2 tombstone), shard = top bits of the state hash
+    static constexpr int NS_BITS = 6, NS = 1 << NS_BITS;
+    struct alignas(128) Shard { std::vector<int> tab; size_t used = 0, live = 0; };  // used = occupied + tombstones; one cache-line pair per shard (threads own shards)
+    Shard shards_[NS];
+    static int shard_of(uint64_t h) { return (int)(h >> (64 - NS_BITS)); }
+    uint64_t key_hash(const uint64_t* st, int32_t depth) const;
+    int push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words, int new_id,
+                 std::vector<Ent>& pending);  // returns 1 when new_id was consumed (vacant entry), 0 when an existing node was updated
     Ent make_ent(int id) const;
     bool ent_less(const Ent& a, const Ent& b) const;  // a strictly below b in the MaxUB order
     int state_cmp(int a, int b) const;  // final tie-break of the ranking between two stored nodes
@@ -77,7 +88,7 @@ private:
     void table_insert(int id);
     int table_find(const uint64_t* st, uint64_t h, int32_t depth) const;
     void table_erase(int id);
-    void rehash(size_t min_cap);
+    void rehash(Shard& sh, size_t min_cap);
     static uint64_t hash_state(const uint64_t* st, int W);
 };
 
@@ -100,7 +111,7 @@ struct Solver {
     std::vector<uint64_t> pre_states, pre_bits; std::vector<NoDupFringe::Item> pre_items;
     void prepop(); void unpop();
     // scratch of one wave (kept to avoid reallocations)
-    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt;
+    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt; std::vector<NoDupFringe::PushRec> push_recs;
 
     Solver(Engine* e, int model_kind, const uint64_t* root_state, int64_t root_value, int wk, uint64_t w, int ws);
     int init(bool push_root);
