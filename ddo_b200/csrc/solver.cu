@@ -297,6 +297,43 @@ int NoDupFringe::pop() {
     --live_;
     return id;
 }
+// The next `k` nodes in pop() order at once (the workload of a wave, parallel.rs:500-559).  Knowing the ids ahead lets every random access
+// -- version words during the selection, then hash, index slot, node record, state and path bits -- be prefetched a few nodes ahead
+// instead of being paid as a chain of cache misses per pop.
+int NoDupFringe::pop_many(int k, std::vector<int>& ids) {
+    ids.clear();
+    if (live_ == 0 || k <= 0) return 0;
+    flush_pending();
+    while ((int)ids.size() < k && ids.size() < live_) {
+        int best_run = -1;
+        for (size_t r = 0; r < runs_.size(); ++r) {
+            auto& run = runs_[r];
+            while (!run.empty() && run.back().ver != ver_[run.back().id]) run.pop_back();  // stale
+            if (run.empty()) continue;
+            if (best_run < 0 || ent_less(runs_[best_run].back(), run.back())) best_run = (int)r;
+        }
+        auto& run = runs_[best_run];
+        const int id = run.back().id;
+        run.pop_back();
+        if (run.size() >= 12) __builtin_prefetch(&ver_[run[run.size() - 12].id]);
+        ++ver_[id];  // any other entry of this node is now stale
+        ids.push_back(id);
+    }
+    const size_t n = ids.size();
+    for (size_t i = 0; i < n; ++i) {
+        if (i + 12 < n) __builtin_prefetch(&hash_[ids[i + 12]]);
+        if (i + 6 < n) {
+            const uint64_t h = hash_[ids[i + 6]];
+            const Shard& sh = shards_[shard_of(h)];
+            __builtin_prefetch(&sh.tab[h & (sh.tab.size() - 1)]);
+            prefetch(ids[i + 6]);
+        }
+        recycle_.push_back(ids[i]);
+        table_erase(ids[i]);
+    }
+    live_ -= n;
+    return (int)n;
+}
 // ---------------------------------------------------------------------------------------------------------------
 // Solver
 // ---------------------------------------------------------------------------------------------------------------
@@ -344,17 +381,19 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             w_items.push_back(it);
             ++explored;
         }
-    } else
-    while ((int)w_items.size() < wave_size && !fringe.empty()) {
-        const int id = fringe.pop();
-        const NoDupFringe::Item it = fringe.item(id);
-        const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
-        if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
-        if (w_items.empty()) top_ub = ub;
-        w_states.insert(w_states.end(), fringe.state(id), fringe.state(id) + W);
-        w_bits.insert(w_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
-        w_items.push_back(it);
-        ++explored;
+    } else {
+        fringe.pop_many(wave_size, pop_ids);
+        for (size_t i = 0; i < pop_ids.size(); ++i) {
+            const int id = pop_ids[i];
+            const NoDupFringe::Item it = fringe.item(id);
+            const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
+            if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
+            if (w_items.empty()) top_ub = ub;
+            w_states.insert(w_states.end(), fringe.state(id), fringe.state(id) + W);
+            w_bits.insert(w_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
+            w_items.push_back(it);
+            ++explored;
+        }
     }
     fringe_ms += now_ms() - t0;
     const double tr_pop = now_ms() - t0;
@@ -662,8 +701,9 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
 void Solver::prepop() {
     const int W = words, PWN = (n_vars + 63) / 64;
     pre_states.clear(); pre_bits.clear(); pre_items.clear();
-    while ((int)pre_items.size() < wave_size && !fringe.empty()) {
-        const int id = fringe.pop();
+    fringe.pop_many(wave_size, pop_ids);
+    for (size_t i = 0; i < pop_ids.size(); ++i) {
+        const int id = pop_ids[i];
         const NoDupFringe::Item it = fringe.item(id);
         const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
         if (ub <= best_lb) { fringe.clear(); break; }  // nothing left can improve on the incumbent (it only grows): safe ahead of time too

@@ -46,6 +46,8 @@ public:
     void push_many(const std::vector<PushRec>& recs);
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
+    int pop_many(int k, std::vector<int>& ids);  // the next min(k, len()) nodes in pop() order; ids valid until the next push
+    void prefetch(int id) const { __builtin_prefetch(&items_[id]); __builtin_prefetch(states_.at(id)); __builtin_prefetch(&bits_[(size_t)id * PW]); }
     const uint64_t* state(int id) const { return states_.at(id); }
     const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
     const Item& item(int id) const { return items_[id]; }
@@ -111,7 +113,7 @@ struct Solver {
     std::vector<uint64_t> pre_states, pre_bits; std::vector<NoDupFringe::Item> pre_items;
     void prepop(); void unpop();
     // scratch of one wave (kept to avoid reallocations)
-    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt; std::vector<NoDupFringe::PushRec> push_recs;
+    std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt; std::vector<NoDupFringe::PushRec> push_recs; std::vector<int> pop_ids;
 
     Solver(Engine* e, int model_kind, const uint64_t* root_state, int64_t root_value, int wk, uint64_t w, int ws);
     int init(bool push_root);

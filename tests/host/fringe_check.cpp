@@ -101,11 +101,20 @@ static void push_par(NoDupFringe& f, const Burst& b, int W, int PW) {
     f.push_many(recs);
 }
 
+// `a` is drained with pop(), `b` with pop_many() in chunks: same nodes in the same order
 static int compare_pops(NoDupFringe& a, NoDupFringe& b, int W, int PW, size_t count, const char* what) {
+    std::vector<int> ids;
+    size_t have = 0, done = 0;
     for (size_t i = 0; i < count; ++i) {
-        if (a.empty() != b.empty()) { std::printf("FAIL %s: emptiness differs after %zu pops\n", what, i); return 1; }
-        if (a.empty()) break;
-        const int x = a.pop(), y = b.pop();
+        if (have == done) {
+            if (a.empty() != b.empty()) { std::printf("FAIL %s: emptiness differs after %zu pops\n", what, i); return 1; }
+            if (a.empty()) break;
+            const size_t want = std::min<size_t>(777, count - i);
+            b.pop_many((int)want, ids);
+            have = ids.size(); done = 0;
+            if (have != std::min(want, a.len())) { std::printf("FAIL %s: pop_many returned %zu of %zu\n", what, have, std::min(want, a.len())); return 1; }
+        }
+        const int x = a.pop(), y = ids[done++];
         const NoDupFringe::Item ia = a.item(x), ib = b.item(y);
         if (ia.value != ib.value || ia.ub != ib.ub || ia.depth != ib.depth || ia.rec != ib.rec || std::memcmp(a.state(x), b.state(y), (size_t)W * 8) ||
             std::memcmp(a.bits(x), b.bits(y), (size_t)PW * 8)) {
@@ -113,6 +122,7 @@ static int compare_pops(NoDupFringe& a, NoDupFringe& b, int W, int PW, size_t co
             return 1;
         }
     }
+    if (a.len() != b.len()) { std::printf("FAIL %s: lengths differ after the drain (%zu vs %zu)\n", what, a.len(), b.len()); return 1; }
     return 0;
 }
 
