@@ -135,8 +135,8 @@ int NoDupFringe::push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t
         bool changed = false;
         if (value > old_lp) {
             items_[id] = Item{value, merged_ub, depth, rec};
-            std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
-            std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
+            std::memset(bits_.at(id), 0, (size_t)PW * 8);
+            std::memcpy(bits_.at(id), bits, (size_t)nbits_words * 8);
             changed = true;
         }
         if (ub > old_ub) { items_[id].ub = ub; changed = true; }
@@ -146,8 +146,8 @@ int NoDupFringe::push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t
     const int id = new_id;  // Vacant, no_duplicate.rs:119-135
     items_[id] = Item{value, ub, depth, rec};
     std::memcpy(states_.at(id), st, (size_t)W * 8);
-    std::memset(&bits_[(size_t)id * PW], 0, (size_t)PW * 8);
-    std::memcpy(&bits_[(size_t)id * PW], bits, (size_t)nbits_words * 8);
+    std::memset(bits_.at(id), 0, (size_t)PW * 8);
+    std::memcpy(bits_.at(id), bits, (size_t)nbits_words * 8);
     int pc = 0;
     if (kind_ == DDO_MODEL_MAX2SAT) { const int32_t* x = reinterpret_cast<const int32_t*>(st); for (int j = 0; j < 2 * W; ++j) pc += x[j] < 0 ? -x[j] : x[j]; }
     else for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
@@ -163,7 +163,7 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     if (fresh) {
         id = (int)items_.size();
         items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
-        states_.grow(); bits_.resize(bits_.size() + PW);
+        states_.grow(); bits_.grow();
     } else id = recycle_.back();
     if (push_one(st, key_hash(st, depth), value, ub, depth, rec, bits, nbits_words, id, pending_)) {
         if (!fresh) recycle_.pop_back();
@@ -199,8 +199,7 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     for (size_t q = 0; q < n; ++q) slot[order[q]] = q < fresh ? (int)(base + q) : recycle_[recycle_.size() - 1 - (q - fresh)];
     recycle_.resize(recycle_.size() - nrec);
     items_.resize(base + fresh); popc_.resize(base + fresh, 0); hash_.resize(base + fresh, 0); ver_.resize(base + fresh, 0);
-    for (size_t i = 0; i < fresh; ++i) states_.grow();
-    bits_.resize(bits_.size() + fresh * (size_t)PW);
+    for (size_t i = 0; i < fresh; ++i) { states_.grow(); bits_.grow(); }
     const double T2 = now_ms();
     std::vector<std::vector<Ent>> pend(T);
     std::vector<std::vector<int>> unused(T);
@@ -258,7 +257,7 @@ void NoDupFringe::flush_pending() {
     runs_.emplace_back();
     runs_.back().swap(pending_);
     // Keep the runs few and geometrically sized (a pop looks at every run's tail): the newest run absorbs its predecessor while that one is
-    // at most twice its size, and beyond eight runs regardless -- O(n log n) merge work over a search, stale entries dropped on the way.
+    // at most twice its size, and beyond eight runs regardless -- O(n log n) merge work over a search.
     while (runs_.size() >= 2) {
         std::vector<Ent>& x = runs_[runs_.size() - 2];
         std::vector<Ent>& y = runs_.back();
@@ -268,8 +267,7 @@ void NoDupFringe::flush_pending() {
         size_t i = 0, j = 0;
         while (i < x.size() || j < y.size()) {
             const bool take_x = j == y.size() || (i < x.size() && !ent_less(y[j], x[i]));
-            const Ent& e = take_x ? x[i++] : y[j++];
-            if (e.ver == ver_[e.id]) m.push_back(e);
+            m.push_back(take_x ? x[i++] : y[j++]);  // stale entries stay (a version lookup per entry would be a cache miss each): pops skip them
         }
         runs_.pop_back();
         runs_.back().swap(m);
@@ -289,7 +287,7 @@ int NoDupFringe::pop() {
     runs_[best_run].pop_back();
     if (runs_[best_run].size() >= 8) {  // the next pops most likely come from the same run: start fetching their node records and states
         const int nid = runs_[best_run][runs_[best_run].size() - 8].id;
-        __builtin_prefetch(&items_[nid]); __builtin_prefetch(states_.at(nid)); __builtin_prefetch(&bits_[(size_t)nid * PW]);
+        __builtin_prefetch(&items_[nid]); __builtin_prefetch(states_.at(nid)); __builtin_prefetch(bits_.at(nid));
     }
     ++ver_[id];  // any other entry of this node is now stale
     recycle_.push_back(id);

@@ -32,7 +32,7 @@ public:
     // kind: DDO_MODEL_MISP -- MispRanking (popcount, BitSet::cmp), states compared without their depth (BitSet alone is the state);
     //       DDO_MODEL_MAX2SAT -- Max2SatRanking (rank = sum |benefit|, heuristics.rs:33-37) refined canonically by (depth, lexicographic
     //       benefits); the depth is part of the state (model.rs:59-62 derives Hash / Eq over both fields).
-    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) { states_.init(words); }
+    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) { states_.init(words); bits_.init(pw); }
     struct Item { int32_t value, ub, depth, rec; };
     size_t len() const { return live_; }
     bool empty() const { return live_ == 0; }
@@ -47,9 +47,9 @@ public:
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
     int pop_many(int k, std::vector<int>& ids);  // the next min(k, len()) nodes in pop() order; ids valid until the next push
-    void prefetch(int id) const { __builtin_prefetch(&items_[id]); __builtin_prefetch(states_.at(id)); __builtin_prefetch(&bits_[(size_t)id * PW]); }
+    void prefetch(int id) const { __builtin_prefetch(&items_[id]); __builtin_prefetch(states_.at(id)); __builtin_prefetch(bits_.at(id)); }
     const uint64_t* state(int id) const { return states_.at(id); }
-    const uint64_t* bits(int id) const { return &bits_[(size_t)id * PW]; }
+    const uint64_t* bits(int id) const { return bits_.at(id); }
     const Item& item(int id) const { return items_[id]; }
 private:
     // Priority structure: the reference's updatable binary heap (no_duplicate.rs:206-323) pops in the MaxUB order, a strict total order
@@ -60,13 +60,12 @@ private:
     int W, PW, kind_;
     // states live in fixed blocks (no reallocation copies: a MAX2SAT fringe holds gigabytes of 2 KB states)
     struct Arena {
-        int W = 1; size_t per_block = 1; std::vector<std::unique_ptr<uint64_t[]>> blocks; size_t count = 0;
-        void init(int w) { W = w; per_block = std::max<size_t>(1, ((size_t)1 << 22) / (size_t)w); }
-        uint64_t* at(size_t id) const { return blocks[id / per_block].get() + (id % per_block) * (size_t)W; }
+        int W = 1; int shift = 0; size_t per_block = 1; std::vector<std::unique_ptr<uint64_t[]>> blocks; size_t count = 0;
+        void init(int w) { W = w; shift = 0; while (((size_t)2 << shift) * (size_t)w <= ((size_t)1 << 22)) ++shift; per_block = (size_t)1 << shift; }  // ~32 MB blocks, a power of two rows
+        uint64_t* at(size_t id) const { return blocks[id >> shift].get() + (id & (per_block - 1)) * (size_t)W; }
         void grow() { if (count == blocks.size() * per_block) blocks.emplace_back(new uint64_t[per_block * (size_t)W]); ++count; }
         void clear() { count = 0; }  // the blocks stay (no page faults when the next search refills them)
-    } states_;
-    std::vector<uint64_t> bits_;
+    } states_, bits_;  // packed states and path bits of the nodes
     std::vector<Item> items_;
     std::vector<int32_t> popc_;  // ranking key of the state: popcount (MISP) / sum |benefit| (MAX2SAT)
     std::vector<uint64_t> hash_;
