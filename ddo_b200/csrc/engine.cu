@@ -153,6 +153,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_PDL")) pdl_enabled = atoi(e) != 0;
+    if (const char* e = getenv("DDO_LAYER_CHUNK")) layer_chunk = std::max(1, atoi(e));
     if (cutset == DDO_FRONTIER) dual_enabled = false;  // the twin's logs start at its fork layer; the frontier sweep reads whole DDs
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     if (const char* e = getenv("DDO_SMALL_WS_FIRST")) { int v = atoi(e); if (v == 0 || v == 32 || v == 64 || v == 128) small_ws_first = v; }
@@ -290,7 +291,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     // flat kernels run grid-stride over the per-layer work plan; the grid only has to be large enough to fill the machine
     const long long max_tiles = (long long)slots * ((E->C + npb - 1) / npb);
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
-    const int CHUNK = 16;
+    const int CHUNK = E->layer_chunk;  // layers launched between two polls of the device's `active` counter (and of the cutoff flag)
     const bool pdl = E->pdl_enabled && !E->profiling;  // the profiling events between launches serialise the stream anyway
     for (int t = 0; t < E->Lmax; ++t) {
         if (use_cl) CUDA_TRY(launch_k(pdl, k_finish_cl<S>, dim3(slots * FCL_CS), dim3(FCL_NT), E->finish_cl_smem, st, ev, t, E->finish_cl_kcap));

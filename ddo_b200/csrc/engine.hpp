@@ -118,6 +118,7 @@ struct Engine {
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
     int cutset_type = DDO_LAST_EXACT_LAYER;
     int num_sms = 148;
+    int layer_chunk = 16;      // layer steps launched between two host polls of the `active` counter / cutoff flag (DDO_LAYER_CHUNK)
     bool pdl_enabled = true;   // programmatic dependent launch of the layer-step kernels (DDO_PDL=0 disables; pdl_enter() in kernels.cuh)
     bool dual_enabled = true;  // fork the relaxed twin at the first cut of a restricted DD (DDO_DUAL=0 disables)
     size_t finish_smem = 0; bool finish_attr_set = false;

@@ -174,7 +174,6 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     const size_t n = recs.size();
     const int T = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency()));
     if (n < 8192) { for (const PushRec& r : recs) push(r.state, r.value, r.ub, r.depth, r.rec, r.bits, r.nbits_words); return; }
-    const double T0 = now_ms();
     // hashes, then the records of every shard in record order (stable counting sort)
     std::vector<uint64_t> h(n);
     {
@@ -190,7 +189,6 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
         std::vector<uint32_t> fill(start.begin(), start.end() - 1);
         for (size_t i = 0; i < n; ++i) order[fill[shard_of(h[i])]++] = (uint32_t)i;
     }
-    const double T1 = now_ms();
     // tentative node slot of every record, handed out in SHARD order so that the slots one thread writes are contiguous (no cache lines
     // shared between threads): recycled slots first, then fresh ones; a record that hits an existing node leaves its slot unused
     std::vector<int> slot(n);
@@ -200,7 +198,6 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     recycle_.resize(recycle_.size() - nrec);
     items_.resize(base + fresh); popc_.resize(base + fresh, 0); hash_.resize(base + fresh, 0); ver_.resize(base + fresh, 0);
     for (size_t i = 0; i < fresh; ++i) { states_.grow(); bits_.grow(); }
-    const double T2 = now_ms();
     std::vector<std::vector<Ent>> pend(T);
     std::vector<std::vector<int>> unused(T);
     std::vector<size_t> added(T, 0);
@@ -225,13 +222,11 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
             });
         for (auto& t : ts) t.join();
     }
-    const double T3 = now_ms();
     for (int w = 0; w < T; ++w) {
         pending_.insert(pending_.end(), pend[w].begin(), pend[w].end());
         recycle_.insert(recycle_.end(), unused[w].begin(), unused[w].end());
         live_ += added[w];
     }
-    if (getenv("DDO_PUSH_TRACE")) std::fprintf(stderr, "push_many n=%zu hash+sort %.2f alloc %.2f insert %.2f merge %.2f ms\n", n, T1 - T0, T2 - T1, T3 - T2, now_ms() - T3);
 }
 void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
