@@ -11,7 +11,7 @@
 // unit-test expectations (oracle/selftest.cpp restates clean.rs:1190-2398,
 // node_flags.rs, no_duplicate.rs tests), the golden graphviz dumps in
 // resources/visualisation_tests (tests/golden/*.dot) and the known optima of
-// the DIMACS / knapsack / MAX2SAT instances asserted by examples/*/tests.rs
+// the DIMACS / knapsack / MAX2SAT / TSPTW instances asserted by examples/*/tests.rs
 // (plus the MAX2SAT model unit vectors of examples/max2sat/model.rs:388-448).
 //
 // Every function cites the reference file:line it follows (paths relative to
@@ -28,6 +28,9 @@
 //   C4. best terminal node = last maximum in C1 order (Rust max_by_key).
 //   C5/C6 (MAX2SAT, models.hpp): stable variable order; ranking ties refined
 //       by (depth, lexicographic benefits).
+//   C7. a FRONTIER cutset is drained by (layer descending, position in the
+//       layer ascending); the reference pushes its nodes in the order of the
+//       bottom-up edge walk (clean.rs:586-606), which inherits the hash order.
 // Everything else (e.g. the order in which relaxed edges are appended,
 // clean.rs:851-866, and the `>=` "last tie wins" rule, clean.rs:215) is verbatim.
 // ============================================================================
@@ -211,7 +214,12 @@ struct DominanceCheckResult { bool dominated; std::optional<isize> threshold; };
 template <class S>
 struct Dominance {
     virtual ~Dominance() = default;
-    virtual std::optional<isize> get_key(const S&) const = 0;  // Key restricted to an integer (all in-scope models)
+    virtual std::optional<isize> get_key(const S&) const = 0;  // integer keys (knapsack); models with a structured key override get_key_bytes
+    virtual std::optional<std::string> get_key_bytes(const S& s) const {  // Dominance::Key as an opaque byte string (dominance.rs:42-45)
+        auto k = get_key(s);
+        if (!k) return std::nullopt;
+        return std::string(reinterpret_cast<const char*>(&*k), sizeof(isize));
+    }
     virtual size_t nb_dimensions(const S&) const = 0;
     virtual isize get_coordinate(const S&, size_t i) const = 0;
     virtual bool use_value() const { return false; }
@@ -256,7 +264,7 @@ struct EmptyDominanceChecker : DominanceChecker<S> {  // dominance/empty.rs:24-4
 template <class S>
 struct SimpleDominanceChecker : DominanceChecker<S> {  // dominance/simple.rs:37-116
     struct Entry { std::shared_ptr<const S> state; isize value; };
-    struct LayerMap { std::unordered_map<isize, std::vector<Entry>> m; std::mutex mu; };
+    struct LayerMap { std::unordered_map<std::string, std::vector<Entry>> m; std::mutex mu; };
     const Dominance<S>* dom;
     std::vector<std::unique_ptr<LayerMap>> data;
     SimpleDominanceChecker(const Dominance<S>* d, size_t nb_variables) : dom(d) {
@@ -264,7 +272,7 @@ struct SimpleDominanceChecker : DominanceChecker<S> {  // dominance/simple.rs:37
     }
     void clear_layer(size_t d) override { std::lock_guard<std::mutex> g(data[d]->mu); data[d]->m.clear(); }
     DominanceCheckResult is_dominated_or_insert(std::shared_ptr<const S> state, size_t depth, isize value) override {  // simple.rs:71-111
-        auto key = dom->get_key(*state);
+        auto key = dom->get_key_bytes(*state);
         if (!key) return {false, std::nullopt};
         auto& L = *data[depth];
         std::lock_guard<std::mutex> g(L.mu);

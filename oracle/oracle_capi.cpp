@@ -4,6 +4,7 @@
 // cpu_baseline / --impl reference legs.
 // ============================================================================
 #include "models.hpp"
+#include "tsptw.hpp"
 #include <cstdio>
 #include <sstream>
 
@@ -384,6 +385,41 @@ int32_t oracle_knapsack_solve(int32_t n, int64_t capacity, const int64_t* profit
     out->has_value = c.best_value.has_value(); out->best_value = c.best_value.value_or(0); out->is_exact = c.is_exact;
     out->best_lb = lb; out->best_ub = ub; out->explored = st.explored; out->expanded = st.expanded; out->transitions = st.transitions; out->compilations = st.compilations;
     if (taken && sol) { for (int32_t i = 0; i < n; ++i) taken[i] = 0; for (auto& d : *sol) taken[d.variable] = (int32_t)d.value; }
+    return 0;
+}
+
+// TSPTW (BASELINE config 4), examples/tsptw/main.rs:66-84 and tests.rs:33-57: TsptwWidth(nb_vars, factor), SimpleDominanceChecker(TsptwDominance),
+// NoDupFringe(MaxUB(TsptwRanking)), DefaultCachingSolver = ParCachingSolverFc (FRONTIER cutset + SimpleCache, solver/mod.rs:30,37).
+// dist: n x n row-major, tw: n x (earliest, latest), both already scaled to integers (instance.rs:86-98).  solver: 0 sequential, 2 parallel(k).
+// perm[variable] = city visited at that step (main.rs:124-139).
+int32_t oracle_tsptw_solve(int32_t n, const int64_t* dist, const int64_t* tw, int32_t factor, int32_t solver, int32_t k, int32_t cutset_type,
+                           int32_t caching, double time_budget_s, oracle_solve_result* out, int32_t* perm) {
+    TsptwInstance inst;
+    inst.nb_nodes = (size_t)n;
+    inst.distances.assign((size_t)n, std::vector<size_t>((size_t)n, 0));
+    for (int32_t i = 0; i < n; ++i) for (int32_t j = 0; j < n; ++j) inst.distances[i][j] = (size_t)dist[(size_t)i * n + j];
+    for (int32_t i = 0; i < n; ++i) inst.timewindows.push_back(TimeWindow{(size_t)tw[2 * i], (size_t)tw[2 * i + 1]});
+    Tsptw pb(inst);
+    TsptwRelax rlx(&pb); TsptwRanking rk; TsptwDominance td;
+    TsptwWidth wh(pb.nb_variables(), (size_t)std::max(1, factor));
+    NoCutoff nocut; std::unique_ptr<TimeBudget> tb;
+    const Cutoff* cut = &nocut;
+    if (time_budget_s > 0) { tb.reset(new TimeBudget(time_budget_s)); cut = tb.get(); }
+    EmptyDominanceChecker<TsptwState> edom; SimpleDominanceChecker<TsptwState> sdom(&td, pb.nb_variables());
+    EmptyCache<TsptwState> ec; SimpleCache<TsptwState, TsptwHash, TsptwEq> sc;
+    MaxUB<TsptwState> mx{&rk};
+    NoDupFringe<TsptwState, TsptwHash, TsptwEq> fringe(mx);
+    SolverConfig<TsptwState> cfg{&pb, &rlx, &rk, &wh, caching ? (DominanceChecker<TsptwState>*)&sdom : (DominanceChecker<TsptwState>*)&edom,
+                                 cut, &fringe, caching ? (Cache<TsptwState>*)&sc : (Cache<TsptwState>*)&ec, cutset_type};
+    std::memset(out, 0, sizeof(*out));
+    double t0 = now_s();
+    Completion c; SolverStats st; isize lb, ub; std::optional<Solution> sol;
+    if (solver == 0) { SequentialSolver<TsptwState, TsptwHash, TsptwEq> s(cfg); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
+    else { ParallelSolver<TsptwState, TsptwHash, TsptwEq> s(cfg, (size_t)k); c = s.maximize(); st = s.stats; lb = s.best_lb; ub = s.best_ub; sol = s.best_sol; }
+    out->seconds = now_s() - t0;
+    out->has_value = c.best_value.has_value(); out->best_value = c.best_value.value_or(0); out->is_exact = c.is_exact;
+    out->best_lb = lb; out->best_ub = ub; out->explored = st.explored; out->expanded = st.expanded; out->transitions = st.transitions; out->compilations = st.compilations;
+    if (perm) { for (int32_t i = 0; i < n; ++i) perm[i] = -1; if (sol) for (auto& d : *sol) perm[d.variable] = (int32_t)d.value; }
     return 0;
 }
 

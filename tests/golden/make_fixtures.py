@@ -5,6 +5,7 @@ Copies the *data* fixtures the reference's own tests use for the hot path (no re
   * resources/misp/*.clq (small ones)    -- DIMACS instances whose optima are asserted in ddo/examples/misp/tests.rs:66-193
   * resources/knapsack/* (small ones)    -- instances whose optima are asserted in ddo/examples/knapsack/tests.rs:65-206
   * resources/max2sat/*.wcnf (small)     -- instances whose optima are asserted in ddo/examples/max2sat/tests.rs:65-103
+  * resources/tsptw/{Langevin,SolomonPotvinBengio}/* (a selection) -- instances whose optima are asserted in ddo/examples/tsptw/tests.rs:80-683
 and writes expected.json with the asserted optima (transcribed from those test files, with their line numbers).
 """
 import json
@@ -18,6 +19,10 @@ OUT = Path(__file__).resolve().parent
 MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "keller4", "hamming8-2", "hamming8-4",
         "brock200_2", "brock200_3", "brock200_4", "c-fat200-5"]
 KNAPSACK_MAX_ITEMS = 200
+TSPTW = ["Langevin/N20ft301.dat", "Langevin/N20ft405.dat", "Langevin/N40ft403.dat", "Langevin/N60ft406.dat", "Langevin/N60ft410.dat",
+         "SolomonPotvinBengio/rc_201.1.txt", "SolomonPotvinBengio/rc_201.3.txt", "SolomonPotvinBengio/rc_202.2.txt", "SolomonPotvinBengio/rc_203.1.txt",
+         "SolomonPotvinBengio/rc_203.4.txt", "SolomonPotvinBengio/rc_205.1.txt", "SolomonPotvinBengio/rc_205.2.txt", "SolomonPotvinBengio/rc_205.4.txt",
+         "SolomonPotvinBengio/rc_206.3.txt", "SolomonPotvinBengio/rc_207.4.txt"]
 MAX2SAT = ["debug", "debug2", "pass", "tautology", "unit", "negative_wt", "frb10-6-1", "frb10-6-2", "frb10-6-3", "frb10-6-4"]
 
 
@@ -55,6 +60,21 @@ def main():
         if n_items <= KNAPSACK_MAX_ITEMS:
             shutil.copy(src, OUT / "knapsack" / name)
             expected["knapsack"][name] = {"optimum": v, "items": n_items, "source": f"ddo/examples/knapsack/tests.rs:{ln}"}
+    # TSPTW: `assert_eq!(<f32 literal>, solve_langevin("<id>"))` / solve_solomon_potvin_bengio; the literal is kept as text (compared as f32)
+    expected["tsptw"] = {}
+    lines = (REF / "ddo/examples/tsptw/tests.rs").read_text().splitlines()
+    for ln, line in enumerate(lines, 1):
+        mm = re.search(r'assert_eq!\(([\d.]+), solve_(langevin|solomon_potvin_bengio)\("([^"]+)"\)\)', line)
+        if not mm:
+            continue
+        name = ("Langevin/" if mm.group(2) == "langevin" else "SolomonPotvinBengio/") + mm.group(3)
+        if name in TSPTW:
+            ignored = "#[ignore]" in lines[ln - 3]
+            assert not ignored, name
+            (OUT / "tsptw" / name).parent.mkdir(parents=True, exist_ok=True)
+            shutil.copy(REF / "resources/tsptw" / name, OUT / "tsptw" / name)
+            expected["tsptw"][name] = {"optimum": mm.group(1), "source": f"ddo/examples/tsptw/tests.rs:{ln}"}
+    assert len(expected["tsptw"]) == len(TSPTW)
     (OUT / "expected.json").write_text(json.dumps(expected, indent=1, sort_keys=True) + "\n")
 
 

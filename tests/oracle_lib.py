@@ -350,6 +350,37 @@ def knapsack_solve(inst, solver="sequential", k=1, width=None, cutset_type=FRONT
     return out
 
 
+class TsptwInstance:
+    """examples/tsptw/instance.rs:51-108: first line = number of nodes, then the distance matrix, then one time window per node; every number is
+    parsed as f32, multiplied by 10000.0 in f32 and truncated to an integer (instance.rs:86-87,97-98)."""
+
+    def __init__(self, text: str):
+        rows = [ln.strip() for ln in text.splitlines()]
+        rows = [ln for ln in rows if ln and not ln.startswith("#")]
+        self.n = int(rows[0].split()[0])
+        scale = np.float32(10000.0)
+        conv = lambda tok: int(np.float32(tok) * scale)  # noqa: E731
+        self.dist = np.zeros((self.n, self.n), dtype=np.int64)
+        for i in range(self.n):
+            for j, tok in enumerate(rows[1 + i].split()):
+                self.dist[i, j] = conv(tok)
+        self.tw = np.array([[conv(t) for t in rows[1 + self.n + i].split()[:2]] for i in range(self.n)], dtype=np.int64)
+
+
+def tsptw_solve(inst: TsptwInstance, factor=1, solver="sequential", k=1, cutset_type=FRONTIER, caching=True, time_budget_s=0.0):
+    """examples/tsptw/tests.rs:33-57 (`solve(instance, width, threads)`); returns the result fields plus `cost` = -(best_value) / 10000 as f32."""
+    res = SolveResult()
+    perm = np.zeros(inst.n, dtype=np.int32)
+    lib().oracle_tsptw_solve.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                         C.POINTER(SolveResult), C.c_void_p]
+    lib().oracle_tsptw_solve(inst.n, _p(np.ascontiguousarray(inst.dist)), _p(np.ascontiguousarray(inst.tw)), factor, 0 if solver == "sequential" else 2, k,
+                             cutset_type, int(caching), time_budget_s, C.byref(res), _p(perm))
+    out = {k_: getattr(res, k_) for k_, _ in SolveResult._fields_}
+    out["perm"] = perm
+    out["cost"] = float(-(np.float32(res.best_value)) / np.float32(10000.0)) if res.has_value else -1.0
+    return out
+
+
 def locbounds_dump(cutset_type=FRONTIER, best_lb=0) -> str:
     buf = C.create_string_buffer(1 << 16)
     n = lib().oracle_locbounds_dump(cutset_type, best_lb, buf, len(buf))

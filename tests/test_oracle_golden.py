@@ -222,3 +222,55 @@ def test_max2sat_restricted_relaxed_bracket_the_optimum(golden_dir):
         lo = o.compile(O.RESTRICTED, w)
         hi = o.compile(O.RELAXED, w)
         assert lo["best_value"] <= 54 <= hi["best_value"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# TSPTW (BASELINE config 4): oracle only so far -- the device model is the next row of the scope table
+# ----------------------------------------------------------------------------------------------------------------
+def _tour_cost(inst, perm):
+    """Travel + waiting time of the tour depot -> perm[0] -> ... -> perm[n-1] (= depot), None when a time window is missed."""
+    t, pos, total = 0, 0, 0
+    for city in perm.tolist():
+        arrive = t + int(inst.dist[pos, city])
+        if arrive > int(inst.tw[city, 1]):
+            return None
+        start = max(arrive, int(inst.tw[city, 0]))
+        total += start - t
+        t, pos = start, city
+    return total
+
+
+def test_tsptw_known_optima(golden_dir):
+    """examples/tsptw/tests.rs:33-57,80-683: `solve(instance, width = 1, threads = 1)` with the DefaultCachingSolver stack (FRONTIER cutset,
+    SimpleCache, SimpleDominanceChecker(TsptwDominance), TsptwWidth, NoDupFringe(MaxUB(TsptwRanking))); the asserted value is
+    -(best_value) / 10000 as f32.  The solution is re-scored as a tour: every city once, every time window met, same cost."""
+    exp = _expected(golden_dir)["tsptw"]
+    assert len(exp) == 15
+    for name, e in exp.items():
+        inst = O.TsptwInstance((golden_dir / "tsptw" / name).read_text())
+        r = O.tsptw_solve(inst)
+        assert r["is_exact"] and r["has_value"], name
+        assert np.float32(r["cost"]) == np.float32(float(e["optimum"])), (name, r["cost"], e["optimum"], e["source"])
+        assert r["best_lb"] == r["best_ub"] == r["best_value"]
+        perm = r["perm"]
+        assert sorted(perm.tolist()) == list(range(inst.n)) and perm[-1] == 0, name
+        assert _tour_cost(inst, perm) == -r["best_value"], name
+
+
+def test_tsptw_solver_variants_agree(golden_dir):
+    """The optimum does not depend on the cutset type, the cache / dominance filters, the width factor or the number of threads."""
+    for name in ("SolomonPotvinBengio/rc_203.4.txt", "SolomonPotvinBengio/rc_205.1.txt", "Langevin/N40ft403.dat"):
+        inst = O.TsptwInstance((golden_dir / "tsptw" / name).read_text())
+        ref = O.tsptw_solve(inst)["best_value"]
+        assert O.tsptw_solve(inst, factor=3)["best_value"] == ref
+        assert O.tsptw_solve(inst, solver="parallel", k=4)["best_value"] == ref
+        assert O.tsptw_solve(inst, cutset_type=O.LEL)["best_value"] == ref
+        r = O.tsptw_solve(inst, caching=False, cutset_type=O.LEL, time_budget_s=30)
+        assert (not r["is_exact"]) or r["best_value"] == ref
+
+
+def test_tsptw_instance_scaling_is_f32():
+    """instance.rs:86-87: `(distance * 10000.0) as usize` in f32 -- 79.4 becomes 794000 exactly but 70.3 becomes 703000 only through f32 rounding."""
+    inst = O.TsptwInstance("2\n0 70.3\n79.4 0\n0 1000.5\n10.25 408\n")
+    assert inst.dist.tolist() == [[0, int(np.float32(70.3) * np.float32(10000.0))], [794000, 0]]
+    assert inst.tw.tolist() == [[0, 10005000], [102500, 4080000]]
