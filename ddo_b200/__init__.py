@@ -6,8 +6,9 @@ include/ddo_b200.h into hand-written sm_100a kernels; there is no CPU fallback.
 """
 from .api import (CompilationType, Completion, CutoffOccurred, Decision, DivBy, FixedWidth, Times, GpuMdd, LAST_EXACT_LAYER, FRONTIER, Max2Sat, Misp, NbUnassignedWidth,
                   ParNoCachingSolverLel, ParNoCachingSolverFc, DefaultSolver, SubProblem, device_count, kernel_launches)
-from .instances import Max2SatInstance, MispInstance, gnp, parse_dimacs, parse_wcnf, random_max2sat, read_dimacs, read_wcnf
+from .instances import (Max2SatInstance, MispInstance, TsptwInstance, gnp, parse_dimacs, parse_tsptw, parse_wcnf, random_max2sat, read_dimacs, read_tsptw,
+                        read_wcnf)
 
 __all__ = ["Times", "DivBy", "CompilationType", "Completion", "CutoffOccurred", "Decision", "FixedWidth", "GpuMdd", "LAST_EXACT_LAYER", "FRONTIER", "Max2Sat", "Misp",
            "NbUnassignedWidth", "ParNoCachingSolverLel", "ParNoCachingSolverFc", "DefaultSolver", "SubProblem", "device_count", "kernel_launches", "MispInstance", "gnp",
-           "parse_dimacs", "read_dimacs", "Max2SatInstance", "parse_wcnf", "random_max2sat", "read_wcnf"]
+           "parse_dimacs", "read_dimacs", "Max2SatInstance", "parse_wcnf", "random_max2sat", "read_wcnf", "TsptwInstance", "parse_tsptw", "read_tsptw"]

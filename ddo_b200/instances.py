@@ -148,6 +148,40 @@ def random_knapsack(n: int, seed: int) -> KnapsackInstance:
 
 
 @dataclass
+@dataclass
+class TsptwInstance:
+    """ddo/examples/tsptw/instance.rs:51-59: nb_nodes (depot included), distance matrix and one time window per node, as integers."""
+    n: int
+    dist: np.ndarray  # [n][n] int64
+    tw: np.ndarray    # [n][2] int64 (earliest, latest)
+    name: str = ""
+
+
+def parse_tsptw(text: str, name: str = "") -> TsptwInstance:
+    """ddo/examples/tsptw/instance.rs:61-108: `#` comment lines and empty lines are skipped; the first line holds the number of nodes, the next
+    n lines the distance matrix, the last n lines `earliest latest`.  Every number is parsed as f32, multiplied by 10000.0 in f32 and truncated
+    to an integer (instance.rs:86-87,97-98) -- 70.3 becomes 702999 or 703000 depending on that rounding, so the arithmetic is done in float32."""
+    rows = [ln.strip() for ln in text.splitlines()]
+    rows = [ln for ln in rows if ln and not ln.startswith("#")]
+    n = int(rows[0].split()[0])
+    scale = np.float32(10000.0)
+
+    def conv(tok: str) -> int:
+        return int(np.float32(tok) * scale)
+
+    dist = np.zeros((n, n), dtype=np.int64)
+    for i in range(n):
+        for j, tok in enumerate(rows[1 + i].split()):
+            dist[i, j] = conv(tok)
+    tw = np.array([[conv(t) for t in rows[1 + n + i].split()[:2]] for i in range(n)], dtype=np.int64)
+    return TsptwInstance(n, dist, tw, name)
+
+
+def read_tsptw(path: str) -> TsptwInstance:
+    with open(path) as f:
+        return parse_tsptw(f.read(), str(path))
+
+
 class Max2SatInstance:
     """A weighted MAX2SAT instance: ``clauses`` is int64[m, 3] = (weight, literal x, literal y); the literal of variable i (0-based) is
     +-(i + 1); x == y encodes a unit clause.  Duplicated clauses keep the LAST weight (the reference inserts into a hash map,

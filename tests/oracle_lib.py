@@ -350,24 +350,14 @@ def knapsack_solve(inst, solver="sequential", k=1, width=None, cutset_type=FRONT
     return out
 
 
-class TsptwInstance:
-    """examples/tsptw/instance.rs:51-108: first line = number of nodes, then the distance matrix, then one time window per node; every number is
-    parsed as f32, multiplied by 10000.0 in f32 and truncated to an integer (instance.rs:86-87,97-98)."""
+def TsptwInstance(text: str):
+    """examples/tsptw/instance.rs:51-108 through the host-side parser of the package (ddo_b200/instances.py::parse_tsptw)."""
+    from ddo_b200.instances import parse_tsptw
 
-    def __init__(self, text: str):
-        rows = [ln.strip() for ln in text.splitlines()]
-        rows = [ln for ln in rows if ln and not ln.startswith("#")]
-        self.n = int(rows[0].split()[0])
-        scale = np.float32(10000.0)
-        conv = lambda tok: int(np.float32(tok) * scale)  # noqa: E731
-        self.dist = np.zeros((self.n, self.n), dtype=np.int64)
-        for i in range(self.n):
-            for j, tok in enumerate(rows[1 + i].split()):
-                self.dist[i, j] = conv(tok)
-        self.tw = np.array([[conv(t) for t in rows[1 + self.n + i].split()[:2]] for i in range(self.n)], dtype=np.int64)
+    return parse_tsptw(text)
 
 
-def tsptw_solve(inst: TsptwInstance, factor=1, solver="sequential", k=1, cutset_type=FRONTIER, caching=True, time_budget_s=0.0):
+def tsptw_solve(inst, factor=1, solver="sequential", k=1, cutset_type=FRONTIER, caching=True, time_budget_s=0.0):
     """examples/tsptw/tests.rs:33-57 (`solve(instance, width, threads)`); returns the result fields plus `cost` = -(best_value) / 10000 as f32."""
     res = SolveResult()
     perm = np.zeros(inst.n, dtype=np.int32)
