@@ -73,3 +73,14 @@ def test_instance_generator_and_dimacs_roundtrip():
     w = parse_dimacs("c comment\np edge 3 2\nn 2 7\ne 1 2\ne 2 3\n")
     assert w.weights.tolist() == [1, 7, 1] and w.src.tolist() == [0, 1] and w.dst.tolist() == [1, 2]
     assert g.initial_state().tolist() == [(1 << 50) - 1]
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/ddo_b200.h must compile as C99 (no C++ types, no torch types) and as C++."""
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ddo_b200.h"\nint main(void) { ddo_completion c; ddo_decision d; (void)c; (void)d; return 0; }\n')
+    inc = str(ROOT / "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True, capture_output=True)
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True, capture_output=True)
