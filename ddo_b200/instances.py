@@ -148,7 +148,6 @@ def random_knapsack(n: int, seed: int) -> KnapsackInstance:
 
 
 @dataclass
-@dataclass
 class TsptwInstance:
     """ddo/examples/tsptw/instance.rs:51-59: nb_nodes (depot included), distance matrix and one time window per node, as integers."""
     n: int
@@ -182,6 +181,7 @@ def read_tsptw(path: str) -> TsptwInstance:
         return parse_tsptw(f.read(), str(path))
 
 
+@dataclass
 class Max2SatInstance:
     """A weighted MAX2SAT instance: ``clauses`` is int64[m, 3] = (weight, literal x, literal y); the literal of variable i (0-based) is
     +-(i + 1); x == y encodes a unit clause.  Duplicated clauses keep the LAST weight (the reference inserts into a hash map,
