@@ -255,8 +255,84 @@ static void test_solvers_knapsack() {
             }
 }
 
+static void test_width() {  // heuristics/width.rs:884-1075 (test_nbunassigned, test_fixedwidth, test_adapters)
+    auto sub = [](size_t decided) {
+        SubProblem<char> s{std::make_shared<const char>('a'), 10, {}, 100, decided};
+        for (size_t i = 0; i < decided; ++i) s.path.push_back(Decision{i, (isize)i});
+        return s;
+    };
+    NbUnassignedWidth<char> nb(5);
+    CHECK(nb.max_width(sub(1)) == 4 && nb.max_width(sub(0)) == 5 && nb.max_width(sub(5)) == 0, "NbUnassignedWidth 4 / 5 / 0");
+    FixedWidth<char> f5(5);
+    CHECK(f5.max_width(sub(1)) == 5 && f5.max_width(sub(0)) == 5 && f5.max_width(sub(5)) == 5, "FixedWidth is constant");
+    CHECK(Times<char>(2, &f5).max_width(sub(5)) == 10 && Times<char>(3, &f5).max_width(sub(5)) == 15 && Times<char>(1, &f5).max_width(sub(5)) == 5 &&
+          Times<char>(10, &f5).max_width(sub(5)) == 50, "Times 10 / 15 / 5 / 50");
+    FixedWidth<char> f4(4), f9(9), f10(10), f0(0);
+    CHECK(DivBy<char>(2, &f4).max_width(sub(5)) == 2 && DivBy<char>(3, &f9).max_width(sub(5)) == 3 && DivBy<char>(1, &f10).max_width(sub(5)) == 10, "DivBy 2 / 3 / 10");
+    CHECK(Times<char>(0, &f10).max_width(sub(5)) == 1 && Times<char>(10, &f0).max_width(sub(5)) == 1, "wrappers never return a zero max_width");
+}
+
+using VecState = std::vector<isize>;
+struct DummyDominance : Dominance<VecState> {  // dominance/simple.rs:226-242
+    std::optional<isize> get_key(const VecState& s) const override { return s[0]; }
+    size_t nb_dimensions(const VecState& s) const override { return s.size(); }
+    isize get_coordinate(const VecState& s, size_t i) const override { return s[i]; }
+};
+struct DummyDominanceWithValue : DummyDominance { bool use_value() const override { return true; } };  // :244-263
+static void test_dominance() {  // dominance/simple.rs:119-224
+    auto st = [](std::initializer_list<isize> v) { return std::make_shared<const VecState>(v); };
+    auto none = [](const DominanceCheckResult& r) { return !r.dominated && !r.threshold; };
+    DummyDominance dd; DummyDominanceWithValue dv;
+    {   // not_dominated_when_keys_are_different
+        SimpleDominanceChecker<VecState> d(&dv, 0);
+        CHECK(none(d.is_dominated_or_insert(st({3, 0}), 0, 3)) && none(d.is_dominated_or_insert(st({2, 0}), 0, 2)) && none(d.is_dominated_or_insert(st({1, 0}), 0, 1)) &&
+              none(d.is_dominated_or_insert(st({0, 0}), 0, 0)), "different keys never dominate");
+    }
+    {   // dominated_when_keys_are_equal
+        SimpleDominanceChecker<VecState> d(&dd, 0);
+        CHECK(none(d.is_dominated_or_insert(st({0, 3}), 0, 0)), "first entry");
+        CHECK(d.is_dominated_or_insert(st({0, 2}), 0, 2).dominated && d.is_dominated_or_insert(st({0, 1}), 0, 1).dominated && d.is_dominated_or_insert(st({0, 0}), 0, 0).dominated,
+              "dominated by coordinates");
+        SimpleDominanceChecker<VecState> e(&dv, 0);
+        CHECK(none(e.is_dominated_or_insert(st({0, 0}), 0, 3)), "first entry (value)");
+        CHECK(e.is_dominated_or_insert(st({0, 0}), 0, 2).dominated && e.is_dominated_or_insert(st({0, 0}), 0, 1).dominated && e.is_dominated_or_insert(st({0, 0}), 0, 0).dominated,
+              "dominated by value");
+    }
+    {   // not_dominated_when_keys_are_equal
+        SimpleDominanceChecker<VecState> d(&dd, 0);
+        CHECK(none(d.is_dominated_or_insert(st({0, 0, 3}), 0, 3)) && none(d.is_dominated_or_insert(st({0, 0, 3}), 0, 1)) && none(d.is_dominated_or_insert(st({0, 1, 1}), 0, 5)) &&
+              none(d.is_dominated_or_insert(st({0, 0, 4}), 0, 3)), "incomparable or better entries are kept");
+        SimpleDominanceChecker<VecState> e(&dv, 0);
+        CHECK(none(e.is_dominated_or_insert(st({0, 0}), 0, 3)) && none(e.is_dominated_or_insert(st({0, 3}), 0, 0)) && none(e.is_dominated_or_insert(st({0, 1}), 0, 1)) &&
+              none(e.is_dominated_or_insert(st({0, 0}), 0, 5)), "incomparable with value");
+    }
+    {   // pruning_threshold_when_value_is_used
+        SimpleDominanceChecker<VecState> d(&dv, 0);
+        CHECK(none(d.is_dominated_or_insert(st({0, 0}), 0, 3)), "first");
+        auto a = d.is_dominated_or_insert(st({0, 0}), 0, 2), b = d.is_dominated_or_insert(st({0, 0}), 0, 1), c = d.is_dominated_or_insert(st({0, -1}), 0, 0);
+        CHECK(a.dominated && a.threshold == std::optional<isize>(2) && b.dominated && b.threshold == std::optional<isize>(2) && c.dominated && c.threshold == std::optional<isize>(3),
+              "thresholds 2 / 2 / 3");
+    }
+    {   // entry_is_added_only_when_dominant / entry_is_removed_when_dominated (sizes of the per-key entry list)
+        SimpleDominanceChecker<VecState> d(&dv, 0);
+        auto size = [&]() { size_t n = 0; for (auto& kv : d.data[0]->m) n += kv.second.size(); return n; };
+        CHECK(none(d.is_dominated_or_insert(st({0, 0}), 0, 3)) && size() == 1, "one entry");
+        auto r = d.is_dominated_or_insert(st({0, 0}), 0, 1);
+        CHECK(r.dominated && r.threshold == std::optional<isize>(2) && size() == 1, "a dominated state is not stored");
+        CHECK(none(d.is_dominated_or_insert(st({0, 1}), 0, 1)) && size() == 2, "incomparable: stored");
+        CHECK(none(d.is_dominated_or_insert(st({0, -1}), 0, 5)) && size() == 3, "incomparable: stored (2)");
+        SimpleDominanceChecker<VecState> e(&dv, 0);
+        auto size_e = [&]() { size_t n = 0; for (auto& kv : e.data[0]->m) n += kv.second.size(); return n; };
+        CHECK(none(e.is_dominated_or_insert(st({0, 0}), 0, 3)) && size_e() == 1, "one entry");
+        CHECK(none(e.is_dominated_or_insert(st({0, 1}), 0, 5)) && size_e() == 1, "the dominated entry is replaced");
+        CHECK(none(e.is_dominated_or_insert(st({0, 2}), 0, 7)) && size_e() == 1, "and again");
+    }
+}
+
 int main() {
     test_flags();
+    test_width();
+    test_dominance();
     test_dummy_dd();
     test_locbounds();
     test_fringe();

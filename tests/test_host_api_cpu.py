@@ -1,0 +1,34 @@
+"""Host-side mirror of the reference interface (ddo_b200/api.py) on CPU: the width heuristics against the vectors of
+ddo/src/implementation/heuristics/width.rs:884-1075, their mapping onto the C ABI, and Solver::gap (abstraction/solver.rs:80-93)."""
+import pytest
+
+from ddo_b200 import Decision, DivBy, FixedWidth, NbUnassignedWidth, SubProblem, Times
+from ddo_b200 import _native as N
+from ddo_b200.api import _width_spec
+
+
+def _sub(decided):
+    return SubProblem("a", 10, [Decision(i, i) for i in range(decided)], 100, decided)
+
+
+def test_width_heuristics_match_the_reference_vectors():
+    nb = NbUnassignedWidth(5)
+    assert (nb.max_width(_sub(1)), nb.max_width(_sub(0)), nb.max_width(_sub(5))) == (4, 5, 0)            # width.rs:890-933
+    f5 = FixedWidth(5)
+    assert (f5.max_width(_sub(1)), f5.max_width(_sub(0)), f5.max_width(_sub(5))) == (5, 5, 5)            # width.rs:942-985
+    assert [Times(k, f5).max_width(_sub(5)) for k in (2, 3, 1, 10)] == [10, 15, 5, 50]                   # width.rs:995-1014
+    assert [DivBy(k, FixedWidth(w)).max_width(_sub(5)) for k, w in ((2, 4), (3, 9), (1, 10))] == [2, 3, 10]  # width.rs:1017-1035
+    assert Times(0, FixedWidth(10)).max_width(_sub(5)) == 1 and Times(10, FixedWidth(0)).max_width(_sub(5)) == 1  # width.rs:1038-1055
+    with pytest.raises(ZeroDivisionError):                                                               # width.rs:1057-1074 (#[should_panic])
+        DivBy(0, FixedWidth(0)).max_width(_sub(5))
+
+
+def test_width_heuristics_map_onto_the_abi():
+    assert _width_spec(FixedWidth(100), 500) == (N.WIDTH_FIXED, 100, 100)
+    assert _width_spec(NbUnassignedWidth(500), 500) == (N.WIDTH_NB_UNASSIGNED, 0, 500)
+    assert _width_spec(Times(3, NbUnassignedWidth(500)), 500) == (N.WIDTH_TIMES_NB_UNASSIGNED, 3, 1500)
+    assert _width_spec(DivBy(4, NbUnassignedWidth(500)), 500) == (N.WIDTH_DIVBY_NB_UNASSIGNED, 4, 500)
+    assert _width_spec(Times(2, FixedWidth(7)), 500) == (N.WIDTH_FIXED, 14, 14)  # a constant folds into FixedWidth
+    assert _width_spec(DivBy(2, FixedWidth(7)), 500) == (N.WIDTH_FIXED, 3, 3)
+    with pytest.raises(TypeError):
+        _width_spec(object(), 5)
