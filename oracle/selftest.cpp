@@ -329,10 +329,31 @@ static void test_dominance() {  // dominance/simple.rs:119-224
     }
 }
 
+static void test_dominance_cmp() {  // abstraction/dominance.rs:134-192
+    DummyDominance dd; DummyDominanceWithValue dv;
+    const VecState z{0, 0, 0};
+    auto pc = [](const Dominance<VecState>& d, const VecState& a, isize va, const VecState& b, isize vb) { return d.partial_cmp(a, va, b, vb); };
+    auto is = [](const std::optional<DominanceCmpResult>& r, int ord, bool only) { return r && (r->ordering < 0 ? -1 : (r->ordering > 0 ? 1 : 0)) == ord && r->only_val_diff == only; };
+    CHECK(!dd.use_value(), "by_default_value_is_unused");
+    CHECK(!pc(dd, z, 0, VecState{0, -1, 1}, 0) && !pc(dv, z, 0, VecState{0, 0, 1}, -1), "partial_cmp: None when coordinates (or the value) disagree");
+    CHECK(is(pc(dd, z, 0, VecState{0, 0, 1}, 0), -1, false) && is(pc(dd, z, 0, VecState{0, 0, 1}, -1), -1, false) && is(pc(dd, z, 0, VecState{0, 0, -1}, 0), 1, false) &&
+          is(pc(dd, z, 0, VecState{0, 0, -1}, 1), 1, false) && is(pc(dd, z, 0, z, 1), 0, false), "partial_cmp without value");
+    CHECK(is(pc(dv, z, 0, z, 1), -1, true) && is(pc(dv, z, 0, VecState{1, 1, 1}, 1), -1, false) && is(pc(dv, z, 0, z, -1), 1, true) &&
+          is(pc(dv, z, 0, VecState{-1, -1, -1}, -1), 1, false) && is(pc(dv, z, 0, z, 0), 0, false), "partial_cmp with value (only_val_diff)");
+    auto sg = [](int c) { return c < 0 ? -1 : (c > 0 ? 1 : 0); };
+    CHECK(sg(dd.cmp(z, 0, VecState{0, 0, 1}, 0)) == -1 && sg(dd.cmp(z, 0, VecState{0, 1, -1}, 0)) == -1 && sg(dd.cmp(z, 0, VecState{0, 0, 1}, -1)) == -1 &&
+          sg(dd.cmp(z, 0, VecState{0, 0, -1}, 0)) == 1 && sg(dd.cmp(z, 0, VecState{0, -1, 1}, 0)) == 1 && sg(dd.cmp(z, 0, VecState{0, 0, -1}, 1)) == 1 &&
+          sg(dd.cmp(z, 0, z, 1)) == 0, "cmp returns the first difference (coordinates)");
+    CHECK(sg(dv.cmp(z, 0, VecState{0, 0, 1}, 0)) == -1 && sg(dv.cmp(z, 0, VecState{0, 1, -1}, 0)) == -1 && sg(dv.cmp(z, 0, VecState{0, 0, -1}, 1)) == -1 &&
+          sg(dv.cmp(z, 0, VecState{0, 0, -1}, 0)) == 1 && sg(dv.cmp(z, 0, VecState{0, -1, 1}, 0)) == 1 && sg(dv.cmp(z, 0, VecState{0, 0, 1}, -1)) == 1 &&
+          sg(dv.cmp(z, 0, z, 0)) == 0, "cmp returns the first difference (value first)");
+}
+
 int main() {
     test_flags();
     test_width();
     test_dominance();
+    test_dominance_cmp();
     test_dummy_dd();
     test_locbounds();
     test_fringe();
