@@ -105,6 +105,17 @@ class DivBy:  # width.rs:875-880
         return max(1, self.inner.max_width(sp) // self.k)
 
 
+def solver_gap(lb: int, ub: int) -> float:
+    """Solver::gap (abstraction/solver.rs:80-93): 1.0 while a bound is missing, else (max(|ub|, |lb|) - min(|ub|, |lb|)) / max(|ub|, |lb|) in f32
+    (0 / 0 is NaN, as in the reference)."""
+    if ub == N.I64_MAX or lb == N.I64_MIN:
+        return 1.0
+    u, l = max(abs(ub), abs(lb)), min(abs(ub), abs(lb))
+    if u == 0:
+        return float("nan")
+    return float(np.float32(u - l) / np.float32(u))
+
+
 def _width_spec(width, nb_vars: int):
     """(kind, parameter, largest width it can ask for) of a WidthHeuristic for the C ABI."""
     if isinstance(width, FixedWidth):
@@ -455,12 +466,8 @@ class ParNoCachingSolverLel:
     def best_upper_bound(self) -> int:  # solver.rs:86
         return int(N.lib().ddo_solver_best_upper_bound(self.h))
 
-    def gap(self) -> float:  # solver.rs:84-93
-        lb, ub = self.best_lower_bound(), self.best_upper_bound()
-        lb = N.I64_MAX if lb == N.I64_MIN else abs(lb)
-        ub = N.I64_MAX if ub == N.I64_MIN else abs(ub)
-        u, l = max(lb, ub), min(lb, ub)
-        return 0.0 if u == 0 else (u - l) / u
+    def gap(self) -> float:  # solver.rs:80-93
+        return solver_gap(self.best_lower_bound(), self.best_upper_bound())
 
     def explored(self) -> int:  # solver.rs:96
         return int(N.lib().ddo_solver_explored(self.h))

@@ -4,7 +4,7 @@ import pytest
 
 from ddo_b200 import Decision, DivBy, FixedWidth, NbUnassignedWidth, SubProblem, Times
 from ddo_b200 import _native as N
-from ddo_b200.api import _width_spec
+from ddo_b200.api import _width_spec, solver_gap
 
 
 def _sub(decided):
@@ -32,3 +32,13 @@ def test_width_heuristics_map_onto_the_abi():
     assert _width_spec(DivBy(2, FixedWidth(7)), 500) == (N.WIDTH_FIXED, 3, 3)
     with pytest.raises(TypeError):
         _width_spec(object(), 5)
+
+
+def test_solver_gap_is_the_reference_formula():
+    """abstraction/solver.rs:80-93 and the expectations of parallel.rs:1152-1254 (gap is 1 before the search, 0 once the bounds meet)."""
+    import math
+
+    assert solver_gap(N.I64_MIN, N.I64_MAX) == 1.0 and solver_gap(N.I64_MIN, 220) == 1.0 and solver_gap(5, N.I64_MAX) == 1.0
+    assert solver_gap(220, 220) == 0.0 and solver_gap(-7, -7) == 0.0
+    assert solver_gap(13, 16) == pytest.approx(3 / 16) and solver_gap(-16, -13) == pytest.approx(3 / 16)
+    assert math.isnan(solver_gap(0, 0))
