@@ -981,12 +981,11 @@ public:
         if (best_sol) std::stable_sort(best_sol->begin(), best_sol->end(), [](const Decision& a, const Decision& b) { return a.variable < b.variable; });
         return Completion{!aborted, best_sol ? std::optional<isize>(best_lb) : std::nullopt};
     }
-    double gap() const {  // abstraction/solver.rs:84-93
-        isize lb = best_lb, ub = best_ub;
-        if (lb < 0) { if (lb == ISIZE_MIN) lb = ISIZE_MAX; else lb = -lb; }
-        if (ub < 0) { if (ub == ISIZE_MIN) ub = ISIZE_MAX; else ub = -ub; }
-        isize u = std::max(lb, ub), l = std::min(lb, ub);
-        return u == 0 ? 0.0 : (double)(u - l) / (double)u;  // the reference divides without the zero check
+    double gap() const {  // abstraction/solver.rs:80-93: 1 while a bound is missing, else (u - l) / u over the absolute bounds, in f32
+        if (best_ub == ISIZE_MAX || best_lb == ISIZE_MIN) return 1.0;
+        isize aub = best_ub < 0 ? -best_ub : best_ub, alb = best_lb < 0 ? -best_lb : best_lb;
+        isize u = std::max(aub, alb), l = std::min(aub, alb);
+        return (double)((float)(u - l) / (float)u);  // 0 / 0 is NaN, as in the reference
     }
 private:
     SolverConfig<S> c_;

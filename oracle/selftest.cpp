@@ -255,6 +255,45 @@ static void test_solvers_knapsack() {
             }
 }
 
+static void test_solvers_knapsack7_and_primal() {  // parallel.rs:981-1254, sequential.rs (same vectors): 7 items, set_primal, gap
+    for (int cutset : {LAST_EXACT_LAYER, FRONTIER})
+        for (int flavour = 0; flavour < 2; ++flavour) {
+            Knapsack pb(50, {60, 210, 12, 5, 100, 120, 110}, {10, 45, 20, 4, 20, 30, 50});
+            KPRelax rlx(&pb); KPRanking rk; NbUnassignedWidth<KnapsackState> w(pb.nb_variables()); NoCutoff nocut;
+            EmptyDominanceChecker<KnapsackState> edom;
+            MaxUB<KnapsackState> mx{&rk};
+            NoDupFringe<KnapsackState, KnapsackHash, KnapsackEq> fr(mx);
+            EmptyCache<KnapsackState> ec; SimpleCache<KnapsackState, KnapsackHash, KnapsackEq> sc;
+            Cache<KnapsackState>* cache = cutset == FRONTIER ? (Cache<KnapsackState>*)&sc : (Cache<KnapsackState>*)&ec;  // DdLel / DdFc, parallel.rs:658-659
+            SolverConfig<KnapsackState> cfg{&pb, &rlx, &rk, &w, &edom, &nocut, &fr, cache, cutset};
+            Completion c; Solution sol;
+            if (flavour == 0) { SequentialSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg); c = s.maximize(); sol = *s.best_sol; }
+            else { ParallelSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg, 1); c = s.maximize(); sol = *s.best_sol; }
+            CHECK(c.is_exact && c.best_value == std::optional<isize>(220), "7-item knapsack -> 220 (parallel.rs:981-1150)");
+            CHECK(same_path(sol, {{0, 0}, {1, 0}, {2, 0}, {3, 0}, {4, 1}, {5, 1}, {6, 0}}), "decisions: items 4 and 5 (parallel.rs:1012-1021)");
+        }
+    {   // set_primal_overwrites_best_value_and_sol_if_it_improves (parallel.rs:1153-1199), gap (:1201-1254)
+        Knapsack pb(50, {60, 100, 120}, {10, 20, 30});
+        KPRelax rlx(&pb); KPRanking rk; NbUnassignedWidth<KnapsackState> w(pb.nb_variables()); NoCutoff nocut;
+        EmptyDominanceChecker<KnapsackState> edom; MaxUB<KnapsackState> mx{&rk};
+        NoDupFringe<KnapsackState, KnapsackHash, KnapsackEq> fr(mx); EmptyCache<KnapsackState> ec;
+        SolverConfig<KnapsackState> cfg{&pb, &rlx, &rk, &w, &edom, &nocut, &fr, &ec, LAST_EXACT_LAYER};
+        SequentialSolver<KnapsackState, KnapsackHash, KnapsackEq> s(cfg);
+        CHECK(s.best_lb == ISIZE_MIN && s.best_ub == ISIZE_MAX && !s.best_sol && s.gap() == 1.0, "defaults: lb -inf, ub +inf, no solution, gap 1 (parallel.rs:662-876,1201-1225)");
+        Solution one{Decision{0, 10}};
+        s.set_primal(10, one); CHECK(s.best_sol && s.best_lb == 10, "set_primal(10)");
+        s.set_primal(5, one); CHECK(s.best_sol && s.best_lb == 10, "set_primal(5) does not improve");
+        s.set_primal(10000, one); CHECK(s.best_sol && s.best_lb == 10000, "set_primal(10000)");
+        Completion c = s.maximize();
+        CHECK(c.is_exact && c.best_value == std::optional<isize>(10000) && s.best_sol, "a better primal survives maximize()");
+        NoDupFringe<KnapsackState, KnapsackHash, KnapsackEq> fr2(mx);
+        SolverConfig<KnapsackState> cfg2{&pb, &rlx, &rk, &w, &edom, &nocut, &fr2, &ec, LAST_EXACT_LAYER};
+        SequentialSolver<KnapsackState, KnapsackHash, KnapsackEq> s2(cfg2);
+        Completion c2 = s2.maximize();
+        CHECK(c2.is_exact && c2.best_value == std::optional<isize>(220) && s2.gap() == 0.0, "gap 0 once the optimum is proven (parallel.rs:1227-1254)");
+    }
+}
+
 static void test_width() {  // heuristics/width.rs:884-1075 (test_nbunassigned, test_fixedwidth, test_adapters)
     auto sub = [](size_t decided) {
         SubProblem<char> s{std::make_shared<const char>('a'), 10, {}, 100, decided};
@@ -358,6 +397,7 @@ int main() {
     test_locbounds();
     test_fringe();
     test_solvers_knapsack();
+    test_solvers_knapsack7_and_primal();
     std::printf("%s: %d checks, %d failed\n", g_fail ? "SELFTEST FAILED" : "SELFTEST OK", g_checks, g_fail);
     return g_fail ? 1 : 0;
 }
