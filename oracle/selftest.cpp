@@ -294,6 +294,24 @@ static void test_solvers_knapsack7_and_primal() {  // parallel.rs:981-1254, sequ
     }
 }
 
+static void test_maxub_and_defaults() {  // subproblem_ranking.rs:134-175, abstraction/dp.rs:128-137, cutoff.rs (NoCutoff / TimeBudget)
+    CmpChar rk; MaxUB<char> cmp{&rk};
+    auto sp = [](char c, isize value, isize ub) { return SubProblem<char>{std::make_shared<const char>(c), value, {}, ub, 0}; };
+    auto sg = [](int c) { return c < 0 ? -1 : (c > 0 ? 1 : 0); };
+    CHECK(sg(cmp.compare(sp('a', 42, 300), sp('b', 42, 100))) == 1 && sg(cmp.compare(sp('b', 42, 100), sp('a', 42, 300))) == -1, "MaxUB: upper bound first");
+    CHECK(sg(cmp.compare(sp('a', 42, 300), sp('b', 2, 300))) == 1 && sg(cmp.compare(sp('b', 2, 300), sp('a', 42, 300))) == -1, "MaxUB: then the longest path");
+    CHECK(sg(cmp.compare(sp('a', 42, 300), sp('b', 42, 300))) == -1 && sg(cmp.compare(sp('a', 42, 300), sp('a', 42, 300))) == 0, "MaxUB: then the state ranking; equal to itself");
+    LocBoundsRelax lr; struct NoRub : Relaxation<char> {
+        char merge(const std::vector<const char*>&) const override { return 'M'; }
+        isize relax(const char&, const char&, const char&, Decision, isize c) const override { return c; }
+    } nr;
+    LocBoundsPb pb;
+    CHECK(nr.fast_upper_bound('x') == ISIZE_MAX && pb.is_impacted_by(Variable{10}, 'x'), "defaults: fast_upper_bound = +inf, every state impacted by every variable");
+    (void)lr;
+    NoCutoff nc; TimeBudget far(3600.0), gone(0.0);
+    CHECK(!nc.must_stop() && !far.must_stop() && gone.must_stop(), "NoCutoff never stops; TimeBudget stops only once elapsed");
+}
+
 static void test_width() {  // heuristics/width.rs:884-1075 (test_nbunassigned, test_fixedwidth, test_adapters)
     auto sub = [](size_t decided) {
         SubProblem<char> s{std::make_shared<const char>('a'), 10, {}, 100, decided};
@@ -390,6 +408,7 @@ static void test_dominance_cmp() {  // abstraction/dominance.rs:134-192
 
 int main() {
     test_flags();
+    test_maxub_and_defaults();
     test_width();
     test_dominance();
     test_dominance_cmp();
