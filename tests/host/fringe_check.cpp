@@ -69,13 +69,41 @@ static void push_model(Model& m, int kind, const Burst& b, int W, int PW) {
         o.ub = merged;
     }
 }
+// MaxUB (subproblem_ranking.rs:86-90) over the model's ranking, written from the reference's definitions (not from solver.cu):
+//   MISP    MispRanking = (len, BitSet::cmp) (misp/main.rs:203-208); BitSet::cmp compares the ascending member lists lexicographically;
+//   MAX2SAT Max2SatRanking = rank = sum |benefit| (heuristics.rs:33-37), refined canonically by (depth, lexicographic signed benefits).
+static int ref_cmp(int kind, int W, const uint64_t* sa, const NoDupFringe::Item& a, const uint64_t* sb, const NoDupFringe::Item& b) {
+    if (a.ub != b.ub) return a.ub < b.ub ? -1 : 1;
+    if (a.value != b.value) return a.value < b.value ? -1 : 1;
+    if (kind == DDO_MODEL_MAX2SAT) {
+        const int32_t* x = reinterpret_cast<const int32_t*>(sa); const int32_t* y = reinterpret_cast<const int32_t*>(sb);
+        long long rx = 0, ry = 0;
+        for (int j = 0; j < 2 * W; ++j) { rx += std::llabs((long long)x[j]); ry += std::llabs((long long)y[j]); }
+        if (rx != ry) return rx < ry ? -1 : 1;
+        if (a.depth != b.depth) return a.depth < b.depth ? -1 : 1;
+        for (int j = 0; j < 2 * W; ++j) if (x[j] != y[j]) return x[j] < y[j] ? -1 : 1;
+        return 0;
+    }
+    std::vector<int> ma, mb;
+    for (int v = 0; v < 64 * W; ++v) { if ((sa[v >> 6] >> (v & 63)) & 1) ma.push_back(v); if ((sb[v >> 6] >> (v & 63)) & 1) mb.push_back(v); }
+    if (ma.size() != mb.size()) return ma.size() < mb.size() ? -1 : 1;
+    if (ma == mb) return 0;
+    return std::lexicographical_compare(ma.begin(), ma.end(), mb.begin(), mb.end()) ? -1 : 1;
+}
+
 // pops `count` nodes of f: each must be the model's entry for its state, and the (ub, value) keys must never increase (MaxUB order,
 // subproblem_ranking.rs:86-90)
 static int check_against_model(NoDupFringe& f, Model& m, int kind, int W, int PW, size_t count, const char* what) {
     std::tuple<int32_t, int32_t> prev{INT32_MAX, INT32_MAX};
+    std::vector<uint64_t> prev_state; NoDupFringe::Item prev_item{};
     for (size_t i = 0; i < count && !f.empty(); ++i) {
         const int x = f.pop();
         const NoDupFringe::Item it = f.item(x);
+        if (!prev_state.empty() && ref_cmp(kind, W, prev_state.data(), prev_item, f.state(x), it) <= 0) {
+            std::printf("FAIL %s: pop %zu is not below its predecessor in the reference's MaxUB order\n", what, i);
+            return 1;
+        }
+        prev_state.assign(f.state(x), f.state(x) + W); prev_item = it;
         auto key = model_key(kind, f.state(x), W, it.depth);
         auto mi = m.find(key);
         if (mi == m.end()) { std::printf("FAIL %s: popped a state the model does not hold\n", what); return 1; }
