@@ -17,7 +17,7 @@ REF = Path("/root/reference")
 OUT = Path(__file__).resolve().parent
 
 MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "keller4", "hamming8-2", "hamming8-4",
-        "brock200_2", "brock200_3", "brock200_4", "c-fat200-5"]
+        "brock200_2", "brock200_3", "brock200_4", "c-fat200-5", "c-fat200-1", "c-fat200-2", "p_hat300-1"]
 KNAPSACK_MAX_ITEMS = 200
 TSPTW = ["Langevin/N20ft301.dat", "Langevin/N20ft405.dat", "Langevin/N40ft403.dat", "Langevin/N60ft406.dat", "Langevin/N60ft410.dat",
          "SolomonPotvinBengio/rc_201.1.txt", "SolomonPotvinBengio/rc_201.3.txt", "SolomonPotvinBengio/rc_202.2.txt", "SolomonPotvinBengio/rc_203.1.txt",

@@ -100,7 +100,8 @@ def _expected(golden_dir):
     return json.loads((golden_dir / "expected.json").read_text())
 
 
-FAST_MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "hamming8-2", "brock200_2", "c-fat200-5"]
+FAST_MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "hamming8-2", "brock200_2", "c-fat200-5", "c-fat200-1", "c-fat200-2",
+             "p_hat300-1"]
 SLOW_MISP = ["keller4", "brock200_3"]
 
 
