@@ -42,6 +42,34 @@ struct M2Handle {
         for (size_t i = 0; i < pb.nb_vars; ++i) q[i] = (int32_t)s.sub[i];
     }
 };
+// TSPTW states cross the ABI as 16 uint64 words (the depth travels separately, like MAX2SAT):
+//   [0] position: bit 63 set = Position::Virtual, else the node id in the low 16 bits      [1..4]  the Virtual pool (Set256)
+//   [5] earliest (= duration of a FixedAmount)   [6] latest (= earliest when FixedAmount)   [7] flags: bit 0 FuzzyAmount, bit 1 maybe_visit is Some
+//   [8..11] must_visit (Set256)                  [12..15] maybe_visit (Set256, zero when None)
+struct TsptwHandle {
+    using State = TsptwState; using Hash = TsptwHash; using Eq = TsptwEq;
+    Tsptw pb;
+    TsptwRelax rlx;
+    TsptwRanking rk;
+    explicit TsptwHandle(TsptwInstance inst) : pb(std::move(inst)), rlx(&pb) {}
+    size_t abi_words() const { return 16; }
+    State state_from_abi(const uint64_t* p, size_t depth) const {
+        TsptwState s;
+        s.virtual_pos = (p[0] >> 63) & 1; s.node = (uint16_t)(p[0] & 0xFFFF);
+        for (int j = 0; j < 4; ++j) { s.pool.w[j] = s.virtual_pos ? p[1 + j] : 0; s.must_visit.w[j] = p[8 + j]; }
+        s.earliest = (size_t)p[5]; s.fuzzy = p[7] & 1; s.latest = s.fuzzy ? (size_t)p[6] : s.earliest;
+        s.has_maybe = (p[7] >> 1) & 1;
+        for (int j = 0; j < 4; ++j) s.maybe_visit.w[j] = s.has_maybe ? p[12 + j] : 0;
+        s.depth = (uint16_t)depth;
+        return s;
+    }
+    void state_to_abi(const State& s, uint64_t* p) const {
+        std::memset(p, 0, 16 * 8);
+        p[0] = s.virtual_pos ? (1ull << 63) : (uint64_t)s.node;
+        for (int j = 0; j < 4; ++j) { if (s.virtual_pos) p[1 + j] = s.pool.w[j]; p[8 + j] = s.must_visit.w[j]; if (s.has_maybe) p[12 + j] = s.maybe_visit.w[j]; }
+        p[5] = s.earliest; p[6] = s.fuzzy ? s.latest : s.earliest; p[7] = (s.fuzzy ? 1u : 0u) | (s.has_maybe ? 2u : 0u);
+    }
+};
 template <class H>
 struct DD {
     using S = typename H::State;
@@ -387,6 +415,32 @@ int32_t oracle_knapsack_solve(int32_t n, int64_t capacity, const int64_t* profit
     if (taken && sol) { for (int32_t i = 0; i < n; ++i) taken[i] = 0; for (auto& d : *sol) taken[d.variable] = (int32_t)d.value; }
     return 0;
 }
+
+// TSPTW at the DD level (the checker of the device model to come): same entry points as the MISP / MAX2SAT models
+static TsptwInstance make_tsptw_instance(int32_t n, const int64_t* dist, const int64_t* tw) {
+    TsptwInstance inst;
+    inst.nb_nodes = (size_t)n;
+    inst.distances.assign((size_t)n, std::vector<size_t>((size_t)n, 0));
+    for (int32_t i = 0; i < n; ++i) for (int32_t j = 0; j < n; ++j) inst.distances[i][j] = (size_t)dist[(size_t)i * n + j];
+    for (int32_t i = 0; i < n; ++i) inst.timewindows.push_back(TimeWindow{(size_t)tw[2 * i], (size_t)tw[2 * i + 1]});
+    return inst;
+}
+void* oracle_tsptw_new(int32_t n, const int64_t* dist, const int64_t* tw) { return new TsptwHandle(make_tsptw_instance(n, dist, tw)); }
+void oracle_tsptw_free(void* h) { delete (TsptwHandle*)h; }
+int32_t oracle_tsptw_words(void* h) { return (int32_t)((TsptwHandle*)h)->abi_words(); }
+void oracle_tsptw_initial_state(void* hp, uint64_t* out) { TsptwHandle* h = (TsptwHandle*)hp; h->state_to_abi(h->pb.initial_state(), out); }
+void* oracle_tsptw_dd_new(void* h, int32_t cutset_type) { return new DD<TsptwHandle>((TsptwHandle*)h, cutset_type); }
+void oracle_tsptw_dd_free(void* dd) { delete (DD<TsptwHandle>*)dd; }
+int32_t oracle_tsptw_dd_compile(void* ddp, int32_t comp_type, uint64_t max_width, const uint64_t* root_state, int64_t root_value,
+                                uint64_t root_depth, int64_t best_lb, int32_t cutoff_now, oracle_dd_result* out) {
+    return dd_compile((DD<TsptwHandle>*)ddp, comp_type, max_width, root_state, root_value, root_depth, best_lb, cutoff_now, out);
+}
+int32_t oracle_tsptw_dd_layers(void* ddp, int32_t* vars, int32_t* widths, int32_t cap) { return dd_layers((DD<TsptwHandle>*)ddp, vars, widths, cap); }
+int32_t oracle_tsptw_dd_cutset(void* ddp, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, int32_t* path_lens, int32_t* paths,
+                               int32_t cap, int32_t path_stride) {
+    return dd_cutset((DD<TsptwHandle>*)ddp, states, values, ubs, depths, path_lens, paths, cap, path_stride);
+}
+int32_t oracle_tsptw_dd_solution(void* ddp, int32_t exact, int32_t* vars, int32_t* vals, int32_t cap) { return dd_solution((DD<TsptwHandle>*)ddp, exact, vars, vals, cap); }
 
 // TSPTW (BASELINE config 4), examples/tsptw/main.rs:66-84 and tests.rs:33-57: TsptwWidth(nb_vars, factor), SimpleDominanceChecker(TsptwDominance),
 // NoDupFringe(MaxUB(TsptwRanking)), DefaultCachingSolver = ParCachingSolverFc (FRONTIER cutset + SimpleCache, solver/mod.rs:30,37).

@@ -103,6 +103,18 @@ def lib():
         _lib.oracle_m2s_stepper_set_lb.argtypes = [C.c_void_p, C.c_int64]
         _lib.oracle_m2s_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         _lib.oracle_m2s_stepper_finish.argtypes = [C.c_void_p]
+        _lib.oracle_tsptw_new.restype = C.c_void_p
+        _lib.oracle_tsptw_new.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.oracle_tsptw_free.argtypes = [C.c_void_p]
+        _lib.oracle_tsptw_words.argtypes = [C.c_void_p]
+        _lib.oracle_tsptw_initial_state.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.oracle_tsptw_dd_new.restype = C.c_void_p
+        _lib.oracle_tsptw_dd_new.argtypes = [C.c_void_p, C.c_int32]
+        _lib.oracle_tsptw_dd_free.argtypes = [C.c_void_p]
+        _lib.oracle_tsptw_dd_compile.argtypes = _lib.oracle_misp_dd_compile.argtypes
+        _lib.oracle_tsptw_dd_layers.argtypes = _lib.oracle_misp_dd_layers.argtypes
+        _lib.oracle_tsptw_dd_cutset.argtypes = _lib.oracle_misp_dd_cutset.argtypes
+        _lib.oracle_tsptw_dd_solution.argtypes = _lib.oracle_misp_dd_solution.argtypes
         _lib.oracle_knapsack_solve.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                                C.POINTER(SolveResult), C.c_void_p]
         _lib.oracle_locbounds_dump.argtypes = [C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
@@ -264,6 +276,27 @@ class OracleM2s(_OracleModel):
         out["solution"] = list(zip(sv[: sl.value].tolist(), sx[: sl.value].tolist()))
         out["trace"] = trace[: tl.value].copy()
         return out
+
+
+class OracleTsptw(_OracleModel):
+    """CPU oracle for one TSPTW instance at the DD level (states: 16 uint64 words, see oracle_capi.cpp::TsptwHandle) -- the checker of the
+    TSPTW device model to come; `compile` is the shared _OracleModel.compile."""
+
+    PREFIX = "tsptw"
+
+    def __init__(self, inst):
+        self.inst = inst
+        self.h = lib().oracle_tsptw_new(inst.n, _p(np.ascontiguousarray(inst.dist)), _p(np.ascontiguousarray(inst.tw)))
+        self.words = lib().oracle_tsptw_words(self.h)
+        inst.initial_state = self.initial_state  # what _OracleModel.compile asks the instance for
+
+    def initial_state(self):
+        out = np.zeros(self.words, dtype=np.uint64)
+        lib().oracle_tsptw_initial_state(self.h, _p(out))
+        return out
+
+    def initial_value(self):
+        return 0
 
 
 def _m2s_compile_many(self, roots_states, roots_values, roots_depths, widths, best_lb, threads, cutset_type=LEL, time_budget_s=0.0):

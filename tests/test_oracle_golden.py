@@ -275,3 +275,46 @@ def test_tsptw_instance_scaling_is_f32():
     inst = O.TsptwInstance("2\n0 70.3\n79.4 0\n0 1000.5\n10.25 408\n")
     assert inst.dist.tolist() == [[0, int(np.float32(70.3) * np.float32(10000.0))], [794000, 0]]
     assert inst.tw.tolist() == [[0, 10005000], [102500, 4080000]]
+
+
+def test_tsptw_dd_level_checker(golden_dir):
+    """The DD-level entry points the TSPTW device model will be compared against (oracle_capi.cpp::TsptwHandle, 16-word packed states):
+    restricted <= optimum <= relaxed, the frontier cutset is a superset in size of nothing less than the last exact layer's marked nodes'
+    parents, states survive the ABI round trip, and branching on a relaxed DD's exact cutset recovers the optimum."""
+    from ddo_b200 import parse_tsptw
+
+    recovered = 0
+    for name in ("SolomonPotvinBengio/rc_207.4.txt", "SolomonPotvinBengio/rc_203.4.txt", "SolomonPotvinBengio/rc_205.1.txt"):
+        inst = parse_tsptw((golden_dir / "tsptw" / name).read_text())
+        opt = O.tsptw_solve(inst)["best_value"]
+        o = O.OracleTsptw(inst)
+        for cutset in (O.LEL, O.FRONTIER):
+            width = 2 if inst.n <= 6 else 5
+            lo = o.compile(O.RESTRICTED, width, cutset_type=cutset)
+            hi = o.compile(O.RELAXED, width, cutset_type=cutset, want_paths=True)
+            assert (not lo["has_best"]) or lo["best_value"] <= opt
+            assert hi["has_best"] and hi["best_value"] >= opt
+            if hi["is_exact"]:
+                assert hi["best_value"] == opt
+                continue
+            assert hi["cutset_size"] > 0
+            assert all(len(p) == d for p, d in zip(hi["cutset_paths"], hi["cutset_depths"].tolist()))
+            assert all(int(u) <= hi["best_value"] for u in hi["cutset_ubs"].tolist())
+            # every cutset node is an exact sub-problem: the best of their own optima (wide restricted DDs are exact here) is the optimum
+            best, all_exact = None, True
+            for i in range(hi["cutset_size"]):
+                if int(hi["cutset_ubs"][i]) < opt:
+                    continue
+                sub = o.compile(O.RESTRICTED, 2000, root_state=hi["cutset_states"][i], root_value=int(hi["cutset_values"][i]),
+                                root_depth=int(hi["cutset_depths"][i]))
+                all_exact = all_exact and bool(sub["is_exact"])
+                if sub["has_best"]:
+                    best = sub["best_value"] if best is None else max(best, sub["best_value"])
+            assert best is None or best <= opt
+            if all_exact:
+                assert best == opt, (name, cutset, best, opt)
+                recovered += 1
+        # the layer-1 width of a relaxed DD is never cut (clean.rs:789), the others are bounded by max_width
+        w = o.compile(O.RELAXED, 5)["layer_widths"].tolist()
+        assert w[0] == 1 and all(x <= 5 for x in w[2:])
+    assert recovered >= 1
