@@ -493,7 +493,9 @@ class ParNoCachingSolverLel:
 
 
 class ParNoCachingSolverFc(ParNoCachingSolverLel):
-    """`ParNoCachingSolverFc` (solver/mod.rs): the same solver over DDs with the FRONTIER cutset (clean.rs:586-606).  MISP device model."""
+    """`ParNoCachingSolverFc` (solver/mod.rs:33): the same solver over DDs with the FRONTIER cutset (clean.rs:586-606), both device models.
+    A FRONTIER engine keeps 12 B per (layer, position) per DD slot on top of the engine's arenas: pass ``batch_cap`` for wide DDs
+    (e.g. 512 slots at W = 10 000, n = 500 are 33 + 31 GB)."""
     CUTSET_TYPE = FRONTIER
 
 
