@@ -318,3 +318,43 @@ def test_tsptw_dd_level_checker(golden_dir):
         w = o.compile(O.RELAXED, 5)["layer_widths"].tolist()
         assert w[0] == 1 and all(x <= 5 for x in w[2:])
     assert recovered >= 1
+
+
+def test_frontier_and_lel_solvers_agree_with_brute_force():
+    """The oracle's FRONTIER path is the checker of the device's frontier kernels: on small random instances the sequential, wave and
+    parallel solvers with either cutset type must all prove the brute-force optimum (MISP: maximum weight independent set by enumeration;
+    MAX2SAT: best assignment by enumeration)."""
+    import itertools
+
+    from ddo_b200 import gnp, random_max2sat
+
+    for seed in range(6):
+        inst = gnp(16, 0.3, 100 + seed)
+        rng = np.random.default_rng(seed)
+        inst.weights[:] = rng.integers(1, 9, size=inst.n)
+        adj = np.zeros((inst.n, inst.n), dtype=bool)
+        adj[inst.src, inst.dst] = True
+        adj[inst.dst, inst.src] = True
+        best = 0
+        for mask in range(1 << inst.n):
+            vs = [v for v in range(inst.n) if mask >> v & 1]
+            if all(not adj[a, b] for a, b in itertools.combinations(vs, 2)):
+                best = max(best, int(inst.weights[vs].sum()))
+        o = O.OracleMisp(inst)
+        for width in (1, 2, 5):
+            for cutset in (O.LEL, O.FRONTIER):
+                for mode, k in (("sequential", 1), ("wave", 4), ("parallel", 3)):
+                    r = o.solve(mode, k=k, width=width, cutset_type=cutset)
+                    assert r["is_exact"] and r["best_value"] == best, (seed, width, cutset, mode)
+    for seed in range(4):
+        inst = random_max2sat(10, 40, 200 + seed)
+        uniq = {}
+        for w, x, y in inst.clauses.tolist():
+            uniq[(min(x, y), max(x, y))] = w
+        best = max(sum(w for (x, y), w in uniq.items() if (a >> (abs(x) - 1) & 1) == (x > 0) or (a >> (abs(y) - 1) & 1) == (y > 0)) for a in range(1 << inst.n))
+        o = O.OracleM2s(inst)
+        for width in (1, 3):
+            for cutset in (O.LEL, O.FRONTIER):
+                for mode, k in (("sequential", 1), ("wave", 4)):
+                    r = o.solve(mode, k=k, width=width, cutset_type=cutset)
+                    assert r["is_exact"] and r["best_value"] == best, (seed, width, cutset, mode)
