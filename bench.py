@@ -3,9 +3,12 @@
 
 One STEP = one `Solver::maximize()` of the instance to proven optimality (solver.rs:56): the root restricted + relaxed DD (width 10 000,
 500 layers) and then every open sub-problem of the branch-and-bound, in waves of `--wave` DDs compiled in lock-step on the device.
-`value` = nodes expanded (the rough-upper-bound test of clean.rs:365 passed) / device time of the compilations (CUDA events on the
-engine's stream, instance resident in HBM); `e2e` = the same count / wall clock of ddo_solver_maximize (host fringe, H2D of every wave's
-roots, D2H of completions and cutsets inside the timed region).  N > 1: the fringe is sharded over the ranks (ddo_b200/sharded.py).
+`value` = nodes expanded (the rough-upper-bound test of clean.rs:365 passed) / WALL CLOCK of ddo_solver_maximize, max over ranks (SURVEY.md
+section 8(d): instance upload excluded, fringe and collectives included; the instance is resident in HBM when the timed region starts);
+`device_value` = the same count / device time of the compilations (CUDA events on the engine's stream); `e2e` = through the reference-
+facing call with host buffers (for this path the same call: every wave's roots go H2D, completions and cutsets D2H inside the timed
+region).  N > 1: the fringe is sharded over the ranks (ddo_b200/sharded.py).  Before printing, the line's objective / bound / explored /
+expanded are checked against the committed oracle trajectory of this exact configuration (tests/golden/config2_trajectory_k<wave>.json).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--wave B] [--impl reference]
 """
@@ -200,20 +203,21 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         dist.destroy_process_group()
         return
+    golden = check_against_golden(wl, args, world, last, explored_all, expanded_all / args.steps)
     cbar = transitions_all / max(expanded_all, 1)
     S_bytes = wl.state_bytes(pb)
     b_node = (S_bytes + 8) + cbar * (S_bytes + 16)  # read the parent once, write each child once
     peak, peak_src = load_peaks()
     line = {
-        "metric": wl.metric, "value": expanded_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype,
+        "metric": wl.metric, "value": expanded_all / wall_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall_max * 1e3 / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype,
         "data": "synthetic", "impl": "ddo_b200",
         "config": {"workload": f"{wl.step_desc}, {wl.desc}",
                    "wave_size": args.wave, "batch_cap": args.batch_cap, "objective": int(last["best_lb"]), "proven_upper_bound": int(last["best_ub"]), "is_exact": bool(last["is_exact"]),
                    "explored_subproblems": int(explored_all), "expanded_nodes_per_step": int(expanded_all / args.steps), "waves_per_step_rank0": int(last["waves"]),
                    "l2": "no L2 flush: every step re-runs the whole search (thousands of launches over >10 GB of arenas), far beyond the 126 MB L2",
                    "parallelism": f"fringe sharded over {world} GPU(s); one allreduce(max) of 3 x int64 per wave, no data-path collective"},
-        "wall_ms_per_step": wall_max * 1e3 / args.steps,
+        "device_value": expanded_all / (dev_ms * 1e-3), "device_ms_per_step": dev_ms / args.steps, "golden_check": golden,
         "e2e": {"value": expanded_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "note": "wall clock of ddo_solver_maximize (host fringe, H2D of every wave's roots, D2H of completions and cutsets included)"},
         "gpu_launches": int(launches_all),
@@ -221,12 +225,14 @@ def run_ours(args, rank, world, local_rank):
         "host_fringe_ms_per_step": last["fringe_ms"],
     }
     if kt is not None:
+        if wl.kind == "misp" and kt["k_finish"]["launches"] == 0:  # the persistent whole-DD kernel times in the first slot
+            kt["k_dd"] = kt.pop("k_expand"); kt.pop("k_finish"); kt.pop("k_compact")
         if wl.kind != "misp":
             kt["m2_merge"] = kt.pop("k_small")  # the MAX2SAT engine times its merge kernels in that slot
         dom = max((k for k in kt if k not in ("k_finalize_bottomup", "k_drain")), key=lambda k: kt[k]["ms"])
         dom_gbs = last["expanded"] * b_node / (kt[dom]["ms"] * 1e-3) / 1e9
         traffic = None
-        tf = ROOT / "profiles" / ("r01_traffic.json" if wl.kind == "misp" else "r01_traffic_max2sat.json")
+        tf = ROOT / "profiles" / ("r02_traffic.json" if wl.kind == "misp" else "r01_traffic_max2sat.json")
         if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
             tj = json.loads(tf.read_text())
             for t in tj.get("entries", [tj]):
@@ -240,13 +246,69 @@ def run_ours(args, rank, world, local_rank):
                             "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in kt.items()},
                             "kernel_launches_per_step": {k: v["launches"] for k, v in kt.items()},
                             "achieved_by_kernel": {k: round(last["expanded"] * b_node / (v["ms"] * 1e-3) / 1e9, 1) for k, v in kt.items() if v["ms"] > 0 and k not in ("k_finalize_bottomup", "k_drain")},
-                            "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak,
+                            "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak, "whole_step_frac_wall": (expanded_all / wall_max) * b_node / 1e9 / peak,
                             "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
+    if world == 1 and wl.kind == "misp" and not args.no_config3:
+        line["configs"] = {"config3_max2sat": second_workload_line(args, local_rank)}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def check_against_golden(wl, args, world, last, explored_all, expanded_per_step):
+    """The bench's own configuration against the committed oracle trajectory (tests/golden/config2_trajectory_k<wave>.json, made by
+    tests/golden/make_trajectory.py): objective and proven bound at every N; sub-problems explored and nodes expanded at N = 1, where the
+    search is the oracle wave solver's.  A mismatch is an error, not a number."""
+    if wl.kind != "misp":
+        return {"checked": False, "why": "config 3 is far beyond a proof: parity is tested on DD digests (tests/golden/dd_digests.json)"}
+    f = ROOT / "tests" / "golden" / f"config2_trajectory_k{args.wave}.json"
+    if not f.exists():
+        return {"checked": False, "why": f"no golden for wave {args.wave}"}
+    g = json.loads(f.read_text())
+    if (int(last["best_lb"]), int(last["best_ub"]), bool(last["is_exact"])) != (g["best_lb"], g["best_ub"], True):
+        raise RuntimeError(f"bench result {last['best_lb']} / {last['best_ub']} differs from the oracle golden {g['best_lb']} / {g['best_ub']}")
+    if world == 1 and (int(explored_all), int(expanded_per_step)) != (g["explored"], g["expanded"]):
+        raise RuntimeError(f"bench trajectory (explored {explored_all}, expanded {expanded_per_step}) differs from the oracle golden ({g['explored']}, {g['expanded']})")
+    return {"checked": True, "file": f.name, "objective": g["best_lb"], "explored": g["explored"] if world == 1 else None, "expanded": g["expanded"] if world == 1 else None}
+
+
+def second_workload_line(args, local_rank):
+    """BASELINE config 3 (MAX2SAT 500 vars / 3000 clauses, W = 5000) measured in the same run, so that the driver's default invocation carries a
+    number for it: same definitions as the main line (value = expanded / wall clock of maximize(), device_value = / device time)."""
+    import copy
+    from ddo_b200 import FixedWidth, ParNoCachingSolverLel
+    a = copy.copy(args)
+    a.workload, a.wave, a.batch_cap, a.max_waves = "max2sat", 148, 148, 0
+    wl = Workload(a)
+    pb = wl.problem(local_rank)
+    solver = ParNoCachingSolverLel(pb, FixedWidth(wl.width), wave_size=a.wave, batch_cap=a.batch_cap)
+    solver.maximize(max_waves=wl.max_waves)  # warm-up
+    exp = wall = dev = 0.0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        solver.maximize(max_waves=wl.max_waves)
+        wall += time.perf_counter() - t0
+        st = solver.stats()
+        exp += st["expanded"]; dev += st["device_ms"]
+    S_bytes = wl.state_bytes(pb)
+    b_node = (S_bytes + 8) + 2 * (S_bytes + 16)
+    peak, _ = load_peaks()
+    out = {"metric": wl.metric, "value": exp / wall, "unit": UNIT, "device_value": exp / (dev * 1e-3), "steps": 2, "warmup": 1, "ms_per_step": wall * 1e3 / 2,
+           "workload": f"{wl.step_desc}, {wl.desc}", "whole_step_frac": exp / (dev * 1e-3) * b_node / 1e9 / peak, "bytes_per_node": b_node}
+    solver.close() if hasattr(solver, "close") else None
+    return out
+
+
+def cpu_baseline_subprocess(args):
+    """The CPU leg runs in its own process AFTER the timed region (it would otherwise dilute every GPU-busy sample of this process)."""
+    cmd = [sys.executable, str(Path(__file__).resolve()), "--cpu-baseline-only", "--workload", args.workload, "--cpu-seconds", str(args.cpu_seconds)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"error": (r.stderr or r.stdout)[-300:]}
 
 
 def cpu_baseline(wl, budget_s: float):
@@ -307,21 +369,24 @@ def run_reference(args, rank, world):
         print(json.dumps(line), flush=True)
         return
     o = wl.oracle()
-    budget = max(10.0, min(args.cpu_seconds, 200.0 / max(args.steps, 1)))
+    # every step is maximize() of the SAME instance and width under a TimeBudget of >= 30 s, long enough that the single-threaded root DDs
+    # (W = 10 000) are a small part of it; on a box that finishes the proof inside the box the arm runs the same configuration as ours
+    budget = max(30.0, min(120.0, 300.0 / max(args.steps, 1)))
     small = gnp(200, 0.5, SEED)
     os_ = O.OracleMisp(small)
     for _ in range(args.warmup):  # untimed: a small instance, warms the allocator and the thread pool
         os_.solve("parallel", k=cores, width=100, time_budget_s=2.0)
-    exp, sec, last = 0, 0.0, None
+    exp, sec, last, finished = 0, 0.0, None, True
     for _ in range(args.steps):
         last = o.solve("parallel", k=cores, width=wl.width, time_budget_s=budget)
-        exp += last["expanded"]; sec += last["seconds"]
+        exp += last["expanded"]; sec += last["seconds"]; finished = finished and bool(last["is_exact"])
     v = exp / sec
-    sample = f"ParallelSolver({cores} threads) maximize() under TimeBudget({budget:g} s) per step"
+    sample = f"ParallelSolver({cores} threads) maximize() under TimeBudget({budget:g} s) per step ({'proof completed' if finished else 'cut off before the proof'})"
     line = {"metric": wl.metric, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": wl.dtype.replace("i32 value", "i64 value"), "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"Solver::maximize (time-boxed), {wl.desc}",
-                       "note": "oracle port of ddo's ParallelSolver (Rust toolchain absent); CPU only, rank 0 only", "lb_at_cutoff": int(last["best_lb"])},
+            "config": {"workload": f"Solver::maximize ({'to proven optimality' if finished else 'time-boxed'}), {wl.desc}",
+                       "note": "C++ port of ddo's ParallelSolver (oracle/; the Rust toolchain is absent) -- kind 'port', never real ddo; CPU only, rank 0 only", "lb_at_cutoff": int(last["best_lb"])},
+            "same_config": finished,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -334,11 +399,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--wave", type=int, default=2048, help="open sub-problems popped per wave and per GPU")
     ap.add_argument("--batch-cap", type=int, default=512, help="DDs the general (layer-by-layer) engine compiles in lock-step")
-    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="TimeBudget of the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="TimeBudget of the CPU baseline sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="misp", choices=["misp", "max2sat"], help="misp = BASELINE config 2 (the headline metric); max2sat = config 3")
     ap.add_argument("--max-waves", type=int, default=0, help="max2sat: waves per step (default 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the secondary MAX2SAT (config 3) measurement carried under 'configs'")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave -- one DD per SM (m2_finish is one CTA per DD)
         if args.wave == 2048: args.wave = 148
@@ -346,6 +413,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline(Workload(args), args.cpu_seconds)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -225,7 +225,7 @@ int64_t ddo_solver_best_upper_bound(const ddo_solver* s) { return s->s->best_ub;
 int ddo_solver_best_value(const ddo_solver* s, int32_t* has, int64_t* value) {
     if (!s) return DDO_ERR_INVALID;
     if (has) *has = s->s->has_sol;
-    if (value) *value = s->s->has_sol ? s->s->best_lb : 0;
+    if (value) *value = s->s->has_sol ? s->s->sol_value : 0;  // the objective of the solution THIS solver holds (best_lb may come from another rank)
     return DDO_OK;
 }
 int ddo_solver_best_solution(const ddo_solver* s, ddo_decision* out, int32_t* len) {

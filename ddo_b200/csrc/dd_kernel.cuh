@@ -1,0 +1,898 @@
+// dd_kernel.cuh -- k_dd: the whole of Mdd::compile (ddo/src/implementation/mdd/clean.rs:345-381 and everything it calls per layer) for
+// one decision diagram inside ONE persistent kernel (MISP device model, sm_100a).
+//
+// Round 1 ran a layer step of the whole batch as three dependent launches (k_finish / k_compact / k_expand); a solve of BASELINE config 2
+// is ~2 800 such steps and the chain, not bandwidth, was its critical path.  Here a thread-block CLUSTER owns one DD from its root to its
+// terminal layer: the layer loop runs inside the kernel, the phases of a layer are separated by cluster barriers (~0.2 us) instead of
+// launches, and the DDs of a batch advance independently -- clusters pull DD slots from a device-side queue, a restricted DD that takes its
+// first width cut publishes its relaxed twin to the same queue (parallel.rs:419-430: the relaxed DD is compiled only when the restricted
+// one is inexact).  The cluster size is chosen per launch: wide clusters when the batch holds a few wide DDs (latency), single CTAs when it
+// holds hundreds (throughput).
+//
+// The layer step itself is restated around one property of MISP under `next_variable` = vertex occurring in the fewest states
+// (misp/main.rs:109-143): most nodes of a layer do NOT contain the branching vertex (mean out-degree 1.18 on config 2), so their only child
+// has their own state, value and exactness (main.rs:77-102).  Such an IDENTITY candidate is never materialised: the dedup table entry, the
+// width-cut keys and the commit of the next layer refer to the parent's row; its hash accumulator, popcount and rough upper bound are
+// carried over; only nodes that contain the vertex (and pruned nodes) touch their 64..128-byte rows before the commit.  The per-vertex
+// occurrence counts behind `next_variable` are maintained INCREMENTALLY (rows that leave the layer are subtracted, rows that enter are
+// added) instead of being recounted over every distinct state of every layer.
+//
+// Semantics are those of kernels.cuh (same canonical rules C1-C4, same logs plog / clog / nlog / vlog / rslog / lel_* and DDCtl fields), so
+// k_finalize, k_bottomup, the cutset drains and the FRONTIER kernels consume a DD compiled here unchanged.
+#pragma once
+#include "kernels.cuh"
+
+namespace ddo {
+
+constexpr int DD_NT = 512, DD_NW = DD_NT / 32;
+constexpr uint32_t DD_IDENT = 1u << 30;          // candidate flag: the state row of this candidate is its parent's row in the current layer
+constexpr uint32_t DD_CMASK = DD_IDENT - 1u;
+
+// byte offsets into the dynamic shared memory of a CTA (computed on the host, dd_layout())
+struct DDLayout {
+    int slice, maxch, capc, smem_keys;  // nodes of a layer per CTA, 32-node chunks per CTA, candidates per CTA, keys / lists in shared memory ?
+    unsigned o_D, o_master, o_stage, o_cnt, o_off, o_koff, o_fb, o_kb, o_keys, o_ulist, o_stat, total;
+};
+
+struct DDFixed {
+    int scan[40];
+    unsigned long long red64[40];
+    unsigned int hist[2][256];
+    unsigned int ghist[256];
+    unsigned long long merged[2][16];  // [0] OR of the merged-away states of this CTA, [1] of the cluster
+    unsigned long long xch[2][8];      // exchange slots (double-buffered across cluster barriers)
+    int misc[16];
+    int job;
+    unsigned long long cnt[2];         // expanded nodes / transitions of the DD being compiled (this CTA's share)
+    unsigned int tour[DD_NT];
+};
+
+// ---- hashing: multilinear over the 32-bit halves, h = fin(sum_j w32[j] * m32[j]); the accumulator is stored with every node so that the
+// NO child of a node (one bit cleared) and an identity child cost no pass over the row
+__device__ __forceinline__ uint32_t dd_mul32(int j) { return (uint32_t)(mix64(0x9E3779B97F4A7C15ULL * (uint64_t)(j + 1)) >> 32) | 1u; }
+template <int S> __device__ __forceinline__ uint64_t dd_hacc(const uint64_t (&w)[S]) {
+    uint64_t a = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) a += (uint64_t)(uint32_t)w[j] * dd_mul32(2 * j) + (uint64_t)(uint32_t)(w[j] >> 32) * dd_mul32(2 * j + 1);
+    return a;
+}
+__device__ __forceinline__ uint64_t dd_hfin(uint64_t a) { a ^= a >> 32; a *= 0x9E3779B97F4A7C15ULL; a ^= a >> 29; return a; }
+
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// ---- device work queue: q[0] next primary, q[1] / q[2] head / tail of the twin queue, q[3] DDs finished or never needed, q[4] total
+__device__ int dd_fetch_job(const EV& ev, int count) {
+    int* q = ev.dq;
+    const long long t0 = clock64();
+    for (;;) {
+        if (clock64() - t0 > 20000000000ll) { q[5] = 1; return -1; }  // watchdog (~10 s): a lost job must not hang the device
+        const int t2 = ld_volatile_i32(q + 2), h2 = ld_volatile_i32(q + 1);
+        if (h2 < t2) {  // twins first: they are the wide DDs of the batch
+            if (atomicCAS(q + 1, h2, h2 + 1) == h2) {
+                int s;
+                while ((s = ld_volatile_i32(ev.dq_jobs + h2)) < 0) __nanosleep(100);
+                return s;
+            }
+            continue;
+        }
+        const int h1 = ld_volatile_i32(q);
+        if (h1 < count) {
+            if (atomicCAS(q, h1, h1 + 1) == h1) return h1;
+            continue;
+        }
+        if (ld_volatile_i32(q + 3) >= ld_volatile_i32(q + 4)) return -1;
+        __nanosleep(500);
+    }
+}
+
+// =================================================================================================================
+// k_dd_init: DD control blocks (clean.rs:383-405) and the queue
+// =================================================================================================================
+static __global__ void k_dd_init(EV ev, int count, int comp_type, long long best_lb, int dual) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slots = dual ? 2 * count : count;
+    if (k == 0) { ev.dq[0] = 0; ev.dq[1] = 0; ev.dq[2] = 0; ev.dq[3] = 0; ev.dq[4] = slots; *ev.active = 0; }
+    if (k >= slots) return;
+    ev.dq_jobs[k] = -1;
+    const bool twin = k >= count;
+    const int p = twin ? k - count : k;
+    DDCtl c{};
+    c.status = twin ? ST_WAITING : ST_ACTIVE; c.ncand = 0; c.n_cur = 0; c.var = -1;
+    c.width = ev.root_width[p]; c.comp_type = twin ? DDO_RELAXED : comp_type; c.root_depth = ev.root_depth[p]; c.lel = -1;
+    c.t_term = -1; c.best_pos = -1; c.best_exact_pos = -1; c.root_value = ev.root_val[p];
+    c.best_lb = best_lb; c.primary = -1; c.fork_t = -1;  // a twin compiled here owns all its logs (it restarts from the root)
+    ev.ctl[k] = c;
+}
+
+// =================================================================================================================
+// the per-DD compiler
+// =================================================================================================================
+template <int S>
+struct DDC {
+    static constexpr int W32 = 2 * S;          // 32-bit words of a state row
+    static constexpr int SROW = W32 + 1;       // padded row stride of the histogram staging buffers (conflict-free column reads)
+    const EV& ev; const DDLayout& L; DDFixed& fx; unsigned char* dsm;
+    cg::cluster_group cl;
+    unsigned CS, rank;
+    int tid, lane, warp;
+    int xphase = 0, hphase = 0;
+    // shared-memory views
+    int* D[2]; unsigned int* master; uint32_t* stage; int* cnt_s; int* off_s; int* koff_s; uint2* fb_s; uint2* kb_s;
+    unsigned long long* keys; uint32_t* ulist; uint8_t* stat;
+    // the DD
+    int k, rk; size_t cb, lb, nb; DDCtl* ctl;
+    int comp, W; long long best_lb;
+    // histogram staging of this warp
+    int st_cnt = 0; unsigned st_minus = 0; int hcnt[W32];
+
+    __device__ DDC(const EV& e, const DDLayout& l, DDFixed& f, unsigned char* d) : ev(e), L(l), fx(f), dsm(d), cl(cg::this_cluster()) {
+        CS = cl.num_blocks(); rank = cl.block_rank();
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        D[0] = reinterpret_cast<int*>(dsm + L.o_D); D[1] = D[0] + ev.HN;
+        master = reinterpret_cast<unsigned int*>(dsm + L.o_master);
+        stage = reinterpret_cast<uint32_t*>(dsm + L.o_stage) + (size_t)warp * 32 * SROW;
+        cnt_s = reinterpret_cast<int*>(dsm + L.o_cnt); off_s = reinterpret_cast<int*>(dsm + L.o_off); koff_s = reinterpret_cast<int*>(dsm + L.o_koff);
+        fb_s = reinterpret_cast<uint2*>(dsm + L.o_fb); kb_s = reinterpret_cast<uint2*>(dsm + L.o_kb);
+    }
+
+    // ---- cluster exchange of up to 8 block-uniform values --------------------------------------------------------------------
+    __device__ void publish(const unsigned long long* v, int n) { if (tid == 0) for (int i = 0; i < n; ++i) fx.xch[xphase][i] = v[i]; }
+    __device__ unsigned long long peer(int i, unsigned r) { return *cl.map_shared_rank(&fx.xch[xphase][i], r); }
+    __device__ void xnext() { xphase ^= 1; }
+    template <class Op> __device__ void allreduce(unsigned long long* v, int n, Op op) {
+        publish(v, n); cl.sync();
+        for (int i = 0; i < n; ++i) { unsigned long long acc = peer(i, 0); for (unsigned r = 1; r < CS; ++r) acc = op(acc, peer(i, r)); v[i] = acc; }
+        xnext();
+    }
+    __device__ int xscan(int v, int* total) {  // exclusive prefix over the ranks of one block-uniform count
+        unsigned long long x = (unsigned long long)(unsigned)v;
+        publish(&x, 1); cl.sync();
+        int pre = 0, tot = 0;
+        for (unsigned r = 0; r < CS; ++r) { const int y = (int)peer(0, r); if (r < rank) pre += y; tot += y; }
+        xnext(); *total = tot; return pre;
+    }
+
+    // ---- rows ---------------------------------------------------------------------------------------------------------------
+    // state row of candidate c of the layer being built (parents in cur_state[buf])
+    __device__ __forceinline__ const uint64_t* cand_row(uint32_t c_with_flag, int buf) const {
+        const uint32_t c = c_with_flag & DD_CMASK;
+        return (c_with_flag & DD_IDENT) ? ev.cur_state[buf] + (nb + (c >> 1)) * S : ev.cand_state + (cb + c) * S;
+    }
+    __device__ __forceinline__ void load_row_cg(const uint64_t* p, uint64_t (&w)[S]) const {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int j = 0; j < S / 2; ++j) { const uint4 x = ld_cg_u4(q + j); w[2 * j] = u4lo(x); w[2 * j + 1] = u4hi(x); }
+    }
+    __device__ __forceinline__ void store_row(uint64_t* p, const uint64_t (&w)[S]) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+        for (int j = 0; j < S / 2; ++j) q[j] = mk_u4(w[2 * j], w[2 * j + 1]);
+    }
+    __device__ __forceinline__ int row_rub(const uint64_t (&w)[S], int pc) const {  // fast_upper_bound, misp/main.rs:191-193
+        if (ev.unit_weights) return pc;
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) { uint64_t x = w[j]; const int32_t* wp = ev.weight + j * 64; while (x) { const int b = __ffsll((long long)x) - 1; r += wp[b]; x &= x - 1; } }
+        return r;
+    }
+
+    // ---- histogram staging: rows that enter (+) or leave (-) the set of distinct states are buffered per warp and bit-transposed 32 at a
+    // time into per-lane counters (lane b of column j counts vertex 32 j + b); flushed into D[e] once per phase
+    __device__ void stage_flush() {
+        if (st_cnt == 0) return;
+        __syncwarp();
+        const bool mine = lane < st_cnt;
+        const bool minus = (st_minus >> lane) & 1u;
+        const unsigned any_plus = __ballot_sync(FULL_MASK, mine && !minus), any_minus = __ballot_sync(FULL_MASK, mine && minus);
+#pragma unroll
+        for (int j = 0; j < W32; ++j) {
+            const uint32_t x = mine ? stage[lane * SROW + j] : 0u;
+            if (any_plus) hcnt[j] += __popc(warp_transpose32(minus ? 0u : x));
+            if (any_minus) hcnt[j] -= __popc(warp_transpose32(minus ? x : 0u));
+        }
+        __syncwarp();
+        st_cnt = 0; st_minus = 0;
+    }
+    // warp-collective: every lane with `has` appends its row (minus: it leaves the layer)
+    __device__ void stage_rows(bool has, const uint64_t (&w)[S], bool minus) {
+        const unsigned m = __ballot_sync(FULL_MASK, has);
+        if (!m) return;
+        const int add = __popc(m);
+        if (st_cnt + add > 32) stage_flush();
+        if (has) {
+            const int r = st_cnt + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int j = 0; j < S; ++j) { stage[r * SROW + 2 * j] = (uint32_t)w[j]; stage[r * SROW + 2 * j + 1] = (uint32_t)(w[j] >> 32); }
+        }
+        if (minus) st_minus |= (add == 32 ? 0xFFFFFFFFu : ((1u << add) - 1u)) << st_cnt;
+        st_cnt += add;
+    }
+    __device__ void stage_commit(int e) {  // end of a phase: counters of this lane -> D[e]
+        stage_flush();
+#pragma unroll
+        for (int j = 0; j < W32; ++j) if (hcnt[j]) { atomicAdd(&D[e][32 * j + lane], hcnt[j]); hcnt[j] = 0; }
+    }
+
+    // ---- open-addressing insert (next_l.entry(), clean.rs:738-775 + append_edge_to! :199-220) ---------------------------------------
+    // returns true when candidate c claimed a slot (a new distinct state); rep = claimer of the state
+    template <class RowFn>
+    __device__ __forceinline__ bool insert(uint64_t hacc, uint32_t c, uint32_t ident, int value, uint32_t fl, int buf, RowFn my_row, uint32_t& rep, uint32_t& slot_out) {
+        const uint64_t h = dd_hfin(hacc);
+        const uint32_t tag = (uint32_t)(h >> 32);
+        const unsigned long long entry = ((unsigned long long)tag << 32) | c | ident;
+        uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+        unsigned long long* tab = ev.table + (size_t)k * ev.T;
+        uint64_t w[S]; bool loaded = false;
+        for (;;) {
+            const unsigned long long old = atomicCAS(tab + slot, EMPTY64, entry);
+            if (old == EMPTY64) { rep = c; slot_out = slot; return true; }
+            if ((uint32_t)(old >> 32) == tag) {
+                if (!loaded) { my_row(w); loaded = true; }
+                const uint32_t oe = (uint32_t)old;
+                const uint4* orow = reinterpret_cast<const uint4*>(cand_row(oe, buf));
+                bool eq = true;
+#pragma unroll
+                for (int q = 0; q < S / 2; ++q) { const uint4 o4 = ld_cg_u4(orow + q); eq = eq && u4lo(o4) == w[2 * q] && u4hi(o4) == w[2 * q + 1]; }
+                if (eq) {
+                    const uint32_t oc = oe & DD_CMASK;
+                    atomicMax(ev.cand_agg + cb + oc, pack_key(value, c));   // value_top = max, `>=`: the last (largest) candidate wins ties
+                    atomicMin(ev.cand_first + cb + oc, c);                    // canonical identity = first candidate (rule C1)
+                    if (fl & NF_INEXACT) ev.cand_inex[cb + oc] = 1;           // exact &= parent.exact
+                    rep = oc; slot_out = NONE32;
+                    return false;
+                }
+            }
+            slot = (slot + 1) & (uint32_t)(ev.T - 1);
+        }
+    }
+
+    // ---- E: expansion of layer t (clean.rs:360-370, :728-776; misp/main.rs:77-102,191-193) --------------------------------------------
+    __device__ void expand(int t, int n, int var) {
+        const int buf = t & 1, e = t & 1;
+        const int slice_lo = min((int)rank * L.slice, n), slice_hi = min(slice_lo + L.slice, n);
+        const int nch = (slice_hi - slice_lo + 31) >> 5;
+        const int vw = var >> 6;
+        const uint64_t bit = 1ull << (var & 63);
+        const int wv = ev.weight[var];
+        const uint64_t hdelta = (uint64_t)(1u << (var & 31)) * (uint64_t)dd_mul32(var >> 5);
+        uint64_t ncr[S];  // complement-adjacency row of the branching vertex (misp/main.rs:82), once per thread and layer
+        {
+            const uint4* q = reinterpret_cast<const uint4*>(ev.nc + (size_t)var * S);
+#pragma unroll
+            for (int j = 0; j < S / 2; ++j) { const uint4 x = __ldg(q + j); ncr[2 * j] = u4lo(x); ncr[2 * j + 1] = u4hi(x); }
+        }
+        int my_exp = 0, my_tr = 0, no_claims = 0;
+        for (int ch = warp; ch < nch; ch += DD_NW) {
+            const int i = slice_lo + 32 * ch + lane;
+            const bool active = i < slice_hi;
+            uint64_t w[S];
+            bool have_row = false;
+            uint32_t rep_y = NONE32, rep_n = NONE32, slot_y = NONE32, slot_n = NONE32;
+            bool minus_parent = false, plus_yes = false;
+            uint64_t wy[S];
+            if (active) {
+                const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i);
+                const uint64_t hacc = (uint64_t)m.x | ((uint64_t)m.y << 32);
+                const int val = (int)m.z, pc = (int)(m.w & 0xFFFFu);
+                const uint32_t fl = m.w >> 16;
+                const int rub = ev.unit_weights ? pc : __ldcg(ev.vb[buf] + nb + i);
+                const bool expandable = ((long long)rub + (long long)val) > best_lb;  // clean.rs:364-365
+                const uint64_t* prow = ev.cur_state[buf] + (nb + i) * S;
+                if (!expandable) {
+                    load_row_cg(prow, w); have_row = true; minus_parent = true;  // the node leaves without a child
+                } else {
+                    const bool has_v = (__ldcg(prow + vw) & bit) != 0;  // misp/main.rs:96
+                    ++my_exp; my_tr += has_v ? 2 : 1;
+                    const uint32_t c_yes = 2u * i, c_no = 2u * i + 1u;  // for_each_in_domain order: YES then NO (main.rs:95-102)
+                    if (!has_v) {
+                        // identity candidate: the child IS the parent's state (value, exactness, hash, popcount carried over)
+                        ev.cand_agg[cb + c_no] = pack_key(val, c_no);
+                        ev.cand_first[cb + c_no] = c_no;
+                        ev.cand_inex[cb + c_no] = (uint8_t)(fl & NF_INEXACT);
+                        __threadfence();
+                        const bool claimed = insert(hacc, c_no, DD_IDENT, val, fl, buf, [&](uint64_t (&r)[S]) { load_row_cg(prow, r); }, rep_n, slot_n);
+                        rep_n |= DD_IDENT;
+                        if (!claimed) { load_row_cg(prow, w); have_row = true; minus_parent = true; }  // its state is already counted through the claimer
+                    } else {
+                        load_row_cg(prow, w); have_row = true;
+#pragma unroll
+                        for (int j = 0; j < S; ++j) if (j == vw) w[j] &= ~bit;  // res.remove(var), main.rs:79: w is now the NO child
+                        int pcy = 0;
+#pragma unroll
+                        for (int j = 0; j < S; ++j) { wy[j] = w[j] & ncr[j]; pcy += __popcll(wy[j]); }  // main.rs:82
+                        const uint64_t hy = dd_hacc<S>(wy), hn = hacc - hdelta;
+                        store_row(ev.cand_state + (cb + c_yes) * S, wy);
+                        store_row(ev.cand_state + (cb + c_no) * S, w);
+                        const int valy = val + wv;  // main.rs:87-93
+                        ev.cand_agg[cb + c_yes] = pack_key(valy, c_yes); ev.cand_agg[cb + c_no] = pack_key(val, c_no);
+                        *reinterpret_cast<uint2*>(ev.cand_first + cb + c_yes) = make_uint2(c_yes, c_no);
+                        *reinterpret_cast<uchar2*>(ev.cand_inex + cb + c_yes) = make_uchar2((uint8_t)(fl & NF_INEXACT), (uint8_t)(fl & NF_INEXACT));
+                        *reinterpret_cast<uint2*>(ev.cand_rank + cb + c_yes) = make_uint2((uint32_t)pcy, (uint32_t)(pc - 1));
+                        ev.cand_hacc[cb + c_yes] = hy; ev.cand_hacc[cb + c_no] = hn;
+                        if (!ev.unit_weights) { ev.cand_rub[cb + c_yes] = row_rub(wy, pcy); ev.cand_rub[cb + c_no] = rub - wv; }
+                        __threadfence();
+                        plus_yes = insert(hy, c_yes, 0u, valy, fl, buf, [&](uint64_t (&r)[S]) {
+#pragma unroll
+                            for (int j = 0; j < S; ++j) r[j] = wy[j]; }, rep_y, slot_y);
+                        const bool claimed_n = insert(hn, c_no, 0u, val, fl, buf, [&](uint64_t (&r)[S]) {
+#pragma unroll
+                            for (int j = 0; j < S; ++j) r[j] = w[j]; }, rep_n, slot_n);
+                        if (claimed_n) ++no_claims;  // parent row out, NO row in: only the branching vertex loses an occurrence
+                        else { minus_parent = true; }
+#pragma unroll
+                        for (int j = 0; j < S; ++j) if (j == vw) w[j] |= bit;  // back to the parent's row for the histogram
+                    }
+                }
+                *reinterpret_cast<uint2*>(ev.cand_rep + cb + 2u * i) = make_uint2(rep_y, rep_n);
+                *reinterpret_cast<uint2*>(ev.cand_slot + cb + 2u * i) = make_uint2(slot_y, slot_n);
+            }
+            (void)have_row;
+            stage_rows(minus_parent, w, true);
+            stage_rows(plus_yes, wy, false);
+        }
+        stage_commit(e);
+        // counters
+        my_exp = warp_reduce(my_exp, [](int a, int b) { return a + b; });
+        my_tr = warp_reduce(my_tr, [](int a, int b) { return a + b; });
+        no_claims = warp_reduce(no_claims, [](int a, int b) { return a + b; });
+        if (lane == 0) {
+            if (no_claims) atomicAdd(&D[e][var], -no_claims);
+            if (my_exp) { atomicAdd(&fx.cnt[0], (unsigned long long)my_exp); atomicAdd(&fx.cnt[1], (unsigned long long)my_tr); }
+        }
+    }
+
+    // compare two distinct candidates (with their DD_IDENT flags) by the cut order (clean.rs:803-808 + misp/main.rs:205-208)
+    __device__ bool better(uint32_t a, uint32_t b, uint32_t rep_a, uint32_t rep_b, int pca, int pcb, int buf) const {
+        const int va = key_value(ev.cand_agg[cb + rep_a]), vb2 = key_value(ev.cand_agg[cb + rep_b]);
+        if (va != vb2) return va > vb2;
+        if (pca != pcb) return pca > pcb;
+        const uint64_t* ra = cand_row(a, buf); const uint64_t* rb = cand_row(b, buf);
+        for (int j = 0; j < S; ++j) { const uint64_t xa = lex_word(__ldcg(ra + j)), xb = lex_word(__ldcg(rb + j)); if (xa != xb) return xa > xb; }
+        return false;
+    }
+    __device__ __forceinline__ int cand_pc(uint32_t cf, int buf) const {
+        const uint32_t c = cf & DD_CMASK;
+        return (cf & DD_IDENT) ? (int)(ld_cg_u4(ev.nmeta[buf] + nb + (c >> 1)).w & 0xFFFFu) : (int)__ldcg(ev.cand_rank + cb + c);
+    }
+
+    __device__ void run(int slot, int count, int dual);
+};
+
+template <int S>
+__device__ void DDC<S>::run(int slot, int count, int dual) {
+    k = slot; rk = k >= count ? k - count : k;
+    cb = (size_t)k * ev.C; lb = (size_t)k * ev.Lmax; nb = (size_t)k * ev.Wcap;
+    ctl = ev.ctl + k;
+    comp = ctl->comp_type; W = ctl->width; best_lb = ctl->best_lb;
+    const bool relaxed = comp == DDO_RELAXED;
+    if (L.smem_keys) {
+        keys = reinterpret_cast<unsigned long long*>(dsm + L.o_keys); ulist = reinterpret_cast<uint32_t*>(dsm + L.o_ulist); stat = dsm + L.o_stat;
+    } else {
+        const size_t sb = (size_t)k * ev.C2 + (size_t)rank * L.capc;
+        keys = ev.dd_keys + sb; ulist = ev.dd_ulist + sb; stat = ev.dd_stat + sb;
+    }
+#pragma unroll
+    for (int j = 0; j < W32; ++j) hcnt[j] = 0;
+    st_cnt = 0; st_minus = 0;
+    const int HS = ev.HN / (int)CS;          // vertices whose occurrence counts this CTA owns
+    const int u_lo = (int)rank * HS, u_hi = u_lo + HS;
+
+    // ---- root (clean.rs:383-405): node 0 of layer 0 ----------------------------------------------------------------------------
+    for (int i = tid; i < 2 * ev.HN; i += DD_NT) D[0][i] = 0;
+    if (tid == 0) { fx.cnt[0] = 0; fx.cnt[1] = 0; }
+    unsigned long long best = ~0ull;
+    for (int u = u_lo + tid; u < u_hi; u += DD_NT) {
+        const unsigned c = (unsigned)((ev.root_state[(size_t)rk * S + (u >> 6)] >> (u & 63)) & 1ull);
+        master[u] = c;
+        if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)u);
+    }
+    if (rank == 0 && tid < 32) {
+        uint64_t w[S]; int pc = 0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) { w[j] = ev.root_state[(size_t)rk * S + j]; pc += __popcll(w[j]); }
+        if (tid == 0) {
+            store_row(ev.cur_state[0] + nb * S, w);
+            const uint64_t ha = dd_hacc<S>(w);
+            ev.nmeta[0][nb] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)ctl->root_value, (uint32_t)pc);
+            if (!ev.unit_weights) ev.vb[0][nb] = row_rub(w, pc);
+            ev.plog[lb * ev.Wcap] = PLOG_CAND_MASK;
+            ev.nlog[lb] = 1; ev.rslog[lb * 2] = -1; ev.rslog[lb * 2 + 1] = -1;
+        }
+    }
+    best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, fx.red64);
+    allreduce(&best, 1, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; });
+    int var = best == ~0ull ? -1 : (int)(uint32_t)best;
+    int n = 1, t = 0, lel = -1;
+    bool twin_pushed = false;
+    if (rank == 0 && tid == 0) ev.vlog[lb] = var;
+    if (var < 0) {  // the root is a terminal node (clean.rs:350,608-632)
+        if (rank == 0 && tid == 0) {
+            ctl->has_best = 1; ctl->best_value = ctl->root_value; ctl->best_pos = 0;
+            ctl->has_best_exact = 1; ctl->best_exact_value = ctl->root_value; ctl->best_exact_pos = 0;
+            ctl->status = ST_DONE; ctl->t_term = 0; ctl->n_cur = 1; ctl->var = -1; ctl->ncand = 1;
+        }
+    }
+    __threadfence();
+    cl.sync();
+
+    while (var >= 0) {
+        const int buf = t & 1, nbuf = buf ^ 1, e = t & 1;
+        // D[e ^ 1] was last read by the peers two barriers ago: clear it for the next epoch
+        for (int i = tid; i < ev.HN; i += DD_NT) D[e ^ 1][i] = 0;
+        expand(t, n, var);
+        __threadfence();
+        cl.sync();  // ---- S1: every candidate of layer t+1 is inserted ------------------------------------------------------------
+
+        // ---- next_variable (misp/main.rs:109-143): occurrence counts of the distinct states of layer t+1, argmin, lowest index on ties
+        best = ~0ull;
+        for (int u = u_lo + tid; u < u_hi; u += DD_NT) {
+            int d = 0;
+            for (unsigned r = 0; r < CS; ++r) d += *cl.map_shared_rank(&D[e][u], r);
+            const unsigned m = master[u] + (unsigned)d;
+            master[u] = m;
+            if (m) best = min(best, ((unsigned long long)m << 32) | (unsigned)u);
+        }
+        // ---- first candidates (rule C1): candidate c represents its state iff it is the smallest candidate that produced it -----------
+        const int ncand = 2 * n;
+        const int slice_lo = min((int)rank * L.slice, n), slice_hi = min(slice_lo + L.slice, n);
+        const int nch = (slice_hi - slice_lo + 31) >> 5;
+        for (int ch = warp; ch < nch; ch += DD_NW) {
+            const int i = slice_lo + 32 * ch + lane;
+            bool fy = false, fn = false;
+            if (i < slice_hi) {
+                const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+                if (rp.x != NONE32) fy = __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)) == 2u * i;
+                if (rp.y != NONE32) fn = __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)) == 2u * i + 1u;
+            }
+            const unsigned by = __ballot_sync(FULL_MASK, fy), bn = __ballot_sync(FULL_MASK, fn);
+            if (lane == 0) { fb_s[ch] = make_uint2(by, bn); cnt_s[ch] = __popc(by) + __popc(bn); }
+        }
+        __syncthreads();
+        int Ublk;
+        {
+            const int per = (nch + DD_NT - 1) / DD_NT;  // (1 unless the slice holds more than 16 384 nodes)
+            int c = 0;
+            for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) c += cnt_s[ch]; }
+            int o = block_excl_scan(c, &Ublk, fx.scan);
+            for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) { off_s[ch] = o; o += cnt_s[ch]; } }
+        }
+        best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, fx.red64);
+        unsigned long long x2[2] = {(unsigned long long)(unsigned)Ublk, best};
+        publish(x2, 2);
+        cl.sync();  // ---- S2 ---------------------------------------------------------------------------------------------------------
+        int U = 0, cta_off = 0;
+        best = ~0ull;
+        for (unsigned r = 0; r < CS; ++r) { const int y = (int)peer(0, r); if (r < rank) cta_off += y; U += y; best = min(best, peer(1, r)); }
+        xnext();
+        const int tn = t + 1;  // the layer being decided
+        if (U == 0) {  // every node was pruned: empty layer (clean.rs:667-669) -> no best node
+            if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->t_term = tn; ctl->has_best = 0; ctl->has_best_exact = 0; ev.nlog[lb + tn] = 0; }
+            break;
+        }
+        const bool terminal = best == ~0ull;  // next_variable == None: layer t+1 is the terminal layer
+        const int var_next = terminal ? -1 : (int)(uint32_t)best;
+        bool cut = false; int need = 0;
+        if (!terminal) {
+            if (comp == DDO_RESTRICTED && U > W) { cut = true; need = W; }                   // clean.rs:782-787
+            else if (relaxed && U > W && tn >= 2) { cut = true; need = W - 1; }             // clean.rs:788-793 (layers.len() > 1)
+        }
+        if (!cut && U > ev.Wcap) {
+            if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->overflow = 1; ctl->t_term = tn; }
+            break;
+        }
+        if (cut && comp == DDO_RESTRICTED && dual && !twin_pushed) {  // the restricted DD is inexact: its relaxed twin is needed (parallel.rs:425-430)
+            twin_pushed = true;
+            if (rank == 0 && tid == 0) { const int idx = atomicAdd(ev.dq + 2, 1); ev.dq_jobs[idx] = count + k; __threadfence(); }
+        }
+        // ---- ordered list of the distinct candidates of this CTA; keys of the width cut ------------------------------------------------
+        if (cut) {
+            for (int ch = warp; ch < nch; ch += DD_NW) {
+                const uint2 fb = fb_s[ch];
+                const int i = slice_lo + 32 * ch + lane;
+                const unsigned lt = (1u << lane) - 1u;
+                const int base = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
+                const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
+                if (fy | fn) {
+                    const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+                    if (fy) {
+                        const uint32_t cf = (2u * i) | (rp.x & DD_IDENT);
+                        ulist[base] = cf; stat[base] = 0;
+                        keys[base] = (__ldcg(ev.cand_agg + cb + (rp.x & DD_CMASK)) & 0xFFFFFFFF00000000ull) | (unsigned)cand_pc(cf, buf);
+                    }
+                    if (fn) {
+                        const int li = base + (fy ? 1 : 0);
+                        const uint32_t cf = (2u * i + 1u) | (rp.y & DD_IDENT);
+                        ulist[li] = cf; stat[li] = 0;
+                        keys[li] = (__ldcg(ev.cand_agg + cb + (rp.y & DD_CMASK)) & 0xFFFFFFFF00000000ull) | (unsigned)cand_pc(cf, buf);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- MSD radix select of the `need` best by (value_top, popcount, BitSet::cmp) -- clean.rs:803-808 / :819-824 ---------------
+            bool done = false;
+            if (need == 0) { for (int li = tid; li < Ublk; li += DD_NT) stat[li] = 2; done = true; }
+            for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
+                if (chunk > 0) {  // the next MK members of every still undecided state (member_key)
+                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) {
+                        uint64_t w[S];
+                        load_row_cg(cand_row(ulist[li], buf), w);
+                        keys[li] = member_key<S>(w, MemberKey<S>::MK * (chunk - 1));
+                    }
+                    __syncthreads();
+                }
+                unsigned long long kk[2] = {0ull, 0ull};
+                for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) { const unsigned long long x = keys[li]; kk[0] |= x; kk[1] |= ~x; }
+                kk[0] = block_reduce(kk[0], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
+                kk[1] = block_reduce(kk[1], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
+                allreduce(kk, 2, [](unsigned long long a, unsigned long long b) { return a | b; });
+                const unsigned long long diff = kk[0] ^ ~kk[1];
+                for (int byte = 7; byte >= 0 && !done; --byte) {
+                    if (((diff >> (8 * byte)) & 0xff) == 0) continue;
+                    unsigned int* h = fx.hist[hphase];
+                    for (int i = tid; i < 256; i += DD_NT) h[i] = 0;
+                    __syncthreads();
+                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) atomicAdd(&h[(keys[li] >> (8 * byte)) & 0xff], 1u);
+                    cl.sync();
+                    for (int i = tid; i < 256; i += DD_NT) {
+                        unsigned int a = 0;
+                        for (unsigned r = 0; r < CS; ++r) a += *cl.map_shared_rank(&h[i], r);
+                        fx.ghist[i] = a;
+                    }
+                    hphase ^= 1;
+                    __syncthreads();
+                    if (warp == 0) {
+                        int c8[8]; int s8 = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { c8[q] = (int)fx.ghist[255 - (lane * 8 + q)]; s8 += c8[q]; }
+                        int inc = s8;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
+                        const int before = inc - s8;
+                        if (before < need && need <= inc) {
+                            int acc = before;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (acc < need && need <= acc + c8[q]) { fx.misc[0] = 255 - (lane * 8 + q); fx.misc[1] = acc; fx.misc[2] = c8[q]; }
+                                acc += c8[q];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int b = fx.misc[0], above = fx.misc[1], inb = fx.misc[2];
+                    need -= above;
+                    const bool all_keep = (need == inb);
+                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) {
+                        const int d = (int)((keys[li] >> (8 * byte)) & 0xff);
+                        if (d > b) stat[li] = 1; else if (d < b) stat[li] = 2; else if (all_keep) stat[li] = 1;
+                    }
+                    __syncthreads();
+                    if (all_keep) done = true;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- stable positions of the survivors (rule C3) ------------------------------------------------------------------------------
+        int nkeep, kcta = cta_off;
+        if (cut) {
+            for (int ch = warp; ch < nch; ch += DD_NW) {
+                const uint2 fb = fb_s[ch];
+                const unsigned lt = (1u << lane) - 1u;
+                const int base = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
+                const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
+                const bool ky = fy && stat[base] == 1, kn = fn && stat[base + (fy ? 1 : 0)] == 1;
+                const unsigned by = __ballot_sync(FULL_MASK, ky), bn = __ballot_sync(FULL_MASK, kn);
+                if (lane == 0) { kb_s[ch] = make_uint2(by, bn); cnt_s[ch] = __popc(by) + __popc(bn); }
+            }
+            __syncthreads();
+            int kblk;
+            {
+                const int per = (nch + DD_NT - 1) / DD_NT;
+                int c = 0;
+                for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) c += cnt_s[ch]; }
+                int o = block_excl_scan(c, &kblk, fx.scan);
+                for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) { koff_s[ch] = o; o += cnt_s[ch]; } }
+            }
+            kcta = xscan(kblk, &nkeep);
+        } else {
+            nkeep = U;
+        }
+        int n_next = nkeep, s_pos = -1, r_pos = -1;
+        int mpos = -1;          // position of the node that receives the merged-away states (relaxed cut)
+        uint32_t saved = NONE32;  // candidate kept next to a recycled node (clean.rs:868-871)
+
+        // ---- relaxation: merge the overflow (clean.rs:826-876; misp/main.rs:172-178 union) -------------------------------------------
+        if (cut && relaxed) {
+            if (tid < 16) fx.merged[0][tid] = 0;
+            __syncthreads();
+            uint64_t acc[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) acc[j] = 0;
+            unsigned long long mkey = 0;
+            for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2) {
+                const uint32_t cf = ulist[li];
+                uint64_t w[S];
+                load_row_cg(cand_row(cf, buf), w);
+#pragma unroll
+                for (int j = 0; j < S; ++j) acc[j] |= w[j];
+                const uint32_t rp = __ldcg(ev.cand_rep + cb + (cf & DD_CMASK)) & DD_CMASK;
+                mkey = max(mkey, __ldcg(ev.cand_agg + cb + rp));
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const uint64_t x = warp_reduce(acc[j], [](uint64_t a, uint64_t b) { return a | b; });
+                if (lane == 0 && x) atomicOr(&fx.merged[0][j], (unsigned long long)x);
+            }
+            mkey = block_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
+            allreduce(&mkey, 1, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });  // (its barrier also publishes merged[0])
+            if (tid < S) {
+                unsigned long long m = 0;
+                for (unsigned r = 0; r < CS; ++r) m |= *cl.map_shared_rank(&fx.merged[0][tid], r);
+                fx.merged[1][tid] = m;
+            }
+            __syncthreads();
+            // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state.  Every CTA runs the same lookup (cluster-uniform).
+            if (tid == 0) {
+                uint64_t mw[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j) mw[j] = fx.merged[1][j];
+                const uint64_t h = dd_hfin(dd_hacc<S>(mw));
+                const uint32_t tag = (uint32_t)(h >> 32);
+                uint32_t sl = (uint32_t)h & (uint32_t)(ev.T - 1);
+                const unsigned long long* tab = ev.table + (size_t)k * ev.T;
+                int recycled = -1, rec_rep = -1;
+                for (;;) {
+                    const unsigned long long en = __ldcg(tab + sl);
+                    if (en == EMPTY64) break;
+                    if ((uint32_t)(en >> 32) == tag) {
+                        const uint64_t* orow = cand_row((uint32_t)en, buf);
+                        bool eq = true;
+                        for (int j = 0; j < S; ++j) eq = eq && __ldcg(orow + j) == mw[j];
+                        if (eq) { rec_rep = (int)((uint32_t)en & DD_CMASK); recycled = (int)__ldcg(ev.cand_first + cb + rec_rep); break; }
+                    }
+                    sl = (sl + 1) & (uint32_t)(ev.T - 1);
+                }
+                fx.misc[4] = recycled; fx.misc[5] = rec_rep;
+            }
+            __syncthreads();
+            int recycled = fx.misc[4];
+            const int rec_rep = fx.misc[5];
+            // is the state's first candidate kept ?  Its owner CTA knows; everybody learns it through one exchange.
+            unsigned long long rinfo = 0;  // (kept ? position + 1 : 0) published by the owner
+            if (recycled >= 0) {
+                const int ri = recycled >> 1;
+                if (ri >= slice_lo && ri < slice_hi) {
+                    const int ch = (ri - slice_lo) >> 5, ln = (ri - slice_lo) & 31;
+                    const uint2 kb = kb_s[ch];
+                    const bool kept = (((recycled & 1) ? kb.y : kb.x) >> ln) & 1u;
+                    if (kept) {
+                        const unsigned lt = (1u << ln) - 1u;
+                        const int p = kcta + koff_s[ch] + __popc(kb.x & lt) + __popc(kb.y & lt) + (((recycled & 1) && ((kb.x >> ln) & 1u)) ? 1 : 0);
+                        rinfo = (unsigned long long)(p + 1);
+                    }
+                }
+            }
+            allreduce(&rinfo, 1, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+            if (rinfo == 0) recycled = -1;
+            if (recycled >= 0) {
+                // the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node (clean.rs:868-871)
+                uint32_t bestc = NONE32, bestrep = 0; int bestpc = 0;
+                for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2) {
+                    const uint32_t cf = ulist[li];
+                    const uint32_t rp = __ldcg(ev.cand_rep + cb + (cf & DD_CMASK)) & DD_CMASK;
+                    const int pc = cand_pc(cf, buf);
+                    if (bestc == NONE32 || better(cf, bestc, rp, bestrep, pc, bestpc, buf)) { bestc = cf; bestrep = rp; bestpc = pc; }
+                }
+                fx.tour[tid] = bestc;
+                __syncthreads();
+                for (int d = DD_NT / 2; d > 0; d >>= 1) {
+                    if (tid < d) {
+                        const uint32_t a = fx.tour[tid], b2 = fx.tour[tid + d];
+                        if (b2 != NONE32) {
+                            bool take = a == NONE32;
+                            if (!take) {
+                                const uint32_t ra = __ldcg(ev.cand_rep + cb + (a & DD_CMASK)) & DD_CMASK, rb = __ldcg(ev.cand_rep + cb + (b2 & DD_CMASK)) & DD_CMASK;
+                                take = better(b2, a, rb, ra, cand_pc(b2, buf), cand_pc(a, buf), buf);
+                            }
+                            if (take) fx.tour[tid] = b2;
+                        }
+                    }
+                    __syncthreads();
+                }
+                unsigned long long bc = fx.tour[0];
+                publish(&bc, 1); cl.sync();
+                for (unsigned r = 0; r < CS; ++r) {
+                    const uint32_t c2 = (uint32_t)peer(0, r);
+                    if (c2 == NONE32) continue;
+                    bool take = saved == NONE32;
+                    if (!take) {
+                        const uint32_t ra = __ldcg(ev.cand_rep + cb + (saved & DD_CMASK)) & DD_CMASK, rb = __ldcg(ev.cand_rep + cb + (c2 & DD_CMASK)) & DD_CMASK;
+                        take = better(c2, saved, rb, ra, cand_pc(c2, buf), cand_pc(saved, buf), buf);
+                    }
+                    if (take) saved = c2;
+                }
+                xnext();
+                s_pos = nkeep; r_pos = (int)rinfo - 1; n_next = nkeep + 1; mpos = r_pos;
+                cl.sync();  // every CTA has read cand_agg[rec_rep] through better() before rank 0 rewrites it
+                if (rank == 0 && tid == 0) {
+                    // the recycled node receives every relaxed edge: RELAXED flag, value_top = max (`>=`: the appended edges win ties)
+                    const unsigned long long rkey = __ldcg(ev.cand_agg + cb + rec_rep);
+                    if (key_value(mkey) >= key_value(rkey)) ev.cand_agg[cb + rec_rep] = mkey;
+                    ev.cand_inex[cb + rec_rep] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
+                }
+                __threadfence();
+                cl.sync();  // ... and the commit below reads the rewritten record
+                for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2 && ulist[li] == saved) stat[li] = 3;  // kept at s_pos
+            } else {
+                mpos = nkeep; n_next = nkeep + 1;
+                if (rank == 0 && tid < 32) {  // new merged node (clean.rs:832-849) written straight into the next layer
+                    uint64_t mw[S]; int pc = 0;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) { mw[j] = fx.merged[1][j]; pc += __popcll(mw[j]); }
+                    if (tid == 0) {
+                        store_row(ev.cur_state[nbuf] + (nb + mpos) * S, mw);
+                        const uint64_t ha = dd_hacc<S>(mw);
+                        ev.nmeta[nbuf][nb + mpos] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)key_value(mkey), (uint32_t)pc | ((NF_INEXACT | NF_RELAXED) << 16));
+                        if (!ev.unit_weights) ev.vb[nbuf][nb + mpos] = row_rub(mw, pc);
+                        ev.plog[(lb + tn) * ev.Wcap + mpos] = ((uint32_t)mkey & PLOG_CAND_MASK) | PLOG_INEXACT | PLOG_RELAXED;
+                    }
+                    // its occurrences enter the histogram of the next epoch (one lane per 32-bit column)
+                    for (int j = lane; j < W32; j += 32) {
+                        uint32_t x = (uint32_t)(fx.merged[1][j >> 1] >> ((j & 1) * 32));
+                        while (x) { const int b = __ffs((int)x) - 1; atomicAdd(&D[e ^ 1][32 * j + b], 1); x &= x - 1; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- commit of layer t+1 (_move_to_next_layer, clean.rs:657-687): rows, node records, parent log, positions ----------------------
+        unsigned long long b_all = 0, b_ex = 0;  // terminal layer: (biased value, pos + 1), last maximum (rule C4)
+        for (int ch = warp; ch < nch; ch += DD_NW) {
+            const uint2 fb = fb_s[ch];
+            const int i = slice_lo + 32 * ch + lane;
+            const unsigned lt = (1u << lane) - 1u;
+            const int fbase = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
+            const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
+            uint2 kb = fb; int kbase = cta_off + fbase;
+            if (cut) { kb = kb_s[ch]; kbase = kcta + koff_s[ch] + __popc(kb.x & lt) + __popc(kb.y & lt); }
+            uint64_t wdrop[S];
+            bool drop_any = false;
+            uint2 rp = make_uint2(NONE32, NONE32);
+            if (fy | fn) rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const bool isf = d == 0 ? fy : fn;
+                bool dropped = false;
+                uint64_t w[S];
+                if (isf) {
+                    const uint32_t c = 2u * i + d;
+                    const uint32_t rflag = d == 0 ? rp.x : rp.y;
+                    const uint32_t cf = c | (rflag & DD_IDENT);
+                    const uint32_t rpc = rflag & DD_CMASK;
+                    const int li = fbase + (d == 1 && fy ? 1 : 0);
+                    bool keep = (((d == 0 ? kb.x : kb.y) >> lane) & 1u) != 0;
+                    int pos = kbase + (d == 1 && ((kb.x >> lane) & 1u) ? 1 : 0);
+                    if (cut && !keep) {
+                        if (stat[li] == 3) { keep = true; pos = s_pos; }   // the saved node of the recycled corner case
+                        else { dropped = true; pos = relaxed ? mpos : -1; }
+                    }
+                    ev.pos_of[cb + c] = dropped ? (pos < 0 ? NONE32 : (uint32_t)pos) : (uint32_t)pos;
+                    if (keep) {
+                        const unsigned long long key = __ldcg(ev.cand_agg + cb + rpc);
+                        const uint32_t fl = __ldcg(ev.cand_inex + cb + rpc);
+                        const int value = key_value(key);
+                        load_row_cg(cand_row(cf, buf), w);
+                        store_row(ev.cur_state[nbuf] + (nb + pos) * S, w);
+                        uint64_t ha; int pc;
+                        if (cf & DD_IDENT) { const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i); ha = (uint64_t)m.x | ((uint64_t)m.y << 32); pc = (int)(m.w & 0xFFFFu); if (!ev.unit_weights) ev.vb[nbuf][nb + pos] = __ldcg(ev.vb[buf] + nb + i); }
+                        else { ha = ev.cand_hacc[cb + c]; pc = (int)ev.cand_rank[cb + c]; if (!ev.unit_weights) ev.vb[nbuf][nb + pos] = ev.cand_rub[cb + c]; }
+                        ev.nmeta[nbuf][nb + pos] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)value, (uint32_t)pc | (fl << 16));
+                        ev.plog[(lb + tn) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
+                        if (terminal) {
+                            const unsigned long long kk = (key & 0xFFFFFFFF00000000ull) | (unsigned)(pos + 1);
+                            b_all = max(b_all, kk);
+                            if (!(fl & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk);
+                        }
+                    } else {
+                        load_row_cg(cand_row(cf, buf), w);  // a state that leaves the layer: its occurrences leave the histogram
+                    }
+                }
+                // (a node has at most one dropped candidate per decision; both may be dropped: stage them one after the other)
+                if (d == 0) {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) wdrop[j] = w[j];
+                    drop_any = dropped;
+                } else {
+                    stage_rows(drop_any, wdrop, true);
+                    stage_rows(dropped, w, true);
+                }
+            }
+        }
+        stage_commit(e ^ 1);
+        if (terminal) {
+            unsigned long long bb[2];
+            bb[0] = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
+            bb[1] = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
+            allreduce(bb, 2, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+            if (rank == 0 && tid == 0) {
+                ctl->has_best = 1; ctl->best_value = key_value(bb[0]); ctl->best_pos = (int)(uint32_t)bb[0] - 1;
+                ctl->has_best_exact = bb[1] != 0;
+                if (bb[1]) { ctl->best_exact_value = key_value(bb[1]); ctl->best_exact_pos = (int)(uint32_t)bb[1] - 1; }
+            }
+        }
+        const bool first_cut = cut && lel < 0;
+        if (first_cut) lel = t;  // _maybe_save_lel, clean.rs:796-800: the parent layer of the first squashed layer
+        if (rank == 0 && tid == 0) {
+            ev.nlog[lb + tn] = n_next; ev.vlog[lb + tn] = var_next;
+            ev.rslog[(lb + tn) * 2] = s_pos; ev.rslog[(lb + tn) * 2 + 1] = r_pos;
+            if (first_cut) ctl->lel = t;
+        }
+        if (first_cut && relaxed) {  // layer t is the last exact layer: keep its nodes for the cutset (clean.rs:566-583)
+            for (int i = slice_lo + tid; i < slice_hi; i += DD_NT) {
+                uint64_t w[S];
+                load_row_cg(ev.cur_state[buf] + (nb + i) * S, w);
+                store_row(ev.lel_state + (nb + i) * S, w);
+                const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i);
+                ev.lel_val[nb + i] = (int)m.z;
+                ev.lel_rub[nb + i] = ev.unit_weights ? (int)(m.w & 0xFFFFu) : __ldcg(ev.vb[buf] + nb + i);
+            }
+        }
+        __threadfence();
+        cl.sync();  // ---- S5: positions of every first candidate are published -----------------------------------------------------------
+        // ---- child log (relaxed DDs: edge (parent c / 2, decision) -> node of layer t+1) and release of the hash slots -------------------
+        for (int ch = warp; ch < nch; ch += DD_NW) {
+            const int i = slice_lo + 32 * ch + lane;
+            if (i < slice_hi) {
+                const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+                const uint2 sl = *reinterpret_cast<const uint2*>(ev.cand_slot + cb + 2u * i);
+                if (sl.x != NONE32) ev.table[(size_t)k * ev.T + sl.x] = EMPTY64;
+                if (sl.y != NONE32) ev.table[(size_t)k * ev.T + sl.y] = EMPTY64;
+                if (relaxed) {
+                    uint32_t cy = NONE32, cn = NONE32;
+                    if (rp.x != NONE32) cy = __ldcg(ev.pos_of + cb + __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)));
+                    if (rp.y != NONE32) cn = __ldcg(ev.pos_of + cb + __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)));
+                    *reinterpret_cast<uint2*>(ev.clog + (lb + t) * ev.C + 2u * i) = make_uint2(cy, cn);
+                }
+            }
+        }
+        (void)ncand;
+        if (terminal) {
+            if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->t_term = tn; ctl->n_cur = n_next; ctl->var = -1; ctl->ncand = ncand; }
+            break;
+        }
+        __threadfence();
+        cl.sync();  // ---- end of the layer step ---------------------------------------------------------------------------------------------
+        t = tn; n = n_next; var = var_next;
+    }
+    // ---- the DD is complete -----------------------------------------------------------------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        if (fx.cnt[0]) { atomicAdd(&ctl->expanded, fx.cnt[0]); atomicAdd(&ctl->transitions, fx.cnt[1]); }
+    }
+    __threadfence();
+    cl.sync();
+    if (rank == 0 && tid == 0) {
+        // a restricted DD that never needed a cut is exact: its relaxed twin will never be compiled (parallel.rs:421-423)
+        const int fin = (dual && k < count && !twin_pushed) ? 2 : 1;
+        __threadfence();
+        atomicAdd(ev.dq + 3, fin);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(DD_NT, 1) k_dd(const __grid_constant__ EV ev, const __grid_constant__ DDLayout L, int count, int dual) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ DDFixed fx;
+    DDC<S> c(ev, L, fx, dsm);
+    for (;;) {
+        if (c.rank == 0 && c.tid == 0) fx.job = dd_fetch_job(ev, count);
+        c.cl.sync();
+        const int slot = *c.cl.map_shared_rank(&fx.job, 0);
+        c.cl.sync();  // everybody has read the job before rank 0 fetches the next one (or leaves)
+        if (slot < 0) break;
+        c.run(slot, count, dual);
+    }
+}
+
+}  // namespace ddo

@@ -1,6 +1,7 @@
 // engine.cu -- host side of the batch DD-compilation engine: arenas in HBM, the per-layer launch loop, result fetch.
 #include "kernels.cuh"
 #include "frontier.cuh"
+#include "dd_kernel.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -139,6 +140,11 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ev.smem_keys = finish_smem <= 200 * 1024;
     if (ev.smem_keys) { ev.gkeys = nullptr; ev.ustat = nullptr; }
     else { finish_smem = 0; ALLOC(ev.gkeys, KC); ALLOC(ev.ustat, KC); }
+    ev.C2 = C + 1024;
+    for (int b = 0; b < 2; ++b) ALLOC(ev.nmeta[b], KW);
+    ALLOC(ev.cand_hacc, KC); ALLOC(ev.cand_rub, KC);
+    ALLOC(ev.dd_keys, (size_t)K * ev.C2); ALLOC(ev.dd_ulist, (size_t)K * ev.C2); ALLOC(ev.dd_stat, (size_t)K * ev.C2);
+    ALLOC(ev.dq, 8); ALLOC(ev.dq_jobs, K);
     ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
     ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
@@ -151,6 +157,8 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_out.state, out_cap * S); ALLOC(d_out.val, out_cap); ALLOC(d_out.ub, out_cap); ALLOC(d_out.dd, out_cap); ALLOC(d_out.path, out_cap * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    if (const char* e = getenv("DDO_DD")) dd_enabled = atoi(e) != 0;
+    if (const char* e = getenv("DDO_DD_CS")) dd_cs = atoi(e);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_PDL")) pdl_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_LAYER_CHUNK")) layer_chunk = std::max(1, atoi(e));
@@ -247,6 +255,57 @@ int Engine::prof_collect() {
     return DDO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// persistent whole-DD kernel (dd_kernel.cuh): one cluster per DD, the layer loop inside the kernel
+// ---------------------------------------------------------------------------------------------------------------
+static DDLayout dd_layout(const Engine* E, int cs) {
+    DDLayout L{};
+    const int S = E->S, HN = 64 * S;
+    L.slice = (((E->Wcap + cs - 1) / cs) + 31) & ~31;
+    L.maxch = L.slice / 32;
+    L.capc = 2 * L.slice;
+    unsigned o = 0;
+    auto take = [&](size_t bytes) { const unsigned at = o; o += (unsigned)((bytes + 15) & ~(size_t)15); return at; };
+    L.o_D = take((size_t)2 * HN * 4); L.o_master = take((size_t)HN * 4);
+    L.o_stage = take((size_t)DD_NW * 32 * (2 * S + 1) * 4);
+    L.o_cnt = take((size_t)L.maxch * 4); L.o_off = take((size_t)L.maxch * 4); L.o_koff = take((size_t)L.maxch * 4);
+    L.o_fb = take((size_t)L.maxch * 8); L.o_kb = take((size_t)L.maxch * 8);
+    L.smem_keys = (size_t)L.capc * 13 <= 96 * 1024;
+    if (L.smem_keys) { L.o_keys = take((size_t)L.capc * 8); L.o_ulist = take((size_t)L.capc * 4); L.o_stat = take((size_t)L.capc); }
+    L.total = o;
+    return L;
+}
+
+template <int S>
+static int run_dd(Engine* E, int count, int slots, int comp_type, int64_t best_lb) {
+    const EV& ev = E->ev;
+    cudaStream_t st = E->stream;
+    const int dual = slots > count;
+    if (!E->dd_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        E->dd_attr_set = true;
+    }
+    // cluster size: wide clusters while every DD of the batch (twins included) can have its own, single CTAs for large batches
+    int cs = 1;
+    if (E->dd_cs > 0) cs = E->dd_cs;
+    else { for (int c = 8; c >= 1; c >>= 1) if (slots * c <= E->num_sms) { cs = c; break; } }
+    const DDLayout L = dd_layout(E, cs);
+    int nclusters = std::min(slots, std::max(1, E->num_sms / cs));
+    k_dd_init<<<(slots + 127) / 128, 128, 0, st>>>(ev, count, comp_type, (long long)best_lb, dual);
+    E->prof_mark(-1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nclusters * cs); cfg.blockDim = dim3(DD_NT); cfg.dynamicSmemBytes = L.total; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dd<S>, ev, L, count, dual));
+    E->prof_mark(0);
+    g_kernel_launches += 2; ++E->dd_launches;
+    return DDO_OK;
+}
+
 // launch with (pdl) or without programmatic stream serialization: see pdl_enter() in kernels.cuh
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -284,6 +343,13 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         CUDA_TRY(cudaFuncSetAttribute(k_finish_cl<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_cl_smem));
         E->finish_cl_attr_set = true;
     }
+    bool use_dd = E->dd_enabled && E->model != nullptr;
+    for (int i = 0; i < count && use_dd; ++i) if (E->h_root_width[i] < 1) use_dd = false;  // max_width 0 (restricted): the layer-by-layer kernels keep that corner
+    if (use_dd) {
+        if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;
+        const int rc = run_dd<S>(E, count, slots, comp_type, best_lb);
+        if (rc != DDO_OK) return rc;
+    } else {
     k_init<S><<<slots, 64, 0, st>>>(ev, count, comp_type, (long long)best_lb, slots > count);
     ++g_kernel_launches;
     E->prof_mark(-1);
@@ -310,6 +376,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
             if (*E->h_active <= 0) break;
             if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;  // Cutoff::must_stop polled between layers (clean.rs:352)
         }
+    }
     }
     // one more k_finish turns TERMINAL into DONE; harmless otherwise
     k_finalize<<<(slots + 63) / 64, 64, 0, st>>>(ev, slots);
@@ -417,13 +484,16 @@ int Engine::compile_small_launch(int count, int64_t best_lb, int ws) {
 }
 
 int Engine::fetch_ctl(int count) {
-    if (ctl_fetched && count <= last_count) return DDO_OK;
+    if (ctl_fetched && count <= last_count) {
+        if (ctl_overflow) { set_error("a layer outgrew max_width_cap (Exact compilation needs a larger cap)"); return DDO_ERR_CAPACITY; }
+        return DDO_OK;
+    }
     CUDA_TRY(cudaSetDevice(device));
     bytes_d2h += (unsigned long long)((size_t)last_count * sizeof(DDCtl)); CUDA_TRY(cudaMemcpyAsync(h_ctl, ev.ctl, (size_t)last_count * sizeof(DDCtl), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    ctl_fetched = true;
+    ctl_fetched = true; ctl_overflow = false;
     for (int i = 0; i < last_count; ++i)
-        if (h_ctl[i].overflow) { set_error("a layer outgrew max_width_cap (Exact compilation needs a larger cap)"); return DDO_ERR_CAPACITY; }
+        if (h_ctl[i].overflow) { ctl_overflow = true; set_error("a layer outgrew max_width_cap (Exact compilation needs a larger cap)"); return DDO_ERR_CAPACITY; }
     return DDO_OK;
 }
 

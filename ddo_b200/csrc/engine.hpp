@@ -92,6 +92,12 @@ struct EV {
     // in canonical order (layer descending, position ascending): node = layer << FC_POS_BITS | position, upper bound, scratch (value_bot, then
     // the local output index of a drain)
     uint32_t* fc_node; int32_t* fc_ub; int32_t* fc_aux; unsigned long long fc_cap;
+    // persistent whole-DD kernel (dd_kernel.cuh): node records {hash accumulator lo, hi, value_top, popcount | flags << 16} of the two layer
+    // buffers, per-candidate hash accumulator / rough upper bound of the materialised candidates, global fall-back of the per-CTA cut lists
+    // (stride C2 per DD), the device work queue and the twin jobs published by restricted DDs
+    uint4* nmeta[2]; unsigned long long* cand_hacc; int32_t* cand_rub;
+    unsigned long long* dd_keys; uint32_t* dd_ulist; uint8_t* dd_stat; int C2;
+    int* dq; int* dq_jobs;
 };
 constexpr int FC_POS_BITS = 21;
 
@@ -124,6 +130,8 @@ struct Engine {
     size_t finish_smem = 0; bool finish_attr_set = false;
     int compact1_min = 1;  // thread-per-candidate compaction (k_compact1) for batches of >= compact1_min DD slots (DDO_COMPACT1_MIN)
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
+    bool dd_enabled = true; int dd_cs = 0; bool dd_attr_set = false;  // persistent whole-DD kernel k_dd (DDO_DD=0 disables); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
+    unsigned long long dd_launches = 0;
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -139,7 +147,7 @@ struct Engine {
     int32_t* h_out_tt = nullptr;   // layer of every record inside its DD (LEL: the DD's last exact layer)
     size_t out_cap = 0;            // records the drain buffers hold (LEL: K * Wcap)
     int last_drain_total = 0;      // records of the last ddo_mdd_drain_cutset_batch
-    int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false;
+    int last_count = 0; int last_comp_type = -1; int staged = 0; bool ctl_fetched = false; bool ctl_overflow = false;  // verdict of the last fetch_ctl: an overflowed batch keeps failing
     size_t bytes_allocated = 0;
     unsigned long long layer_steps = 0;  // layer steps (k_finish + k_compact + k_expand) launched so far
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;  // traffic over PCIe / NVLink-C2C issued by this engine

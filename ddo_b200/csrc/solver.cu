@@ -230,6 +230,10 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
 }
 void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
+    // entries re-keyed or popped since they were queued are dropped first: a stale entry's slot may hold another state by now, and the
+    // comparator must never dereference it (the runs below stay sorted by the keys of LIVE nodes only)
+    pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [this](const Ent& e) { return e.ver != ver_[e.id]; }), pending_.end());
+    if (pending_.empty()) return;
     auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
     if (pending_.size() < (1u << 15)) std::sort(pending_.begin(), pending_.end(), less);
     else {  // a wide wave's cutsets (hundreds of thousands of nodes): sort eight slices on eight threads, then merge pairwise
@@ -260,9 +264,12 @@ void NoDupFringe::flush_pending() {
         std::vector<Ent> m;
         m.reserve(x.size() + y.size());
         size_t i = 0, j = 0;
-        while (i < x.size() || j < y.size()) {
+        auto skip_stale = [this](const std::vector<Ent>& v, size_t& q) { while (q < v.size() && v[q].ver != ver_[v[q].id]) ++q; };
+        for (;;) {  // stale entries are dropped BEFORE they are compared (their slot may have been recycled for another state)
+            skip_stale(x, i); skip_stale(y, j);
+            if (i == x.size() && j == y.size()) break;
             const bool take_x = j == y.size() || (i < x.size() && !ent_less(y[j], x[i]));
-            m.push_back(take_x ? x[i++] : y[j++]);  // stale entries stay (a version lookup per entry would be a cache miss each): pops skip them
+            m.push_back(take_x ? x[i++] : y[j++]);
         }
         runs_.pop_back();
         runs_.back().swap(m);
@@ -338,7 +345,7 @@ Solver::Solver(Engine* e, int kind, const uint64_t* rs, int64_t rv, int wk, uint
 
 int Solver::init(bool push_root) {  // parallel.rs:368-385
     fringe.clear(); recs.clear(); pre_valid = false; pre_items.clear();
-    best_lb = INT64_MIN; best_ub = INT64_MAX; has_sol = false; best_sol.clear(); aborted = false;
+    best_lb = INT64_MIN; best_ub = INT64_MAX; has_sol = false; sol_value = INT64_MIN; best_sol.clear(); aborted = false;
     explored = expanded = transitions = compilations = waves = 0; device_ms = fringe_ms = 0;
     if (push_root) {
         std::vector<uint64_t> bits(1, 0);
@@ -356,6 +363,14 @@ void Solver::full_path(int32_t rec, const uint64_t* bits, int32_t depth, std::ve
 }
 
 int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
+    const int rc = wave_body(cutoff_flag, out3);
+    // Err(CutoffOccurred) (clean.rs:352-354 -> parallel.rs:479-489 abort_search): the nodes of this wave are gone from the fringe, so the
+    // search can no longer prove optimality -- finish() must not close the gap
+    if (rc == DDO_CUTOFF) aborted = true;
+    return rc;
+}
+
+int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const int W = words, PWN = (n_vars + 63) / 64;
     // ---- get_workload (parallel.rs:500-559): pop up to wave_size open sub-problems ---------------------------------------------
     double t0 = now_ms();
@@ -408,6 +423,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
         values[i] = w_items[i].value; depths[i] = w_items[i].depth;
     }
+    auto past_deadline = [&]() { return (deadline_ms > 0 && now_ms() >= deadline_ms) || (cutoff_flag && *cutoff_flag); };  // TimeBudget polled before every device batch
     struct Res { bool exact = false, has = false; int32_t best = 0; };
     std::vector<Res> res(cnt);
     const int64_t lb0 = best_lb;  // every restricted DD of the wave is compiled against this snapshot
@@ -439,7 +455,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         best_sol.clear();
         full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], w_items[wave_index].depth, best_sol);
         best_sol.insert(best_sol.end(), dd.begin(), dd.begin() + len);
-        has_sol = true;
+        has_sol = true; sol_value = best_lb;
         return DDO_OK;
     };
 
@@ -462,7 +478,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 best_sol.clear();
                 full_path(w_items[wave_index].rec, &w_bits[(size_t)wave_index * PWN], w_items[wave_index].depth, best_sol);
                 best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
-                has_sol = true;
+                has_sol = true; sol_value = best_lb;
                 return true;
             }
         return false;
@@ -558,6 +574,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     std::vector<int> slot_wave;
     for (size_t s0 = 0; s0 < ov.size(); s0 += (size_t)chunk) {
         const int oc = (int)std::min<size_t>((size_t)chunk, ov.size() - s0);
+        if (past_deadline()) return DDO_CUTOFF;
         rc = stage_subset(&ov[s0], oc);
         if (rc != DDO_OK) return rc;
         rc = dual ? eng->compile_dual(oc, lb0, cutoff_flag, &ms) : eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
@@ -623,6 +640,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             p_direct = open.size() <= (size_t)cap;
             for (size_t s0 = 0; s0 < open.size(); s0 += (size_t)cap) {
                 const int oc = (int)std::min<size_t>((size_t)cap, open.size() - s0);
+                if (past_deadline()) return DDO_CUTOFF;
                 rc = stage_subset(&open[s0], oc);
                 if (rc != DDO_OK) return rc;
                 rc = eng->compile_staged(oc, DDO_RELAXED, lb1, cutoff_flag, &ms);
@@ -657,7 +675,7 @@ int Solver::wave(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                     best_sol.clear();
                     full_path(w_items[wi].rec, &w_bits[(size_t)wi * PWN], w_items[wi].depth, best_sol);
                     best_sol.insert(best_sol.end(), it->second.begin(), it->second.end());
-                    has_sol = true; got = true;
+                    has_sol = true; sol_value = best_lb; got = true;
                 }
             if (!got) { rc = take_solution(improver, DDO_RELAXED, lb1); if (rc != DDO_OK) return rc; }
         }
@@ -721,6 +739,7 @@ int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact
     int rc = init(true);
     if (rc != DDO_OK) return rc;
     const double t_end = time_budget_s > 0 ? now_ms() + time_budget_s * 1000.0 : 0;
+    deadline_ms = t_end;
     volatile int32_t cutoff = 0;
     pipeline = true; pre_valid = false;
     for (;;) {
@@ -731,13 +750,13 @@ int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact
         if (rc == DDO_CUTOFF) { aborted = true; break; }
         if (rc != DDO_OK) return rc;
     }
-    pipeline = false; pre_valid = false;
+    pipeline = false; pre_valid = false; deadline_ms = 0;
     if (aborted) fringe.clear();  // abort_search, parallel.rs:479-489
     else best_ub = best_lb;
     std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });  // parallel.rs:605
     if (is_exact) *is_exact = !aborted;
     if (has_value) *has_value = has_sol;
-    if (best_value) *best_value = has_sol ? best_lb : 0;
+    if (best_value) *best_value = has_sol ? sol_value : 0;
     return DDO_OK;
 }
 

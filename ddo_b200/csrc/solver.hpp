@@ -101,6 +101,8 @@ struct Solver {
     std::vector<PathRec> recs;
     int64_t best_lb = INT64_MIN, best_ub = INT64_MAX;
     bool has_sol = false; std::vector<ddo_decision> best_sol;
+    int64_t sol_value = INT64_MIN;   // objective of best_sol: best_lb may be raised from outside (another rank's incumbent) without a solution
+    double deadline_ms = 0;          // TimeBudget of the running maximize() (0 = none), polled before every device batch
     bool aborted = false;
     uint64_t explored = 0, expanded = 0, transitions = 0, compilations = 0, waves = 0;
     double device_ms = 0, fringe_ms = 0;
@@ -117,6 +119,7 @@ struct Solver {
     Solver(Engine* e, int model_kind, const uint64_t* root_state, int64_t root_value, int wk, uint64_t w, int ws);
     int init(bool push_root);
     int wave(const volatile int32_t* cutoff_flag, int64_t out3[3]);
+    int wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]);
     int maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact, int32_t* has_value, int64_t* best_value);
     void finish();
     void full_path(int32_t rec, const uint64_t* bits, int32_t depth, std::vector<ddo_decision>& out) const;

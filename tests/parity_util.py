@@ -8,6 +8,48 @@ import oracle_lib as O
 from ddo_b200 import CompilationType, GpuMdd, Max2Sat, Misp, SubProblem
 from ddo_b200 import _native as N
 
+def _sha(*arrays) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def oracle_digest(ref: dict, comp_type: int) -> dict:
+    """Digest of one oracle DD (tests/golden/make_dd_goldens.py); device_digest() builds the same from the C ABI's outputs."""
+    d = {"has_best": int(ref["has_best"]), "best_value": int(ref["best_value"]) if ref["has_best"] else None, "is_exact": int(ref["is_exact"]),
+         "has_best_exact": int(ref["has_best_exact"]), "best_exact_value": int(ref["best_exact_value"]) if ref["has_best_exact"] else None,
+         "expanded": int(ref["expanded"]), "transitions": int(ref["transitions"]), "lel": int(ref["lel"]), "n_layers": int(len(ref["layer_vars"])),
+         "layers_sha": _sha(np.asarray(ref["layer_vars"], dtype=np.int32), np.asarray(ref["layer_widths"], dtype=np.int32))}
+    if comp_type == O.RELAXED:
+        d["cutset_size"] = int(ref["cutset_size"])
+        d["cutset_sha"] = _sha(np.asarray(ref["cutset_states"], dtype=np.uint64), np.asarray(ref["cutset_values"], dtype=np.int64),
+                               np.asarray(ref["cutset_ubs"], dtype=np.int64), np.asarray(ref["cutset_depths"], dtype=np.int32))
+    sol = ref["best_exact_solution"]
+    d["best_exact_solution_sha"] = None if sol is None else _sha(np.asarray(sol, dtype=np.int32))
+    return d
+
+
+def device_digest(mdd: GpuMdd, index: int, comp_type: int, root_depth: int = 0) -> dict:
+    c = mdd._last[index]
+    v, w = mdd.layer_trace(index)
+    d = {"has_best": int(c.best_value is not None), "best_value": c.best_value, "is_exact": int(c.is_exact),
+         "has_best_exact": int(c.best_exact_value is not None), "best_exact_value": c.best_exact_value,
+         "expanded": int(c.expanded), "transitions": int(c.transitions), "lel": (c.lel_depth - root_depth) if c.lel_depth >= 0 else -1,
+         "n_layers": int(len(v)), "layers_sha": _sha(np.asarray(v, dtype=np.int32), np.asarray(w, dtype=np.int32))}
+    if comp_type == O.RELAXED:
+        cs = mdd.drain_cutset(index, with_paths=False)
+        d["cutset_size"] = len(cs)
+        words = len(cs[0].state) if cs else 0
+        d["cutset_sha"] = _sha(np.asarray([sp.state for sp in cs], dtype=np.uint64).reshape(len(cs), words) if cs else np.zeros((0, 0), dtype=np.uint64),
+                               np.asarray([sp.value for sp in cs], dtype=np.int64), np.asarray([sp.ub for sp in cs], dtype=np.int64),
+                               np.asarray([sp.depth for sp in cs], dtype=np.int32))
+    sol = mdd.best_exact_solution(index) if c.best_exact_value is not None else None
+    d["best_exact_solution_sha"] = None if sol is None else _sha(np.asarray([(x.variable, x.value) for x in sol], dtype=np.int32))
+    return d
+
+
 CT = {O.EXACT: CompilationType.Exact, O.RELAXED: CompilationType.Relaxed, O.RESTRICTED: CompilationType.Restricted}
 
 

@@ -220,3 +220,35 @@ def test_kernel_variants_give_the_same_search(monkeypatch, env):
     assert base == alt
     assert base[:6] == (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"])
     assert base[7] == ref["solution"]
+
+
+def test_full_size_config5_root_dds_bit_exact_at_width_20000(golden_dir):
+    """BASELINE config 5 beyond W ~ 11 000, where the cut keys of the one-CTA kernels leave shared memory: MISP G(1000, 0.5) seed 1, W = 20 000,
+    restricted + relaxed root DDs against the oracle's digests (two minutes of CPU, committed in tests/golden/dd_digests.json by
+    tests/golden/make_dd_goldens.py): every scalar of the DecisionDiagram trait, the per-layer trace, the cutset (order, states, values,
+    upper bounds, depths) and the best exact solution."""
+    from parity_util import device_digest
+    g = json.loads((golden_dir / "dd_digests.json").read_text())["config5_misp_n1000_p0.5_seed1_w20000"]
+    inst = gnp(1000, 0.5, 1)
+    pb = Misp(inst)
+    mdd = GpuMdd(pb, g["width"], 1)
+    root = SubProblem(pb.initial_state(), 0)
+    mdd.compile(CompilationType.Restricted, g["width"], root)
+    assert device_digest(mdd, 0, O.RESTRICTED) == g["restricted"]
+    mdd.compile(CompilationType.Relaxed, g["width"], root, best_lb=g["relaxed_best_lb"])
+    assert device_digest(mdd, 0, O.RELAXED) == g["relaxed"]
+    mdd.close()
+
+
+def test_bench_configuration_trajectory_matches_oracle_golden(golden_dir):
+    """The bench's own configuration (wave 2048, batch cap 512) on BASELINE config 2: the trajectory of tests/golden/config2_trajectory_k2048.json
+    (the oracle's wave solver, tests/golden/make_trajectory.py 2048)."""
+    g = json.loads((golden_dir / "config2_trajectory_k2048.json").read_text())
+    s = ParNoCachingSolverLel(Misp(gnp(500, 0.5, 1)), FixedWidth(g["width"]), wave_size=2048, batch_cap=512)
+    comp = s.maximize()
+    st = s.stats()
+    assert comp.is_exact and comp.best_value == g["best_value"] == 13
+    assert (s.best_lower_bound(), s.best_upper_bound()) == (g["best_lb"], g["best_ub"])
+    got = (s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]))
+    assert got == (g["explored"], g["expanded"], g["transitions"], g["compilations"], g["waves"])
+    assert sorted(d.variable for d in s.best_solution() if d.value == 1) == g["solution"]

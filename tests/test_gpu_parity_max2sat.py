@@ -123,3 +123,21 @@ def test_full_size_config3_root_dds_and_properties():
         assert np.all(b[assigned] == 0)
     mdd.close()
     check_instance(inst, [8], model="m2s", check_paths=False)
+
+
+def test_full_size_config3_root_dds_bit_exact(golden_dir):
+    """BASELINE config 3 at full size, bit-exact: MAX2SAT 500 variables / 3000 clauses seed 1, W = 5000 -- the restricted root DD and the
+    relaxed root DD (compiled against the restricted value) against the oracle's digests (tests/golden/dd_digests.json, made by
+    tests/golden/make_dd_goldens.py in ~3 minutes of CPU): every scalar, the per-layer trace, the cutset and the best exact solution."""
+    import json
+    from parity_util import device_digest
+    g = json.loads((golden_dir / "dd_digests.json").read_text())["config3_max2sat_n500_c3000_seed1_w5000"]
+    inst = random_max2sat(500, 3000, 1)
+    pb = Max2Sat(inst)
+    mdd = GpuMdd(pb, g["width"], 1)
+    root = SubProblem(pb.initial_state(), pb.initial_value())
+    mdd.compile(CompilationType.Restricted, g["width"], root)
+    assert device_digest(mdd, 0, O.RESTRICTED) == g["restricted"]
+    mdd.compile(CompilationType.Relaxed, g["width"], root, best_lb=g["relaxed_best_lb"])
+    assert device_digest(mdd, 0, O.RELAXED) == g["relaxed"]
+    mdd.close()
