@@ -3,19 +3,26 @@
 //
 // Round 1 ran a layer step of the whole batch as three dependent launches (k_finish / k_compact / k_expand); a solve of BASELINE config 2
 // is ~2 800 such steps and the chain, not bandwidth, was its critical path.  Here a thread-block CLUSTER owns one DD from its root to its
-// terminal layer: the layer loop runs inside the kernel, the phases of a layer are separated by cluster barriers (~0.2 us) instead of
-// launches, and the DDs of a batch advance independently -- clusters pull DD slots from a device-side queue, a restricted DD that takes its
-// first width cut publishes its relaxed twin to the same queue (parallel.rs:419-430: the relaxed DD is compiled only when the restricted
-// one is inexact).  The cluster size is chosen per launch: wide clusters when the batch holds a few wide DDs (latency), single CTAs when it
-// holds hundreds (throughput).
+// terminal layer: the layer loop runs inside the kernel, the phases of a layer are separated by cluster barriers instead of launches, and
+// the DDs of a batch advance independently -- clusters pull DD slots from a device-side queue, a restricted DD that takes its first width
+// cut publishes its relaxed twin to the same queue (parallel.rs:419-430: the relaxed DD is compiled only when the restricted one is
+// inexact).  The cluster size is chosen per launch: wide clusters when the batch holds a few wide DDs (latency), single CTAs when it holds
+// hundreds (throughput).
 //
-// The layer step itself is restated around one property of MISP under `next_variable` = vertex occurring in the fewest states
+// The layer step is restated around one property of MISP under `next_variable` = vertex occurring in the fewest states
 // (misp/main.rs:109-143): most nodes of a layer do NOT contain the branching vertex (mean out-degree 1.18 on config 2), so their only child
 // has their own state, value and exactness (main.rs:77-102).  Such an IDENTITY candidate is never materialised: the dedup table entry, the
 // width-cut keys and the commit of the next layer refer to the parent's row; its hash accumulator, popcount and rough upper bound are
 // carried over; only nodes that contain the vertex (and pruned nodes) touch their 64..128-byte rows before the commit.  The per-vertex
 // occurrence counts behind `next_variable` are maintained INCREMENTALLY (rows that leave the layer are subtracted, rows that enter are
 // added) instead of being recounted over every distinct state of every layer.
+//
+// Synchronisation budget of a layer (cluster barriers): 3 without a width cut (candidates inserted / counts exchanged / layer committed),
+// 6-7 with one.  Everything exchanged between the CTAs of a cluster is PUSHED into the peers' shared memory before a barrier (remote
+// stores / remote atomics, fire and forget) and read locally after it -- a pulled value costs a ~215-cycle DSMEM round trip per peer.  The
+// width cut is one histogram pass over a dense (value_top, popcount) key; the candidates of the boundary bucket are gathered into rank 0,
+// which resolves BitSet::cmp among them with block barriers only (a generic MSD radix select over the whole cluster remains as the
+// fall-back for key ranges or buckets that do not fit).
 //
 // Semantics are those of kernels.cuh (same canonical rules C1-C4, same logs plog / clog / nlog / vlog / rslog / lel_* and DDCtl fields), so
 // k_finalize, k_bottomup, the cutset drains and the FRONTIER kernels consume a DD compiled here unchanged.
@@ -27,11 +34,14 @@ namespace ddo {
 constexpr int DD_NT = 512, DD_NW = DD_NT / 32;
 constexpr uint32_t DD_IDENT = 1u << 30;          // candidate flag: the state row of this candidate is its parent's row in the current layer
 constexpr uint32_t DD_CMASK = DD_IDENT - 1u;
+constexpr int DD_NB = 2048;                      // bins of the dense (value_top, popcount) histogram of the width cut
+constexpr int DD_GCAP = 2048;                    // boundary-bucket candidates rank 0 can resolve alone
+constexpr int DD_MAXCS = 16;
 
 // byte offsets into the dynamic shared memory of a CTA (computed on the host, dd_layout())
 struct DDLayout {
     int slice, maxch, capc, smem_keys;  // nodes of a layer per CTA, 32-node chunks per CTA, candidates per CTA, keys / lists in shared memory ?
-    unsigned o_D, o_master, o_stage, o_cnt, o_off, o_koff, o_fb, o_kb, o_keys, o_ulist, o_stat, total;
+    unsigned o_D, o_master, o_stage, o_cnt, o_off, o_koff, o_fb, o_kb, o_keys, o_ulist, o_stat, o_lh, o_gh, o_garr, o_gkeys, o_gstat, o_und, total;
 };
 
 struct DDFixed {
@@ -39,12 +49,19 @@ struct DDFixed {
     unsigned long long red64[40];
     unsigned int hist[2][256];
     unsigned int ghist[256];
-    unsigned long long merged[2][16];  // [0] OR of the merged-away states of this CTA, [1] of the cluster
-    unsigned long long xch[2][8];      // exchange slots (double-buffered across cluster barriers)
+    unsigned long long merged[17];               // OR of the merged-away states of this CTA (+ their best key in [16])
+    unsigned long long mx[DD_MAXCS][17];         // ... of every CTA of the cluster (pushed)
+    unsigned long long xch[2][8][DD_MAXCS];      // exchange slots [phase][slot][source rank] (pushed, double-buffered across barriers)
+    int kbx[2][DD_MAXCS];                        // boundary-bucket candidates kept per rank (pushed by rank 0)
+    int kbc[DD_MAXCS];
     int misc[16];
+    int red4[DD_NW][4];
     int job;
-    unsigned long long cnt[2];         // expanded nodes / transitions of the DD being compiled (this CTA's share)
+    int gcnt;                                    // rank 0: candidates gathered so far
+    int ucnt;                                    // undecided candidates of this CTA
+    unsigned long long cnt[2];                   // expanded nodes / transitions of the DD being compiled (this CTA's share)
     unsigned int tour[DD_NT];
+    long long prof[16]; long long prof_t;       // DDO_DD_PROF: cycles of rank 0 / thread 0 per phase
 };
 
 // ---- hashing: multilinear over the 32-bit halves, h = fin(sum_j w32[j] * m32[j]); the accumulator is stored with every node so that the
@@ -59,6 +76,7 @@ template <int S> __device__ __forceinline__ uint64_t dd_hacc(const uint64_t (&w)
 __device__ __forceinline__ uint64_t dd_hfin(uint64_t a) { a ^= a >> 32; a *= 0x9E3779B97F4A7C15ULL; a ^= a >> 29; return a; }
 
 __device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 
 // ---- device work queue: q[0] next primary, q[1] / q[2] head / tail of the twin queue, q[3] DDs finished or never needed, q[4] total
 __device__ int dd_fetch_job(const EV& ev, int count) {
@@ -91,7 +109,7 @@ __device__ int dd_fetch_job(const EV& ev, int count) {
 static __global__ void k_dd_init(EV ev, int count, int comp_type, long long best_lb, int dual) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int slots = dual ? 2 * count : count;
-    if (k == 0) { ev.dq[0] = 0; ev.dq[1] = 0; ev.dq[2] = 0; ev.dq[3] = 0; ev.dq[4] = slots; *ev.active = 0; }
+    if (k == 0) { ev.dq[0] = 0; ev.dq[1] = 0; ev.dq[2] = 0; ev.dq[3] = 0; ev.dq[4] = slots; ev.dq[5] = 0; *ev.active = 0; }
     if (k >= slots) return;
     ev.dq_jobs[k] = -1;
     const bool twin = k >= count;
@@ -115,13 +133,15 @@ struct DDC {
     cg::cluster_group cl;
     unsigned CS, rank;
     int tid, lane, warp;
-    int xphase = 0, hphase = 0;
+    int xphase = 0, hphase = 0, kphase = 0;
     // shared-memory views
     int* D[2]; unsigned int* master; uint32_t* stage; int* cnt_s; int* off_s; int* koff_s; uint2* fb_s; uint2* kb_s;
     unsigned long long* keys; uint32_t* ulist; uint8_t* stat;
+    unsigned int* lh; unsigned int* gh; unsigned long long* garr; unsigned long long* gkeys; uint8_t* gstat; uint32_t* und;
     // the DD
     int k, rk; size_t cb, lb, nb; DDCtl* ctl;
     int comp, W; long long best_lb;
+    unsigned long long* tabs[2];
     // histogram staging of this warp
     int st_cnt = 0; unsigned st_minus = 0; int hcnt[W32];
 
@@ -133,23 +153,47 @@ struct DDC {
         stage = reinterpret_cast<uint32_t*>(dsm + L.o_stage) + (size_t)warp * 32 * SROW;
         cnt_s = reinterpret_cast<int*>(dsm + L.o_cnt); off_s = reinterpret_cast<int*>(dsm + L.o_off); koff_s = reinterpret_cast<int*>(dsm + L.o_koff);
         fb_s = reinterpret_cast<uint2*>(dsm + L.o_fb); kb_s = reinterpret_cast<uint2*>(dsm + L.o_kb);
+        lh = reinterpret_cast<unsigned int*>(dsm + L.o_lh); gh = reinterpret_cast<unsigned int*>(dsm + L.o_gh);
+        garr = reinterpret_cast<unsigned long long*>(dsm + L.o_garr); gkeys = reinterpret_cast<unsigned long long*>(dsm + L.o_gkeys);
+        gstat = dsm + L.o_gstat; und = reinterpret_cast<uint32_t*>(dsm + L.o_und);
     }
 
-    // ---- cluster exchange of up to 8 block-uniform values --------------------------------------------------------------------
-    __device__ void publish(const unsigned long long* v, int n) { if (tid == 0) for (int i = 0; i < n; ++i) fx.xch[xphase][i] = v[i]; }
-    __device__ unsigned long long peer(int i, unsigned r) { return *cl.map_shared_rank(&fx.xch[xphase][i], r); }
-    __device__ void xnext() { xphase ^= 1; }
-    template <class Op> __device__ void allreduce(unsigned long long* v, int n, Op op) {
-        publish(v, n); cl.sync();
-        for (int i = 0; i < n; ++i) { unsigned long long acc = peer(i, 0); for (unsigned r = 1; r < CS; ++r) acc = op(acc, peer(i, r)); v[i] = acc; }
-        xnext();
+    // ---- cluster exchange of up to 8 block-uniform values: pushed into every peer, read locally after the barrier ---------------------
+    __device__ __forceinline__ void push(int nvals, unsigned long long v0, unsigned long long v1 = 0, unsigned long long v2 = 0, unsigned long long v3 = 0,
+                                         unsigned long long v4 = 0, unsigned long long v5 = 0) {
+        if (tid < nvals * (int)CS) {
+            const int slot = tid / (int)CS; const unsigned r = tid % CS;
+            const unsigned long long v = slot == 0 ? v0 : slot == 1 ? v1 : slot == 2 ? v2 : slot == 3 ? v3 : slot == 4 ? v4 : v5;
+            *cl.map_shared_rank(&fx.xch[xphase][slot][rank], r) = v;
+        }
     }
-    __device__ int xscan(int v, int* total) {  // exclusive prefix over the ranks of one block-uniform count
-        unsigned long long x = (unsigned long long)(unsigned)v;
-        publish(&x, 1); cl.sync();
-        int pre = 0, tot = 0;
-        for (unsigned r = 0; r < CS; ++r) { const int y = (int)peer(0, r); if (r < rank) pre += y; tot += y; }
-        xnext(); *total = tot; return pre;
+    __device__ __forceinline__ unsigned long long got(int slot, unsigned r) const { return fx.xch[xphase][slot][r]; }
+    __device__ __forceinline__ void xnext() { xphase ^= 1; }
+    template <class Op> __device__ unsigned long long allreduce1(unsigned long long v, Op op) {
+        push(1, v); cl.sync();
+        unsigned long long acc = got(0, 0);
+        for (unsigned r = 1; r < CS; ++r) acc = op(acc, got(0, r));
+        xnext();
+        return acc;
+    }
+    // sum over the block of 4 ints per thread (results broadcast)
+    __device__ void block_sum4(int (&v)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = warp_reduce(v[q], [](int a, int b) { return a + b; });
+        __syncthreads();
+        if (lane == 0) for (int q = 0; q < 4; ++q) fx.red4[warp][q] = v[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { int s = 0; for (int w2 = 0; w2 < DD_NW; ++w2) s += fx.red4[w2][q]; v[q] = s; }
+    }
+    __device__ void block_max4(int (&v)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = warp_reduce(v[q], [](int a, int b) { return a > b ? a : b; });
+        __syncthreads();
+        if (lane == 0) for (int q = 0; q < 4; ++q) fx.red4[warp][q] = v[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { int s = INT32_MIN; for (int w2 = 0; w2 < DD_NW; ++w2) s = max(s, fx.red4[w2][q]); v[q] = s; }
     }
 
     // ---- rows ---------------------------------------------------------------------------------------------------------------
@@ -216,12 +260,12 @@ struct DDC {
     // ---- open-addressing insert (next_l.entry(), clean.rs:738-775 + append_edge_to! :199-220) ---------------------------------------
     // returns true when candidate c claimed a slot (a new distinct state); rep = claimer of the state
     template <class RowFn>
-    __device__ __forceinline__ bool insert(uint64_t hacc, uint32_t c, uint32_t ident, int value, uint32_t fl, int buf, RowFn my_row, uint32_t& rep, uint32_t& slot_out) {
+    __device__ __forceinline__ bool insert(unsigned long long* tab, uint64_t hacc, uint32_t c, uint32_t ident, int value, uint32_t fl, int buf, RowFn my_row, uint32_t& rep,
+                                           uint32_t& slot_out) {
         const uint64_t h = dd_hfin(hacc);
         const uint32_t tag = (uint32_t)(h >> 32);
         const unsigned long long entry = ((unsigned long long)tag << 32) | c | ident;
         uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
-        unsigned long long* tab = ev.table + (size_t)k * ev.T;
         uint64_t w[S]; bool loaded = false;
         for (;;) {
             const unsigned long long old = atomicCAS(tab + slot, EMPTY64, entry);
@@ -246,9 +290,35 @@ struct DDC {
         }
     }
 
+    // ---- child log of the PREVIOUS layer step (relaxed DDs: edge (parent c / 2, decision) -> node of the layer committed last) and release
+    // of the hash slots its candidates claimed; runs at the start of the next step, off the critical path (the table, the positions and the
+    // first-candidate links are double-buffered by layer parity)
+    __device__ void trail(int tp, int n_prev, bool relaxed) {
+        const int slice_lo = min((int)rank * L.slice, n_prev), slice_hi = min(slice_lo + L.slice, n_prev);
+        const int nch = (slice_hi - slice_lo + 31) >> 5;
+        unsigned long long* tab = tabs[tp & 1];
+        const uint32_t* pos = (tp & 1) ? ev.ulist : ev.pos_of;  // positions of layer tp + 1, written by its commit
+        for (int ch = warp; ch < nch; ch += DD_NW) {
+            const int i = slice_lo + 32 * ch + lane;
+            if (i < slice_hi) {
+                const uint2 sl = *reinterpret_cast<const uint2*>(ev.cand_slot + cb + 2u * i);
+                if (sl.x != NONE32) tab[sl.x] = EMPTY64;
+                if (sl.y != NONE32) tab[sl.y] = EMPTY64;
+                if (relaxed) {
+                    const uint2 f = *reinterpret_cast<const uint2*>(ev.cand_f + cb + 2u * i);
+                    uint32_t cy = NONE32, cn = NONE32;
+                    if (f.x != NONE32) cy = __ldcg(pos + cb + f.x);
+                    if (f.y != NONE32) cn = __ldcg(pos + cb + f.y);
+                    *reinterpret_cast<uint2*>(ev.clog + (lb + tp) * ev.C + 2u * i) = make_uint2(cy, cn);
+                }
+            }
+        }
+    }
+
     // ---- E: expansion of layer t (clean.rs:360-370, :728-776; misp/main.rs:77-102,191-193) --------------------------------------------
     __device__ void expand(int t, int n, int var) {
         const int buf = t & 1, e = t & 1;
+        unsigned long long* tab = tabs[t & 1];
         const int slice_lo = min((int)rank * L.slice, n), slice_hi = min(slice_lo + L.slice, n);
         const int nch = (slice_hi - slice_lo + 31) >> 5;
         const int vw = var >> 6;
@@ -266,7 +336,6 @@ struct DDC {
             const int i = slice_lo + 32 * ch + lane;
             const bool active = i < slice_hi;
             uint64_t w[S];
-            bool have_row = false;
             uint32_t rep_y = NONE32, rep_n = NONE32, slot_y = NONE32, slot_n = NONE32;
             bool minus_parent = false, plus_yes = false;
             uint64_t wy[S];
@@ -279,7 +348,7 @@ struct DDC {
                 const bool expandable = ((long long)rub + (long long)val) > best_lb;  // clean.rs:364-365
                 const uint64_t* prow = ev.cur_state[buf] + (nb + i) * S;
                 if (!expandable) {
-                    load_row_cg(prow, w); have_row = true; minus_parent = true;  // the node leaves without a child
+                    load_row_cg(prow, w); minus_parent = true;  // the node leaves without a child
                 } else {
                     const bool has_v = (__ldcg(prow + vw) & bit) != 0;  // misp/main.rs:96
                     ++my_exp; my_tr += has_v ? 2 : 1;
@@ -289,12 +358,12 @@ struct DDC {
                         ev.cand_agg[cb + c_no] = pack_key(val, c_no);
                         ev.cand_first[cb + c_no] = c_no;
                         ev.cand_inex[cb + c_no] = (uint8_t)(fl & NF_INEXACT);
-                        __threadfence();
-                        const bool claimed = insert(hacc, c_no, DD_IDENT, val, fl, buf, [&](uint64_t (&r)[S]) { load_row_cg(prow, r); }, rep_n, slot_n);
+                        fence_cluster();
+                        const bool claimed = insert(tab, hacc, c_no, DD_IDENT, val, fl, buf, [&](uint64_t (&r)[S]) { load_row_cg(prow, r); }, rep_n, slot_n);
                         rep_n |= DD_IDENT;
-                        if (!claimed) { load_row_cg(prow, w); have_row = true; minus_parent = true; }  // its state is already counted through the claimer
+                        if (!claimed) { load_row_cg(prow, w); minus_parent = true; }  // its state is already counted through the claimer
                     } else {
-                        load_row_cg(prow, w); have_row = true;
+                        load_row_cg(prow, w);
 #pragma unroll
                         for (int j = 0; j < S; ++j) if (j == vw) w[j] &= ~bit;  // res.remove(var), main.rs:79: w is now the NO child
                         int pcy = 0;
@@ -310,11 +379,11 @@ struct DDC {
                         *reinterpret_cast<uint2*>(ev.cand_rank + cb + c_yes) = make_uint2((uint32_t)pcy, (uint32_t)(pc - 1));
                         ev.cand_hacc[cb + c_yes] = hy; ev.cand_hacc[cb + c_no] = hn;
                         if (!ev.unit_weights) { ev.cand_rub[cb + c_yes] = row_rub(wy, pcy); ev.cand_rub[cb + c_no] = rub - wv; }
-                        __threadfence();
-                        plus_yes = insert(hy, c_yes, 0u, valy, fl, buf, [&](uint64_t (&r)[S]) {
+                        fence_cluster();
+                        plus_yes = insert(tab, hy, c_yes, 0u, valy, fl, buf, [&](uint64_t (&r)[S]) {
 #pragma unroll
                             for (int j = 0; j < S; ++j) r[j] = wy[j]; }, rep_y, slot_y);
-                        const bool claimed_n = insert(hn, c_no, 0u, val, fl, buf, [&](uint64_t (&r)[S]) {
+                        const bool claimed_n = insert(tab, hn, c_no, 0u, val, fl, buf, [&](uint64_t (&r)[S]) {
 #pragma unroll
                             for (int j = 0; j < S; ++j) r[j] = w[j]; }, rep_n, slot_n);
                         if (claimed_n) ++no_claims;  // parent row out, NO row in: only the branching vertex loses an occurrence
@@ -326,7 +395,6 @@ struct DDC {
                 *reinterpret_cast<uint2*>(ev.cand_rep + cb + 2u * i) = make_uint2(rep_y, rep_n);
                 *reinterpret_cast<uint2*>(ev.cand_slot + cb + 2u * i) = make_uint2(slot_y, slot_n);
             }
-            (void)have_row;
             stage_rows(minus_parent, w, true);
             stage_rows(plus_yes, wy, false);
         }
@@ -343,7 +411,7 @@ struct DDC {
 
     // compare two distinct candidates (with their DD_IDENT flags) by the cut order (clean.rs:803-808 + misp/main.rs:205-208)
     __device__ bool better(uint32_t a, uint32_t b, uint32_t rep_a, uint32_t rep_b, int pca, int pcb, int buf) const {
-        const int va = key_value(ev.cand_agg[cb + rep_a]), vb2 = key_value(ev.cand_agg[cb + rep_b]);
+        const int va = key_value(__ldcg(ev.cand_agg + cb + rep_a)), vb2 = key_value(__ldcg(ev.cand_agg + cb + rep_b));
         if (va != vb2) return va > vb2;
         if (pca != pcb) return pca > pcb;
         const uint64_t* ra = cand_row(a, buf); const uint64_t* rb = cand_row(b, buf);
@@ -355,6 +423,89 @@ struct DDC {
         return (cf & DD_IDENT) ? (int)(ld_cg_u4(ev.nmeta[buf] + nb + (c >> 1)).w & 0xFFFFu) : (int)__ldcg(ev.cand_rank + cb + c);
     }
 
+    // ---- MSD radix select of the `need` best among the undecided (st == 0) entries of kk / st / list[0 .. n): 1 = keep, 2 = drop.
+    // Chunk 0 of a key is what kk holds on entry (used when first_chunk == 0), chunk j >= 1 packs the next MK members of the state
+    // (member_key).  CLUSTER: the entries are spread over the CTAs of the cluster (digit histograms summed through DSMEM, one cluster
+    // barrier per digit); otherwise this CTA alone, block barriers only.
+    template <bool CLUSTER>
+    __device__ void radix_select(unsigned long long* kk, uint8_t* st, const uint32_t* list, const unsigned long long* list64, int n, int need, int first_chunk, int buf) {
+        bool done = false;
+        if (need == 0) { for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) st[li] = 2; done = true; }
+        for (int chunk = first_chunk; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
+            if (chunk > 0) {  // the next MK members of every still undecided state
+                for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) {
+                    uint64_t w[S];
+                    load_row_cg(cand_row(list ? list[li] : (uint32_t)list64[li], buf), w);
+                    kk[li] = member_key<S>(w, MemberKey<S>::MK * (chunk - 1));
+                }
+                __syncthreads();
+            }
+            unsigned long long k0 = 0ull, k1 = 0ull;
+            for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) { const unsigned long long x = kk[li]; k0 |= x; k1 |= ~x; }
+            k0 = block_reduce(k0, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
+            k1 = block_reduce(k1, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
+            if (CLUSTER) {
+                push(2, k0, k1); cl.sync();
+                k0 = 0; k1 = 0;
+                for (unsigned r = 0; r < CS; ++r) { k0 |= got(0, r); k1 |= got(1, r); }
+                xnext();
+            }
+            const unsigned long long diff = k0 ^ ~k1;
+            for (int byte = 7; byte >= 0 && !done; --byte) {
+                if (((diff >> (8 * byte)) & 0xff) == 0) continue;
+                unsigned int* h = fx.hist[hphase];
+                for (int i = tid; i < 256; i += DD_NT) h[i] = 0;
+                __syncthreads();
+                for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) atomicAdd(&h[(kk[li] >> (8 * byte)) & 0xff], 1u);
+                if (CLUSTER) {
+                    cl.sync();
+                    for (int i = tid; i < 256; i += DD_NT) {
+                        unsigned int a = 0;
+                        for (unsigned r = 0; r < CS; ++r) a += *cl.map_shared_rank(&h[i], r);
+                        fx.ghist[i] = a;
+                    }
+                    hphase ^= 1;
+                } else {
+                    __syncthreads();
+                    for (int i = tid; i < 256; i += DD_NT) fx.ghist[i] = h[i];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    int c8[8]; int s8 = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { c8[q] = (int)fx.ghist[255 - (lane * 8 + q)]; s8 += c8[q]; }
+                    int inc = s8;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
+                    const int before = inc - s8;
+                    if (before < need && need <= inc) {
+                        int acc = before;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (acc < need && need <= acc + c8[q]) { fx.misc[0] = 255 - (lane * 8 + q); fx.misc[1] = acc; fx.misc[2] = c8[q]; }
+                            acc += c8[q];
+                        }
+                    }
+                }
+                __syncthreads();
+                const int b = fx.misc[0], above = fx.misc[1], inb = fx.misc[2];
+                need -= above;
+                const bool all_keep = (need == inb);
+                for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) {
+                    const int d = (int)((kk[li] >> (8 * byte)) & 0xff);
+                    if (d > b) st[li] = 1; else if (d < b) st[li] = 2; else if (all_keep) st[li] = 1;
+                }
+                __syncthreads();
+                if (all_keep) done = true;
+            }
+        }
+        __syncthreads();
+    }
+
+    // phase timer (thread 0 of rank 0; ev.dd_prof != nullptr only in profiling runs)
+    __device__ __forceinline__ void prof(int phase) {
+        if (ev.dd_prof && rank == 0 && tid == 0) { const long long c = clock64(); fx.prof[phase] += c - fx.prof_t; fx.prof_t = c; }
+    }
     __device__ void run(int slot, int count, int dual);
 };
 
@@ -364,6 +515,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
     cb = (size_t)k * ev.C; lb = (size_t)k * ev.Lmax; nb = (size_t)k * ev.Wcap;
     ctl = ev.ctl + k;
     comp = ctl->comp_type; W = ctl->width; best_lb = ctl->best_lb;
+    tabs[0] = ev.table + (size_t)k * ev.T; tabs[1] = ev.table + ((size_t)ev.K + k) * ev.T;
     const bool relaxed = comp == DDO_RELAXED;
     if (L.smem_keys) {
         keys = reinterpret_cast<unsigned long long*>(dsm + L.o_keys); ulist = reinterpret_cast<uint32_t*>(dsm + L.o_ulist); stat = dsm + L.o_stat;
@@ -379,7 +531,8 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
 
     // ---- root (clean.rs:383-405): node 0 of layer 0 ----------------------------------------------------------------------------
     for (int i = tid; i < 2 * ev.HN; i += DD_NT) D[0][i] = 0;
-    if (tid == 0) { fx.cnt[0] = 0; fx.cnt[1] = 0; }
+    for (int i = tid; i < DD_NB; i += DD_NT) gh[i] = 0;
+    if (tid == 0) { fx.cnt[0] = 0; fx.cnt[1] = 0; fx.gcnt = 0; }
     unsigned long long best = ~0ull;
     for (int u = u_lo + tid; u < u_hi; u += DD_NT) {
         const unsigned c = (unsigned)((ev.root_state[(size_t)rk * S + (u >> 6)] >> (u & 63)) & 1ull);
@@ -400,10 +553,10 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
         }
     }
     best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, fx.red64);
-    allreduce(&best, 1, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; });
+    best = allreduce1(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; });
     int var = best == ~0ull ? -1 : (int)(uint32_t)best;
-    int n = 1, t = 0, lel = -1;
-    bool twin_pushed = false;
+    int n = 1, t = 0, lel = -1, n_prev = 0;
+    bool twin_pushed = false, have_trail = false;
     if (rank == 0 && tid == 0) ev.vlog[lb] = var;
     if (var < 0) {  // the root is a terminal node (clean.rs:350,608-632)
         if (rank == 0 && tid == 0) {
@@ -412,25 +565,34 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             ctl->status = ST_DONE; ctl->t_term = 0; ctl->n_cur = 1; ctl->var = -1; ctl->ncand = 1;
         }
     }
-    __threadfence();
     cl.sync();
 
+    if (ev.dd_prof && rank == 0 && tid == 0) { for (int i = 0; i < 16; ++i) fx.prof[i] = 0; fx.prof_t = clock64(); }
     while (var >= 0) {
         const int buf = t & 1, nbuf = buf ^ 1, e = t & 1;
+        uint32_t* pos_w = (t & 1) ? ev.ulist : ev.pos_of;  // positions of the first candidates of this step (read by the next step's trail)
         // D[e ^ 1] was last read by the peers two barriers ago: clear it for the next epoch
         for (int i = tid; i < ev.HN; i += DD_NT) D[e ^ 1][i] = 0;
+        if (have_trail) trail(t - 1, n_prev, relaxed);
+        prof(0);
         expand(t, n, var);
-        __threadfence();
+        prof(1);
         cl.sync();  // ---- S1: every candidate of layer t+1 is inserted ------------------------------------------------------------
+        prof(2);
 
-        // ---- next_variable (misp/main.rs:109-143): occurrence counts of the distinct states of layer t+1, argmin, lowest index on ties
+        // ---- next_variable (misp/main.rs:109-143): occurrence counts of the distinct states of layer t+1, argmin, lowest index on ties.
+        // Thread (u, r) fetches rank r's delta of vertex u; the CS lanes of a vertex fold them with shuffles.
         best = ~0ull;
-        for (int u = u_lo + tid; u < u_hi; u += DD_NT) {
-            int d = 0;
-            for (unsigned r = 0; r < CS; ++r) d += *cl.map_shared_rank(&D[e][u], r);
-            const unsigned m = master[u] + (unsigned)d;
-            master[u] = m;
-            if (m) best = min(best, ((unsigned long long)m << 32) | (unsigned)u);
+        for (int base = 0; base < HS * (int)CS; base += DD_NT) {
+            const int idx = base + tid;
+            const int u = u_lo + idx / (int)CS; const unsigned r = idx % CS;
+            int d = idx < HS * (int)CS ? *cl.map_shared_rank(&D[e][u], r) : 0;
+            for (unsigned s = 1; s < CS; s <<= 1) d += __shfl_xor_sync(FULL_MASK, d, s);
+            if (r == 0 && idx < HS * (int)CS) {
+                const unsigned m = master[u] + (unsigned)d;
+                master[u] = m;
+                if (m) best = min(best, ((unsigned long long)m << 32) | (unsigned)u);
+            }
         }
         // ---- first candidates (rule C1): candidate c represents its state iff it is the smallest candidate that produced it -----------
         const int ncand = 2 * n;
@@ -441,8 +603,10 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             bool fy = false, fn = false;
             if (i < slice_hi) {
                 const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
-                if (rp.x != NONE32) fy = __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)) == 2u * i;
-                if (rp.y != NONE32) fn = __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)) == 2u * i + 1u;
+                uint32_t f0 = NONE32, f1 = NONE32;
+                if (rp.x != NONE32) { f0 = __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)); fy = f0 == 2u * i; }
+                if (rp.y != NONE32) { f1 = __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)); fn = f1 == 2u * i + 1u; }
+                *reinterpret_cast<uint2*>(ev.cand_f + cb + 2u * i) = make_uint2(f0, f1);
             }
             const unsigned by = __ballot_sync(FULL_MASK, fy), bn = __ballot_sync(FULL_MASK, fn);
             if (lane == 0) { fb_s[ch] = make_uint2(by, bn); cnt_s[ch] = __popc(by) + __popc(bn); }
@@ -457,12 +621,49 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) { off_s[ch] = o; o += cnt_s[ch]; } }
         }
         best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, fx.red64);
-        unsigned long long x2[2] = {(unsigned long long)(unsigned)Ublk, best};
-        publish(x2, 2);
+        // ---- ordered list of the distinct candidates of this CTA and the keys of the width cut (only when a cut is possible: U <= 2 n) ---
+        const bool may_cut = comp != DDO_EXACT && ncand > W;
+        int mm[4] = {INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN};  // max value, max -value, max popcount, max -popcount
+        if (may_cut) {
+            for (int ch = warp; ch < nch; ch += DD_NW) {
+                const uint2 fb = fb_s[ch];
+                const int i = slice_lo + 32 * ch + lane;
+                const unsigned lt = (1u << lane) - 1u;
+                const int base = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
+                const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
+                if (fy | fn) {
+                    const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+#pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        if (!(d == 0 ? fy : fn)) continue;
+                        const uint32_t rpx = d == 0 ? rp.x : rp.y;
+                        const int li = base + (d == 1 && fy ? 1 : 0);
+                        const uint32_t cf = (2u * i + d) | (rpx & DD_IDENT);
+                        const int pc = cand_pc(cf, buf);
+                        const unsigned long long ag = __ldcg(ev.cand_agg + cb + (rpx & DD_CMASK));
+                        const int value = key_value(ag);
+                        ulist[li] = cf; stat[li] = 0;
+                        keys[li] = (ag & 0xFFFFFFFF00000000ull) | (unsigned)pc;
+                        mm[0] = max(mm[0], value); mm[1] = max(mm[1], -value); mm[2] = max(mm[2], pc); mm[3] = max(mm[3], -pc);
+                    }
+                }
+            }
+            block_max4(mm);
+        }
+        push(6, (unsigned long long)(unsigned)Ublk, best, (unsigned long long)(uint32_t)mm[0], (unsigned long long)(uint32_t)mm[1], (unsigned long long)(uint32_t)mm[2],
+             (unsigned long long)(uint32_t)mm[3]);
+        prof(3);
         cl.sync();  // ---- S2 ---------------------------------------------------------------------------------------------------------
+        prof(4);
         int U = 0, cta_off = 0;
         best = ~0ull;
-        for (unsigned r = 0; r < CS; ++r) { const int y = (int)peer(0, r); if (r < rank) cta_off += y; U += y; best = min(best, peer(1, r)); }
+        for (unsigned r = 0; r < CS; ++r) {
+            const int y = (int)got(0, r);
+            if (r < rank) cta_off += y;
+            U += y; best = min(best, got(1, r));
+            mm[0] = max(mm[0], (int)(uint32_t)got(2, r)); mm[1] = max(mm[1], (int)(uint32_t)got(3, r));
+            mm[2] = max(mm[2], (int)(uint32_t)got(4, r)); mm[3] = max(mm[3], (int)(uint32_t)got(5, r));
+        }
         xnext();
         const int tn = t + 1;  // the layer being decided
         if (U == 0) {  // every node was pruned: empty layer (clean.rs:667-669) -> no best node
@@ -484,97 +685,127 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             twin_pushed = true;
             if (rank == 0 && tid == 0) { const int idx = atomicAdd(ev.dq + 2, 1); ev.dq_jobs[idx] = count + k; __threadfence(); }
         }
-        // ---- ordered list of the distinct candidates of this CTA; keys of the width cut ------------------------------------------------
+
+        // ---- width cut: the `need` best by (value_top, popcount, BitSet::cmp) -- clean.rs:803-808 / :819-824 ----------------------------
+        int nkeep = U, kcta = cta_off;
         if (cut) {
-            for (int ch = warp; ch < nch; ch += DD_NW) {
-                const uint2 fb = fb_s[ch];
-                const int i = slice_lo + 32 * ch + lane;
-                const unsigned lt = (1u << lane) - 1u;
-                const int base = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
-                const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
-                if (fy | fn) {
-                    const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
-                    if (fy) {
-                        const uint32_t cf = (2u * i) | (rp.x & DD_IDENT);
-                        ulist[base] = cf; stat[base] = 0;
-                        keys[base] = (__ldcg(ev.cand_agg + cb + (rp.x & DD_CMASK)) & 0xFFFFFFFF00000000ull) | (unsigned)cand_pc(cf, buf);
-                    }
-                    if (fn) {
-                        const int li = base + (fy ? 1 : 0);
-                        const uint32_t cf = (2u * i + 1u) | (rp.y & DD_IDENT);
-                        ulist[li] = cf; stat[li] = 0;
-                        keys[li] = (__ldcg(ev.cand_agg + cb + (rp.y & DD_CMASK)) & 0xFFFFFFFF00000000ull) | (unsigned)cand_pc(cf, buf);
-                    }
+            const int vmin = -mm[1], pcmin = -mm[3];
+            const long long VR = (long long)mm[0] - vmin + 1, PR = (long long)mm[2] - pcmin + 1;
+            const bool dense = !ev.dd_generic && VR * PR <= DD_NB;
+            bool fallback = !dense;
+            int first_chunk = 0;
+            if (need == 0) {  // relaxed DD of width 1: every candidate is merged away
+                for (int li = tid; li < Ublk; li += DD_NT) stat[li] = 2;
+                __syncthreads();
+                nkeep = 0; kcta = 0; fallback = false;
+            } else if (dense) {
+                // one pass: histogram of the dense key (value_top - vmin) * PR + (popcount - pcmin), summed into every CTA by remote atomics
+                const int nbins = (int)(VR * PR);
+                for (int i = tid; i < nbins; i += DD_NT) lh[i] = 0;
+                __syncthreads();
+                for (int li = tid; li < Ublk; li += DD_NT) {
+                    const unsigned long long x = keys[li];
+                    atomicAdd(&lh[(key_value(x) - vmin) * (int)PR + ((int)(uint32_t)x - pcmin)], 1u);
                 }
-            }
-            __syncthreads();
-            // ---- MSD radix select of the `need` best by (value_top, popcount, BitSet::cmp) -- clean.rs:803-808 / :819-824 ---------------
-            bool done = false;
-            if (need == 0) { for (int li = tid; li < Ublk; li += DD_NT) stat[li] = 2; done = true; }
-            for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
-                if (chunk > 0) {  // the next MK members of every still undecided state (member_key)
-                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) {
-                        uint64_t w[S];
-                        load_row_cg(cand_row(ulist[li], buf), w);
-                        keys[li] = member_key<S>(w, MemberKey<S>::MK * (chunk - 1));
-                    }
-                    __syncthreads();
+                __syncthreads();
+                for (int i = tid; i < nbins; i += DD_NT) {
+                    const unsigned v = lh[i];
+                    if (v) for (unsigned r = 0; r < CS; ++r) atomicAdd(cl.map_shared_rank(&gh[i], r), v);
                 }
-                unsigned long long kk[2] = {0ull, 0ull};
-                for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) { const unsigned long long x = keys[li]; kk[0] |= x; kk[1] |= ~x; }
-                kk[0] = block_reduce(kk[0], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
-                kk[1] = block_reduce(kk[1], [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
-                allreduce(kk, 2, [](unsigned long long a, unsigned long long b) { return a | b; });
-                const unsigned long long diff = kk[0] ^ ~kk[1];
-                for (int byte = 7; byte >= 0 && !done; --byte) {
-                    if (((diff >> (8 * byte)) & 0xff) == 0) continue;
-                    unsigned int* h = fx.hist[hphase];
-                    for (int i = tid; i < 256; i += DD_NT) h[i] = 0;
-                    __syncthreads();
-                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) atomicAdd(&h[(keys[li] >> (8 * byte)) & 0xff], 1u);
-                    cl.sync();
-                    for (int i = tid; i < 256; i += DD_NT) {
-                        unsigned int a = 0;
-                        for (unsigned r = 0; r < CS; ++r) a += *cl.map_shared_rank(&h[i], r);
-                        fx.ghist[i] = a;
-                    }
-                    hphase ^= 1;
-                    __syncthreads();
-                    if (warp == 0) {
-                        int c8[8]; int s8 = 0;
+                cl.sync();  // ---- S3 ---------------------------------------------------------------------------------------------------
+                {   // bucket b with  #(bin > b) < need <= #(bin >= b): every thread owns 4 consecutive bins, largest first
+                    int c4[4]; int s4 = 0;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) { c8[q] = (int)fx.ghist[255 - (lane * 8 + q)]; s8 += c8[q]; }
-                        int inc = s8;
+                    for (int q = 0; q < 4; ++q) { const int bi = nbins - 1 - (4 * tid + q); c4[q] = bi >= 0 ? (int)gh[bi] : 0; s4 += c4[q]; }
+                    int tot;
+                    const int before = block_excl_scan(s4, &tot, fx.scan);
+                    if (before < need && need <= before + s4) {
+                        int acc = before;
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
-                        const int before = inc - s8;
-                        if (before < need && need <= inc) {
-                            int acc = before;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (acc < need && need <= acc + c8[q]) { fx.misc[0] = 255 - (lane * 8 + q); fx.misc[1] = acc; fx.misc[2] = c8[q]; }
-                                acc += c8[q];
-                            }
+                        for (int q = 0; q < 4; ++q) {
+                            if (acc < need && need <= acc + c4[q]) { fx.misc[0] = nbins - 1 - (4 * tid + q); fx.misc[1] = acc; fx.misc[2] = c4[q]; }
+                            acc += c4[q];
                         }
                     }
                     __syncthreads();
-                    const int b = fx.misc[0], above = fx.misc[1], inb = fx.misc[2];
-                    need -= above;
-                    const bool all_keep = (need == inb);
-                    for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 0) {
-                        const int d = (int)((keys[li] >> (8 * byte)) & 0xff);
-                        if (d > b) stat[li] = 1; else if (d < b) stat[li] = 2; else if (all_keep) stat[li] = 1;
+                    for (int i = tid; i < nbins; i += DD_NT) gh[i] = 0;  // (the next remote adds come two barriers later at the earliest)
+                }
+                const int b = fx.misc[0], above = fx.misc[1], inb = fx.misc[2];
+                need -= above;
+                const bool all_keep = need == inb;
+                if (tid == 0) fx.ucnt = 0;
+                __syncthreads();
+                int cnts[4] = {0, 0, 0, 0};  // kept for sure, in the boundary bucket
+                for (int li = tid; li < Ublk; li += DD_NT) {
+                    const unsigned long long x = keys[li];
+                    const int bin = (key_value(x) - vmin) * (int)PR + ((int)(uint32_t)x - pcmin);
+                    if (bin > b) { stat[li] = 1; ++cnts[0]; }
+                    else if (bin < b) stat[li] = 2;
+                    else {
+                        ++cnts[1];
+                        if (all_keep) stat[li] = 1;
+                        else if (inb <= DD_GCAP) und[atomicAdd(&fx.ucnt, 1)] = (uint32_t)li;
                     }
+                }
+                block_sum4(cnts);
+                const int above_l = cnts[0], inb_l = cnts[1];
+                if (all_keep) {
+                    push(1, (unsigned long long)(unsigned)(above_l + inb_l));
+                    cl.sync();  // ---- S4' -------------------------------------------------------------------------------------------
+                    nkeep = 0; kcta = 0;
+                    for (unsigned r = 0; r < CS; ++r) { const int y = (int)got(0, r); if (r < rank) kcta += y; nkeep += y; }
+                    xnext();
+                } else if (inb <= DD_GCAP) {
+                    // the candidates of the boundary bucket go to rank 0, which orders them by BitSet::cmp alone
+                    if (tid == 0) fx.misc[3] = inb_l ? atomicAdd(cl.map_shared_rank(&fx.gcnt, 0), inb_l) : 0;
                     __syncthreads();
-                    if (all_keep) done = true;
+                    const int gbase = fx.misc[3];
+                    for (int j = tid; j < inb_l; j += DD_NT) {
+                        const uint32_t li = und[j];
+                        *cl.map_shared_rank(&garr[gbase + j], 0) = (unsigned long long)ulist[li] | ((unsigned long long)li << 32) | ((unsigned long long)rank << 56);
+                    }
+                    push(1, (unsigned long long)(unsigned)above_l);
+                    cl.sync();  // ---- S4 --------------------------------------------------------------------------------------------
+                    int above_r[DD_MAXCS];
+                    for (unsigned r = 0; r < CS; ++r) above_r[r] = (int)got(0, r);
+                    xnext();
+                    if (rank == 0) {
+                        for (int j = tid; j < inb; j += DD_NT) gstat[j] = 0;
+                        if (tid < DD_MAXCS) fx.kbc[tid] = 0;
+                        __syncthreads();
+                        radix_select<false>(gkeys, gstat, nullptr, garr, inb, need, 1, buf);
+                        for (int j = tid; j < inb; j += DD_NT) {
+                            const unsigned long long g = garr[j];
+                            const unsigned owner = (unsigned)(g >> 56); const uint32_t li = (uint32_t)(g >> 32) & 0xFFFFFFu;
+                            const uint8_t s = gstat[j];
+                            if (L.smem_keys) *cl.map_shared_rank(&stat[li], owner) = s;
+                            else ev.dd_stat[(size_t)k * ev.C2 + (size_t)owner * L.capc + li] = s;
+                            if (s == 1) atomicAdd(&fx.kbc[owner], 1);
+                        }
+                        __syncthreads();
+                        if (tid < (int)(CS * CS)) *cl.map_shared_rank(&fx.kbx[kphase][tid % CS], tid / CS) = fx.kbc[tid % CS];
+                        if (tid == 0) fx.gcnt = 0;
+                    }
+                    cl.sync();  // ---- S5 --------------------------------------------------------------------------------------------
+                    nkeep = 0; kcta = 0;
+                    for (unsigned r = 0; r < CS; ++r) { const int y = above_r[r] + fx.kbx[kphase][r]; if (r < rank) kcta += y; nkeep += y; }
+                    kphase ^= 1;
+                } else {
+                    fallback = true; first_chunk = 1;  // a boundary bucket too large for one CTA: the generic select continues from chunk 1
                 }
             }
-            __syncthreads();
-        }
-
-        // ---- stable positions of the survivors (rule C3) ------------------------------------------------------------------------------
-        int nkeep, kcta = cta_off;
-        if (cut) {
+            if (fallback) {
+                radix_select<true>(keys, stat, ulist, nullptr, Ublk, need, first_chunk, buf);
+                int cnts[4] = {0, 0, 0, 0};
+                for (int li = tid; li < Ublk; li += DD_NT) cnts[0] += stat[li] == 1;
+                block_sum4(cnts);
+                push(1, (unsigned long long)(unsigned)cnts[0]);
+                cl.sync();
+                nkeep = 0; kcta = 0;
+                for (unsigned r = 0; r < CS; ++r) { const int y = (int)got(0, r); if (r < rank) kcta += y; nkeep += y; }
+                xnext();
+            }
+            // keep flags and local offsets of the survivors
             for (int ch = warp; ch < nch; ch += DD_NW) {
                 const uint2 fb = fb_s[ch];
                 const unsigned lt = (1u << lane) - 1u;
@@ -585,25 +816,21 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 if (lane == 0) { kb_s[ch] = make_uint2(by, bn); cnt_s[ch] = __popc(by) + __popc(bn); }
             }
             __syncthreads();
-            int kblk;
             {
                 const int per = (nch + DD_NT - 1) / DD_NT;
-                int c = 0;
+                int c = 0, kblk;
                 for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) c += cnt_s[ch]; }
                 int o = block_excl_scan(c, &kblk, fx.scan);
                 for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) { koff_s[ch] = o; o += cnt_s[ch]; } }
             }
-            kcta = xscan(kblk, &nkeep);
-        } else {
-            nkeep = U;
         }
+        prof(5);
         int n_next = nkeep, s_pos = -1, r_pos = -1;
         int mpos = -1;          // position of the node that receives the merged-away states (relaxed cut)
-        uint32_t saved = NONE32;  // candidate kept next to a recycled node (clean.rs:868-871)
 
         // ---- relaxation: merge the overflow (clean.rs:826-876; misp/main.rs:172-178 union) -------------------------------------------
         if (cut && relaxed) {
-            if (tid < 16) fx.merged[0][tid] = 0;
+            if (tid < 17) fx.merged[tid] = 0;
             __syncthreads();
             uint64_t acc[S];
 #pragma unroll
@@ -621,33 +848,39 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 const uint64_t x = warp_reduce(acc[j], [](uint64_t a, uint64_t b) { return a | b; });
-                if (lane == 0 && x) atomicOr(&fx.merged[0][j], (unsigned long long)x);
+                if (lane == 0 && x) atomicOr(&fx.merged[j], (unsigned long long)x);
             }
-            mkey = block_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
-            allreduce(&mkey, 1, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });  // (its barrier also publishes merged[0])
-            if (tid < S) {
-                unsigned long long m = 0;
-                for (unsigned r = 0; r < CS; ++r) m |= *cl.map_shared_rank(&fx.merged[0][tid], r);
-                fx.merged[1][tid] = m;
-            }
+            mkey = warp_reduce(mkey, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+            if (lane == 0 && mkey) atomicMax(&fx.merged[16], mkey);
             __syncthreads();
-            // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state.  Every CTA runs the same lookup (cluster-uniform).
+            if (tid < (S + 1) * (int)CS) {  // every CTA's union and best key, pushed to every peer
+                const int j = tid / (int)CS; const unsigned r = tid % CS;
+                const int src = j < S ? j : 16;
+                *cl.map_shared_rank(&fx.mx[rank][src], r) = fx.merged[src];
+            }
+            cl.sync();  // ---- S6 -----------------------------------------------------------------------------------------------------
+            if (tid < 17) { unsigned long long m = 0; if (tid < S) for (unsigned r = 0; r < CS; ++r) m |= fx.mx[r][tid]; else if (tid == 16) for (unsigned r = 0; r < CS; ++r) m = max(m, fx.mx[r][16]); fx.merged[tid] = m; }
+            __syncthreads();
+            mkey = fx.merged[16];
+            // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state.  Every CTA runs the same lookup (cluster-uniform);
+            // the table of this parity is only released by the next step's trail.
             if (tid == 0) {
                 uint64_t mw[S];
 #pragma unroll
-                for (int j = 0; j < S; ++j) mw[j] = fx.merged[1][j];
+                for (int j = 0; j < S; ++j) mw[j] = fx.merged[j];
                 const uint64_t h = dd_hfin(dd_hacc<S>(mw));
                 const uint32_t tag = (uint32_t)(h >> 32);
                 uint32_t sl = (uint32_t)h & (uint32_t)(ev.T - 1);
-                const unsigned long long* tab = ev.table + (size_t)k * ev.T;
+                const unsigned long long* tab = tabs[t & 1];
                 int recycled = -1, rec_rep = -1;
                 for (;;) {
                     const unsigned long long en = __ldcg(tab + sl);
                     if (en == EMPTY64) break;
                     if ((uint32_t)(en >> 32) == tag) {
-                        const uint64_t* orow = cand_row((uint32_t)en, buf);
+                        const uint4* orow = reinterpret_cast<const uint4*>(cand_row((uint32_t)en, buf));
                         bool eq = true;
-                        for (int j = 0; j < S; ++j) eq = eq && __ldcg(orow + j) == mw[j];
+#pragma unroll
+                        for (int q = 0; q < S / 2; ++q) { const uint4 o4 = ld_cg_u4(orow + q); eq = eq && u4lo(o4) == mw[2 * q] && u4hi(o4) == mw[2 * q + 1]; }
                         if (eq) { rec_rep = (int)((uint32_t)en & DD_CMASK); recycled = (int)__ldcg(ev.cand_first + cb + rec_rep); break; }
                     }
                     sl = (sl + 1) & (uint32_t)(ev.T - 1);
@@ -657,9 +890,9 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             __syncthreads();
             int recycled = fx.misc[4];
             const int rec_rep = fx.misc[5];
-            // is the state's first candidate kept ?  Its owner CTA knows; everybody learns it through one exchange.
-            unsigned long long rinfo = 0;  // (kept ? position + 1 : 0) published by the owner
             if (recycled >= 0) {
+                // (rare) is the state's first candidate kept ?  Its owner CTA knows; everybody learns it through one exchange.
+                unsigned long long rinfo = 0;  // (kept ? position + 1 : 0) published by the owner
                 const int ri = recycled >> 1;
                 if (ri >= slice_lo && ri < slice_hi) {
                     const int ch = (ri - slice_lo) >> 5, ln = (ri - slice_lo) & 31;
@@ -671,9 +904,10 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                         rinfo = (unsigned long long)(p + 1);
                     }
                 }
+                rinfo = allreduce1(rinfo, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+                if (rinfo == 0) recycled = -1;
+                else r_pos = (int)rinfo - 1;
             }
-            allreduce(&rinfo, 1, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
-            if (rinfo == 0) recycled = -1;
             if (recycled >= 0) {
                 // the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node (clean.rs:868-871)
                 uint32_t bestc = NONE32, bestrep = 0; int bestpc = 0;
@@ -699,10 +933,10 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     }
                     __syncthreads();
                 }
-                unsigned long long bc = fx.tour[0];
-                publish(&bc, 1); cl.sync();
+                push(1, (unsigned long long)fx.tour[0]); cl.sync();
+                uint32_t saved = NONE32;
                 for (unsigned r = 0; r < CS; ++r) {
-                    const uint32_t c2 = (uint32_t)peer(0, r);
+                    const uint32_t c2 = (uint32_t)got(0, r);
                     if (c2 == NONE32) continue;
                     bool take = saved == NONE32;
                     if (!take) {
@@ -712,7 +946,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     if (take) saved = c2;
                 }
                 xnext();
-                s_pos = nkeep; r_pos = (int)rinfo - 1; n_next = nkeep + 1; mpos = r_pos;
+                s_pos = nkeep; n_next = nkeep + 1; mpos = r_pos;
                 cl.sync();  // every CTA has read cand_agg[rec_rep] through better() before rank 0 rewrites it
                 if (rank == 0 && tid == 0) {
                     // the recycled node receives every relaxed edge: RELAXED flag, value_top = max (`>=`: the appended edges win ties)
@@ -720,15 +954,15 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     if (key_value(mkey) >= key_value(rkey)) ev.cand_agg[cb + rec_rep] = mkey;
                     ev.cand_inex[cb + rec_rep] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
                 }
-                __threadfence();
                 cl.sync();  // ... and the commit below reads the rewritten record
                 for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2 && ulist[li] == saved) stat[li] = 3;  // kept at s_pos
             } else {
+                r_pos = -1;
                 mpos = nkeep; n_next = nkeep + 1;
                 if (rank == 0 && tid < 32) {  // new merged node (clean.rs:832-849) written straight into the next layer
                     uint64_t mw[S]; int pc = 0;
 #pragma unroll
-                    for (int j = 0; j < S; ++j) { mw[j] = fx.merged[1][j]; pc += __popcll(mw[j]); }
+                    for (int j = 0; j < S; ++j) { mw[j] = fx.merged[j]; pc += __popcll(mw[j]); }
                     if (tid == 0) {
                         store_row(ev.cur_state[nbuf] + (nb + mpos) * S, mw);
                         const uint64_t ha = dd_hacc<S>(mw);
@@ -738,7 +972,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     }
                     // its occurrences enter the histogram of the next epoch (one lane per 32-bit column)
                     for (int j = lane; j < W32; j += 32) {
-                        uint32_t x = (uint32_t)(fx.merged[1][j >> 1] >> ((j & 1) * 32));
+                        uint32_t x = (uint32_t)(fx.merged[j >> 1] >> ((j & 1) * 32));
                         while (x) { const int b = __ffs((int)x) - 1; atomicAdd(&D[e ^ 1][32 * j + b], 1); x &= x - 1; }
                     }
                 }
@@ -746,6 +980,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             __syncthreads();
         }
 
+        prof(6);
         // ---- commit of layer t+1 (_move_to_next_layer, clean.rs:657-687): rows, node records, parent log, positions ----------------------
         unsigned long long b_all = 0, b_ex = 0;  // terminal layer: (biased value, pos + 1), last maximum (rule C4)
         for (int ch = warp; ch < nch; ch += DD_NW) {
@@ -756,15 +991,15 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
             uint2 kb = fb; int kbase = cta_off + fbase;
             if (cut) { kb = kb_s[ch]; kbase = kcta + koff_s[ch] + __popc(kb.x & lt) + __popc(kb.y & lt); }
-            uint64_t wdrop[S];
-            bool drop_any = false;
+            uint64_t w0[S], w1[S];
+            bool drop0 = false, drop1 = false;
             uint2 rp = make_uint2(NONE32, NONE32);
             if (fy | fn) rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 const bool isf = d == 0 ? fy : fn;
+                uint64_t (&w)[S] = d == 0 ? w0 : w1;
                 bool dropped = false;
-                uint64_t w[S];
                 if (isf) {
                     const uint32_t c = 2u * i + d;
                     const uint32_t rflag = d == 0 ? rp.x : rp.y;
@@ -777,12 +1012,12 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                         if (stat[li] == 3) { keep = true; pos = s_pos; }   // the saved node of the recycled corner case
                         else { dropped = true; pos = relaxed ? mpos : -1; }
                     }
-                    ev.pos_of[cb + c] = dropped ? (pos < 0 ? NONE32 : (uint32_t)pos) : (uint32_t)pos;
+                    pos_w[cb + c] = pos < 0 ? NONE32 : (uint32_t)pos;
+                    load_row_cg(cand_row(cf, buf), w);  // (a dropped state: its occurrences leave the histogram)
                     if (keep) {
                         const unsigned long long key = __ldcg(ev.cand_agg + cb + rpc);
                         const uint32_t fl = __ldcg(ev.cand_inex + cb + rpc);
                         const int value = key_value(key);
-                        load_row_cg(cand_row(cf, buf), w);
                         store_row(ev.cur_state[nbuf] + (nb + pos) * S, w);
                         uint64_t ha; int pc;
                         if (cf & DD_IDENT) { const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i); ha = (uint64_t)m.x | ((uint64_t)m.y << 32); pc = (int)(m.w & 0xFFFFu); if (!ev.unit_weights) ev.vb[nbuf][nb + pos] = __ldcg(ev.vb[buf] + nb + i); }
@@ -790,35 +1025,29 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                         ev.nmeta[nbuf][nb + pos] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)value, (uint32_t)pc | (fl << 16));
                         ev.plog[(lb + tn) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
                         if (terminal) {
-                            const unsigned long long kk = (key & 0xFFFFFFFF00000000ull) | (unsigned)(pos + 1);
-                            b_all = max(b_all, kk);
-                            if (!(fl & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk);
+                            const unsigned long long kk2 = (key & 0xFFFFFFFF00000000ull) | (unsigned)(pos + 1);
+                            b_all = max(b_all, kk2);
+                            if (!(fl & (NF_INEXACT | NF_RELAXED))) b_ex = max(b_ex, kk2);
                         }
-                    } else {
-                        load_row_cg(cand_row(cf, buf), w);  // a state that leaves the layer: its occurrences leave the histogram
                     }
                 }
-                // (a node has at most one dropped candidate per decision; both may be dropped: stage them one after the other)
-                if (d == 0) {
-#pragma unroll
-                    for (int j = 0; j < S; ++j) wdrop[j] = w[j];
-                    drop_any = dropped;
-                } else {
-                    stage_rows(drop_any, wdrop, true);
-                    stage_rows(dropped, w, true);
-                }
+                if (d == 0) drop0 = dropped; else drop1 = dropped;
             }
+            stage_rows(drop0, w0, true);
+            stage_rows(drop1, w1, true);
         }
         stage_commit(e ^ 1);
         if (terminal) {
-            unsigned long long bb[2];
-            bb[0] = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
-            bb[1] = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
-            allreduce(bb, 2, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+            b_all = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
+            b_ex = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
+            push(2, b_all, b_ex); cl.sync();
+            b_all = 0; b_ex = 0;
+            for (unsigned r = 0; r < CS; ++r) { b_all = max(b_all, got(0, r)); b_ex = max(b_ex, got(1, r)); }
+            xnext();
             if (rank == 0 && tid == 0) {
-                ctl->has_best = 1; ctl->best_value = key_value(bb[0]); ctl->best_pos = (int)(uint32_t)bb[0] - 1;
-                ctl->has_best_exact = bb[1] != 0;
-                if (bb[1]) { ctl->best_exact_value = key_value(bb[1]); ctl->best_exact_pos = (int)(uint32_t)bb[1] - 1; }
+                ctl->has_best = 1; ctl->best_value = key_value(b_all); ctl->best_pos = (int)(uint32_t)b_all - 1;
+                ctl->has_best_exact = b_ex != 0;
+                if (b_ex) { ctl->best_exact_value = key_value(b_ex); ctl->best_exact_pos = (int)(uint32_t)b_ex - 1; }
             }
         }
         const bool first_cut = cut && lel < 0;
@@ -838,38 +1067,23 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 ev.lel_rub[nb + i] = ev.unit_weights ? (int)(m.w & 0xFFFFu) : __ldcg(ev.vb[buf] + nb + i);
             }
         }
-        __threadfence();
-        cl.sync();  // ---- S5: positions of every first candidate are published -----------------------------------------------------------
-        // ---- child log (relaxed DDs: edge (parent c / 2, decision) -> node of layer t+1) and release of the hash slots -------------------
-        for (int ch = warp; ch < nch; ch += DD_NW) {
-            const int i = slice_lo + 32 * ch + lane;
-            if (i < slice_hi) {
-                const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
-                const uint2 sl = *reinterpret_cast<const uint2*>(ev.cand_slot + cb + 2u * i);
-                if (sl.x != NONE32) ev.table[(size_t)k * ev.T + sl.x] = EMPTY64;
-                if (sl.y != NONE32) ev.table[(size_t)k * ev.T + sl.y] = EMPTY64;
-                if (relaxed) {
-                    uint32_t cy = NONE32, cn = NONE32;
-                    if (rp.x != NONE32) cy = __ldcg(ev.pos_of + cb + __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)));
-                    if (rp.y != NONE32) cn = __ldcg(ev.pos_of + cb + __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)));
-                    *reinterpret_cast<uint2*>(ev.clog + (lb + t) * ev.C + 2u * i) = make_uint2(cy, cn);
-                }
-            }
-        }
-        (void)ncand;
+        prof(7);
+        cl.sync();  // ---- end of the layer step: layer t+1 and the positions of its first candidates are published ---------------------------
+        prof(8);
+        n_prev = n; have_trail = true;
         if (terminal) {
+            trail(t, n, relaxed);
             if (rank == 0 && tid == 0) { ctl->status = ST_DONE; ctl->t_term = tn; ctl->n_cur = n_next; ctl->var = -1; ctl->ncand = ncand; }
+            have_trail = false;
             break;
         }
-        __threadfence();
-        cl.sync();  // ---- end of the layer step ---------------------------------------------------------------------------------------------
         t = tn; n = n_next; var = var_next;
     }
     // ---- the DD is complete -----------------------------------------------------------------------------------------------------------------
+    // (a DD that ended on an empty or overflowing layer leaves its last candidates in the tables: the host clears them before the next batch)
     __syncthreads();
-    if (tid == 0) {
-        if (fx.cnt[0]) { atomicAdd(&ctl->expanded, fx.cnt[0]); atomicAdd(&ctl->transitions, fx.cnt[1]); }
-    }
+    if (tid == 0 && fx.cnt[0]) { atomicAdd(&ctl->expanded, fx.cnt[0]); atomicAdd(&ctl->transitions, fx.cnt[1]); }
+    if (ev.dd_prof && rank == 0 && tid == 0) for (int i = 0; i < 16; ++i) atomicAdd((unsigned long long*)ev.dd_prof + i, (unsigned long long)fx.prof[i]);
     __threadfence();
     cl.sync();
     if (rank == 0 && tid == 0) {

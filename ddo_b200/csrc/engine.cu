@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 namespace ddo {
 
@@ -144,8 +145,11 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     for (int b = 0; b < 2; ++b) ALLOC(ev.nmeta[b], KW);
     ALLOC(ev.cand_hacc, KC); ALLOC(ev.cand_rub, KC);
     ALLOC(ev.dd_keys, (size_t)K * ev.C2); ALLOC(ev.dd_ulist, (size_t)K * ev.C2); ALLOC(ev.dd_stat, (size_t)K * ev.C2);
-    ALLOC(ev.dq, 8); ALLOC(ev.dq_jobs, K);
-    ALLOC(ev.table, (size_t)K * T); ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
+    ALLOC(ev.dq, 8); ALLOC(ev.dq_jobs, K); ALLOC(ev.cand_f, KC);
+    ev.dd_generic = 0; ev.dd_prof = nullptr;
+    if (const char* e = getenv("DDO_DD_PROF")) if (atoi(e)) { ALLOC(ev.dd_prof, 16); CUDA_TRY(cudaMemsetAsync(ev.dd_prof, 0, 128, stream)); }
+    if (const char* e = getenv("DDO_DD_GENERIC")) ev.dd_generic = atoi(e) != 0;
+    ALLOC(ev.table, (size_t)2 * K * T); /* k_dd alternates between two tables by layer parity */ ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
     ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
     ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
@@ -165,7 +169,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     if (cutset == DDO_FRONTIER) dual_enabled = false;  // the twin's logs start at its fork layer; the frontier sweep reads whole DDs
     if (const char* e = getenv("DDO_SMALL_WS")) { int v = atoi(e); if (v == 0 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) small_ws = v; }
     if (const char* e = getenv("DDO_SMALL_WS_FIRST")) { int v = atoi(e); if (v == 0 || v == 32 || v == 64 || v == 128) small_ws_first = v; }
-    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)K * T * 8, stream));
+    CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)2 * K * T * 8, stream));
     CUDA_TRY(cudaMemsetAsync(ev.finish_counter, 0, 16, stream));
     { int rr = reserve_roots(K); if (rr != DDO_OK) return rr; }
     CUDA_TRY(cudaMallocHost(&h_ctl, (size_t)K * sizeof(DDCtl)));
@@ -177,6 +181,16 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
 }
 
 void Engine::destroy() {
+    if (ev.dd_prof) {  // DDO_DD_PROF=1: cycles per phase of k_dd over the life of the engine
+        long long h[16];
+        if (cudaMemcpy(h, ev.dd_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const char* names[9] = {"trail", "expand", "S1 wait", "first/list", "S2 wait", "cut", "merge", "commit", "S_end wait"};
+            long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
+            fprintf(stderr, "[k_dd phases, rank 0 thread 0 cycles]");
+            for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * h[i] / tot : 0.0);
+            fprintf(stderr, " | total %.2f ms @1.9GHz\n", tot / 1.9e6);
+        }
+    }
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
     prof_events.clear();
     for (void* p : allocations) cudaFree(p);
@@ -270,8 +284,10 @@ static DDLayout dd_layout(const Engine* E, int cs) {
     L.o_stage = take((size_t)DD_NW * 32 * (2 * S + 1) * 4);
     L.o_cnt = take((size_t)L.maxch * 4); L.o_off = take((size_t)L.maxch * 4); L.o_koff = take((size_t)L.maxch * 4);
     L.o_fb = take((size_t)L.maxch * 8); L.o_kb = take((size_t)L.maxch * 8);
-    L.smem_keys = (size_t)L.capc * 13 <= 96 * 1024;
+    L.smem_keys = (size_t)L.capc * 13 <= 64 * 1024 && o + (size_t)L.capc * 13 + 80 * 1024 <= 190 * 1024;
     if (L.smem_keys) { L.o_keys = take((size_t)L.capc * 8); L.o_ulist = take((size_t)L.capc * 4); L.o_stat = take((size_t)L.capc); }
+    L.o_lh = take((size_t)DD_NB * 4); L.o_gh = take((size_t)DD_NB * 4);
+    L.o_garr = take((size_t)DD_GCAP * 8); L.o_gkeys = take((size_t)DD_GCAP * 8); L.o_gstat = take((size_t)DD_GCAP); L.o_und = take((size_t)DD_GCAP * 4);
     L.total = o;
     return L;
 }
@@ -291,6 +307,7 @@ static int run_dd(Engine* E, int count, int slots, int comp_type, int64_t best_l
     if (E->dd_cs > 0) cs = E->dd_cs;
     else { for (int c = 8; c >= 1; c >>= 1) if (slots * c <= E->num_sms) { cs = c; break; } }
     const DDLayout L = dd_layout(E, cs);
+    if (L.total > 200 * 1024) { set_error("k_dd: shared-memory layout does not fit"); return DDO_ERR_UNSUPPORTED; }
     int nclusters = std::min(slots, std::max(1, E->num_sms / cs));
     k_dd_init<<<(slots + 127) / 128, 128, 0, st>>>(ev, count, comp_type, (long long)best_lb, dual);
     E->prof_mark(-1);
@@ -398,6 +415,7 @@ static int compile_impl(Engine* E, int count, int slots, int comp_type, int64_t 
     const EV& ev = E->ev;
     CUDA_TRY(cudaSetDevice(E->device));
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)slots * E->T * 8, E->stream));
+    if (E->dd_enabled && E->model) CUDA_TRY(cudaMemsetAsync(ev.table + (size_t)E->K * E->T, 0xFF, (size_t)slots * E->T * 8, E->stream));
     CUDA_TRY(cudaMemsetAsync(ev.vhist, 0, (size_t)slots * 64 * E->S * 4, E->stream));
     CUDA_TRY(cudaMemsetAsync(ev.ucount, 0, (size_t)slots * 4, E->stream));
     CUDA_TRY(cudaEventRecord(E->ev0, E->stream));

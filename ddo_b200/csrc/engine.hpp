@@ -98,6 +98,9 @@ struct EV {
     uint4* nmeta[2]; unsigned long long* cand_hacc; int32_t* cand_rub;
     unsigned long long* dd_keys; uint32_t* dd_ulist; uint8_t* dd_stat; int C2;
     int* dq; int* dq_jobs;
+    uint32_t* cand_f;   // [K][C] first candidate of every candidate's state (NONE32: no child), for the deferred child log
+    long long* dd_prof; // [16] cycles per phase of k_dd (rank 0 / thread 0), DDO_DD_PROF=1 only
+    int dd_generic;     // force the generic cluster-wide radix select of the width cut (DDO_DD_GENERIC=1, tests)
 };
 constexpr int FC_POS_BITS = 21;
 
