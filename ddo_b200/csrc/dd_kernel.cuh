@@ -17,6 +17,12 @@
 // occurrence counts behind `next_variable` are maintained INCREMENTALLY (rows that leave the layer are subtracted, rows that enter are
 // added) instead of being recounted over every distinct state of every layer.
 //
+// Everything a layer step decides from lives in SHARED memory, distributed over the CTAs of the cluster: the node records of the two
+// layer buffers (hash accumulator, value_top, popcount, flags) and the candidate records (value_top / best parent, first candidate,
+// exactness, claimer-or-slot word, position) belong to the CTA that owns the node; a duplicate found in another CTA's slice is merged by
+// remote atomics on that CTA's shared memory (atom.shared::cluster).  Only the state rows, the dedup table and the logs stay in global
+// memory (L2-resident), so the dependent chain of a phase is one L2 round trip per row instead of one per record.
+//
 // Synchronisation budget of a layer (cluster barriers): 3 without a width cut (candidates inserted / counts exchanged / layer committed),
 // 6-7 with one.  Everything exchanged between the CTAs of a cluster is PUSHED into the peers' shared memory before a barrier (remote
 // stores / remote atomics, fire and forget) and read locally after it -- a pulled value costs a ~215-cycle DSMEM round trip per peer.  The
@@ -37,11 +43,13 @@ constexpr uint32_t DD_CMASK = DD_IDENT - 1u;
 constexpr int DD_NB = 2048;                      // bins of the dense (value_top, popcount) histogram of the width cut
 constexpr int DD_GCAP = 2048;                    // boundary-bucket candidates rank 0 can resolve alone
 constexpr int DD_MAXCS = 16;
+constexpr uint32_t RS_CLAIM = 1u << 31;          // claimer-or-slot word of a candidate: NONE32 | RS_CLAIM | ident | hash slot | ident | claimer
 
 // byte offsets into the dynamic shared memory of a CTA (computed on the host, dd_layout())
 struct DDLayout {
-    int slice, maxch, capc, smem_keys;  // nodes of a layer per CTA, 32-node chunks per CTA, candidates per CTA, keys / lists in shared memory ?
-    unsigned o_D, o_master, o_stage, o_cnt, o_off, o_koff, o_fb, o_kb, o_keys, o_ulist, o_stat, o_lh, o_gh, o_garr, o_gkeys, o_gstat, o_und, total;
+    int slice, maxch, capc, weighted;  // nodes of a layer per CTA, 32-node chunks per CTA, candidates per CTA, weighted instance (rough upper bounds kept)
+    unsigned o_D, o_master, o_stage, o_cnt, o_off, o_koff, o_fb, o_kb, o_keys, o_ulist, o_stat, o_lh, o_gh;
+    unsigned o_agg, o_first, o_rs, o_f, o_pos, o_inex, o_pcy, o_nm, o_rub, total;
 };
 
 struct DDFixed {
@@ -138,6 +146,10 @@ struct DDC {
     int* D[2]; unsigned int* master; uint32_t* stage; int* cnt_s; int* off_s; int* koff_s; uint2* fb_s; uint2* kb_s;
     unsigned long long* keys; uint32_t* ulist; uint8_t* stat;
     unsigned int* lh; unsigned int* gh; unsigned long long* garr; unsigned long long* gkeys; uint8_t* gstat; uint32_t* und;
+    // records of this CTA's slice: candidates [cbase, cbase + capc), nodes [node0, node0 + slice)
+    uint32_t* s_val32; uint32_t* s_bp; uint32_t* s_first; uint32_t* s_rs; uint32_t* s_f; uint32_t* s_pos; uint8_t* s_inex; uint16_t* s_pcy;
+    uint4* s_nm[2]; int32_t* s_rub[2];
+    unsigned cbase; int node0;
     // the DD
     int k, rk; size_t cb, lb, nb; DDCtl* ctl;
     int comp, W; long long best_lb;
@@ -153,12 +165,46 @@ struct DDC {
         stage = reinterpret_cast<uint32_t*>(dsm + L.o_stage) + (size_t)warp * 32 * SROW;
         cnt_s = reinterpret_cast<int*>(dsm + L.o_cnt); off_s = reinterpret_cast<int*>(dsm + L.o_off); koff_s = reinterpret_cast<int*>(dsm + L.o_koff);
         fb_s = reinterpret_cast<uint2*>(dsm + L.o_fb); kb_s = reinterpret_cast<uint2*>(dsm + L.o_kb);
+        keys = reinterpret_cast<unsigned long long*>(dsm + L.o_keys); ulist = reinterpret_cast<uint32_t*>(dsm + L.o_ulist); stat = dsm + L.o_stat;
         lh = reinterpret_cast<unsigned int*>(dsm + L.o_lh); gh = reinterpret_cast<unsigned int*>(dsm + L.o_gh);
-        garr = reinterpret_cast<unsigned long long*>(dsm + L.o_garr); gkeys = reinterpret_cast<unsigned long long*>(dsm + L.o_gkeys);
-        gstat = dsm + L.o_gstat; und = reinterpret_cast<uint32_t*>(dsm + L.o_und);
+        // scratch of the boundary-bucket resolution, aliased with regions that are idle during the width cut: the gathered list (rank 0)
+        // over the staging buffers (empty between the expansion and the commit), its keys over the cut keys, the undecided list over lh
+        garr = reinterpret_cast<unsigned long long*>(dsm + L.o_stage); gstat = dsm + L.o_stage + (size_t)DD_GCAP * 8;
+        gkeys = keys; und = lh;
+        s_val32 = reinterpret_cast<uint32_t*>(dsm + L.o_agg); s_bp = s_val32 + L.capc; s_first = reinterpret_cast<uint32_t*>(dsm + L.o_first);
+        s_rs = reinterpret_cast<uint32_t*>(dsm + L.o_rs); s_f = reinterpret_cast<uint32_t*>(dsm + L.o_f); s_pos = reinterpret_cast<uint32_t*>(dsm + L.o_pos);
+        s_inex = dsm + L.o_inex; s_pcy = reinterpret_cast<uint16_t*>(dsm + L.o_pcy);
+        s_nm[0] = reinterpret_cast<uint4*>(dsm + L.o_nm); s_nm[1] = s_nm[0] + L.slice;
+        s_rub[0] = reinterpret_cast<int32_t*>(dsm + L.o_rub); s_rub[1] = s_rub[0] + L.slice;
+        cbase = rank * (unsigned)L.capc; node0 = (int)rank * L.slice;
     }
 
-    // ---- cluster exchange of up to 8 block-uniform values: pushed into every peer, read locally after the barrier ---------------------
+    // ---- records of ANY candidate / node of the DD: the owner's shared memory (local or remote through DSMEM) --------------------------
+    template <class T> __device__ __forceinline__ T* cptr(T* arr, uint32_t c) const {
+        const unsigned o = (c >> 1) / (unsigned)L.slice;
+        T* p = arr + (c - o * (unsigned)L.capc);
+        return o == rank ? p : cl.map_shared_rank(p, o);
+    }
+    template <class T> __device__ __forceinline__ T* nptr(T* arr, int i) const {
+        const unsigned o = (unsigned)i / (unsigned)L.slice;
+        T* p = arr + (i - (int)o * L.slice);
+        return o == rank ? p : cl.map_shared_rank(p, o);
+    }
+    // (biased value_top << 32 | best parent candidate) of claimer `rep`.  The two halves are separate 32-bit words updated by NATIVE 32-bit
+    // atomics: a 64-bit atomic on shared memory is a lock-based CAS loop (ATOMS.CAST.SPIN) that atomics arriving from other CTAs of the
+    // cluster do not respect -- measured as lost value_top updates.  value_top = max is taken while the candidates are inserted, the best
+    // parent (largest candidate among those reaching the final value: `>=`, last tie wins, clean.rs:215) one phase later.
+    __device__ __forceinline__ unsigned long long agg_of(uint32_t rep) const { return ((unsigned long long)*cptr(s_val32, rep) << 32) | *cptr(s_bp, rep); }
+    __device__ __forceinline__ static uint32_t vbias(int v) { return (uint32_t)v ^ 0x80000000u; }
+    // claimer (= the candidate that holds value_top / exactness of the state) of candidate c, from its claimer-or-slot word
+    __device__ __forceinline__ static uint32_t rep_of(uint32_t c, uint32_t rs) { return (rs & RS_CLAIM) ? c : (rs & DD_CMASK); }
+
+    __device__ __forceinline__ void csync() {
+        if (ev.dd_dbg & 4) { __threadfence(); fence_cluster(); __syncthreads(); }
+        cl.sync();
+        if (ev.dd_dbg & 4) { fence_cluster(); __syncthreads(); }
+    }
+    // ---- cluster exchange of up to 6 block-uniform values: pushed into every peer, read locally after the barrier ---------------------
     __device__ __forceinline__ void push(int nvals, unsigned long long v0, unsigned long long v1 = 0, unsigned long long v2 = 0, unsigned long long v3 = 0,
                                          unsigned long long v4 = 0, unsigned long long v5 = 0) {
         if (tid < nvals * (int)CS) {
@@ -170,13 +216,13 @@ struct DDC {
     __device__ __forceinline__ unsigned long long got(int slot, unsigned r) const { return fx.xch[xphase][slot][r]; }
     __device__ __forceinline__ void xnext() { xphase ^= 1; }
     template <class Op> __device__ unsigned long long allreduce1(unsigned long long v, Op op) {
-        push(1, v); cl.sync();
+        push(1, v); csync();
         unsigned long long acc = got(0, 0);
         for (unsigned r = 1; r < CS; ++r) acc = op(acc, got(0, r));
         xnext();
         return acc;
     }
-    // sum over the block of 4 ints per thread (results broadcast)
+    // sum / max over the block of 4 ints per thread (results broadcast)
     __device__ void block_sum4(int (&v)[4]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = warp_reduce(v[q], [](int a, int b) { return a + b; });
@@ -221,18 +267,17 @@ struct DDC {
     }
 
     // ---- histogram staging: rows that enter (+) or leave (-) the set of distinct states are buffered per warp and bit-transposed 32 at a
-    // time into per-lane counters (lane b of column j counts vertex 32 j + b); flushed into D[e] once per phase
+    // time into per-lane counters (lane b of column j counts vertex 32 j + b): ONE transpose serves both signs (after it, bit r of a lane's
+    // word belongs to staged row r, and st_minus marks the rows that leave).  Flushed into D[e] at the end of an expansion.
     __device__ void stage_flush() {
         if (st_cnt == 0) return;
         __syncwarp();
         const bool mine = lane < st_cnt;
-        const bool minus = (st_minus >> lane) & 1u;
-        const unsigned any_plus = __ballot_sync(FULL_MASK, mine && !minus), any_minus = __ballot_sync(FULL_MASK, mine && minus);
+        const unsigned minus = st_minus;
 #pragma unroll
         for (int j = 0; j < W32; ++j) {
-            const uint32_t x = mine ? stage[lane * SROW + j] : 0u;
-            if (any_plus) hcnt[j] += __popc(warp_transpose32(minus ? 0u : x));
-            if (any_minus) hcnt[j] -= __popc(warp_transpose32(minus ? x : 0u));
+            const uint32_t tr = warp_transpose32(mine ? stage[lane * SROW + j] : 0u);
+            hcnt[j] += __popc(tr & ~minus) - __popc(tr & minus);
         }
         __syncwarp();
         st_cnt = 0; st_minus = 0;
@@ -251,17 +296,16 @@ struct DDC {
         if (minus) st_minus |= (add == 32 ? 0xFFFFFFFFu : ((1u << add) - 1u)) << st_cnt;
         st_cnt += add;
     }
-    __device__ void stage_commit(int e) {  // end of a phase: counters of this lane -> D[e]
+    __device__ void stage_commit(int e) {  // end of an expansion: counters of this lane -> D[e]
         stage_flush();
 #pragma unroll
         for (int j = 0; j < W32; ++j) if (hcnt[j]) { atomicAdd(&D[e][32 * j + lane], hcnt[j]); hcnt[j] = 0; }
     }
 
     // ---- open-addressing insert (next_l.entry(), clean.rs:738-775 + append_edge_to! :199-220) ---------------------------------------
-    // returns true when candidate c claimed a slot (a new distinct state); rep = claimer of the state
+    // returns the claimer-or-slot word of candidate c: RS_CLAIM | slot when it claimed a slot (a new distinct state), else the claimer
     template <class RowFn>
-    __device__ __forceinline__ bool insert(unsigned long long* tab, uint64_t hacc, uint32_t c, uint32_t ident, int value, uint32_t fl, int buf, RowFn my_row, uint32_t& rep,
-                                           uint32_t& slot_out) {
+    __device__ __forceinline__ uint32_t insert(unsigned long long* tab, uint64_t hacc, uint32_t c, uint32_t ident, int value, uint32_t fl, int buf, RowFn my_row) {
         const uint64_t h = dd_hfin(hacc);
         const uint32_t tag = (uint32_t)(h >> 32);
         const unsigned long long entry = ((unsigned long long)tag << 32) | c | ident;
@@ -269,7 +313,7 @@ struct DDC {
         uint64_t w[S]; bool loaded = false;
         for (;;) {
             const unsigned long long old = atomicCAS(tab + slot, EMPTY64, entry);
-            if (old == EMPTY64) { rep = c; slot_out = slot; return true; }
+            if (old == EMPTY64) return RS_CLAIM | ident | slot;
             if ((uint32_t)(old >> 32) == tag) {
                 if (!loaded) { my_row(w); loaded = true; }
                 const uint32_t oe = (uint32_t)old;
@@ -279,11 +323,10 @@ struct DDC {
                 for (int q = 0; q < S / 2; ++q) { const uint4 o4 = ld_cg_u4(orow + q); eq = eq && u4lo(o4) == w[2 * q] && u4hi(o4) == w[2 * q + 1]; }
                 if (eq) {
                     const uint32_t oc = oe & DD_CMASK;
-                    atomicMax(ev.cand_agg + cb + oc, pack_key(value, c));   // value_top = max, `>=`: the last (largest) candidate wins ties
-                    atomicMin(ev.cand_first + cb + oc, c);                    // canonical identity = first candidate (rule C1)
-                    if (fl & NF_INEXACT) ev.cand_inex[cb + oc] = 1;           // exact &= parent.exact
-                    rep = oc; slot_out = NONE32;
-                    return false;
+                    atomicMax(cptr(s_val32, oc), vbias(value));                 // value_top = max
+                    atomicMin(cptr(s_first, oc), c);                            // canonical identity = first candidate (rule C1)
+                    if (fl & NF_INEXACT) *cptr(s_inex, oc) = 1;                 // exact &= parent.exact
+                    return ident | oc;
                 }
             }
             slot = (slot + 1) & (uint32_t)(ev.T - 1);
@@ -291,24 +334,23 @@ struct DDC {
     }
 
     // ---- child log of the PREVIOUS layer step (relaxed DDs: edge (parent c / 2, decision) -> node of the layer committed last) and release
-    // of the hash slots its candidates claimed; runs at the start of the next step, off the critical path (the table, the positions and the
-    // first-candidate links are double-buffered by layer parity)
+    // of the hash slots its candidates claimed; runs at the start of the next step, off the critical path (the tables alternate by layer parity)
     __device__ void trail(int tp, int n_prev, bool relaxed) {
-        const int slice_lo = min((int)rank * L.slice, n_prev), slice_hi = min(slice_lo + L.slice, n_prev);
+        const int slice_lo = min(node0, n_prev), slice_hi = min(slice_lo + L.slice, n_prev);
         const int nch = (slice_hi - slice_lo + 31) >> 5;
         unsigned long long* tab = tabs[tp & 1];
-        const uint32_t* pos = (tp & 1) ? ev.ulist : ev.pos_of;  // positions of layer tp + 1, written by its commit
         for (int ch = warp; ch < nch; ch += DD_NW) {
             const int i = slice_lo + 32 * ch + lane;
             if (i < slice_hi) {
-                const uint2 sl = *reinterpret_cast<const uint2*>(ev.cand_slot + cb + 2u * i);
-                if (sl.x != NONE32) tab[sl.x] = EMPTY64;
-                if (sl.y != NONE32) tab[sl.y] = EMPTY64;
+                const unsigned lc = 2u * (unsigned)(i - node0);
+                const uint2 rs = *reinterpret_cast<const uint2*>(s_rs + lc);
+                if (rs.x != NONE32 && (rs.x & RS_CLAIM)) tab[rs.x & DD_CMASK] = EMPTY64;
+                if (rs.y != NONE32 && (rs.y & RS_CLAIM)) tab[rs.y & DD_CMASK] = EMPTY64;
                 if (relaxed) {
-                    const uint2 f = *reinterpret_cast<const uint2*>(ev.cand_f + cb + 2u * i);
+                    const uint2 f = *reinterpret_cast<const uint2*>(s_f + lc);
                     uint32_t cy = NONE32, cn = NONE32;
-                    if (f.x != NONE32) cy = __ldcg(pos + cb + f.x);
-                    if (f.y != NONE32) cn = __ldcg(pos + cb + f.y);
+                    if (f.x != NONE32) cy = *cptr(s_pos, f.x);
+                    if (f.y != NONE32) cn = *cptr(s_pos, f.y);
                     *reinterpret_cast<uint2*>(ev.clog + (lb + tp) * ev.C + 2u * i) = make_uint2(cy, cn);
                 }
             }
@@ -319,12 +361,12 @@ struct DDC {
     __device__ void expand(int t, int n, int var) {
         const int buf = t & 1, e = t & 1;
         unsigned long long* tab = tabs[t & 1];
-        const int slice_lo = min((int)rank * L.slice, n), slice_hi = min(slice_lo + L.slice, n);
+        const int slice_lo = min(node0, n), slice_hi = min(slice_lo + L.slice, n);
         const int nch = (slice_hi - slice_lo + 31) >> 5;
         const int vw = var >> 6;
         const uint64_t bit = 1ull << (var & 63);
         const int wv = ev.weight[var];
-        const uint64_t hdelta = (uint64_t)(1u << (var & 31)) * (uint64_t)dd_mul32(var >> 5);
+        const uint64_t hdelta = (uint64_t)(1u << (var & 31)) * (uint64_t)dd_mul32(var >> 5);  // hash accumulator of the branching vertex's bit
         uint64_t ncr[S];  // complement-adjacency row of the branching vertex (misp/main.rs:82), once per thread and layer
         {
             const uint4* q = reinterpret_cast<const uint4*>(ev.nc + (size_t)var * S);
@@ -336,15 +378,18 @@ struct DDC {
             const int i = slice_lo + 32 * ch + lane;
             const bool active = i < slice_hi;
             uint64_t w[S];
-            uint32_t rep_y = NONE32, rep_n = NONE32, slot_y = NONE32, slot_n = NONE32;
+            uint32_t rs_y = NONE32, rs_n = NONE32;
             bool minus_parent = false, plus_yes = false;
             uint64_t wy[S];
             if (active) {
-                const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i);
+                const int il = i - node0;
+                const unsigned lc = 2u * (unsigned)il;
+                const uint4 m = s_nm[buf][il];
                 const uint64_t hacc = (uint64_t)m.x | ((uint64_t)m.y << 32);
                 const int val = (int)m.z, pc = (int)(m.w & 0xFFFFu);
                 const uint32_t fl = m.w >> 16;
-                const int rub = ev.unit_weights ? pc : __ldcg(ev.vb[buf] + nb + i);
+                if (ev.dd_dbgbuf) { atomicAdd(ev.dd_dbgbuf + 4 * ev.Lmax + 4 * t, val); atomicAdd(ev.dd_dbgbuf + 4 * ev.Lmax + 4 * t + 1, pc); atomicAdd(ev.dd_dbgbuf + 4 * ev.Lmax + 4 * t + 2, (int)fl); atomicAdd(ev.dd_dbgbuf + 4 * ev.Lmax + 4 * t + 3, (int)(hacc & 0xFFFF)); }
+                const int rub = ev.unit_weights ? pc : s_rub[buf][il];
                 const bool expandable = ((long long)rub + (long long)val) > best_lb;  // clean.rs:364-365
                 const uint64_t* prow = ev.cur_state[buf] + (nb + i) * S;
                 if (!expandable) {
@@ -355,13 +400,12 @@ struct DDC {
                     const uint32_t c_yes = 2u * i, c_no = 2u * i + 1u;  // for_each_in_domain order: YES then NO (main.rs:95-102)
                     if (!has_v) {
                         // identity candidate: the child IS the parent's state (value, exactness, hash, popcount carried over)
-                        ev.cand_agg[cb + c_no] = pack_key(val, c_no);
-                        ev.cand_first[cb + c_no] = c_no;
-                        ev.cand_inex[cb + c_no] = (uint8_t)(fl & NF_INEXACT);
+                        s_val32[lc + 1] = vbias(val); s_bp[lc + 1] = 0;
+                        s_first[lc + 1] = c_no;
+                        s_inex[lc + 1] = (uint8_t)(fl & NF_INEXACT);
                         fence_cluster();
-                        const bool claimed = insert(tab, hacc, c_no, DD_IDENT, val, fl, buf, [&](uint64_t (&r)[S]) { load_row_cg(prow, r); }, rep_n, slot_n);
-                        rep_n |= DD_IDENT;
-                        if (!claimed) { load_row_cg(prow, w); minus_parent = true; }  // its state is already counted through the claimer
+                        rs_n = insert(tab, hacc, c_no, DD_IDENT, val, fl, buf, [&](uint64_t (&r)[S]) { load_row_cg(prow, r); });
+                        if (!(rs_n & RS_CLAIM)) { load_row_cg(prow, w); minus_parent = true; }  // its state is already counted through the claimer
                     } else {
                         load_row_cg(prow, w);
 #pragma unroll
@@ -373,27 +417,25 @@ struct DDC {
                         store_row(ev.cand_state + (cb + c_yes) * S, wy);
                         store_row(ev.cand_state + (cb + c_no) * S, w);
                         const int valy = val + wv;  // main.rs:87-93
-                        ev.cand_agg[cb + c_yes] = pack_key(valy, c_yes); ev.cand_agg[cb + c_no] = pack_key(val, c_no);
-                        *reinterpret_cast<uint2*>(ev.cand_first + cb + c_yes) = make_uint2(c_yes, c_no);
-                        *reinterpret_cast<uchar2*>(ev.cand_inex + cb + c_yes) = make_uchar2((uint8_t)(fl & NF_INEXACT), (uint8_t)(fl & NF_INEXACT));
-                        *reinterpret_cast<uint2*>(ev.cand_rank + cb + c_yes) = make_uint2((uint32_t)pcy, (uint32_t)(pc - 1));
-                        ev.cand_hacc[cb + c_yes] = hy; ev.cand_hacc[cb + c_no] = hn;
-                        if (!ev.unit_weights) { ev.cand_rub[cb + c_yes] = row_rub(wy, pcy); ev.cand_rub[cb + c_no] = rub - wv; }
+                        *reinterpret_cast<uint2*>(s_val32 + lc) = make_uint2(vbias(valy), vbias(val)); *reinterpret_cast<uint2*>(s_bp + lc) = make_uint2(0u, 0u);
+                        *reinterpret_cast<uint2*>(s_first + lc) = make_uint2(c_yes, c_no);
+                        *reinterpret_cast<uchar2*>(s_inex + lc) = make_uchar2((uint8_t)(fl & NF_INEXACT), (uint8_t)(fl & NF_INEXACT));
+                        s_pcy[il] = (uint16_t)pcy;
                         fence_cluster();
-                        plus_yes = insert(tab, hy, c_yes, 0u, valy, fl, buf, [&](uint64_t (&r)[S]) {
+                        rs_y = insert(tab, hy, c_yes, 0u, valy, fl, buf, [&](uint64_t (&r)[S]) {
 #pragma unroll
-                            for (int j = 0; j < S; ++j) r[j] = wy[j]; }, rep_y, slot_y);
-                        const bool claimed_n = insert(tab, hn, c_no, 0u, val, fl, buf, [&](uint64_t (&r)[S]) {
+                            for (int j = 0; j < S; ++j) r[j] = wy[j]; });
+                        rs_n = insert(tab, hn, c_no, 0u, val, fl, buf, [&](uint64_t (&r)[S]) {
 #pragma unroll
-                            for (int j = 0; j < S; ++j) r[j] = w[j]; }, rep_n, slot_n);
-                        if (claimed_n) ++no_claims;  // parent row out, NO row in: only the branching vertex loses an occurrence
-                        else { minus_parent = true; }
+                            for (int j = 0; j < S; ++j) r[j] = w[j]; });
+                        plus_yes = (rs_y & RS_CLAIM) != 0;
+                        if (rs_n & RS_CLAIM) ++no_claims;  // parent row out, NO row in: only the branching vertex loses an occurrence
+                        else minus_parent = true;
 #pragma unroll
                         for (int j = 0; j < S; ++j) if (j == vw) w[j] |= bit;  // back to the parent's row for the histogram
                     }
                 }
-                *reinterpret_cast<uint2*>(ev.cand_rep + cb + 2u * i) = make_uint2(rep_y, rep_n);
-                *reinterpret_cast<uint2*>(ev.cand_slot + cb + 2u * i) = make_uint2(slot_y, slot_n);
+                *reinterpret_cast<uint2*>(s_rs + lc) = make_uint2(rs_y, rs_n);
             }
             stage_rows(minus_parent, w, true);
             stage_rows(plus_yes, wy, false);
@@ -409,18 +451,24 @@ struct DDC {
         }
     }
 
+    // popcount / claimer of ANY candidate of the layer being built (with its DD_IDENT flag)
+    __device__ int cand_pc(uint32_t cf, int buf) const {
+        const uint32_t c = cf & DD_CMASK;
+        const int i = (int)(c >> 1);
+        if (!(cf & DD_IDENT) && !(c & 1u)) return (int)*nptr(s_pcy, i);
+        const int pc = (int)(nptr(s_nm[buf], i)->w & 0xFFFFu);
+        return (cf & DD_IDENT) ? pc : pc - 1;
+    }
+    __device__ uint32_t cand_rep(uint32_t cf) const { const uint32_t c = cf & DD_CMASK; return rep_of(c, *cptr(s_rs, c)); }
     // compare two distinct candidates (with their DD_IDENT flags) by the cut order (clean.rs:803-808 + misp/main.rs:205-208)
-    __device__ bool better(uint32_t a, uint32_t b, uint32_t rep_a, uint32_t rep_b, int pca, int pcb, int buf) const {
-        const int va = key_value(__ldcg(ev.cand_agg + cb + rep_a)), vb2 = key_value(__ldcg(ev.cand_agg + cb + rep_b));
+    __device__ bool better(uint32_t a, uint32_t b, int buf) const {
+        const int va = key_value(agg_of(cand_rep(a))), vb2 = key_value(agg_of(cand_rep(b)));
         if (va != vb2) return va > vb2;
+        const int pca = cand_pc(a, buf), pcb = cand_pc(b, buf);
         if (pca != pcb) return pca > pcb;
         const uint64_t* ra = cand_row(a, buf); const uint64_t* rb = cand_row(b, buf);
         for (int j = 0; j < S; ++j) { const uint64_t xa = lex_word(__ldcg(ra + j)), xb = lex_word(__ldcg(rb + j)); if (xa != xb) return xa > xb; }
         return false;
-    }
-    __device__ __forceinline__ int cand_pc(uint32_t cf, int buf) const {
-        const uint32_t c = cf & DD_CMASK;
-        return (cf & DD_IDENT) ? (int)(ld_cg_u4(ev.nmeta[buf] + nb + (c >> 1)).w & 0xFFFFu) : (int)__ldcg(ev.cand_rank + cb + c);
     }
 
     // ---- MSD radix select of the `need` best among the undecided (st == 0) entries of kk / st / list[0 .. n): 1 = keep, 2 = drop.
@@ -445,7 +493,7 @@ struct DDC {
             k0 = block_reduce(k0, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
             k1 = block_reduce(k1, [](unsigned long long a, unsigned long long b) { return a | b; }, 0ull, fx.red64);
             if (CLUSTER) {
-                push(2, k0, k1); cl.sync();
+                push(2, k0, k1); csync();
                 k0 = 0; k1 = 0;
                 for (unsigned r = 0; r < CS; ++r) { k0 |= got(0, r); k1 |= got(1, r); }
                 xnext();
@@ -458,7 +506,7 @@ struct DDC {
                 __syncthreads();
                 for (int li = tid; li < n; li += DD_NT) if (st[li] == 0) atomicAdd(&h[(kk[li] >> (8 * byte)) & 0xff], 1u);
                 if (CLUSTER) {
-                    cl.sync();
+                    csync();
                     for (int i = tid; i < 256; i += DD_NT) {
                         unsigned int a = 0;
                         for (unsigned r = 0; r < CS; ++r) a += *cl.map_shared_rank(&h[i], r);
@@ -517,12 +565,6 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
     comp = ctl->comp_type; W = ctl->width; best_lb = ctl->best_lb;
     tabs[0] = ev.table + (size_t)k * ev.T; tabs[1] = ev.table + ((size_t)ev.K + k) * ev.T;
     const bool relaxed = comp == DDO_RELAXED;
-    if (L.smem_keys) {
-        keys = reinterpret_cast<unsigned long long*>(dsm + L.o_keys); ulist = reinterpret_cast<uint32_t*>(dsm + L.o_ulist); stat = dsm + L.o_stat;
-    } else {
-        const size_t sb = (size_t)k * ev.C2 + (size_t)rank * L.capc;
-        keys = ev.dd_keys + sb; ulist = ev.dd_ulist + sb; stat = ev.dd_stat + sb;
-    }
 #pragma unroll
     for (int j = 0; j < W32; ++j) hcnt[j] = 0;
     st_cnt = 0; st_minus = 0;
@@ -539,18 +581,16 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
         master[u] = c;
         if (c) best = min(best, ((unsigned long long)c << 32) | (unsigned)u);
     }
-    if (rank == 0 && tid < 32) {
+    if (rank == 0 && tid == 0) {
         uint64_t w[S]; int pc = 0;
 #pragma unroll
         for (int j = 0; j < S; ++j) { w[j] = ev.root_state[(size_t)rk * S + j]; pc += __popcll(w[j]); }
-        if (tid == 0) {
-            store_row(ev.cur_state[0] + nb * S, w);
-            const uint64_t ha = dd_hacc<S>(w);
-            ev.nmeta[0][nb] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)ctl->root_value, (uint32_t)pc);
-            if (!ev.unit_weights) ev.vb[0][nb] = row_rub(w, pc);
-            ev.plog[lb * ev.Wcap] = PLOG_CAND_MASK;
-            ev.nlog[lb] = 1; ev.rslog[lb * 2] = -1; ev.rslog[lb * 2 + 1] = -1;
-        }
+        store_row(ev.cur_state[0] + nb * S, w);
+        const uint64_t ha = dd_hacc<S>(w);
+        s_nm[0][0] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)ctl->root_value, (uint32_t)pc);
+        if (L.weighted) s_rub[0][0] = row_rub(w, pc);
+        ev.plog[lb * ev.Wcap] = PLOG_CAND_MASK;
+        ev.nlog[lb] = 1; ev.rslog[lb * 2] = -1; ev.rslog[lb * 2 + 1] = -1;
     }
     best = block_reduce(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; }, ~0ull, fx.red64);
     best = allreduce1(best, [](unsigned long long a, unsigned long long b) { return a < b ? a : b; });
@@ -565,19 +605,18 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             ctl->status = ST_DONE; ctl->t_term = 0; ctl->n_cur = 1; ctl->var = -1; ctl->ncand = 1;
         }
     }
-    cl.sync();
+    csync();
 
     if (ev.dd_prof && rank == 0 && tid == 0) { for (int i = 0; i < 16; ++i) fx.prof[i] = 0; fx.prof_t = clock64(); }
     while (var >= 0) {
         const int buf = t & 1, nbuf = buf ^ 1, e = t & 1;
-        uint32_t* pos_w = (t & 1) ? ev.ulist : ev.pos_of;  // positions of the first candidates of this step (read by the next step's trail)
         // D[e ^ 1] was last read by the peers two barriers ago: clear it for the next epoch
         for (int i = tid; i < ev.HN; i += DD_NT) D[e ^ 1][i] = 0;
         if (have_trail) trail(t - 1, n_prev, relaxed);
         prof(0);
         expand(t, n, var);
         prof(1);
-        cl.sync();  // ---- S1: every candidate of layer t+1 is inserted ------------------------------------------------------------
+        csync();  // ---- S1: every candidate of layer t+1 is inserted ------------------------------------------------------------
         prof(2);
 
         // ---- next_variable (misp/main.rs:109-143): occurrence counts of the distinct states of layer t+1, argmin, lowest index on ties.
@@ -596,17 +635,36 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
         }
         // ---- first candidates (rule C1): candidate c represents its state iff it is the smallest candidate that produced it -----------
         const int ncand = 2 * n;
-        const int slice_lo = min((int)rank * L.slice, n), slice_hi = min(slice_lo + L.slice, n);
+        const int slice_lo = min(node0, n), slice_hi = min(slice_lo + L.slice, n);
         const int nch = (slice_hi - slice_lo + 31) >> 5;
+        const int wv_t = ev.weight[var];
         for (int ch = warp; ch < nch; ch += DD_NW) {
             const int i = slice_lo + 32 * ch + lane;
             bool fy = false, fn = false;
             if (i < slice_hi) {
-                const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+                const unsigned lc = 2u * (unsigned)(i - node0);
+                const uint2 rs = *reinterpret_cast<const uint2*>(s_rs + lc);
                 uint32_t f0 = NONE32, f1 = NONE32;
-                if (rp.x != NONE32) { f0 = __ldcg(ev.cand_first + cb + (rp.x & DD_CMASK)); fy = f0 == 2u * i; }
-                if (rp.y != NONE32) { f1 = __ldcg(ev.cand_first + cb + (rp.y & DD_CMASK)); fn = f1 == 2u * i + 1u; }
-                *reinterpret_cast<uint2*>(ev.cand_f + cb + 2u * i) = make_uint2(f0, f1);
+                const int pval = (int)s_nm[buf][i - node0].z;
+                if (rs.x != NONE32) {
+                    const uint32_t rep = rep_of(2u * i, rs.x);
+                    f0 = *cptr(s_first, rep); fy = f0 == 2u * i;
+                    if (*cptr(s_val32, rep) == vbias(pval + wv_t)) atomicMax(cptr(s_bp, rep), 2u * i);       // a best parent of its state
+                }
+                if (rs.y != NONE32) {
+                    const uint32_t rep = rep_of(2u * i + 1u, rs.y);
+                    f1 = *cptr(s_first, rep); fn = f1 == 2u * i + 1u;
+                    if (*cptr(s_val32, rep) == vbias(pval)) atomicMax(cptr(s_bp, rep), 2u * i + 1u);
+                }
+                *reinterpret_cast<uint2*>(s_f + lc) = make_uint2(f0, f1);
+                if (ev.dd_dbgbuf) {
+                    const int ncl = ((rs.x != NONE32 && (rs.x & RS_CLAIM)) ? 1 : 0) + ((rs.y != NONE32 && (rs.y & RS_CLAIM)) ? 1 : 0);
+                    const int ncd = (rs.x != NONE32 ? 1 : 0) + (rs.y != NONE32 ? 1 : 0);
+                    if (ncl) atomicAdd(ev.dd_dbgbuf + 4 * t, ncl);
+                    if (fy || fn) atomicAdd(ev.dd_dbgbuf + 4 * t + 1, (fy ? 1 : 0) + (fn ? 1 : 0));
+                    if (ncd) atomicAdd(ev.dd_dbgbuf + 4 * t + 2, ncd);
+                    atomicAdd(ev.dd_dbgbuf + 4 * t + 3, 1);
+                }
             }
             const unsigned by = __ballot_sync(FULL_MASK, fy), bn = __ballot_sync(FULL_MASK, fn);
             if (lane == 0) { fb_s[ch] = make_uint2(by, bn); cnt_s[ch] = __popc(by) + __popc(bn); }
@@ -632,18 +690,21 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 const int base = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
                 const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
                 if (fy | fn) {
-                    const uint2 rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+                    const int il = i - node0;
+                    const unsigned lc = 2u * (unsigned)il;
+                    const uint2 rs = *reinterpret_cast<const uint2*>(s_rs + lc);
+                    const int ppc = (int)(s_nm[buf][il].w & 0xFFFFu);
 #pragma unroll
                     for (int d = 0; d < 2; ++d) {
                         if (!(d == 0 ? fy : fn)) continue;
-                        const uint32_t rpx = d == 0 ? rp.x : rp.y;
+                        const uint32_t rsx = d == 0 ? rs.x : rs.y;
                         const int li = base + (d == 1 && fy ? 1 : 0);
-                        const uint32_t cf = (2u * i + d) | (rpx & DD_IDENT);
-                        const int pc = cand_pc(cf, buf);
-                        const unsigned long long ag = __ldcg(ev.cand_agg + cb + (rpx & DD_CMASK));
-                        const int value = key_value(ag);
-                        ulist[li] = cf; stat[li] = 0;
-                        keys[li] = (ag & 0xFFFFFFFF00000000ull) | (unsigned)pc;
+                        const uint32_t c = 2u * i + d;
+                        const int pc = (rsx & DD_IDENT) ? ppc : (d == 0 ? (int)s_pcy[il] : ppc - 1);
+                        const uint32_t vb = *cptr(s_val32, rep_of(c, rsx));
+                        const int value = (int)(vb ^ 0x80000000u);
+                        ulist[li] = c | (rsx & DD_IDENT); stat[li] = 0;
+                        keys[li] = ((unsigned long long)vb << 32) | (unsigned)pc;
                         mm[0] = max(mm[0], value); mm[1] = max(mm[1], -value); mm[2] = max(mm[2], pc); mm[3] = max(mm[3], -pc);
                     }
                 }
@@ -653,7 +714,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
         push(6, (unsigned long long)(unsigned)Ublk, best, (unsigned long long)(uint32_t)mm[0], (unsigned long long)(uint32_t)mm[1], (unsigned long long)(uint32_t)mm[2],
              (unsigned long long)(uint32_t)mm[3]);
         prof(3);
-        cl.sync();  // ---- S2 ---------------------------------------------------------------------------------------------------------
+        csync();  // ---- S2 ---------------------------------------------------------------------------------------------------------
         prof(4);
         int U = 0, cta_off = 0;
         best = ~0ull;
@@ -712,7 +773,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     const unsigned v = lh[i];
                     if (v) for (unsigned r = 0; r < CS; ++r) atomicAdd(cl.map_shared_rank(&gh[i], r), v);
                 }
-                cl.sync();  // ---- S3 ---------------------------------------------------------------------------------------------------
+                csync();  // ---- S3 ---------------------------------------------------------------------------------------------------
                 {   // bucket b with  #(bin > b) < need <= #(bin >= b): every thread owns 4 consecutive bins, largest first
                     int c4[4]; int s4 = 0;
 #pragma unroll
@@ -734,7 +795,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 need -= above;
                 const bool all_keep = need == inb;
                 if (tid == 0) fx.ucnt = 0;
-                __syncthreads();
+                __syncthreads();  // (lh is read no more: its memory now holds the undecided list)
                 int cnts[4] = {0, 0, 0, 0};  // kept for sure, in the boundary bucket
                 for (int li = tid; li < Ublk; li += DD_NT) {
                     const unsigned long long x = keys[li];
@@ -751,7 +812,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 const int above_l = cnts[0], inb_l = cnts[1];
                 if (all_keep) {
                     push(1, (unsigned long long)(unsigned)(above_l + inb_l));
-                    cl.sync();  // ---- S4' -------------------------------------------------------------------------------------------
+                    csync();  // ---- S4' -------------------------------------------------------------------------------------------
                     nkeep = 0; kcta = 0;
                     for (unsigned r = 0; r < CS; ++r) { const int y = (int)got(0, r); if (r < rank) kcta += y; nkeep += y; }
                     xnext();
@@ -765,7 +826,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                         *cl.map_shared_rank(&garr[gbase + j], 0) = (unsigned long long)ulist[li] | ((unsigned long long)li << 32) | ((unsigned long long)rank << 56);
                     }
                     push(1, (unsigned long long)(unsigned)above_l);
-                    cl.sync();  // ---- S4 --------------------------------------------------------------------------------------------
+                    csync();  // ---- S4 --------------------------------------------------------------------------------------------
                     int above_r[DD_MAXCS];
                     for (unsigned r = 0; r < CS; ++r) above_r[r] = (int)got(0, r);
                     xnext();
@@ -778,15 +839,14 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                             const unsigned long long g = garr[j];
                             const unsigned owner = (unsigned)(g >> 56); const uint32_t li = (uint32_t)(g >> 32) & 0xFFFFFFu;
                             const uint8_t s = gstat[j];
-                            if (L.smem_keys) *cl.map_shared_rank(&stat[li], owner) = s;
-                            else ev.dd_stat[(size_t)k * ev.C2 + (size_t)owner * L.capc + li] = s;
+                            *cl.map_shared_rank(&stat[li], owner) = s;
                             if (s == 1) atomicAdd(&fx.kbc[owner], 1);
                         }
                         __syncthreads();
                         if (tid < (int)(CS * CS)) *cl.map_shared_rank(&fx.kbx[kphase][tid % CS], tid / CS) = fx.kbc[tid % CS];
                         if (tid == 0) fx.gcnt = 0;
                     }
-                    cl.sync();  // ---- S5 --------------------------------------------------------------------------------------------
+                    csync();  // ---- S5 --------------------------------------------------------------------------------------------
                     nkeep = 0; kcta = 0;
                     for (unsigned r = 0; r < CS; ++r) { const int y = above_r[r] + fx.kbx[kphase][r]; if (r < rank) kcta += y; nkeep += y; }
                     kphase ^= 1;
@@ -800,7 +860,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 for (int li = tid; li < Ublk; li += DD_NT) cnts[0] += stat[li] == 1;
                 block_sum4(cnts);
                 push(1, (unsigned long long)(unsigned)cnts[0]);
-                cl.sync();
+                csync();
                 nkeep = 0; kcta = 0;
                 for (unsigned r = 0; r < CS; ++r) { const int y = (int)got(0, r); if (r < rank) kcta += y; nkeep += y; }
                 xnext();
@@ -825,7 +885,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             }
         }
         prof(5);
-        int n_next = nkeep, s_pos = -1, r_pos = -1;
+        int n_next = nkeep, sv_pos = -1, r_pos = -1;
         int mpos = -1;          // position of the node that receives the merged-away states (relaxed cut)
 
         // ---- relaxation: merge the overflow (clean.rs:826-876; misp/main.rs:172-178 union) -------------------------------------------
@@ -842,8 +902,9 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 load_row_cg(cand_row(cf, buf), w);
 #pragma unroll
                 for (int j = 0; j < S; ++j) acc[j] |= w[j];
-                const uint32_t rp = __ldcg(ev.cand_rep + cb + (cf & DD_CMASK)) & DD_CMASK;
-                mkey = max(mkey, __ldcg(ev.cand_agg + cb + rp));
+                const uint32_t c = cf & DD_CMASK;
+                const uint32_t rs = s_rs[c - cbase];
+                mkey = max(mkey, agg_of(rep_of(c, rs)));
             }
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -858,8 +919,13 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 const int src = j < S ? j : 16;
                 *cl.map_shared_rank(&fx.mx[rank][src], r) = fx.merged[src];
             }
-            cl.sync();  // ---- S6 -----------------------------------------------------------------------------------------------------
-            if (tid < 17) { unsigned long long m = 0; if (tid < S) for (unsigned r = 0; r < CS; ++r) m |= fx.mx[r][tid]; else if (tid == 16) for (unsigned r = 0; r < CS; ++r) m = max(m, fx.mx[r][16]); fx.merged[tid] = m; }
+            csync();  // ---- S6 -----------------------------------------------------------------------------------------------------
+            if (tid < 17) {
+                unsigned long long m = 0;
+                if (tid < S) for (unsigned r = 0; r < CS; ++r) m |= fx.mx[r][tid];
+                else if (tid == 16) for (unsigned r = 0; r < CS; ++r) m = max(m, fx.mx[r][16]);
+                fx.merged[tid] = m;
+            }
             __syncthreads();
             mkey = fx.merged[16];
             // recycled ? (clean.rs:830): a KEPT node whose state equals the merged state.  Every CTA runs the same lookup (cluster-uniform);
@@ -881,7 +947,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                         bool eq = true;
 #pragma unroll
                         for (int q = 0; q < S / 2; ++q) { const uint4 o4 = ld_cg_u4(orow + q); eq = eq && u4lo(o4) == mw[2 * q] && u4hi(o4) == mw[2 * q + 1]; }
-                        if (eq) { rec_rep = (int)((uint32_t)en & DD_CMASK); recycled = (int)__ldcg(ev.cand_first + cb + rec_rep); break; }
+                        if (eq) { rec_rep = (int)((uint32_t)en & DD_CMASK); recycled = (int)*cptr(s_first, (uint32_t)rec_rep); break; }
                     }
                     sl = (sl + 1) & (uint32_t)(ev.T - 1);
                 }
@@ -910,51 +976,35 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             }
             if (recycled >= 0) {
                 // the best merged-away node ("saved") stays in the layer, un-deleted, next to the recycled node (clean.rs:868-871)
-                uint32_t bestc = NONE32, bestrep = 0; int bestpc = 0;
+                uint32_t bestc = NONE32;
                 for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2) {
                     const uint32_t cf = ulist[li];
-                    const uint32_t rp = __ldcg(ev.cand_rep + cb + (cf & DD_CMASK)) & DD_CMASK;
-                    const int pc = cand_pc(cf, buf);
-                    if (bestc == NONE32 || better(cf, bestc, rp, bestrep, pc, bestpc, buf)) { bestc = cf; bestrep = rp; bestpc = pc; }
+                    if (bestc == NONE32 || better(cf, bestc, buf)) bestc = cf;
                 }
                 fx.tour[tid] = bestc;
                 __syncthreads();
                 for (int d = DD_NT / 2; d > 0; d >>= 1) {
                     if (tid < d) {
                         const uint32_t a = fx.tour[tid], b2 = fx.tour[tid + d];
-                        if (b2 != NONE32) {
-                            bool take = a == NONE32;
-                            if (!take) {
-                                const uint32_t ra = __ldcg(ev.cand_rep + cb + (a & DD_CMASK)) & DD_CMASK, rb = __ldcg(ev.cand_rep + cb + (b2 & DD_CMASK)) & DD_CMASK;
-                                take = better(b2, a, rb, ra, cand_pc(b2, buf), cand_pc(a, buf), buf);
-                            }
-                            if (take) fx.tour[tid] = b2;
-                        }
+                        if (b2 != NONE32 && (a == NONE32 || better(b2, a, buf))) fx.tour[tid] = b2;
                     }
                     __syncthreads();
                 }
-                push(1, (unsigned long long)fx.tour[0]); cl.sync();
+                push(1, (unsigned long long)fx.tour[0]); csync();
                 uint32_t saved = NONE32;
                 for (unsigned r = 0; r < CS; ++r) {
                     const uint32_t c2 = (uint32_t)got(0, r);
-                    if (c2 == NONE32) continue;
-                    bool take = saved == NONE32;
-                    if (!take) {
-                        const uint32_t ra = __ldcg(ev.cand_rep + cb + (saved & DD_CMASK)) & DD_CMASK, rb = __ldcg(ev.cand_rep + cb + (c2 & DD_CMASK)) & DD_CMASK;
-                        take = better(c2, saved, rb, ra, cand_pc(c2, buf), cand_pc(saved, buf), buf);
-                    }
-                    if (take) saved = c2;
+                    if (c2 != NONE32 && (saved == NONE32 || better(c2, saved, buf))) saved = c2;
                 }
                 xnext();
-                s_pos = nkeep; n_next = nkeep + 1; mpos = r_pos;
-                cl.sync();  // every CTA has read cand_agg[rec_rep] through better() before rank 0 rewrites it
+                sv_pos = nkeep; n_next = nkeep + 1; mpos = r_pos;
+                csync();  // every CTA has read the recycled node's record through better() before rank 0 rewrites it
                 if (rank == 0 && tid == 0) {
                     // the recycled node receives every relaxed edge: RELAXED flag, value_top = max (`>=`: the appended edges win ties)
-                    const unsigned long long rkey = __ldcg(ev.cand_agg + cb + rec_rep);
-                    if (key_value(mkey) >= key_value(rkey)) ev.cand_agg[cb + rec_rep] = mkey;
-                    ev.cand_inex[cb + rec_rep] |= (uint8_t)(NF_INEXACT | NF_RELAXED);
+                    if (key_value(mkey) >= key_value(agg_of((uint32_t)rec_rep))) { *cptr(s_val32, (uint32_t)rec_rep) = (uint32_t)(mkey >> 32); *cptr(s_bp, (uint32_t)rec_rep) = (uint32_t)mkey; }
+                    *cptr(s_inex, (uint32_t)rec_rep) |= (uint8_t)(NF_INEXACT | NF_RELAXED);
                 }
-                cl.sync();  // ... and the commit below reads the rewritten record
+                csync();  // ... and the commit below reads the rewritten record
                 for (int li = tid; li < Ublk; li += DD_NT) if (stat[li] == 2 && ulist[li] == saved) stat[li] = 3;  // kept at s_pos
             } else {
                 r_pos = -1;
@@ -966,8 +1016,8 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                     if (tid == 0) {
                         store_row(ev.cur_state[nbuf] + (nb + mpos) * S, mw);
                         const uint64_t ha = dd_hacc<S>(mw);
-                        ev.nmeta[nbuf][nb + mpos] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)key_value(mkey), (uint32_t)pc | ((NF_INEXACT | NF_RELAXED) << 16));
-                        if (!ev.unit_weights) ev.vb[nbuf][nb + mpos] = row_rub(mw, pc);
+                        *nptr(s_nm[nbuf], mpos) = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)key_value(mkey), (uint32_t)pc | ((NF_INEXACT | NF_RELAXED) << 16));
+                        if (L.weighted) *nptr(s_rub[nbuf], mpos) = row_rub(mw, pc);
                         ev.plog[(lb + tn) * ev.Wcap + mpos] = ((uint32_t)mkey & PLOG_CAND_MASK) | PLOG_INEXACT | PLOG_RELAXED;
                     }
                     // its occurrences enter the histogram of the next epoch (one lane per 32-bit column)
@@ -982,10 +1032,14 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
 
         prof(6);
         // ---- commit of layer t+1 (_move_to_next_layer, clean.rs:657-687): rows, node records, parent log, positions ----------------------
+        const uint64_t hdelta = (uint64_t)(1u << (var & 31)) * (uint64_t)dd_mul32(var >> 5);
+        const int wv = ev.weight[var];
         unsigned long long b_all = 0, b_ex = 0;  // terminal layer: (biased value, pos + 1), last maximum (rule C4)
         for (int ch = warp; ch < nch; ch += DD_NW) {
             const uint2 fb = fb_s[ch];
             const int i = slice_lo + 32 * ch + lane;
+            const int il = i - node0;
+            const unsigned lc = 2u * (unsigned)il;
             const unsigned lt = (1u << lane) - 1u;
             const int fbase = off_s[ch] + __popc(fb.x & lt) + __popc(fb.y & lt);
             const bool fy = (fb.x >> lane) & 1u, fn = (fb.y >> lane) & 1u;
@@ -993,8 +1047,9 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
             if (cut) { kb = kb_s[ch]; kbase = kcta + koff_s[ch] + __popc(kb.x & lt) + __popc(kb.y & lt); }
             uint64_t w0[S], w1[S];
             bool drop0 = false, drop1 = false;
-            uint2 rp = make_uint2(NONE32, NONE32);
-            if (fy | fn) rp = *reinterpret_cast<const uint2*>(ev.cand_rep + cb + 2u * i);
+            uint2 rs = make_uint2(NONE32, NONE32);
+            uint4 pm = make_uint4(0, 0, 0, 0);
+            if (fy | fn) { rs = *reinterpret_cast<const uint2*>(s_rs + lc); pm = s_nm[buf][il]; }
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 const bool isf = d == 0 ? fy : fn;
@@ -1002,27 +1057,33 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 bool dropped = false;
                 if (isf) {
                     const uint32_t c = 2u * i + d;
-                    const uint32_t rflag = d == 0 ? rp.x : rp.y;
-                    const uint32_t cf = c | (rflag & DD_IDENT);
-                    const uint32_t rpc = rflag & DD_CMASK;
+                    const uint32_t rsx = d == 0 ? rs.x : rs.y;
+                    const uint32_t cf = c | (rsx & DD_IDENT);
                     const int li = fbase + (d == 1 && fy ? 1 : 0);
                     bool keep = (((d == 0 ? kb.x : kb.y) >> lane) & 1u) != 0;
                     int pos = kbase + (d == 1 && ((kb.x >> lane) & 1u) ? 1 : 0);
                     if (cut && !keep) {
-                        if (stat[li] == 3) { keep = true; pos = s_pos; }   // the saved node of the recycled corner case
+                        if (stat[li] == 3) { keep = true; pos = sv_pos; }   // the saved node of the recycled corner case
                         else { dropped = true; pos = relaxed ? mpos : -1; }
                     }
-                    pos_w[cb + c] = pos < 0 ? NONE32 : (uint32_t)pos;
+                    s_pos[lc + d] = pos < 0 ? NONE32 : (uint32_t)pos;
                     load_row_cg(cand_row(cf, buf), w);  // (a dropped state: its occurrences leave the histogram)
                     if (keep) {
-                        const unsigned long long key = __ldcg(ev.cand_agg + cb + rpc);
-                        const uint32_t fl = __ldcg(ev.cand_inex + cb + rpc);
+                        unsigned long long key; uint32_t fl;
+                        { const uint32_t rep = rep_of(c, rsx); key = agg_of(rep); fl = *cptr(s_inex, rep); }
                         const int value = key_value(key);
                         store_row(ev.cur_state[nbuf] + (nb + pos) * S, w);
+                        const uint64_t pha = (uint64_t)pm.x | ((uint64_t)pm.y << 32);
+                        const int ppc = (int)(pm.w & 0xFFFFu);
                         uint64_t ha; int pc;
-                        if (cf & DD_IDENT) { const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i); ha = (uint64_t)m.x | ((uint64_t)m.y << 32); pc = (int)(m.w & 0xFFFFu); if (!ev.unit_weights) ev.vb[nbuf][nb + pos] = __ldcg(ev.vb[buf] + nb + i); }
-                        else { ha = ev.cand_hacc[cb + c]; pc = (int)ev.cand_rank[cb + c]; if (!ev.unit_weights) ev.vb[nbuf][nb + pos] = ev.cand_rub[cb + c]; }
-                        ev.nmeta[nbuf][nb + pos] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)value, (uint32_t)pc | (fl << 16));
+                        if (rsx & DD_IDENT) { ha = pha; pc = ppc; }
+                        else if (d == 1) { ha = pha - hdelta; pc = ppc - 1; }
+                        else { ha = dd_hacc<S>(w); pc = (int)s_pcy[il]; }
+                        *nptr(s_nm[nbuf], pos) = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), (uint32_t)value, (uint32_t)pc | (fl << 16));
+                        if (L.weighted) {
+                            const int prub = s_rub[buf][il];
+                            *nptr(s_rub[nbuf], pos) = (rsx & DD_IDENT) ? prub : (d == 1 ? prub - wv : row_rub(w, pc));
+                        }
                         ev.plog[(lb + tn) * ev.Wcap + pos] = ((uint32_t)key & PLOG_CAND_MASK) | ((fl & NF_INEXACT) ? PLOG_INEXACT : 0u) | ((fl & NF_RELAXED) ? PLOG_RELAXED : 0u);
                         if (terminal) {
                             const unsigned long long kk2 = (key & 0xFFFFFFFF00000000ull) | (unsigned)(pos + 1);
@@ -1033,14 +1094,13 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 }
                 if (d == 0) drop0 = dropped; else drop1 = dropped;
             }
-            stage_rows(drop0, w0, true);
+            stage_rows(drop0, w0, true);   // (flushed into the next epoch's counters by the next expansion)
             stage_rows(drop1, w1, true);
         }
-        stage_commit(e ^ 1);
         if (terminal) {
             b_all = block_reduce(b_all, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
             b_ex = block_reduce(b_ex, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, fx.red64);
-            push(2, b_all, b_ex); cl.sync();
+            push(2, b_all, b_ex); csync();
             b_all = 0; b_ex = 0;
             for (unsigned r = 0; r < CS; ++r) { b_all = max(b_all, got(0, r)); b_ex = max(b_ex, got(1, r)); }
             xnext();
@@ -1054,7 +1114,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
         if (first_cut) lel = t;  // _maybe_save_lel, clean.rs:796-800: the parent layer of the first squashed layer
         if (rank == 0 && tid == 0) {
             ev.nlog[lb + tn] = n_next; ev.vlog[lb + tn] = var_next;
-            ev.rslog[(lb + tn) * 2] = s_pos; ev.rslog[(lb + tn) * 2 + 1] = r_pos;
+            ev.rslog[(lb + tn) * 2] = sv_pos; ev.rslog[(lb + tn) * 2 + 1] = r_pos;
             if (first_cut) ctl->lel = t;
         }
         if (first_cut && relaxed) {  // layer t is the last exact layer: keep its nodes for the cutset (clean.rs:566-583)
@@ -1062,13 +1122,13 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 uint64_t w[S];
                 load_row_cg(ev.cur_state[buf] + (nb + i) * S, w);
                 store_row(ev.lel_state + (nb + i) * S, w);
-                const uint4 m = ld_cg_u4(ev.nmeta[buf] + nb + i);
+                const uint4 m = s_nm[buf][i - node0];
                 ev.lel_val[nb + i] = (int)m.z;
-                ev.lel_rub[nb + i] = ev.unit_weights ? (int)(m.w & 0xFFFFu) : __ldcg(ev.vb[buf] + nb + i);
+                ev.lel_rub[nb + i] = ev.unit_weights ? (int)(m.w & 0xFFFFu) : s_rub[buf][i - node0];
             }
         }
         prof(7);
-        cl.sync();  // ---- end of the layer step: layer t+1 and the positions of its first candidates are published ---------------------------
+        csync();  // ---- end of the layer step: layer t+1 and the positions of its first candidates are published ---------------------------
         prof(8);
         n_prev = n; have_trail = true;
         if (terminal) {
@@ -1085,7 +1145,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
     if (tid == 0 && fx.cnt[0]) { atomicAdd(&ctl->expanded, fx.cnt[0]); atomicAdd(&ctl->transitions, fx.cnt[1]); }
     if (ev.dd_prof && rank == 0 && tid == 0) for (int i = 0; i < 16; ++i) atomicAdd((unsigned long long*)ev.dd_prof + i, (unsigned long long)fx.prof[i]);
     __threadfence();
-    cl.sync();
+    csync();  // (nobody starts the next DD while a peer may still read this one's records)
     if (rank == 0 && tid == 0) {
         // a restricted DD that never needed a cut is exact: its relaxed twin will never be compiled (parallel.rs:421-423)
         const int fin = (dual && k < count && !twin_pushed) ? 2 : 1;

@@ -141,12 +141,11 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ev.smem_keys = finish_smem <= 200 * 1024;
     if (ev.smem_keys) { ev.gkeys = nullptr; ev.ustat = nullptr; }
     else { finish_smem = 0; ALLOC(ev.gkeys, KC); ALLOC(ev.ustat, KC); }
-    ev.C2 = C + 1024;
-    for (int b = 0; b < 2; ++b) ALLOC(ev.nmeta[b], KW);
-    ALLOC(ev.cand_hacc, KC); ALLOC(ev.cand_rub, KC);
-    ALLOC(ev.dd_keys, (size_t)K * ev.C2); ALLOC(ev.dd_ulist, (size_t)K * ev.C2); ALLOC(ev.dd_stat, (size_t)K * ev.C2);
-    ALLOC(ev.dq, 8); ALLOC(ev.dq_jobs, K); ALLOC(ev.cand_f, KC);
-    ev.dd_generic = 0; ev.dd_prof = nullptr;
+    ALLOC(ev.dq, 8); ALLOC(ev.dq_jobs, K);
+    ev.dd_generic = 0; ev.dd_prof = nullptr; ev.dd_dbg = 0;
+    if (const char* e = getenv("DDO_DD_DBG")) ev.dd_dbg = atoi(e);
+    ev.dd_dbgbuf = nullptr;
+    if (ev.dd_dbg & 8) { ALLOC(ev.dd_dbgbuf, 8 * (size_t)Lmax); CUDA_TRY(cudaMemsetAsync(ev.dd_dbgbuf, 0, 32 * (size_t)Lmax, stream)); }
     if (const char* e = getenv("DDO_DD_PROF")) if (atoi(e)) { ALLOC(ev.dd_prof, 16); CUDA_TRY(cudaMemsetAsync(ev.dd_prof, 0, 128, stream)); }
     if (const char* e = getenv("DDO_DD_GENERIC")) ev.dd_generic = atoi(e) != 0;
     ALLOC(ev.table, (size_t)2 * K * T); /* k_dd alternates between two tables by layer parity */ ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
@@ -181,6 +180,12 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
 }
 
 void Engine::destroy() {
+    if (ev.dd_dbgbuf) {
+        std::vector<int> h(8 * (size_t)Lmax);
+        if (cudaMemcpy(h.data(), ev.dd_dbgbuf, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int t = 0; t < Lmax; ++t) if (h[4 * t + 3]) fprintf(stderr, "[dbg] t=%d nodes=%d cands=%d claimers=%d firsts=%d%s\n", t, h[4 * t + 3], h[4 * t + 2], h[4 * t], h[4 * t + 1], h[4 * t] != h[4 * t + 1] ? "  <-- MISMATCH" : "");
+        for (int t = 0; t < Lmax; ++t) if (h[4 * t + 3]) fprintf(stderr, "[sum] t=%d val=%d pc=%d fl=%d h=%d\n", t, h[4 * Lmax + 4 * t], h[4 * Lmax + 4 * t + 1], h[4 * Lmax + 4 * t + 2], h[4 * Lmax + 4 * t + 3]);
+    }
     if (ev.dd_prof) {  // DDO_DD_PROF=1: cycles per phase of k_dd over the life of the engine
         long long h[16];
         if (cudaMemcpy(h, ev.dd_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -278,18 +283,26 @@ static DDLayout dd_layout(const Engine* E, int cs) {
     L.slice = (((E->Wcap + cs - 1) / cs) + 31) & ~31;
     L.maxch = L.slice / 32;
     L.capc = 2 * L.slice;
+    L.weighted = E->model && !E->model->unit_weights;
     unsigned o = 0;
     auto take = [&](size_t bytes) { const unsigned at = o; o += (unsigned)((bytes + 15) & ~(size_t)15); return at; };
     L.o_D = take((size_t)2 * HN * 4); L.o_master = take((size_t)HN * 4);
-    L.o_stage = take((size_t)DD_NW * 32 * (2 * S + 1) * 4);
+    L.o_stage = take(std::max((size_t)DD_NW * 32 * (2 * S + 1) * 4, (size_t)DD_GCAP * 9));  // (the gathered boundary bucket aliases the staging rows)
     L.o_cnt = take((size_t)L.maxch * 4); L.o_off = take((size_t)L.maxch * 4); L.o_koff = take((size_t)L.maxch * 4);
     L.o_fb = take((size_t)L.maxch * 8); L.o_kb = take((size_t)L.maxch * 8);
-    L.smem_keys = (size_t)L.capc * 13 <= 64 * 1024 && o + (size_t)L.capc * 13 + 80 * 1024 <= 190 * 1024;
-    if (L.smem_keys) { L.o_keys = take((size_t)L.capc * 8); L.o_ulist = take((size_t)L.capc * 4); L.o_stat = take((size_t)L.capc); }
+    L.o_keys = take(std::max((size_t)L.capc, (size_t)DD_GCAP) * 8); L.o_ulist = take((size_t)L.capc * 4); L.o_stat = take((size_t)L.capc);
     L.o_lh = take((size_t)DD_NB * 4); L.o_gh = take((size_t)DD_NB * 4);
-    L.o_garr = take((size_t)DD_GCAP * 8); L.o_gkeys = take((size_t)DD_GCAP * 8); L.o_gstat = take((size_t)DD_GCAP); L.o_und = take((size_t)DD_GCAP * 4);
+    L.o_agg = take((size_t)L.capc * 8); L.o_first = take((size_t)L.capc * 4); L.o_rs = take((size_t)L.capc * 4); L.o_f = take((size_t)L.capc * 4);
+    L.o_pos = take((size_t)L.capc * 4); L.o_inex = take((size_t)L.capc); L.o_pcy = take((size_t)L.slice * 2);
+    L.o_nm = take((size_t)2 * L.slice * 16); L.o_rub = take(L.weighted ? (size_t)2 * L.slice * 4 : 16);
     L.total = o;
     return L;
+}
+
+// smallest cluster size whose per-CTA slice of the records fits the shared memory of an SM (0: none does, the layer-by-layer kernels run)
+static int dd_min_cs(const Engine* E, size_t max_dyn) {
+    for (int cs = 1; cs <= DD_MAXCS; cs <<= 1) if (dd_layout(E, cs).total <= max_dyn) return cs;
+    return 0;
 }
 
 template <int S>
@@ -297,17 +310,12 @@ static int run_dd(Engine* E, int count, int slots, int comp_type, int64_t best_l
     const EV& ev = E->ev;
     cudaStream_t st = E->stream;
     const int dual = slots > count;
-    if (!E->dd_attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        E->dd_attr_set = true;
-    }
-    // cluster size: wide clusters while every DD of the batch (twins included) can have its own, single CTAs for large batches
-    int cs = 1;
-    if (E->dd_cs > 0) cs = E->dd_cs;
-    else { for (int c = 8; c >= 1; c >>= 1) if (slots * c <= E->num_sms) { cs = c; break; } }
+    // cluster size: the smallest whose slice of the records fits an SM; doubled while every DD of the batch (twins included) still gets
+    // a cluster of its own (latency of a lone wide DD)
+    int cs = E->dd_min_cs;
+    while (2 * cs <= DD_MAXCS && slots * 2 * cs <= E->num_sms) cs *= 2;
+    if (E->dd_cs >= E->dd_min_cs && E->dd_cs <= DD_MAXCS) cs = E->dd_cs;
     const DDLayout L = dd_layout(E, cs);
-    if (L.total > 200 * 1024) { set_error("k_dd: shared-memory layout does not fit"); return DDO_ERR_UNSUPPORTED; }
     int nclusters = std::min(slots, std::max(1, E->num_sms / cs));
     k_dd_init<<<(slots + 127) / 128, 128, 0, st>>>(ev, count, comp_type, (long long)best_lb, dual);
     E->prof_mark(-1);
@@ -360,7 +368,20 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         CUDA_TRY(cudaFuncSetAttribute(k_finish_cl<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->finish_cl_smem));
         E->finish_cl_attr_set = true;
     }
-    bool use_dd = E->dd_enabled && E->model != nullptr;
+    if (E->dd_enabled && E->model && !E->dd_attr_set) {  // once per engine: can k_dd hold a slice of this engine's widest layer in shared memory ?
+        cudaFuncAttributes fa{};
+        CUDA_TRY(cudaFuncGetAttributes(&fa, k_dd<S>));
+        int optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, E->device));
+        const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+        E->dd_min_cs = dd_min_cs(E, max_dyn);
+        if (E->dd_min_cs > 0) {
+            CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+            CUDA_TRY(cudaFuncSetAttribute(k_dd<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+        E->dd_attr_set = true;
+    }
+    bool use_dd = E->dd_enabled && E->model != nullptr && E->dd_min_cs > 0;
     for (int i = 0; i < count && use_dd; ++i) if (E->h_root_width[i] < 1) use_dd = false;  // max_width 0 (restricted): the layer-by-layer kernels keep that corner
     if (use_dd) {
         if (cutoff_flag && *cutoff_flag) return DDO_CUTOFF;

@@ -92,14 +92,12 @@ struct EV {
     // in canonical order (layer descending, position ascending): node = layer << FC_POS_BITS | position, upper bound, scratch (value_bot, then
     // the local output index of a drain)
     uint32_t* fc_node; int32_t* fc_ub; int32_t* fc_aux; unsigned long long fc_cap;
-    // persistent whole-DD kernel (dd_kernel.cuh): node records {hash accumulator lo, hi, value_top, popcount | flags << 16} of the two layer
-    // buffers, per-candidate hash accumulator / rough upper bound of the materialised candidates, global fall-back of the per-CTA cut lists
-    // (stride C2 per DD), the device work queue and the twin jobs published by restricted DDs
-    uint4* nmeta[2]; unsigned long long* cand_hacc; int32_t* cand_rub;
-    unsigned long long* dd_keys; uint32_t* dd_ulist; uint8_t* dd_stat; int C2;
+    // persistent whole-DD kernel (dd_kernel.cuh): the device work queue and the twin jobs published by restricted DDs (the node and
+    // candidate records of a DD live in the shared memory of its cluster)
     int* dq; int* dq_jobs;
-    uint32_t* cand_f;   // [K][C] first candidate of every candidate's state (NONE32: no child), for the deferred child log
     long long* dd_prof; // [16] cycles per phase of k_dd (rank 0 / thread 0), DDO_DD_PROF=1 only
+    int* dd_dbgbuf;     // (debug, DDO_DD_DBG & 8) per layer: claimers, first candidates, candidates, nodes
+    int dd_dbg;         // debug switches of k_dd (DDO_DD_DBG)
     int dd_generic;     // force the generic cluster-wide radix select of the width cut (DDO_DD_GENERIC=1, tests)
 };
 constexpr int FC_POS_BITS = 21;
@@ -133,7 +131,7 @@ struct Engine {
     size_t finish_smem = 0; bool finish_attr_set = false;
     int compact1_min = 1;  // thread-per-candidate compaction (k_compact1) for batches of >= compact1_min DD slots (DDO_COMPACT1_MIN)
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
-    bool dd_enabled = true; int dd_cs = 0; bool dd_attr_set = false;  // persistent whole-DD kernel k_dd (DDO_DD=0 disables); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
+    bool dd_enabled = true; int dd_cs = 0; bool dd_attr_set = false; int dd_min_cs = 0;  // persistent whole-DD kernel k_dd (DDO_DD=0 disables); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
     unsigned long long dd_launches = 0;
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;
