@@ -325,6 +325,11 @@ static int run_dd(Engine* E, int count, int slots, int comp_type, int64_t best_l
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (ev.dd_prof) {
+        int maxc = -1;
+        cudaOccupancyMaxActiveClusters(&maxc, k_dd<S>, &cfg);
+        fprintf(stderr, "[k_dd launch] slots %d cluster size %d clusters %d (max active clusters %d) dynamic smem %u B\n", slots, cs, nclusters, maxc, L.total);
+    }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dd<S>, ev, L, count, dual));
     E->prof_mark(0);
     g_kernel_launches += 2; ++E->dd_launches;

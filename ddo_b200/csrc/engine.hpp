@@ -131,7 +131,7 @@ struct Engine {
     size_t finish_smem = 0; bool finish_attr_set = false;
     int compact1_min = 1;  // thread-per-candidate compaction (k_compact1) for batches of >= compact1_min DD slots (DDO_COMPACT1_MIN)
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
-    bool dd_enabled = true; int dd_cs = 0; bool dd_attr_set = false; int dd_min_cs = 0;  // persistent whole-DD kernel k_dd (DDO_DD=0 disables); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
+    bool dd_enabled = false; int dd_cs = 0; bool dd_attr_set = false; int dd_min_cs = 0;  // persistent whole-DD kernel k_dd (opt-in: DDO_DD=1; see DESIGN.md section 4b for where it stands); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
     unsigned long long dd_launches = 0;
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;

@@ -810,6 +810,61 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
         int nactive = U;
         bool done = false;
         if (need == 0) { for (int ui = tid; ui < U; ui += NT) stat[ui] = 2; done = true; }
+        if (!done) {
+            // first pass over the DENSE key (value_top - vmin) * PR + (popcount - pcmin) (see finish_body_cl): one histogram pass places
+            // the cut inside one (value_top, popcount) bucket; the radix passes below only order that bucket
+            unsigned long long hi = 0, lo = 0;  // (max value, max popcount) and (max -value, max -popcount), biased, packed for two block folds each
+            int mm[4] = {INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN};
+            for (int ui = tid; ui < U; ui += NT) {
+                const unsigned long long x = keys[ui];
+                const int v = key_value(x), pc = (int)(((uint32_t)x) >> 20);
+                mm[0] = max(mm[0], v); mm[1] = max(mm[1], -v); mm[2] = max(mm[2], pc); mm[3] = max(mm[3], -pc);
+            }
+            (void)hi; (void)lo;
+            unsigned long long m4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m4[q] = block_reduce((unsigned long long)((uint32_t)mm[q] ^ 0x80000000u), [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, 0ull, sm.red64);
+            const int vmax = (int)((uint32_t)m4[0] ^ 0x80000000u), vmin = -(int)((uint32_t)m4[1] ^ 0x80000000u);
+            const int pcmax = (int)((uint32_t)m4[2] ^ 0x80000000u), pcmin = -(int)((uint32_t)m4[3] ^ 0x80000000u);
+            const long long VR = (long long)vmax - vmin + 1, PR = (long long)pcmax - pcmin + 1;
+            if (VR * PR <= 2048) {
+                const int nbins = (int)(VR * PR);
+                __syncthreads();
+                for (int i = tid; i < nbins; i += NT) sm.hist[i] = 0;
+                __syncthreads();
+                for (int ui = tid; ui < U; ui += NT) {
+                    const unsigned long long x = keys[ui];
+                    atomicAdd(&sm.hist[(key_value(x) - vmin) * (int)PR + ((int)(((uint32_t)x) >> 20) - pcmin)], 1u);
+                }
+                __syncthreads();
+                {
+                    int c2[2]; int s2 = 0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { const int bi = nbins - 1 - (2 * tid + q); c2[q] = bi >= 0 ? (int)sm.hist[bi] : 0; s2 += c2[q]; }
+                    int tot;
+                    const int before = block_excl_scan(s2, &tot, sm.scan);
+                    if (before < need && need <= before + s2) {
+                        int acc = before;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            if (acc < need && need <= acc + c2[q]) { sm.misc[0] = nbins - 1 - (2 * tid + q); sm.misc[1] = acc; sm.misc[2] = c2[q]; }
+                            acc += c2[q];
+                        }
+                    }
+                    __syncthreads();
+                }
+                const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
+                need -= above; nactive = inb;
+                const bool all_keep = need == inb;
+                for (int ui = tid; ui < U; ui += NT) {
+                    const unsigned long long x = keys[ui];
+                    const int bin = (key_value(x) - vmin) * (int)PR + ((int)(((uint32_t)x) >> 20) - pcmin);
+                    if (bin > b) stat[ui] = 1; else if (bin < b) stat[ui] = 2; else if (all_keep) stat[ui] = 1;
+                }
+                __syncthreads();
+                if (all_keep) done = true;
+            }
+        }
         for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
             // key chunk 0: (value_top, popcount, two smallest members); chunk j >= 1: the next MK members of the state (member_key)
             if (chunk > 0) {
@@ -1057,35 +1112,42 @@ namespace cg = cooperative_groups;
 constexpr int FCL_CS = 8;
 constexpr int FCL_NT = 256;
 
+constexpr int FCL_DB = 2048;  // bins of the dense (value_top, popcount) histogram of the width cut
+
 struct FinishClSmem {
     int scan[40];
     unsigned long long red64[40];
-    unsigned int hist[2][256];        // local digit histograms, double-buffered across cluster barriers
-    unsigned int ghist[256];          // cluster-wide digit histogram
+    unsigned int hist[256];           // local digit histogram of one radix pass
+    unsigned int ghist[2][256];       // cluster-wide digit histogram: every CTA adds its non-zero bins into every peer (remote atomics), double-buffered
+    unsigned int dh[FCL_DB];          // local / cluster-wide histogram of the dense (value_top, popcount) key of the first pass
+    unsigned int dgh[FCL_DB];
     unsigned long long merged[32];
-    unsigned long long xch[2][4];     // exchange slots (double-buffered): up to 4 block-uniform values per exchange
+    unsigned long long xch[2][4][FCL_CS];  // exchange slots [phase][value][source rank]: PUSHED into every peer before a cluster barrier, read locally after it
     int misc[16];
+    int red4[FCL_NT / 32][4];
 };
 
+// Exchanges between the CTAs of the cluster.  A value is pushed (remote store, fire and forget) into every peer's shared memory before the
+// barrier and read locally after it: a pulled value costs one ~215-cycle DSMEM round trip PER PEER, serialised in the fold loop (round 1).
 struct ClusterXchg {
     cg::cluster_group cl; FinishClSmem* sm; int phase; int hphase; unsigned rank;
     // fold of up to 4 block-uniform values over the CTAs of the cluster; result uniform in the whole cluster
     template <class Op> __device__ void allreduce(unsigned long long* v, int n, Op op) {
-        if (threadIdx.x == 0) for (int i = 0; i < n; ++i) sm->xch[phase][i] = v[i];
+        if ((int)threadIdx.x < n * FCL_CS) { const int i = threadIdx.x / FCL_CS; *cl.map_shared_rank(&sm->xch[phase][i][rank], threadIdx.x % FCL_CS) = v[i]; }
         cl.sync();
         for (int i = 0; i < n; ++i) {
-            unsigned long long acc = *cl.map_shared_rank(&sm->xch[phase][i], 0);
-            for (unsigned r = 1; r < FCL_CS; ++r) acc = op(acc, *cl.map_shared_rank(&sm->xch[phase][i], r));
+            unsigned long long acc = sm->xch[phase][i][0];
+            for (unsigned r = 1; r < FCL_CS; ++r) acc = op(acc, sm->xch[phase][i][r]);
             v[i] = acc;
         }
         phase ^= 1;
     }
     // exclusive prefix over the ranks of one block-uniform count; *total = sum over the cluster
     __device__ int scan(int v, int* total) {
-        if (threadIdx.x == 0) sm->xch[phase][0] = (unsigned long long)(unsigned)v;
+        if (threadIdx.x < FCL_CS) *cl.map_shared_rank(&sm->xch[phase][0][rank], threadIdx.x) = (unsigned long long)(unsigned)v;
         cl.sync();
         int pre = 0, tot = 0;
-        for (unsigned r = 0; r < FCL_CS; ++r) { const int x = (int)*cl.map_shared_rank(&sm->xch[phase][0], r); if (r < rank) pre += x; tot += x; }
+        for (unsigned r = 0; r < FCL_CS; ++r) { const int x = (int)sm->xch[phase][0][r]; if (r < rank) pre += x; tot += x; }
         phase ^= 1;
         *total = tot;
         return pre;
@@ -1100,6 +1162,8 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
     ClusterXchg X{cl, &sm, 0, 0, rank};
     const int k = blockIdx.x / FCL_CS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 512; i += FCL_NT) (&sm.ghist[0][0])[i] = 0;   // (the peers add into them only after the cluster barriers of step A)
+    for (int i = tid; i < FCL_DB; i += FCL_NT) sm.dgh[i] = 0;
     const int gt = (int)rank * NT + tid;  // thread index in the cluster: candidate chunks are contiguous in this order
     DDCtl* ctl = ev.ctl + k;
     const int status = ctl->status;
@@ -1239,6 +1303,74 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
     if (cut) {
         bool done = false;
         if (need == 0) { for (int li = tid; li < Ublk; li += NT) stat[li] = 2; done = true; }
+        if (!done) {
+            // ---- first pass over a DENSE key.  value_top and the popcount span a few dozen values each in one layer, so the pair
+            // (value_top - vmin) * PR + (popcount - pcmin) usually fits FCL_DB bins: ONE histogram pass (summed into every CTA by remote
+            // atomics, one cluster barrier) places the cut inside one (value_top, popcount) bucket, where round 1 walked four to five
+            // 8-bit digits of the 64-bit key with a barrier and eight serialised DSMEM reads per bin each.
+            int mm[4] = {INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN};  // max value, max -value, max popcount, max -popcount
+            for (int li = tid; li < Ublk; li += NT) {
+                const unsigned long long x = keys[li];
+                const int v = key_value(x), pc = (int)(((uint32_t)x) >> 20);
+                mm[0] = max(mm[0], v); mm[1] = max(mm[1], -v); mm[2] = max(mm[2], pc); mm[3] = max(mm[3], -pc);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mm[q] = warp_reduce(mm[q], [](int a, int b) { return a > b ? a : b; });
+            __syncthreads();
+            if (lane == 0) for (int q = 0; q < 4; ++q) sm.red4[warp][q] = mm[q];
+            __syncthreads();
+            unsigned long long m4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { int x = INT32_MIN; for (int w2 = 0; w2 < NT / 32; ++w2) x = max(x, sm.red4[w2][q]); m4[q] = (unsigned long long)((uint32_t)x ^ 0x80000000u); }
+            X.allreduce(m4, 4, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; });
+            const int vmax = (int)((uint32_t)m4[0] ^ 0x80000000u), vmin = -(int)((uint32_t)m4[1] ^ 0x80000000u);
+            const int pcmax = (int)((uint32_t)m4[2] ^ 0x80000000u), pcmin = -(int)((uint32_t)m4[3] ^ 0x80000000u);
+            const long long VR = (long long)vmax - vmin + 1, PR = (long long)pcmax - pcmin + 1;
+            if (VR * PR <= FCL_DB) {
+                const int nbins = (int)(VR * PR);
+                for (int i = tid; i < nbins; i += NT) sm.dh[i] = 0;
+                __syncthreads();
+                for (int li = tid; li < Ublk; li += NT) {
+                    const unsigned long long x = keys[li];
+                    atomicAdd(&sm.dh[(key_value(x) - vmin) * (int)PR + ((int)(((uint32_t)x) >> 20) - pcmin)], 1u);
+                }
+                __syncthreads();
+                for (int i = tid; i < nbins; i += NT) {
+                    const unsigned v = sm.dh[i];
+                    if (v) for (unsigned r = 0; r < FCL_CS; ++r) atomicAdd(cl.map_shared_rank(&sm.dgh[i], r), v);
+                }
+                cl.sync();
+                {   // bucket b with  #(bin > b) < need <= #(bin >= b): every thread owns FCL_DB / NT consecutive bins, largest first
+                    constexpr int PER = FCL_DB / NT;
+                    int c8[PER]; int s8 = 0;
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) { const int bi = nbins - 1 - (PER * tid + q); c8[q] = bi >= 0 ? (int)sm.dgh[bi] : 0; s8 += c8[q]; }
+                    int tot;
+                    const int before = block_excl_scan(s8, &tot, sm.scan);
+                    if (before < need && need <= before + s8) {
+                        int acc = before;
+#pragma unroll
+                        for (int q = 0; q < PER; ++q) {
+                            if (acc < need && need <= acc + c8[q]) { sm.misc[0] = nbins - 1 - (PER * tid + q); sm.misc[1] = acc; sm.misc[2] = c8[q]; }
+                            acc += c8[q];
+                        }
+                    }
+                    __syncthreads();
+                }
+                const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
+                need -= above;
+                const bool all_keep = need == inb;
+                for (int li = tid; li < Ublk; li += NT) {
+                    const unsigned long long x = keys[li];
+                    const int bin = (key_value(x) - vmin) * (int)PR + ((int)(((uint32_t)x) >> 20) - pcmin);
+                    if (bin > b) stat[li] = 1; else if (bin < b) stat[li] = 2; else if (all_keep) stat[li] = 1;
+                }
+                __syncthreads();
+                if (all_keep) done = true;
+            }
+        }
+        // ---- the rest of the order (the two smallest members in the key's low bits, then BitSet::cmp over member-index chunks): MSD radix
+        // select over the still undecided candidates, one cluster barrier per digit
         for (int chunk = 0; chunk <= MemberKey<S>::CHUNKS && !done; ++chunk) {
             if (chunk > 0) {  // the next MK members of every still undecided state (member_key)
                 for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) keys[li] = member_key<S>(ev.cand_state + (cb + ev.ulist[cb + cta_off + li]) * S, MemberKey<S>::MK * (chunk - 1));
@@ -1253,22 +1385,22 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
             const unsigned long long diff = kk[0] ^ ~kk[1];
             for (int byte = 7; byte >= 0 && !done; --byte) {
                 if (((diff >> (8 * byte)) & 0xff) == 0) continue;
-                unsigned int* h = sm.hist[X.hphase];
+                unsigned int* h = sm.hist;
+                unsigned int* gh = sm.ghist[X.hphase];
                 for (int i = tid; i < 256; i += NT) h[i] = 0;
                 __syncthreads();
                 for (int li = tid; li < Ublk; li += NT) if (stat[li] == 0) atomicAdd(&h[(key_of(li) >> (8 * byte)) & 0xff], 1u);
-                cl.sync();
-                for (int i = tid; i < 256; i += NT) {
-                    unsigned int a = 0;
-                    for (unsigned r = 0; r < FCL_CS; ++r) a += *cl.map_shared_rank(&h[i], r);
-                    sm.ghist[i] = a;
-                }
-                X.hphase ^= 1;
                 __syncthreads();
+                for (int i = tid; i < 256; i += NT) {
+                    const unsigned v = h[i];
+                    if (v) for (unsigned r = 0; r < FCL_CS; ++r) atomicAdd(cl.map_shared_rank(&gh[i], r), v);
+                }
+                cl.sync();
+                X.hphase ^= 1;
                 if (warp == 0) {
                     int c8[8]; int s8 = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { c8[q] = (int)sm.ghist[255 - (lane * 8 + q)]; s8 += c8[q]; }
+                    for (int q = 0; q < 8; ++q) { c8[q] = (int)gh[255 - (lane * 8 + q)]; s8 += c8[q]; }
                     int inc = s8;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { int nn = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += nn; }
@@ -1283,6 +1415,7 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
                     }
                 }
                 __syncthreads();
+                for (int i = tid; i < 256; i += NT) gh[i] = 0;  // (the peers add into this buffer again two barriers from now at the earliest)
                 const int b = sm.misc[0], above = sm.misc[1], inb = sm.misc[2];
                 need -= above;
                 const bool all_keep = (need == inb);
@@ -1396,11 +1529,11 @@ __device__ void finish_body_cl(const EV& ev, int t, FinishClSmem& sm, unsigned l
             }
             unsigned long long bc = s_best[0];
             // best over the cluster: every CTA folds the eight local winners in rank order with the same comparator
-            if (tid == 0) sm.xch[X.phase][0] = bc;
+            if (tid < FCL_CS) *cl.map_shared_rank(&sm.xch[X.phase][0][rank], tid) = bc;
             cl.sync();
             uint32_t saved = NONE32;
             for (unsigned r = 0; r < FCL_CS; ++r) {
-                const uint32_t c = (uint32_t)*cl.map_shared_rank(&sm.xch[X.phase][0], r);
+                const uint32_t c = (uint32_t)sm.xch[X.phase][0][r];
                 if (c != NONE32 && (saved == NONE32 || cand_better<S>(ev, cb, c, saved))) saved = c;
             }
             X.phase ^= 1;

@@ -252,3 +252,22 @@ def test_bench_configuration_trajectory_matches_oracle_golden(golden_dir):
     got = (s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"]), int(st["waves"]))
     assert got == (g["explored"], g["expanded"], g["transitions"], g["compilations"], g["waves"])
     assert sorted(d.variable for d in s.best_solution() if d.value == 1) == g["solution"]
+
+
+@pytest.mark.parametrize("cs", ["1", "4", "16"])
+def test_persistent_whole_dd_kernel_matches_oracle(monkeypatch, cs):
+    """The opt-in persistent whole-DD kernel (dd_kernel.cuh, DDO_DD=1: one thread-block cluster compiles a DD from root to terminal layer, node
+    and candidate records in distributed shared memory) at several cluster sizes: DD-level parity over widths / best_lb (cuts, pruning,
+    merges, the recycled corner), and a dual-mode solve against the oracle's wave solver."""
+    monkeypatch.setenv("DDO_DD", "1")
+    monkeypatch.setenv("DDO_DD_CS", cs)
+    check_instance(gnp(100, 0.3, 5), [1, 2, 3, 13, 50, 400], best_lbs=(N.I64_MIN, 6))
+    check_instance(gnp(129, 0.5, 7), [8, 400], best_lbs=(N.I64_MIN, 5))
+    inst = gnp(110, 0.25, 23)
+    s = ParNoCachingSolverLel(Misp(inst), FixedWidth(24), wave_size=48, batch_cap=32)
+    c = s.maximize()
+    st = s.stats()
+    ref = O.OracleMisp(inst).solve("wave", k=48, width=24)
+    assert (c.best_value, c.is_exact, s.explored(), int(st["expanded"]), int(st["transitions"]), int(st["compilations"])) == \
+        (ref["best_value"], bool(ref["is_exact"]), ref["explored"], ref["expanded"], ref["transitions"], ref["compilations"])
+    assert sorted(d.variable for d in s.best_solution() if d.value == 1) == ref["solution"]
