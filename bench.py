@@ -132,7 +132,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from ddo_b200 import FixedWidth, ParNoCachingSolverLel, kernel_launches
-    from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
+    from ddo_b200.sharded import NativeComm, sharded_maximize
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -144,7 +144,13 @@ def run_ours(args, rank, world, local_rank):
     pb = wl.problem(local_rank)
     solver = ParNoCachingSolverLel(pb, FixedWidth(wl.width), wave_size=args.wave, batch_cap=args.batch_cap)
     sampler = ClockSampler(local_rank)
-    allred = torch_allreduce_max(torch.device("cuda", local_rank)) if world > 1 else None
+    comm = None
+    if world > 1:  # the search's own collectives go through the C ABI (ddo_comm_*: NCCL from C++); torch.distributed only bootstraps the id and times
+        def bootstrap(raw):
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = NativeComm(rank, world, local_rank, bootstrap)
 
     def barrier():
         if world > 1:
@@ -159,7 +165,8 @@ def run_ours(args, rank, world, local_rank):
             comp = solver.maximize(max_waves=wl.max_waves)
             res = {"best_lb": solver.best_lower_bound(), "best_ub": solver.best_upper_bound(), "is_exact": comp.is_exact}
         else:
-            res = sharded_maximize(solver, rank, world, allred, max_waves=wl.max_waves)
+            res = sharded_maximize(solver, rank, world, comm, max_waves=wl.max_waves)
+            res = {k: res[k] for k in ("best_lb", "best_ub", "is_exact", "handoffs", "nodes_sent", "collectives")}
         wall = time.perf_counter() - t0
         s1 = solver.stats()
         # init() resets the counters, so s1 holds this step only (bytes are cumulative engine counters)
@@ -214,9 +221,9 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "impl": "ddo_b200",
         "config": {"workload": f"{wl.step_desc}, {wl.desc}",
                    "wave_size": args.wave, "batch_cap": args.batch_cap, "objective": int(last["best_lb"]), "proven_upper_bound": int(last["best_ub"]), "is_exact": bool(last["is_exact"]),
-                   "explored_subproblems": int(explored_all), "expanded_nodes_per_step": int(expanded_all / args.steps), "waves_per_step_rank0": int(last["waves"]),
+                   "explored_subproblems": int(explored_all), "handoffs_rank0": last.get("handoffs"), "nodes_sent_rank0": last.get("nodes_sent"), "collectives_rank0": last.get("collectives"), "expanded_nodes_per_step": int(expanded_all / args.steps), "waves_per_step_rank0": int(last["waves"]),
                    "l2": "no L2 flush: every step re-runs the whole search (thousands of launches over >10 GB of arenas), far beyond the 126 MB L2",
-                   "parallelism": f"fringe sharded over {world} GPU(s); one allreduce(max) of 3 x int64 per wave, no data-path collective"},
+                   "parallelism": f"fringe sharded over {world} GPU(s); one all-gather of 4 x int64 per rank per wave (ddo_comm_allgather, NCCL from the C ABI), open nodes handed from loaded to idle ranks point to point"},
         "device_value": expanded_all / (dev_ms * 1e-3), "device_ms_per_step": dev_ms / args.steps, "golden_check": golden,
         "e2e": {"value": expanded_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "note": "wall clock of ddo_solver_maximize (host fringe, H2D of every wave's roots, D2H of completions and cutsets included)"},

@@ -443,6 +443,42 @@ class ParNoCachingSolverLel:
     def retain_share(self, rank: int, nranks: int):
         N.check(N.lib().ddo_solver_retain_share(self.h, rank, nranks), "ddo_solver_retain_share")
 
+    # work hand-off between ranks (ddo_b200/sharded.py): packed open nodes as one int64 array
+    def export_open(self, max_nodes: int) -> np.ndarray:
+        """Up to `max_nodes` open nodes (every other one of the best 2 * max_nodes) as rows of int64:
+        [value, ub, depth, state words ..., (variable, value) x nb_variables]."""
+        n, w = self.problem.nb_variables(), self.problem.words
+        states = np.zeros((max(max_nodes, 1), w), dtype=np.uint64)
+        values = np.zeros(max(max_nodes, 1), dtype=np.int64)
+        ubs = np.zeros(max(max_nodes, 1), dtype=np.int64)
+        depths = np.zeros(max(max_nodes, 1), dtype=np.int32)
+        paths = np.zeros((max(max_nodes, 1), n, 2), dtype=np.int32)
+        cnt = C.c_int32(0)
+        N.check(N.lib().ddo_solver_export_open(self.h, max_nodes, _ptr(states), _ptr(values), _ptr(ubs), _ptr(depths), _ptr(paths), C.byref(cnt)), "ddo_solver_export_open")
+        k = cnt.value
+        out = np.zeros((k, 3 + w + n), dtype=np.int64)
+        out[:, 0], out[:, 1], out[:, 2] = values[:k], ubs[:k], depths[:k]
+        out[:, 3:3 + w] = states[:k].view(np.int64)
+        out[:, 3 + w:] = (paths[:k, :, 0].astype(np.int64) << 32) | (paths[:k, :, 1].astype(np.int64) & 0xFFFFFFFF)
+        return out
+
+    def import_open(self, rows: np.ndarray):
+        n, w = self.problem.nb_variables(), self.problem.words
+        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3 + w + n)
+        k = rows.shape[0]
+        if k == 0:
+            return
+        states = np.ascontiguousarray(rows[:, 3:3 + w]).view(np.uint64)
+        values, ubs = np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1])
+        depths = np.ascontiguousarray(rows[:, 2].astype(np.int32))
+        paths = np.zeros((k, n, 2), dtype=np.int32)
+        paths[:, :, 0] = (rows[:, 3 + w:] >> 32).astype(np.int32)
+        paths[:, :, 1] = (rows[:, 3 + w:] & 0xFFFFFFFF).astype(np.uint32).view(np.int32).reshape(k, n)
+        N.check(N.lib().ddo_solver_import_open(self.h, k, _ptr(states), _ptr(values), _ptr(ubs), _ptr(depths), _ptr(paths)), "ddo_solver_import_open")
+
+    def node_words(self) -> int:
+        return 3 + self.problem.words + self.problem.nb_variables()
+
     def finish(self):
         N.lib().ddo_solver_finish(self.h)
 

@@ -214,6 +214,18 @@ int ddo_solver_wave(ddo_solver* s, const volatile int32_t* cutoff_flag, int64_t 
 }
 int ddo_solver_set_lower_bound(ddo_solver* s, int64_t lb) { if (!s) return DDO_ERR_INVALID; if (lb > s->s->best_lb) s->s->best_lb = lb; return DDO_OK; }
 int ddo_solver_retain_share(ddo_solver* s, int32_t rank, int32_t nranks) { GUARD_BEGIN if (!s) return DDO_ERR_INVALID; return s->s->retain_share(rank, nranks); GUARD_END }
+int ddo_solver_export_open(ddo_solver* s, int32_t max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count) {
+    GUARD_BEGIN
+    if (!s) { set_error("null argument"); return DDO_ERR_INVALID; }
+    return s->s->export_open(max_nodes, states, values, ubs, depths, paths, count);
+    GUARD_END
+}
+int ddo_solver_import_open(ddo_solver* s, int32_t count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths) {
+    GUARD_BEGIN
+    if (!s) { set_error("null argument"); return DDO_ERR_INVALID; }
+    return s->s->import_open(count, states, values, ubs, depths, paths);
+    GUARD_END
+}
 int ddo_solver_finish(ddo_solver* s) {
     if (!s) return DDO_ERR_INVALID;
     s->s->finish();

@@ -779,4 +779,56 @@ int Solver::retain_share(int rank, int nranks) {
     return DDO_OK;
 }
 
+
+int Solver::export_open(int max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count) {
+    if (max_nodes < 0 || !states || !values || !ubs || !depths || !paths || !count) { set_error("export_open: invalid argument"); return DDO_ERR_INVALID; }
+    if (pre_valid) unpop();
+    const int W = words, PWN = (n_vars + 63) / 64;
+    struct Keep { std::vector<uint64_t> state, bits; NoDupFringe::Item it; };
+    std::vector<Keep> keep;
+    int out = 0;
+    std::vector<ddo_decision> path;
+    for (int idx = 0; out < max_nodes && !fringe.empty(); ++idx) {
+        const int id = fringe.pop();
+        const NoDupFringe::Item it = fringe.item(id);
+        if (idx & 1) {  // every other node of the MaxUB order leaves
+            std::memcpy(states + (size_t)out * W, fringe.state(id), (size_t)W * 8);
+            values[out] = it.value; ubs[out] = it.ub == INT32_MAX ? INT64_MAX : it.ub; depths[out] = it.depth;
+            path.clear();
+            full_path(it.rec, fringe.bits(id), it.depth, path);
+            if ((int)path.size() != it.depth) { set_error("export_open: inconsistent path"); return DDO_ERR_INVALID; }
+            std::copy(path.begin(), path.end(), paths + (size_t)out * n_vars);
+            ++out;
+        } else {
+            Keep k; k.state.assign(fringe.state(id), fringe.state(id) + W); k.bits.assign(fringe.bits(id), fringe.bits(id) + PWN); k.it = it;
+            keep.push_back(std::move(k));
+        }
+    }
+    for (auto& k : keep) fringe.push(k.state.data(), k.it.value, k.it.ub, k.it.depth, k.it.rec, k.bits.data(), PWN);
+    *count = out;
+    return DDO_OK;
+}
+
+int Solver::import_open(int count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths) {
+    if (count < 0 || (count > 0 && (!states || !values || !ubs || !depths || !paths))) { set_error("import_open: invalid argument"); return DDO_ERR_INVALID; }
+    const int W = words, PWN = (n_vars + 63) / 64;
+    std::vector<uint64_t> bits(PWN);
+    for (int i = 0; i < count; ++i) {
+        const int d = depths[i];
+        if (d < 0 || d > n_vars) { set_error("import_open: bad depth"); return DDO_ERR_INVALID; }
+        if ((int64_t)ubs[i] <= best_lb) continue;  // parallel.rs:460-461: nothing to gain from this node any more
+        PathRec pr; pr.parent_rec = -1; pr.base_depth = 0; pr.vars.resize(d);
+        std::fill(bits.begin(), bits.end(), 0ull);
+        for (int j = 0; j < d; ++j) {
+            const ddo_decision& dec = paths[(size_t)i * n_vars + j];
+            pr.vars[j] = dec.variable;
+            if (dec.value == eng->bit_value[1]) bits[j >> 6] |= 1ull << (j & 63);
+        }
+        recs.push_back(std::move(pr));
+        const int64_t ub = ubs[i];
+        fringe.push(states + (size_t)i * W, (int32_t)values[i], ub >= INT32_MAX ? INT32_MAX : (int32_t)ub, d, (int)recs.size() - 1, bits.data(), PWN);
+    }
+    return DDO_OK;
+}
+
 }  // namespace ddo

@@ -124,6 +124,12 @@ struct Solver {
     void finish();
     void full_path(int32_t rec, const uint64_t* bits, int32_t depth, std::vector<ddo_decision>& out) const;
     int retain_share(int rank, int nranks);
+    // Work hand-off between ranks (the reference's workers share ONE fringe, parallel.rs:500-559; here a rank whose fringe runs dry is
+    // refilled by a loaded one).  export_open pops up to 2 * max_nodes of the best open nodes, gives away every other one (so donor and
+    // receiver keep nodes of the same quality) and re-queues the rest; a node travels as packed state, value, upper bound, depth and its
+    // FULL decision path.  import_open queues such nodes (each gets a path record of its own).
+    int export_open(int max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count);
+    int import_open(int count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths);
 };
 
 }  // namespace ddo

@@ -60,6 +60,9 @@ class MispInstance:
             s[w] = np.uint64(_MASK if bits == 64 else (1 << bits) - 1)
         return s
 
+    def has_edge(self, a: int, b: int) -> bool:
+        return bool(np.any(((self.src == a) & (self.dst == b)) | ((self.src == b) & (self.dst == a))))
+
     def to_dimacs(self) -> str:
         lines = [f"p edge {self.n} {len(self.src)}"]
         for i, w in enumerate(self.weights):

@@ -164,6 +164,15 @@ int ddo_solver_set_lower_bound(ddo_solver*, int64_t best_lb);          /* adopt 
 /* initial deal of the open sub-problems over `nranks` processes (one per GPU): every rank compiled the same root DD; this keeps every
  * nranks-th node of the common MaxUB order and drops the others -- the path shards with no data-path collective. */
 int ddo_solver_retain_share(ddo_solver*, int32_t rank, int32_t nranks);
+/* Work hand-off between ranks.  The reference's workers pull from ONE shared fringe (parallel.rs:500-559), so its load balances itself;
+ * here a rank whose fringe runs dry is refilled by a loaded one.  export_open pops up to 2 * max_nodes of the best open nodes, hands out
+ * every other one (donor and receiver keep nodes of the same quality) and re-queues the rest.  A node travels as packed state
+ * [state_words], value, upper bound (INT64_MAX: none yet), depth and its full decision path (paths has nb_variables slots per node, the
+ * first `depth` are used).  import_open queues such nodes (those whose bound no longer beats the incumbent are dropped, parallel.rs:461). */
+int ddo_solver_export_open(ddo_solver*, int32_t max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths,
+                           int32_t* count);
+int ddo_solver_import_open(ddo_solver*, int32_t count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths,
+                           const ddo_decision* paths);
 int ddo_solver_finish(ddo_solver*);                                    /* best_ub = best_lb when the fringe is empty (parallel.rs:512-515) */
 int64_t ddo_solver_best_lower_bound(const ddo_solver*);                /* solver.rs:83 */
 int64_t ddo_solver_best_upper_bound(const ddo_solver*);                /* solver.rs:86 */
@@ -174,6 +183,22 @@ uint64_t ddo_solver_fringe_len(const ddo_solver*);
 /* stats[0..7] = expanded nodes, transitions, compilations, waves, device ms in compile (CUDA events), host ms in fringe,
  * bytes copied host->device and device->host by the engine since it was created */
 int ddo_solver_stats(const ddo_solver*, double stats[8]);
+
+/* ---- Collectives between the ranks of a fringe-sharded search (one process per GPU): replaces `Mutex<Critical>` of
+ * implementation/solver/parallel.rs:32-81 (best_lb read at :398 / :426, written at :446-453; termination test at :512) across processes.
+ * NCCL over NVLink, loaded at run time (libnccl.so.2); buffers are HOST memory, staged through the communicator's device scratch.
+ * Bootstrap: rank 0 calls ddo_comm_unique_id and hands the 128 bytes to the other ranks by any out-of-band channel. */
+typedef struct ddo_comm ddo_comm;
+int ddo_comm_unique_id(void* id128);
+int ddo_comm_init(int32_t nranks, int32_t rank, const void* id128, int device, ddo_comm** out);
+void ddo_comm_destroy(ddo_comm*);
+/* one collective per wave: in place max over the ranks of `count` int64 ({best_lb, ub of the best open node, has_work}) ... */
+int ddo_comm_allreduce_max(ddo_comm*, int64_t* values, int32_t count);
+/* ... or, when the driver also balances the fringes, the same words of EVERY rank: recv[r * count + i] = rank r's values[i] */
+int ddo_comm_allgather(ddo_comm*, const int64_t* values, int32_t count, int64_t* recv);
+/* point-to-point hand-off of packed open nodes (ddo_solver_export_open / import_open) and of the final solution */
+int ddo_comm_send(ddo_comm*, const void* buf, int64_t bytes, int32_t peer);
+int ddo_comm_recv(ddo_comm*, void* buf, int64_t bytes, int32_t peer);
 
 #ifdef __cplusplus
 }

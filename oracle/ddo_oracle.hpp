@@ -1053,6 +1053,7 @@ public:
     SolverStats stats;
     isize best_lb = ISIZE_MIN, best_ub = ISIZE_MAX;
     std::optional<Solution> best_sol;
+    isize sol_value = ISIZE_MIN;  // objective of best_sol (best_lb may be raised from outside: set_lower_bound)
     bool aborted = false;
     uint64_t max_waves = UINT64_MAX;
     // per-wave trace for parity tests: (wave size, best_lb after wave, fringe size after wave)
@@ -1062,7 +1063,7 @@ public:
     // ---- stepwise form (what the fringe-sharded multi-GPU driver calls between its allreduce(max) steps) ----
     void init(bool push_root) {
         c_.fringe->clear();
-        best_lb = ISIZE_MIN; best_ub = ISIZE_MAX; best_sol.reset(); aborted = false; stats = SolverStats(); trace.clear();
+        best_lb = ISIZE_MIN; best_ub = ISIZE_MAX; best_sol.reset(); sol_value = ISIZE_MIN; aborted = false; stats = SolverStats(); trace.clear();
         mdds_.clear();
         for (size_t i = 0; i < K_; ++i) mdds_.emplace_back(c_.cutset_type);
         if (push_root) c_.fringe->push(SubProblem<S>{std::make_shared<const S>(c_.problem->initial_state()), c_.problem->initial_value(), {}, ISIZE_MAX, 0});
@@ -1134,6 +1135,20 @@ public:
         c_.fringe->clear();
         for (auto& n : keep) c_.fringe->push(std::move(n));
     }
+    // work hand-off between ranks (mirrors Solver::export_open / import_open of the device solver): every other one of the best
+    // 2 * max_nodes open nodes leaves, the rest is queued again
+    std::vector<SubProblem<S>> export_open(size_t max_nodes) {
+        std::vector<SubProblem<S>> out, keep;
+        for (size_t idx = 0; out.size() < max_nodes && !c_.fringe->is_empty(); ++idx) {
+            SubProblem<S> n = *c_.fringe->pop();
+            if (idx & 1) out.push_back(std::move(n)); else keep.push_back(std::move(n));
+        }
+        for (auto& n : keep) c_.fringe->push(std::move(n));
+        return out;
+    }
+    void import_open(std::vector<SubProblem<S>>&& nodes) {
+        for (auto& n : nodes) if (n.ub > best_lb) c_.fringe->push(std::move(n));
+    }
     void finish() {
         if (c_.fringe->is_empty() && !aborted) best_ub = best_lb;
         if (best_sol) std::stable_sort(best_sol->begin(), best_sol->end(), [](const Decision& a, const Decision& b) { return a.variable < b.variable; });
@@ -1158,7 +1173,7 @@ private:
     void account(const Mdd<S, Hash, Eq>& m) { stats.compilations++; stats.expanded += m.expanded; stats.transitions += m.transitions; }
     void maybe_update_best(const Mdd<S, Hash, Eq>& m) {
         isize v = m.best_exact_value().value_or(ISIZE_MIN);
-        if (v > best_lb) { best_lb = v; best_sol = m.best_exact_solution(); }
+        if (v > best_lb) { best_lb = v; best_sol = m.best_exact_solution(); sol_value = v; }
     }
     void abort_search() { aborted = true; c_.fringe->clear(); }
 };

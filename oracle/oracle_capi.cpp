@@ -221,6 +221,33 @@ template <class H> void stepper_state(Stepper<H>* s, int64_t out[6]) {
     auto& w = *s->solver;
     out[0] = w.best_lb; out[1] = w.best_ub; out[2] = (int64_t)w.fringe_len(); out[3] = (int64_t)w.stats.explored; out[4] = (int64_t)w.stats.expanded; out[5] = w.best_sol.has_value();
 }
+// rows of int64: [value, ub, depth, state words ..., (variable << 32 | value) x nb_variables] -- the layout of ddo_b200/api.py export_open
+template <class H> int32_t stepper_export(Stepper<H>* s, int32_t max_nodes, int64_t* rows) {
+    const size_t W = s->h->abi_words(), n = s->h->pb.nb_variables(), RW = 3 + W + n;
+    auto nodes = s->solver->export_open((size_t)max_nodes);
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        int64_t* r = rows + i * RW;
+        std::memset(r, 0, RW * 8);
+        r[0] = nodes[i].value; r[1] = nodes[i].ub; r[2] = (int64_t)nodes[i].depth;
+        s->h->state_to_abi(*nodes[i].state, (uint64_t*)(r + 3));
+        for (size_t j = 0; j < nodes[i].path.size(); ++j) r[3 + W + j] = ((int64_t)nodes[i].path[j].variable << 32) | ((int64_t)nodes[i].path[j].value & 0xFFFFFFFFll);
+    }
+    return (int32_t)nodes.size();
+}
+template <class H> void stepper_import(Stepper<H>* s, int32_t count, const int64_t* rows) {
+    using S = typename H::State;
+    const size_t W = s->h->abi_words(), n = s->h->pb.nb_variables(), RW = 3 + W + n;
+    std::vector<SubProblem<S>> nodes;
+    for (int32_t i = 0; i < count; ++i) {
+        const int64_t* r = rows + (size_t)i * RW;
+        SubProblem<S> sp;
+        sp.value = r[0]; sp.ub = r[1]; sp.depth = (size_t)r[2];
+        sp.state = std::make_shared<const S>(s->h->state_from_abi((const uint64_t*)(r + 3), sp.depth));
+        for (size_t j = 0; j < sp.depth; ++j) sp.path.push_back(Decision{(size_t)(r[3 + W + j] >> 32), (isize)(int32_t)(r[3 + W + j] & 0xFFFFFFFFll)});
+        nodes.push_back(std::move(sp));
+    }
+    s->solver->import_open(std::move(nodes));
+}
 template <class H> int32_t stepper_wave(Stepper<H>* s, int64_t out3[3]) { isize o[3]; bool ok = s->solver->wave(o); out3[0] = o[0]; out3[1] = o[1]; out3[2] = o[2]; return ok ? 0 : 1; }
 }  // namespace
 
@@ -304,6 +331,8 @@ void oracle_m2s_stepper_state(void* s, int64_t out[6]) { stepper_state((Stepper<
 void oracle_m2s_stepper_set_lb(void* s, int64_t lb) { ((Stepper<M2Handle>*)s)->solver->set_lower_bound(lb); }
 void oracle_m2s_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((Stepper<M2Handle>*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
 void oracle_m2s_stepper_finish(void* s) { ((Stepper<M2Handle>*)s)->solver->finish(); }
+int32_t oracle_m2s_stepper_export(void* s, int32_t max_nodes, int64_t* rows) { return stepper_export((Stepper<M2Handle>*)s, max_nodes, rows); }
+void oracle_m2s_stepper_import(void* s, int32_t count, const int64_t* rows) { stepper_import((Stepper<M2Handle>*)s, count, rows); }
 
 // CPU baseline of a batch of independent sub-problems: for each root, restricted DD then (if inexact) relaxed DD, all against the same
 // best_lb, on `threads` worker threads each owning one Mdd (the ParallelSolver worker body, parallel.rs:391-437, without the fringe).
@@ -383,6 +412,17 @@ int32_t oracle_misp_stepper_wave(void* s, int64_t out3[3]) { isize o[3]; bool ok
 void oracle_misp_stepper_set_lb(void* s, int64_t lb) { ((MispStepper*)s)->solver->set_lower_bound(lb); }
 void oracle_misp_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((MispStepper*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
 void oracle_misp_stepper_finish(void* s) { ((MispStepper*)s)->solver->finish(); }
+int64_t oracle_misp_stepper_sol_value(void* s) { return ((MispStepper*)s)->solver->sol_value; }
+int32_t oracle_misp_stepper_export(void* s, int32_t max_nodes, int64_t* rows) { return stepper_export((MispStepper*)s, max_nodes, rows); }
+void oracle_misp_stepper_import(void* s, int32_t count, const int64_t* rows) { stepper_import((MispStepper*)s, count, rows); }
+// solution of the stepper's solver: returns its length (-1: none), decisions sorted by variable; *value = objective of that solution
+int32_t oracle_misp_stepper_solution(void* s, int32_t* vars, int32_t* vals, int32_t cap) {
+    auto& w = *((MispStepper*)s)->solver;
+    if (!w.best_sol) return -1;
+    int32_t n = 0;
+    for (const Decision& d : *w.best_sol) { if (n < cap) { vars[n] = (int32_t)d.variable; vals[n] = (int32_t)d.value; } ++n; }
+    return n;
+}
 // out[0..5] = best_lb, best_ub, fringe_len, explored, expanded, has_solution
 void oracle_misp_stepper_state(void* s, int64_t out[6]) {
     auto& w = *((MispStepper*)s)->solver;

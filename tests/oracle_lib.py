@@ -74,6 +74,12 @@ def lib():
         _lib.oracle_misp_stepper_set_lb.argtypes = [C.c_void_p, C.c_int64]
         _lib.oracle_misp_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         _lib.oracle_misp_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
+        for pre in ("misp", "m2s"):
+            getattr(_lib, f"oracle_{pre}_stepper_export").argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            getattr(_lib, f"oracle_{pre}_stepper_import").argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        _lib.oracle_misp_stepper_solution.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _lib.oracle_misp_stepper_sol_value.restype = C.c_int64
+        _lib.oracle_misp_stepper_sol_value.argtypes = [C.c_void_p]
         _lib.oracle_m2s_new.restype = C.c_void_p
         _lib.oracle_m2s_new.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
         _lib.oracle_m2s_free.argtypes = [C.c_void_p]
@@ -370,6 +376,37 @@ class OracleStepper:
 
     def expanded(self):
         return self._state()[4]
+
+    # work hand-off / solution gather of ddo_b200.sharded (same packed rows as the device solver's export_open / import_open)
+    def node_words(self):
+        return 3 + self.o.words + self.o.inst.n
+
+    def export_open(self, max_nodes):
+        rows = np.zeros((max(max_nodes, 1), self.node_words()), dtype=np.int64)
+        k = self._f("stepper_export")(self.h, max_nodes, _p(rows))
+        return rows[:k].copy()
+
+    def import_open(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, self.node_words())
+        if rows.shape[0]:
+            self._f("stepper_import")(self.h, rows.shape[0], _p(rows))
+
+    def best_value(self):
+        if self.p != "misp":
+            return None
+        v = int(lib().oracle_misp_stepper_sol_value(self.h))
+        return None if v == I64_MIN else v
+
+    def best_solution(self):
+        if self.p != "misp":
+            return None
+        n = self.o.inst.n
+        sv = np.zeros(n + 1, dtype=np.int32); sx = np.zeros(n + 1, dtype=np.int32)
+        ln = lib().oracle_misp_stepper_solution(self.h, _p(sv), _p(sx), n + 1)
+        if ln < 0:
+            return None
+        from ddo_b200 import Decision
+        return [Decision(int(a), int(b)) for a, b in zip(sv[:ln], sx[:ln])]
 
 
 def knapsack_solve(inst, solver="sequential", k=1, width=None, cutset_type=FRONTIER, caching=True):

@@ -30,8 +30,40 @@ class _ThreadAllreduce:
         return f
 
 
-def _run(world, make_stepper):
-    ar = _ThreadAllreduce(world)
+class _ThreadComm:
+    """The comm interface of ddo_b200.sharded (allgather / send / recv) between `world` threads of one process."""
+
+    def __init__(self, world):
+        import queue
+        self.world = world
+        self.slots = [None] * world
+        self.bar = threading.Barrier(world)
+        self.q = {(a, b): queue.Queue() for a in range(world) for b in range(world)}
+
+    def for_rank(self, rank):
+        import numpy as np
+        outer = self
+
+        class C:
+            def allgather(self, vals):
+                outer.slots[rank] = list(vals)
+                outer.bar.wait()
+                out = np.asarray(outer.slots, dtype=np.int64)
+                outer.bar.wait()
+                return out
+
+            def send(self, arr, peer):
+                outer.q[(rank, peer)].put(np.array(arr, dtype=np.int64).reshape(-1).copy())
+
+            def recv(self, count, peer):
+                a = outer.q[(peer, rank)].get(timeout=120)
+                assert a.size == count
+                return a
+        return C()
+
+
+def _run(world, make_stepper, new_protocol=False):
+    ar = _ThreadComm(world) if new_protocol else _ThreadAllreduce(world)
     res = [None] * world
     err = []
 
@@ -77,3 +109,23 @@ def test_device_ranks_follow_the_oracle_ranks_max2sat():
     for d, r in zip(dev, ref):
         assert d["is_exact"] and d["best_lb"] == d["best_ub"] == oracle.solve("wave", k=16, width=10)["best_value"]
         assert (d["waves"], d["explored"], d["expanded"]) == (r["waves"], r["explored"], r["expanded"])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_rebalanced_device_ranks_follow_the_oracle_ranks(world):
+    """The round-2 protocol (one all-gather per wave, open nodes handed from loaded to idle ranks through ddo_solver_export_open /
+    ddo_solver_import_open, solution gathered from the rank that holds it): device ranks and oracle ranks exchange the same nodes and
+    follow the same trajectories; every rank returns the optimum with an independent set of that size."""
+    inst = gnp(130, 0.35, 11)
+    pb = Misp(inst)
+    dev = _run(world, lambda: ParNoCachingSolverLel(pb, FixedWidth(6), wave_size=8), new_protocol=True)
+    oracle = O.OracleMisp(inst)
+    ref = _run(world, lambda: O.OracleStepper(oracle, 8, 6), new_protocol=True)
+    single = oracle.solve("wave", k=8, width=6)
+    assert sum(d["nodes_sent"] for d in dev) == sum(d["nodes_received"] for d in dev) > 0
+    for d, r in zip(dev, ref):
+        assert d["is_exact"] and d["best_lb"] == d["best_ub"] == single["best_value"] == d["best_value"]
+        assert (d["waves"], d["collectives"], d["handoffs"], d["nodes_sent"], d["nodes_received"], d["explored"], d["expanded"]) == \
+            (r["waves"], r["collectives"], r["handoffs"], r["nodes_sent"], r["nodes_received"], r["explored"], r["expanded"])
+        chosen = [v for v, x in d["solution"] if x == 1]
+        assert len(chosen) == single["best_value"] and all(not inst.has_edge(a, b) for i, a in enumerate(chosen) for b in chosen[i + 1:])

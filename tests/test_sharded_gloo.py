@@ -26,7 +26,7 @@ def _worker(rank, world, port, spec, out_dir):
 
     import oracle_lib as O
     from ddo_b200.instances import gnp, parse_dimacs, random_max2sat
-    from ddo_b200.sharded import sharded_maximize, torch_allreduce_max
+    from ddo_b200.sharded import TorchComm, sharded_maximize, torch_allreduce_max
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -36,7 +36,8 @@ def _worker(rank, world, port, spec, out_dir):
     else:
         oracle = O.OracleMisp(gnp(*spec["gnp"]) if "gnp" in spec else parse_dimacs((ROOT / "tests" / "golden" / "misp" / spec["file"]).read_text()))
     stepper = O.OracleStepper(oracle, spec["wave"], spec.get("width"))
-    res = sharded_maximize(stepper, rank, world, torch_allreduce_max())
+    comm = torch_allreduce_max() if spec.get("round1") else TorchComm()
+    res = sharded_maximize(stepper, rank, world, comm, rebalance=spec.get("rebalance", True))
     res.update(rank=rank, explored=stepper.explored(), expanded=stepper.expanded())
     Path(out_dir, f"r{rank}.json").write_text(json.dumps(res))
     dist.destroy_process_group()
@@ -61,8 +62,16 @@ def test_sharded_bnb_agrees_with_single_process(world, tmp_path):
     # the shards partition the root's open nodes: every rank explored the root + a share, none did all the work alone
     assert all(r["explored"] >= 1 for r in res)
     assert sum(r["explored"] for r in res) >= single["explored"] - (0) and max(r["explored"] for r in res) < single["explored"] + world
-    # one collective per wave (two allreduce calls of 3 x int64: incumbent/termination, then bound), nothing on the data path
-    assert all(r["collectives"] <= 2 * r["waves"] + 1 for r in res)
+    # ONE collective per wave (an all-gather of 4 x int64 per rank: incumbent, bound, fringe length, held solution), nothing on the data path
+    assert all(r["collectives"] <= r["waves"] + 1 for r in res)
+    # every rank returns the optimum WITH a solution of that value (the bound and the solution travel together)
+    from ddo_b200.instances import gnp as _g
+    inst = _g(*spec["gnp"])
+    for r in res:
+        assert r["best_value"] == single["best_value"]
+        chosen = [v for v, x in r["solution"] if x == 1]
+        assert len(chosen) == single["best_value"] and all(not inst.has_edge(a, b) for i, a in enumerate(chosen) for b in chosen[i + 1:])
+    assert all(r["solution"] == res[0]["solution"] for r in res)
 
 
 def test_sharded_bnb_known_optimum_dimacs(tmp_path):
@@ -82,3 +91,34 @@ def test_sharded_bnb_max2sat_agrees_with_single_process(tmp_path):
     for r in res:
         assert r["is_exact"] and r["best_lb"] == r["best_ub"] == single["best_value"]
     assert all(r["explored"] >= 1 for r in res) and max(r["explored"] for r in res) < single["explored"] + 2
+
+
+def test_handoff_plan_is_deterministic_and_refills_the_empty_ranks():
+    from ddo_b200.sharded import MAX_HANDOFF, handoff_plan
+
+    assert handoff_plan([100, 100, 100, 100]) == []  # balanced: nothing moves
+    assert handoff_plan([0, 0]) == [] and handoff_plan([5000]) == []
+    plan = handoff_plan([0, 40000, 3, 20000])
+    assert plan == handoff_plan([0, 40000, 3, 20000])
+    assert {d for _, d, _ in plan} == {0, 2} and {s for s, _, _ in plan} <= {1, 3}
+    assert all(0 < c <= MAX_HANDOFF for _, _, c in plan) and len({s for s, _, _ in plan}) == len(plan)  # a donor serves one receiver per wave
+    assert handoff_plan([10, 1200]) == [(1, 0, 298)]  # half of what the donor holds above the mean (605)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rebalancing_moves_open_nodes_and_keeps_the_optimum(world, tmp_path):
+    """An instance whose static deal is lopsided: with the hand-off the ranks exchange open nodes (state, value, bound, depth, full path) and
+    still prove the single-process optimum; the explored totals stay close to the single-process search; the round-1 protocol (static deal,
+    two allreduce per wave) gives the same optimum."""
+    import oracle_lib as O
+    from ddo_b200.instances import gnp
+
+    spec = {"gnp": (120, 0.3, 3), "wave": 4, "width": 4}
+    single = O.OracleMisp(gnp(*spec["gnp"])).solve("wave", k=spec["wave"], width=spec["width"])
+    res = _run(world, spec, tmp_path)
+    assert all(r["is_exact"] and r["best_lb"] == r["best_ub"] == single["best_value"] == r["best_value"] for r in res)
+    assert sum(r["nodes_sent"] for r in res) == sum(r["nodes_received"] for r in res) > 0
+    old = _run(world, dict(spec, round1=True), tmp_path)
+    assert all(r["is_exact"] and r["best_lb"] == single["best_value"] for r in old)
+    # balance: the busiest rank of the rebalanced run explores less than the busiest rank of the static deal
+    assert max(r["explored"] for r in res) <= max(r["explored"] for r in old)
