@@ -165,7 +165,7 @@ def run_ours(args, rank, world, local_rank):
             comp = solver.maximize(max_waves=wl.max_waves)
             res = {"best_lb": solver.best_lower_bound(), "best_ub": solver.best_upper_bound(), "is_exact": comp.is_exact}
         else:
-            res = sharded_maximize(solver, rank, world, comm, max_waves=wl.max_waves)
+            res = solver.maximize_sharded(comm, max_waves=wl.max_waves)  # ddo_solver_maximize_sharded: the whole protocol in one native call per rank
             res = {k: res[k] for k in ("best_lb", "best_ub", "is_exact", "handoffs", "nodes_sent", "collectives")}
         wall = time.perf_counter() - t0
         s1 = solver.stats()

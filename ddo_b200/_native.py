@@ -60,8 +60,10 @@ SYMBOLS = {
     "ddo_solver_wave": (C.c_int, [_P, _P, C.POINTER(C.c_int64 * 3)]),
     "ddo_solver_set_lower_bound": (C.c_int, [_P, C.c_int64]),
     "ddo_solver_retain_share": (C.c_int, [_P, C.c_int32, C.c_int32]),
-    "ddo_solver_export_open": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
-    "ddo_solver_import_open": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ddo_solver_node_words": (C.c_int32, [_P]),
+    "ddo_solver_export_open": (C.c_int, [_P, C.c_int32, _P, C.POINTER(C.c_int32)]),
+    "ddo_solver_import_open": (C.c_int, [_P, C.c_int32, _P]),
+    "ddo_solver_maximize_sharded": (C.c_int, [_P, _P, C.c_double, C.c_uint64, C.c_int32, C.POINTER(C.c_int64 * 8)]),
     "ddo_solver_finish": (C.c_int, [_P]),
     "ddo_solver_best_lower_bound": (C.c_int64, [_P]),
     "ddo_solver_best_upper_bound": (C.c_int64, [_P]),
@@ -73,6 +75,8 @@ SYMBOLS = {
     "ddo_comm_unique_id": (C.c_int, [_P]),
     "ddo_comm_init": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_int, C.POINTER(_P)]),
     "ddo_comm_destroy": (None, [_P]),
+    "ddo_comm_size": (C.c_int32, [_P]),
+    "ddo_comm_rank": (C.c_int32, [_P]),
     "ddo_comm_allreduce_max": (C.c_int, [_P, _P, C.c_int32]),
     "ddo_comm_allgather": (C.c_int, [_P, _P, C.c_int32, _P]),
     "ddo_comm_send": (C.c_int, [_P, _P, C.c_int64, C.c_int32]),

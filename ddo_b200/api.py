@@ -443,41 +443,30 @@ class ParNoCachingSolverLel:
     def retain_share(self, rank: int, nranks: int):
         N.check(N.lib().ddo_solver_retain_share(self.h, rank, nranks), "ddo_solver_retain_share")
 
-    # work hand-off between ranks (ddo_b200/sharded.py): packed open nodes as one int64 array
+    # work hand-off between ranks (ddo_b200/sharded.py): packed open nodes, ddo_solver_node_words() int64 words each
+    def node_words(self) -> int:
+        return int(N.lib().ddo_solver_node_words(self.h))
+
     def export_open(self, max_nodes: int) -> np.ndarray:
-        """Up to `max_nodes` open nodes (every other one of the best 2 * max_nodes) as rows of int64:
-        [value, ub, depth, state words ..., (variable, value) x nb_variables]."""
-        n, w = self.problem.nb_variables(), self.problem.words
-        states = np.zeros((max(max_nodes, 1), w), dtype=np.uint64)
-        values = np.zeros(max(max_nodes, 1), dtype=np.int64)
-        ubs = np.zeros(max(max_nodes, 1), dtype=np.int64)
-        depths = np.zeros(max(max_nodes, 1), dtype=np.int32)
-        paths = np.zeros((max(max_nodes, 1), n, 2), dtype=np.int32)
+        rows = np.zeros((max(max_nodes, 1), self.node_words()), dtype=np.int64)
         cnt = C.c_int32(0)
-        N.check(N.lib().ddo_solver_export_open(self.h, max_nodes, _ptr(states), _ptr(values), _ptr(ubs), _ptr(depths), _ptr(paths), C.byref(cnt)), "ddo_solver_export_open")
-        k = cnt.value
-        out = np.zeros((k, 3 + w + n), dtype=np.int64)
-        out[:, 0], out[:, 1], out[:, 2] = values[:k], ubs[:k], depths[:k]
-        out[:, 3:3 + w] = states[:k].view(np.int64)
-        out[:, 3 + w:] = (paths[:k, :, 0].astype(np.int64) << 32) | (paths[:k, :, 1].astype(np.int64) & 0xFFFFFFFF)
-        return out
+        N.check(N.lib().ddo_solver_export_open(self.h, max_nodes, _ptr(rows), C.byref(cnt)), "ddo_solver_export_open")
+        return rows[:cnt.value].copy()
 
     def import_open(self, rows: np.ndarray):
-        n, w = self.problem.nb_variables(), self.problem.words
-        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3 + w + n)
-        k = rows.shape[0]
-        if k == 0:
-            return
-        states = np.ascontiguousarray(rows[:, 3:3 + w]).view(np.uint64)
-        values, ubs = np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1])
-        depths = np.ascontiguousarray(rows[:, 2].astype(np.int32))
-        paths = np.zeros((k, n, 2), dtype=np.int32)
-        paths[:, :, 0] = (rows[:, 3 + w:] >> 32).astype(np.int32)
-        paths[:, :, 1] = (rows[:, 3 + w:] & 0xFFFFFFFF).astype(np.uint32).view(np.int32).reshape(k, n)
-        N.check(N.lib().ddo_solver_import_open(self.h, k, _ptr(states), _ptr(values), _ptr(ubs), _ptr(depths), _ptr(paths)), "ddo_solver_import_open")
+        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, self.node_words())
+        if rows.shape[0]:
+            N.check(N.lib().ddo_solver_import_open(self.h, rows.shape[0], _ptr(rows)), "ddo_solver_import_open")
 
-    def node_words(self) -> int:
-        return 3 + self.problem.words + self.problem.nb_variables()
+    def maximize_sharded(self, comm, time_budget_s: float = 0.0, max_waves: int = 0, rebalance: bool = True):
+        """`Solver::maximize` of a fringe-sharded search: ONE native call per rank (ddo_solver_maximize_sharded); `comm` is a
+        ddo_b200.sharded.NativeComm.  Returns the dict ddo_b200.sharded.sharded_maximize returns."""
+        out = (C.c_int64 * 8)()
+        N.check(N.lib().ddo_solver_maximize_sharded(self.h, comm.h, time_budget_s, max_waves, int(rebalance), C.byref(out)), "ddo_solver_maximize_sharded")
+        sol = self.best_solution()
+        return {"best_lb": int(out[0]), "best_ub": int(out[1]), "is_exact": bool(out[2]), "waves": int(out[3]), "collectives": int(out[4]), "handoffs": int(out[5]),
+                "nodes_sent": int(out[6]), "nodes_received": int(out[7]), "best_value": self.best_value(),
+                "solution": None if sol is None else [(d.variable, d.value) for d in sol]}
 
     def finish(self):
         N.lib().ddo_solver_finish(self.h)

@@ -214,16 +214,28 @@ int ddo_solver_wave(ddo_solver* s, const volatile int32_t* cutoff_flag, int64_t 
 }
 int ddo_solver_set_lower_bound(ddo_solver* s, int64_t lb) { if (!s) return DDO_ERR_INVALID; if (lb > s->s->best_lb) s->s->best_lb = lb; return DDO_OK; }
 int ddo_solver_retain_share(ddo_solver* s, int32_t rank, int32_t nranks) { GUARD_BEGIN if (!s) return DDO_ERR_INVALID; return s->s->retain_share(rank, nranks); GUARD_END }
-int ddo_solver_export_open(ddo_solver* s, int32_t max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count) {
+int32_t ddo_solver_node_words(const ddo_solver* s) { return s ? s->s->node_words() : 0; }
+int ddo_solver_export_open(ddo_solver* s, int32_t max_nodes, int64_t* rows, int32_t* count) {
     GUARD_BEGIN
     if (!s) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return s->s->export_open(max_nodes, states, values, ubs, depths, paths, count);
+    return s->s->export_open(max_nodes, rows, count);
     GUARD_END
 }
-int ddo_solver_import_open(ddo_solver* s, int32_t count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths) {
+int ddo_solver_import_open(ddo_solver* s, int32_t count, const int64_t* rows) {
     GUARD_BEGIN
     if (!s) { set_error("null argument"); return DDO_ERR_INVALID; }
-    return s->s->import_open(count, states, values, ubs, depths, paths);
+    return s->s->import_open(count, rows);
+    GUARD_END
+}
+int ddo_solver_maximize_sharded(ddo_solver* s, ddo_comm* comm, double time_budget_s, uint64_t max_waves, int32_t rebalance, int64_t out[8]) {
+    GUARD_BEGIN
+    if (!s || !comm || !out) { set_error("null argument"); return DDO_ERR_INVALID; }
+    ShardComm cm;
+    cm.ctx = comm; cm.nranks = ddo_comm_size(comm); cm.rank = ddo_comm_rank(comm);
+    cm.allgather = [](void* c, const int64_t* v, int32_t n, int64_t* r) { return ddo_comm_allgather((ddo_comm*)c, v, n, r); };
+    cm.send = [](void* c, const void* b, int64_t n, int32_t p) { return ddo_comm_send((ddo_comm*)c, b, n, p); };
+    cm.recv = [](void* c, void* b, int64_t n, int32_t p) { return ddo_comm_recv((ddo_comm*)c, b, n, p); };
+    return s->s->maximize_sharded(cm, time_budget_s, max_waves, rebalance != 0, out);
     GUARD_END
 }
 int ddo_solver_finish(ddo_solver* s) {
@@ -250,7 +262,7 @@ int ddo_solver_best_solution(const ddo_solver* s, ddo_decision* out, int32_t* le
     return DDO_OK;
 }
 uint64_t ddo_solver_explored(const ddo_solver* s) { return s->s->explored; }
-uint64_t ddo_solver_fringe_len(const ddo_solver* s) { return s->s->fringe.len(); }
+uint64_t ddo_solver_fringe_len(const ddo_solver* s) { return s->s->open_len(); }
 int ddo_solver_stats(const ddo_solver* s, double stats[8]) {
     if (!s || !stats) return DDO_ERR_INVALID;
     stats[0] = (double)s->s->expanded; stats[1] = (double)s->s->transitions; stats[2] = (double)s->s->compilations; stats[3] = (double)s->s->waves;

@@ -121,6 +121,9 @@ void ddo_comm_destroy(ddo_comm* c) {
     delete c;
 }
 
+int32_t ddo_comm_size(const ddo_comm* c) { return c ? c->nranks : 0; }
+int32_t ddo_comm_rank(const ddo_comm* c) { return c ? c->rank : -1; }
+
 int ddo_comm_allreduce_max(ddo_comm* c, int64_t* values, int32_t count) {
     if (!c || !values || count < 1) return fail("ddo_comm_allreduce_max: invalid argument", DDO_ERR_INVALID);
     cudaSetDevice(c->device);

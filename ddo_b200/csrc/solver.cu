@@ -780,10 +780,10 @@ int Solver::retain_share(int rank, int nranks) {
 }
 
 
-int Solver::export_open(int max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count) {
-    if (max_nodes < 0 || !states || !values || !ubs || !depths || !paths || !count) { set_error("export_open: invalid argument"); return DDO_ERR_INVALID; }
+int Solver::export_open(int max_nodes, int64_t* rows, int32_t* count) {
+    if (max_nodes < 0 || !rows || !count) { set_error("export_open: invalid argument"); return DDO_ERR_INVALID; }
     if (pre_valid) unpop();
-    const int W = words, PWN = (n_vars + 63) / 64;
+    const int W = words, PWN = (n_vars + 63) / 64, RW = node_words();
     struct Keep { std::vector<uint64_t> state, bits; NoDupFringe::Item it; };
     std::vector<Keep> keep;
     int out = 0;
@@ -792,12 +792,15 @@ int Solver::export_open(int max_nodes, uint64_t* states, int64_t* values, int64_
         const int id = fringe.pop();
         const NoDupFringe::Item it = fringe.item(id);
         if (idx & 1) {  // every other node of the MaxUB order leaves
-            std::memcpy(states + (size_t)out * W, fringe.state(id), (size_t)W * 8);
-            values[out] = it.value; ubs[out] = it.ub == INT32_MAX ? INT64_MAX : it.ub; depths[out] = it.depth;
+            int64_t* r = rows + (size_t)out * RW;
+            std::memset(r, 0, (size_t)RW * 8);
+            r[0] = it.value; r[1] = it.ub == INT32_MAX ? INT64_MAX : it.ub; r[2] = it.depth;
+            std::memcpy(r + 3, fringe.state(id), (size_t)W * 8);
             path.clear();
             full_path(it.rec, fringe.bits(id), it.depth, path);
             if ((int)path.size() != it.depth) { set_error("export_open: inconsistent path"); return DDO_ERR_INVALID; }
-            std::copy(path.begin(), path.end(), paths + (size_t)out * n_vars);
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(r + 3 + W);
+            for (int j = 0; j < it.depth; ++j) d16[j] = (uint16_t)(path[j].variable | (path[j].value == eng->bit_value[1] ? 0x8000 : 0));
             ++out;
         } else {
             Keep k; k.state.assign(fringe.state(id), fringe.state(id) + W); k.bits.assign(fringe.bits(id), fringe.bits(id) + PWN); k.it = it;
@@ -809,25 +812,151 @@ int Solver::export_open(int max_nodes, uint64_t* states, int64_t* values, int64_
     return DDO_OK;
 }
 
-int Solver::import_open(int count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths) {
-    if (count < 0 || (count > 0 && (!states || !values || !ubs || !depths || !paths))) { set_error("import_open: invalid argument"); return DDO_ERR_INVALID; }
-    const int W = words, PWN = (n_vars + 63) / 64;
+int Solver::import_open(int count, const int64_t* rows) {
+    if (count < 0 || (count > 0 && !rows)) { set_error("import_open: invalid argument"); return DDO_ERR_INVALID; }
+    if (pre_valid) unpop();  // the imported nodes compete with the ones popped ahead of time
+    const int W = words, PWN = (n_vars + 63) / 64, RW = node_words();
     std::vector<uint64_t> bits(PWN);
     for (int i = 0; i < count; ++i) {
-        const int d = depths[i];
+        const int64_t* r = rows + (size_t)i * RW;
+        const int d = (int)r[2];
         if (d < 0 || d > n_vars) { set_error("import_open: bad depth"); return DDO_ERR_INVALID; }
-        if ((int64_t)ubs[i] <= best_lb) continue;  // parallel.rs:460-461: nothing to gain from this node any more
+        if (r[1] <= best_lb) continue;  // parallel.rs:460-461: nothing to gain from this node any more
         PathRec pr; pr.parent_rec = -1; pr.base_depth = 0; pr.vars.resize(d);
         std::fill(bits.begin(), bits.end(), 0ull);
+        const uint16_t* d16 = reinterpret_cast<const uint16_t*>(r + 3 + W);
         for (int j = 0; j < d; ++j) {
-            const ddo_decision& dec = paths[(size_t)i * n_vars + j];
-            pr.vars[j] = dec.variable;
-            if (dec.value == eng->bit_value[1]) bits[j >> 6] |= 1ull << (j & 63);
+            pr.vars[j] = d16[j] & 0x7FFF;
+            if (d16[j] & 0x8000) bits[j >> 6] |= 1ull << (j & 63);
         }
         recs.push_back(std::move(pr));
-        const int64_t ub = ubs[i];
-        fringe.push(states + (size_t)i * W, (int32_t)values[i], ub >= INT32_MAX ? INT32_MAX : (int32_t)ub, d, (int)recs.size() - 1, bits.data(), PWN);
+        fringe.push(reinterpret_cast<const uint64_t*>(r + 3), (int32_t)r[0], r[1] >= INT32_MAX ? INT32_MAX : (int32_t)r[1], d, (int)recs.size() - 1, bits.data(), PWN);
     }
+    return DDO_OK;
+}
+
+// The fringe-sharded search as ONE native call (the protocol of ddo_b200/sharded.py, which drives CPU stand-ins in
+// the tests): root DD on every rank, deterministic deal, then per wave one all-gather of {best_lb, bound of the best open node, open nodes,
+// objective of the held solution} and -- only when the fringes are out of balance -- point-to-point hand-offs of packed open nodes.  At the
+// end the solution travels from the lowest rank that holds one of the optimal value to the others.
+// out[8] = best_lb, best_ub, is_exact, waves, collectives, hand-offs, nodes sent, nodes received.
+int Solver::maximize_sharded(const ShardComm& cm, double time_budget_s, uint64_t max_waves, bool rebalance, int64_t out[8]) {
+    const int world = cm.nranks, rank = cm.rank;
+    int rc = init(true);
+    if (rc != DDO_OK) return rc;
+    const double t_end = time_budget_s > 0 ? now_ms() + time_budget_s * 1000.0 : 0;
+    deadline_ms = t_end;
+    pipeline = true; pre_valid = false;
+    volatile int32_t cutoff = 0;
+    int64_t o3[3];
+    rc = wave(&cutoff, o3);  // the root DD: identical on every rank
+    if (rc != DDO_OK && rc != DDO_CUTOFF) return rc;
+    if (pre_valid) unpop();
+    rc = retain_share(rank, world);
+    if (rc != DDO_OK) return rc;
+    int64_t lb = best_lb, top = INT64_MIN, glob_ub = INT64_MAX;
+    uint64_t nwaves = 1, colls = 0, handoffs = 0, sent = 0, received = 0;
+    std::vector<int64_t> mine(4), all((size_t)4 * world), rows;
+    const int RW = node_words();
+    bool cut = rc == DDO_CUTOFF;
+    for (;;) {
+        mine[0] = best_lb; mine[1] = top; mine[2] = (int64_t)open_len(); mine[3] = has_sol ? sol_value : INT64_MIN;
+        if (cut) mine[2] = -1;  // a rank that ran out of time stops everybody
+        rc = cm.allgather(cm.ctx, mine.data(), 4, all.data());  // ---- the ONE collective of the wave
+        if (rc != DDO_OK) return rc;
+        ++colls;
+        int64_t g_lb = INT64_MIN, g_top = INT64_MIN, total = 0; bool any_cut = false;
+        std::vector<int64_t> lens(world);
+        for (int r = 0; r < world; ++r) {
+            g_lb = std::max(g_lb, all[4 * r]); g_top = std::max(g_top, all[4 * r + 1]);
+            if (all[4 * r + 2] < 0) any_cut = true;
+            lens[r] = std::max<int64_t>(0, all[4 * r + 2]); total += lens[r];
+        }
+        if (g_lb > best_lb) best_lb = g_lb;
+        lb = best_lb;
+        if (g_top != INT64_MIN) glob_ub = g_top;
+        if (any_cut) { aborted = true; break; }
+        if (total == 0) break;
+        if (rebalance) {
+            // the same plan on every rank: the emptiest ranks (below a quarter of the mean) are refilled by the fullest ones, a donor serves
+            // one receiver per wave and gives half of what it holds above the mean
+            const double mean = (double)total / world;
+            std::vector<int> lo(world), hi(world);
+            for (int r = 0; r < world; ++r) lo[r] = hi[r] = r;
+            std::stable_sort(lo.begin(), lo.end(), [&](int a, int b) { return lens[a] < lens[b]; });
+            std::stable_sort(hi.begin(), hi.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+            std::vector<char> used(world, 0);
+            if (world >= 2 && total >= 2 * world)
+                for (int dst : lo) {
+                    if ((double)lens[dst] * 4 >= mean) break;
+                    for (int src : hi) {
+                        if (src == dst || used[src] || (double)lens[src] <= mean || lens[src] < 2 * kMinDonor) continue;
+                        const int64_t cnt = (int64_t)std::min<double>({(double)kMaxHandoff, ((double)lens[src] - mean) / 2 + 1, (double)((lens[src] - kMinDonor) / 2),
+                                                                       std::max<double>(mean - (double)lens[dst], 1.0)});
+                        if (cnt > 0) {
+                            used[src] = 1; lens[src] -= cnt; lens[dst] += cnt;
+                            if (rank == src) {
+                                rows.resize((size_t)cnt * RW);
+                                int32_t k = 0;
+                                rc = export_open((int)cnt, rows.data(), &k);
+                                if (rc != DDO_OK) return rc;
+                                int64_t kk = k;
+                                rc = cm.send(cm.ctx, &kk, 8, dst);
+                                if (rc == DDO_OK && k) rc = cm.send(cm.ctx, rows.data(), (int64_t)k * RW * 8, dst);
+                                if (rc != DDO_OK) return rc;
+                                ++handoffs; sent += (uint64_t)k;
+                            } else if (rank == dst) {
+                                int64_t kk = 0;
+                                rc = cm.recv(cm.ctx, &kk, 8, src);
+                                if (rc != DDO_OK) return rc;
+                                if (kk) {
+                                    rows.resize((size_t)kk * RW);
+                                    rc = cm.recv(cm.ctx, rows.data(), kk * RW * 8, src);
+                                    if (rc == DDO_OK) rc = import_open((int)kk, rows.data());
+                                    if (rc != DDO_OK) return rc;
+                                }
+                                ++handoffs; received += (uint64_t)kk;
+                            }
+                        }
+                        break;
+                    }
+                }
+        }
+        rc = wave(&cutoff, o3);  // a rank with an empty fringe returns immediately (top = INT64_MIN)
+        if (rc == DDO_CUTOFF) { cut = true; top = INT64_MIN; continue; }
+        if (rc != DDO_OK) return rc;
+        top = o3[1];
+        ++nwaves;
+        if ((max_waves && nwaves >= max_waves) || (t_end > 0 && now_ms() >= t_end)) cut = true;  // the others learn it from the next gather
+    }
+    pipeline = false; deadline_ms = 0;
+    if (pre_valid) unpop();
+    if (aborted) fringe.clear(); else best_ub = best_lb;
+    if (aborted && glob_ub != INT64_MAX) best_ub = std::max(glob_ub, best_lb);
+    // the solution travels once, from the lowest rank that holds one of the optimal value
+    int owner = -1;
+    for (int r = 0; r < world && owner < 0; ++r) if (all[4 * r + 3] == best_lb) owner = r;
+    if (owner >= 0 && world > 1) {
+        std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });
+        if (rank == owner) {
+            int64_t k = (int64_t)best_sol.size();
+            for (int r = 0; r < world; ++r) if (r != owner) {
+                rc = cm.send(cm.ctx, &k, 8, r);
+                if (rc == DDO_OK && k) rc = cm.send(cm.ctx, best_sol.data(), k * (int64_t)sizeof(ddo_decision), r);
+                if (rc != DDO_OK) return rc;
+            }
+        } else {
+            int64_t k = 0;
+            rc = cm.recv(cm.ctx, &k, 8, owner);
+            if (rc != DDO_OK) return rc;
+            best_sol.resize((size_t)k);
+            if (k) { rc = cm.recv(cm.ctx, best_sol.data(), k * (int64_t)sizeof(ddo_decision), owner); if (rc != DDO_OK) return rc; }
+            has_sol = true; sol_value = best_lb;
+        }
+    }
+    std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });
+    out[0] = best_lb; out[1] = best_ub; out[2] = !aborted; out[3] = (int64_t)nwaves; out[4] = (int64_t)colls; out[5] = (int64_t)handoffs;
+    out[6] = (int64_t)sent; out[7] = (int64_t)received;
     return DDO_OK;
 }
 

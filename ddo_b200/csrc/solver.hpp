@@ -93,6 +93,15 @@ private:
     static uint64_t hash_state(const uint64_t* st, int W);
 };
 
+// the collectives a sharded search needs, as plain function pointers (ddo_comm_* in production; anything else in tests)
+struct ShardComm {
+    void* ctx; int nranks, rank;
+    int (*allgather)(void* ctx, const int64_t* values, int32_t count, int64_t* recv);
+    int (*send)(void* ctx, const void* buf, int64_t bytes, int32_t peer);
+    int (*recv)(void* ctx, void* buf, int64_t bytes, int32_t peer);
+};
+constexpr int64_t kMaxHandoff = 8192, kMinDonor = 64;  // open nodes per hand-off; what a donor keeps for itself
+
 struct Solver {
     Engine* eng; int model_kind; int n_vars, words;
     std::vector<uint64_t> root_state; int64_t root_value;  // Problem::initial_state / initial_value
@@ -128,8 +137,12 @@ struct Solver {
     // refilled by a loaded one).  export_open pops up to 2 * max_nodes of the best open nodes, gives away every other one (so donor and
     // receiver keep nodes of the same quality) and re-queues the rest; a node travels as packed state, value, upper bound, depth and its
     // FULL decision path.  import_open queues such nodes (each gets a path record of its own).
-    int export_open(int max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths, int32_t* count);
-    int import_open(int count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths, const ddo_decision* paths);
+    // packed node: int64 words [value, ub (INT64_MAX: none), depth, state words ..., decisions four per word: 16 bits each = variable | bit << 15]
+    int node_words() const { return 3 + words + (n_vars + 3) / 4; }
+    int export_open(int max_nodes, int64_t* rows, int32_t* count);
+    int import_open(int count, const int64_t* rows);
+    int maximize_sharded(const ShardComm& cm, double time_budget_s, uint64_t max_waves, bool rebalance, int64_t out[8]);
+    size_t open_len() const { return fringe.len() + (pre_valid ? pre_items.size() : 0); }  // nodes popped ahead of time are still open
 };
 
 }  // namespace ddo

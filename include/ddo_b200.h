@@ -166,13 +166,13 @@ int ddo_solver_set_lower_bound(ddo_solver*, int64_t best_lb);          /* adopt 
 int ddo_solver_retain_share(ddo_solver*, int32_t rank, int32_t nranks);
 /* Work hand-off between ranks.  The reference's workers pull from ONE shared fringe (parallel.rs:500-559), so its load balances itself;
  * here a rank whose fringe runs dry is refilled by a loaded one.  export_open pops up to 2 * max_nodes of the best open nodes, hands out
- * every other one (donor and receiver keep nodes of the same quality) and re-queues the rest.  A node travels as packed state
- * [state_words], value, upper bound (INT64_MAX: none yet), depth and its full decision path (paths has nb_variables slots per node, the
- * first `depth` are used).  import_open queues such nodes (those whose bound no longer beats the incumbent are dropped, parallel.rs:461). */
-int ddo_solver_export_open(ddo_solver*, int32_t max_nodes, uint64_t* states, int64_t* values, int64_t* ubs, int32_t* depths, ddo_decision* paths,
-                           int32_t* count);
-int ddo_solver_import_open(ddo_solver*, int32_t count, const uint64_t* states, const int64_t* values, const int64_t* ubs, const int32_t* depths,
-                           const ddo_decision* paths);
+ * every other one (donor and receiver keep nodes of the same quality) and re-queues the rest.  A node travels as ddo_solver_node_words()
+ * int64 words: value, upper bound (INT64_MAX: none yet), depth, the packed state [state_words], then its full decision path, four
+ * decisions per word, 16 bits each (variable | path bit << 15; path bit 1 = YES / T).  import_open queues such nodes (those whose bound no
+ * longer beats the incumbent are dropped, parallel.rs:461). */
+int32_t ddo_solver_node_words(const ddo_solver*);
+int ddo_solver_export_open(ddo_solver*, int32_t max_nodes, int64_t* rows, int32_t* count);
+int ddo_solver_import_open(ddo_solver*, int32_t count, const int64_t* rows);
 int ddo_solver_finish(ddo_solver*);                                    /* best_ub = best_lb when the fringe is empty (parallel.rs:512-515) */
 int64_t ddo_solver_best_lower_bound(const ddo_solver*);                /* solver.rs:83 */
 int64_t ddo_solver_best_upper_bound(const ddo_solver*);                /* solver.rs:86 */
@@ -189,6 +189,8 @@ int ddo_solver_stats(const ddo_solver*, double stats[8]);
  * NCCL over NVLink, loaded at run time (libnccl.so.2); buffers are HOST memory, staged through the communicator's device scratch.
  * Bootstrap: rank 0 calls ddo_comm_unique_id and hands the 128 bytes to the other ranks by any out-of-band channel. */
 typedef struct ddo_comm ddo_comm;
+int32_t ddo_comm_size(const ddo_comm*);
+int32_t ddo_comm_rank(const ddo_comm*);
 int ddo_comm_unique_id(void* id128);
 int ddo_comm_init(int32_t nranks, int32_t rank, const void* id128, int device, ddo_comm** out);
 void ddo_comm_destroy(ddo_comm*);
@@ -199,6 +201,11 @@ int ddo_comm_allgather(ddo_comm*, const int64_t* values, int32_t count, int64_t*
 /* point-to-point hand-off of packed open nodes (ddo_solver_export_open / import_open) and of the final solution */
 int ddo_comm_send(ddo_comm*, const void* buf, int64_t bytes, int32_t peer);
 int ddo_comm_recv(ddo_comm*, void* buf, int64_t bytes, int32_t peer);
+/* Solver::maximize of a fringe-sharded search as ONE call per rank (what a Rust host binds): root DD on every rank, deterministic deal,
+ * one ddo_comm_allgather per wave, hand-offs of open nodes when `rebalance` != 0, solution gathered from the rank that holds it
+ * (ddo_solver_best_value / best_solution afterwards).  out[8] = best_lb, best_ub, is_exact, waves, collectives, hand-offs, nodes sent,
+ * nodes received.  Every rank must call it with the same arguments. */
+int ddo_solver_maximize_sharded(ddo_solver*, ddo_comm*, double time_budget_s, uint64_t max_waves, int32_t rebalance, int64_t out[8]);
 
 #ifdef __cplusplus
 }

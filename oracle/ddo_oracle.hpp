@@ -1083,41 +1083,60 @@ public:
         if (wave.empty()) { out3[0] = best_lb; out3[2] = 0; return true; }
         best_ub = top_ub;
         stats.waves += 1;
-        auto& mdds = mdds_;
+        // The K workers of the wave are emulated with ONE decision diagram (a wave of 2 048 sub-problems with a few dozen wide DDs would
+        // otherwise keep gigabytes of arenas alive): what a worker's DD is asked for later -- its best exact value and solution, its
+        // cutset -- is taken right after its compilation and applied in wave order, exactly as when every worker kept its own DD.
+        Mdd<S, Hash, Eq>& mdd = mdds_[0];
         EmptyCache<S> cache;
+        struct Found { size_t i; isize v; std::optional<Solution> sol; };
+        auto remember = [&](std::vector<Found>& out, size_t i, isize floor_) {  // only a DD that beats the snapshot can become the incumbent
+            const isize v = mdd.best_exact_value().value_or(ISIZE_MIN);
+            if (v > floor_) out.push_back(Found{i, v, mdd.best_exact_solution()});
+        };
+        auto apply = [&](std::vector<Found>& found) {  // maybe_update_best in wave order: the first DD reaching a new maximum keeps its solution
+            for (auto& f : found) if (f.v > best_lb) { best_lb = f.v; best_sol = std::move(f.sol); sol_value = f.v; }
+        };
         // restricted
         isize lb = best_lb;
         std::vector<char> exact(wave.size(), 0);
         std::vector<size_t> widths(wave.size());
+        std::vector<Found> found;
         for (size_t i = 0; i < wave.size(); ++i) {
             widths[i] = c_.width->max_width(wave[i]);
             CompilationInput<S> in{CompilationType::Restricted, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
             Completion comp;
-            if (!mdds[i].compile(in, &comp)) return false;
+            if (!mdd.compile(in, &comp)) return false;
             exact[i] = comp.is_exact;
-            account(mdds[i]);
+            account(mdd);
+            remember(found, i, lb);
         }
-        for (size_t i = 0; i < wave.size(); ++i) maybe_update_best(mdds[i]);
+        apply(found);
         // relaxed
         lb = best_lb;
-        std::vector<char> relaxed_done(wave.size(), 0);
+        found.clear();
+        std::vector<std::pair<size_t, std::vector<SubProblem<S>>>> cutsets;
         for (size_t i = 0; i < wave.size(); ++i) {
             if (exact[i]) continue;
             CompilationInput<S> in{CompilationType::Relaxed, c_.problem, c_.relaxation, c_.ranking, c_.cutoff, widths[i], &wave[i], lb, &cache, c_.dominance};
             Completion comp;
-            if (!mdds[i].compile(in, &comp)) return false;
-            relaxed_done[i] = 1;
+            if (!mdd.compile(in, &comp)) return false;
             exact[i] = comp.is_exact;
-            account(mdds[i]);
+            account(mdd);
+            remember(found, i, lb);
+            if (!comp.is_exact) {
+                cutsets.emplace_back(i, std::vector<SubProblem<S>>());
+                auto& cs = cutsets.back().second;
+                const isize ub = wave[i].ub;
+                mdd.drain_cutset([&](SubProblem<S> n) {
+                    n.ub = std::min(ub, n.ub);
+                    if (n.ub > lb) cs.push_back(std::move(n));  // (lb <= the final incumbent of the wave: the filter below is the binding one)
+                });
+            }
         }
-        for (size_t i = 0; i < wave.size(); ++i) if (relaxed_done[i]) maybe_update_best(mdds[i]);
-        for (size_t i = 0; i < wave.size(); ++i) {
-            if (!relaxed_done[i] || exact[i]) continue;
-            isize ub = wave[i].ub, blb = best_lb;
-            mdds[i].drain_cutset([&](SubProblem<S> n) {
-                n.ub = std::min(ub, n.ub);
-                if (n.ub > blb) c_.fringe->push(std::move(n));
-            });
+        apply(found);
+        for (auto& pr : cutsets) {
+            const isize blb = best_lb;
+            for (auto& n : pr.second) if (n.ub > blb) c_.fringe->push(std::move(n));
         }
         trace.push_back({wave.size(), best_lb, c_.fringe->len(), top_ub});
         out3[0] = best_lb; out3[2] = c_.fringe->is_empty() ? 0 : 1;

@@ -19,6 +19,7 @@ struct MispHandle {
     MispRanking rk;
     MispHandle(size_t n, const isize* w, size_t m, const int32_t* s, const int32_t* d) : pb(n, w, m, s, d), rlx(&pb) {}
     size_t abi_words() const { return pb.words; }  // uint64 words of a packed state at the ABI
+    static isize other_decision() { return 0; }    // NO (the decision a 0 path bit stands for)
     State state_from_abi(const uint64_t* p, size_t /*depth*/) const { BitState s; s.w.assign(p, p + pb.words); return s; }
     void state_to_abi(const State& s, uint64_t* p) const { std::memcpy(p, s.w.data(), pb.words * 8); }
 };
@@ -30,6 +31,7 @@ struct M2Handle {
     Max2SatRanking rk;
     M2Handle(size_t n, const std::vector<M2Clause>& c) : pb(n, c), rlx(&pb) {}
     size_t abi_words() const { return (pb.nb_vars + 1) / 2; }
+    static isize other_decision() { return -1; }   // F
     State state_from_abi(const uint64_t* p, size_t depth) const {
         const int32_t* q = (const int32_t*)p;
         M2State s{depth, std::vector<isize>(pb.nb_vars)};
@@ -221,29 +223,34 @@ template <class H> void stepper_state(Stepper<H>* s, int64_t out[6]) {
     auto& w = *s->solver;
     out[0] = w.best_lb; out[1] = w.best_ub; out[2] = (int64_t)w.fringe_len(); out[3] = (int64_t)w.stats.explored; out[4] = (int64_t)w.stats.expanded; out[5] = w.best_sol.has_value();
 }
-// rows of int64: [value, ub, depth, state words ..., (variable << 32 | value) x nb_variables] -- the layout of ddo_b200/api.py export_open
+// packed open nodes, the layout of ddo_solver_export_open: int64 words [value, ub, depth, state words ..., decisions four per word, 16 bits
+// each = variable | path bit << 15]; path bit 1 = the model's "positive" decision (MISP YES = 1, MAX2SAT T = +1), 0 = the other one
+template <class H> size_t stepper_node_words(Stepper<H>* s) { return 3 + s->h->abi_words() + (s->h->pb.nb_variables() + 3) / 4; }
 template <class H> int32_t stepper_export(Stepper<H>* s, int32_t max_nodes, int64_t* rows) {
-    const size_t W = s->h->abi_words(), n = s->h->pb.nb_variables(), RW = 3 + W + n;
+    const size_t W = s->h->abi_words(), RW = stepper_node_words(s);
     auto nodes = s->solver->export_open((size_t)max_nodes);
     for (size_t i = 0; i < nodes.size(); ++i) {
         int64_t* r = rows + i * RW;
         std::memset(r, 0, RW * 8);
         r[0] = nodes[i].value; r[1] = nodes[i].ub; r[2] = (int64_t)nodes[i].depth;
         s->h->state_to_abi(*nodes[i].state, (uint64_t*)(r + 3));
-        for (size_t j = 0; j < nodes[i].path.size(); ++j) r[3 + W + j] = ((int64_t)nodes[i].path[j].variable << 32) | ((int64_t)nodes[i].path[j].value & 0xFFFFFFFFll);
+        uint16_t* d16 = (uint16_t*)(r + 3 + W);
+        for (size_t j = 0; j < nodes[i].path.size(); ++j) d16[j] = (uint16_t)(nodes[i].path[j].variable | (nodes[i].path[j].value == 1 ? 0x8000 : 0));
     }
     return (int32_t)nodes.size();
 }
 template <class H> void stepper_import(Stepper<H>* s, int32_t count, const int64_t* rows) {
     using S = typename H::State;
-    const size_t W = s->h->abi_words(), n = s->h->pb.nb_variables(), RW = 3 + W + n;
+    const size_t W = s->h->abi_words(), RW = stepper_node_words(s);
+    const isize other = s->h->other_decision();
     std::vector<SubProblem<S>> nodes;
     for (int32_t i = 0; i < count; ++i) {
         const int64_t* r = rows + (size_t)i * RW;
         SubProblem<S> sp;
         sp.value = r[0]; sp.ub = r[1]; sp.depth = (size_t)r[2];
         sp.state = std::make_shared<const S>(s->h->state_from_abi((const uint64_t*)(r + 3), sp.depth));
-        for (size_t j = 0; j < sp.depth; ++j) sp.path.push_back(Decision{(size_t)(r[3 + W + j] >> 32), (isize)(int32_t)(r[3 + W + j] & 0xFFFFFFFFll)});
+        const uint16_t* d16 = (const uint16_t*)(r + 3 + W);
+        for (size_t j = 0; j < sp.depth; ++j) sp.path.push_back(Decision{(size_t)(d16[j] & 0x7FFF), (d16[j] & 0x8000) ? (isize)1 : other});
         nodes.push_back(std::move(sp));
     }
     s->solver->import_open(std::move(nodes));
@@ -331,6 +338,7 @@ void oracle_m2s_stepper_state(void* s, int64_t out[6]) { stepper_state((Stepper<
 void oracle_m2s_stepper_set_lb(void* s, int64_t lb) { ((Stepper<M2Handle>*)s)->solver->set_lower_bound(lb); }
 void oracle_m2s_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((Stepper<M2Handle>*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
 void oracle_m2s_stepper_finish(void* s) { ((Stepper<M2Handle>*)s)->solver->finish(); }
+int32_t oracle_m2s_stepper_node_words(void* s) { return (int32_t)stepper_node_words((Stepper<M2Handle>*)s); }
 int32_t oracle_m2s_stepper_export(void* s, int32_t max_nodes, int64_t* rows) { return stepper_export((Stepper<M2Handle>*)s, max_nodes, rows); }
 void oracle_m2s_stepper_import(void* s, int32_t count, const int64_t* rows) { stepper_import((Stepper<M2Handle>*)s, count, rows); }
 
@@ -413,6 +421,7 @@ void oracle_misp_stepper_set_lb(void* s, int64_t lb) { ((MispStepper*)s)->solver
 void oracle_misp_stepper_retain_share(void* s, int32_t rank, int32_t nranks) { ((MispStepper*)s)->solver->retain_share((size_t)rank, (size_t)nranks); }
 void oracle_misp_stepper_finish(void* s) { ((MispStepper*)s)->solver->finish(); }
 int64_t oracle_misp_stepper_sol_value(void* s) { return ((MispStepper*)s)->solver->sol_value; }
+int32_t oracle_misp_stepper_node_words(void* s) { return (int32_t)stepper_node_words((MispStepper*)s); }
 int32_t oracle_misp_stepper_export(void* s, int32_t max_nodes, int64_t* rows) { return stepper_export((MispStepper*)s, max_nodes, rows); }
 void oracle_misp_stepper_import(void* s, int32_t count, const int64_t* rows) { stepper_import((MispStepper*)s, count, rows); }
 // solution of the stepper's solver: returns its length (-1: none), decisions sorted by variable; *value = objective of that solution

@@ -75,6 +75,7 @@ def lib():
         _lib.oracle_misp_stepper_retain_share.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         _lib.oracle_misp_stepper_state.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 6)]
         for pre in ("misp", "m2s"):
+            getattr(_lib, f"oracle_{pre}_stepper_node_words").argtypes = [C.c_void_p]
             getattr(_lib, f"oracle_{pre}_stepper_export").argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
             getattr(_lib, f"oracle_{pre}_stepper_import").argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         _lib.oracle_misp_stepper_solution.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
@@ -379,7 +380,7 @@ class OracleStepper:
 
     # work hand-off / solution gather of ddo_b200.sharded (same packed rows as the device solver's export_open / import_open)
     def node_words(self):
-        return 3 + self.o.words + self.o.inst.n
+        return int(self._f("stepper_node_words")(self.h))
 
     def export_open(self, max_nodes):
         rows = np.zeros((max(max_nodes, 1), self.node_words()), dtype=np.int64)
