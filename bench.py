@@ -405,7 +405,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--wave", type=int, default=2048, help="open sub-problems popped per wave and per GPU")
-    ap.add_argument("--batch-cap", type=int, default=512, help="DDs the general (layer-by-layer) engine compiles in lock-step")
+    ap.add_argument("--batch-cap", type=int, default=4096, help="DD slots of the general (layer-by-layer) engine: how many DDs a batch may hold in lock-step when the log pool allows (it holds 512 full-depth DDs; deeper sub-problems log fewer layers)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="TimeBudget of the CPU baseline sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="misp", choices=["misp", "max2sat"], help="misp = BASELINE config 2 (the headline metric); max2sat = config 3")
@@ -416,7 +416,7 @@ def main():
     args = ap.parse_args()
     if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave -- one DD per SM (m2_finish is one CTA per DD)
         if args.wave == 2048: args.wave = 148
-        if args.batch_cap == 512: args.batch_cap = 148
+        if args.batch_cap == 4096: args.batch_cap = 148
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

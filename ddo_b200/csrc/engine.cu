@@ -113,6 +113,10 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     model = m; device = dev; cutset_type = cutset; n_vars = m->n; abi_words = m->words;
     K = batch_cap; Wcap = (int)((std::max<uint64_t>(max_width_cap, 2) + 1) & ~1ull); C = 2 * Wcap; T = next_pow2(std::max(3 * Wcap, 64)); S = m->S;
     Lmax = m->n + 1; PW = (Lmax + 63) / 64;
+    Klog = std::min(K, 512);
+    if (const char* e = getenv("DDO_LOG_SLOTS")) Klog = std::max(1, std::min(K, atoi(e)));
+    if (cutset == DDO_FRONTIER) Klog = K;  // the frontier records are per slot and per layer: no pooling
+    pool_layers = (size_t)Klog * Lmax; Lcur = Lmax; staged_layers = Lmax;
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -121,7 +125,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     const size_t KW = (size_t)K * Wcap, KC = (size_t)K * C, KL = (size_t)K * Lmax;
     ev.K = K; ev.Wcap = Wcap; ev.C = C; ev.T = T; ev.Lmax = Lmax; ev.n = m->n; ev.S = S; ev.PW = PW;
     ev.HN = 64 * S; ev.unit_weights = m->unit_weights; ev.weight = m->d_weight; ev.nc = m->d_nc;
-    ALLOC(ev.ctl, K); ALLOC(ev.active, 4); ALLOC(ev.tile_off_e, K + 1); ALLOC(ev.tile_off_c, K + 1); ALLOC(ev.finish_counter, 4);
+    ALLOC(ev.ctl, K); ALLOC(ev.active, 4); ALLOC(ev.tile_off_e, K + 1); ALLOC(ev.tile_off_c, K + 1); ALLOC(ev.finish_counter, 4); ALLOC(ev.fin_list, 2 * (size_t)K); ALLOC(ev.fin_cnt, 4);
     for (int b = 0; b < 2; ++b) { ALLOC(ev.cur_state[b], KW * S); ALLOC(ev.cur_val[b], KW); ALLOC(ev.cur_flag[b], KW); ALLOC(ev.vb[b], KW); }
     ALLOC(ev.cur_rub, KW);
     ALLOC(ev.cand_state, KC * S); ALLOC(ev.cand_rep, KC); ALLOC(ev.cand_first, KC); ALLOC(ev.cand_agg, KC); ALLOC(ev.cand_inex, KC);
@@ -149,17 +153,18 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     if (const char* e = getenv("DDO_DD_PROF")) if (atoi(e)) { ALLOC(ev.dd_prof, 16); CUDA_TRY(cudaMemsetAsync(ev.dd_prof, 0, 128, stream)); }
     if (const char* e = getenv("DDO_DD_GENERIC")) ev.dd_generic = atoi(e) != 0;
     ALLOC(ev.table, (size_t)2 * K * T); /* k_dd alternates between two tables by layer parity */ ALLOC(ev.vhist, (size_t)K * 64 * S); ALLOC(ev.ucount, K);
-    ALLOC(ev.plog, KL * Wcap); ALLOC(ev.clog, KL * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
+    ALLOC(ev.plog, pool_layers * Wcap); ALLOC(ev.clog, pool_layers * C); ALLOC(ev.nlog, KL); ALLOC(ev.vlog, KL); ALLOC(ev.rslog, KL * 2);
     ALLOC(ev.lel_state, KW * S); ALLOC(ev.lel_val, KW); ALLOC(ev.lel_rub, KW);
     ALLOC(ev.cs_ub, KW); ALLOC(ev.cs_marked, KW);
     ALLOC(ev.best_path, (size_t)K * PW); ALLOC(ev.best_exact_path, (size_t)K * PW);
-    // drain buffers
-    out_cap = KW;
+    // drain buffers: the cutsets of one batch (at most Klog slots' worth of records: a batch of more, shallower DDs drains fewer nodes each)
+    out_cap = (size_t)Klog * Wcap;
     ev.fc_node = nullptr; ev.fc_ub = nullptr; ev.fc_aux = nullptr; ev.fc_cap = 0; d_out.tt = nullptr;
     if (cutset == DDO_FRONTIER) { int fr = alloc_frontier(&ev.fc_node, &ev.fc_ub, &ev.fc_aux, &ev.fc_cap); if (fr != DDO_OK) return fr; }
     ALLOC(d_out.state, out_cap * S); ALLOC(d_out.val, out_cap); ALLOC(d_out.ub, out_cap); ALLOC(d_out.dd, out_cap); ALLOC(d_out.path, out_cap * PW);
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
+    if (const char* e = getenv("DDO_FINISH_SPLIT_MIN")) finish_split_min = atoi(e);
     if (const char* e = getenv("DDO_DD")) dd_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_DD_CS")) dd_cs = atoi(e);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
@@ -231,9 +236,16 @@ int Engine::reserve_roots(int count) {
     return DDO_OK;
 }
 
+int Engine::slots_for(int layers_needed) const {
+    if (cutset_type == DDO_FRONTIER) return std::min(K, Klog);
+    return (int)std::min<size_t>((size_t)K, pool_layers / (size_t)std::max(1, layers_needed));
+}
+
 int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
     if (count < 1 || count > root_cap) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
     const int words = abi_words;
+    staged_layers = 1;
+    for (int i = 0; i < count; ++i) staged_layers = std::max(staged_layers, n_vars - depths[i] + 1);
     for (int i = 0; i < count; ++i) {
         if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
         if (values[i] < -(1ll << 30) || values[i] > (1ll << 30)) { set_error("root value outside the 31-bit device range"); return DDO_ERR_UNSUPPORTED; }
@@ -402,9 +414,14 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
     const int flat_grid = (int)std::min<long long>(max_tiles, (long long)E->num_sms * 8);
     const int CHUNK = E->layer_chunk;  // layers launched between two polls of the device's `active` counter (and of the cutoff flag)
     const bool pdl = E->pdl_enabled && !E->profiling;  // the profiling events between launches serialise the stream anyway
-    for (int t = 0; t < E->Lmax; ++t) {
+    for (int t = 0; t < E->Lcur; ++t) {
         if (use_cl) CUDA_TRY(launch_k(pdl, k_finish_cl<S>, dim3(slots * FCL_CS), dim3(FCL_NT), E->finish_cl_smem, st, ev, t, E->finish_cl_kcap));
-        else CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(slots), dim3(1024), E->finish_smem, st, ev, t));
+        else if (slots < E->finish_split_min) CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(slots), dim3(1024), E->finish_smem, st, ev, t, 0));
+        else {  // a large batch: the wide DDs one per SM, the narrow ones five to an SM (kernels.cuh, k_finish_s)
+            CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(std::min(slots, E->num_sms)), dim3(1024), E->finish_smem, st, ev, t, 1));
+            CUDA_TRY(launch_k(pdl, k_finish_s<S>, dim3(std::min(slots, E->num_sms * 6)), dim3(256), 0, st, ev, t, slots));
+            ++g_kernel_launches;
+        }
         E->prof_mark(1);
         if (use_c1) CUDA_TRY(launch_k(pdl, k_compact1<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         else CUDA_TRY(launch_k(pdl, k_compact<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
@@ -413,7 +430,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         else CUDA_TRY(launch_k(pdl, k_expand<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         E->prof_mark(0);
         g_kernel_launches += 3; ++E->layer_steps;
-        if ((t % CHUNK) == CHUNK - 1 || t == E->Lmax - 1) {
+        if ((t % CHUNK) == CHUNK - 1 || t == E->Lcur - 1) {
             E->bytes_d2h += sizeof(int); CUDA_TRY(cudaMemcpyAsync(E->h_active, ev.active, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             if (*E->h_active <= 0) break;
@@ -438,6 +455,10 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
 }
 
 static int compile_impl(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
+    // the log stride of this batch: the layers its deepest DD can have (every kernel and every host-side read of the logs uses ev.Lmax)
+    E->Lcur = std::min(E->Lmax, std::max(1, E->staged_layers));
+    if ((size_t)slots * (size_t)E->Lcur > E->pool_layers) { set_error("batch too large for the log pool: slots x (nb_variables - depth + 1) layers exceed it (see Engine::slots_for)"); return DDO_ERR_CAPACITY; }
+    E->ev.Lmax = E->Lcur;
     const EV& ev = E->ev;
     CUDA_TRY(cudaSetDevice(E->device));
     CUDA_TRY(cudaMemsetAsync(ev.table, 0xFF, (size_t)slots * E->T * 8, E->stream));
@@ -564,7 +585,7 @@ int Engine::best_solution(int index, int exact, ddo_decision* out, int32_t* len)
     std::vector<uint64_t> bits(PW);
     std::vector<int32_t> vars(Lmax);
     bytes_d2h += (unsigned long long)(PW * 8); CUDA_TRY(cudaMemcpyAsync(bits.data(), (exact ? ev.best_exact_path : ev.best_path) + (size_t)index * PW, PW * 8, cudaMemcpyDeviceToHost, stream));
-    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lcur, (size_t)Lcur * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int i = 0; i < L; ++i) {  // reference order: terminal -> root (clean.rs:337-341)
         const int tt = L - 1 - i;
@@ -582,8 +603,8 @@ int Engine::layer_trace(int index, int32_t* vars, int32_t* widths, int cap) {
     const DDCtl& c = h_ctl[index];
     const int L = std::max(0, c.t_term);  // expanded layers: 0..t_term-1
     std::vector<int32_t> v(Lmax), w(Lmax);
-    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(v.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
-    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(w.data(), ev.nlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(v.data(), ev.vlog + (size_t)index * Lcur, (size_t)Lcur * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(w.data(), ev.nlog + (size_t)index * Lcur, (size_t)Lcur * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int i = 0; i < L && i < cap; ++i) { vars[i] = v[i]; widths[i] = w[i]; }
     return L;
@@ -618,6 +639,7 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
     CUDA_TRY(cudaStreamSynchronize(stream));
     const int total = ((int32_t*)h_counts)[last_count];
     if (total == 0) { prof_used = 0; return 0; }
+    if ((size_t)total > out_cap) { prof_used = 0; set_error("cutsets of the batch exceed the drain buffers (lower batch_cap or raise DDO_LOG_SLOTS)"); return DDO_ERR_CAPACITY; }
     if (pw > 8) CUDA_TRY(cudaMemsetAsync(d_out.path, 0, (size_t)total * pw * 8, stream));
     const dim3 grid((Wcap + 255) / 256, last_count);
     switch (S) {
@@ -629,7 +651,7 @@ int Engine::drain_all(int count, const int64_t* ub_cap, const int64_t* lb_filter
     ++g_kernel_launches;
     prof_mark(4);
     if (!h_out_state) {
-        const size_t KW = (size_t)K * Wcap;
+        const size_t KW = out_cap;
         CUDA_TRY(cudaMallocHost(&h_out_state, KW * S * 8));
         CUDA_TRY(cudaMallocHost(&h_out_val, KW * 4));
         CUDA_TRY(cudaMallocHost(&h_out_ub, KW * 4));
@@ -708,16 +730,16 @@ int Engine::drain_all_frontier(int count, const int64_t* ub_cap, const int64_t* 
 // branching variables of every DD of the last batch in ONE copy: [slots][Lmax] (a per-DD copy + synchronize costs ~10 us each, and a wide
 // wave drains hundreds of DDs)
 int Engine::fetch_vars_all(int slots, std::vector<int32_t>& vars) {
-    vars.resize((size_t)slots * Lmax);
-    bytes_d2h += (unsigned long long)((size_t)slots * Lmax * 4);
-    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog, (size_t)slots * Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    vars.resize((size_t)slots * Lcur);
+    bytes_d2h += (unsigned long long)((size_t)slots * Lcur * 4);
+    CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog, (size_t)slots * Lcur * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return DDO_OK;
 }
 
 int Engine::fetch_vars(int index, std::vector<int32_t>& vars) {
     vars.resize(Lmax);
-    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lmax, (size_t)Lmax * 4, cudaMemcpyDeviceToHost, stream));
+    bytes_d2h += (unsigned long long)((size_t)Lmax * 4); CUDA_TRY(cudaMemcpyAsync(vars.data(), ev.vlog + (size_t)index * Lcur, (size_t)Lcur * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return DDO_OK;
 }

@@ -61,6 +61,7 @@ struct EV {
     const uint64_t* nc;
     DDCtl* ctl;
     int* active;  // number of DDs still compiling
+    int* fin_list; int* fin_cnt;  // [2][K] DD slots whose next finish is wide / narrow, [2] their counts (written by the plan step of the previous layer)
     int* tile_off_e; int* tile_off_c; unsigned int* finish_counter;  // per-layer work plan of k_expand / k_compact (exclusive tile offsets, [K+1])
     // staged roots
     uint64_t* root_state; int32_t* root_val; int32_t* root_depth; int32_t* root_width;
@@ -123,6 +124,11 @@ struct Engine {
     int32_t bit_value[2] = {0, 1};     // decision value of a path bit: MISP NO / YES; MAX2SAT F = -1 / T = +1
     int device = 0;
     int K = 0, Wcap = 0, C = 0, T = 0, Lmax = 0, S = 0, PW = 0;
+    // The parent / child logs (12 B per node and layer: 60 of the 65 MB of a DD slot at W = 10 000, n = 500) are ONE pool of `pool_layers`
+    // layer records shared by the DDs of a batch: a batch of sub-problems deep in the search needs n - depth + 1 layers per DD, not n + 1,
+    // so the same memory holds several times more DDs in lock-step (Lcur = log stride of the current batch, set by stage_roots).
+    int Klog = 0, Lcur = 0; size_t pool_layers = 0; int staged_layers = 0;
+    virtual int slots_for(int layers_needed) const;  // DD slots a batch whose deepest DD has `layers_needed` layers may use
     int cutset_type = DDO_LAST_EXACT_LAYER;
     int num_sms = 148;
     int layer_chunk = 16;      // layer steps launched between two host polls of the `active` counter / cutoff flag (DDO_LAYER_CHUNK)
@@ -133,6 +139,7 @@ struct Engine {
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
     bool dd_enabled = false; int dd_cs = 0; bool dd_attr_set = false; int dd_min_cs = 0;  // persistent whole-DD kernel k_dd (opt-in: DDO_DD=1; see DESIGN.md section 4b for where it stands); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
     unsigned long long dd_launches = 0;
+    int finish_split_min = 160;  // batches of at least this many DD slots run the finish in two size classes (k_finish + k_finish_s; DDO_FINISH_SPLIT_MIN)
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

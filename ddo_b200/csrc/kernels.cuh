@@ -192,7 +192,8 @@ __global__ void k_init(EV ev, int count, int comp_type, long long best_lb, int d
             ev.cand_rank[cb] = ((uint32_t)pc << 20) | rank_pad<S>(got, mk);
         }
         ev.cand_slot[cb] = NONE32; ev.uflag[cb] = 0;
-        if (k == 0) *ev.active = count;
+        if (k == 0) { *ev.active = count; ev.fin_cnt[0] = 0; ev.fin_cnt[1] = count; }
+        ev.fin_list[ev.K + k] = k;
     }
     // vertex histogram of the (single) root state, consumed by k_finish(0)
     for (int u = threadIdx.x; u < S * 64; u += blockDim.x)
@@ -656,10 +657,12 @@ __device__ unsigned long long member_key(const uint64_t* st, int first_rank) {
 }
 
 // Keys / status of the distinct candidates live in shared memory when 2*Wcap of them fit (ev.smem_keys), else in global scratch.
-template <int S>
-__device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long long* keys, uint8_t* stat) {
-    constexpr int NT = 1024;
-    const int k = blockIdx.x;
+// The two size classes of the finish of a large batch: DDs whose coming layer has more than FIN_SMALL_C candidates (k_finish: one DD per
+// SM) and the others (k_finish_s: five to six per SM).  The DDs of each class are LISTED by the plan step of the previous layer (a DD
+// that is done is in neither list, so the tail of a batch -- a few long DDs among hundreds of finished ones -- costs no empty CTAs).
+constexpr int FIN_SMALL_C = 2048;
+template <int S, int NT>
+__device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long long* keys, uint8_t* stat, int k) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DDCtl* ctl = ev.ctl + k;
     const int status = ctl->status;
@@ -838,16 +841,17 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
                 }
                 __syncthreads();
                 {
-                    int c2[2]; int s2 = 0;
+                    constexpr int PER = 2048 / NT;
+                    int c2[PER]; int s2 = 0;
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) { const int bi = nbins - 1 - (2 * tid + q); c2[q] = bi >= 0 ? (int)sm.hist[bi] : 0; s2 += c2[q]; }
+                    for (int q = 0; q < PER; ++q) { const int bi = nbins - 1 - (PER * tid + q); c2[q] = bi >= 0 ? (int)sm.hist[bi] : 0; s2 += c2[q]; }
                     int tot;
                     const int before = block_excl_scan(s2, &tot, sm.scan);
                     if (before < need && need <= before + s2) {
                         int acc = before;
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            if (acc < need && need <= acc + c2[q]) { sm.misc[0] = nbins - 1 - (2 * tid + q); sm.misc[1] = acc; sm.misc[2] = c2[q]; }
+                        for (int q = 0; q < PER; ++q) {
+                            if (acc < need && need <= acc + c2[q]) { sm.misc[0] = nbins - 1 - (PER * tid + q); sm.misc[1] = acc; sm.misc[2] = c2[q]; }
                             acc += c2[q];
                         }
                     }
@@ -1060,25 +1064,15 @@ __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long l
     }
 }
 
+// work plan of the two flat kernels that follow a finish: the last CTA to finish scans the per-DD tile counts
 template <int S>
-__global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
-    pdl_enter();
-    __shared__ FinishSmem sm;
-    __shared__ int s_last;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    {
-        unsigned long long* keys; uint8_t* stat;
-        if (ev.smem_keys) { keys = reinterpret_cast<unsigned long long*>(dyn_smem); stat = dyn_smem + (size_t)ev.C * 8; }
-        else { keys = ev.gkeys + (size_t)blockIdx.x * ev.C; stat = ev.ustat + (size_t)blockIdx.x * ev.C; }
-        finish_body<S>(ev, t, sm, keys, stat);
-    }
-    // ---- work plan of the two flat kernels that follow: the last CTA to finish scans the per-DD tile counts --------------------
+__device__ void finish_plan(const EV& ev, FinishSmem& sm, int* s_last, int count) {  // count = DD slots of the batch
     constexpr int G = S / 2, PER_TILE = 256 / G;
-    const int tid = threadIdx.x, count = gridDim.x;
+    const int tid = threadIdx.x;
     __syncthreads();
-    if (tid == 0) { __threadfence(); s_last = (atomicAdd(ev.finish_counter, 1u) == (unsigned)count - 1u); }
+    if (tid == 0) { __threadfence(); *s_last = (atomicAdd(ev.finish_counter, 1u) == gridDim.x - 1u); }
     __syncthreads();
-    if (!s_last) return;
+    if (!*s_last) return;
     __threadfence();
     const volatile DDCtl* vc = ev.ctl;
     const int per = (count + blockDim.x - 1) / blockDim.x;
@@ -1098,7 +1092,71 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t) {
         oe += st == ST_ACTIVE ? (vc[k].n_cur + PER_TILE - 1) / PER_TILE : 0;
         oc += (st == ST_ACTIVE || st == ST_TERMINAL) ? (vc[k].ncand + PER_TILE - 1) / PER_TILE : 0;
     }
-    if (tid == 0) { ev.tile_off_e[count] = tote; ev.tile_off_c[count] = totc; *ev.finish_counter = 0; }
+    // the finish of the NEXT layer: its candidates are two per node of the layer decided now (a waiting twin forks with its primary's)
+    int nb = 0, ns = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        if (st == ST_DONE) continue;
+        const int src = st == ST_WAITING ? vc[k].primary : k;
+        if (st == ST_WAITING && (src < 0 || vc[src].status == ST_DONE || vc[src].status == ST_TERMINAL)) continue;  // its primary ended without a cut: the twin never forks
+        (st != ST_TERMINAL && 2 * vc[src].n_cur > FIN_SMALL_C) ? ++nb : ++ns;
+    }
+    int totb, tots;
+    int ob = block_excl_scan(nb, &totb, sm.scan);
+    int os = block_excl_scan(ns, &tots, sm.scan);
+    for (int k = lo; k < hi; ++k) {
+        const int st = vc[k].status;
+        if (st == ST_DONE) continue;
+        const int src = st == ST_WAITING ? vc[k].primary : k;
+        if (st == ST_WAITING && (src < 0 || vc[src].status == ST_DONE || vc[src].status == ST_TERMINAL)) continue;
+        if (st != ST_TERMINAL && 2 * vc[src].n_cur > FIN_SMALL_C) ev.fin_list[ob++] = k; else ev.fin_list[ev.K + os++] = k;
+    }
+    if (tid == 0) { ev.tile_off_e[count] = tote; ev.tile_off_c[count] = totc; *ev.finish_counter = 0; ev.fin_cnt[0] = totb; ev.fin_cnt[1] = tots; }
+}
+
+// size_class 0: every DD of the batch (blockIdx.x = DD slot), followed by the work plan; 1: the listed wide DDs, no plan (k_finish_s runs
+// next and writes it)
+template <int S>
+__global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t, int size_class) {
+    pdl_enter();
+    __shared__ FinishSmem sm;
+    __shared__ int s_last;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    {
+        unsigned long long* keys; uint8_t* stat;
+        if (ev.smem_keys) { keys = reinterpret_cast<unsigned long long*>(dyn_smem); stat = dyn_smem + (size_t)ev.C * 8; }
+        else { keys = ev.gkeys + (size_t)blockIdx.x * ev.C; stat = ev.ustat + (size_t)blockIdx.x * ev.C; }
+        if (size_class == 0) finish_body<S, 1024>(ev, t, sm, keys, stat, blockIdx.x);
+        else {
+            const int nb = ev.fin_cnt[0];
+            for (int j = blockIdx.x; j < nb; j += gridDim.x) {
+                const int k = ev.fin_list[j];
+                if (!ev.smem_keys) { keys = ev.gkeys + (size_t)k * ev.C; stat = ev.ustat + (size_t)k * ev.C; }
+                finish_body<S, 1024>(ev, t, sm, keys, stat, k);
+                __syncthreads();
+            }
+        }
+    }
+    if (size_class == 0) finish_plan<S>(ev, sm, &s_last, gridDim.x);
+}
+
+// k_finish_s: the finish of the NARROW DDs of a large batch.  k_finish holds the cut keys of up to 2 * Wcap candidates in shared memory
+// and runs 1024 threads, so one DD occupies an SM; a batch of a thousand DDs whose layers hold a few hundred nodes then takes seven
+// rounds of CTAs per layer step for work a quarter of a CTA could do.  Here a DD with at most FIN_SMALL_C candidates gets 256 threads
+// and 18 KB of keys: five to six DDs per SM.
+template <int S>
+__global__ void __launch_bounds__(256) k_finish_s(EV ev, int t, int slots) {
+    pdl_enter();
+    __shared__ FinishSmem sm;
+    __shared__ int s_last;
+    __shared__ __align__(16) unsigned long long s_keys[FIN_SMALL_C];
+    __shared__ __align__(16) uint8_t s_stat[FIN_SMALL_C];
+    const int ns = ev.fin_cnt[1];
+    for (int j = blockIdx.x; j < ns; j += gridDim.x) {
+        finish_body<S, 256>(ev, t, sm, s_keys, s_stat, ev.fin_list[ev.K + j]);
+        __syncthreads();
+    }
+    finish_plan<S>(ev, sm, &s_last, slots);
 }
 
 // =================================================================================================================

@@ -162,6 +162,7 @@ int M2Engine::create_m2s(const M2Model* m, int dev, uint64_t max_width_cap, int 
     const int NW = m->NW;
     S = NW / 2;  // uint64 words of a device state row (the drain buffers and root staging of the base class are sized with it)
     Lmax = m->n + 1; PW = (Lmax + 63) / 64;
+    Klog = K; pool_layers = (size_t)K * Lmax; Lcur = Lmax;  // (this engine keeps one full-depth log per slot)
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));

@@ -430,7 +430,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     float ms = 0;
     int rc;
     double tr_small = 0, tr_general = 0; const uint64_t tr_steps0 = eng->layer_steps, tr_exp0 = expanded;  // DDO_WAVE_TRACE (diagnostics only)
-    const int cap = eng->K;  // DDs the general engine compiles in lock-step
+    int cap = eng->K;  // DDs the general engine compiles in lock-step (set below from the depth of the sub-problems that need it)
     std::vector<uint64_t> w2, s2; std::vector<int64_t> v2; std::vector<int32_t> d2;
     auto stage_subset = [&](const int* idx, int oc) -> int {
         w2.resize(oc); s2.resize((size_t)oc * W); v2.resize(oc); d2.resize(oc);
@@ -557,7 +557,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                 cur_dd = j;
                 const int lel = frontier ? std::max(0, eng->h_ctl[j].t_term) : eng->h_ctl[j].lel;  // layers whose variables the paths may use
                 pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
-                p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lmax, vars.begin() + (size_t)j * eng->Lmax + lel);
+                p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lcur, vars.begin() + (size_t)j * eng->Lcur + lel);
             }
             if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
             p_bits.resize(p_bits.size() + PWN, 0ull);
@@ -568,6 +568,11 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
         return DDO_OK;
     };
+    {   // the deeper the sub-problems, the fewer layers their DDs log, the more of them fit the log pool (Engine::slots_for)
+        int lneed = 1;
+        for (int i : ov) lneed = std::max(lneed, n_vars - depths[i] + 1);
+        cap = std::max(1, eng->slots_for(lneed));
+    }
     bool dual = eng->dual_enabled && cap >= 2;
     for (int i : ov) if (widths[i] < 1) dual = false;
     const int chunk = dual ? cap / 2 : cap;
