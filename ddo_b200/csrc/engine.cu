@@ -165,6 +165,7 @@ int Engine::create(const MispModel* m, int dev, uint64_t max_width_cap, int batc
     ALLOC(d_out.count, K + 1); ALLOC(d_out.offset, K + 1); ALLOC(d_out.loc, KW);
     ALLOC(d_ub_cap, K); ALLOC(d_lb_filter, K);
     if (const char* e = getenv("DDO_FINISH_SPLIT_MIN")) finish_split_min = atoi(e);
+    if (const char* e = getenv("DDO_EXPAND2")) expand2 = atoi(e) != 0;
     if (const char* e = getenv("DDO_DD")) dd_enabled = atoi(e) != 0;
     if (const char* e = getenv("DDO_DD_CS")) dd_cs = atoi(e);
     if (const char* e = getenv("DDO_DUAL")) dual_enabled = atoi(e) != 0;
@@ -426,7 +427,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         if (use_c1) CUDA_TRY(launch_k(pdl, k_compact1<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         else CUDA_TRY(launch_k(pdl, k_compact<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         E->prof_mark(2);
-        if (use_e1) CUDA_TRY(launch_k(pdl, k_expand1<S>, dim3(e1_grid), dim3(256), e1_smem, st, ev, t, slots));
+        if (E->expand2) CUDA_TRY(launch_k(pdl, k_expand2<S>, dim3(E->num_sms * 3), dim3(256), 0, st, ev, t, slots));
+        else if (use_e1) CUDA_TRY(launch_k(pdl, k_expand1<S>, dim3(e1_grid), dim3(256), e1_smem, st, ev, t, slots));
         else CUDA_TRY(launch_k(pdl, k_expand<S>, dim3(flat_grid), dim3(256), 0, st, ev, t, slots));
         E->prof_mark(0);
         g_kernel_launches += 3; ++E->layer_steps;

@@ -139,6 +139,7 @@ struct Engine {
     int expand1_min = 1; bool expand1_attr_set = false;  // thread-per-node expansion (k_expand1) for batches of >= expand1_min DD slots
     bool dd_enabled = false; int dd_cs = 0; bool dd_attr_set = false; int dd_min_cs = 0;  // persistent whole-DD kernel k_dd (opt-in: DDO_DD=1; see DESIGN.md section 4b for where it stands); dd_cs: forced cluster size (DDO_DD_CS), 0 = by batch size
     unsigned long long dd_launches = 0;
+    bool expand2 = false;        // warp-autonomous expansion kernel k_expand2 (DDO_EXPAND2=1; measured slower than k_expand1: 279 vs 167 ms per config-2 solve -- its per-warp histogram flushes cost more global atomics than the block barriers they remove)
     int finish_split_min = 160;  // batches of at least this many DD slots run the finish in two size classes (k_finish + k_finish_s; DDO_FINISH_SPLIT_MIN)
     int finish_cl_max = 128; int finish_cl_kcap = 0; size_t finish_cl_smem = 0; bool finish_cl_attr_set = false;  // cluster finish: used for batches of <= finish_cl_max DD slots
     cudaStream_t stream = nullptr;

@@ -612,6 +612,190 @@ __global__ void __launch_bounds__(256, DDO_EXPAND1_MINB) k_expand1(EV ev, int t,
 }
 
 // =================================================================================================================
+// k_expand2: the thread-per-node expansion of k_expand1 with WARP-autonomous bookkeeping.  The round-1 profile of k_expand1 in the batched
+// regime put 39 % of its stall samples on block barriers (per-tile counter reset / flush, claim-mask prefix, histogram hand-over) and 12 %
+// on the binary search over the work plan that every thread repeated.  Here a warp owns a contiguous range of 32-node units of the plan:
+//   * the claimed (= distinct) rows are staged in a 32-row buffer of the warp's own, bit-transposed when it fills, and counted into
+//     per-lane registers (lane b of column j counts vertex 32 j + b); the registers are flushed to the DD's vertex histogram only when
+//     the warp moves on to another DD or ends -- no block barrier anywhere in the kernel;
+//   * expanded / transition / distinct counters are warp ballots, added to the DD's control block at the same moments;
+//   * the plan is searched once per warp and then walked forward.
+// Everything written (candidate rows and records, hash table, histogram, counters) is what k_expand1 writes.
+// =================================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256, 3) k_expand2(EV ev, int t, int count) {
+    pdl_enter();
+    constexpr int G = S / 2;                 // 128-bit chunks per state
+    constexpr int PLAN = 256 / G;            // nodes per tile of the work plan (written by k_finish for k_expand's geometry)
+    constexpr int UPT = PLAN / 32;           // 32-node units per plan tile
+    constexpr int W32 = 2 * S, SROW = W32 + 1;
+    __shared__ uint32_t s_stage[8][32 * SROW];
+    const int* off = ev.tile_off_e;
+    const int total_units = off[count] * UPT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* stage = s_stage[warp];
+    const int nwarps = gridDim.x * 8, gw = warp * gridDim.x + blockIdx.x;  // consecutive unit ranges go to different CTAs: a narrow batch still spreads over every SM
+    const int upw = (total_units + nwarps - 1) / nwarps;
+    const int u_lo = min(gw * upw, total_units), u_hi = min(u_lo + upw, total_units);
+    if (u_lo >= u_hi) return;
+    const int buf = t & 1;
+    int hcnt[W32];
+#pragma unroll
+    for (int j = 0; j < W32; ++j) hcnt[j] = 0;
+    int st_cnt = 0;
+    unsigned n_exp = 0, n_tr = 0, n_claim = 0;
+    int k = plan_find(off, count, u_lo / UPT);
+    int cur_k = k;
+    auto stage_flush = [&]() {
+        if (st_cnt == 0) return;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < W32; ++j) hcnt[j] += __popc(warp_transpose32(lane < st_cnt ? stage[lane * SROW + j] : 0u));
+        __syncwarp();
+        st_cnt = 0;
+    };
+    auto dd_flush = [&](int kk) {  // counters and vertex occurrences of DD kk gathered by this warp
+        stage_flush();
+#pragma unroll
+        for (int j = 0; j < W32; ++j) if (hcnt[j]) { atomicAdd(ev.vhist + (size_t)kk * ev.HN + 32 * j + lane, (unsigned)hcnt[j]); hcnt[j] = 0; }
+        if (lane == 0) {
+            if (n_exp) { atomicAdd(&ev.ctl[kk].expanded, (unsigned long long)n_exp); atomicAdd(&ev.ctl[kk].transitions, (unsigned long long)n_tr); }
+            if (n_claim) atomicAdd(ev.ucount + kk, n_claim);
+        }
+        n_exp = 0; n_tr = 0; n_claim = 0;
+    };
+    for (int u = u_lo; u < u_hi; ++u) {
+        const int tile = u / UPT;
+        while (off[k + 1] <= tile) ++k;
+        if (k != cur_k) { dd_flush(cur_k); cur_k = k; }
+        const DDCtl* ctl = ev.ctl + k;
+        const int n_cur = ctl->n_cur;
+        const int node = (tile - off[k]) * PLAN + (u % UPT) * 32 + lane;
+        const bool active = node < n_cur;
+        const int v = ctl->var;
+        const int vw = v >> 6;
+        const uint64_t bit = 1ull << (v & 63);
+        const size_t cb = (size_t)k * ev.C;
+        uint64_t w[S], wy[S];
+        int val = 0; uint32_t fl = 0;
+        bool expandable = false, has_v = false, claimed0 = false, claimed1 = false;
+        if (active) {
+            const size_t nb = (size_t)k * ev.Wcap + node;
+            const uint4* src = reinterpret_cast<const uint4*>(ev.cur_state[buf] + nb * S);
+#pragma unroll
+            for (int q = 0; q < G; ++q) { const uint4 x = ld_stream_u4(src + q); w[2 * q] = u4lo(x); w[2 * q + 1] = u4hi(x); }
+            val = ev.cur_val[buf][nb];
+            fl = ev.cur_flag[buf][nb];
+            int rub = 0;
+            if (ev.unit_weights) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) rub += __popcll(w[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < S; ++j) { uint64_t x = w[j]; const int32_t* wp = ev.weight + j * 64; while (x) { const int b = __ffsll((long long)x) - 1; rub += wp[b]; x &= x - 1; } }
+            }
+            expandable = ((long long)rub + (long long)val) > ctl->best_lb;  // clean.rs:364-365
+#pragma unroll
+            for (int j = 0; j < S; ++j) if (j == vw && (w[j] & bit)) has_v = true;  // misp/main.rs:96
+            ev.cur_rub[nb] = rub;
+            *reinterpret_cast<uint2*>(ev.cand_rep + cb + 2u * node) = make_uint2(NONE32, NONE32);
+            *reinterpret_cast<uchar2*>(ev.uflag + cb + 2u * node) = make_uchar2(0, 0);
+        }
+        n_exp += __popc(__ballot_sync(FULL_MASK, expandable));
+        n_tr += __popc(__ballot_sync(FULL_MASK, expandable)) + __popc(__ballot_sync(FULL_MASK, expandable && has_v));
+        if (expandable) {
+            const uint32_t c_yes = 2u * node, c_no = 2u * node + 1u;  // for_each_in_domain order: YES then NO (main.rs:95-102)
+#pragma unroll
+            for (int j = 0; j < S; ++j) if (j == vw) w[j] &= ~bit;  // res.remove(var), main.rs:79: w is the NO child from here on
+            const uint4* ncrow = reinterpret_cast<const uint4*>(ev.nc + (size_t)v * S);
+            uint64_t hsh[2]; int vals[2];
+            // both children are written first, ONE fence publishes their rows, then both are inserted
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (d == 0 && !has_v) continue;
+                const uint32_t c = d == 0 ? c_yes : c_no;
+                uint4* dst = reinterpret_cast<uint4*>(ev.cand_state + (cb + c) * S);
+                uint64_t hs = 0; int pc = 0; int got = 0; uint32_t mk = 0;
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    uint64_t a0 = w[2 * q], a1 = w[2 * q + 1];
+                    if (d == 0) { const uint4 n4 = __ldg(ncrow + q); a0 &= u4lo(n4); a1 &= u4hi(n4); wy[2 * q] = a0; wy[2 * q + 1] = a1; }  // main.rs:82
+                    st_stream_u4(dst + q, mk_u4(a0, a1));
+                    hs += a0 * hash_mul(2 * q) + a1 * hash_mul(2 * q + 1);
+                    pc += __popcll(a0) + __popcll(a1);
+                    rank_take<S>(a0, 128 * q, got, mk); rank_take<S>(a1, 128 * q + 64, got, mk);
+                }
+                const int value = d == 0 ? val + ev.weight[v] : val;  // main.rs:87-93
+                hsh[d] = mix64(hs); vals[d] = value;
+                ev.cand_rank[cb + c] = ((uint32_t)pc << 20) | rank_pad<S>(got, mk);
+                ev.cand_agg[cb + c] = pack_key(value, c);
+                ev.cand_first[cb + c] = c;
+                ev.cand_inex[cb + c] = (uint8_t)(fl & NF_INEXACT);
+            }
+            __threadfence();
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (d == 0 && !has_v) continue;
+                const uint32_t c = d == 0 ? c_yes : c_no;
+                const uint64_t h = hsh[d];
+                const int value = vals[d];
+                const uint32_t tag = (uint32_t)(h >> 32);
+                const unsigned long long entry = ((unsigned long long)tag << 32) | c;
+                uint32_t slot = (uint32_t)h & (uint32_t)(ev.T - 1);
+                unsigned long long* tab = ev.table + (size_t)k * ev.T;
+                for (;;) {
+                    const unsigned long long old = atomicCAS(tab + slot, EMPTY64, entry);
+                    if (old == EMPTY64) {  // Entry::Vacant: a new distinct state of the next layer
+                        ev.cand_rep[cb + c] = c; ev.cand_slot[cb + c] = slot;
+                        if (d == 0) claimed0 = true; else claimed1 = true;
+                        break;
+                    }
+                    if ((uint32_t)(old >> 32) == tag) {
+                        const uint32_t oc = (uint32_t)old;
+                        const uint4* orow = reinterpret_cast<const uint4*>(ev.cand_state + (cb + oc) * S);
+                        bool eq = true;
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            const uint64_t a0 = d == 0 ? wy[2 * q] : w[2 * q], a1 = d == 0 ? wy[2 * q + 1] : w[2 * q + 1];
+                            const uint4 o4 = ld_cg_u4(orow + q);
+                            eq = eq && u4lo(o4) == a0 && u4hi(o4) == a1;
+                        }
+                        if (eq) {  // Entry::Occupied, clean.rs:766-774 + append_edge_to! :199-220
+                            atomicMax(ev.cand_agg + cb + oc, pack_key(value, c));
+                            atomicMin(ev.cand_first + cb + oc, c);
+                            if (fl & NF_INEXACT) ev.cand_inex[cb + oc] = 1;
+                            ev.cand_rep[cb + c] = oc;
+                            break;
+                        }
+                    }
+                    slot = (slot + 1) & (uint32_t)(ev.T - 1);
+                }
+            }
+        }
+        // the claimed rows join the vertex histogram of the layer being built (misp/main.rs:131-135)
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const bool has = d == 0 ? claimed0 : claimed1;
+            const unsigned m = __ballot_sync(FULL_MASK, has);
+            if (!m) continue;
+            const int add = __popc(m);
+            n_claim += (unsigned)add;
+            if (st_cnt + add > 32) stage_flush();
+            if (has) {
+                const int r = st_cnt + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const uint64_t x = d == 0 ? wy[j] : w[j];
+                    stage[r * SROW + 2 * j] = (uint32_t)x; stage[r * SROW + 2 * j + 1] = (uint32_t)(x >> 32);
+                }
+            }
+            st_cnt += add;
+        }
+    }
+    dd_flush(cur_k);
+}
+
+// =================================================================================================================
 // k_finish: one CTA per DD.  Decides everything about layer t (whose candidates were produced by k_expand(t-1)).
 // =================================================================================================================
 struct FinishSmem {

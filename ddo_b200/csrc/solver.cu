@@ -236,8 +236,8 @@ void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
     auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
     if (pending_.size() < (1u << 15)) std::sort(pending_.begin(), pending_.end(), less);
-    else {  // a wide wave's cutsets (hundreds of thousands of nodes): sort eight slices on eight threads, then merge pairwise
-        constexpr int T = 8;
+    else {  // a wide wave's cutsets (hundreds of thousands of nodes): sort sixteen slices on as many threads, then merge pairwise
+        constexpr int T = 16;
         const size_t n = pending_.size();
         size_t cut[T + 1];
         for (int i = 0; i <= T; ++i) cut[i] = n * (size_t)i / T;
@@ -260,7 +260,7 @@ void NoDupFringe::flush_pending() {
     while (runs_.size() >= 2) {
         std::vector<Ent>& x = runs_[runs_.size() - 2];
         std::vector<Ent>& y = runs_.back();
-        if (x.size() > 2 * y.size() && runs_.size() <= 8) break;
+        if (runs_.size() <= 8) break;  // a pop compares the tails of at most eight runs; merging half a million entries costs more than that saves
         std::vector<Ent> m;
         m.reserve(x.size() + y.size());
         size_t i = 0, j = 0;
