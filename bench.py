@@ -378,7 +378,7 @@ def run_reference(args, rank, world):
     o = wl.oracle()
     # every step is maximize() of the SAME instance and width under a TimeBudget of >= 30 s, long enough that the single-threaded root DDs
     # (W = 10 000) are a small part of it; on a box that finishes the proof inside the box the arm runs the same configuration as ours
-    budget = max(30.0, min(120.0, 300.0 / max(args.steps, 1)))
+    budget = max(30.0, min(90.0, 240.0 / max(args.steps, 1)))
     small = gnp(200, 0.5, SEED)
     os_ = O.OracleMisp(small)
     for _ in range(args.warmup):  # untimed: a small instance, warms the allocator and the thread pool
@@ -405,8 +405,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--wave", type=int, default=2048, help="open sub-problems popped per wave and per GPU")
-    ap.add_argument("--batch-cap", type=int, default=4096, help="DD slots of the general (layer-by-layer) engine: how many DDs a batch may hold in lock-step when the log pool allows (it holds 512 full-depth DDs; deeper sub-problems log fewer layers)")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="TimeBudget of the CPU baseline sample")
+    ap.add_argument("--batch-cap", type=int, default=2048, help="DD slots of the general (layer-by-layer) engine: how many DDs a batch may hold in lock-step when the log pool allows (it holds 512 full-depth DDs; deeper sub-problems log fewer layers)")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="TimeBudget of the CPU baseline sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="misp", choices=["misp", "max2sat"], help="misp = BASELINE config 2 (the headline metric); max2sat = config 3")
     ap.add_argument("--max-waves", type=int, default=0, help="max2sat: waves per step (default 2)")
@@ -416,7 +416,7 @@ def main():
     args = ap.parse_args()
     if args.workload == "max2sat":  # 2 KB states: fewer, larger DDs per wave -- one DD per SM (m2_finish is one CTA per DD)
         if args.wave == 2048: args.wave = 148
-        if args.batch_cap == 4096: args.batch_cap = 148
+        if args.batch_cap == 2048: args.batch_cap = 148
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -883,6 +883,7 @@ __device__ void DDC<S>::run(int slot, int count, int dual) {
                 int o = block_excl_scan(c, &kblk, fx.scan);
                 for (int q = 0; q < per; ++q) { const int ch = tid * per + q; if (ch < nch) { koff_s[ch] = o; o += cnt_s[ch]; } }
             }
+            __syncthreads();  // koff_s is read by other threads in the commit (a restricted cut has no barrier in between)
         }
         prof(5);
         int n_next = nkeep, sv_pos = -1, r_pos = -1;
