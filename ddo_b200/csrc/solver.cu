@@ -74,6 +74,7 @@ bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
 }
 
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
+    drop_cold();
     states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); ver_.clear(); recycle_.clear();
     pending_.clear(); runs_.clear(); live_ = 0;
     for (Shard& sh : shards_) { std::fill(sh.tab.begin(), sh.tab.end(), -1); sh.used = 0; sh.live = 0; }  // the tables keep their size for the next search
@@ -159,7 +160,7 @@ int NoDupFringe::push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t
 }
 void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t depth, int32_t rec, const uint64_t* bits, int nbits_words) {
     int id;
-    const bool fresh = recycle_.empty();
+    const bool fresh = recycle_.empty() || cold_busy();  // no slot is reused while a background sort may still compare its old state
     if (fresh) {
         id = (int)items_.size();
         items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
@@ -174,7 +175,9 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     const size_t n = recs.size();
     const int T = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency()));
     if (n < 8192) { for (const PushRec& r : recs) push(r.state, r.value, r.ub, r.depth, r.rec, r.bits, r.nbits_words); return; }
+    for (Run& r : runs_) if (r.cold) join_cold(r);  // the burst reuses recycled slots
     // hashes, then the records of every shard in record order (stable counting sort)
+    static const bool prof = std::getenv("DDO_FRINGE_PROF") != nullptr; double tp0 = now_ms(), tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
     std::vector<uint64_t> h(n);
     {
         std::vector<std::thread> ts;
@@ -182,6 +185,7 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
             ts.emplace_back([&, w] { for (size_t i = n * w / T; i < n * (w + 1) / T; ++i) h[i] = key_hash(recs[i].state, recs[i].depth); });
         for (auto& t : ts) t.join();
     }
+    tp1 = now_ms();
     std::vector<uint32_t> start(NS + 1, 0), order(n);
     for (size_t i = 0; i < n; ++i) ++start[shard_of(h[i]) + 1];
     for (int s = 0; s < NS; ++s) start[s + 1] += start[s];
@@ -191,6 +195,7 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     }
     // tentative node slot of every record, handed out in SHARD order so that the slots one thread writes are contiguous (no cache lines
     // shared between threads): recycled slots first, then fresh ones; a record that hits an existing node leaves its slot unused
+    tp2 = now_ms();
     std::vector<int> slot(n);
     const size_t nrec = std::min(n, recycle_.size());
     const size_t base = items_.size(), fresh = n - nrec;
@@ -198,6 +203,7 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     recycle_.resize(recycle_.size() - nrec);
     items_.resize(base + fresh); popc_.resize(base + fresh, 0); hash_.resize(base + fresh, 0); ver_.resize(base + fresh, 0);
     for (size_t i = 0; i < fresh; ++i) { states_.grow(); bits_.grow(); }
+    tp3 = now_ms();
     std::vector<std::vector<Ent>> pend(T);
     std::vector<std::vector<int>> unused(T);
     std::vector<size_t> added(T, 0);
@@ -222,45 +228,51 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
             });
         for (auto& t : ts) t.join();
     }
+    tp4 = now_ms();
     for (int w = 0; w < T; ++w) {
         pending_.insert(pending_.end(), pend[w].begin(), pend[w].end());
         recycle_.insert(recycle_.end(), unused[w].begin(), unused[w].end());
         live_ += added[w];
     }
+    if (prof) std::fprintf(stderr, "[push_many %zu] hash %.1f  order %.1f  slots %.1f  insert %.1f  gather %.1f ms\n", n, tp1 - tp0, tp2 - tp1, tp3 - tp2, tp4 - tp3, now_ms() - tp4);
 }
 void NoDupFringe::flush_pending() {
     if (pending_.empty()) return;
+    static const bool prof = std::getenv("DDO_FRINGE_PROF") != nullptr; const double tf0 = now_ms(); double tf1 = 0, tf2 = 0; const size_t nf = pending_.size();
     // entries re-keyed or popped since they were queued are dropped first: a stale entry's slot may hold another state by now, and the
     // comparator must never dereference it (the runs below stay sorted by the keys of LIVE nodes only)
     pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [this](const Ent& e) { return e.ver != ver_[e.id]; }), pending_.end());
     if (pending_.empty()) return;
     auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
-    if (pending_.size() < (1u << 15)) std::sort(pending_.begin(), pending_.end(), less);
-    else {  // a wide wave's cutsets (hundreds of thousands of nodes): sort sixteen slices on as many threads, then merge pairwise
-        constexpr int T = 16;
-        const size_t n = pending_.size();
-        size_t cut[T + 1];
-        for (int i = 0; i <= T; ++i) cut[i] = n * (size_t)i / T;
-        {
-            std::vector<std::thread> ts;
-            for (int i = 0; i < T; ++i) ts.emplace_back([&, i] { std::sort(pending_.begin() + cut[i], pending_.begin() + cut[i + 1], less); });
-            for (auto& t : ts) t.join();
-        }
-        for (int step = 1; step < T; step *= 2) {
-            std::vector<std::thread> ts;
-            for (int i = 0; i + step < T; i += 2 * step)
-                ts.emplace_back([&, i, step] { std::inplace_merge(pending_.begin() + cut[i], pending_.begin() + cut[i + step], pending_.begin() + cut[std::min(i + 2 * step, T)], less); });
-            for (auto& t : ts) t.join();
-        }
+    tf1 = now_ms();
+    Run nr;
+    if (pending_.size() < (1u << 15) || !async_sort_) { sort_ents(pending_); nr.v.swap(pending_); }
+    else {
+        // a wide wave's cutsets (hundreds of thousands of nodes): the next waves only need the best few thousand of them -- select those,
+        // sort them now, and let a background thread sort the rest while the device works
+        std::nth_element(pending_.begin(), pending_.end() - kHot, pending_.end(), less);
+        nr.v.assign(pending_.end() - kHot, pending_.end());
+        std::sort(nr.v.begin(), nr.v.end(), less);
+        pending_.resize(pending_.size() - kHot);
+        nr.cold.reset(new Cold());
+        nr.cold->ents.swap(pending_);
+        Cold* c = nr.cold.get();
+        c->th = std::thread([this, c] { sort_ents(c->ents); c->done.store(true, std::memory_order_release); });
+        ++cold_open_;
     }
-    runs_.emplace_back();
-    runs_.back().swap(pending_);
-    // Keep the runs few and geometrically sized (a pop looks at every run's tail): the newest run absorbs its predecessor while that one is
-    // at most twice its size, and beyond eight runs regardless -- O(n log n) merge work over a search.
-    while (runs_.size() >= 2) {
-        std::vector<Ent>& x = runs_[runs_.size() - 2];
-        std::vector<Ent>& y = runs_.back();
-        if (runs_.size() <= 8) break;  // a pop compares the tails of at most eight runs; merging half a million entries costs more than that saves
+    pending_.clear();
+    tf2 = now_ms();
+    if (prof && nf > 10000) std::fprintf(stderr, "[flush %zu] stale filter %.1f  sort %.1f ms\n", nf, tf1 - tf0, tf2 - tf1);
+    runs_.push_back(std::move(nr));
+    // Keep the runs few (a pop compares the tails of at most eight runs; merging half a million entries more often costs more than that
+    // saves): beyond eight, the last two runs that are not being sorted in the background are merged.  The order of the runs is irrelevant
+    // (the MaxUB order is strict over live entries).
+    while (runs_.size() > 8) {
+        size_t k = runs_.size() - 1;
+        while (k >= 1 && (runs_[k].cold || runs_[k - 1].cold)) --k;
+        if (k < 1) { k = runs_.size() - 1; if (runs_[k].cold) join_cold(runs_[k]); if (runs_[k - 1].cold) join_cold(runs_[k - 1]); }
+        std::vector<Ent>& x = runs_[k - 1].v;
+        std::vector<Ent>& y = runs_[k].v;
         std::vector<Ent> m;
         m.reserve(x.size() + y.size());
         size_t i = 0, j = 0;
@@ -271,8 +283,52 @@ void NoDupFringe::flush_pending() {
             const bool take_x = j == y.size() || (i < x.size() && !ent_less(y[j], x[i]));
             m.push_back(take_x ? x[i++] : y[j++]);
         }
-        runs_.pop_back();
-        runs_.back().swap(m);
+        runs_[k - 1].v.swap(m);
+        runs_.erase(runs_.begin() + (long)k);
+    }
+}
+void NoDupFringe::sort_ents(std::vector<Ent>& v) const {
+    auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
+    if (v.size() < (1u << 15)) { std::sort(v.begin(), v.end(), less); return; }
+    constexpr int T = 16;  // sixteen slices on as many threads, then pairwise merges
+    const size_t n = v.size();
+    size_t cut[T + 1];
+    for (int i = 0; i <= T; ++i) cut[i] = n * (size_t)i / T;
+    {
+        std::vector<std::thread> ts;
+        for (int i = 0; i < T; ++i) ts.emplace_back([&, i] { std::sort(v.begin() + cut[i], v.begin() + cut[i + 1], less); });
+        for (auto& t : ts) t.join();
+    }
+    for (int step = 1; step < T; step *= 2) {
+        std::vector<std::thread> ts;
+        for (int i = 0; i + step < T; i += 2 * step)
+            ts.emplace_back([&, i, step] { std::inplace_merge(v.begin() + cut[i], v.begin() + cut[i + step], v.begin() + cut[std::min(i + 2 * step, T)], less); });
+        for (auto& t : ts) t.join();
+    }
+}
+void NoDupFringe::join_cold(Run& run) {
+    Cold& c = *run.cold;
+    c.th.join();
+    --cold_open_;
+    c.ents.insert(c.ents.end(), run.v.begin(), run.v.end());  // every cold entry is below every entry of the sorted part
+    run.v.swap(c.ents);
+    run.cold.reset();
+}
+bool NoDupFringe::cold_busy() {
+    if (cold_open_ == 0) return false;
+    for (Run& r : runs_) if (r.cold && r.cold->done.load(std::memory_order_acquire)) join_cold(r);
+    return cold_open_ > 0;
+}
+void NoDupFringe::drop_cold() {
+    for (Run& r : runs_) if (r.cold) { r.cold->th.join(); r.cold.reset(); }
+    cold_open_ = 0;
+}
+std::vector<NoDupFringe::Ent>& NoDupFringe::tail_run(size_t r) {
+    Run& run = runs_[r];
+    for (;;) {
+        while (!run.v.empty() && run.v.back().ver != ver_[run.v.back().id]) run.v.pop_back();  // stale
+        if (!run.v.empty() || !run.cold) return run.v;
+        join_cold(run);
     }
 }
 int NoDupFringe::pop() {
@@ -280,15 +336,15 @@ int NoDupFringe::pop() {
     flush_pending();
     int best_run = -1;
     for (size_t r = 0; r < runs_.size(); ++r) {
-        auto& run = runs_[r];
-        while (!run.empty() && run.back().ver != ver_[run.back().id]) run.pop_back();  // stale
+        auto& run = tail_run(r);
         if (run.empty()) continue;
-        if (best_run < 0 || ent_less(runs_[best_run].back(), run.back())) best_run = (int)r;
+        if (best_run < 0 || ent_less(runs_[best_run].v.back(), run.back())) best_run = (int)r;
     }
-    const int id = runs_[best_run].back().id;
-    runs_[best_run].pop_back();
-    if (runs_[best_run].size() >= 8) {  // the next pops most likely come from the same run: start fetching their node records and states
-        const int nid = runs_[best_run][runs_[best_run].size() - 8].id;
+    auto& brun = runs_[best_run].v;
+    const int id = brun.back().id;
+    brun.pop_back();
+    if (brun.size() >= 8) {  // the next pops most likely come from the same run: start fetching their node records and states
+        const int nid = brun[brun.size() - 8].id;
         __builtin_prefetch(&items_[nid]); __builtin_prefetch(states_.at(nid)); __builtin_prefetch(bits_.at(nid));
     }
     ++ver_[id];  // any other entry of this node is now stale
@@ -300,39 +356,96 @@ int NoDupFringe::pop() {
 // The next `k` nodes in pop() order at once (the workload of a wave, parallel.rs:500-559).  Knowing the ids ahead lets every random access
 // -- version words during the selection, then hash, index slot, node record, state and path bits -- be prefetched a few nodes ahead
 // instead of being paid as a chain of cache misses per pop.
-int NoDupFringe::pop_many(int k, std::vector<int>& ids) {
+int NoDupFringe::pop_many(int k, std::vector<int>& ids, const PopOut* out) {
     ids.clear();
+    if (out) { out->items->clear(); out->states->clear(); out->bits->clear(); }
     if (live_ == 0 || k <= 0) return 0;
     flush_pending();
-    while ((int)ids.size() < k && ids.size() < live_) {
-        int best_run = -1;
-        for (size_t r = 0; r < runs_.size(); ++r) {
-            auto& run = runs_[r];
-            while (!run.empty() && run.back().ver != ver_[run.back().id]) run.pop_back();  // stale
-            if (run.empty()) continue;
-            if (best_run < 0 || ent_less(runs_[best_run].back(), run.back())) best_run = (int)r;
+    static double acc1 = 0, acc2 = 0; static bool reg = false;
+    if (!reg && std::getenv("DDO_FRINGE_PROF")) { reg = true; std::atexit([] { std::fprintf(stderr, "[pop_many] select %.1f ms, erase + copy %.1f ms\n", acc1, acc2); }); }
+    const double tpm0 = now_ms();
+    const size_t want = std::min<size_t>((size_t)k, live_);
+    const size_t R = runs_.size();
+    // 1. selection = a merge of the runs' live entries from their tails down (what pop() picks one by one).  Every run keeps a short
+    //    look-ahead of validated (live) positions, refilled a chunk at a time: the version loads of a chunk are independent, so their
+    //    cache misses overlap (a pop()-style loop pays one miss per pop behind an unpredictable branch).
+    constexpr size_t CHUNK = 48;
+    if (cand_.size() < R) cand_.resize(R);
+    head_.assign(R, 0); scan_.resize(R);
+    for (size_t r = 0; r < R; ++r) { cand_[r].clear(); scan_[r] = runs_[r].v.size(); }
+    auto refill = [&](size_t r) -> bool {  // false: the run has no live entry left
+        std::vector<uint32_t>& c = cand_[r];
+        for (;;) {
+            const std::vector<Ent>& v = runs_[r].v;
+            size_t q = scan_[r];
+            const size_t stop = c.size() + CHUNK;
+            while (q > 0 && c.size() < stop) {
+                --q;
+                if (q >= 16) __builtin_prefetch(&ver_[v[q - 16].id]);
+                if (v[q].ver == ver_[v[q].id]) c.push_back((uint32_t)q);
+            }
+            scan_[r] = q;
+            if (head_[r] < c.size()) return true;
+            if (!runs_[r].cold) return false;
+            const size_t shift = runs_[r].cold->ents.size();  // the sorted part is used up: the background-sorted part joins below it
+            join_cold(runs_[r]);
+            for (uint32_t& x : c) x += (uint32_t)shift;
+            scan_[r] = shift;
         }
-        auto& run = runs_[best_run];
-        const int id = run.back().id;
-        run.pop_back();
-        if (run.size() >= 12) __builtin_prefetch(&ver_[run[run.size() - 12].id]);
-        ++ver_[id];  // any other entry of this node is now stale
-        ids.push_back(id);
+    };
+    // runs ordered by their heads, best first; after a pop only the run it came from moves (usually it stays in front)
+    int order[64]; int no = 0;
+    auto head_ent = [&](int r) -> const Ent& { return runs_[r].v[cand_[r][head_[r]]]; };
+    for (size_t r = 0; r < R && r < 64; ++r) {
+        if (!refill(r)) continue;
+        int p = no++;
+        while (p > 0 && ent_less(head_ent(order[p - 1]), head_ent((int)r))) { order[p] = order[p - 1]; --p; }
+        order[p] = (int)r;
     }
+    ids.reserve(want);
+    while (ids.size() < want && no > 0) {
+        const int r = order[0];
+        ids.push_back(head_ent(r).id);
+        ++head_[r];
+        if (head_[r] >= cand_[r].size() && !refill((size_t)r)) { for (int p = 1; p < no; ++p) order[p - 1] = order[p]; --no; continue; }
+        int p = 0;
+        while (p + 1 < no && ent_less(head_ent(r), head_ent(order[p + 1]))) { order[p] = order[p + 1]; ++p; }
+        order[p] = r;
+    }
+    for (size_t r = 0; r < R; ++r) if (head_[r] > 0) runs_[r].v.resize(cand_[r][head_[r] - 1]);  // the taken entries and the stale ones above them
     const size_t n = ids.size();
+    const double tpm1 = now_ms(); acc1 += tpm1 - tpm0;
+    struct Fin { double& a; double t; ~Fin() { a += now_ms() - t; } } fin{acc2, tpm1};
+    // 3. per node: version bump (any other entry of the node is stale from here on), index erase, slot recycling, and the copy of its record
+    //    for the caller -- every random access prefetched a few nodes ahead
+    if (out) { out->items->reserve(n); out->states->reserve(n * (size_t)W); out->bits->reserve(n * (size_t)out->bits_words); }
+    constexpr size_t D1 = 24, D2 = 12;
     for (size_t i = 0; i < n; ++i) {
-        if (i + 12 < n) __builtin_prefetch(&hash_[ids[i + 12]]);
-        if (i + 6 < n) {
-            const uint64_t h = hash_[ids[i + 6]];
+        if (i + D1 < n) { __builtin_prefetch(&hash_[ids[i + D1]]); __builtin_prefetch(&ver_[ids[i + D1]], 1); }
+        if (i + D2 < n) {
+            const uint64_t h = hash_[ids[i + D2]];
             const Shard& sh = shards_[shard_of(h)];
-            __builtin_prefetch(&sh.tab[h & (sh.tab.size() - 1)]);
-            prefetch(ids[i + 6]);
+            __builtin_prefetch(&sh.tab[h & (sh.tab.size() - 1)], 1);
+            prefetch(ids[i + D2]);
         }
-        recycle_.push_back(ids[i]);
-        table_erase(ids[i]);
+        const int id = ids[i];
+        ++ver_[id];
+        recycle_.push_back(id);
+        table_erase(id);
+        if (out) {
+            out->items->push_back(items_[id]);
+            out->states->insert(out->states->end(), states_.at(id), states_.at(id) + W);
+            out->bits->insert(out->bits->end(), bits_.at(id), bits_.at(id) + out->bits_words);
+        }
     }
     live_ -= n;
     return (int)n;
+}
+// DDO_FRINGE_PROF: wall-clock accounting of a solve by host phase (diagnostics; printed at the end of maximize())
+namespace {
+struct PhaseProf { double f_stage = 0, f_launch = 0, f_prepop = 0, f_wait = 0, f_res = 0, f_prep = 0; double pop = 0, small_wall = 0, small_dev = 0, stage = 0, gen_wall = 0, gen_dev = 0, fetch = 0, collect = 0, enqueue = 0, waves_wall = 0; };
+PhaseProf g_prof;
+struct PhaseTimer { double& acc; double t0; explicit PhaseTimer(double& a) : acc(a), t0(now_ms()) {} ~PhaseTimer() { acc += now_ms() - t0; } };
 }
 // ---------------------------------------------------------------------------------------------------------------
 // Solver
@@ -341,6 +454,9 @@ Solver::Solver(Engine* e, int kind, const uint64_t* rs, int64_t rv, int wk, uint
     : eng(e), model_kind(kind), n_vars(e->n_vars), words(e->abi_words), root_state(rs, rs + e->abi_words), root_value(rv), width_kind(wk), width(w),
       wave_size(ws), fringe(e->abi_words, (e->n_vars + 63) / 64, kind) {
     if (const char* p = std::getenv("DDO_WAVE_TRACE")) trace_file = std::fopen(p, "w");
+}
+Solver::~Solver() {
+    if (trace_file) std::fclose(trace_file);
 }
 
 int Solver::init(bool push_root) {  // parallel.rs:368-385
@@ -377,34 +493,27 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     const double tr_wave0 = t0;
     int64_t top_ub = INT64_MIN;
     w_states.clear(); w_bits.clear(); w_items.clear();
-    if (pre_valid) {  // the nodes popped ahead of time, re-checked against the current incumbent in pop order
-        pre_valid = false;
-        for (size_t i = 0; i < pre_items.size(); ++i) {
-            const NoDupFringe::Item it = pre_items[i];
-            const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
-            if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
-            if (w_items.empty()) top_ub = ub;
-            w_states.insert(w_states.end(), &pre_states[i * W], &pre_states[i * W] + W);
-            w_bits.insert(w_bits.end(), &pre_bits[i * PWN], &pre_bits[i * PWN] + PWN);
-            w_items.push_back(it);
-            ++explored;
-        }
-    } else {
-        fringe.pop_many(wave_size, pop_ids);
-        for (size_t i = 0; i < pop_ids.size(); ++i) {
-            const int id = pop_ids[i];
-            const NoDupFringe::Item it = fringe.item(id);
-            const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
-            if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
-            if (w_items.empty()) top_ub = ub;
-            w_states.insert(w_states.end(), fringe.state(id), fringe.state(id) + W);
-            w_bits.insert(w_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
-            w_items.push_back(it);
-            ++explored;
-        }
+    if (!pre_valid) {  // (otherwise: the nodes were popped ahead of time, while the device compiled the previous wave)
+        const NoDupFringe::PopOut po{&pre_items, &pre_states, &pre_bits, PWN};
+        fringe.pop_many(wave_size, pop_ids, &po);
     }
+    pre_valid = false;
+    for (size_t i = 0; i < pre_items.size(); ++i) {  // re-checked against the current incumbent in pop order
+        const NoDupFringe::Item it = pre_items[i];
+        const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
+        if (ub <= best_lb) { fringe.clear(); break; }  // parallel.rs:531-535
+        if (w_items.empty()) top_ub = ub;
+        w_states.insert(w_states.end(), &pre_states[i * W], &pre_states[i * W] + W);
+        w_bits.insert(w_bits.end(), &pre_bits[i * PWN], &pre_bits[i * PWN] + PWN);
+        w_items.push_back(it);
+        ++explored;
+    }
+    pre_items.clear();
     fringe_ms += now_ms() - t0;
     const double tr_pop = now_ms() - t0;
+    g_prof.pop += tr_pop;
+    PhaseTimer wave_timer(g_prof.waves_wall);
+    const double t_prep0 = now_ms();
     out3[1] = top_ub;
     const int cnt = (int)w_items.size();
     if (cnt == 0) { out3[0] = best_lb; out3[2] = 0; return DDO_OK; }
@@ -423,6 +532,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         }
         values[i] = w_items[i].value; depths[i] = w_items[i].depth;
     }
+    g_prof.f_prep += now_ms() - t_prep0;
     auto past_deadline = [&]() { return (deadline_ms > 0 && now_ms() >= deadline_ms) || (cutoff_flag && *cutoff_flag); };  // TimeBudget polled before every device batch
     struct Res { bool exact = false, has = false; int32_t best = 0; };
     std::vector<Res> res(cnt);
@@ -487,14 +597,16 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     // ---- 1a. shared-memory fast path: one CTA per sub-problem; DDs that never need a cut are exact and finish here ----------------
     std::vector<int> ov;  // sub-problems that need the general engine (a layer outgrew the fast path)
     if (eng->small_ws > 0) {
-        rc = eng->stage_roots(cnt, widths.data(), w_states.data(), values.data(), depths.data());
+        PhaseTimer small_timer(g_prof.small_wall);
+        { PhaseTimer pt(g_prof.f_stage); rc = eng->stage_roots(cnt, widths.data(), w_states.data(), values.data(), depths.data()); }
         if (rc != DDO_OK) return rc;
-        rc = eng->compile_small_launch(cnt, lb0, eng->small_ws_first > 0 && eng->small_ws_first < eng->small_ws ? eng->small_ws_first : eng->small_ws);
+        { PhaseTimer pt(g_prof.f_launch); rc = eng->compile_small_launch(cnt, lb0, eng->small_ws_first > 0 && eng->small_ws_first < eng->small_ws ? eng->small_ws_first : eng->small_ws); }
         if (rc != DDO_OK) return rc;
-        if (pipeline) { const double tp = now_ms(); prepop(); fringe_ms += now_ms() - tp; }  // overlaps the device
-        rc = eng->compile_small_wait(&ms);
+        if (pipeline) { PhaseTimer pt(g_prof.f_prepop); const double tp = now_ms(); prepop(); fringe_ms += now_ms() - tp; }  // overlaps the device
+        { PhaseTimer pt(g_prof.f_wait); rc = eng->compile_small_wait(&ms); }
         if (rc != DDO_OK) return rc;
-        device_ms += ms; tr_small += ms;
+        PhaseTimer res_timer(g_prof.f_res);
+        device_ms += ms; tr_small += ms; g_prof.small_dev += ms;
         for (int i = 0; i < cnt; ++i) {
             const SmallOut& o = eng->h_small[i];
             if (o.status != 0) { ov.push_back(i); continue; }
@@ -512,7 +624,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             if (rc != DDO_OK) return rc;
             rc = eng->compile_small_wait(&ms);
             if (rc != DDO_OK) return rc;
-            device_ms += ms; tr_small += ms;
+            device_ms += ms; tr_small += ms; g_prof.small_dev += ms;
             for (size_t j = 0; j < ov1.size(); ++j) {
                 const SmallOut& o = eng->h_small[j];
                 const int i = ov1[j];
@@ -542,11 +654,15 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     std::vector<int64_t> caps, lbs;
     std::vector<int32_t> vars;
     // collects the cutset records of the last relaxed batch: slot -> wave index through `slot_wave`
+    static const bool fringe_prof = std::getenv("DDO_FRINGE_PROF") != nullptr;
     bool p_direct = false;  // the wave's only relaxed batch: its records are pushed straight from the engine's pinned drain buffer (no staging copy)
     auto collect_drain = [&](int slots, const std::vector<int>& slot_wave) -> int {
         int pw = 1;
+        PhaseTimer collect_timer(g_prof.collect);
+        const double tc0 = now_ms();
         const int total = eng->drain_all(slots, caps.data(), lbs.data(), &pw);
         if (total < 0) return total;
+        const double tc1 = now_ms();
         p_states.reserve(p_states.size() + (size_t)total * W); p_bits.reserve(p_bits.size() + (size_t)total * PWN);
         p_val.reserve(p_val.size() + total); p_ub.reserve(p_ub.size() + total);
         int cur_dd = -1;
@@ -566,6 +682,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
             p_tt.push_back(frontier ? eng->h_out_tt[r] : pend.back().lel);
             pend.back().count++;
         }
+        if (fringe_prof && total > 10000) std::fprintf(stderr, "[collect_drain %d] drain_all %.1f  collect %.1f ms\n", total, tc1 - tc0, now_ms() - tc1);
         return DDO_OK;
     };
     {   // the deeper the sub-problems, the fewer layers their DDs log, the more of them fit the log pool (Engine::slots_for)
@@ -580,11 +697,12 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     for (size_t s0 = 0; s0 < ov.size(); s0 += (size_t)chunk) {
         const int oc = (int)std::min<size_t>((size_t)chunk, ov.size() - s0);
         if (past_deadline()) return DDO_CUTOFF;
-        rc = stage_subset(&ov[s0], oc);
+        { PhaseTimer pt(g_prof.stage); rc = stage_subset(&ov[s0], oc); }
         if (rc != DDO_OK) return rc;
-        rc = dual ? eng->compile_dual(oc, lb0, cutoff_flag, &ms) : eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms);
+        { PhaseTimer pt(g_prof.gen_wall); rc = dual ? eng->compile_dual(oc, lb0, cutoff_flag, &ms) : eng->compile_staged(oc, DDO_RESTRICTED, lb0, cutoff_flag, &ms); }
         if (rc != DDO_OK) return rc;
-        device_ms += ms; tr_general += ms;
+        device_ms += ms; tr_general += ms; g_prof.gen_dev += ms;
+        PhaseTimer fetch_timer(g_prof.fetch);
         rc = eng->fetch_ctl(dual ? 2 * oc : oc);
         if (rc != DDO_OK) return rc;
         for (int j = 0; j < oc; ++j) {
@@ -703,8 +821,11 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
                                                          w_items[pd.wave_index].depth + p_tt[r], rec_id, (p_tt[r] + 63) / 64});
             }
         }
+        const double tq = now_ms();
+        PhaseTimer enq_timer(g_prof.enqueue);
         fringe.push_many(push_recs);  // enqueue_cutset (parallel.rs:456-469) in wave order
         fringe_ms += now_ms() - t0;
+        if (fringe_prof && push_recs.size() > 10000) std::fprintf(stderr, "[enqueue %zu] build %.1f  push_many %.1f ms\n", push_recs.size(), tq - t0, now_ms() - tq);
     }
     if (trace_file)
         std::fprintf(trace_file, "%llu %d %zu %zu %.3f %.3f %llu %llu %zu %.3f %.3f\n", (unsigned long long)waves, cnt, ov.size(), open.size(), tr_small, tr_general,
@@ -715,17 +836,16 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
 }
 
 void Solver::prepop() {
-    const int W = words, PWN = (n_vars + 63) / 64;
-    pre_states.clear(); pre_bits.clear(); pre_items.clear();
-    fringe.pop_many(wave_size, pop_ids);
-    for (size_t i = 0; i < pop_ids.size(); ++i) {
-        const int id = pop_ids[i];
-        const NoDupFringe::Item it = fringe.item(id);
-        const int64_t ub = it.ub == INT32_MAX ? INT64_MAX : it.ub;
-        if (ub <= best_lb) { fringe.clear(); break; }  // nothing left can improve on the incumbent (it only grows): safe ahead of time too
-        pre_states.insert(pre_states.end(), fringe.state(id), fringe.state(id) + W);
-        pre_bits.insert(pre_bits.end(), fringe.bits(id), fringe.bits(id) + PWN);
-        pre_items.push_back(it);
+    const int PWN = (n_vars + 63) / 64;
+    const NoDupFringe::PopOut po{&pre_items, &pre_states, &pre_bits, PWN};
+    fringe.pop_many(wave_size, pop_ids, &po);
+    for (size_t i = 0; i < pre_items.size(); ++i) {
+        const int64_t ub = pre_items[i].ub == INT32_MAX ? INT64_MAX : pre_items[i].ub;
+        if (ub <= best_lb) {  // nothing left can improve on the incumbent (it only grows): safe ahead of time too
+            fringe.clear();
+            pre_items.resize(i); pre_states.resize(i * (size_t)words); pre_bits.resize(i * (size_t)PWN);
+            break;
+        }
     }
     pre_valid = !pre_items.empty();
 }
@@ -756,6 +876,12 @@ int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact
         if (rc != DDO_OK) return rc;
     }
     pipeline = false; pre_valid = false; deadline_ms = 0;
+    if (std::getenv("DDO_FRINGE_PROF")) {
+        const PhaseProf& q = g_prof;
+        std::fprintf(stderr, "[solve] waves wall %.1f (+pop %.1f) | fast path wall %.1f (device %.1f) | general: stage %.1f, compile wall %.1f (device %.1f), fetch+capture(+collect) %.1f, "
+                     "collect %.1f, enqueue (push_many only) %.1f ms | fast path: widths %.1f stage %.1f launch %.1f prepop %.1f wait %.1f results(+tier 2) %.1f\n", q.waves_wall, q.pop, q.small_wall, q.small_dev, q.stage, q.gen_wall, q.gen_dev, q.fetch, q.collect, q.enqueue, q.f_prep, q.f_stage, q.f_launch, q.f_prepop, q.f_wait, q.f_res);
+        g_prof = PhaseProf{};
+    }
     if (aborted) fringe.clear();  // abort_search, parallel.rs:479-489
     else best_ub = best_lb;
     std::stable_sort(best_sol.begin(), best_sol.end(), [](const ddo_decision& a, const ddo_decision& b) { return a.variable < b.variable; });  // parallel.rs:605

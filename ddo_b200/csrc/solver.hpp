@@ -9,8 +9,11 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "engine.hpp"
@@ -32,7 +35,13 @@ public:
     // kind: DDO_MODEL_MISP -- MispRanking (popcount, BitSet::cmp), states compared without their depth (BitSet alone is the state);
     //       DDO_MODEL_MAX2SAT -- Max2SatRanking (rank = sum |benefit|, heuristics.rs:33-37) refined canonically by (depth, lexicographic
     //       benefits); the depth is part of the state (model.rs:59-62 derives Hash / Eq over both fields).
-    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) { states_.init(words); bits_.init(pw); }
+    NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) {
+        states_.init(words); bits_.init(pw);
+        if (const char* e = std::getenv("DDO_FRINGE_ASYNC")) async_sort_ = std::atoi(e) != 0;
+    }
+    ~NoDupFringe() { drop_cold(); }
+    NoDupFringe(const NoDupFringe&) = delete;
+    NoDupFringe& operator=(const NoDupFringe&) = delete;
     struct Item { int32_t value, ub, depth, rec; };
     size_t len() const { return live_; }
     bool empty() const { return live_ == 0; }
@@ -46,7 +55,10 @@ public:
     void push_many(const std::vector<PushRec>& recs);
     // no_duplicate.rs:144-164; returns node id (valid until the next push)
     int pop();
-    int pop_many(int k, std::vector<int>& ids);  // the next min(k, len()) nodes in pop() order; ids valid until the next push
+    // the next min(k, len()) nodes in pop() order; ids valid until the next push.  With `out`, the records of the popped nodes (item, packed
+    // state, the first bits_words words of the path bits) are appended to the caller's vectors while their cache lines arrive.
+    struct PopOut { std::vector<Item>* items; std::vector<uint64_t>* states; std::vector<uint64_t>* bits; int bits_words; };
+    int pop_many(int k, std::vector<int>& ids, const PopOut* out = nullptr);
     void prefetch(int id) const { __builtin_prefetch(&items_[id]); __builtin_prefetch(states_.at(id)); __builtin_prefetch(bits_.at(id)); }
     const uint64_t* state(int id) const { return states_.at(id); }
     const uint64_t* bits(int id) const { return bits_.at(id); }
@@ -61,7 +73,9 @@ private:
     // states live in fixed blocks (no reallocation copies: a MAX2SAT fringe holds gigabytes of 2 KB states)
     struct Arena {
         int W = 1; int shift = 0; size_t per_block = 1; std::vector<std::unique_ptr<uint64_t[]>> blocks; size_t count = 0;
-        void init(int w) { W = w; shift = 0; while (((size_t)2 << shift) * (size_t)w <= ((size_t)1 << 22)) ++shift; per_block = (size_t)1 << shift; }  // ~32 MB blocks, a power of two rows
+        void init(int w) {  // ~32 MB blocks, a power of two rows; the block list never reallocates (a background sort reads it while the owner grows it)
+            W = w; shift = 0; while (((size_t)2 << shift) * (size_t)w <= ((size_t)1 << 22)) ++shift; per_block = (size_t)1 << shift; blocks.reserve(1 << 15);
+        }
         uint64_t* at(size_t id) const { return blocks[id >> shift].get() + (id & (per_block - 1)) * (size_t)W; }
         void grow() { if (count == blocks.size() * per_block) blocks.emplace_back(new uint64_t[per_block * (size_t)W]); ++count; }
         void clear() { count = 0; }  // the blocks stay (no page faults when the next search refills them)
@@ -72,7 +86,21 @@ private:
     std::vector<uint32_t> ver_;
     std::vector<int> recycle_;
     std::vector<Ent> pending_;
-    std::vector<std::vector<Ent>> runs_;
+    // A run is sorted ascending (pops take the back).  A large burst is split at flush time: its best kHot entries are sorted at once (`v`),
+    // the rest (`cold`, every entry below every entry of `v`) is sorted by a background thread while the device compiles the next wave and
+    // joins the run when `v` is used up.  While such a sort is in flight no node slot is recycled (its comparator reads node states).
+    struct Cold { std::vector<Ent> ents; std::thread th; std::atomic<bool> done{false}; };
+    struct Run { std::vector<Ent> v; std::unique_ptr<Cold> cold; };
+    std::vector<Run> runs_;
+    int cold_open_ = 0;
+    std::vector<std::vector<uint32_t>> cand_; std::vector<size_t> head_, scan_;  // scratch of pop_many
+    bool async_sort_ = true;  // DDO_FRINGE_ASYNC=0: sort every burst at once (A/B runs)
+    static constexpr size_t kHot = 16384;
+    void sort_ents(std::vector<Ent>& v) const;
+    void join_cold(Run& run);
+    bool cold_busy();   // true while a background sort is still running (finished ones are folded into their runs)
+    void drop_cold();
+    std::vector<Ent>& tail_run(size_t r);  // run r with stale tail entries dropped and, if its sorted part is used up, its cold part joined
     size_t live_ = 0;
     // state index: NS open-addressing tables (node id, -1 empty, -2 tombstone), shard = top bits of the state hash
     static constexpr int NS_BITS = 6, NS = 1 << NS_BITS;
@@ -122,6 +150,9 @@ struct Solver {
     bool pipeline = false, pre_valid = false;
     std::vector<uint64_t> pre_states, pre_bits; std::vector<NoDupFringe::Item> pre_items;
     void prepop(); void unpop();
+    ~Solver();
+    Solver(const Solver&) = delete;
+    Solver& operator=(const Solver&) = delete;
     // scratch of one wave (kept to avoid reallocations)
     std::vector<uint64_t> w_states, w_bits, p_states, p_bits; std::vector<NoDupFringe::Item> w_items; std::vector<int32_t> p_val, p_ub, p_vars, p_tt; std::vector<NoDupFringe::PushRec> push_recs; std::vector<int> pop_ids;
 
