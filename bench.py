@@ -207,6 +207,9 @@ def run_ours(args, rank, world, local_rank):
     explored_all = allred_f(last["explored"], dist.ReduceOp.SUM if world > 1 else None)
     h2d_all = allred_f(last["h2d"], dist.ReduceOp.SUM if world > 1 else None)
     d2h_all = allred_f(last["d2h"], dist.ReduceOp.SUM if world > 1 else None)
+    cfg3 = None
+    if wl.kind == "misp" and not args.no_config3:  # every rank takes part (the fringe of config 3 is sharded like the main workload's)
+        cfg3 = second_workload_line(args, local_rank, world, comm)
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -255,8 +258,8 @@ def run_ours(args, rank, world, local_rank):
                             "achieved_by_kernel": {k: round(last["expanded"] * b_node / (v["ms"] * 1e-3) / 1e9, 1) for k, v in kt.items() if v["ms"] > 0 and k not in ("k_finalize_bottomup", "k_drain")},
                             "whole_step_frac": (expanded_all / (dev_ms * 1e-3)) * b_node / 1e9 / peak, "whole_step_frac_wall": (expanded_all / wall_max) * b_node / 1e9 / peak,
                             "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
-    if world == 1 and wl.kind == "misp" and not args.no_config3:
-        line["configs"] = {"config3_max2sat": second_workload_line(args, local_rank)}
+    if cfg3 is not None:
+        line["configs"] = {"config3_max2sat": cfg3}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(line), flush=True)
@@ -281,29 +284,50 @@ def check_against_golden(wl, args, world, last, explored_all, expanded_per_step)
     return {"checked": True, "file": f.name, "objective": g["best_lb"], "explored": g["explored"] if world == 1 else None, "expanded": g["expanded"] if world == 1 else None}
 
 
-def second_workload_line(args, local_rank):
-    """BASELINE config 3 (MAX2SAT 500 vars / 3000 clauses, W = 5000) measured in the same run, so that the driver's default invocation carries a
-    number for it: same definitions as the main line (value = expanded / wall clock of maximize(), device_value = / device time)."""
+def second_workload_line(args, local_rank, world=1, comm=None):
+    """BASELINE config 3 (MAX2SAT 500 vars / 3000 clauses, W = 5000, "1->8 B200 fringe-sharded") measured in the same run, so that the driver's
+    default invocation carries a number for it at every N: same definitions as the main line (value = expanded / wall clock of maximize(),
+    device_value = / device time).  At N > 1 every rank compiles the root DD pair, keeps its share of the root's cutset and runs its own
+    waves on it (ddo_solver_maximize_sharded): the per-GPU work is fixed, the total grows with N -- weak scaling.  The root pair is compiled
+    by every rank but counted once."""
     import copy
+    import torch
+    import torch.distributed as dist
     from ddo_b200 import FixedWidth, ParNoCachingSolverLel
     a = copy.copy(args)
     a.workload, a.wave, a.batch_cap, a.max_waves = "max2sat", 148, 148, 0
     wl = Workload(a)
     pb = wl.problem(local_rank)
     solver = ParNoCachingSolverLel(pb, FixedWidth(wl.width), wave_size=a.wave, batch_cap=a.batch_cap)
-    solver.maximize(max_waves=wl.max_waves)  # warm-up
-    exp = wall = dev = 0.0
-    for _ in range(2):
+
+    def run(max_waves):
         t0 = time.perf_counter()
-        solver.maximize(max_waves=wl.max_waves)
-        wall += time.perf_counter() - t0
-        st = solver.stats()
-        exp += st["expanded"]; dev += st["device_ms"]
+        if world == 1:
+            solver.maximize(max_waves=max_waves)
+        else:
+            solver.maximize_sharded(comm, max_waves=max_waves)
+        return time.perf_counter() - t0, solver.stats()
+
+    solver.maximize(max_waves=1)  # warm-up; also the size of the root DD pair (the same on every rank, no collective involved)
+    st_root = solver.stats()
+    run(wl.max_waves)
+    exp = wall = dev = 0.0
+    if world > 1:
+        dist.barrier()
+    for _ in range(2):
+        w, st = run(wl.max_waves)
+        wall += w; exp += st["expanded"]; dev += st["device_ms"]
+    if world > 1:
+        t = torch.tensor([exp], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        exp = float(t.item()) - 2 * (world - 1) * st_root["expanded"]
+        t = torch.tensor([wall, dev], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, dev = float(t[0].item()), float(t[1].item())
     S_bytes = wl.state_bytes(pb)
     b_node = (S_bytes + 8) + 2 * (S_bytes + 16)
     peak, _ = load_peaks()
-    out = {"metric": wl.metric, "value": exp / wall, "unit": UNIT, "device_value": exp / (dev * 1e-3), "steps": 2, "warmup": 1, "ms_per_step": wall * 1e3 / 2,
-           "workload": f"{wl.step_desc}, {wl.desc}", "whole_step_frac": exp / (dev * 1e-3) * b_node / 1e9 / peak, "bytes_per_node": b_node}
+    out = {"metric": wl.metric, "value": exp / wall, "unit": UNIT, "device_value": exp / (dev * 1e-3), "n_gpus": world, "scaling": "weak", "steps": 2, "warmup": 2,
+           "ms_per_step": wall * 1e3 / 2, "expanded_nodes_per_step": exp / 2, "workload": f"{wl.step_desc}, {wl.desc}",
+           "whole_step_frac": exp / (dev * 1e-3) * b_node / 1e9 / (peak * world), "bytes_per_node": b_node}
     solver.close() if hasattr(solver, "close") else None
     return out
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 
 namespace ddo {
@@ -453,7 +454,11 @@ struct PhaseTimer { double& acc; double t0; explicit PhaseTimer(double& a) : acc
 Solver::Solver(Engine* e, int kind, const uint64_t* rs, int64_t rv, int wk, uint64_t w, int ws)
     : eng(e), model_kind(kind), n_vars(e->n_vars), words(e->abi_words), root_state(rs, rs + e->abi_words), root_value(rv), width_kind(wk), width(w),
       wave_size(ws), fringe(e->abi_words, (e->n_vars + 63) / 64, kind) {
-    if (const char* p = std::getenv("DDO_WAVE_TRACE")) trace_file = std::fopen(p, "w");
+    if (const char* p = std::getenv("DDO_WAVE_TRACE")) {  // one file per rank under torchrun
+        std::string path(p);
+        if (const char* r = std::getenv("RANK")) path += std::string(".rank") + r;
+        trace_file = std::fopen(path.c_str(), "w");
+    }
 }
 Solver::~Solver() {
     if (trace_file) std::fclose(trace_file);
@@ -993,8 +998,10 @@ int Solver::maximize_sharded(const ShardComm& cm, double time_budget_s, uint64_t
     for (;;) {
         mine[0] = best_lb; mine[1] = top; mine[2] = (int64_t)open_len(); mine[3] = has_sol ? sol_value : INT64_MIN;
         if (cut) mine[2] = -1;  // a rank that ran out of time stops everybody
+        const double tg0 = now_ms();
         rc = cm.allgather(cm.ctx, mine.data(), 4, all.data());  // ---- the ONE collective of the wave
         if (rc != DDO_OK) return rc;
+        const double tg1 = now_ms();
         ++colls;
         int64_t g_lb = INT64_MIN, g_top = INT64_MIN, total = 0; bool any_cut = false;
         std::vector<int64_t> lens(world);
@@ -1053,6 +1060,8 @@ int Solver::maximize_sharded(const ShardComm& cm, double time_budget_s, uint64_t
                     }
                 }
         }
+        if (trace_file)  // "G": wave about to run, ms spent in the gather (= waiting for the slowest rank), ms in hand-offs, own open nodes, all open nodes
+            std::fprintf(trace_file, "G %llu %.3f %.3f %lld %lld\n", (unsigned long long)nwaves + 1, tg1 - tg0, now_ms() - tg1, (long long)mine[2], (long long)total);
         rc = wave(&cutoff, o3);  // a rank with an empty fringe returns immediately (top = INT64_MIN)
         if (rc == DDO_CUTOFF) { cut = true; top = INT64_MIN; continue; }
         if (rc != DDO_OK) return rc;
