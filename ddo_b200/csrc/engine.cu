@@ -420,7 +420,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
         else if (slots < E->finish_split_min) CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(slots), dim3(1024), E->finish_smem, st, ev, t, 0));
         else {  // a large batch: the wide DDs one per SM, the narrow ones five to an SM (kernels.cuh, k_finish_s)
             CUDA_TRY(launch_k(pdl, k_finish<S>, dim3(std::min(slots, E->num_sms)), dim3(1024), E->finish_smem, st, ev, t, 1));
-            CUDA_TRY(launch_k(pdl, k_finish_s<S>, dim3(std::min(slots, E->num_sms * 6)), dim3(256), 0, st, ev, t, slots));
+            CUDA_TRY(launch_k(pdl, k_finish_s<S>, dim3(std::min(slots, E->num_sms * (FIN_S_NT == 128 ? 7 : 6))), dim3(FIN_S_NT), 0, st, ev, t, slots));
             ++g_kernel_launches;
         }
         E->prof_mark(1);

@@ -210,6 +210,24 @@ __device__ __forceinline__ int plan_find(const int* off, int count, int tile) {
     return lo;
 }
 
+// The same lookup by a whole warp in two dependent round trips instead of log2(count): 32 samples of the plan pick a segment, the segment's
+// entries pick the DD.  Every lane of the warp must call it with the same arguments.
+__device__ __forceinline__ int plan_find_warp(const int* off, int count, int tile) {
+    const int lane = threadIdx.x & 31;
+    const int str = (count + 31) >> 5;
+    const bool le1 = off[min(lane * str, count - 1)] <= tile;  // monotone over the lanes; lane 0 reads off[0] = 0
+    const int seg = 31 - __clz(__ballot_sync(0xffffffffu, le1));
+    const int base = min(seg * str, count - 1), end = min(base + str, count);
+    int best = base;
+    for (int j = base; j < end; j += 32) {
+        const int i = j + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, i < end && off[i] <= tile);
+        if (!b) break;
+        best = j + 31 - __clz(b);
+    }
+    return best;
+}
+
 #ifndef DDO_EXPAND_MINB
 #define DDO_EXPAND_MINB 8
 #endif
@@ -427,7 +445,7 @@ __global__ void __launch_bounds__(256, DDO_EXPAND1_MINB) k_expand1(EV ev, int t,
     for (int i = tid; i < 64 * S; i += 256) s_hist[i] = 0;
     if (tid == 0) s_claims = 0;
     int hist_k = -1;
-    int k = tile_lo < tile_hi ? plan_find(off, count, tile_lo) : 0;
+    int k = tile_lo < tile_hi ? plan_find_warp(off, count, tile_lo) : 0;  // (block-uniform condition: whole warps call it)
     const int buf = t & 1;
     for (int tile = tile_lo; tile < tile_hi;) {
         while (off[k + 1] <= tile) ++k;
@@ -1328,8 +1346,12 @@ __global__ void __launch_bounds__(1024, 1) k_finish(EV ev, int t, int size_class
 // and runs 1024 threads, so one DD occupies an SM; a batch of a thousand DDs whose layers hold a few hundred nodes then takes seven
 // rounds of CTAs per layer step for work a quarter of a CTA could do.  Here a DD with at most FIN_SMALL_C candidates gets 256 threads
 // and 18 KB of keys: five to six DDs per SM.
+#ifndef DDO_FIN_S_NT
+#define DDO_FIN_S_NT 256
+#endif
+constexpr int FIN_S_NT = DDO_FIN_S_NT;  // threads of a k_finish_s CTA (128 threads, seven CTAs per SM, measured slower: k_finish 246 vs 224 ms per config-2 solve)
 template <int S>
-__global__ void __launch_bounds__(256) k_finish_s(EV ev, int t, int slots) {
+__global__ void __launch_bounds__(FIN_S_NT) k_finish_s(EV ev, int t, int slots) {
     pdl_enter();
     __shared__ FinishSmem sm;
     __shared__ int s_last;
@@ -1337,7 +1359,7 @@ __global__ void __launch_bounds__(256) k_finish_s(EV ev, int t, int slots) {
     __shared__ __align__(16) uint8_t s_stat[FIN_SMALL_C];
     const int ns = ev.fin_cnt[1];
     for (int j = blockIdx.x; j < ns; j += gridDim.x) {
-        finish_body<S, 256>(ev, t, sm, s_keys, s_stat, ev.fin_list[ev.K + j]);
+        finish_body<S, FIN_S_NT>(ev, t, sm, s_keys, s_stat, ev.fin_list[ev.K + j]);
         __syncthreads();
     }
     finish_plan<S>(ev, sm, &s_last, slots);
@@ -1952,7 +1974,7 @@ __global__ void __launch_bounds__(256) k_compact1(EV ev, int t, int count) {
     const int wglobal = (blockIdx.x * 256 + threadIdx.x) >> 5, wstride = (gridDim.x * 256) >> 5;
     for (int u = wglobal; u < total_units; u += wstride) {
         const int tile = u / UPT;
-        const int k = plan_find(off, count, tile);
+        const int k = plan_find_warp(off, count, tile);
         const DDCtl* ctl = ev.ctl + k;
         const int ncand = ctl->ncand;
         const int c0 = (tile - off[k]) * CPB + (u % UPT) * 32;

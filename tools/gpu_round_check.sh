@@ -1,4 +1,2 @@
-DDO_FRINGE_PROF=1 timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -E '^\[solve\]|^\[pop_many|ms_per_step' | cut -c1-700 | tail -4
-DDO_POP_THREAD=0 timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"host_fringe_ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*'
-timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"host_fringe_ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*'
-timeout 900 python -m pytest tests -m gpu -x -q -k "trajectory or sharded or solver or fringe or max2sat" 2>&1 | tail -3
+timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"host_fringe_ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*\|"kernel_ms_per_step": {[^}]*}'
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
