@@ -424,6 +424,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own log lines (its version banner) must not land on stdout next to the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
