@@ -59,12 +59,12 @@ static inline uint64_t lex_word_host(uint64_t w) {  // ~bitreverse: larger = Gre
     return ~__builtin_bswap64(w);
 }
 NoDupFringe::Ent NoDupFringe::make_ent(int id) const {
-    const Item& it = items_[id];
+    const Item& it = hdr(id).it;
     Ent e;
     e.k1 = ((uint64_t)((uint32_t)it.ub ^ 0x80000000u) << 32) | ((uint32_t)it.value ^ 0x80000000u);
-    if (kind_ == DDO_MODEL_MAX2SAT) e.k2 = ((uint64_t)(uint32_t)popc_[id] << 32) | ((uint64_t)(uint32_t)it.depth << 8);  // (rank, depth)
-    else e.k2 = ((uint64_t)(uint16_t)popc_[id] << 48) | (lex_word_host(state(id)[0]) >> 16);
-    e.id = id; e.ver = ver_[id];
+    if (kind_ == DDO_MODEL_MAX2SAT) e.k2 = ((uint64_t)(uint32_t)hdr(id).popc << 32) | ((uint64_t)(uint32_t)it.depth << 8);  // (rank, depth)
+    else e.k2 = ((uint64_t)(uint16_t)hdr(id).popc << 48) | (lex_word_host(state(id)[0]) >> 16);
+    e.id = id; e.ver = hdr(id).ver;
     return e;
 }
 bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
@@ -76,7 +76,7 @@ bool NoDupFringe::ent_less(const Ent& a, const Ent& b) const {
 
 void NoDupFringe::clear() {  // no_duplicate.rs:168-174
     drop_cold();
-    states_.clear(); bits_.clear(); items_.clear(); popc_.clear(); hash_.clear(); ver_.clear(); recycle_.clear();
+    nodes_.clear(); recycle_.clear();
     pending_.clear(); runs_.clear(); live_ = 0;
     for (Shard& sh : shards_) { std::fill(sh.tab.begin(), sh.tab.end(), -1); sh.used = 0; sh.live = 0; }  // the tables keep their size for the next search
 }
@@ -89,16 +89,16 @@ void NoDupFringe::rehash(Shard& sh, size_t min_cap) {
     const size_t mask = cap - 1;
     for (int id : old)
         if (id >= 0) {
-            size_t s = hash_[id] & mask;
+            size_t s = hdr(id).hash & mask;
             while (sh.tab[s] >= 0) s = (s + 1) & mask;
             sh.tab[s] = id; ++sh.used;
         }
 }
 void NoDupFringe::table_insert(int id) {
-    Shard& sh = shards_[shard_of(hash_[id])];
+    Shard& sh = shards_[shard_of(hdr(id).hash)];
     if ((sh.used + 1) * 2 > sh.tab.size()) rehash(sh, (sh.live + 1) * 4);
     const size_t mask = sh.tab.size() - 1;
-    size_t s = hash_[id] & mask;
+    size_t s = hdr(id).hash & mask;
     while (sh.tab[s] >= 0) s = (s + 1) & mask;
     if (sh.tab[s] == -1) ++sh.used;
     sh.tab[s] = id; ++sh.live;
@@ -110,15 +110,15 @@ int NoDupFringe::table_find(const uint64_t* st, uint64_t h, int32_t depth) const
     size_t s = h & mask;
     while (sh.tab[s] != -1) {
         const int id = sh.tab[s];
-        if (id >= 0 && hash_[id] == h && std::memcmp(state(id), st, (size_t)W * 8) == 0 && (kind_ != DDO_MODEL_MAX2SAT || items_[id].depth == depth)) return id;
+        if (id >= 0 && hdr(id).hash == h && std::memcmp(state(id), st, (size_t)W * 8) == 0 && (kind_ != DDO_MODEL_MAX2SAT || hdr(id).it.depth == depth)) return id;
         s = (s + 1) & mask;
     }
     return -1;
 }
 void NoDupFringe::table_erase(int id) {
-    Shard& sh = shards_[shard_of(hash_[id])];
+    Shard& sh = shards_[shard_of(hdr(id).hash)];
     const size_t mask = sh.tab.size() - 1;
-    size_t s = hash_[id] & mask;
+    size_t s = hdr(id).hash & mask;
     while (sh.tab[s] != id) s = (s + 1) & mask;
     sh.tab[s] = -2; --sh.live;
 }
@@ -132,29 +132,29 @@ int NoDupFringe::push_one(const uint64_t* st, uint64_t h, int32_t value, int32_t
     const int found = table_find(st, h, depth);
     if (found >= 0) {  // Occupied, no_duplicate.rs:92-118: keep the longer path, ub = max of the known ubs
         const int id = found;
-        const int32_t old_lp = items_[id].value, old_ub = items_[id].ub;
+        const int32_t old_lp = hdr(id).it.value, old_ub = hdr(id).it.ub;
         const int32_t merged_ub = std::max(ub, old_ub);
         bool changed = false;
         if (value > old_lp) {
-            items_[id] = Item{value, merged_ub, depth, rec};
-            std::memset(bits_.at(id), 0, (size_t)PW * 8);
-            std::memcpy(bits_.at(id), bits, (size_t)nbits_words * 8);
+            hdr(id).it = Item{value, merged_ub, depth, rec};
+            std::memset(bits_w(id), 0, (size_t)PW * 8);
+            std::memcpy(bits_w(id), bits, (size_t)nbits_words * 8);
             changed = true;
         }
-        if (ub > old_ub) { items_[id].ub = ub; changed = true; }
-        if (changed) { ++ver_[id]; pending.push_back(make_ent(id)); }  // re-keyed: the old entry goes stale
+        if (ub > old_ub) { hdr(id).it.ub = ub; changed = true; }
+        if (changed) { ++hdr(id).ver; pending.push_back(make_ent(id)); }  // re-keyed: the old entry goes stale
         return 0;
     }
     const int id = new_id;  // Vacant, no_duplicate.rs:119-135
-    items_[id] = Item{value, ub, depth, rec};
-    std::memcpy(states_.at(id), st, (size_t)W * 8);
-    std::memset(bits_.at(id), 0, (size_t)PW * 8);
-    std::memcpy(bits_.at(id), bits, (size_t)nbits_words * 8);
+    hdr(id).it = Item{value, ub, depth, rec};
+    std::memcpy(state_w(id), st, (size_t)W * 8);
+    std::memset(bits_w(id), 0, (size_t)PW * 8);
+    std::memcpy(bits_w(id), bits, (size_t)nbits_words * 8);
     int pc = 0;
     if (kind_ == DDO_MODEL_MAX2SAT) { const int32_t* x = reinterpret_cast<const int32_t*>(st); for (int j = 0; j < 2 * W; ++j) pc += x[j] < 0 ? -x[j] : x[j]; }
     else for (int j = 0; j < W; ++j) pc += __builtin_popcountll(st[j]);
-    popc_[id] = pc; hash_[id] = h;
-    ++ver_[id];
+    hdr(id).popc = pc; hdr(id).hash = h;
+    ++hdr(id).ver;
     table_insert(id);
     pending.push_back(make_ent(id));
     return 1;
@@ -163,9 +163,8 @@ void NoDupFringe::push(const uint64_t* st, int32_t value, int32_t ub, int32_t de
     int id;
     const bool fresh = recycle_.empty() || cold_busy();  // no slot is reused while a background sort may still compare its old state
     if (fresh) {
-        id = (int)items_.size();
-        items_.push_back(Item{}); popc_.push_back(0); hash_.push_back(0); ver_.push_back(0);
-        states_.grow(); bits_.grow();
+        id = (int)nodes_.count;
+        new_node();
     } else id = recycle_.back();
     if (push_one(st, key_hash(st, depth), value, ub, depth, rec, bits, nbits_words, id, pending_)) {
         if (!fresh) recycle_.pop_back();
@@ -199,11 +198,10 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
     tp2 = now_ms();
     std::vector<int> slot(n);
     const size_t nrec = std::min(n, recycle_.size());
-    const size_t base = items_.size(), fresh = n - nrec;
+    const size_t base = nodes_.count, fresh = n - nrec;
     for (size_t q = 0; q < n; ++q) slot[order[q]] = q < fresh ? (int)(base + q) : recycle_[recycle_.size() - 1 - (q - fresh)];
     recycle_.resize(recycle_.size() - nrec);
-    items_.resize(base + fresh); popc_.resize(base + fresh, 0); hash_.resize(base + fresh, 0); ver_.resize(base + fresh, 0);
-    for (size_t i = 0; i < fresh; ++i) { states_.grow(); bits_.grow(); }
+    for (size_t i = 0; i < fresh; ++i) nodes_.grow();  // (their headers are initialised by the thread that fills them: no pass over cold memory here)
     tp3 = now_ms();
     std::vector<std::vector<Ent>> pend(T);
     std::vector<std::vector<int>> unused(T);
@@ -221,6 +219,7 @@ void NoDupFringe::push_many(const std::vector<PushRec>& recs) {
                     for (uint32_t q = start[s]; q < start[s + 1]; ++q) {
                         const uint32_t i = order[q];
                         const PushRec& r = recs[i];
+                        if ((size_t)slot[i] >= base) hdr(slot[i]).ver = 0;
                         if (push_one(r.state, h[i], r.value, r.ub, r.depth, r.rec, r.bits, r.nbits_words, slot[i], pend[w])) ++add;
                         else unused[w].push_back(slot[i]);
                     }
@@ -242,12 +241,15 @@ void NoDupFringe::flush_pending() {
     static const bool prof = std::getenv("DDO_FRINGE_PROF") != nullptr; const double tf0 = now_ms(); double tf1 = 0, tf2 = 0; const size_t nf = pending_.size();
     // entries re-keyed or popped since they were queued are dropped first: a stale entry's slot may hold another state by now, and the
     // comparator must never dereference it (the runs below stay sorted by the keys of LIVE nodes only)
-    pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [this](const Ent& e) { return e.ver != ver_[e.id]; }), pending_.end());
+    pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [this](const Ent& e) { return e.ver != hdr(e.id).ver; }), pending_.end());
     if (pending_.empty()) return;
     auto less = [this](const Ent& a, const Ent& b) { return ent_less(a, b); };
     tf1 = now_ms();
     Run nr;
-    if (pending_.size() < (1u << 15) || !async_sort_) { sort_ents(pending_); nr.v.swap(pending_); }
+    // a burst is split when it holds more than the next two waves can pop from it: 4096 entries of a mid-sized burst (the cutsets of a
+    // narrow wave, ~10 000 nodes: 0.5 ms instead of 1.7 ms of sorting on the critical path, a dozen times per solve), 16 384 of a large one
+    const size_t kHot = pending_.size() >= (1u << 16) ? kHotLarge : kHotSmall;
+    if (pending_.size() < 2 * kHotSmall || !async_sort_) { sort_ents(pending_); nr.v.swap(pending_); }
     else {
         // a wide wave's cutsets (hundreds of thousands of nodes): the next waves only need the best few thousand of them -- select those,
         // sort them now, and let a background thread sort the rest while the device works
@@ -277,7 +279,7 @@ void NoDupFringe::flush_pending() {
         std::vector<Ent> m;
         m.reserve(x.size() + y.size());
         size_t i = 0, j = 0;
-        auto skip_stale = [this](const std::vector<Ent>& v, size_t& q) { while (q < v.size() && v[q].ver != ver_[v[q].id]) ++q; };
+        auto skip_stale = [this](const std::vector<Ent>& v, size_t& q) { while (q < v.size() && v[q].ver != hdr(v[q].id).ver) ++q; };
         for (;;) {  // stale entries are dropped BEFORE they are compared (their slot may have been recycled for another state)
             skip_stale(x, i); skip_stale(y, j);
             if (i == x.size() && j == y.size()) break;
@@ -327,7 +329,7 @@ void NoDupFringe::drop_cold() {
 std::vector<NoDupFringe::Ent>& NoDupFringe::tail_run(size_t r) {
     Run& run = runs_[r];
     for (;;) {
-        while (!run.v.empty() && run.v.back().ver != ver_[run.v.back().id]) run.v.pop_back();  // stale
+        while (!run.v.empty() && run.v.back().ver != hdr(run.v.back().id).ver) run.v.pop_back();  // stale
         if (!run.v.empty() || !run.cold) return run.v;
         join_cold(run);
     }
@@ -346,9 +348,9 @@ int NoDupFringe::pop() {
     brun.pop_back();
     if (brun.size() >= 8) {  // the next pops most likely come from the same run: start fetching their node records and states
         const int nid = brun[brun.size() - 8].id;
-        __builtin_prefetch(&items_[nid]); __builtin_prefetch(states_.at(nid)); __builtin_prefetch(bits_.at(nid));
+        prefetch(nid);
     }
-    ++ver_[id];  // any other entry of this node is now stale
+    ++hdr(id).ver;  // any other entry of this node is now stale
     recycle_.push_back(id);
     table_erase(id);
     --live_;
@@ -382,8 +384,8 @@ int NoDupFringe::pop_many(int k, std::vector<int>& ids, const PopOut* out) {
             const size_t stop = c.size() + CHUNK;
             while (q > 0 && c.size() < stop) {
                 --q;
-                if (q >= 16) __builtin_prefetch(&ver_[v[q - 16].id]);
-                if (v[q].ver == ver_[v[q].id]) c.push_back((uint32_t)q);
+                if (q >= 16) __builtin_prefetch(nodes_.at(v[q - 16].id));
+                if (v[q].ver == hdr(v[q].id).ver) c.push_back((uint32_t)q);
             }
             scan_[r] = q;
             if (head_[r] < c.size()) return true;
@@ -422,21 +424,21 @@ int NoDupFringe::pop_many(int k, std::vector<int>& ids, const PopOut* out) {
     if (out) { out->items->reserve(n); out->states->reserve(n * (size_t)W); out->bits->reserve(n * (size_t)out->bits_words); }
     constexpr size_t D1 = 24, D2 = 12;
     for (size_t i = 0; i < n; ++i) {
-        if (i + D1 < n) { __builtin_prefetch(&hash_[ids[i + D1]]); __builtin_prefetch(&ver_[ids[i + D1]], 1); }
+        if (i + D1 < n) __builtin_prefetch(nodes_.at(ids[i + D1]), 1);  // header: item, hash, version
         if (i + D2 < n) {
-            const uint64_t h = hash_[ids[i + D2]];
+            const uint64_t h = hdr(ids[i + D2]).hash;
             const Shard& sh = shards_[shard_of(h)];
             __builtin_prefetch(&sh.tab[h & (sh.tab.size() - 1)], 1);
             prefetch(ids[i + D2]);
         }
         const int id = ids[i];
-        ++ver_[id];
+        ++hdr(id).ver;
         recycle_.push_back(id);
         table_erase(id);
         if (out) {
-            out->items->push_back(items_[id]);
-            out->states->insert(out->states->end(), states_.at(id), states_.at(id) + W);
-            out->bits->insert(out->bits->end(), bits_.at(id), bits_.at(id) + out->bits_words);
+            out->items->push_back(hdr(id).it);
+            out->states->insert(out->states->end(), state_w(id), state_w(id) + W);
+            out->bits->insert(out->bits->end(), bits_w(id), bits_w(id) + out->bits_words);
         }
     }
     live_ -= n;
@@ -668,24 +670,39 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
         const int total = eng->drain_all(slots, caps.data(), lbs.data(), &pw);
         if (total < 0) return total;
         const double tc1 = now_ms();
-        p_states.reserve(p_states.size() + (size_t)total * W); p_bits.reserve(p_bits.size() + (size_t)total * PWN);
-        p_val.reserve(p_val.size() + total); p_ub.reserve(p_ub.size() + total);
-        int cur_dd = -1;
         if (total > 0) { const int r2 = eng->fetch_vars_all(slots, vars); if (r2 != DDO_OK) return r2; }
+        const size_t base = p_val.size();
+        p_val.resize(base + total); p_ub.resize(base + total); p_tt.resize(base + total);
+        p_bits.resize((base + total) * (size_t)PWN, 0ull);
+        if (!p_direct) p_states.resize((base + total) * (size_t)W);
+        // the DD boundaries (records arrive grouped by DD slot), sequentially: one Pending per DD that drained something
+        int cur_dd = -1;
         for (int r = 0; r < total; ++r) {
             const int j = eng->h_out_dd[r];
             if (j != cur_dd) {
                 cur_dd = j;
                 const int lel = frontier ? std::max(0, eng->h_ctl[j].t_term) : eng->h_ctl[j].lel;  // layers whose variables the paths may use
-                pend.push_back(Pending{slot_wave[j], lel, (int)p_val.size(), 0});
+                pend.push_back(Pending{slot_wave[j], lel, (int)(base + r), 0});
                 p_vars.insert(p_vars.end(), vars.begin() + (size_t)j * eng->Lcur, vars.begin() + (size_t)j * eng->Lcur + lel);
             }
-            if (!p_direct) p_states.insert(p_states.end(), &eng->h_out_state[(size_t)r * eng->S], &eng->h_out_state[(size_t)r * eng->S] + W);
-            p_bits.resize(p_bits.size() + PWN, 0ull);
-            std::memcpy(&p_bits[p_bits.size() - PWN], &eng->h_out_path[(size_t)r * pw], (size_t)std::min(pw, PWN) * 8);
-            p_val.push_back(eng->h_out_val[r]); p_ub.push_back(eng->h_out_ub[r]);
-            p_tt.push_back(frontier ? eng->h_out_tt[r] : pend.back().lel);
             pend.back().count++;
+        }
+        // the records themselves: independent copies, on a few threads when the batch drained a wide wave's cutsets
+        auto fill = [&](int r0, int r1) {
+            for (int r = r0; r < r1; ++r) {
+                const size_t q = base + r;
+                if (!p_direct) std::memcpy(&p_states[q * W], &eng->h_out_state[(size_t)r * eng->S], (size_t)W * 8);
+                std::memcpy(&p_bits[q * PWN], &eng->h_out_path[(size_t)r * pw], (size_t)std::min(pw, PWN) * 8);
+                p_val[q] = eng->h_out_val[r]; p_ub[q] = eng->h_out_ub[r];
+                p_tt[q] = frontier ? eng->h_out_tt[r] : eng->h_ctl[eng->h_out_dd[r]].lel;
+            }
+        };
+        if (total < 32768) fill(0, total);
+        else {
+            constexpr int T = 8;
+            std::vector<std::thread> ts;
+            for (int w = 0; w < T; ++w) ts.emplace_back(fill, (int)((int64_t)total * w / T), (int)((int64_t)total * (w + 1) / T));
+            for (auto& t : ts) t.join();
         }
         if (fringe_prof && total > 10000) std::fprintf(stderr, "[collect_drain %d] drain_all %.1f  collect %.1f ms\n", total, tc1 - tc0, now_ms() - tc1);
         return DDO_OK;

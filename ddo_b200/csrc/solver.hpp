@@ -36,7 +36,7 @@ public:
     //       DDO_MODEL_MAX2SAT -- Max2SatRanking (rank = sum |benefit|, heuristics.rs:33-37) refined canonically by (depth, lexicographic
     //       benefits); the depth is part of the state (model.rs:59-62 derives Hash / Eq over both fields).
     NoDupFringe(int words, int pw, int kind = 0) : W(words), PW(pw), kind_(kind) {
-        states_.init(words); bits_.init(pw);
+        nodes_.init(HW + words + pw);
         if (const char* e = std::getenv("DDO_FRINGE_ASYNC")) async_sort_ = std::atoi(e) != 0;
     }
     ~NoDupFringe() { drop_cold(); }
@@ -59,10 +59,10 @@ public:
     // state, the first bits_words words of the path bits) are appended to the caller's vectors while their cache lines arrive.
     struct PopOut { std::vector<Item>* items; std::vector<uint64_t>* states; std::vector<uint64_t>* bits; int bits_words; };
     int pop_many(int k, std::vector<int>& ids, const PopOut* out = nullptr);
-    void prefetch(int id) const { __builtin_prefetch(&items_[id]); __builtin_prefetch(states_.at(id)); __builtin_prefetch(bits_.at(id)); }
-    const uint64_t* state(int id) const { return states_.at(id); }
-    const uint64_t* bits(int id) const { return bits_.at(id); }
-    const Item& item(int id) const { return items_[id]; }
+    void prefetch(int id) const { const char* p = reinterpret_cast<const char*>(nodes_.at(id)); for (int b = 0; b < (HW + W + PW) * 8; b += 64) __builtin_prefetch(p + b); }
+    const uint64_t* state(int id) const { return nodes_.at(id) + HW; }
+    const uint64_t* bits(int id) const { return nodes_.at(id) + HW + W; }
+    const Item& item(int id) const { return hdr(id).it; }
 private:
     // Priority structure: the reference's updatable binary heap (no_duplicate.rs:206-323) pops in the MaxUB order, a strict total order
     // for MISP (ub, value, then MispRanking on distinct states).  Pushes arrive in bursts (the cutsets of a wave) and pops in bursts (the
@@ -79,14 +79,19 @@ private:
         uint64_t* at(size_t id) const { return blocks[id >> shift].get() + (id & (per_block - 1)) * (size_t)W; }
         void grow() { if (count == blocks.size() * per_block) blocks.emplace_back(new uint64_t[per_block * (size_t)W]); ++count; }
         void clear() { count = 0; }  // the blocks stay (no page faults when the next search refills them)
-    } states_, bits_;  // packed states and path bits of the nodes
-    std::vector<Item> items_;
-    std::vector<int32_t> popc_;  // ranking key of the state: popcount (MISP) / sum |benefit| (MAX2SAT)
-    std::vector<uint64_t> hash_;
-    std::vector<uint32_t> ver_;
+    } nodes_;
+    // One record per node: [Hdr][packed state, W words][path bits, PW words], contiguous (160 bytes for MISP at n = 500): a pop touches one
+    // run of adjacent cache lines instead of one line in each of five arrays.
+    struct Hdr { Item it; uint64_t hash; uint32_t ver; int32_t popc; };  // popc = ranking key of the state: popcount (MISP) / sum |benefit| (MAX2SAT)
+    static constexpr int HW = 4;  // header words
+    static_assert(sizeof(Hdr) == HW * 8, "node header layout");
+    Hdr& hdr(int id) const { return *reinterpret_cast<Hdr*>(nodes_.at(id)); }
+    uint64_t* state_w(int id) const { return nodes_.at(id) + HW; }
+    uint64_t* bits_w(int id) const { return nodes_.at(id) + HW + W; }
+    void new_node() { nodes_.grow(); Hdr& h = hdr((int)nodes_.count - 1); h.it = Item{}; h.hash = 0; h.ver = 0; h.popc = 0; }
     std::vector<int> recycle_;
     std::vector<Ent> pending_;
-    // A run is sorted ascending (pops take the back).  A large burst is split at flush time: its best kHot entries are sorted at once (`v`),
+    // A run is sorted ascending (pops take the back).  A large burst is split at flush time: its best few thousand entries are sorted at once (`v`),
     // the rest (`cold`, every entry below every entry of `v`) is sorted by a background thread while the device compiles the next wave and
     // joins the run when `v` is used up.  While such a sort is in flight no node slot is recycled (its comparator reads node states).
     struct Cold { std::vector<Ent> ents; std::thread th; std::atomic<bool> done{false}; };
@@ -95,7 +100,7 @@ private:
     int cold_open_ = 0;
     std::vector<std::vector<uint32_t>> cand_; std::vector<size_t> head_, scan_;  // scratch of pop_many
     bool async_sort_ = true;  // DDO_FRINGE_ASYNC=0: sort every burst at once (A/B runs)
-    static constexpr size_t kHot = 16384;
+    static constexpr size_t kHotLarge = 16384, kHotSmall = 4096;
     void sort_ents(std::vector<Ent>& v) const;
     void join_cold(Run& run);
     bool cold_busy();   // true while a background sort is still running (finished ones are folded into their runs)
