@@ -242,11 +242,21 @@ int Engine::slots_for(int layers_needed) const {
     return (int)std::min<size_t>((size_t)K, pool_layers / (size_t)std::max(1, layers_needed));
 }
 
+int Engine::layers_bound(const uint64_t* state, int depth) const {
+    int b = n_vars - depth + 1;
+    if (model && state) {  // the MISP model
+        int pc = 0;
+        for (int j = 0; j < abi_words; ++j) pc += __builtin_popcountll(state[j]);
+        b = std::min(b, pc + 2);
+    }
+    return std::max(1, std::min(b, Lmax));
+}
+
 int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
     if (count < 1 || count > root_cap) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
     const int words = abi_words;
     staged_layers = 1;
-    for (int i = 0; i < count; ++i) staged_layers = std::max(staged_layers, n_vars - depths[i] + 1);
+    for (int i = 0; i < count; ++i) staged_layers = std::max(staged_layers, layers_bound(states + (size_t)i * words, depths[i]));
     for (int i = 0; i < count; ++i) {
         if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
         if (values[i] < -(1ll << 30) || values[i] > (1ll << 30)) { set_error("root value outside the 31-bit device range"); return DDO_ERR_UNSUPPORTED; }
@@ -459,7 +469,7 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
 static int compile_impl(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
     // the log stride of this batch: the layers its deepest DD can have (every kernel and every host-side read of the logs uses ev.Lmax)
     E->Lcur = std::min(E->Lmax, std::max(1, E->staged_layers));
-    if ((size_t)slots * (size_t)E->Lcur > E->pool_layers) { set_error("batch too large for the log pool: slots x (nb_variables - depth + 1) layers exceed it (see Engine::slots_for)"); return DDO_ERR_CAPACITY; }
+    if ((size_t)slots * (size_t)E->Lcur > E->pool_layers) { set_error("batch too large for the log pool: slots x layers of its deepest DD exceed it (see Engine::slots_for, Engine::layers_bound)"); return DDO_ERR_CAPACITY; }
     E->ev.Lmax = E->Lcur;
     const EV& ev = E->ev;
     CUDA_TRY(cudaSetDevice(E->device));

@@ -129,6 +129,11 @@ struct Engine {
     // so the same memory holds several times more DDs in lock-step (Lcur = log stride of the current batch, set by stage_roots).
     int Klog = 0, Lcur = 0; size_t pool_layers = 0; int staged_layers = 0;
     virtual int slots_for(int layers_needed) const;  // DD slots a batch whose deepest DD has `layers_needed` layers may use
+    // Layers (log entries) a DD rooted at `state` / `depth` can have.  Every model: one per undecided variable, plus the terminal layer.
+    // MISP: next_variable only returns a vertex that some state of the layer still holds (misp/main.rs:109-143), every state is a subset
+    // of the root state and a branched vertex leaves every descendant, so a DD has at most popcount(root state) layers -- for the
+    // sub-problems of G(500, 0.5) a quarter of n - depth, i.e. four times the DDs per batch in the same log pool.
+    int layers_bound(const uint64_t* state, int depth) const;
     int cutset_type = DDO_LAST_EXACT_LAYER;
     int num_sms = 148;
     int layer_chunk = 16;      // layer steps launched between two host polls of the `active` counter / cutoff flag (DDO_LAYER_CHUNK)

@@ -709,7 +709,7 @@ int Solver::wave_body(const volatile int32_t* cutoff_flag, int64_t out3[3]) {
     };
     {   // the deeper the sub-problems, the fewer layers their DDs log, the more of them fit the log pool (Engine::slots_for)
         int lneed = 1;
-        for (int i : ov) lneed = std::max(lneed, n_vars - depths[i] + 1);
+        for (int i : ov) lneed = std::max(lneed, eng->layers_bound(&w_states[(size_t)i * W], depths[i]));
         cap = std::max(1, eng->slots_for(lneed));
     }
     bool dual = eng->dual_enabled && cap >= 2;
