@@ -255,8 +255,6 @@ int Engine::layers_bound(const uint64_t* state, int depth) const {
 int Engine::stage_roots(int count, const uint64_t* widths, const uint64_t* states, const int64_t* values, const int32_t* depths) {
     if (count < 1 || count > root_cap) { set_error("batch larger than batch_cap"); return DDO_ERR_CAPACITY; }
     const int words = abi_words;
-    staged_layers = 1;
-    for (int i = 0; i < count; ++i) staged_layers = std::max(staged_layers, layers_bound(states + (size_t)i * words, depths[i]));
     for (int i = 0; i < count; ++i) {
         if (widths[i] > (uint64_t)Wcap) { set_error("max_width larger than max_width_cap"); return DDO_ERR_CAPACITY; }
         if (values[i] < -(1ll << 30) || values[i] > (1ll << 30)) { set_error("root value outside the 31-bit device range"); return DDO_ERR_UNSUPPORTED; }
@@ -468,6 +466,8 @@ static int run_layers(Engine* E, int count, int slots, int comp_type, int64_t be
 
 static int compile_impl(Engine* E, int count, int slots, int comp_type, int64_t best_lb, const volatile int32_t* cutoff_flag, float* device_ms) {
     // the log stride of this batch: the layers its deepest DD can have (every kernel and every host-side read of the logs uses ev.Lmax)
+    E->staged_layers = 1;  // (from the host copies of the staged roots: the fast path stages every wave and never needs it)
+    for (int i = 0; i < count; ++i) E->staged_layers = std::max(E->staged_layers, E->layers_bound(E->h_root_state + (size_t)i * E->S, E->h_root_depth[i]));
     E->Lcur = std::min(E->Lmax, std::max(1, E->staged_layers));
     if ((size_t)slots * (size_t)E->Lcur > E->pool_layers) { set_error("batch too large for the log pool: slots x layers of its deepest DD exceed it (see Engine::slots_for, Engine::layers_bound)"); return DDO_ERR_CAPACITY; }
     E->ev.Lmax = E->Lcur;

@@ -862,7 +862,10 @@ __device__ unsigned long long member_key(const uint64_t* st, int first_rank) {
 // The two size classes of the finish of a large batch: DDs whose coming layer has more than FIN_SMALL_C candidates (k_finish: one DD per
 // SM) and the others (k_finish_s: five to six per SM).  The DDs of each class are LISTED by the plan step of the previous layer (a DD
 // that is done is in neither list, so the tail of a batch -- a few long DDs among hundreds of finished ones -- costs no empty CTAs).
-constexpr int FIN_SMALL_C = 2048;
+#ifndef DDO_FIN_SMALL_C
+#define DDO_FIN_SMALL_C 2048
+#endif
+constexpr int FIN_SMALL_C = DDO_FIN_SMALL_C;
 template <int S, int NT>
 __device__ void finish_body(const EV& ev, int t, FinishSmem& sm, unsigned long long* keys, uint8_t* stat, int k) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -1,3 +1,3 @@
-for i in 1 2; do timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*\|"host_fringe_ms_per_step": [0-9.]*' | tr '\n' ' '; echo; done
-echo "LOG_SLOTS 1024 cap 4096"; DDO_LOG_SLOTS=1024 timeout 300 python bench.py --steps 3 --warmup 2 --no-config3 --no-cpu-baseline --batch-cap 4096 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*\|"kernel_ms_per_step": {[^}]*}\|"kernel_launches_per_step": {[^}]*}'
-DDO_FRINGE_PROF=1 timeout 300 python bench.py --steps 2 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -E '^\[solve\]' | cut -c1-600 | head -2 | tail -1
+DDO_FRINGE_PROF=1 timeout 300 python bench.py --steps 2 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -E '^\[solve\]' | cut -c1-600 | head -2 | tail -1 > gpurun_out/r02_solve_phases.txt; cat gpurun_out/r02_solve_phases.txt
+timeout 300 python bench.py --steps 3 --warmup 3 --no-config3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"device_ms_per_step": [0-9.]*'
+timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -2
