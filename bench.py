@@ -268,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
         line["configs"] = {"config3_max2sat": cfg3}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -403,7 +403,7 @@ def run_reference(args, rank, world):
                 "config": {"workload": f"time-boxed DD compilations, {wl.desc}", "note": "oracle port of ddo's DD compilation (Rust toolchain absent); CPU only, rank 0 only"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     o = wl.oracle()
     # every step is maximize() of the SAME instance and width under a TimeBudget of >= 30 s, long enough that the single-threaded root DDs
@@ -426,11 +426,27 @@ def run_reference(args, rank, world):
             "same_config": finished,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line of the run, on the process's original stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own log lines (its version banner) must not land on stdout next to the JSON line
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there): everything but the JSON line goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -452,7 +468,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.cpu_baseline_only:
-        print(json.dumps(cpu_baseline(Workload(args), args.cpu_seconds)), flush=True)
+        emit(cpu_baseline(Workload(args), args.cpu_seconds))
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -1,3 +1,2 @@
-timeout 900 python bench.py > gpurun_out/r02_bench_ours.json 2> gpurun_out/r02_bench_ours.err; tail -c 300 gpurun_out/r02_bench_ours.err
-grep -o '"value": [0-9.]*, "unit": "nodes/s", "n_gpus": 1, "steps": 3, "warmup": 3, "ms_per_step": [0-9.]*' gpurun_out/r02_bench_ours.json
-timeout 600 python -m pytest tests -m gpu -x -q -k "full_size" 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r02_bench_2gpu_final.json 2> gpurun_out/r02_bench_2gpu_final.err
+tail -c 200 gpurun_out/r02_bench_2gpu_final.err; head -c 1200 gpurun_out/r02_bench_2gpu_final.json
