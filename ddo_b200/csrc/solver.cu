@@ -914,7 +914,9 @@ int Solver::maximize(double time_budget_s, uint64_t max_waves, int32_t* is_exact
 }
 
 // Initial deal of the open sub-problems across ranks: every rank compiled the same root DD, so each one simply
-// keeps every nranks-th node of the common MaxUB order -- no data-path collective.
+// keeps its share of the common MaxUB order -- no data-path collective.  The deal rotates (node idx goes to rank (idx + idx / nranks)
+// mod nranks): with a plain round-robin rank 0 receives the best node of every group of nranks, which in MaxUB order is the one with the
+// largest remaining graph, and carries twice the work of the others (profiles/r02_rank_timeline_8gpu.txt).
 int Solver::retain_share(int rank, int nranks) {
     if (nranks <= 1) return DDO_OK;
     if (rank < 0 || rank >= nranks) { set_error("retain_share: bad rank"); return DDO_ERR_INVALID; }
@@ -923,7 +925,7 @@ int Solver::retain_share(int rank, int nranks) {
     const int W = words, PWN = (n_vars + 63) / 64;
     for (size_t idx = 0; !fringe.empty(); ++idx) {
         const int id = fringe.pop();
-        if ((int)(idx % (size_t)nranks) != rank) continue;
+        if ((int)((idx + idx / (size_t)nranks) % (size_t)nranks) != rank) continue;  // rotating: a plain idx % nranks hands rank 0 the best node of every group
         Keep k; k.state.assign(fringe.state(id), fringe.state(id) + W); k.bits.assign(fringe.bits(id), fringe.bits(id) + PWN); k.it = fringe.item(id);
         keep.push_back(std::move(k));
     }

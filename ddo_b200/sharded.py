@@ -1,7 +1,7 @@
 """Fringe-sharded branch-and-bound over several GPUs of one box (one process per GPU).
 
 SURVEY.md section 8(e): the open sub-problems are independent, so the path shards with NO data-path collective.  Every rank compiles the
-root DD (identical, deterministic), keeps every `world`-th open node of the common MaxUB order (`retain_share`), and then runs waves on its
+root DD (identical, deterministic), keeps its share of the open nodes of the common MaxUB order (`retain_share`: a rotating deal), and then runs waves on its
 own fringe.  After each wave ONE collective -- an all-gather of four int64 per rank: [best_lb, ub of the best open node, fringe length,
 objective of the locally held solution] -- synchronises the incumbent lower bound, the global proven upper bound, termination AND tells
 every rank how loaded the others are.  This replaces the mutex-protected `Critical` block of ddo/src/implementation/solver/parallel.rs:32-81

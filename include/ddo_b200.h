@@ -161,8 +161,9 @@ int ddo_solver_init(ddo_solver*, int32_t push_root);                   /* parall
 /* one wave; out3 = {best_lb, ub of the best open node before the wave (INT64_MIN if none), 1 if work remains after it} */
 int ddo_solver_wave(ddo_solver*, const volatile int32_t* cutoff_flag, int64_t out3[3]);
 int ddo_solver_set_lower_bound(ddo_solver*, int64_t best_lb);          /* adopt a bound found elsewhere (cf. set_primal, solver.rs:77) */
-/* initial deal of the open sub-problems over `nranks` processes (one per GPU): every rank compiled the same root DD; this keeps every
- * nranks-th node of the common MaxUB order and drops the others -- the path shards with no data-path collective. */
+/* initial deal of the open sub-problems over `nranks` processes (one per GPU): every rank compiled the same root DD; this keeps this
+ * rank's share of the common MaxUB order (node i goes to rank (i + i / nranks) mod nranks) and drops the others -- the path shards with no
+ * data-path collective. */
 int ddo_solver_retain_share(ddo_solver*, int32_t rank, int32_t nranks);
 /* Work hand-off between ranks.  The reference's workers pull from ONE shared fringe (parallel.rs:500-559), so its load balances itself;
  * here a rank whose fringe runs dry is refilled by a loaded one.  export_open pops up to 2 * max_nodes of the best open nodes, hands out

@@ -1149,7 +1149,7 @@ public:
         std::vector<SubProblem<S>> keep;
         for (size_t idx = 0; !c_.fringe->is_empty(); ++idx) {
             SubProblem<S> n = *c_.fringe->pop();
-            if (idx % nranks == rank) keep.push_back(std::move(n));
+            if ((idx + idx / nranks) % nranks == rank) keep.push_back(std::move(n));  // rotating deal (as Solver::retain_share of the device solver)
         }
         c_.fringe->clear();
         for (auto& n : keep) c_.fringe->push(std::move(n));
