@@ -42,3 +42,30 @@ def test_solver_gap_is_the_reference_formula():
     assert solver_gap(220, 220) == 0.0 and solver_gap(-7, -7) == 0.0
     assert solver_gap(13, 16) == pytest.approx(3 / 16) and solver_gap(-16, -13) == pytest.approx(3 / 16)
     assert math.isnan(solver_gap(0, 0))
+
+
+def test_misp_dd_never_has_more_layers_than_its_root_state_has_vertices():
+    """The log pool of the device engine sizes a batch by Engine::layers_bound: a MISP DD rooted at a state with p vertices has at most p
+    layers below its root (next_variable only returns a vertex that some state of the layer still holds, misp/main.rs:109-143; every state
+    is a subset of the root state; a branched vertex leaves all descendants).  Checked on the oracle: restricted and relaxed DDs of
+    sub-problems (cutset nodes of a narrow relaxed root DD) of random graphs of different densities."""
+    import numpy as np
+
+    import oracle_lib as O
+    from ddo_b200.instances import gnp
+
+    checked = 0
+    for n, p, seed in ((60, 0.2, 3), (90, 0.5, 5), (120, 0.1, 7), (70, 0.8, 11)):
+        o = O.OracleMisp(gnp(n, p, seed))
+        root = o.compile(O.RELAXED, 8)
+        assert len(root["layer_vars"]) <= n
+        for st, val, dep in list(zip(root["cutset_states"], root["cutset_values"], root["cutset_depths"]))[:12]:
+            pc = sum(bin(int(w)).count("1") for w in st)
+            assert pc <= n - int(dep)
+            for comp, width in ((O.RESTRICTED, 5), (O.RELAXED, 5), (O.RELAXED, 1000)):
+                r = o.compile(comp, width, root_state=np.asarray(st, dtype=np.uint64), root_value=int(val), root_depth=int(dep))
+                assert r["rc"] == 0
+                assert len(r["layer_vars"]) <= pc, (n, p, seed, pc, len(r["layer_vars"]))
+                assert len(set(int(v) for v in r["layer_vars"])) == len(r["layer_vars"])  # every vertex is branched on at most once
+                checked += 1
+    assert checked >= 60
