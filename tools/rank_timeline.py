@@ -12,7 +12,9 @@ for r in range(N):
             gl.append((int(p[1]), float(p[2]), float(p[3]), int(p[4]), int(p[5])))
         else:
             wl.append((int(p[0]), int(p[1]), int(p[2]), int(p[3]), float(p[4]), float(p[5]), int(p[6]), int(p[7]), int(p[8]), float(p[9]), float(p[10])))
-    wl = wl[[i for i, w in enumerate(wl) if w[0] == 1][-1]:]  # the last solve of the file (wave numbers restart at 1)
+    starts = [i for i, w in enumerate(wl) if w[0] == 1] + [len(wl)]  # wave numbers restart at 1 with every solve
+    segs = [wl[a:b] for a, b in zip(starts, starts[1:]) if b - a > 1]   # (bench.py ends with a one-wave solve that sizes the root DD pair)
+    wl = segs[-1]
     gl = gl[[i for i, g in enumerate(gl) if g[0] == 2][-1]:]
     ranks.append((wl, gl))
 print(f"# {N} ranks, one config-2 solve (MISP G(500,0.5), W = 10 000, waves of 2048 per rank); times in ms")
