@@ -1,3 +1,8 @@
-timeout 300 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | tail -2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r02_bench_2gpu_final.json 2> gpurun_out/r02_bench_2gpu_final.err
-tail -c 200 gpurun_out/r02_bench_2gpu_final.err; grep -o '"value": [0-9.]*, "unit": "nodes/s", "n_gpus": 2, "steps": 3, "warmup": 2, "ms_per_step": [0-9.]*\|"expanded_nodes_per_step": [0-9]*\|"device_ms_per_step": [0-9.]*' gpurun_out/r02_bench_2gpu_final.json
+# Round-end validation on one B200 (run through gpurun): smoke, the default bench line, the reference arm, the whole GPU suite.
+# usage: gpurun --timeout 2400 -- 'bash tools/gpu_round_check.sh'   (outputs under gpurun_out/)
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 300 gpurun_out/bench_ours.err
+timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.txt 2>&1; tail -2 gpurun_out/gpu_tests.txt
+DDO_FRINGE_PROF=1 timeout 300 python bench.py --steps 2 --warmup 2 --no-config3 --no-cpu-baseline 2>&1 | grep -E '^\[solve\]' | cut -c1-600 | head -2 | tail -1 > gpurun_out/solve_phases.txt; cat gpurun_out/solve_phases.txt
+head -c 400 gpurun_out/bench_ours.json
