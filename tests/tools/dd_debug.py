@@ -1,7 +1,7 @@
 """Debug: device layer trace of one DD vs the oracle (first differing layer)."""
 import os, sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import oracle_lib as O
 from ddo_b200 import CompilationType, GpuMdd, Misp, SubProblem, gnp
 n, p, seed, W = int(sys.argv[1]), float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])

@@ -1,6 +1,6 @@
 import sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import oracle_lib as O
 from ddo_b200 import random_max2sat, Max2Sat, GpuMdd, SubProblem, CompilationType

@@ -2,7 +2,7 @@
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import oracle_lib as O  # noqa: E402
 from ddo_b200 import FixedWidth, Misp, ParNoCachingSolverFc, ParNoCachingSolverLel, gnp  # noqa: E402

@@ -10,8 +10,8 @@ run() {  # run <label> <env...> -- <script>
     env "${@:1:$#-1}" timeout 900 compute-sanitizer --tool $tool python "${@: -1}" 2>&1 | grep -E "ERROR SUMMARY|parity ok|RACECHECK SUMMARY|hazard|Error|error" | head -8
   done
 }
-run "MAX2SAT engine" X=1 tools/m2s_tiny.py
-run "MISP engine (lock-step kernels, FRONTIER kernels)" X=1 tools/misp_tiny.py
-run "MISP engine, two-class finish forced" DDO_FINISH_SPLIT_MIN=2 DDO_FINISH_CL_MAX=0 tools/misp_tiny.py
-run "MISP engine, persistent whole-DD kernel, single-CTA clusters" DDO_DD=1 DDO_DD_CS=1 tools/misp_tiny.py
-run "MISP engine, persistent whole-DD kernel, clusters of 4" DDO_DD=1 DDO_DD_CS=4 tools/misp_tiny.py
+run "MAX2SAT engine" X=1 tests/tools/m2s_tiny.py
+run "MISP engine (lock-step kernels, FRONTIER kernels)" X=1 tests/tools/misp_tiny.py
+run "MISP engine, two-class finish forced" DDO_FINISH_SPLIT_MIN=2 DDO_FINISH_CL_MAX=0 tests/tools/misp_tiny.py
+run "MISP engine, persistent whole-DD kernel, single-CTA clusters" DDO_DD=1 DDO_DD_CS=1 tests/tools/misp_tiny.py
+run "MISP engine, persistent whole-DD kernel, clusters of 4" DDO_DD=1 DDO_DD_CS=4 tests/tools/misp_tiny.py
