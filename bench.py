@@ -145,11 +145,12 @@ def run_ours(args, rank, world, local_rank):
     solver = ParNoCachingSolverLel(pb, FixedWidth(wl.width), wave_size=args.wave, batch_cap=args.batch_cap)
     sampler = ClockSampler(local_rank)
     comm = None
+
+    def bootstrap(raw):
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
     if world > 1:  # the search's own collectives go through the C ABI (ddo_comm_*: NCCL from C++); torch.distributed only bootstraps the id and times
-        def bootstrap(raw):
-            box = [raw]
-            dist.broadcast_object_list(box, src=0)
-            return box[0]
         comm = NativeComm(rank, world, local_rank, bootstrap)
 
     def barrier():
@@ -164,6 +165,12 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             comp = solver.maximize(max_waves=wl.max_waves)
             res = {"best_lb": solver.best_lower_bound(), "best_ub": solver.best_upper_bound(), "is_exact": comp.is_exact}
+        elif args.async_shards:  # opt-in: status board in shared memory, no per-wave collective (ddo_b200/sharded.py::sharded_maximize_async)
+            from ddo_b200.sharded import StatusBoard, sharded_maximize_async
+            board = StatusBoard(rank, world, solver.node_words(), pb.nb_variables(), bootstrap)
+            res = sharded_maximize_async(solver, rank, world, board, max_waves=wl.max_waves)
+            board.close()
+            res = {k: res[k] for k in ("best_lb", "best_ub", "is_exact", "handoffs", "nodes_sent", "collectives")}
         else:
             res = solver.maximize_sharded(comm, max_waves=wl.max_waves)  # ddo_solver_maximize_sharded: the whole protocol in one native call per rank
             res = {k: res[k] for k in ("best_lb", "best_ub", "is_exact", "handoffs", "nodes_sent", "collectives")}
@@ -232,7 +239,7 @@ def run_ours(args, rank, world, local_rank):
                    "wave_size": args.wave, "batch_cap": args.batch_cap, "objective": int(last["best_lb"]), "proven_upper_bound": int(last["best_ub"]), "is_exact": bool(last["is_exact"]),
                    "explored_subproblems": int(explored_all), "handoffs_rank0": last.get("handoffs"), "nodes_sent_rank0": last.get("nodes_sent"), "collectives_rank0": last.get("collectives"), "expanded_nodes_per_step": int(expanded_all / args.steps), "replicated_root_nodes_not_counted": (world - 1) * root_expanded, "waves_per_step_rank0": int(last["waves"]),
                    "l2": "no L2 flush: every step re-runs the whole search (thousands of launches over >10 GB of arenas), far beyond the 126 MB L2",
-                   "parallelism": f"fringe sharded over {world} GPU(s); one all-gather of 4 x int64 per rank per wave (ddo_comm_allgather, NCCL from the C ABI), open nodes handed from loaded to idle ranks point to point"},
+                   "parallelism": (f"fringe sharded over {world} GPU(s); asynchronous status board in shared memory, no per-wave collective, idle ranks ask the fullest rank for open nodes" if args.async_shards else f"fringe sharded over {world} GPU(s); one all-gather of 4 x int64 per rank per wave (ddo_comm_allgather, NCCL from the C ABI), open nodes handed from loaded to idle ranks point to point")},
         "device_value": expanded_all / (dev_ms * 1e-3), "device_ms_per_step": dev_ms / args.steps, "golden_check": golden,
         "e2e": {"value": expanded_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "note": "wall clock of ddo_solver_maximize (host fringe, H2D of every wave's roots, D2H of completions and cutsets included)"},
@@ -458,6 +465,7 @@ def main():
     ap.add_argument("--workload", default="misp", choices=["misp", "max2sat"], help="misp = BASELINE config 2 (the headline metric); max2sat = config 3")
     ap.add_argument("--max-waves", type=int, default=0, help="max2sat: waves per step (default 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--async-shards", action="store_true", help="N > 1: the asynchronous status-board protocol instead of one all-gather per wave (opt-in, see DESIGN.md section 6)")
     ap.add_argument("--no-config3", action="store_true", help="skip the secondary MAX2SAT (config 3) measurement carried under 'configs'")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

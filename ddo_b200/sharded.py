@@ -248,3 +248,189 @@ def _sharded_maximize_allreduce(stepper, rank: int, world: int, allreduce_max, m
         stepper.finish()
         best_ub = lb
     return {"best_lb": lb, "best_ub": best_ub, "waves": waves, "collectives": colls, "is_exact": not aborted}
+
+
+# ----------------------------------------------------------------------------------------------------------------------------------
+# Asynchronous variant (opt-in; `bench.py --async-shards`): no per-wave collective at all.
+#
+# The ranks of ONE box share a status board in POSIX shared memory -- the closest thing to the reference's `Mutex<Critical>`
+# (parallel.rs:32-81) between processes: every rank publishes its incumbent, the size of its fringe and whether it is idle, and reads
+# the others' words whenever it likes.  Nobody waits for a slower rank (profiles/r02_rank_timeline_*: with the blocking gather a rank
+# spends up to two thirds of a solve waiting at it).  A rank whose fringe ran dry asks the fullest rank for work; the donor answers
+# between two of its waves by writing packed open nodes (export_open) into the requester's mailbox.  Termination (parallel.rs:512): all
+# ranks idle, no request or mail pending, nodes sent == nodes received, seen twice in a row by rank 0.
+# ----------------------------------------------------------------------------------------------------------------------------------
+class StatusBoard:
+    """int64 words in shared memory.  header: [done, owner of the solution, solution length]; per rank RW words:
+    [lb, open nodes, idle, sent, received, objective of the local solution, asks rank (-1 none), mailbox state (0 empty / 1 full), mailbox count];
+    then one mailbox of `mail_nodes * node_words` words per rank and one solution area."""
+    HDR, RW = 8, 16
+    LB, LEN, IDLE, SENT, RECV, SOL, ASK, MAIL, MCNT, WAVES = range(10)
+
+    def __init__(self, rank: int, world: int, node_words: int, n_vars: int, bootstrap, mail_nodes: int = 2048):
+        import mmap
+        import os
+        self.rank, self.world, self.nw, self.mail_nodes = rank, world, node_words, mail_nodes
+        self.sol_words = n_vars + 1
+        words = self.HDR + world * self.RW + world * mail_nodes * node_words + self.sol_words
+        # a file in /dev/shm mapped by every rank (plain mmap: multiprocessing.shared_memory would hand the segment to a resource tracker
+        # that unlinks it when the first attached process exits)
+        if rank == 0:
+            self.path = f"/dev/shm/ddo_board_{os.getpid()}_{int.from_bytes(os.urandom(4), 'little'):08x}"
+            fd = os.open(self.path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, words * 8)
+            self.path = bootstrap(self.path)
+        else:
+            self.path = bootstrap(None)
+            fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(fd, words * 8)
+        os.close(fd)
+        self.w = np.frombuffer(self.mm, dtype=np.int64)
+        self.mail0 = self.HDR + world * self.RW
+        self.sol0 = self.mail0 + world * mail_nodes * node_words
+        if rank == 0:
+            for r in range(world):
+                self.set(r, self.LB, I64_MIN); self.set(r, self.SOL, I64_MIN); self.set(r, self.ASK, -1)
+        bootstrap(None) if rank else bootstrap("ready")  # nobody reads the board before rank 0 initialised it
+
+    def get(self, r, f): return int(self.w[self.HDR + r * self.RW + f])
+    def set(self, r, f, v): self.w[self.HDR + r * self.RW + f] = v
+    def col(self, f): return [self.get(r, f) for r in range(self.world)]
+    def mailbox(self, r): return self.w[self.mail0 + r * self.mail_nodes * self.nw: self.mail0 + (r + 1) * self.mail_nodes * self.nw]
+
+    def close(self):
+        import os
+        self.w = None
+        try:
+            self.mm.close()
+        except BufferError:  # a view of the mailbox is still alive somewhere: the mapping goes with the process
+            pass
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except FileNotFoundError:
+                pass
+
+
+def sharded_maximize_async(stepper, rank: int, world: int, board: StatusBoard, max_waves: int = 0, poll_s: float = 1e-4):
+    """Returns dict(best_lb, best_ub, waves, handoffs, nodes_sent, nodes_received, is_exact, best_value, solution); no collectives."""
+    import time
+    B, me = board, rank
+    stepper.init(True)
+    lb, top, more = stepper.wave()  # the root DD: identical on every rank
+    stepper.retain_share(rank, world)
+    waves, handoffs, sent, received = 1, 0, 0, 0
+    aborted = False
+    nw = stepper.node_words()
+
+    def publish(idle):
+        sv = stepper.best_value()
+        B.set(me, B.SOL, I64_MIN if sv is None else sv)
+        B.set(me, B.LB, lb); B.set(me, B.LEN, stepper.fringe_len()); B.set(me, B.WAVES, waves)
+        B.set(me, B.IDLE, 1 if idle else 0)
+
+    def adopt():
+        nonlocal lb
+        g = max(B.col(B.LB))
+        if g > lb:
+            stepper.set_lower_bound(g); lb = g
+
+    def serve():
+        """answer the ranks that ask this one for work: half of what this rank holds above MIN_DONOR, or nothing"""
+        nonlocal handoffs, sent
+        for r in range(world):
+            if r == me or B.get(r, B.ASK) != me or B.get(r, B.MAIL) != 0:
+                continue
+            have = stepper.fringe_len()
+            cnt = min(B.mail_nodes, (have - MIN_DONOR) // 2) if have >= 2 * MIN_DONOR else 0
+            k = 0
+            if cnt > 0:
+                out = stepper.export_open(cnt)
+                k = int(out.shape[0])
+                if k:
+                    B.mailbox(r)[:k * nw] = np.ascontiguousarray(out, dtype=np.int64).reshape(-1)
+            B.set(r, B.MCNT, k)
+            sent += k
+            B.set(me, B.SENT, sent)      # before the mail becomes visible: sent >= received at all times
+            B.set(r, B.MAIL, 1)
+            handoffs += 1 if k else 0
+
+    publish(False)
+    while True:
+        if B.w[0]:
+            break
+        adopt()
+        serve()
+        if stepper.fringe_len() == 0:
+            if B.get(me, B.MAIL) == 1:  # the answer to this rank's request
+                k = B.get(me, B.MCNT)
+                if k:
+                    B.set(me, B.IDLE, 0)  # active BEFORE the nodes count as received (termination test below)
+                    rows = np.array(B.mailbox(me)[:k * nw], dtype=np.int64).reshape(k, nw)
+                    stepper.import_open(rows)
+                    received += k
+                    B.set(me, B.RECV, received)
+                    handoffs += 1
+                B.set(me, B.ASK, -1)
+                B.set(me, B.MAIL, 0)
+                if k:
+                    publish(False)
+                    continue
+            publish(True)
+            if B.get(me, B.ASK) == -1 and B.get(me, B.MAIL) == 0:
+                lens = B.col(B.LEN)
+                donor = max((r for r in range(world) if r != me and not B.get(r, B.IDLE) and lens[r] >= 2 * MIN_DONOR), key=lambda r: (lens[r], -r), default=-1)
+                if donor >= 0:
+                    B.set(me, B.ASK, donor)
+            if me == 0:  # termination: two identical quiet scans in a row (counters first, flags after)
+                def scan():
+                    s, r = B.col(B.SENT), B.col(B.RECV)
+                    quiet = sum(s) == sum(r) and all(B.col(B.IDLE)) and all(a == -1 for a in B.col(B.ASK)) and not any(B.col(B.MAIL))
+                    return quiet, (tuple(s), tuple(r))
+                q1, c1 = scan()
+                if q1:
+                    q2, c2 = scan()
+                    if q2 and c1 == c2:
+                        B.w[0] = 1
+                        break
+            time.sleep(poll_s)
+            continue
+        publish(False)
+        if max_waves and waves >= max_waves:
+            aborted = True
+            B.w[0] = 2  # a rank that ran out of budget stops everybody
+            break
+        lb, top, more = stepper.wave()
+        waves += 1
+        publish(False)
+    aborted = aborted or int(B.w[0]) == 2
+    adopt()
+    if not aborted:
+        stepper.finish()
+    publish(True)
+    # the solution: the lowest rank holding one of the optimal value writes it to the board
+    solution, value = None, None
+    deadline = time.time() + 60
+    while True:  # every rank has published its final words once all of them show the final bound or are idle
+        if all(B.col(B.IDLE)) or time.time() > deadline:
+            break
+        time.sleep(poll_s)
+    g_lb = max(B.col(B.LB))
+    owners = [r for r in range(world) if B.get(r, B.SOL) == g_lb]
+    if owners and hasattr(stepper, "best_solution"):
+        owner, value = owners[0], g_lb
+        if me == owner:
+            sol = stepper.best_solution() or []
+            packed = np.asarray([(d.variable << 32) | (d.value & 0xFFFFFFFF) for d in sol], dtype=np.int64)
+            B.w[B.sol0 + 1: B.sol0 + 1 + packed.size] = packed
+            B.w[B.sol0] = packed.size
+            B.w[2] = 1  # published
+            solution = [(d.variable, d.value) for d in sol]
+        else:
+            while not B.w[2] and time.time() < deadline:
+                time.sleep(poll_s)
+            k = int(B.w[B.sol0])
+            solution = [(int(x >> 32), int(np.int32(np.uint32(x & 0xFFFFFFFF)))) for x in B.w[B.sol0 + 1: B.sol0 + 1 + k].tolist()]
+    B.set(me, B.WAVES, -waves)  # (this rank is done with the board)
+    return {"best_lb": g_lb, "best_ub": g_lb if not aborted else None, "waves": waves, "collectives": 0, "handoffs": handoffs, "nodes_sent": sent,
+            "nodes_received": received, "is_exact": not aborted, "best_value": value, "solution": solution}

@@ -129,3 +129,49 @@ def test_rebalanced_device_ranks_follow_the_oracle_ranks(world):
             (r["waves"], r["collectives"], r["handoffs"], r["nodes_sent"], r["nodes_received"], r["explored"], r["expanded"])
         chosen = [v for v, x in d["solution"] if x == 1]
         assert len(chosen) == single["best_value"] and all(not inst.has_edge(a, b) for i, a in enumerate(chosen) for b in chosen[i + 1:])
+
+
+def test_asynchronous_board_protocol_over_device_solvers():
+    """The opt-in asynchronous protocol (ddo_b200.sharded.sharded_maximize_async: status board in shared memory, no collective) with two
+    and three device solvers as ranks (threads of this process): every rank proves the optimum and returns one common independent set."""
+    from ddo_b200.sharded import StatusBoard, sharded_maximize_async
+
+    inst = gnp(130, 0.35, 11)
+    pb = Misp(inst)
+    single = O.OracleMisp(inst).solve("wave", k=8, width=6)
+    for world in (2, 3):
+        box, bar = [None], threading.Barrier(world)
+        res, err = [None] * world, []
+
+        def bootstrap_for(rank):
+            def f(obj):
+                if rank == 0:
+                    box[0] = obj
+                bar.wait()
+                out = box[0]
+                bar.wait()
+                return out
+            return f
+
+        def work(rank):
+            try:
+                st = ParNoCachingSolverLel(pb, FixedWidth(6), wave_size=8)
+                board = StatusBoard(rank, world, st.node_words(), inst.n, bootstrap_for(rank), mail_nodes=256)
+                res[rank] = sharded_maximize_async(st, rank, world, board)
+                bar.wait()
+                board.close()
+            except Exception as e:
+                err.append(e)
+                bar.abort()
+
+        ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not err, err
+        assert all(r["is_exact"] and r["best_lb"] == single["best_value"] == r["best_value"] and r["collectives"] == 0 for r in res)
+        assert sum(r["nodes_sent"] for r in res) == sum(r["nodes_received"] for r in res)
+        chosen = [v for v, x in res[0]["solution"] if x == 1]
+        assert len(chosen) == single["best_value"] and all(not inst.has_edge(a, b) for i, a in enumerate(chosen) for b in chosen[i + 1:])
+        assert all(r["solution"] == res[0]["solution"] for r in res)

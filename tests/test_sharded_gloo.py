@@ -36,8 +36,20 @@ def _worker(rank, world, port, spec, out_dir):
     else:
         oracle = O.OracleMisp(gnp(*spec["gnp"]) if "gnp" in spec else parse_dimacs((ROOT / "tests" / "golden" / "misp" / spec["file"]).read_text()))
     stepper = O.OracleStepper(oracle, spec["wave"], spec.get("width"))
-    comm = torch_allreduce_max() if spec.get("round1") else TorchComm()
-    res = sharded_maximize(stepper, rank, world, comm, rebalance=spec.get("rebalance", True))
+    if spec.get("async"):
+        from ddo_b200.sharded import StatusBoard, sharded_maximize_async
+
+        def bootstrap(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        board = StatusBoard(rank, world, stepper.node_words(), oracle.inst.n, bootstrap, mail_nodes=256)
+        res = sharded_maximize_async(stepper, rank, world, board)
+        dist.barrier()
+        board.close()
+    else:
+        comm = torch_allreduce_max() if spec.get("round1") else TorchComm()
+        res = sharded_maximize(stepper, rank, world, comm, rebalance=spec.get("rebalance", True))
     res.update(rank=rank, explored=stepper.explored(), expanded=stepper.expanded())
     Path(out_dir, f"r{rank}.json").write_text(json.dumps(res))
     dist.destroy_process_group()
@@ -122,3 +134,22 @@ def test_rebalancing_moves_open_nodes_and_keeps_the_optimum(world, tmp_path):
     assert all(r["is_exact"] and r["best_lb"] == single["best_value"] for r in old)
     # balance: the busiest rank of the rebalanced run explores less than the busiest rank of the static deal
     assert max(r["explored"] for r in res) <= max(r["explored"] for r in old)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_asynchronous_board_protocol_proves_the_optimum_without_collectives(world, tmp_path):
+    """The opt-in asynchronous protocol (status board in shared memory, no per-wave collective, idle ranks ask the fullest rank for work):
+    every rank ends with the single-process optimum and one common, valid solution; every node sent was received; termination is detected."""
+    import oracle_lib as O
+    from ddo_b200.instances import gnp
+
+    spec = {"gnp": (120, 0.3, 3), "wave": 4, "width": 4, "async": True}
+    inst = gnp(*spec["gnp"])
+    single = O.OracleMisp(inst).solve("wave", k=spec["wave"], width=spec["width"])
+    res = _run(world, spec, tmp_path)
+    assert all(r["is_exact"] and r["best_lb"] == r["best_ub"] == single["best_value"] == r["best_value"] for r in res)
+    assert all(r["collectives"] == 0 for r in res)
+    assert sum(r["nodes_sent"] for r in res) == sum(r["nodes_received"] for r in res)
+    assert all(r["solution"] == res[0]["solution"] for r in res)
+    chosen = [v for v, x in res[0]["solution"] if x == 1]
+    assert len(chosen) == single["best_value"] and all(not inst.has_edge(a, b) for i, a in enumerate(chosen) for b in chosen[i + 1:])
