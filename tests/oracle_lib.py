@@ -452,3 +452,13 @@ def locbounds_dump(cutset_type=FRONTIER, best_lb=0) -> str:
 def run_selftest() -> subprocess.CompletedProcess:
     build()
     return subprocess.run([str(SELFTEST)], capture_output=True, text=True)
+
+
+def read_clq(golden_dir, name: str) -> str:
+    """Text of the DIMACS fixture `name` under tests/golden/misp (the two n = 500 instances are stored gzip-compressed)."""
+    import gzip
+    from pathlib import Path
+    p = Path(golden_dir) / "misp" / f"{name}.clq"
+    if p.exists():
+        return p.read_text()
+    return gzip.decompress((Path(golden_dir) / "misp" / f"{name}.clq.gz").read_bytes()).decode()

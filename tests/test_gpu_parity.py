@@ -71,12 +71,12 @@ def test_error_behaviour_matches_reference():
 FAST = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "c-fat200-5"]
 
 
-@pytest.mark.parametrize("name", FAST + ["brock200_2", "hamming8-2"])
+@pytest.mark.parametrize("name", FAST + ["brock200_2", "hamming8-2", "c-fat500-1", "c-fat500-2"])
 def test_solver_known_optima_and_wave_trace_parity(golden_dir, name):
     """Solver::maximize on the reference's DIMACS fixtures: asserted optimum (misp/tests.rs), proven bound, and the exact same
     branch-and-bound trajectory as the oracle's wave solver (explored / expanded / transitions / compilations)."""
     exp = json.loads((golden_dir / "expected.json").read_text())["misp"][name]["optimum"]
-    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    inst = parse_dimacs(O.read_clq(golden_dir, name), name)
     pb = Misp(inst)
     K = 16
     s = ParNoCachingSolverLel(pb, NbUnassignedWidth(inst.n), wave_size=K)

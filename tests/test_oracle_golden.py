@@ -101,7 +101,7 @@ def _expected(golden_dir):
 
 
 FAST_MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "hamming8-2", "brock200_2", "c-fat200-5", "c-fat200-1", "c-fat200-2",
-             "p_hat300-1"]
+             "p_hat300-1", "c-fat500-1", "c-fat500-2"]
 SLOW_MISP = ["keller4", "brock200_3"]
 
 
@@ -109,7 +109,7 @@ SLOW_MISP = ["keller4", "brock200_3"]
 def test_misp_known_optima_parallel_solver(golden_dir, name):
     """examples/misp/tests.rs: DefaultSolver (parallel, LEL, NbUnassignedWidth) proves the asserted optimum."""
     exp = _expected(golden_dir)["misp"][name]
-    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    inst = parse_dimacs(O.read_clq(golden_dir, name), name)
     r = O.OracleMisp(inst).solve("parallel", k=8)
     assert r["is_exact"] and r["best_value"] == exp["optimum"], exp["source"]
     assert r["best_lb"] == r["best_ub"] == exp["optimum"]
@@ -126,7 +126,7 @@ def _check_independent(inst, sol, value):
 def test_misp_sequential_wave_and_parallel_agree(golden_dir, name):
     """Objective and proven bound are schedule independent; wave K=1 is exactly the sequential solver."""
     exp = _expected(golden_dir)["misp"][name]["optimum"]
-    inst = parse_dimacs((golden_dir / "misp" / f"{name}.clq").read_text(), name)
+    inst = parse_dimacs(O.read_clq(golden_dir, name), name)
     o = O.OracleMisp(inst)
     seq = o.solve("sequential")
     w1 = o.solve("wave", k=1)
