@@ -19,7 +19,7 @@ OUT = Path(__file__).resolve().parent
 MISP = ["johnson8-2-4", "hamming6-4", "hamming6-2", "MANN_a9", "johnson8-4-4", "keller4", "hamming8-2", "hamming8-4",
         "brock200_2", "brock200_3", "brock200_4", "c-fat200-5", "c-fat200-1", "c-fat200-2", "p_hat300-1"]
 MISP_GZ = ["c-fat500-1", "c-fat500-2"]  # the two n = 500 instances of the non-ignored tests (1.1 MB of edges each): stored gzip-compressed
-KNAPSACK_MAX_ITEMS = 200
+KNAPSACK_MAX_ITEMS = 500  # (the 1000- and 2000-item instances of the non-ignored tests take the CPU oracle 20 - 150 s each: checked once, not committed)
 TSPTW = ["Langevin/N20ft301.dat", "Langevin/N20ft405.dat", "Langevin/N40ft403.dat", "Langevin/N60ft406.dat", "Langevin/N60ft410.dat",
          "SolomonPotvinBengio/rc_201.1.txt", "SolomonPotvinBengio/rc_201.3.txt", "SolomonPotvinBengio/rc_202.2.txt", "SolomonPotvinBengio/rc_203.1.txt",
          "SolomonPotvinBengio/rc_203.4.txt", "SolomonPotvinBengio/rc_205.1.txt", "SolomonPotvinBengio/rc_205.2.txt", "SolomonPotvinBengio/rc_205.4.txt",
