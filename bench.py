@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
                             "note": "achieved = expanded nodes of one step x bytes_per_node / summed CUDA-event duration of the dominant kernel's launches"}
     if cfg3 is not None:
         line["configs"] = {"config3_max2sat": cfg3}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (the CPU leg is reported at N = 1 only)
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
     emit(line)
     if world > 1:
